@@ -1,0 +1,117 @@
+"""Location-scale variational family (mean-field / full-rank Gaussian).
+
+TEST INFRASTRUCTURE (see oracle/__init__.py).  Restates
+src/families/location_scale.jl of the reference; matrices are column-major in the
+reference, here samples are COLUMNS of a (D, M) numpy array exactly as there
+(`eachsample = eachcol`, src/utils.jl:6).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+LOG2PI = float(np.log(2.0 * np.pi))
+H0 = 0.5 * (LOG2PI + 1.0)   # entropy(Normal(0,1)), Appendix B of SURVEY.md
+
+
+class MvLocationScale:
+    """src/families/location_scale.jl:15-19 with dist = Normal(0, 1).
+
+    `scale` is a 1-D array (Diagonal -> MeanFieldGaussian, :139-141) or a 2-D lower
+    triangular array (LowerTriangular -> FullRankGaussian, :124-128).
+    """
+
+    def __init__(self, location, scale):
+        self.location = np.array(location, copy=True)
+        self.scale = np.array(scale, copy=True)
+        assert self.scale.ndim in (1, 2)
+        if self.scale.ndim == 2:
+            assert self.scale.shape == (len(self.location),) * 2
+
+    @property
+    def is_meanfield(self) -> bool:
+        return self.scale.ndim == 1
+
+    def __len__(self):                       # :45
+        return len(self.location)
+
+    @property
+    def dtype(self):
+        return self.location.dtype
+
+    def scale_diag(self) -> np.ndarray:
+        return self.scale if self.is_meanfield else np.diag(self.scale)
+
+    # -- Optimisers.destructure ------------------------------------------------------
+    def destructure(self) -> np.ndarray:
+        """Mean-field: flat = [location; diag(scale)] (location_scale.jl:39-43).
+        Full-rank: generic Functors path = [location; vec(scale)] column-major with the
+        zero upper triangle present (unpinned by reference tests).
+        """
+        if self.is_meanfield:
+            return np.concatenate([self.location, self.scale])
+        return np.concatenate([self.location, self.scale.reshape(-1, order="F")])
+
+    def restructure(self, flat: np.ndarray) -> "MvLocationScale":
+        """RestructureMeanField (location_scale.jl:32-37) / generic restructure."""
+        D = len(self.location)
+        flat = np.asarray(flat)
+        if self.is_meanfield:
+            assert flat.shape == (2 * D,)
+            return MvLocationScale(flat[:D], flat[D:])
+        assert flat.shape == (D + D * D,)
+        return MvLocationScale(flat[:D], flat[D:].reshape(D, D, order="F"))
+
+    # -- StatsBase.entropy (location_scale.jl:52-57) -------------------------------
+    def entropy(self):
+        D = len(self.location)
+        return D * self.dtype.type(H0) + np.sum(np.log(self.scale_diag()))
+
+    # -- Distributions.logpdf (location_scale.jl:59-63) ----------------------------
+    def standardize(self, z: np.ndarray) -> np.ndarray:
+        """z_std = scale \\ (z - location); z is (D,) or (D, M)."""
+        r = z - (self.location if z.ndim == 1 else self.location[:, None])
+        if self.is_meanfield:
+            return r / (self.scale if z.ndim == 1 else self.scale[:, None])
+        from scipy.linalg import solve_triangular
+        return solve_triangular(self.scale, r, lower=True)
+
+    def logpdf(self, z: np.ndarray):
+        """sum(logpdf(Normal(0,1), z_std)) - logdet(scale); vectorised over columns."""
+        u = self.standardize(z)
+        return np.sum(-0.5 * (u * u + LOG2PI), axis=0) - np.sum(np.log(self.scale_diag()))
+
+    # -- Distributions.rand (location_scale.jl:71-87) ------------------------------
+    def rand_from_eps(self, eps: np.ndarray) -> np.ndarray:
+        """scale * eps .+ location (dense, :76) / diag(scale) .* eps .+ location (:86)."""
+        if self.is_meanfield:
+            return self.scale[:, None] * eps + self.location[:, None]
+        return self.scale @ eps + self.location[:, None]
+
+    # -- mean / var / cov (location_scale.jl:98-113), mean(Normal(0,1)) = 0, var = 1 --
+    def mean(self):
+        return self.location.copy()
+
+    def var(self):
+        if self.is_meanfield:
+            return self.scale ** 2
+        return np.sum(self.scale ** 2, axis=1)          # diag(C C')
+
+    def cov(self):
+        if self.is_meanfield:
+            return np.diag(self.scale ** 2)
+        return self.scale @ self.scale.T
+
+
+def MeanFieldGaussian(mu, diag_scale) -> MvLocationScale:
+    """location_scale.jl:139-141."""
+    diag_scale = np.asarray(diag_scale)
+    assert diag_scale.ndim == 1
+    return MvLocationScale(mu, diag_scale)
+
+
+def FullRankGaussian(mu, L) -> MvLocationScale:
+    """location_scale.jl:124-128; L must be lower triangular."""
+    L = np.asarray(L)
+    assert L.ndim == 2 and np.allclose(L, np.tril(L))
+    return MvLocationScale(mu, L)

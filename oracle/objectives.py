@@ -1,0 +1,158 @@
+"""ELBO objectives: RepGradELBO (+ entropy estimators), ScoreGradELBO, SubsampledObjective.
+
+TEST INFRASTRUCTURE (see oracle/__init__.py).
+
+The reference differentiates a forward closure with an AD backend
+(src/AdvancedVI.jl:47-98).  Here the forward closures are restated 1:1
+(`repgrad_forward`, `scoregrad_forward`) and the gradients are the closed forms of
+SURVEY.md Appendix A; tests/test_oracle_gradients.py checks every closed form against
+central finite differences of the restated forward with eps held fixed, which is what
+an AD backend would return.
+
+eps is an explicit argument everywhere: `rand(rng, q, M)` of the reference
+(src/algorithms/repgradelbo.jl:107) becomes `q.rand_from_eps(eps)`.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from .family import MvLocationScale
+
+ENTROPIES = ("ClosedFormEntropy", "MonteCarloEntropy", "StickingTheLandingEntropy",
+             "ClosedFormEntropyZeroGradient", "StickingTheLandingEntropyZeroGradient")
+
+
+# -- src/algorithms/entropy.jl -------------------------------------------------------------
+def estimate_entropy(kind: str, samples: np.ndarray, q: MvLocationScale, q_stop: MvLocationScale):
+    if kind == "ClosedFormEntropyZeroGradient":          # entropy.jl:13-15
+        return q_stop.entropy()
+    if kind == "ClosedFormEntropy":                      # entropy.jl:27-29
+        return q.entropy()
+    if kind == "MonteCarloEntropy":                      # entropy.jl:42-46
+        return np.mean(-q.logpdf(samples))
+    if kind == "StickingTheLandingEntropy":              # entropy.jl:59-65
+        return np.mean(-q_stop.logpdf(samples))
+    if kind == "StickingTheLandingEntropyZeroGradient":  # entropy.jl:80-90
+        return np.mean(-q_stop.logpdf(samples)) - q.entropy() + q_stop.entropy()
+    raise ValueError(kind)
+
+
+# -- src/algorithms/repgradelbo.jl ---------------------------------------------------------
+def estimate_energy_with_samples(prob, samples: np.ndarray, per_sample: bool = False):
+    """mean(logdensity(prob, z_m) for each column)  (repgradelbo.jl:84-86).
+    per_sample=True loops over columns exactly like the reference (M separate calls)."""
+    if per_sample:
+        return np.mean([prob.logdensity(samples[:, m]) for m in range(samples.shape[1])])
+    return np.mean(prob.logdensity_batch(samples))
+
+
+def repgrad_forward(params, q_template: MvLocationScale, q_stop: MvLocationScale, prob,
+                    eps: np.ndarray, entropy: str):
+    """estimate_repgradelbo_ad_forward (repgradelbo.jl:142-149): returns -ELBO."""
+    q = q_template.restructure(params)
+    samples = q.rand_from_eps(eps)                               # reparam_with_entropy :104-110
+    ent = estimate_entropy(entropy, samples, q, q_stop)
+    energy = estimate_energy_with_samples(prob, samples)
+    return -(energy + ent)
+
+
+def _scale_grad_pack(q: MvLocationScale, g_mu, g_scale):
+    if q.is_meanfield:
+        return np.concatenate([g_mu, g_scale])
+    return np.concatenate([g_mu, np.tril(g_scale).reshape(-1, order="F")])
+
+
+def repgrad_value_and_gradient(params, q_template: MvLocationScale, prob, eps: np.ndarray,
+                               entropy: str, per_sample: bool = False):
+    """estimate_gradient! for RepGradELBO (repgradelbo.jl:151-177) with q_stop =
+    restructure(params) (:162).  Returns (value = -ELBO, gradient, elbo).
+    Closed forms: SURVEY.md Appendix A.1-A.3."""
+    q = q_template.restructure(params)
+    M = eps.shape[1]
+    Z = q.rand_from_eps(eps)
+    if per_sample:   # reference-shaped: one logdensity_and_gradient call per column
+        lg = [prob.logdensity_and_gradient(Z[:, m]) for m in range(M)]
+        logp = np.array([a for a, _ in lg]); G = np.stack([b for _, b in lg], axis=1)
+    else:
+        logp, G = prob.logdensity_and_gradient_batch(Z)
+    ent = estimate_entropy(entropy, Z, q, q)
+    value = -(np.mean(logp) + ent)
+    sd = q.scale_diag()
+    stl = entropy in ("StickingTheLandingEntropy", "StickingTheLandingEntropyZeroGradient")
+    if stl:
+        # w_m = g_m - grad_z log q_stop(z_m) = g_m + L^{-T} eps_m
+        if q.is_meanfield:
+            W = G + eps / sd[:, None]
+        else:
+            from scipy.linalg import solve_triangular
+            W = G + solve_triangular(q.scale.T, eps, lower=False)
+    else:
+        W = G
+    g_mu = -np.mean(W, axis=1)
+    if q.is_meanfield:
+        g_sc = -np.mean(W * eps, axis=1)
+        inv = 1.0 / sd
+    else:
+        g_sc = -np.tril(W @ eps.T) / M
+        inv = np.diag(1.0 / sd)
+    if entropy in ("ClosedFormEntropy", "MonteCarloEntropy"):
+        g_sc = g_sc - inv                       # -grad H(q)
+    elif entropy == "StickingTheLandingEntropyZeroGradient":
+        g_sc = g_sc + inv                       # value has -H(q) added: A.3 + grad H(q)
+    return value, _scale_grad_pack(q, g_mu, g_sc), -value
+
+
+def repgrad_estimate_objective(q: MvLocationScale, prob, eps, entropy="ClosedFormEntropy"):
+    """estimate_objective(rng, obj::RepGradELBO, q, prob) (repgradelbo.jl:112-118)."""
+    samples = q.rand_from_eps(eps)
+    ent = estimate_entropy(entropy, samples, q, q)
+    return -(estimate_energy_with_samples(prob, samples) + ent)
+
+
+# -- src/algorithms/scoregradelbo.jl -------------------------------------------------------
+def scoregrad_forward(params, q_template: MvLocationScale, samples_stop, logprob_stop):
+    """estimate_scoregradelbo_ad_forward (scoregradelbo.jl:87-94): VarGrad value."""
+    q = q_template.restructure(params)
+    f = q.logpdf(samples_stop) - logprob_stop
+    return (np.mean(f * f) - np.mean(f) ** 2) / 2
+
+
+def scoregrad_value_and_gradient(params, q_template: MvLocationScale, prob, eps):
+    """estimate_gradient! for ScoreGradELBO (scoregradelbo.jl:96-117).
+    Returns (value = VarGrad, gradient, elbo).  Closed form: Appendix A.4."""
+    q = q_template.restructure(params)
+    M = eps.shape[1]
+    Z = q.rand_from_eps(eps)                              # :107 (not differentiated)
+    logpi = prob.logdensity_batch(Z)                      # :108
+    logq = q.logpdf(Z)
+    f = logq - logpi
+    value = (np.mean(f * f) - np.mean(f) ** 2) / 2
+    c = f - np.mean(f)
+    u = q.standardize(Z)                                  # == eps up to rounding
+    sd = q.scale_diag()
+    if q.is_meanfield:
+        g_mu = np.mean(c[None, :] * u, axis=1) / sd
+        g_sc = np.mean(c[None, :] * (u * u - 1.0), axis=1) / sd
+    else:
+        from scipy.linalg import solve_triangular
+        # d logq/d mu = L^{-T} u ; d logq/d L = tril(L^{-T} u u') - diag(1/L_ii)
+        Linv_T_u = solve_triangular(q.scale.T, u, lower=False)
+        g_mu = np.mean(c[None, :] * Linv_T_u, axis=1)
+        S = (u * c[None, :]) @ u.T / M
+        g_sc = np.tril(solve_triangular(q.scale.T, S, lower=False)) - np.mean(c) * np.diag(1.0 / sd)
+    elbo = np.mean(logpi - logq)                          # :113-114
+    return value, _scale_grad_pack(q, g_mu, g_sc), elbo
+
+
+def scoregrad_estimate_objective(q: MvLocationScale, prob, eps):
+    """estimate_objective(rng, obj::ScoreGradELBO, ...) (scoregradelbo.jl:58-65)."""
+    Z = q.rand_from_eps(eps)
+    return -np.mean(prob.logdensity_batch(Z) - q.logpdf(Z))
+
+
+# -- src/algorithms/common.jl:29-38 --------------------------------------------------------
+def estimate_objective(q: MvLocationScale, prob, eps, entropy="MonteCarloEntropy"):
+    """estimate_objective(rng, alg::ParamSpaceSGD, q, prob; n_samples, entropy): always a
+    fresh RepGradELBO with MonteCarloEntropy by default, ignoring subsampling."""
+    return repgrad_estimate_objective(q, prob, eps, entropy)
