@@ -1,0 +1,242 @@
+// Internal declarations shared by the translation units of libavi_b200.so.
+// Not part of the ABI (include/avi.h is).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/avi.h"
+
+#define AVI_VERSION 100
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing
+void avi_set_error(const avi_ctx* ctx, const std::string& msg);
+#define AVI_FAIL(ctx, code, msg)                                   \
+    do {                                                           \
+        avi_set_error((ctx), std::string(__func__) + ": " + (msg)); \
+        return (code);                                             \
+    } while (0)
+#define AVI_CUDA(ctx, expr)                                                              \
+    do {                                                                                 \
+        cudaError_t e__ = (expr);                                                        \
+        if (e__ != cudaSuccess) {                                                        \
+            avi_set_error((ctx), std::string(__func__) + ": " #expr ": " +               \
+                                     cudaGetErrorString(e__));                           \
+            return AVI_ERR_CUDA;                                                         \
+        }                                                                                \
+    } while (0)
+#define AVI_CHECK(expr)                       \
+    do {                                      \
+        int32_t s__ = (expr);                 \
+        if (s__ != AVI_OK) return s__;        \
+    } while (0)
+// after a kernel launch: count it and surface launch-configuration errors
+#define AVI_LAUNCHED(ctx)                                                        \
+    do {                                                                         \
+        (ctx)->launches++;                                                       \
+        cudaError_t e__ = cudaGetLastError();                                    \
+        if (e__ != cudaSuccess) {                                                \
+            avi_set_error((ctx), std::string(__func__) + ": kernel launch: " +   \
+                                     cudaGetErrorString(e__));                   \
+            return AVI_ERR_CUDA;                                                 \
+        }                                                                        \
+    } while (0)
+
+static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+static inline int64_t ceil_div(int64_t x, int64_t m) { return (x + m - 1) / m; }
+
+// ---------------------------------------------------------------------------------------------
+struct avi_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaDeviceProp prop{};
+    mutable std::string err;
+    int64_t launches = 0;
+    bool capturing = false;   // a CUDA graph capture is open on `stream`
+    // exchange step (multi-rank)
+    int rank = 0, nranks = 1;
+    avi_allreduce_fn ar_fn = nullptr;
+    void* ar_user = nullptr;
+    // per-kernel device timing for bench.py's roofline (CUDA events around the named hot kernels;
+    // forces eager launches while enabled)
+    bool timing = false;
+    struct KTimer {
+        std::string name;
+        std::vector<cudaEvent_t> ev;   // start/stop pairs not yet folded in
+        double total_ms = 0.0;
+        int64_t count = 0;
+    };
+    std::vector<KTimer> timers;
+    bool comm_capturable = false;   // the exchange is a kernel of ours (comm.cu), safe inside a graph
+    void* comm = nullptr;           // struct CommState* (comm.cu)
+};
+
+void avi_ktime_mark(avi_ctx* ctx, const char* name);   // records one event; calls come in start/stop pairs
+struct AviTimed {
+    avi_ctx* c; const char* n;
+    AviTimed(avi_ctx* ctx, const char* name) : c(ctx), n(name) { if (c->timing) avi_ktime_mark(c, n); }
+    ~AviTimed() { if (c->timing) avi_ktime_mark(c, n); }
+};
+
+// device allocation with error plumbing (zero-filled)
+int32_t avi_dev_alloc(avi_ctx* ctx, void** p, size_t bytes);
+template <typename T>
+static inline int32_t avi_alloc(avi_ctx* ctx, T** p, size_t count) {
+    return avi_dev_alloc(ctx, reinterpret_cast<void**>(p), count * sizeof(T));
+}
+// blocking copies ordered on the ctx stream (never the legacy stream: see avi_dev_alloc)
+static inline cudaError_t avi_copy(avi_ctx* ctx, void* dst, const void* src, size_t bytes, cudaMemcpyKind kind) {
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, kind, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    return e;
+}
+template <typename T>
+static inline void avi_free(T*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+// Device-resident step state read by the kernels (so a captured CUDA graph can be replayed
+// with a moving step counter / minibatch cursor).
+struct ObjDeviceState {
+    unsigned long long step;   // optimisation step whose eps is drawn next
+    unsigned long long key;    // Philox key
+    long long batch_cursor;    // index of the minibatch used by the next subsampled step
+    int halted;                // set when the value slot was not finite: later steps are no-ops
+    int trace_pos;             // next slot of the per-call (value, elbo) trace
+};
+
+// Layout shared by every sample-major buffer: row m (one Monte-Carlo sample) holds `ld` floats,
+// coordinate i at [m * ld + i]  ==  a D x M column-major matrix with leading dimension ld.
+struct avi_model {
+    avi_ctx* ctx = nullptr;
+    int D = 0;
+    int capability = 1;
+    int64_t generation = 0;   // bumped whenever device buffers are reallocated (captured graphs go stale)
+    virtual ~avi_model() {}
+    // logp[m] = log pi(z_m); G (nullable) = grad log pi(z_m), same layout as Z.
+    virtual int32_t eval(const float* Z, int ld, int M, float* logp, float* G) = 0;
+    // Fused mean-field path: a1[i] = sum_m G[m][i], a2[i] = sum_m G[m][i] * E[m][i] without
+    // materialising G (a1, a2 hold D floats and are overwritten).  Optional.
+    virtual bool has_gradsums() const { return false; }
+    virtual int32_t eval_gradsums(const float* Z, const float* E, int ld, int M, float* logp,
+                                  float* a1, float* a2) {
+        return AVI_ERR_UNSUPPORTED;
+    }
+    virtual int32_t subsample(const int32_t* idx_host, int64_t batch) {
+        return AVI_OK;   // AdvancedVI.subsample default: identity (src/AdvancedVI.jl:313)
+    }
+    virtual int32_t set_gemm_mode(int mode) { return AVI_OK; }
+    // Device-side minibatch selection for the fused multi-step loop: the rows of iteration k are
+    // idx_dev[k * batch .. (k+1) * batch) with k = st->batch_cursor read ON THE DEVICE.
+    virtual int32_t subsample_dev(const int32_t* idx_dev, int64_t batch, const ObjDeviceState* st) {
+        return AVI_ERR_UNSUPPORTED;
+    }
+    // restrict the target to the data rows [r0, r0 + nr) (multi-rank row sharding)
+    virtual int32_t set_row_shard(int64_t r0, int64_t nr) { return AVI_ERR_UNSUPPORTED; }
+    virtual bool needs_sync_eval() const { return false; }   // host callback: not graph-capturable
+};
+
+// accumulator layout (floats): 4 vectors of `accv` entries + ACC_NSCAL scalars
+//   RepGrad : v0 = sum_m g, v1 = sum_m g*eps, v2 = sum_m eps, v3 = sum_m eps^2
+//             s0 = sum_m logp, s1 = sum_m |eps_m|^2
+//   ScoreGrad: v0 = sum_m f*eps, v1 = sum_m f*eps^2, v2 = sum_m eps, v3 = sum_m eps^2
+//             s0 = sum_m logp, s1 = sum |eps|^2, s2 = sum f, s3 = sum f^2
+//   full-rank: v0 = sum_m w (RepGrad) / sum_m f*u (ScoreGrad, u = L^-T eps), v2 = sum_m u,
+//              followed by one (RepGrad) or two (ScoreGrad) D x D column-major matrix blocks.
+// This vector is what the exchange step all-reduces when the samples are sharded.
+enum { ACC_NSCAL = 8 };
+
+struct avi_obj {
+    avi_ctx* ctx = nullptr;
+    avi_model* model = nullptr;
+    int family = 0, objective = 0, entropy = 0;
+    int D = 0, M = 0;         // M = global number of Monte-Carlo samples
+    int m0 = 0, Mloc = 0;     // this rank's shard
+    int shard_axis = 0;       // AVI_SHARD_*
+    int64_t generation = 0;   // bumped when buffers / shard / target change (captured graphs go stale)
+    int ld = 0, accv = 0;     // leading dimension of sample-major buffers; padded vector length
+    int cap_M = 0;            // sample capacity of the buffers below
+    int64_t P = 0;
+    int64_t acc_len = 0;
+    unsigned long long key = 0, step = 0;   // host mirror of d_state
+    // device buffers
+    ObjDeviceState* d_state = nullptr;
+    float* d_lambda = nullptr;   // P (used by the host-buffer entry points)
+    float* Z = nullptr;          // cap_M x ld
+    float* E = nullptr;          // cap_M x ld
+    float* G = nullptr;          // cap_M x ld
+    float* U = nullptr;          // cap_M x ld (full-rank: L^{-T} eps)
+    float* logp = nullptr;       // cap_M
+    float* esq = nullptr;        // cap_M : |eps_m|^2
+    float* fbuf = nullptr;       // cap_M : ScoreGrad f_m
+    float* acc = nullptr;        // acc_len
+    float* grad = nullptr;       // P
+    float* out = nullptr;        // 4 : value, elbo, logdet, ScoreGrad centring shift
+    // pinned host staging
+    float* h_lambda = nullptr;   // P
+    float* h_grad = nullptr;     // P + 4
+};
+
+struct avi_opt {
+    avi_ctx* ctx = nullptr;
+    avi_obj* obj = nullptr;
+    int rule = 0, op = 0, averager = 0;
+    float hyper[4] = {0, 0, 0, 0};
+    float op_param = 0, avg_param = 0;
+    int64_t P = 0;
+    int64_t iteration = 0;
+    // device state
+    float* lam = nullptr;    // P current iterate
+    float* m1 = nullptr;     // P Adam first moment  | DoG/DoWG x0
+    float* m2 = nullptr;     // P Adam second moment
+    float* avg = nullptr;    // P averaged iterate
+    float* sc = nullptr;     // 16 scalars: see opt.cu
+    float* norm_part = nullptr;   // per-CTA partial norms (DoG/DoWG)
+    float* trace = nullptr;       // 2 * trace_cap (value, elbo) per iteration of one call
+    int trace_cap = 0;
+    float* h_trace = nullptr;     // pinned
+    int32_t* idx_dev = nullptr;   // minibatch indices of one avi_opt_steps_subsampled call
+    int64_t idx_cap = 0;
+    // captured iteration
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    bool graph_subsampled = false;
+    int64_t graph_batch = 0;
+    int64_t graph_gen = -1;
+    int64_t graph_launches = 0;   // kernels per captured iteration
+};
+
+// ---------------------------------------------------------------------------------------------
+// entry points implemented across the .cu files (all enqueue on ctx->stream)
+int32_t avi_obj_ensure_capacity(avi_obj* o, int M);
+// rand(rng, q, M): Z = mu + scale * eps for samples [m0, m0 + Mloc) of the step/key held in *st
+// (or in *ov when ov != nullptr, a host value).  E, esq always written.
+int32_t avi_family_sample(avi_obj* o, const float* lambda, float* Z, float* E, float* esq, int Mloc,
+                          int m0, const ObjDeviceState* st, const ObjDeviceState* ov);
+int32_t avi_objective_local(avi_obj* o, const float* lambda);          // sample + model + reduce -> acc
+int32_t avi_objective_finalize(avi_obj* o, const float* lambda, float* grad, float* out);  // acc -> grad
+// forward-only chunk for estimate_objective: sums_dev = {sum logp, sum |eps|^2, logdet}
+int32_t avi_objective_forward_chunk(avi_obj* o, const float* lambda, int m0, int Mc, const ObjDeviceState* ov,
+                                    float* sums_dev);
+int32_t avi_exchange(avi_ctx* ctx, float* buf, int64_t count);          // all-reduce (no-op single rank)
+int32_t avi_obj_advance(avi_obj* o);                                    // step += 1 on the device
+
+// generic SIMT fp32 GEMM:  C[a*sc_r + b*sc_c] = alpha * sum_k A[a*sa_r + k*sa_k] * B[b*sb_r + k*sb_k],
+// a < Ma, b < Nb, k < K; bounds-checked.
+int32_t avi_gemm_simt(avi_ctx* ctx, const float* A, long long sa_r, long long sa_k, const float* B,
+                      long long sb_r, long long sb_k, float* C, long long sc_r, long long sc_c, int Ma,
+                      int Nb, int K, float alpha);
+// U = L^{-T} E for a column-major lower-triangular L (D x D): row m of U solves L' u = e_m.
+int32_t avi_trsm_lt(avi_ctx* ctx, const float* L, int D, const float* E, float* U, int ld, int M);
+
+// models
+int32_t avi_model_mvnormal_diag_make(avi_ctx* ctx, const float* mu, const float* sigma, int D, avi_model** out);
+int32_t avi_model_glm_make(avi_ctx* ctx, const float* X, const float* y, int64_t n, int d, int64_t n_data,
+                           int likelihood, int variant, int gemm_mode, avi_model** out);
+int32_t avi_model_hostcallback_make(avi_ctx* ctx, int D, int capability, avi_logdensity_fn cb, void* user,
+                                    avi_model** out);

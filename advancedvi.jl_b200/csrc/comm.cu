@@ -1,0 +1,170 @@
+// Exchange step over NVLink / NVSwitch peer memory: a one-shot all-reduce written as one kernel.
+//
+// The payload of the path's single exchange is small (mean-field: 4 D + 8 floats = 16 KB at
+// D = 1025; full-rank: a few MB), i.e. latency-bound, and it sits in the middle of a captured
+// CUDA-graph iteration.  Every rank owns a "symmetric" buffer (two data slots + a flag word per
+// peer) that all peers map through CUDA IPC.  One launch per exchange:
+//   1. copy the local partial sums into my slot (seq & 1),
+//   2. the last CTA to finish publishes: a release store of `seq` into flag[my_rank] of EVERY peer,
+//   3. every CTA waits until all flags in my own array reached `seq` (acquire loads, local memory),
+//   4. every rank sums the nranks slots over NVLink in rank order 0..n-1  => bit-identical result
+//      on all ranks, independent of arrival order (keeps "same seed => same run").
+// Slot parity replaces a second barrier: a rank can only overwrite slot s at seq+2 after every
+// peer published seq+1, which they do after finishing their reads of seq.
+// No NCCL call, no host involvement: safe inside a graph.
+#include <cstring>
+
+#include "avi_internal.cuh"
+
+namespace {
+
+constexpr int MAX_RANKS = 16;
+constexpr int FLAG_WORDS = 64;   // flag area: MAX_RANKS words used, padded to 256 B
+
+struct CommDev {
+    unsigned int seq, arrive, depart, pad;
+};
+
+struct PeerTable {
+    float* data[MAX_RANKS];
+    unsigned int* flags[MAX_RANKS];
+};
+
+struct CommState {
+    int rank = 0, nranks = 1;
+    int64_t max_floats = 0;
+    void* base = nullptr;        // my symmetric allocation: [flags (256 B) | slot 0 | slot 1]
+    void* peer_base[MAX_RANKS] = {nullptr};
+    bool opened[MAX_RANKS] = {false};
+    CommDev* dev = nullptr;
+    PeerTable table{};
+    bool connected = false;
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ float ld_relaxed_sys(const float* p) {
+    float v;
+    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(256)
+k_allreduce_oneshot(float* __restrict__ buf, long long count, long long slot_stride, PeerTable t, int rank,
+                    int nranks, CommDev* __restrict__ cd) {
+    const unsigned int seq = *reinterpret_cast<volatile unsigned int*>(&cd->seq) + 1u;
+    const long long off = (long long)(seq & 1u) * slot_stride;
+    float* mine = t.data[rank] + off;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) mine[i] = buf[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(&cd->arrive, 1u) == gridDim.x - 1) {
+            cd->arrive = 0;
+            __threadfence_system();
+            for (int r = 0; r < nranks; ++r) st_release_sys(t.flags[r] + rank, seq);
+        }
+    }
+    if (threadIdx.x < nranks) {
+        const unsigned int* f = t.flags[rank] + threadIdx.x;
+        while ((int)(ld_acquire_sys(f) - seq) < 0) { }
+    }
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        float s = 0.0f;
+        for (int r = 0; r < nranks; ++r) s += ld_relaxed_sys(t.data[r] + off + i);
+        buf[i] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(&cd->depart, 1u) == gridDim.x - 1) {
+            cd->depart = 0;
+            *reinterpret_cast<volatile unsigned int*>(&cd->seq) = seq;
+        }
+    }
+}
+
+CommState* state(avi_ctx* ctx) { return static_cast<CommState*>(ctx->comm); }
+
+int32_t finish_connect(avi_ctx* ctx, CommState* cs) {
+    for (int r = 0; r < cs->nranks; ++r) {
+        cs->table.flags[r] = static_cast<unsigned int*>(cs->peer_base[r]);
+        cs->table.data[r] = reinterpret_cast<float*>(static_cast<char*>(cs->peer_base[r]) + FLAG_WORDS * 4);
+    }
+    cs->connected = true;
+    ctx->rank = cs->rank; ctx->nranks = cs->nranks;
+    ctx->comm_capturable = true;
+    return AVI_OK;
+}
+
+}  // namespace
+
+int32_t avi_comm_exchange(avi_ctx* ctx, float* buf, int64_t count) {
+    CommState* cs = state(ctx);
+    if (!cs || !cs->connected) return AVI_ERR_UNSUPPORTED;
+    if (count > cs->max_floats) AVI_FAIL(ctx, AVI_ERR_COMM, "exchange payload larger than the symmetric buffer");
+    int grid = (int)std::min<int64_t>(ceil_div(count, 256 * 8), 64);
+    if (grid < 1) grid = 1;
+    k_allreduce_oneshot<<<grid, 256, 0, ctx->stream>>>(buf, count, cs->max_floats, cs->table, cs->rank, cs->nranks, cs->dev);
+    AVI_LAUNCHED(ctx);
+    return AVI_OK;
+}
+
+void avi_comm_destroy(avi_ctx* ctx) {
+    CommState* cs = state(ctx);
+    if (!cs) return;
+    for (int r = 0; r < MAX_RANKS; ++r)
+        if (cs->opened[r]) cudaIpcCloseMemHandle(cs->peer_base[r]);
+    if (cs->base) cudaFree(cs->base);
+    if (cs->dev) cudaFree(cs->dev);
+    delete cs;
+    ctx->comm = nullptr;
+}
+
+extern "C" {
+
+// Allocate this rank's symmetric buffer for payloads of up to max_floats floats and export its
+// CUDA IPC handle (64 bytes) for the peers.
+int32_t avi_comm_buffer(avi_ctx* ctx, int64_t max_floats, char* handle_out) {
+    if (!ctx || max_floats <= 0 || !handle_out) return AVI_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    avi_comm_destroy(ctx);
+    CommState* cs = new CommState();
+    ctx->comm = cs;
+    cs->max_floats = round_up(max_floats, 64);
+    const size_t bytes = FLAG_WORDS * 4 + 2 * (size_t)cs->max_floats * sizeof(float);
+    AVI_CHECK(avi_dev_alloc(ctx, &cs->base, bytes));
+    AVI_CHECK(avi_alloc(ctx, &cs->dev, 1));
+    cudaIpcMemHandle_t h;
+    AVI_CUDA(ctx, cudaIpcGetMemHandle(&h, cs->base));
+    static_assert(sizeof(h) == 64, "CUDA IPC handle size");
+    std::memcpy(handle_out, &h, 64);
+    return AVI_OK;
+}
+
+// handles: nranks x 64 bytes, entry r exported by rank r (all-gathered by the host: torch.distributed
+// in the Python mirror, MPI.jl / Distributed from Julia).  Entry `rank` is this rank's own.
+int32_t avi_comm_connect(avi_ctx* ctx, int32_t rank, int32_t nranks, const char* handles) {
+    if (!ctx || !handles || nranks < 1 || nranks > MAX_RANKS || rank < 0 || rank >= nranks) return AVI_ERR_INVALID;
+    CommState* cs = state(ctx);
+    if (!cs || !cs->base) AVI_FAIL(ctx, AVI_ERR_STATE, "call avi_comm_buffer first");
+    cudaSetDevice(ctx->device);
+    cs->rank = rank; cs->nranks = nranks;
+    for (int r = 0; r < nranks; ++r) {
+        if (r == rank) { cs->peer_base[r] = cs->base; continue; }
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, handles + 64 * (size_t)r, 64);
+        AVI_CUDA(ctx, cudaIpcOpenMemHandle(&cs->peer_base[r], h, cudaIpcMemLazyEnablePeerAccess));
+        cs->opened[r] = true;
+    }
+    return finish_connect(ctx, cs);
+}
+
+}  // extern "C"

@@ -1,0 +1,454 @@
+// K1 (eps-sample + affine transform + |eps|^2) and K3 (reduction over the M samples to the
+// gradient of the variational parameters) for the location-scale Gaussian family, plus the
+// objective orchestration:  local phase -> [exchange] -> finalize.
+//
+// Replaces (reference file:line, paths under /root/reference):
+//   rand(rng, q, M)                      src/families/location_scale.jl:71-87
+//   entropy(q) / logpdf(q, z)            src/families/location_scale.jl:52-63
+//   estimate_entropy (5 estimators)      src/algorithms/entropy.jl:13-15, 27-29, 42-46, 59-65, 80-90
+//   estimate_repgradelbo_ad_forward + AD src/algorithms/repgradelbo.jl:142-177
+//   estimate_scoregradelbo_ad_forward    src/algorithms/scoregradelbo.jl:87-117
+// Gradients are the closed forms of SURVEY.md Appendix A (checked against finite differences of
+// the restated forward in tests/test_oracle_gradients.py).
+#include "avi_internal.cuh"
+#include "device_utils.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// K1: one CTA per Monte-Carlo sample; thread t owns coordinates 4q..4q+3 (one Philox block).
+// Writes Z = mu + s .* eps (mean-field), E = eps (both zero in the padding columns i >= D) and
+// |eps_m|^2.  FULLRANK writes only E (Z = L * eps + mu comes from k_fr_affine).
+template <bool FULLRANK>
+__global__ void __launch_bounds__(256)
+k_sample(const float* __restrict__ lambda, int D, int ld, int m0, const ObjDeviceState* __restrict__ st,
+         ObjDeviceState st_val, int use_val, uint32_t stream_id, float* __restrict__ Z,
+         float* __restrict__ E, float* __restrict__ esq) {
+    __shared__ float sm[33];
+    const unsigned long long step = use_val ? st_val.step : st->step;
+    const unsigned long long key = use_val ? st_val.key : st->key;
+    const int m = blockIdx.x;
+    const float* mu = lambda;
+    const float* sc = lambda + D;
+    float part = 0.0f;
+    for (int q = threadIdx.x; q < ld / 4; q += blockDim.x) {
+        float4 e = normal4((uint32_t)q, (uint32_t)(m0 + m), step, stream_id, key);
+        const int i = 4 * q;
+        float ev[4] = {e.x, e.y, e.z, e.w}, zv[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if (i + c < D) {
+                part = fmaf(ev[c], ev[c], part);
+                zv[c] = FULLRANK ? 0.0f : fmaf(__ldg(sc + i + c), ev[c], __ldg(mu + i + c));
+            } else {
+                ev[c] = 0.0f; zv[c] = 0.0f;
+            }
+        }
+        *reinterpret_cast<float4*>(E + (size_t)m * ld + i) = make_float4(ev[0], ev[1], ev[2], ev[3]);
+        if (!FULLRANK)
+            *reinterpret_cast<float4*>(Z + (size_t)m * ld + i) = make_float4(zv[0], zv[1], zv[2], zv[3]);
+    }
+    float tot = block_sum(part, sm);
+    if (threadIdx.x == 0) esq[m] = tot;
+}
+
+// full-rank affine map: Z[m][i] = mu[i] + sum_{j <= i} L[i + D*j] * E[m][j].
+// CTA = 64 coordinates x 16 samples; L tile and eps tile staged through shared memory.
+constexpr int FA_TI = 64, FA_TM = 16, FA_TK = 32;
+__global__ void __launch_bounds__(256)
+k_fr_affine(const float* __restrict__ lambda, int D, int ld, int Mloc, const float* __restrict__ E,
+            float* __restrict__ Z) {
+    __shared__ float Ls[FA_TK][FA_TI + 1];   // Ls[k][i] = L[i0 + i][k0 + k]
+    __shared__ float Es[FA_TM][FA_TK + 1];   // Es[m][k]
+    const float* L = lambda + D;
+    const int i0 = blockIdx.x * FA_TI, mb = blockIdx.y * FA_TM;
+    const int ti = threadIdx.x & 63, tm = threadIdx.x >> 6;   // thread: coordinate ti, samples tm*4..+3
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const int kmax = min(D, i0 + FA_TI);   // lower triangular: j <= i
+    for (int k0 = 0; k0 < kmax; k0 += FA_TK) {
+        for (int e = threadIdx.x; e < FA_TK * FA_TI; e += 256) {
+            int i = e & 63, k = e >> 6;
+            int gi = i0 + i, gk = k0 + k;
+            Ls[k][i] = (gi < D && gk <= gi) ? __ldg(L + (size_t)gk * D + gi) : 0.0f;
+        }
+        for (int e = threadIdx.x; e < FA_TM * FA_TK; e += 256) {
+            int k = e & 31, mm = e >> 5;
+            int gm = mb + mm, gk = k0 + k;
+            Es[mm][k] = (gm < Mloc && gk < D) ? E[(size_t)gm * ld + gk] : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < FA_TK; ++k) {
+            float l = Ls[k][ti];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[c] = fmaf(l, Es[tm * 4 + c][k], acc[c]);
+        }
+        __syncthreads();
+    }
+    const int gi = i0 + ti;
+    if (gi < ld) {
+        float mu = gi < D ? __ldg(lambda + gi) : 0.0f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            int gm = mb + tm * 4 + c;
+            if (gm < Mloc) Z[(size_t)gm * ld + gi] = gi < D ? acc[c] + mu : 0.0f;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// scalars: s0 = sum logp, s1 = sum |eps|^2; ScoreGrad additionally f_m = log q(z_m) - log pi(z_m)
+// (shifted by f_shift = out[3], see k_finalize_*) and s2 = sum f, s3 = sum f^2.
+// Single CTA => fixed summation order.
+__global__ void __launch_bounds__(1024)
+k_scalars(const float* __restrict__ lambda, int D, int fullrank, int objective, const float* __restrict__ logp,
+          const float* __restrict__ esq, int Mloc, const float* __restrict__ out, float* __restrict__ fbuf,
+          float* __restrict__ scal) {
+    __shared__ float sm[33];
+    float ld_part = 0.0f;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+        size_t idx = fullrank ? (size_t)D + (size_t)i * (D + 1) : (size_t)D + i;
+        ld_part += logf(__ldg(lambda + idx));
+    }
+    const float logdet = block_sum(ld_part, sm);
+    const float shift = out[3];
+    float a = 0.f, b = 0.f, c = 0.f, d = 0.f;
+    for (int m = threadIdx.x; m < Mloc; m += blockDim.x) {
+        float lp = logp[m], es = esq[m];
+        a += lp; b += es;
+        if (objective == AVI_SCOREGRAD) {
+            // log q(z_m) with scale \ (z - mu) == eps:  -|eps|^2/2 - D log(2 pi)/2 - logdet
+            float f = (-0.5f * es - 0.5f * (float)D * AVI_LOG2PI - logdet) - lp - shift;
+            fbuf[m] = f;
+            c += f; d = fmaf(f, f, d);
+        }
+    }
+    a = block_sum(a, sm); b = block_sum(b, sm); c = block_sum(c, sm); d = block_sum(d, sm);
+    if (threadIdx.x == 0) {
+        scal[0] = a; scal[1] = b; scal[2] = c; scal[3] = d;
+        scal[4] = 0.f; scal[5] = 0.f; scal[6] = 0.f; scal[7] = 0.f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K3, mean-field: per-coordinate sums over the local samples.  CTA = 32 coordinates x 32 sample
+// groups; coalesced 128 B rows; fixed-order combine across the 32 groups.
+//   RepGrad  : v0 = sum g, v1 = sum g*eps        (skipped when the target produced them itself)
+//   ScoreGrad: v0 = sum f*eps, v1 = sum f*eps^2
+//   both     : v2 = sum eps, v3 = sum eps^2
+__global__ void __launch_bounds__(1024)
+k_reduce_mf(const float* __restrict__ G, const float* __restrict__ E, const float* __restrict__ fbuf,
+            int ld, int Mloc, int D, int accv, int objective, int skip_g, float* __restrict__ acc) {
+    __shared__ float sm[4][32][33];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int i = blockIdx.x * 32 + tx;
+    float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+    if (i < D) {
+        for (int m = ty; m < Mloc; m += 32) {
+            float e = E[(size_t)m * ld + i];
+            v2 += e; v3 = fmaf(e, e, v3);
+            if (objective == AVI_SCOREGRAD) {
+                float f = fbuf[m];
+                v0 = fmaf(f, e, v0); v1 = fmaf(f * e, e, v1);
+            } else if (!skip_g) {
+                float g = G[(size_t)m * ld + i];
+                v0 += g; v1 = fmaf(g, e, v1);
+            }
+        }
+    }
+    sm[0][ty][tx] = v0; sm[1][ty][tx] = v1; sm[2][ty][tx] = v2; sm[3][ty][tx] = v3;
+    __syncthreads();
+    if (ty < 4 && i < D) {
+        float s = 0.f;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) s += sm[ty][r][tx];
+        if (!(skip_g && ty < 2)) acc[(size_t)ty * accv + i] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// finalize, mean-field: global sums -> gradient of the value slot, value, elbo.
+// Gradient entries are independent; the scalars are recomputed by every CTA in the same fixed
+// order (CTA 0 writes them), so the grid size does not change any result.
+__global__ void __launch_bounds__(256)
+k_finalize_mf(const float* __restrict__ acc, int accv, const float* __restrict__ lambda, int D, int M,
+              int objective, int entropy, float* __restrict__ grad, float* __restrict__ out) {
+    __shared__ float sm[33];
+    const float* s = lambda + D;
+    float part = 0.f;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) part += logf(__ldg(s + i));
+    const float logdet = block_sum(part, sm);
+    const float* scal = acc + 4 * (size_t)accv;
+    const float invM = 1.0f / (float)M;
+    const float *v0 = acc, *v1 = acc + accv, *v2 = acc + 2 * (size_t)accv, *v3 = acc + 3 * (size_t)accv;
+    const int gstride = gridDim.x * blockDim.x;
+    if (objective == AVI_REPGRAD) {
+        const bool stl = entropy == AVI_ENT_STL || entropy == AVI_ENT_STL_ZEROGRAD;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < D; i += gstride) {
+            float si = __ldg(s + i), inv = 1.0f / si;
+            float sg = v0[i], sge = v1[i];
+            if (stl) { sg = fmaf(v2[i], inv, sg); sge = fmaf(v3[i], inv, sge); }   // w = g + eps / s
+            float gm = -sg * invM, gs = -sge * invM;
+            if (entropy == AVI_ENT_CLOSEDFORM || entropy == AVI_ENT_MONTECARLO) gs -= inv;
+            else if (entropy == AVI_ENT_STL_ZEROGRAD) gs += inv;
+            grad[i] = gm; grad[D + i] = gs;
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            float ent = (entropy == AVI_ENT_CLOSEDFORM || entropy == AVI_ENT_CLOSEDFORM_ZEROGRAD)
+                            ? (float)D * AVI_H0 + logdet
+                            : 0.5f * scal[1] * invM + 0.5f * (float)D * AVI_LOG2PI + logdet;
+            float value = -(scal[0] * invM + ent);
+            out[0] = value; out[1] = -value; out[2] = logdet;
+        }
+    } else {
+        const float fbar = scal[2] * invM;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < D; i += gstride) {
+            float inv = 1.0f / __ldg(s + i);
+            grad[i] = (v0[i] - fbar * v2[i]) * invM * inv;
+            grad[D + i] = (v1[i] - fbar * v3[i]) * invM * inv;
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            float shift = out[3];
+            out[0] = 0.5f * (scal[3] * invM - fbar * fbar);   // VarGrad value (shift-invariant)
+            out[1] = -(fbar + shift);                         // elbo = mean(log pi - log q)
+            out[2] = logdet;
+            out[3] = fbar + shift;                            // centre f for the next call
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// full-rank helpers
+// W[m][i] = G[m][i] + U[m][i]   (STL: w = g + L^-T eps), or W[m][i] = f_m * U[m][i] (ScoreGrad)
+__global__ void k_fr_make_w(const float* G, const float* __restrict__ U, const float* __restrict__ fbuf, int ld,
+                            int Mloc, int mode, float* W) {   // W may alias G
+    const int m = blockIdx.x;
+    for (int i = threadIdx.x; i < ld; i += blockDim.x) {
+        size_t p = (size_t)m * ld + i;
+        W[p] = mode == 0 ? G[p] + U[p] : fbuf[m] * U[p];
+    }
+}
+
+// column sums of a sample-major buffer: v[i] = sum_m W[m][i]
+__global__ void __launch_bounds__(1024)
+k_colsum(const float* __restrict__ W, int ld, int Mloc, int D, float* __restrict__ v) {
+    __shared__ float sm[32][33];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int i = blockIdx.x * 32 + tx;
+    float a = 0.f;
+    if (i < D)
+        for (int m = ty; m < Mloc; m += 32) a += W[(size_t)m * ld + i];
+    sm[ty][tx] = a;
+    __syncthreads();
+    if (ty == 0 && i < D) {
+        float s = 0.f;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) s += sm[r][tx];
+        v[i] = s;
+    }
+}
+
+// grad = [ . ; vec(tril(...)) ]: RepGrad  -C1/M -+ diag(1/L_ii);  ScoreGrad  (C1 - fbar C2)/M.
+// C*[j*D + i] = sum_m W[m][i] E[m][j] (column-major L layout).
+__global__ void k_finalize_fr_mat(const float* __restrict__ C1, const float* __restrict__ C2,
+                                  const float* __restrict__ scal, const float* __restrict__ lambda, int D,
+                                  int M, int objective, int entropy, float* __restrict__ grad) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)D * D) return;
+    const int j = (int)(idx / D), i = (int)(idx % D);   // column-major: entry (i, j)
+    const float invM = 1.0f / (float)M;
+    float g = 0.0f;
+    if (i >= j) {
+        if (objective == AVI_REPGRAD) {
+            g = -C1[idx] * invM;
+            if (i == j) {
+                float inv = 1.0f / __ldg(lambda + D + idx);
+                if (entropy == AVI_ENT_CLOSEDFORM || entropy == AVI_ENT_MONTECARLO) g -= inv;
+                else if (entropy == AVI_ENT_STL_ZEROGRAD) g += inv;
+            }
+        } else {
+            const float fbar = scal[2] * invM;
+            g = (C1[idx] - fbar * C2[idx]) * invM;
+        }
+    }
+    grad[D + idx] = g;
+}
+
+__global__ void __launch_bounds__(1024)
+k_finalize_fr_vec(const float* __restrict__ acc, int accv, const float* __restrict__ lambda, int D, int M,
+                  int objective, int entropy, float* __restrict__ grad, float* __restrict__ out) {
+    __shared__ float sm[33];
+    float part = 0.f;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) part += logf(__ldg(lambda + D + (size_t)i * (D + 1)));
+    const float logdet = block_sum(part, sm);
+    const float* scal = acc + 4 * (size_t)accv;
+    const float invM = 1.0f / (float)M;
+    if (objective == AVI_REPGRAD) {
+        for (int i = threadIdx.x; i < D; i += blockDim.x) grad[i] = -acc[i] * invM;
+        if (threadIdx.x == 0) {
+            float ent = (entropy == AVI_ENT_CLOSEDFORM || entropy == AVI_ENT_CLOSEDFORM_ZEROGRAD)
+                            ? (float)D * AVI_H0 + logdet
+                            : 0.5f * scal[1] * invM + 0.5f * (float)D * AVI_LOG2PI + logdet;
+            float value = -(scal[0] * invM + ent);
+            out[0] = value; out[1] = -value; out[2] = logdet;
+        }
+    } else {
+        const float fbar = scal[2] * invM;
+        const float* v2 = acc + 2 * (size_t)accv;
+        for (int i = threadIdx.x; i < D; i += blockDim.x) grad[i] = (acc[i] - fbar * v2[i]) * invM;
+        if (threadIdx.x == 0) {
+            float shift = out[3];
+            out[0] = 0.5f * (scal[3] * invM - fbar * fbar);
+            out[1] = -(fbar + shift);
+            out[2] = logdet;
+            out[3] = fbar + shift;
+        }
+    }
+}
+
+__global__ void k_advance(ObjDeviceState* st) { st->step += 1ull; }
+
+// forward-only chunk sums for estimate_objective: out = {sum logp, sum |eps|^2, logdet}
+__global__ void __launch_bounds__(1024)
+k_forward_sums(const float* __restrict__ lambda, int D, int fullrank, const float* __restrict__ logp,
+               const float* __restrict__ esq, int Mc, float* __restrict__ out) {
+    __shared__ float sm[33];
+    float ld_part = 0.0f;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+        size_t idx = fullrank ? (size_t)D + (size_t)i * (D + 1) : (size_t)D + i;
+        ld_part += logf(__ldg(lambda + idx));
+    }
+    const float logdet = block_sum(ld_part, sm);
+    float a = 0.f, b = 0.f;
+    for (int m = threadIdx.x; m < Mc; m += blockDim.x) { a += logp[m]; b += esq[m]; }
+    a = block_sum(a, sm); b = block_sum(b, sm);
+    if (threadIdx.x == 0) { out[0] = a; out[1] = b; out[2] = logdet; }
+}
+
+}  // namespace
+
+// ==============================================================================================
+int32_t avi_family_sample(avi_obj* o, const float* lambda, float* Z, float* E, float* esq, int Mloc, int m0,
+                          const ObjDeviceState* st, const ObjDeviceState* ov) {
+    avi_ctx* ctx = o->ctx;
+    if (Mloc <= 0) return AVI_OK;
+    ObjDeviceState sv{};
+    int use_val = 0;
+    if (ov) { sv = *ov; use_val = 1; }
+    AviTimed timed(ctx, "sample");
+    if (o->family == AVI_MEANFIELD) {
+        k_sample<false><<<Mloc, 256, 0, ctx->stream>>>(lambda, o->D, o->ld, m0, st, sv, use_val, AVI_STREAM_EPS, Z, E, esq);
+        AVI_LAUNCHED(ctx);
+    } else {
+        k_sample<true><<<Mloc, 256, 0, ctx->stream>>>(lambda, o->D, o->ld, m0, st, sv, use_val, AVI_STREAM_EPS, Z, E, esq);
+        AVI_LAUNCHED(ctx);
+        dim3 grid((unsigned)ceil_div(o->ld, FA_TI), (unsigned)ceil_div(Mloc, FA_TM));
+        k_fr_affine<<<grid, 256, 0, ctx->stream>>>(lambda, o->D, o->ld, Mloc, E, Z);
+        AVI_LAUNCHED(ctx);
+    }
+    return AVI_OK;
+}
+
+int32_t avi_obj_advance(avi_obj* o) {
+    k_advance<<<1, 1, 0, o->ctx->stream>>>(o->d_state);
+    AVI_LAUNCHED(o->ctx);
+    o->step += 1;
+    return AVI_OK;
+}
+
+// local phase: everything that only needs this rank's samples.  Leaves the partial sums in o->acc.
+int32_t avi_objective_local(avi_obj* o, const float* lambda) {
+    avi_ctx* ctx = o->ctx;
+    const int D = o->D, ld = o->ld, Mloc = o->Mloc, accv = o->accv;
+    float* scal = o->acc + 4 * (size_t)accv;
+    if (Mloc <= 0) {   // a rank without samples contributes zeros
+        AVI_CUDA(ctx, cudaMemsetAsync(o->acc, 0, o->acc_len * sizeof(float), ctx->stream));
+        if (o->shard_axis == AVI_SHARD_SAMPLES && ctx->nranks > 1) AVI_CHECK(avi_exchange(ctx, o->acc, o->acc_len));
+        return AVI_OK;
+    }
+    AVI_CHECK(avi_family_sample(o, lambda, o->Z, o->E, o->esq, Mloc, o->m0, o->d_state, nullptr));
+    const bool rep = o->objective == AVI_REPGRAD;
+    const bool stl = o->entropy == AVI_ENT_STL || o->entropy == AVI_ENT_STL_ZEROGRAD;
+    const bool rows = o->shard_axis == AVI_SHARD_ROWS && ctx->nranks > 1;
+    int skip_g = 0;
+    if (rep) {
+        if (o->family == AVI_MEANFIELD && o->model->has_gradsums()) {
+            AVI_CHECK(o->model->eval_gradsums(o->Z, o->E, ld, Mloc, o->logp, o->acc, o->acc + accv));
+            skip_g = 1;
+            if (rows) AVI_CHECK(avi_exchange(ctx, o->acc, 2LL * accv));
+        } else {
+            AVI_CHECK(o->model->eval(o->Z, ld, Mloc, o->logp, o->G));
+            if (rows) AVI_CHECK(avi_exchange(ctx, o->G, (int64_t)Mloc * ld));
+        }
+    } else {
+        AVI_CHECK(o->model->eval(o->Z, ld, Mloc, o->logp, nullptr));
+    }
+    // row sharding: every rank holds all samples and a slice of the data rows; log pi and its
+    // gradient are sums over rows, everything after this point is replicated arithmetic
+    if (rows) AVI_CHECK(avi_exchange(ctx, o->logp, Mloc));
+    k_scalars<<<1, 1024, 0, ctx->stream>>>(lambda, D, o->family == AVI_FULLRANK, o->objective, o->logp, o->esq,
+                                           Mloc, o->out, o->fbuf, scal);
+    AVI_LAUNCHED(ctx);
+    if (o->family == AVI_MEANFIELD) {
+        // with a fused target and a closed-form entropy nothing else is needed (v2, v3 unused)
+        if (!(skip_g && !stl)) {
+            k_reduce_mf<<<(unsigned)ceil_div(D, 32), dim3(32, 32), 0, ctx->stream>>>(
+                o->G, o->E, o->fbuf, ld, Mloc, D, accv, o->objective, skip_g, o->acc);
+            AVI_LAUNCHED(ctx);
+        }
+    } else {
+        float* C1 = scal + ACC_NSCAL;
+        float* C2 = C1 + (size_t)D * D;
+        const float* W = o->G;
+        if (!rep || stl) {
+            AVI_CHECK(avi_trsm_lt(ctx, lambda + D, D, o->E, o->U, ld, Mloc));
+            k_fr_make_w<<<Mloc, 256, 0, ctx->stream>>>(o->G, o->U, o->fbuf, ld, Mloc, rep ? 0 : 1, o->G);
+            AVI_LAUNCHED(ctx);
+        }
+        k_colsum<<<(unsigned)ceil_div(D, 32), dim3(32, 32), 0, ctx->stream>>>(W, ld, Mloc, D, o->acc);
+        AVI_LAUNCHED(ctx);
+        // C1[j*D + i] = sum_m W[m][i] * E[m][j]: contraction over the samples
+        AVI_CHECK(avi_gemm_simt(ctx, o->E, 1, ld, W, 1, ld, C1, D, 1, D, D, Mloc, 1.0f));
+        if (!rep) {
+            k_colsum<<<(unsigned)ceil_div(D, 32), dim3(32, 32), 0, ctx->stream>>>(o->U, ld, Mloc, D,
+                                                                                  o->acc + 2 * (size_t)accv);
+            AVI_LAUNCHED(ctx);
+            AVI_CHECK(avi_gemm_simt(ctx, o->E, 1, ld, o->U, 1, ld, C2, D, 1, D, D, Mloc, 1.0f));
+        }
+    }
+    // sample sharding: the partial sums are the exchange payload
+    if (o->shard_axis == AVI_SHARD_SAMPLES && ctx->nranks > 1) AVI_CHECK(avi_exchange(ctx, o->acc, o->acc_len));
+    return AVI_OK;
+}
+
+int32_t avi_objective_forward_chunk(avi_obj* o, const float* lambda, int m0, int Mc, const ObjDeviceState* ov,
+                                    float* sums_dev) {
+    avi_ctx* ctx = o->ctx;
+    AVI_CHECK(avi_family_sample(o, lambda, o->Z, o->E, o->esq, Mc, m0, o->d_state, ov));
+    AVI_CHECK(o->model->eval(o->Z, o->ld, Mc, o->logp, nullptr));
+    k_forward_sums<<<1, 1024, 0, ctx->stream>>>(lambda, o->D, o->family == AVI_FULLRANK, o->logp, o->esq, Mc, sums_dev);
+    AVI_LAUNCHED(ctx);
+    return AVI_OK;
+}
+
+int32_t avi_objective_finalize(avi_obj* o, const float* lambda, float* grad, float* out) {
+    avi_ctx* ctx = o->ctx;
+    const int D = o->D, accv = o->accv;
+    if (o->family == AVI_MEANFIELD) {
+        unsigned nb = (unsigned)std::min<int64_t>(ceil_div(D, 256), 64);
+        k_finalize_mf<<<nb, 256, 0, ctx->stream>>>(o->acc, accv, lambda, D, o->M, o->objective, o->entropy, grad, out);
+        AVI_LAUNCHED(ctx);
+    } else {
+        const float* scal = o->acc + 4 * (size_t)accv;
+        const float* C1 = scal + ACC_NSCAL;
+        const float* C2 = C1 + (size_t)D * D;
+        size_t n = (size_t)D * D;
+        // the matrix part reads fbar from scal before k_finalize_fr_vec rewrites out[3]
+        k_finalize_fr_mat<<<(unsigned)ceil_div(n, 256), 256, 0, ctx->stream>>>(C1, C2, scal, lambda, D, o->M,
+                                                                              o->objective, o->entropy, grad);
+        AVI_LAUNCHED(ctx);
+        k_finalize_fr_vec<<<1, 1024, 0, ctx->stream>>>(o->acc, accv, lambda, D, o->M, o->objective, o->entropy, grad, out);
+        AVI_LAUNCHED(ctx);
+    }
+    return AVI_OK;
+}

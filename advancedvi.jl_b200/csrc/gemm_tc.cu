@@ -1,0 +1,279 @@
+// tcgen05 / TMEM / TMA contraction  D[a, b] = sum_k A[a, k] * B[b, k]  (both operands K-major fp32
+// rows in HBM, read as TF32) with three fused epilogues:
+//   EPI_GLM_FWD : a = Monte-Carlo sample, b = data row, k = feature.   D = logits.  Writes the
+//                 weighted residual R[a][b] (TF32-rounded: it is the B operand of the backward
+//                 contraction) and per-(row-chunk) partial log-likelihood sums.  The logits never
+//                 reach HBM.                         (X*beta + BernoulliLogit/Normal log-likelihood,
+//                 docs/src/tutorials/subsampling.md:35-36 evaluated for all M samples at once
+//                 instead of the per-sample loop of src/algorithms/repgradelbo.jl:84-86)
+//   EPI_GLM_BWD : a = feature, b = sample, k = data row.  D = X' R = grad_beta log-lik for every
+//                 sample.  Reduced against eps in the epilogue to sum_m g and sum_m g*eps (the
+//                 mean-field pullback of src/families/location_scale.jl:86); G never reaches HBM.
+//   EPI_STORE   : C[ks][b * ldc + a] = D (split-K slabs), for the full-rank family.
+//
+// Structure (one CTA per SM, persistent over work units = (a-block, b-chunk, k-split)):
+//   warp 0      TMA producer   (cp.async.bulk.tensor, 128B swizzle, STAGES-deep mbarrier ring)
+//   warp 1      MMA issuer     (one elected thread: tcgen05.mma.kind::tf32, M = 128, N = NT)
+//   warp 2      TMEM allocator (512 columns = 2 accumulator stages of up to 256 columns)
+//   warps 4-11  epilogue       (tcgen05.ld 32x32b; warp w reads lanes 32*(w%4).., column half w/8)
+#include "avi_internal.cuh"
+#include "device_utils.cuh"
+#include "gemm_tc.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int BM = 128;            // UMMA M (TMEM lanes)
+constexpr int BK = 32;             // fp32 elements per 128-byte swizzle row
+constexpr int STAGES = 4;
+constexpr int A_TILE_BYTES = BM * BK * 4;          // 16 KB
+constexpr int B_TILE_BYTES_MAX = 256 * BK * 4;     // 32 KB
+constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES_MAX;
+constexpr int NUM_THREADS = 384;
+
+struct SmemCtl {
+    uint64_t full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2];
+    uint32_t tmem_base;
+    float ys[2][256];
+};
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + (int)sizeof(SmemCtl);
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+template <int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    SmemCtl* ctl = reinterpret_cast<SmemCtl*>(tiles + STAGES * STAGE_BYTES);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tc::tma_prefetch_desc(&tmA);
+        tc::tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&ctl->full[s], 1); tc::mbar_init(&ctl->empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { tc::mbar_init(&ctl->tmem_full[s], 1); tc::mbar_init(&ctl->tmem_empty[s], 8); }
+        tc::mbar_fence_init();
+    }
+    if (warp == 2) tc::tmem_alloc(&ctl->tmem_base, 512);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = ctl->tmem_base;
+
+    const int NT = p.nt;
+    const int units = p.n_ablk * p.n_bchunk * p.n_ksplit;
+    const uint32_t stage_tx = (uint32_t)(A_TILE_BYTES + NT * BK * 4);
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                const int ab = u % p.n_ablk, bc = (u / p.n_ablk) % p.n_bchunk, ks = u / (p.n_ablk * p.n_bchunk);
+                const int kb0 = ks * p.kb_per_split, kb1 = min(p.n_kblk, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    tc::mbar_wait(&ctl->empty[stage], phase ^ 1);
+                    uint8_t* sa = tiles + stage * STAGE_BYTES;
+                    tc::mbar_arrive_expect_tx(&ctl->full[stage], stage_tx);
+                    tc::tma_load_2d(sa, &tmA, &ctl->full[stage], kb * BK, ab * BM);
+                    tc::tma_load_2d(sa + A_TILE_BYTES, &tmB, &ctl->full[stage], kb * BK, bc * NT);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = tc::idesc_tf32(BM, NT);
+            int stage = 0; uint32_t phase = 0;
+            int as = 0; uint32_t aphase = 0;
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                const int ks = u / (p.n_ablk * p.n_bchunk);
+                const int kb0 = ks * p.kb_per_split, kb1 = min(p.n_kblk, kb0 + p.kb_per_split);
+                tc::mbar_wait(&ctl->tmem_empty[as], aphase ^ 1);
+                tc::fence_after_sync();
+                const uint32_t tacc = tmem_base + (uint32_t)(as * 256);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    tc::mbar_wait(&ctl->full[stage], phase);
+                    tc::fence_after_sync();
+                    const uint32_t sa = tc::smem_u32(tiles + stage * STAGE_BYTES);
+                    const uint64_t da = tc::smem_desc_k_sw128(sa);
+                    const uint64_t db = tc::smem_desc_k_sw128(sa + A_TILE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 8; ++k)   // UMMA K = 8 tf32 = 32 bytes: +2 in 16-byte units
+                        tc::umma_tf32(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                                      (kb > kb0 || k > 0) ? 1u : 0u);
+                    tc::umma_commit(&ctl->empty[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc::umma_commit(&ctl->tmem_full[as]);
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int ew = warp - 4, quarter = warp & 3, half = ew >> 2;
+        const int et = threadIdx.x - 128;   // 0..255
+        const int c_begin = half * (NT / 2), c_end = c_begin + NT / 2;
+        int as = 0; uint32_t aphase = 0;
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            const int ab = u % p.n_ablk, bc = (u / p.n_ablk) % p.n_bchunk, ks = u / (p.n_ablk * p.n_bchunk);
+            const int a = ab * BM + quarter * 32 + lane;   // this thread's accumulator row
+            const bool a_ok = a < p.Ma;
+            if (EPI == EPI_GLM_FWD) {
+                int b = bc * NT + et;
+                if (et < NT) ctl->ys[as][et] = b < p.Nb ? __ldg(p.y + b) : 0.0f;
+                epi_bar_sync();
+            }
+            tc::mbar_wait(&ctl->tmem_full[as], aphase);
+            tc::fence_after_sync();
+            const uint32_t tacc = tmem_base + (uint32_t)(as * 256) + ((uint32_t)(quarter * 32) << 16);
+            float s1 = 0.0f, s2 = 0.0f;
+            for (int c = c_begin; c < c_end; c += 8) {
+                float v[8];
+                tc::tmem_ld8(tacc + (uint32_t)c, v);
+                const int b0 = bc * NT + c;
+                if (EPI == EPI_GLM_FWD) {
+                    float r[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int b = b0 + j;
+                        const float yv = ctl->ys[as][c + j];
+                        float lp, rr;
+                        if (p.likelihood == AVI_GLM_BERNOULLI_LOGIT) {
+                            const float l = v[j];
+                            const float e = __expf(-fabsf(l));
+                            const float inv = __fdividef(1.0f, 1.0f + e);
+                            const float sig = l >= 0.0f ? inv : e * inv;
+                            lp = yv * l - (fmaxf(l, 0.0f) - __logf(inv));   // y l - log1pexp(l)
+                            rr = yv - sig;
+                        } else {
+                            rr = yv - v[j];
+                            lp = -0.5f * AVI_LOG2PI - 0.5f * rr * rr;
+                        }
+                        const bool ok = b < p.Nb;
+                        s1 += ok ? lp : 0.0f;
+                        r[j] = ok ? tc::round_tf32(p.w * rr) : 0.0f;
+                    }
+                    if (a_ok && b0 < p.ldc) {
+                        float4* dst = reinterpret_cast<float4*>(p.C + (size_t)a * p.ldc + b0);
+                        dst[0] = make_float4(r[0], r[1], r[2], r[3]);
+                        dst[1] = make_float4(r[4], r[5], r[6], r[7]);
+                    }
+                } else if (EPI == EPI_GLM_BWD) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int b = b0 + j;
+                        if (b < p.Nb && a_ok) {
+                            const float e = __ldg(p.E + (size_t)b * p.lde + a);
+                            s1 += v[j];
+                            s2 = fmaf(v[j], e, s2);
+                        }
+                    }
+                } else {
+                    float* Cs = p.C + (size_t)ks * p.slab_stride;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int b = b0 + j;
+                        if (b < p.Nb && a_ok) Cs[(size_t)b * p.ldc + a] = v[j];
+                    }
+                }
+            }
+            // accumulator stage drained: hand it back to the MMA warp
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&ctl->tmem_empty[as]);
+            if (EPI == EPI_GLM_FWD) {
+                if (a_ok) p.part1[(size_t)(bc * 2 + half) * p.ldpart + a] = s1;
+            } else if (EPI == EPI_GLM_BWD) {
+                if (a_ok) {
+                    const size_t slab = (size_t)((ks * p.n_bchunk + bc) * 2 + half) * p.ldpart;
+                    p.part1[slab + a] = s1;
+                    p.part2[slab + a] = s2;
+                }
+            }
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+    }
+
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 2) {
+        tc::fence_after_sync();
+        tc::tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
+}
+
+}  // namespace
+
+// rows x cols fp32 matrix with row pitch ld (floats); box = box_rows x 32 floats, 128B swizzle,
+// out-of-bounds elements read as zero.
+int32_t avi_tc_make_tmap(avi_ctx* ctx, CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld,
+                         int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) AVI_FAIL(ctx, AVI_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld % 4) || box_rows < 1 || box_rows > 256 || rows < 1 || cols < 1)
+        AVI_FAIL(ctx, AVI_ERR_INVALID, "tensor map: misaligned operand");
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)ld * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) AVI_FAIL(ctx, AVI_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
+    return AVI_OK;
+}
+
+// Pick the b-chunk width (multiple of 16, <= 256) that minimises the makespan of
+// n_ablk * ceil(Nb / nt) * n_ksplit units on `sms` CTAs.
+int avi_tc_pick_nt(int64_t Nb, int n_ablk, int n_ksplit, int sms, int nt_max) {
+    int best = 16; double best_cost = 1e300;
+    int hi = (int)std::min<int64_t>(nt_max, round_up(Nb, 16));
+    for (int nt = 16; nt <= hi; nt += 16) {
+        int64_t units = (int64_t)n_ablk * ceil_div(Nb, nt) * n_ksplit;
+        int64_t waves = ceil_div(units, sms);
+        double cost = (double)waves * (nt + 24.0);   // +24: per-unit pipeline fill / epilogue tail
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = nt; }
+    }
+    return best;
+}
+
+int32_t avi_tc_launch(avi_ctx* ctx, int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p) {
+    if (p.nt % 16 || p.nt < 16 || p.nt > 256) AVI_FAIL(ctx, AVI_ERR_INVALID, "bad b-chunk width");
+    const int units = p.n_ablk * p.n_bchunk * p.n_ksplit;
+    if (units <= 0) return AVI_OK;
+    static bool attr_done = false;
+    if (!attr_done) {
+        AVI_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tc<EPI_GLM_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        AVI_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tc<EPI_GLM_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        AVI_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tc<EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr_done = true;
+    }
+    const unsigned grid = (unsigned)std::min(units, ctx->prop.multiProcessorCount);
+    AviTimed timed(ctx, epi == EPI_GLM_FWD ? "glm_fwd" : epi == EPI_GLM_BWD ? "glm_bwd" : "gemm_store");
+    if (epi == EPI_GLM_FWD) k_gemm_tc<EPI_GLM_FWD><<<grid, NUM_THREADS, SMEM_BYTES, ctx->stream>>>(tmA, tmB, p);
+    else if (epi == EPI_GLM_BWD) k_gemm_tc<EPI_GLM_BWD><<<grid, NUM_THREADS, SMEM_BYTES, ctx->stream>>>(tmA, tmB, p);
+    else k_gemm_tc<EPI_STORE><<<grid, NUM_THREADS, SMEM_BYTES, ctx->stream>>>(tmA, tmB, p);
+    AVI_LAUNCHED(ctx);
+    return AVI_OK;
+}

@@ -1,0 +1,34 @@
+// Host-side interface of the tcgen05 contraction kernel (gemm_tc.cu).
+#pragma once
+
+#include <cuda.h>
+#include <stdint.h>
+
+struct avi_ctx;
+
+enum { EPI_GLM_FWD = 0, EPI_GLM_BWD = 1, EPI_STORE = 2 };
+
+// D[a, b] = sum_k A[a, k] B[b, k];  a < Ma (blocks of 128), b < Nb (chunks of nt), k in 32-float blocks
+struct TcParams {
+    int Ma, Nb;
+    int n_ablk, n_bchunk, n_ksplit;
+    int n_kblk, kb_per_split;
+    int nt;
+    // epilogue operands
+    float* C;            // FWD: R [a][ldc];  STORE: slabs [ks][b * ldc + a]
+    int ldc;
+    long long slab_stride;
+    const float* y;      // FWD: response per data row (b)
+    float w;             // FWD: likelihood adjustment folded into R
+    int likelihood;
+    const float* E;      // BWD: eps [b][lde]
+    int lde;
+    float* part1;        // FWD: partial log-lik [(bc*2+half)][ldpart];  BWD: sum g  [slab][ldpart]
+    float* part2;        // BWD: sum g*eps
+    int ldpart;
+};
+
+int32_t avi_tc_make_tmap(avi_ctx* ctx, CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld,
+                         int box_rows);
+int avi_tc_pick_nt(int64_t Nb, int n_ablk, int n_ksplit, int sms, int nt_max);
+int32_t avi_tc_launch(avi_ctx* ctx, int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p);

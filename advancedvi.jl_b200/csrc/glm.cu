@@ -1,0 +1,430 @@
+// Hierarchical GLM targets, theta = [beta(d); eta], sigma = exp(eta), evaluated for all M
+// Monte-Carlo samples at once (the reference calls logdensity once per sample,
+// src/algorithms/repgradelbo.jl:84-86, i.e. M GEMVs over X):
+//   variant SUBSAMPLING  docs/src/tutorials/subsampling.md:26-38 (+ subsample :99-102)
+//   variant BASIC        README.md:47-58 under the exp bijector README.md:91-106
+//   likelihood GAUSSIAN  builder-defined Gaussian GLM (BASELINE.json config 4)
+// Arithmetic: SURVEY.md Appendix A.5 / oracle/models.py.
+//
+// Device data: X is kept in both K-major layouts, Xr [n][dK] (features contiguous, forward
+// contraction) and Xc [d][nP] (rows contiguous, backward contraction).  In the TF32 modes the
+// stored X is rounded to TF32 once (round-to-nearest) so the tensor-core reads are exact.
+#include <cmath>
+
+#include "avi_internal.cuh"
+#include "device_utils.cuh"
+#include "gemm_tc.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr float LOG3 = 1.0986122886681098f;
+
+// per-sample prior pieces: pre[m] = {prior_lp, 1/sigma^2, d logp / d eta, |beta|^2}
+__global__ void __launch_bounds__(256)
+k_glm_pre(const float* __restrict__ Z, int ld, int d, int variant, int include_prior, float* __restrict__ Zt,
+          float4* __restrict__ pre) {
+    __shared__ float sm[33];
+    const int m = blockIdx.x;
+    float part = 0.f;
+    for (int i = threadIdx.x; i < ld; i += blockDim.x) {
+        float z = i < d ? Z[(size_t)m * ld + i] : 0.0f;
+        part = fmaf(z, z, part);
+        if (Zt) Zt[(size_t)m * ld + i] = tc::round_tf32(z);
+    }
+    const float bsq = block_sum(part, sm);
+    if (threadIdx.x == 0) {
+        const float eta = Z[(size_t)m * ld + d];
+        const float s2 = expf(2.0f * eta), inv = 1.0f / s2;
+        float lp = -0.5f * (float)d * AVI_LOG2PI - (float)d * eta - 0.5f * bsq * inv - LOG3 - 0.5f * AVI_LOG2PI;
+        float ge = -(float)d + bsq * inv;
+        if (variant == AVI_GLM_SUBSAMPLING) { lp -= s2 / 18.0f; ge -= s2 / 9.0f; }
+        else { lp -= eta * eta / 18.0f; ge -= eta / 9.0f; }
+        pre[m] = include_prior ? make_float4(lp, inv, ge, bsq) : make_float4(0.f, 0.f, 0.f, bsq);
+    }
+}
+
+// SIMT mode: logits in R -> weighted residual in place, per-sample log-likelihood sum
+__global__ void __launch_bounds__(256)
+k_glm_lik(float* __restrict__ R, int ldR, int n, const float* __restrict__ y, int likelihood, float w,
+          float* __restrict__ llsum) {
+    __shared__ float sm[33];
+    const int m = blockIdx.x;
+    float part = 0.f;
+    for (int j = threadIdx.x; j < ldR; j += blockDim.x) {
+        float r = 0.0f;
+        if (j < n) {
+            const float l = R[(size_t)m * ldR + j], yv = __ldg(y + j);
+            if (likelihood == AVI_GLM_BERNOULLI_LOGIT) {
+                part += yv * l - softplus_f(l);
+                r = yv - sigmoid_f(l);
+            } else {
+                r = yv - l;
+                part += -0.5f * AVI_LOG2PI - 0.5f * r * r;
+            }
+        }
+        R[(size_t)m * ldR + j] = w * r;
+    }
+    part = block_sum(part, sm);
+    if (threadIdx.x == 0) llsum[m] = part;
+}
+
+// fused mean-field tail: a1[i] = sum_m G[m][i], a2[i] = sum_m G[m][i] eps[m][i] where
+// G = (split-K partial sums of X'R) - beta / sigma^2 for i < d and d logp / d eta for i == d;
+// the trailing CTAs assemble logp[m] = w * sum(partial log-lik) + prior.
+__global__ void __launch_bounds__(1024)
+k_glm_post_sums(const float* __restrict__ Z, const float* __restrict__ E, int ld, int M, int d,
+                const float4* __restrict__ pre, const float* __restrict__ a1p, const float* __restrict__ a2p,
+                int nslab, int ldslab, const float* __restrict__ llpart, int nparts, int ldpart, float w,
+                int ncoordblk, float* __restrict__ a1, float* __restrict__ a2, float* __restrict__ logp) {
+    if ((int)blockIdx.x >= ncoordblk) {
+        const int m = (blockIdx.x - ncoordblk) * 1024 + threadIdx.y * 32 + threadIdx.x;
+        if (m < M) {
+            float s = 0.f;
+            for (int q = 0; q < nparts; ++q) s += llpart[(size_t)q * ldpart + m];
+            logp[m] = fmaf(w, s, pre[m].x);
+        }
+        return;
+    }
+    __shared__ float sm[2][32][33];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int i = blockIdx.x * 32 + tx;
+    float t1 = 0.f, t2 = 0.f;
+    if (i <= d) {
+        for (int m = ty; m < M; m += 32) {
+            const float4 pm = pre[m];
+            const float e = E[(size_t)m * ld + i];
+            const float g = i < d ? -Z[(size_t)m * ld + i] * pm.y : pm.z;
+            t1 += g; t2 = fmaf(g, e, t2);
+        }
+    }
+    sm[0][ty][tx] = t1; sm[1][ty][tx] = t2;
+    __syncthreads();
+    if (ty < 2 && i <= d) {
+        float s = 0.f;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) s += sm[ty][r][tx];
+        if (i < d) {
+            const float* part = ty == 0 ? a1p : a2p;
+            for (int q = 0; q < nslab; ++q) s += part[(size_t)q * ldslab + i];
+        }
+        (ty == 0 ? a1 : a2)[i] = s;
+    }
+}
+
+// full gradient tail: G[m][i] = sum_s slab[s][m][i] - beta_i / sigma^2, G[m][d] = dlogp/deta, logp[m]
+__global__ void __launch_bounds__(256)
+k_glm_post_full(const float* __restrict__ Z, int ld, int d, const float4* __restrict__ pre,
+                const float* __restrict__ slabs, int nslab, long long slab_stride,
+                const float* __restrict__ llpart, int nparts, int ldpart, float w, float* __restrict__ G,
+                float* __restrict__ logp) {
+    const int m = blockIdx.x;
+    const float4 pm = pre[m];
+    if (G) {
+        for (int i = threadIdx.x; i < ld; i += blockDim.x) {
+            float g = 0.0f;
+            if (i < d) {
+                for (int s = 0; s < nslab; ++s) g += slabs[(size_t)s * slab_stride + (size_t)m * ld + i];
+                g = fmaf(-Z[(size_t)m * ld + i], pm.y, g);
+            } else if (i == d) {
+                g = pm.z;
+            }
+            G[(size_t)m * ld + i] = g;
+        }
+    }
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int q = 0; q < nparts; ++q) s += llpart[(size_t)q * ldpart + m];
+        logp[m] = fmaf(w, s, pm.x);
+    }
+}
+
+// column-major host layout (n x d, ldsrc = n) -> Xr [n][dK] and Xc [d][nP], optionally TF32-rounded
+__global__ void k_glm_layout(const float* __restrict__ src, long long n, int d, int dK, long long nP, int round,
+                             float* __restrict__ Xr, float* __restrict__ Xc) {
+    __shared__ float t[32][33];
+    const long long r0 = (long long)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    // read src[(c0+ty) * n + r0 + tx] (coalesced along rows)
+    for (int yy = threadIdx.y; yy < 32; yy += blockDim.y) {
+        long long r = r0 + threadIdx.x; int c = c0 + yy;
+        float v = (r < n && c < d) ? src[(size_t)c * n + r] : 0.0f;
+        if (round) v = tc::round_tf32(v);
+        t[yy][threadIdx.x] = v;
+        if (r < nP && c < d) Xc[(size_t)c * nP + r] = v;
+    }
+    __syncthreads();
+    for (int yy = threadIdx.y; yy < 32; yy += blockDim.y) {
+        long long r = r0 + yy; int c = c0 + threadIdx.x;
+        if (r < n && c < dK) Xr[(size_t)r * dK + c] = t[threadIdx.x][yy];
+    }
+}
+
+// minibatch gather: rows idx[cursor*batch + j] of the full data -> contiguous batch buffers
+__global__ void k_glm_gather(const float* __restrict__ Xr_full, const float* __restrict__ y_full, int dK, int d,
+                             const int32_t* __restrict__ idx, const ObjDeviceState* __restrict__ st, long long batch,
+                             long long nPb, float* __restrict__ Xr_b, float* __restrict__ Xc_b,
+                             float* __restrict__ y_b) {
+    __shared__ float t[32][33];
+    const int32_t* ix = idx + (st ? st->batch_cursor * batch : 0);
+    const long long j0 = (long long)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    for (int yy = threadIdx.y; yy < 32; yy += blockDim.y) {
+        long long j = j0 + yy; int c = c0 + threadIdx.x;
+        float v = 0.0f;
+        if (j < batch && c < dK) {
+            v = Xr_full[(size_t)ix[j] * dK + c];
+            Xr_b[(size_t)j * dK + c] = v;
+        }
+        t[yy][threadIdx.x] = v;
+        if (blockIdx.y == 0 && threadIdx.x == 0 && j < batch) y_b[j] = y_full[ix[j]];
+    }
+    __syncthreads();
+    for (int yy = threadIdx.y; yy < 32; yy += blockDim.y) {
+        long long j = j0 + threadIdx.x; int c = c0 + yy;
+        if (j < nPb && c < d) Xc_b[(size_t)c * nPb + j] = j < batch ? t[threadIdx.x][yy] : 0.0f;
+    }
+}
+
+struct Glm : avi_model {
+    int d = 0, dK = 0;
+    long long n_full = 0, nP_full = 0, n_data = 0;
+    int likelihood = 0, variant = 0, mode = 0;
+    int nshards = 1; long long rows_global = 0; int include_prior = 1;
+    float *Xr_full = nullptr, *Xc_full = nullptr, *y_full = nullptr;
+    float *Xr_b = nullptr, *Xc_b = nullptr, *y_b = nullptr;
+    long long batch_cap = 0, nP_b = 0;
+    int32_t* idx_own = nullptr; long long idx_own_cap = 0;
+    // active view
+    const float *Xr = nullptr, *Xc = nullptr, *y = nullptr;
+    long long n_act = 0, nP = 0;
+    bool subsampled = false;
+    // work buffers
+    int capM = 0, cap_ld = 0; long long cap_n = 0;
+    long long ldR = 0;
+    float *R = nullptr, *Zt = nullptr, *llpart = nullptr, *a1p = nullptr, *slabs = nullptr;
+    float4* pre = nullptr;
+    long long llpart_cap = 0, ap_cap = 0, slab_cap = 0;
+
+    ~Glm() override {
+        avi_free(Xr_full); avi_free(Xc_full); avi_free(y_full); avi_free(Xr_b); avi_free(Xc_b); avi_free(y_b);
+        avi_free(idx_own); avi_free(R); avi_free(Zt); avi_free(llpart); avi_free(a1p);
+        avi_free(slabs); avi_free(pre);
+    }
+    bool tc_mode() const { return mode != AVI_GEMM_SIMT_FP32; }
+    float likeadj() const {
+        if (variant != AVI_GLM_SUBSAMPLING) return 1.0f;
+        double rows = subsampled ? (double)n_act * nshards : (double)rows_global;
+        return (float)((double)n_data / rows);
+    }
+    void view_full() { Xr = Xr_full; Xc = Xc_full; y = y_full; n_act = n_full; nP = nP_full; subsampled = false; }
+
+    int32_t ensure(int M, int ld) {
+        if (M <= capM && ld == cap_ld && n_act <= cap_n) return AVI_OK;
+        avi_free(R); avi_free(Zt); avi_free(pre);
+        generation++;
+        capM = std::max(M, capM); cap_ld = ld; cap_n = std::max(cap_n, n_act);
+        ldR = round_up(cap_n, 32);
+        AVI_CHECK(avi_alloc(ctx, &R, (size_t)capM * ldR));
+        AVI_CHECK(avi_alloc(ctx, &Zt, (size_t)capM * ld));
+        AVI_CHECK(avi_alloc(ctx, &pre, (size_t)capM));
+        return AVI_OK;
+    }
+    int32_t ensure_buf(float** p, long long* cap, long long need) {
+        if (need <= *cap) return AVI_OK;
+        generation++;
+        avi_free(*p);
+        AVI_CHECK(avi_alloc(ctx, p, (size_t)need));
+        *cap = need;
+        return AVI_OK;
+    }
+
+    // forward: R <- w * resid, llpart/nparts <- partial log-lik sums
+    int32_t forward(const float* Z, int ld, int M, int* nparts) {
+        const float w = likeadj();
+        k_glm_pre<<<M, 256, 0, ctx->stream>>>(Z, ld, d, variant, include_prior, tc_mode() ? Zt : nullptr, pre);
+        AVI_LAUNCHED(ctx);
+        if (!tc_mode()) {
+            AVI_CHECK(ensure_buf(&llpart, &llpart_cap, capM));
+            // logits[m][j] = sum_k Z[m][k] Xr[j][k]
+            AVI_CHECK(avi_gemm_simt(ctx, Z, ld, 1, Xr, dK, 1, R, ldR, 1, M, (int)n_act, d, 1.0f));
+            k_glm_lik<<<M, 256, 0, ctx->stream>>>(R, (int)ldR, (int)n_act, y, likelihood, w, llpart);
+            AVI_LAUNCHED(ctx);
+            *nparts = 1;
+            return AVI_OK;
+        }
+        TcParams p{};
+        p.Ma = M; p.Nb = (int)n_act;
+        p.n_ablk = (int)ceil_div(M, 128);
+        p.nt = avi_tc_pick_nt(n_act, p.n_ablk, 1, ctx->prop.multiProcessorCount, 256);
+        p.n_bchunk = (int)ceil_div(n_act, p.nt);
+        p.n_ksplit = 1; p.n_kblk = (int)ceil_div(d, 32); p.kb_per_split = p.n_kblk;
+        p.C = R; p.ldc = (int)ldR; p.y = y; p.w = w; p.likelihood = likelihood;
+        AVI_CHECK(ensure_buf(&llpart, &llpart_cap, (long long)p.n_bchunk * 2 * capM));
+        p.part1 = llpart; p.ldpart = capM;
+        CUtensorMap tmA, tmB;
+        AVI_CHECK(avi_tc_make_tmap(ctx, &tmA, Zt, M, d, ld, 128));
+        AVI_CHECK(avi_tc_make_tmap(ctx, &tmB, Xr, n_act, d, dK, p.nt));
+        AVI_CHECK(avi_tc_launch(ctx, EPI_GLM_FWD, tmA, tmB, p));
+        *nparts = p.n_bchunk * 2;
+        return AVI_OK;
+    }
+
+    int32_t backward_setup(int M, TcParams* p, CUtensorMap* tmA, CUtensorMap* tmB) {
+        p->Ma = d; p->Nb = M;
+        p->n_ablk = (int)ceil_div(d, 128);
+        p->nt = (int)std::min<int64_t>(256, round_up(M, 16));
+        p->n_bchunk = (int)ceil_div(M, p->nt);
+        p->n_kblk = (int)ceil_div(n_act, 32);
+        int want = std::max(1, ctx->prop.multiProcessorCount / (p->n_ablk * p->n_bchunk));
+        want = std::min(want, p->n_kblk);
+        p->kb_per_split = (int)ceil_div(p->n_kblk, want);
+        p->n_ksplit = (int)ceil_div(p->n_kblk, p->kb_per_split);
+        AVI_CHECK(avi_tc_make_tmap(ctx, tmA, Xc, d, n_act, nP, 128));
+        AVI_CHECK(avi_tc_make_tmap(ctx, tmB, R, M, n_act, ldR, p->nt));
+        return AVI_OK;
+    }
+
+    int32_t eval(const float* Z, int ld, int M, float* logp, float* G) override {
+        if (M <= 0) return AVI_OK;
+        AVI_CHECK(ensure(M, ld));
+        int nparts = 0;
+        AVI_CHECK(forward(Z, ld, M, &nparts));
+        const float w = likeadj();
+        const float* sl = nullptr; int nslab = 0; long long sstride = 0;
+        if (G) {
+            if (!tc_mode()) {
+                // G[m][i] = sum_j R[m][j] Xc[i][j]
+                AVI_CHECK(avi_gemm_simt(ctx, R, ldR, 1, Xc, nP, 1, G, ld, 1, M, d, (int)n_act, 1.0f));
+                sl = G; nslab = 1; sstride = 0;
+            } else {
+                TcParams p{}; CUtensorMap tmA, tmB;
+                AVI_CHECK(backward_setup(M, &p, &tmA, &tmB));
+                sstride = (long long)capM * ld;
+                AVI_CHECK(ensure_buf(&slabs, &slab_cap, sstride * p.n_ksplit));
+                p.C = slabs; p.ldc = ld; p.slab_stride = sstride;
+                AVI_CHECK(avi_tc_launch(ctx, EPI_STORE, tmA, tmB, p));
+                sl = slabs; nslab = p.n_ksplit;
+            }
+        }
+        k_glm_post_full<<<M, 256, 0, ctx->stream>>>(Z, ld, d, pre, sl, nslab, sstride, llpart, nparts, capM, w, G, logp);
+        AVI_LAUNCHED(ctx);
+        return AVI_OK;
+    }
+
+    bool has_gradsums() const override { return tc_mode(); }
+    int32_t eval_gradsums(const float* Z, const float* E, int ld, int M, float* logp, float* a1, float* a2) override {
+        if (M <= 0) return AVI_OK;
+        AVI_CHECK(ensure(M, ld));
+        int nparts = 0;
+        AVI_CHECK(forward(Z, ld, M, &nparts));
+        TcParams p{}; CUtensorMap tmA, tmB;
+        AVI_CHECK(backward_setup(M, &p, &tmA, &tmB));
+        const int nslab = p.n_ksplit * p.n_bchunk * 2;
+        const int ldslab = (int)round_up(d, 32);
+        AVI_CHECK(ensure_buf(&a1p, &ap_cap, 2LL * nslab * ldslab));
+        float* a2p = a1p + (size_t)nslab * ldslab;
+        p.E = E; p.lde = ld; p.part1 = a1p; p.part2 = a2p; p.ldpart = ldslab;
+        AVI_CHECK(avi_tc_launch(ctx, EPI_GLM_BWD, tmA, tmB, p));
+        const int ncb = (int)ceil_div(d + 1, 32);
+        const unsigned grid = (unsigned)(ncb + ceil_div(M, 1024));
+        k_glm_post_sums<<<grid, dim3(32, 32), 0, ctx->stream>>>(Z, E, ld, M, d, pre, a1p, a2p, nslab, ldslab, llpart,
+                                                                nparts, capM, likeadj(), ncb, a1, a2, logp);
+        AVI_LAUNCHED(ctx);
+        return AVI_OK;
+    }
+
+    int32_t ensure_batch(long long batch) {
+        if (batch <= batch_cap) return AVI_OK;
+        avi_free(Xr_b); avi_free(Xc_b); avi_free(y_b);
+        generation++;
+        batch_cap = batch; nP_b = round_up(batch, 32);
+        AVI_CHECK(avi_alloc(ctx, &Xr_b, (size_t)batch_cap * dK));
+        AVI_CHECK(avi_alloc(ctx, &Xc_b, (size_t)d * nP_b));
+        AVI_CHECK(avi_alloc(ctx, &y_b, (size_t)batch_cap));
+        return AVI_OK;
+    }
+    int32_t gather(const int32_t* idx_dev, long long batch, const ObjDeviceState* st) {
+        AVI_CHECK(ensure_batch(batch));
+        // the pitch of Xc_b follows the allocated capacity so that captured tensor maps stay valid
+        dim3 grid((unsigned)ceil_div(nP_b, 32), (unsigned)ceil_div(dK, 32));
+        k_glm_gather<<<grid, dim3(32, 8), 0, ctx->stream>>>(Xr_full, y_full, dK, d, idx_dev, st, batch, nP_b, Xr_b,
+                                                            Xc_b, y_b);
+        AVI_LAUNCHED(ctx);
+        Xr = Xr_b; Xc = Xc_b; y = y_b; n_act = batch; nP = nP_b; subsampled = true;
+        return AVI_OK;
+    }
+    int32_t subsample(const int32_t* idx_host, int64_t batch) override {
+        if (!idx_host) { view_full(); return AVI_OK; }
+        if (batch <= 0) AVI_FAIL(ctx, AVI_ERR_INVALID, "empty batch");
+        for (int64_t j = 0; j < batch; ++j)
+            if (idx_host[j] < 0 || idx_host[j] >= n_full) AVI_FAIL(ctx, AVI_ERR_INVALID, "batch index out of range");
+        if (batch > idx_own_cap) {
+            avi_free(idx_own);
+            AVI_CHECK(avi_alloc(ctx, &idx_own, (size_t)batch));
+            idx_own_cap = batch;
+        }
+        AVI_CUDA(ctx, cudaMemcpyAsync(idx_own, idx_host, batch * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        AVI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // idx_host is only borrowed for the call
+        return gather(idx_own, batch, nullptr);
+    }
+    int32_t subsample_dev(const int32_t* idx_dev, int64_t batch, const ObjDeviceState* st) override {
+        if (batch <= 0 || batch > n_full) AVI_FAIL(ctx, AVI_ERR_INVALID, "bad batch size");
+        return gather(idx_dev, batch, st);
+    }
+    int32_t set_gemm_mode(int m) override {
+        if (m == mode) return AVI_OK;
+        AVI_FAIL(ctx, AVI_ERR_UNSUPPORTED,
+                 "the arithmetic mode fixes how X is stored (exact fp32 or TF32-rounded); create a new target");
+    }
+};
+
+}  // namespace
+
+int32_t avi_model_glm_make(avi_ctx* ctx, const float* X, const float* y, int64_t n, int d, int64_t n_data,
+                           int likelihood, int variant, int gemm_mode, avi_model** out) {
+    if (!X || !y || n <= 0 || d <= 0 || n_data <= 0) AVI_FAIL(ctx, AVI_ERR_INVALID, "bad arguments");
+    if (n > 0x7fffffffLL) AVI_FAIL(ctx, AVI_ERR_UNSUPPORTED, "more than 2^31-1 rows per device");
+    if (likelihood != AVI_GLM_BERNOULLI_LOGIT && likelihood != AVI_GLM_GAUSSIAN) AVI_FAIL(ctx, AVI_ERR_INVALID, "likelihood");
+    if (variant != AVI_GLM_SUBSAMPLING && variant != AVI_GLM_BASIC) AVI_FAIL(ctx, AVI_ERR_INVALID, "variant");
+    if (gemm_mode == AVI_GEMM_TF32X3) AVI_FAIL(ctx, AVI_ERR_UNSUPPORTED, "AVI_GEMM_TF32X3 is not implemented yet");
+    if (gemm_mode != AVI_GEMM_SIMT_FP32 && gemm_mode != AVI_GEMM_TF32) AVI_FAIL(ctx, AVI_ERR_INVALID, "gemm_mode");
+    Glm* g = new Glm();
+    g->ctx = ctx; g->D = d + 1; g->capability = 1;
+    g->d = d; g->dK = (int)round_up(d, 4);
+    g->n_full = n; g->nP_full = round_up(n, 32); g->n_data = n_data; g->rows_global = n;
+    g->likelihood = likelihood; g->variant = variant; g->mode = gemm_mode;
+    float* tmp = nullptr;
+    int32_t rc = avi_alloc(ctx, &g->Xr_full, (size_t)n * g->dK);
+    if (rc == AVI_OK) rc = avi_alloc(ctx, &g->Xc_full, (size_t)d * g->nP_full);
+    if (rc == AVI_OK) rc = avi_alloc(ctx, &g->y_full, (size_t)n);
+    if (rc == AVI_OK) rc = avi_alloc(ctx, &tmp, (size_t)n * d);
+    if (rc != AVI_OK) { avi_free(tmp); delete g; return rc; }
+    cudaError_t e = avi_copy(ctx, tmp, X, (size_t)n * d * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = avi_copy(ctx, g->y_full, y, (size_t)n * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        dim3 grid((unsigned)ceil_div(g->nP_full, 32), (unsigned)ceil_div(g->dK, 32));
+        k_glm_layout<<<grid, dim3(32, 8), 0, ctx->stream>>>(tmp, n, d, g->dK, g->nP_full, g->tc_mode() ? 1 : 0,
+                                                            g->Xr_full, g->Xc_full);
+        ctx->launches++;
+        e = cudaStreamSynchronize(ctx->stream);
+    }
+    avi_free(tmp);
+    if (e != cudaSuccess) {
+        avi_set_error(ctx, std::string("avi_model_glm_make: ") + cudaGetErrorString(e));
+        delete g;
+        return AVI_ERR_CUDA;
+    }
+    g->view_full();
+    *out = g;
+    return AVI_OK;
+}
+
+// declared in api.cu
+int32_t avi_glm_set_data_shard(avi_model* model, int32_t nshards, int64_t rows_global, int32_t include_prior) {
+    Glm* g = dynamic_cast<Glm*>(model);
+    if (!g) return AVI_ERR_UNSUPPORTED;
+    if (nshards < 1 || rows_global < g->n_full) return AVI_ERR_INVALID;
+    g->nshards = nshards; g->rows_global = rows_global; g->include_prior = include_prior ? 1 : 0;
+    return AVI_OK;
+}

@@ -1,0 +1,413 @@
+// K4: the fused SGD step -- Optimisers.update! + operator + averager of
+// src/algorithms/common.jl:91-94 with the parameters resident on the device -- and the
+// multi-iteration driver that replays one captured iteration as a CUDA graph.
+//   rules      Optimisers.Descent / Adam (third-party), DoG / DoWG  src/optimization/rules.jl:17-64
+//   operators  ClipScale  src/optimization/clip_scale.jl:18-29
+//              ProximalLocationScaleEntropy  src/optimization/proximal_location_scale_entropy.jl:32-61
+//   averaging  PolynomialAveraging / NoAveraging  src/optimization/averaging.jl:42-53
+//   non-finite value slot => the step is not applied  src/algorithms/common.jl:83-89
+#include <cmath>
+#include <cstring>
+
+#include "avi_internal.cuh"
+#include "device_utils.cuh"
+
+namespace {
+
+// scalar state sc[]: 0 averaging t | 1 DoG v | 2 DoG r | 3 beta1^t | 4 beta2^t | 5 last step size
+enum { SC_T = 0, SC_V = 1, SC_R = 2, SC_B1T = 3, SC_B2T = 4, SC_ETA = 5, SC_N = 16 };
+
+struct UpdArgs {
+    int rule, op, averager;
+    float h0, h1, h2, h3;   // rule hyper-parameters
+    float op_param, avg_param;
+    int D, fullrank;
+    long long P;
+    int nparts;             // DoG/DoWG: number of partial norms
+};
+
+// DoG / DoWG partial norms: part[2b] = sum (x - x0)^2, part[2b+1] = sum g^2 over the CTA's slice
+__global__ void __launch_bounds__(256)
+k_norms(const float* __restrict__ lam, const float* __restrict__ x0, const float* __restrict__ g, long long P,
+        float* __restrict__ part) {
+    __shared__ float sm[33];
+    float a = 0.f, b = 0.f;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+        float dx = lam[p] - x0[p], gg = g[p];
+        a = fmaf(dx, dx, a); b = fmaf(gg, gg, b);
+    }
+    a = block_sum(a, sm); b = block_sum(b, sm);
+    if (threadIdx.x == 0) { part[2 * blockIdx.x] = a; part[2 * blockIdx.x + 1] = b; }
+}
+
+__device__ __forceinline__ bool is_scale_diag(long long p, int D, int fullrank) {
+    if (p < D) return false;
+    long long q = p - D;
+    return fullrank ? (q % (D + 1) == 0) : true;
+}
+
+// COMMIT = the single CTA also commits the scalar state, the trace entry and the step counter;
+// otherwise k_commit does it after every CTA has read the old scalars.
+template <bool COMMIT>
+__global__ void __launch_bounds__(256)
+k_update(float* __restrict__ lam, const float* __restrict__ grad, float* __restrict__ m1, float* __restrict__ m2,
+         float* __restrict__ avg, float* __restrict__ sc, const float* __restrict__ out,
+         ObjDeviceState* __restrict__ st, float* __restrict__ trace, int trace_cap,
+         const float* __restrict__ norm_part, UpdArgs a) {
+    const float value = out[0];
+    const bool bad = !isfinite(value);
+    const int halted = st->halted;
+    if (halted || bad) {
+        if (COMMIT && threadIdx.x == 0 && !halted) {
+            int tp = st->trace_pos;
+            if (tp < trace_cap) { trace[2 * tp] = value; trace[2 * tp + 1] = out[1]; }
+            st->trace_pos = tp + 1;
+            st->halted = 1;
+        }
+        return;
+    }
+    float eta = 0.f, v_new = 0.f, r_new = 0.f;
+    const float b1t = sc[SC_B1T], b2t = sc[SC_B2T], t_avg = sc[SC_T];
+    if (a.rule == AVI_RULE_DESCENT) {
+        eta = a.h0;
+    } else if (a.rule == AVI_RULE_DOG || a.rule == AVI_RULE_DOWG) {
+        float dx2 = 0.f, g2 = 0.f;
+        for (int q = 0; q < a.nparts; ++q) { dx2 += norm_part[2 * q]; g2 += norm_part[2 * q + 1]; }
+        r_new = fmaxf(sqrtf(dx2), sc[SC_R]);
+        if (a.rule == AVI_RULE_DOG) { v_new = sc[SC_V] + g2; eta = r_new / sqrtf(v_new); }
+        else { float r2 = r_new * r_new; v_new = sc[SC_V] + r2 * g2; eta = r2 / sqrtf(v_new); }
+    }
+    const float w = (a.avg_param + 1.0f) / (t_avg + a.avg_param);
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < a.P; p += (long long)gridDim.x * blockDim.x) {
+        const float g = grad[p];
+        float x = lam[p], dx;
+        if (a.rule == AVI_RULE_ADAM) {
+            float mt = a.h1 * m1[p] + (1.0f - a.h1) * g;
+            float vt = a.h2 * m2[p] + (1.0f - a.h2) * g * g;
+            m1[p] = mt; m2[p] = vt;
+            dx = mt / (1.0f - b1t) / (sqrtf(vt / (1.0f - b2t)) + a.h3) * a.h0;
+        } else {
+            dx = eta * g;
+        }
+        x -= dx;
+        if (a.op != AVI_OP_IDENTITY && is_scale_diag(p, a.D, a.fullrank)) {
+            if (a.op == AVI_OP_CLIPSCALE) x = fmaxf(x, a.op_param);
+            else x = x + (sqrtf(fmaf(x, x, 4.0f * eta)) - x) * 0.5f;
+        }
+        lam[p] = x;
+        if (a.averager == AVI_AVG_POLYNOMIAL) avg[p] = (1.0f - w) * avg[p] + w * x;
+    }
+    if (COMMIT) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            sc[SC_T] = t_avg + 1.0f;
+            sc[SC_ETA] = eta;
+            if (a.rule == AVI_RULE_ADAM) { sc[SC_B1T] = b1t * a.h1; sc[SC_B2T] = b2t * a.h2; }
+            if (a.rule == AVI_RULE_DOG || a.rule == AVI_RULE_DOWG) { sc[SC_V] = v_new; sc[SC_R] = r_new; }
+            int tp = st->trace_pos;
+            if (tp < trace_cap) { trace[2 * tp] = value; trace[2 * tp + 1] = out[1]; }
+            st->trace_pos = tp + 1;
+            st->step += 1ull;
+            st->batch_cursor += 1;
+        }
+    }
+}
+
+__global__ void k_commit(float* __restrict__ sc, const float* __restrict__ out, ObjDeviceState* __restrict__ st,
+                         float* __restrict__ trace, int trace_cap, const float* __restrict__ norm_part, UpdArgs a) {
+    if (threadIdx.x != 0) return;
+    const float value = out[0];
+    if (st->halted) return;
+    int tp = st->trace_pos;
+    if (tp < trace_cap) { trace[2 * tp] = value; trace[2 * tp + 1] = out[1]; }
+    st->trace_pos = tp + 1;
+    if (!isfinite(value)) { st->halted = 1; return; }
+    float eta = a.rule == AVI_RULE_DESCENT ? a.h0 : 0.f;
+    if (a.rule == AVI_RULE_DOG || a.rule == AVI_RULE_DOWG) {
+        float dx2 = 0.f, g2 = 0.f;
+        for (int q = 0; q < a.nparts; ++q) { dx2 += norm_part[2 * q]; g2 += norm_part[2 * q + 1]; }
+        float r_new = fmaxf(sqrtf(dx2), sc[SC_R]), v_new;
+        if (a.rule == AVI_RULE_DOG) { v_new = sc[SC_V] + g2; eta = r_new / sqrtf(v_new); }
+        else { float r2 = r_new * r_new; v_new = sc[SC_V] + r2 * g2; eta = r2 / sqrtf(v_new); }
+        sc[SC_V] = v_new; sc[SC_R] = r_new;
+    }
+    if (a.rule == AVI_RULE_ADAM) { sc[SC_B1T] *= a.h1; sc[SC_B2T] *= a.h2; }
+    sc[SC_T] += 1.0f;
+    sc[SC_ETA] = eta;
+    st->step += 1ull;
+    st->batch_cursor += 1;
+}
+
+__global__ void k_begin_call(ObjDeviceState* st) { st->trace_pos = 0; st->batch_cursor = 0; st->halted = 0; }
+
+UpdArgs make_args(const avi_opt* op) {
+    UpdArgs a{};
+    a.rule = op->rule; a.op = op->op; a.averager = op->averager;
+    a.h0 = op->hyper[0]; a.h1 = op->hyper[1]; a.h2 = op->hyper[2]; a.h3 = op->hyper[3];
+    a.op_param = op->op_param; a.avg_param = op->avg_param;
+    a.D = op->obj->D; a.fullrank = op->obj->family == AVI_FULLRANK; a.P = op->P;
+    return a;
+}
+
+constexpr int NORM_BLOCKS_MAX = 256;
+
+// enqueue ONE iteration of `step` (common.jl:75-104 minus the callback)
+int32_t enqueue_iteration(avi_opt* op, bool subsampled, int64_t batch) {
+    avi_obj* o = op->obj;
+    avi_ctx* ctx = op->ctx;
+    if (subsampled) AVI_CHECK(o->model->subsample_dev(op->idx_dev, batch, o->d_state));
+    AVI_CHECK(avi_objective_local(o, op->lam));
+    AVI_CHECK(avi_objective_finalize(o, op->lam, o->grad, o->out));
+    UpdArgs a = make_args(op);
+    const bool dog = op->rule == AVI_RULE_DOG || op->rule == AVI_RULE_DOWG;
+    const int nb_upd = (int)std::min<int64_t>(ceil_div(op->P, 256 * 4), 4 * ctx->prop.multiProcessorCount);
+    if (dog) {
+        a.nparts = (int)std::min<int64_t>(ceil_div(op->P, 1024), NORM_BLOCKS_MAX);
+        k_norms<<<a.nparts, 256, 0, ctx->stream>>>(op->lam, op->m1, o->grad, op->P, op->norm_part);
+        AVI_LAUNCHED(ctx);
+    }
+    if (nb_upd <= 1) {
+        k_update<true><<<1, 256, 0, ctx->stream>>>(op->lam, o->grad, op->m1, op->m2, op->avg, op->sc, o->out,
+                                                   o->d_state, op->trace, op->trace_cap, op->norm_part, a);
+        AVI_LAUNCHED(ctx);
+    } else {
+        k_update<false><<<nb_upd, 256, 0, ctx->stream>>>(op->lam, o->grad, op->m1, op->m2, op->avg, op->sc, o->out,
+                                                         o->d_state, op->trace, op->trace_cap, op->norm_part, a);
+        AVI_LAUNCHED(ctx);
+        k_commit<<<1, 32, 0, ctx->stream>>>(op->sc, o->out, o->d_state, op->trace, op->trace_cap, op->norm_part, a);
+        AVI_LAUNCHED(ctx);
+    }
+    return AVI_OK;
+}
+
+void drop_graph(avi_opt* op) {
+    if (op->graph_exec) cudaGraphExecDestroy(op->graph_exec);
+    if (op->graph) cudaGraphDestroy(op->graph);
+    op->graph_exec = nullptr; op->graph = nullptr;
+}
+
+int32_t run_steps(avi_opt* op, int32_t n, const int32_t* idx_host, int64_t batch, float* value_host, float* elbo_host,
+                  int32_t* n_done) {
+    avi_obj* o = op->obj;
+    avi_ctx* ctx = op->ctx;
+    if (n_done) *n_done = 0;
+    if (n <= 0) return AVI_OK;
+    cudaSetDevice(ctx->device);
+    const bool subsampled = idx_host != nullptr;
+    if (n > op->trace_cap) {
+        AVI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        avi_free(op->trace);
+        if (op->h_trace) cudaFreeHost(op->h_trace);
+        op->h_trace = nullptr;
+        op->trace_cap = std::max(n, 1024);
+        AVI_CHECK(avi_alloc(ctx, &op->trace, 2 * (size_t)op->trace_cap));
+        AVI_CUDA(ctx, cudaMallocHost(&op->h_trace, 2 * (size_t)op->trace_cap * sizeof(float)));
+        drop_graph(op);
+    }
+    if (subsampled) {
+        const int64_t need = (int64_t)n * batch;
+        if (need > op->idx_cap) {
+            AVI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            avi_free(op->idx_dev);
+            op->idx_cap = need;
+            AVI_CHECK(avi_alloc(ctx, &op->idx_dev, (size_t)need));
+            drop_graph(op);
+        }
+        AVI_CUDA(ctx, cudaMemcpyAsync(op->idx_dev, idx_host, need * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    k_begin_call<<<1, 1, 0, ctx->stream>>>(o->d_state);
+    AVI_LAUNCHED(ctx);
+
+    const bool capturable = !ctx->timing && !o->model->needs_sync_eval() && !(ctx->nranks > 1 && !ctx->comm_capturable);
+    if (capturable) {
+        const int64_t gen = o->generation * 1000003 + o->model->generation;
+        if (op->graph_exec && (op->graph_gen != gen || op->graph_subsampled != subsampled || op->graph_batch != batch))
+            drop_graph(op);
+        if (!op->graph_exec) {
+            // Allocation inside a capture is illegal: run the objective once eagerly so that every
+            // lazily sized buffer exists.  It only writes scratch (no optimiser state, no step counter).
+            if (subsampled) AVI_CHECK(o->model->subsample_dev(op->idx_dev, batch, o->d_state));
+            AVI_CHECK(avi_objective_local(o, op->lam));
+            const int64_t launches0 = ctx->launches;
+            AVI_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+            ctx->capturing = true;
+            int32_t rc = enqueue_iteration(op, subsampled, batch);
+            ctx->capturing = false;
+            cudaGraph_t g = nullptr;
+            cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+            op->graph_launches = ctx->launches - launches0;
+            ctx->launches = launches0;
+            if (rc != AVI_OK) { if (g) cudaGraphDestroy(g); return rc; }
+            if (e != cudaSuccess) AVI_FAIL(ctx, AVI_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+            op->graph = g;
+            AVI_CUDA(ctx, cudaGraphInstantiate(&op->graph_exec, op->graph, 0));
+            op->graph_gen = o->generation * 1000003 + o->model->generation;
+            op->graph_subsampled = subsampled; op->graph_batch = batch;
+        }
+        for (int32_t it = 0; it < n; ++it) AVI_CUDA(ctx, cudaGraphLaunch(op->graph_exec, ctx->stream));
+        ctx->launches += (int64_t)n * op->graph_launches;
+    } else {
+        for (int32_t it = 0; it < n; ++it) AVI_CHECK(enqueue_iteration(op, subsampled, batch));
+    }
+    ObjDeviceState hs{};
+    AVI_CUDA(ctx, cudaMemcpyAsync(op->h_trace, op->trace, 2 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    AVI_CUDA(ctx, cudaMemcpyAsync(&hs, o->d_state, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
+    AVI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const int recorded = std::min(hs.trace_pos, n);
+    const int done = hs.halted ? recorded - 1 : recorded;
+    for (int i = 0; i < recorded; ++i) {
+        if (value_host) value_host[i] = op->h_trace[2 * i];
+        if (elbo_host) elbo_host[i] = op->h_trace[2 * i + 1];
+    }
+    o->step = hs.step;
+    op->iteration += done;
+    if (n_done) *n_done = done;
+    return AVI_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t avi_opt_create(avi_obj* obj, int32_t rule, const float* hyper, int32_t n_hyper, int32_t op_kind,
+                       float op_param, int32_t averager, float avg_param, const float* lambda0_host, int64_t P,
+                       avi_opt** out) {
+    if (!obj || !out) return AVI_ERR_INVALID;
+    avi_ctx* ctx = obj->ctx;
+    *out = nullptr;
+    if (!lambda0_host || P != obj->P) AVI_FAIL(ctx, AVI_ERR_INVALID, "lambda0 must have num_params entries");
+    if (rule < AVI_RULE_DESCENT || rule > AVI_RULE_DOWG) AVI_FAIL(ctx, AVI_ERR_INVALID, "rule");
+    if (op_kind < AVI_OP_IDENTITY || op_kind > AVI_OP_PROXENTROPY) AVI_FAIL(ctx, AVI_ERR_INVALID, "operator");
+    if (averager != AVI_AVG_NONE && averager != AVI_AVG_POLYNOMIAL) AVI_FAIL(ctx, AVI_ERR_INVALID, "averager");
+    if (op_kind == AVI_OP_PROXENTROPY && rule == AVI_RULE_ADAM)
+        AVI_FAIL(ctx, AVI_ERR_UNSUPPORTED,
+                 "ProximalLocationScaleEntropy only supports Descent, DoG and DoWG "
+                 "(src/optimization/proximal_location_scale_entropy.jl:29-44)");
+    cudaSetDevice(ctx->device);
+    avi_opt* op = new avi_opt();
+    op->ctx = ctx; op->obj = obj; op->rule = rule; op->op = op_kind; op->averager = averager;
+    op->op_param = op_param; op->avg_param = avg_param; op->P = P;
+    // defaults: Descent(0.1); Adam(1e-3, (0.9, 0.999), 1e-8); DoG/DoWG(alpha = 1e-6)
+    const float dflt[4][4] = {{0.1f, 0, 0, 0}, {1e-3f, 0.9f, 0.999f, 1e-8f}, {1e-6f, 0, 0, 0}, {1e-6f, 0, 0, 0}};
+    for (int i = 0; i < 4; ++i) op->hyper[i] = (hyper && i < n_hyper) ? hyper[i] : dflt[rule][i];
+    int32_t rc = avi_alloc(ctx, &op->lam, (size_t)P);
+    if (rc == AVI_OK) rc = avi_alloc(ctx, &op->m1, (size_t)P);
+    if (rc == AVI_OK && rule == AVI_RULE_ADAM) rc = avi_alloc(ctx, &op->m2, (size_t)P);
+    if (rc == AVI_OK) rc = avi_alloc(ctx, &op->avg, (size_t)P);
+    if (rc == AVI_OK) rc = avi_alloc(ctx, &op->sc, SC_N);
+    if (rc == AVI_OK) rc = avi_alloc(ctx, &op->norm_part, 2 * NORM_BLOCKS_MAX);
+    if (rc != AVI_OK) { avi_opt_destroy(op); return rc; }
+    float sc[SC_N] = {0};
+    sc[SC_T] = 1.0f;   // PolynomialAveraging state starts at (x0, 1)  (averaging.jl:42)
+    sc[SC_B1T] = op->hyper[1]; sc[SC_B2T] = op->hyper[2];
+    if (rule == AVI_RULE_DOG || rule == AVI_RULE_DOWG) {
+        double nrm = 0.0;
+        for (int64_t p = 0; p < P; ++p) nrm += (double)lambda0_host[p] * lambda0_host[p];
+        sc[SC_R] = op->hyper[0] * (1.0f + (float)std::sqrt(nrm));   // rules.jl:21-23, :52-54
+        avi_copy(ctx, op->m1, lambda0_host, (size_t)P * sizeof(float), cudaMemcpyHostToDevice);   // x0
+    }
+    avi_copy(ctx, op->lam, lambda0_host, (size_t)P * sizeof(float), cudaMemcpyHostToDevice);
+    avi_copy(ctx, op->avg, lambda0_host, (size_t)P * sizeof(float), cudaMemcpyHostToDevice);
+    avi_copy(ctx, op->sc, sc, sizeof(sc), cudaMemcpyHostToDevice);
+    *out = op;
+    return AVI_OK;
+}
+
+int32_t avi_opt_destroy(avi_opt* op) {
+    if (!op) return AVI_OK;
+    cudaStreamSynchronize(op->ctx->stream);
+    drop_graph(op);
+    avi_free(op->lam); avi_free(op->m1); avi_free(op->m2); avi_free(op->avg); avi_free(op->sc);
+    avi_free(op->norm_part); avi_free(op->trace); avi_free(op->idx_dev);
+    if (op->h_trace) cudaFreeHost(op->h_trace);
+    delete op;
+    return AVI_OK;
+}
+
+int32_t avi_opt_steps(avi_opt* op, int32_t n, float* value_host, float* elbo_host, int32_t* n_done) {
+    if (!op) return AVI_ERR_INVALID;
+    return run_steps(op, n, nullptr, 0, value_host, elbo_host, n_done);
+}
+
+int32_t avi_opt_steps_subsampled(avi_opt* op, int32_t n, const int32_t* idx_host, int64_t batch, float* value_host,
+                                 float* elbo_host, int32_t* n_done) {
+    if (!op) return AVI_ERR_INVALID;
+    if (!idx_host || batch <= 0) AVI_FAIL(op->ctx, AVI_ERR_INVALID, "minibatch indices missing");
+    return run_steps(op, n, idx_host, batch, value_host, elbo_host, n_done);
+}
+
+int32_t avi_opt_get(avi_opt* op, float* lambda_host, float* lambda_avg_host, float* grad_host) {
+    if (!op) return AVI_ERR_INVALID;
+    avi_ctx* ctx = op->ctx;
+    const size_t nb = (size_t)op->P * sizeof(float);
+    if (lambda_host) AVI_CUDA(ctx, cudaMemcpyAsync(lambda_host, op->lam, nb, cudaMemcpyDeviceToHost, ctx->stream));
+    if (lambda_avg_host)   // NoAveraging: value(avg_st) is the current iterate (averaging.jl:9-13)
+        AVI_CUDA(ctx, cudaMemcpyAsync(lambda_avg_host, op->averager == AVI_AVG_POLYNOMIAL ? op->avg : op->lam, nb,
+                                      cudaMemcpyDeviceToHost, ctx->stream));
+    if (grad_host) AVI_CUDA(ctx, cudaMemcpyAsync(grad_host, op->obj->grad, nb, cudaMemcpyDeviceToHost, ctx->stream));
+    AVI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return AVI_OK;
+}
+
+int64_t avi_opt_iteration(const avi_opt* op) { return op ? op->iteration : -1; }
+
+// ---- warm start (src/optimize.jl:50, :58-62): [header | lam | m1 | m2 | avg | sc | out] ----------
+struct StateHeader {
+    uint64_t magic, P;
+    int32_t rule, op, averager, family;
+    int64_t iteration;
+    uint64_t key, step;
+};
+static const uint64_t STATE_MAGIC = 0x4156493130305354ull;   // "AVI100ST"
+
+int64_t avi_opt_state_nbytes(const avi_opt* op) {
+    if (!op) return -1;
+    return (int64_t)sizeof(StateHeader) + (int64_t)sizeof(float) * (4 * op->P + SC_N + 4);
+}
+
+int32_t avi_opt_state_export(avi_opt* op, void* buf_host, int64_t nbytes) {
+    if (!op || !buf_host) return AVI_ERR_INVALID;
+    avi_ctx* ctx = op->ctx;
+    if (nbytes < avi_opt_state_nbytes(op)) AVI_FAIL(ctx, AVI_ERR_INVALID, "buffer too small");
+    AVI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    StateHeader h{};
+    h.magic = STATE_MAGIC; h.P = (uint64_t)op->P; h.rule = op->rule; h.op = op->op; h.averager = op->averager;
+    h.family = op->obj->family; h.iteration = op->iteration; h.key = op->obj->key; h.step = op->obj->step;
+    char* p = static_cast<char*>(buf_host);
+    std::memcpy(p, &h, sizeof(h)); p += sizeof(h);
+    const size_t nb = (size_t)op->P * sizeof(float);
+    const float* parts[4] = {op->lam, op->m1, op->m2, op->avg};
+    for (int i = 0; i < 4; ++i) {
+        if (parts[i]) AVI_CUDA(ctx, avi_copy(ctx, p, parts[i], nb, cudaMemcpyDeviceToHost));
+        else std::memset(p, 0, nb);
+        p += nb;
+    }
+    AVI_CUDA(ctx, avi_copy(ctx, p, op->sc, SC_N * sizeof(float), cudaMemcpyDeviceToHost)); p += SC_N * sizeof(float);
+    AVI_CUDA(ctx, avi_copy(ctx, p, op->obj->out, 4 * sizeof(float), cudaMemcpyDeviceToHost));
+    return AVI_OK;
+}
+
+int32_t avi_opt_state_import(avi_opt* op, const void* buf_host, int64_t nbytes) {
+    if (!op || !buf_host) return AVI_ERR_INVALID;
+    avi_ctx* ctx = op->ctx;
+    if (nbytes < avi_opt_state_nbytes(op)) AVI_FAIL(ctx, AVI_ERR_INVALID, "buffer too small");
+    StateHeader h{};
+    const char* p = static_cast<const char*>(buf_host);
+    std::memcpy(&h, p, sizeof(h)); p += sizeof(h);
+    if (h.magic != STATE_MAGIC || h.P != (uint64_t)op->P || h.rule != op->rule || h.op != op->op ||
+        h.averager != op->averager || h.family != op->obj->family)
+        AVI_FAIL(ctx, AVI_ERR_STATE, "state does not belong to an optimiser of this configuration");
+    AVI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const size_t nb = (size_t)op->P * sizeof(float);
+    float* parts[4] = {op->lam, op->m1, op->m2, op->avg};
+    for (int i = 0; i < 4; ++i) {
+        if (parts[i]) AVI_CUDA(ctx, avi_copy(ctx, parts[i], p, nb, cudaMemcpyHostToDevice));
+        p += nb;
+    }
+    AVI_CUDA(ctx, avi_copy(ctx, op->sc, p, SC_N * sizeof(float), cudaMemcpyHostToDevice)); p += SC_N * sizeof(float);
+    AVI_CUDA(ctx, avi_copy(ctx, op->obj->out, p, 4 * sizeof(float), cudaMemcpyHostToDevice));
+    op->iteration = h.iteration;
+    return avi_obj_seed(op->obj, h.key, h.step);
+}
+
+}  // extern "C"

@@ -1,0 +1,7 @@
+"""Importable alias of the `advancedvi.jl_b200/` package directory (its name contains a dot)."""
+import os as _os
+
+_real = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "advancedvi.jl_b200")
+__path__ = [_real]
+with open(_os.path.join(_real, "__init__.py")) as _f:
+    exec(compile(_f.read(), _os.path.join(_real, "__init__.py"), "exec"))

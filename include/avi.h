@@ -1,0 +1,203 @@
+/* avi.h -- C ABI of the B200-native ELBO-gradient engine (libavi_b200.so).
+ *
+ * Drop-in boundary for ONE path of TuringLang/AdvancedVI.jl v0.7.0: the Monte-Carlo ELBO
+ * gradient estimator over the location-scale Gaussian family and the SGD step around it.
+ * Host code (Julia via @ccall, or the Python mirror in advancedvi.jl_b200/) binds exactly
+ * these symbols; no torch / CUDA types appear in any signature.  File:line citations are
+ * relative to the reference checkout (/root/reference).
+ *
+ * Conventions
+ *   - every function returns int32 status (AVI_OK == 0); avi_last_error(ctx) gives the
+ *     message of the last failure on that ctx (ctx == NULL: last failure of a create call);
+ *   - element type is float32 only (the Julia glue raises ArgumentError otherwise);
+ *   - matrices are column-major, Monte-Carlo samples are COLUMNS (src/utils.jl:6);
+ *   - flat parameter vector lambda: mean-field [mu(D); diag(scale)(D)]
+ *     (src/families/location_scale.jl:39-43), full-rank [mu(D); vec(L)(D*D)] with the
+ *     zero strict upper triangle present (Optimisers.destructure through Functors);
+ *   - `*_host` pointers are host memory borrowed for the call, `*_dev` are device memory;
+ *   - a ctx and its handles are used by one host thread at a time; one CUDA stream per ctx;
+ *   - a non-finite objective value is NOT an error here: the caller's `step` raises
+ *     (src/algorithms/common.jl:83-89);
+ *   - there is no CPU fallback: without a CUDA device avi_ctx_create fails.
+ */
+#ifndef AVI_H
+#define AVI_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct avi_ctx avi_ctx;     /* device + stream + (optional) communicator          */
+typedef struct avi_model avi_model; /* target log-density: LogDensityProblems plugin side */
+typedef struct avi_obj avi_obj;     /* variational objective + family (L3 + L2 of SURVEY) */
+typedef struct avi_opt avi_opt;     /* fused SGD step: rule + operator + averager         */
+
+enum { AVI_OK = 0, AVI_ERR_INVALID = 1, AVI_ERR_CUDA = 2, AVI_ERR_UNSUPPORTED = 3,
+       AVI_ERR_COMM = 4, AVI_ERR_STATE = 5, AVI_ERR_CALLBACK = 6 };
+
+/* MeanFieldGaussian / FullRankGaussian (src/families/location_scale.jl:124-141) */
+enum { AVI_MEANFIELD = 0, AVI_FULLRANK = 1 };
+/* RepGradELBO (src/algorithms/repgradelbo.jl:21-24) / ScoreGradELBO (scoregradelbo.jl:15-17) */
+enum { AVI_REPGRAD = 0, AVI_SCOREGRAD = 1 };
+/* entropy estimators, src/algorithms/entropy.jl:11-15, 25-29, 40-46, 57-65, 78-90 */
+enum { AVI_ENT_CLOSEDFORM = 0, AVI_ENT_MONTECARLO = 1, AVI_ENT_STL = 2,
+       AVI_ENT_CLOSEDFORM_ZEROGRAD = 3, AVI_ENT_STL_ZEROGRAD = 4 };
+/* Optimisers.Descent / Adam, src/optimization/rules.jl:48-64 (DoG), :17-34 (DoWG) */
+enum { AVI_RULE_DESCENT = 0, AVI_RULE_ADAM = 1, AVI_RULE_DOG = 2, AVI_RULE_DOWG = 3 };
+/* IdentityOperator (src/AdvancedVI.jl:199), ClipScale (clip_scale.jl:8-29),
+ * ProximalLocationScaleEntropy (proximal_location_scale_entropy.jl:20-61) */
+enum { AVI_OP_IDENTITY = 0, AVI_OP_CLIPSCALE = 1, AVI_OP_PROXENTROPY = 2 };
+/* NoAveraging / PolynomialAveraging (src/optimization/averaging.jl:7-53) */
+enum { AVI_AVG_NONE = 0, AVI_AVG_POLYNOMIAL = 1 };
+/* GLM targets: likelihood and which docs model the prior follows
+ * (docs/src/tutorials/subsampling.md:26-38 | README.md:47-58 + :91-106) */
+enum { AVI_GLM_BERNOULLI_LOGIT = 0, AVI_GLM_GAUSSIAN = 1 };
+enum { AVI_GLM_SUBSAMPLING = 0, AVI_GLM_BASIC = 1 };
+/* arithmetic of the X*beta / X'*r contractions */
+enum { AVI_GEMM_SIMT_FP32 = 0, AVI_GEMM_TF32 = 1, AVI_GEMM_TF32X3 = 2 };
+/* which axis a multi-rank run partitions */
+enum { AVI_SHARD_NONE = 0, AVI_SHARD_SAMPLES = 1, AVI_SHARD_ROWS = 2 };
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+int32_t avi_version(void);
+const char* avi_last_error(const avi_ctx* ctx);
+int32_t avi_ctx_create(int32_t device, avi_ctx** out);
+int32_t avi_ctx_destroy(avi_ctx* ctx);
+int32_t avi_ctx_synchronize(avi_ctx* ctx);
+/* device info for callers that size work (SM count, bytes of HBM) */
+int32_t avi_ctx_info(avi_ctx* ctx, int32_t* sm_count, int64_t* hbm_bytes, int32_t* cc_major, int32_t* cc_minor);
+/* number of kernels launched on this ctx since creation (bench.py "gpu_launches") */
+int64_t avi_ctx_launch_count(const avi_ctx* ctx);
+
+/* Device timing of the named hot kernels ("sample", "glm_fwd", "glm_bwd", "gemm_store") with CUDA events
+ * on the ctx stream, for roofline reporting.  While enabled, avi_opt_steps launches eagerly (no graph). */
+int32_t avi_ctx_timing(avi_ctx* ctx, int32_t enable);
+int32_t avi_ctx_timing_get(avi_ctx* ctx, const char* name, double* total_ms, int64_t* count);
+
+/* Multi-rank plumbing.  The exchange step of the path is ONE sum-all-reduce of the partial
+ * accumulator [grad sums ; scalars] per step.  The library does not own a communicator:
+ * the host supplies the exchange as a callback that runs between the local phase and the
+ * replicated finalize (NCCL through torch.distributed in the Python mirror, NCCL.jl /
+ * MPI.jl from Julia).  buf_dev is device memory of `count` floats, reduced in place on the
+ * ctx stream whose handle is `stream` (a cudaStream_t). */
+typedef int32_t (*avi_allreduce_fn)(void* user, float* buf_dev, int64_t count, void* stream);
+int32_t avi_ctx_set_allreduce(avi_ctx* ctx, avi_allreduce_fn fn, void* user, int32_t rank, int32_t nranks);
+/* Native exchange over NVLink peer memory (one-shot all-reduce kernel of ours, graph-capturable; takes
+ * precedence over the callback).  Each rank: avi_comm_buffer (allocates its symmetric buffer for payloads
+ * of up to max_floats floats, writes its 64-byte CUDA IPC handle), the host all-gathers the handles,
+ * then avi_comm_connect with the nranks x 64-byte table. */
+int32_t avi_comm_buffer(avi_ctx* ctx, int64_t max_floats, char* handle_out_64);
+int32_t avi_comm_connect(avi_ctx* ctx, int32_t rank, int32_t nranks, const char* handles);
+/* the cudaStream_t every call on this ctx enqueues on (for hosts that order their own work after it) */
+void* avi_ctx_stream(avi_ctx* ctx);
+
+/* ---- targets (replace the user's per-sample logdensity called at
+ *      src/algorithms/repgradelbo.jl:84-86 and the MixedADLogDensityProblem pullback,
+ *      src/mixedad_logdensity.jl:23-34) ---------------------------------------------------- */
+/* logpdf(MvNormal(mu, Diagonal(sigma.^2)), z): test/models/normal.jl:8-11, :56-75 */
+int32_t avi_model_mvnormal_diag_create(avi_ctx* ctx, const float* mu_host, const float* sigma_host,
+                                       int32_t D, avi_model** out);
+/* Hierarchical GLM, theta = [beta(d); log sigma].  X_host is n x d column-major and y_host has
+ * n entries (0/1 for Bernoulli-logit); both are copied to the device once.  n_data is the
+ * full-data size used for the likelihood adjustment n_data / n_batch. */
+int32_t avi_model_glm_create(avi_ctx* ctx, const float* X_host, const float* y_host, int64_t n,
+                             int32_t d, int64_t n_data, int32_t likelihood, int32_t variant,
+                             int32_t gemm_mode, avi_model** out);
+/* Any other LogDensityProblem: cb is called once per sample with z (D floats, host) and must
+ * write *logp and, when grad != NULL, grad (D floats).  Non-zero return aborts the call. */
+typedef int32_t (*avi_logdensity_fn)(void* user, const float* z, int32_t D, float* logp, float* grad);
+int32_t avi_model_hostcallback_create(avi_ctx* ctx, int32_t D, int32_t capability,
+                                      avi_logdensity_fn cb, void* user, avi_model** out);
+/* AdvancedVI.subsample(prob, batch) (src/AdvancedVI.jl:303-313;
+ * docs/src/tutorials/subsampling.md:99-102): restrict a GLM target to the rows idx_host[0..batch)
+ * (0-based) with likelihood adjustment n_data / batch.  idx_host == NULL restores all rows. */
+int32_t avi_model_subsample(avi_model* model, const int32_t* idx_host, int64_t batch);
+/* Multi-rank data sharding (n-axis): this target instance was created from one of
+ * `nshards` disjoint row slices holding rows_global rows in total.  The likelihood adjustment
+ * becomes n_data / rows_global (n_data / (batch * nshards) after avi_model_subsample) and the
+ * prior terms are included only when include_prior != 0 (exactly one rank), so that the sum of
+ * the per-rank log-densities and gradients is the full-data one. */
+int32_t avi_model_set_data_shard(avi_model* model, int32_t nshards, int64_t rows_global, int32_t include_prior);
+int32_t avi_model_dimension(const avi_model* model);      /* LogDensityProblems.dimension    */
+int32_t avi_model_capability(const avi_model* model);     /* LogDensityProblems.capabilities */
+int32_t avi_model_set_gemm_mode(avi_model* model, int32_t gemm_mode);
+/* Batched LogDensityProblems.logdensity / logdensity_and_gradient on device data:
+ * Z_dev is D x M column-major with leading dimension ldz; logp_dev has M entries; G_dev is
+ * D x M with leading dimension ldz. */
+int32_t avi_model_logdensity(avi_model* model, const float* Z_dev, int32_t ldz, int32_t M, float* logp_dev);
+int32_t avi_model_logdensity_and_gradient(avi_model* model, const float* Z_dev, int32_t ldz, int32_t M,
+                                          float* logp_dev, float* G_dev);
+/* Same with host buffers (D x M column-major, ld = D); copies in and out. */
+int32_t avi_model_logdensity_and_gradient_host(avi_model* model, const float* Z_host, int32_t M,
+                                               float* logp_host, float* G_host /* may be NULL */);
+int32_t avi_model_destroy(avi_model* model);
+
+/* ---- objective: init / estimate_gradient! / estimate_objective
+ *      (src/algorithms/abstractobjective.jl:25-86) ----------------------------------------- */
+int32_t avi_obj_create(avi_ctx* ctx, avi_model* model, int32_t family, int32_t objective,
+                       int32_t entropy, int32_t M, avi_obj** out);
+/* set_objective_state_problem (repgradelbo.jl:31-39, scoregradelbo.jl:24-32) */
+int32_t avi_obj_set_model(avi_obj* obj, avi_model* model);
+/* eps[i, m] at step t is a pure function of (key, t, m, i) (Philox4x32-10 + Box-Muller);
+ * the host draws `key` from its rng once, so "same seed => identical run"
+ * (test/algorithms/klminrepgraddescent.jl:40-57) holds. */
+int32_t avi_obj_seed(avi_obj* obj, uint64_t key, uint64_t step);
+int32_t avi_obj_get_step(const avi_obj* obj, uint64_t* step);
+/* partition the Monte-Carlo samples: this rank evaluates samples [m0, m0 + M_local) of M */
+int32_t avi_obj_set_sample_shard(avi_obj* obj, int32_t m0, int32_t M_local);
+/* which axis the ranks of this ctx partition: AVI_SHARD_SAMPLES (set by avi_obj_set_sample_shard)
+ * exchanges the partial gradient sums; AVI_SHARD_ROWS (targets sharded with
+ * avi_model_set_data_shard, every rank holds all M samples) exchanges log pi and its gradient sums */
+int32_t avi_obj_set_shard_axis(avi_obj* obj, int32_t axis);
+int64_t avi_obj_num_params(const avi_obj* obj);
+/* estimate_gradient! (repgradelbo.jl:151-177 / scoregradelbo.jl:96-117): lambda in, gradient
+ * of the value slot out; *value = -ELBO (RepGrad) or VarGrad (ScoreGrad), *elbo = info.elbo.
+ * Uses the eps of the current step and then advances the step counter.  Blocking. */
+int32_t avi_obj_estimate_gradient(avi_obj* obj, const float* lambda_host, int64_t P,
+                                  float* grad_host, float* value, float* elbo);
+/* estimate_objective (repgradelbo.jl:112-118 / scoregradelbo.jl:58-65 / common.jl:29-38):
+ * forward only with n_samples draws and the given entropy estimator; returns -ELBO.
+ * objective == AVI_SCOREGRAD ignores `entropy`. */
+int32_t avi_obj_estimate_objective(avi_obj* obj, const float* lambda_host, int64_t P, int32_t n_samples,
+                                   int32_t objective, int32_t entropy, uint64_t key, float* neg_elbo);
+/* rand(rng, q, M) (src/families/location_scale.jl:71-87): Z_host and eps_host (either may be
+ * NULL) receive D x M column-major draws of the current step WITHOUT advancing it. */
+int32_t avi_obj_rand(avi_obj* obj, const float* lambda_host, int64_t P, float* Z_host, float* eps_host);
+int32_t avi_obj_destroy(avi_obj* obj);
+
+/* ---- minibatch order: ReshufflingBatchSubsampling (src/reshuffling.jl:27-32) --------------------
+ * In-place Fisher-Yates shuffle of perm_inout[0..n) driven by Philox4x32-10 (key, shuffle_index);
+ * the k-th reshuffle of a run uses shuffle_index = k, so a run is a pure function of its key. */
+int32_t avi_shuffle(uint64_t key, uint64_t shuffle_index, int64_t n, int32_t* perm_inout);
+
+/* ---- fused step: Optimisers.update! + operator + averager
+ *      (src/algorithms/common.jl:91-94) with parameters resident on the device ------------- */
+/* hyper: Descent {eta}; Adam {eta, beta1, beta2, epsilon}; DoG/DoWG {alpha}.
+ * op_param: ClipScale epsilon.  avg_param: PolynomialAveraging eta. */
+int32_t avi_opt_create(avi_obj* obj, int32_t rule, const float* hyper, int32_t n_hyper, int32_t op,
+                       float op_param, int32_t averager, float avg_param, const float* lambda0_host,
+                       int64_t P, avi_opt** out);
+/* n iterations of `step` (common.jl:69-104) without the callback; per-iteration value slot and
+ * elbo go to the host arrays (n entries each, either may be NULL).  Stops early and returns
+ * AVI_OK with *n_done < n when the value slot is not finite (the caller raises).  One stream
+ * synchronisation at the end. */
+int32_t avi_opt_steps(avi_opt* opt, int32_t n, float* value_host, float* elbo_host, int32_t* n_done);
+/* same, with the minibatch of every iteration given up front: idx_host holds n * batch row
+ * indices (SubsampledObjective, src/algorithms/subsampledobjective.jl:64-90) */
+int32_t avi_opt_steps_subsampled(avi_opt* opt, int32_t n, const int32_t* idx_host, int64_t batch,
+                                 float* value_host, float* elbo_host, int32_t* n_done);
+/* current iterate, averaged iterate (output(), common.jl:63-67) and last gradient */
+int32_t avi_opt_get(avi_opt* opt, float* lambda_host, float* lambda_avg_host, float* grad_host);
+int64_t avi_opt_iteration(const avi_opt* opt);
+/* warm start (src/optimize.jl:50, :58-62): serialise / restore the complete device state */
+int64_t avi_opt_state_nbytes(const avi_opt* opt);
+int32_t avi_opt_state_export(avi_opt* opt, void* buf_host, int64_t nbytes);
+int32_t avi_opt_state_import(avi_opt* opt, const void* buf_host, int64_t nbytes);
+int32_t avi_opt_destroy(avi_opt* opt);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVI_H */
