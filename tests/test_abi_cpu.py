@@ -1,0 +1,99 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol include/avi.h
+declares, fails loudly without a GPU, and its host-side integer path (the minibatch permutation) is
+bit-exact against the oracle.  No compute calls."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import reshuffling as R
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "avi.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    names = set(re.findall(r"\b(avi_[a-z0-9_]+)\s*\(", txt))
+    return sorted(n for n in names if not n.endswith("_fn"))
+
+
+def test_library_exports_every_declared_symbol(avi):
+    lib = C.CDLL(avi._lib.LIB_PATH)
+    syms = declared_symbols()
+    assert len(syms) >= 45
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, missing
+    # ... and the ctypes mirror binds every one of them with a signature
+    unbound = [s for s in syms if s not in avi._lib.SIGNATURES]
+    assert not unbound, unbound
+    assert avi._lib.lib.avi_version() == 100
+
+
+def test_no_cpu_fallback(avi):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(avi.AviError, match="no CUDA device"):
+        avi.Context(0)
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 5, 8, 100, 1001])
+@pytest.mark.parametrize("key,k", [(1, 0), (0x38BEF07CF9CC549D, 3), (2 ** 64 - 1, 2 ** 32 - 1)])
+def test_shuffle_is_bit_exact_against_oracle(avi, n, key, k):
+    """avi_shuffle == Random.shuffle replacement of src/reshuffling.jl:29 (oracle/reshuffling.py)."""
+    perm = np.arange(n, dtype=np.int32)
+    assert avi._lib.lib.avi_shuffle(key, k, n, avi._lib.iptr(perm)) == 0
+    assert np.array_equal(perm, R.philox_shuffle(np.arange(n), key, k))
+
+
+@pytest.mark.parametrize("n,bs", [(8, 3), (8, 4), (10, 1), (7, 7), (50, 8)])
+def test_reshuffling_state_machine_matches_oracle(avi, n, bs):
+    """Host mirror of ReshufflingBatchSubsampling (src/reshuffling.jl:38-60) vs the oracle, incl. the
+    drop-trailing swap and the (epoch, step) info."""
+    from advancedvi_jl_b200.api import _sub_init, _sub_step
+    sub, subo = avi.ReshufflingBatchSubsampling(np.arange(n), bs), R.ReshufflingBatchSubsampling(np.arange(n), bs)
+    assert len(sub) == len(subo)
+    for drop in (False, True):
+        st, sto = _sub_init(sub, 9), R.sub_init(subo, 9)
+        for _ in range(3 * len(sub) + 2):
+            b, st, info = _sub_step(sub, st, drop)
+            bo, sto, infoo = R.sub_step(subo, sto, drop)
+            assert np.array_equal(b, bo) and info == infoo
+
+
+def test_family_container_and_eltype(avi):
+    """Diagonal destructure has length 2d and round-trips (test/families/location_scale.jl:146-155);
+    Float64 is rejected (the reference supports both, the B200 path is Float32 only)."""
+    d = 5
+    q = avi.MeanFieldGaussian(np.arange(d, dtype=np.float32), np.arange(1, d + 1, dtype=np.float32))
+    lam = q.destructure()
+    assert lam.shape == (2 * d,) and lam.dtype == np.float32
+    q2 = q.restructure(lam)
+    assert np.array_equal(q2.location, q.location) and np.array_equal(q2.scale, q.scale)
+    Lm = np.tril(np.ones((d, d), np.float32))
+    qf = avi.FullRankGaussian(np.zeros(d, np.float32), Lm)
+    assert qf.destructure().shape == (d + d * d,)
+    assert np.array_equal(qf.restructure(qf.destructure()).scale, Lm)
+    with pytest.raises(TypeError, match="Float32"):
+        avi.MeanFieldGaussian(np.zeros(d), np.ones(d))
+    with pytest.raises(ValueError):
+        avi.FullRankGaussian(np.zeros(d, np.float32), np.ones((d, d), np.float32))
+
+
+def test_algorithm_constructors(avi):
+    """constructors.jl:58-77, :136-157, :213-231: defaults and the entropy whitelist."""
+    a = avi.KLMinRepGradDescent()
+    assert isinstance(a.optimizer, avi.DoWG) and isinstance(a.averager, avi.PolynomialAveraging)
+    assert isinstance(a.operator, avi.IdentityOperator) and a.objective.n_samples == 1
+    assert isinstance(a.objective.entropy, avi.ClosedFormEntropy)
+    with pytest.raises(ValueError):
+        avi.KLMinRepGradDescent(entropy=avi.ClosedFormEntropyZeroGradient())
+    p = avi.KLMinRepGradProxDescent()
+    assert isinstance(p.operator, avi.ProximalLocationScaleEntropy)
+    assert isinstance(p.objective.entropy, avi.ClosedFormEntropyZeroGradient)
+    s = avi.KLMinScoreGradDescent(n_samples=7, subsampling=avi.ReshufflingBatchSubsampling(np.arange(10), 2))
+    assert isinstance(s.objective, avi.SubsampledObjective) and s.objective.n_samples == 7
+    assert avi.ADVI is avi.KLMinRepGradDescent and avi.BBVI is avi.KLMinScoreGradDescent
