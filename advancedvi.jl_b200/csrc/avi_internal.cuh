@@ -110,6 +110,16 @@ struct ObjDeviceState {
     int trace_pos;             // next slot of the per-call (value, elbo) trace
 };
 
+// A target may ask the mean-field sampling kernel to produce its per-sample preprocessing in the same
+// pass over z (kind 1: hierarchical GLM -> TF32-rounded copy of beta for the tensor-core contraction and
+// the prior terms of glm_prior.cuh), saving one launch per step.
+struct SampleHook {
+    int kind = 0;
+    int d = 0, variant = 0, include_prior = 1;
+    float* Zt = nullptr;
+    float4* pre = nullptr;
+};
+
 // Layout shared by every sample-major buffer: row m (one Monte-Carlo sample) holds `ld` floats,
 // coordinate i at [m * ld + i]  ==  a D x M column-major matrix with leading dimension ld.
 struct avi_model {
@@ -131,6 +141,8 @@ struct avi_model {
         return AVI_OK;   // AdvancedVI.subsample default: identity (src/AdvancedVI.jl:313)
     }
     virtual int32_t set_gemm_mode(int mode) { return AVI_OK; }
+    // fills *h and returns true when the next eval / eval_gradsums on these samples may skip its own pass
+    virtual bool sample_hook(int ld, int M, SampleHook* h) { return false; }
     // Device-side minibatch selection for the fused multi-step loop: the rows of iteration k are
     // idx_dev[k * batch .. (k+1) * batch) with k = st->batch_cursor read ON THE DEVICE.
     virtual int32_t subsample_dev(const int32_t* idx_dev, int64_t batch, const ObjDeviceState* st) {
@@ -217,14 +229,15 @@ int32_t avi_obj_ensure_capacity(avi_obj* o, int M);
 // rand(rng, q, M): Z = mu + scale * eps for samples [m0, m0 + Mloc) of the step/key held in *st
 // (or in *ov when ov != nullptr, a host value).  E, esq always written.
 int32_t avi_family_sample(avi_obj* o, const float* lambda, float* Z, float* E, float* esq, int Mloc,
-                          int m0, const ObjDeviceState* st, const ObjDeviceState* ov);
+                          int m0, const ObjDeviceState* st, const ObjDeviceState* ov, const SampleHook* hook = nullptr);
 int32_t avi_objective_local(avi_obj* o, const float* lambda);          // sample + model + reduce -> acc
 int32_t avi_objective_finalize(avi_obj* o, const float* lambda, float* grad, float* out);  // acc -> grad
 // forward-only chunk for estimate_objective: sums_dev = {sum logp, sum |eps|^2, logdet}
 int32_t avi_objective_forward_chunk(avi_obj* o, const float* lambda, int m0, int Mc, const ObjDeviceState* ov,
                                     float* sums_dev);
 int32_t avi_exchange(avi_ctx* ctx, float* buf, int64_t count);          // all-reduce (no-op single rank)
-int32_t avi_obj_advance(avi_obj* o);                                    // step += 1 on the device
+int32_t avi_obj_advance(avi_obj* o);
+bool avi_obj_defers_scalars(const avi_obj* o);                                    // step += 1 on the device
 
 // generic SIMT fp32 GEMM:  C[a*sc_r + b*sc_c] = alpha * sum_k A[a*sa_r + k*sa_k] * B[b*sb_r + k*sb_k],
 // a < Ma, b < Nb, k < K; bounds-checked.

@@ -12,6 +12,9 @@
 // the restated forward in tests/test_oracle_gradients.py).
 #include "avi_internal.cuh"
 #include "device_utils.cuh"
+#include "glm_prior.cuh"
+#include "mf_finalize.cuh"
+#include "tc_common.cuh"
 
 namespace {
 
@@ -19,22 +22,23 @@ namespace {
 // K1: one CTA per Monte-Carlo sample; thread t owns coordinates 4q..4q+3 (one Philox block).
 // Writes Z = mu + s .* eps (mean-field), E = eps (both zero in the padding columns i >= D) and
 // |eps_m|^2.  FULLRANK writes only E (Z = L * eps + mu comes from k_fr_affine).
-template <bool FULLRANK>
+template <bool FULLRANK, bool HOOK>
 __global__ void __launch_bounds__(256)
 k_sample(const float* __restrict__ lambda, int D, int ld, int m0, const ObjDeviceState* __restrict__ st,
          ObjDeviceState st_val, int use_val, uint32_t stream_id, float* __restrict__ Z,
-         float* __restrict__ E, float* __restrict__ esq) {
+         float* __restrict__ E, float* __restrict__ esq, SampleHook hk) {
     __shared__ float sm[33];
+    __shared__ float s_eta;
     const unsigned long long step = use_val ? st_val.step : st->step;
     const unsigned long long key = use_val ? st_val.key : st->key;
     const int m = blockIdx.x;
     const float* mu = lambda;
     const float* sc = lambda + D;
-    float part = 0.0f;
+    float part = 0.0f, bsq = 0.0f;
     for (int q = threadIdx.x; q < ld / 4; q += blockDim.x) {
         float4 e = normal4((uint32_t)q, (uint32_t)(m0 + m), step, stream_id, key);
         const int i = 4 * q;
-        float ev[4] = {e.x, e.y, e.z, e.w}, zv[4];
+        float ev[4] = {e.x, e.y, e.z, e.w}, zv[4], zt[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             if (i + c < D) {
@@ -43,13 +47,25 @@ k_sample(const float* __restrict__ lambda, int D, int ld, int m0, const ObjDevic
             } else {
                 ev[c] = 0.0f; zv[c] = 0.0f;
             }
+            if (HOOK) {
+                const bool is_beta = i + c < hk.d;
+                bsq = is_beta ? fmaf(zv[c], zv[c], bsq) : bsq;
+                zt[c] = is_beta ? tc::round_tf32(zv[c]) : 0.0f;
+                if (i + c == hk.d) s_eta = zv[c];
+            }
         }
         *reinterpret_cast<float4*>(E + (size_t)m * ld + i) = make_float4(ev[0], ev[1], ev[2], ev[3]);
         if (!FULLRANK)
             *reinterpret_cast<float4*>(Z + (size_t)m * ld + i) = make_float4(zv[0], zv[1], zv[2], zv[3]);
+        if (HOOK && hk.Zt)
+            *reinterpret_cast<float4*>(hk.Zt + (size_t)m * ld + i) = make_float4(zt[0], zt[1], zt[2], zt[3]);
     }
     float tot = block_sum(part, sm);
-    if (threadIdx.x == 0) esq[m] = tot;
+    if (HOOK) bsq = block_sum(bsq, sm);   // the barriers inside also publish s_eta
+    if (threadIdx.x == 0) {
+        esq[m] = tot;
+        if (HOOK) hk.pre[m] = glm_prior_terms(bsq, s_eta, hk.d, hk.variant, hk.include_prior);
+    }
 }
 
 // full-rank affine map: Z[m][i] = mu[i] + sum_{j <= i} L[i + D*j] * E[m][j].
@@ -172,48 +188,20 @@ k_reduce_mf(const float* __restrict__ G, const float* __restrict__ E, const floa
 // order (CTA 0 writes them), so the grid size does not change any result.
 __global__ void __launch_bounds__(256)
 k_finalize_mf(const float* __restrict__ acc, int accv, const float* __restrict__ lambda, int D, int M,
-              int objective, int entropy, float* __restrict__ grad, float* __restrict__ out) {
+              int objective, int entropy, const float* __restrict__ logp, const float* __restrict__ esq, int Mloc,
+              int deferred, float* __restrict__ grad, float* __restrict__ out) {
     __shared__ float sm[33];
     const float* s = lambda + D;
-    float part = 0.f;
-    for (int i = threadIdx.x; i < D; i += blockDim.x) part += logf(__ldg(s + i));
-    const float logdet = block_sum(part, sm);
-    const float* scal = acc + 4 * (size_t)accv;
-    const float invM = 1.0f / (float)M;
-    const float *v0 = acc, *v1 = acc + accv, *v2 = acc + 2 * (size_t)accv, *v3 = acc + 3 * (size_t)accv;
-    const int gstride = gridDim.x * blockDim.x;
-    if (objective == AVI_REPGRAD) {
-        const bool stl = entropy == AVI_ENT_STL || entropy == AVI_ENT_STL_ZEROGRAD;
-        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < D; i += gstride) {
-            float si = __ldg(s + i), inv = 1.0f / si;
-            float sg = v0[i], sge = v1[i];
-            if (stl) { sg = fmaf(v2[i], inv, sg); sge = fmaf(v3[i], inv, sge); }   // w = g + eps / s
-            float gm = -sg * invM, gs = -sge * invM;
-            if (entropy == AVI_ENT_CLOSEDFORM || entropy == AVI_ENT_MONTECARLO) gs -= inv;
-            else if (entropy == AVI_ENT_STL_ZEROGRAD) gs += inv;
-            grad[i] = gm; grad[D + i] = gs;
-        }
-        if (blockIdx.x == 0 && threadIdx.x == 0) {
-            float ent = (entropy == AVI_ENT_CLOSEDFORM || entropy == AVI_ENT_CLOSEDFORM_ZEROGRAD)
-                            ? (float)D * AVI_H0 + logdet
-                            : 0.5f * scal[1] * invM + 0.5f * (float)D * AVI_LOG2PI + logdet;
-            float value = -(scal[0] * invM + ent);
-            out[0] = value; out[1] = -value; out[2] = logdet;
-        }
-    } else {
-        const float fbar = scal[2] * invM;
-        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < D; i += gstride) {
-            float inv = 1.0f / __ldg(s + i);
-            grad[i] = (v0[i] - fbar * v2[i]) * invM * inv;
-            grad[D + i] = (v1[i] - fbar * v3[i]) * invM * inv;
-        }
-        if (blockIdx.x == 0 && threadIdx.x == 0) {
-            float shift = out[3];
-            out[0] = 0.5f * (scal[3] * invM - fbar * fbar);   // VarGrad value (shift-invariant)
-            out[1] = -(fbar + shift);                         // elbo = mean(log pi - log q)
-            out[2] = logdet;
-            out[3] = fbar + shift;                            // centre f for the next call
-        }
+    const MfSums S = mf_collect_sums(lambda, D, acc + 4 * (size_t)accv, logp, esq, Mloc, deferred, sm);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < D; i += gridDim.x * blockDim.x) {
+        float gm, gs;
+        mf_grad_entry(acc, accv, __ldg(s + i), i, M, objective, entropy, S, gm, gs);
+        grad[i] = gm; grad[D + i] = gs;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        float value, elbo, shift_next;
+        mf_outputs(D, M, objective, entropy, S, out[3], value, elbo, shift_next);
+        out[0] = value; out[1] = elbo; out[2] = S.logdet; out[3] = shift_next;
     }
 }
 
@@ -329,7 +317,7 @@ k_forward_sums(const float* __restrict__ lambda, int D, int fullrank, const floa
 
 // ==============================================================================================
 int32_t avi_family_sample(avi_obj* o, const float* lambda, float* Z, float* E, float* esq, int Mloc, int m0,
-                          const ObjDeviceState* st, const ObjDeviceState* ov) {
+                          const ObjDeviceState* st, const ObjDeviceState* ov, const SampleHook* hook) {
     avi_ctx* ctx = o->ctx;
     if (Mloc <= 0) return AVI_OK;
     ObjDeviceState sv{};
@@ -337,16 +325,26 @@ int32_t avi_family_sample(avi_obj* o, const float* lambda, float* Z, float* E, f
     if (ov) { sv = *ov; use_val = 1; }
     AviTimed timed(ctx, "sample");
     if (o->family == AVI_MEANFIELD) {
-        k_sample<false><<<Mloc, 256, 0, ctx->stream>>>(lambda, o->D, o->ld, m0, st, sv, use_val, AVI_STREAM_EPS, Z, E, esq);
+        if (hook && hook->kind == 1)
+            k_sample<false, true><<<Mloc, 256, 0, ctx->stream>>>(lambda, o->D, o->ld, m0, st, sv, use_val, AVI_STREAM_EPS, Z, E, esq, *hook);
+        else
+            k_sample<false, false><<<Mloc, 256, 0, ctx->stream>>>(lambda, o->D, o->ld, m0, st, sv, use_val, AVI_STREAM_EPS, Z, E, esq, SampleHook{});
         AVI_LAUNCHED(ctx);
     } else {
-        k_sample<true><<<Mloc, 256, 0, ctx->stream>>>(lambda, o->D, o->ld, m0, st, sv, use_val, AVI_STREAM_EPS, Z, E, esq);
+        k_sample<true, false><<<Mloc, 256, 0, ctx->stream>>>(lambda, o->D, o->ld, m0, st, sv, use_val, AVI_STREAM_EPS, Z, E, esq, SampleHook{});
         AVI_LAUNCHED(ctx);
         dim3 grid((unsigned)ceil_div(o->ld, FA_TI), (unsigned)ceil_div(Mloc, FA_TM));
         k_fr_affine<<<grid, 256, 0, ctx->stream>>>(lambda, o->D, o->ld, Mloc, E, Z);
         AVI_LAUNCHED(ctx);
     }
     return AVI_OK;
+}
+
+// Mean-field RepGrad without a sample-sharded exchange: sum logp / sum |eps|^2 feed only the value slot,
+// so the finalize kernel takes them from the per-sample vectors itself (one launch less per step).
+bool avi_obj_defers_scalars(const avi_obj* o) {
+    return o->family == AVI_MEANFIELD && o->objective == AVI_REPGRAD && o->Mloc > 0 &&
+           !(o->shard_axis == AVI_SHARD_SAMPLES && o->ctx->nranks > 1);
 }
 
 int32_t avi_obj_advance(avi_obj* o) {
@@ -366,7 +364,9 @@ int32_t avi_objective_local(avi_obj* o, const float* lambda) {
         if (o->shard_axis == AVI_SHARD_SAMPLES && ctx->nranks > 1) AVI_CHECK(avi_exchange(ctx, o->acc, o->acc_len));
         return AVI_OK;
     }
-    AVI_CHECK(avi_family_sample(o, lambda, o->Z, o->E, o->esq, Mloc, o->m0, o->d_state, nullptr));
+    SampleHook hook;
+    const bool hooked = o->family == AVI_MEANFIELD && o->model->sample_hook(ld, Mloc, &hook);
+    AVI_CHECK(avi_family_sample(o, lambda, o->Z, o->E, o->esq, Mloc, o->m0, o->d_state, nullptr, hooked ? &hook : nullptr));
     const bool rep = o->objective == AVI_REPGRAD;
     const bool stl = o->entropy == AVI_ENT_STL || o->entropy == AVI_ENT_STL_ZEROGRAD;
     const bool rows = o->shard_axis == AVI_SHARD_ROWS && ctx->nranks > 1;
@@ -386,9 +386,11 @@ int32_t avi_objective_local(avi_obj* o, const float* lambda) {
     // row sharding: every rank holds all samples and a slice of the data rows; log pi and its
     // gradient are sums over rows, everything after this point is replicated arithmetic
     if (rows) AVI_CHECK(avi_exchange(ctx, o->logp, Mloc));
-    k_scalars<<<1, 1024, 0, ctx->stream>>>(lambda, D, o->family == AVI_FULLRANK, o->objective, o->logp, o->esq,
-                                           Mloc, o->out, o->fbuf, scal);
-    AVI_LAUNCHED(ctx);
+    if (!avi_obj_defers_scalars(o)) {
+        k_scalars<<<1, 1024, 0, ctx->stream>>>(lambda, D, o->family == AVI_FULLRANK, o->objective, o->logp, o->esq,
+                                               Mloc, o->out, o->fbuf, scal);
+        AVI_LAUNCHED(ctx);
+    }
     if (o->family == AVI_MEANFIELD) {
         // with a fused target and a closed-form entropy nothing else is needed (v2, v3 unused)
         if (!(skip_g && !stl)) {
@@ -436,7 +438,8 @@ int32_t avi_objective_finalize(avi_obj* o, const float* lambda, float* grad, flo
     const int D = o->D, accv = o->accv;
     if (o->family == AVI_MEANFIELD) {
         unsigned nb = (unsigned)std::min<int64_t>(ceil_div(D, 256), 64);
-        k_finalize_mf<<<nb, 256, 0, ctx->stream>>>(o->acc, accv, lambda, D, o->M, o->objective, o->entropy, grad, out);
+        k_finalize_mf<<<nb, 256, 0, ctx->stream>>>(o->acc, accv, lambda, D, o->M, o->objective, o->entropy, o->logp,
+                                                   o->esq, o->Mloc, avi_obj_defers_scalars(o) ? 1 : 0, grad, out);
         AVI_LAUNCHED(ctx);
     } else {
         const float* scal = o->acc + 4 * (size_t)accv;

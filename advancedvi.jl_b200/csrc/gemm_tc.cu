@@ -12,10 +12,10 @@
 //   EPI_STORE   : C[ks][b * ldc + a] = D (split-K slabs), for the full-rank family.
 //
 // Structure (one CTA per SM, persistent over work units = (a-block, b-chunk, k-split)):
-//   warp 0      TMA producer   (cp.async.bulk.tensor, 128B swizzle, STAGES-deep mbarrier ring)
+//   warp 0      TMA producer   (cp.async.bulk.tensor, 128B swizzle, mbarrier ring as deep as shared memory allows)
 //   warp 1      MMA issuer     (one elected thread: tcgen05.mma.kind::tf32, M = 128, N = NT)
 //   warp 2      TMEM allocator (512 columns = 2 accumulator stages of up to 256 columns)
-//   warps 4-11  epilogue       (tcgen05.ld 32x32b; warp w reads lanes 32*(w%4).., column half w/8)
+//   warps 4-19  epilogue       (tcgen05.ld 32x32b; warp w reads lanes 32*(w%4).., column quarter (w-4)/4)
 #include "avi_internal.cuh"
 #include "device_utils.cuh"
 #include "gemm_tc.cuh"
@@ -25,27 +25,30 @@ namespace {
 
 constexpr int BM = 128;            // UMMA M (TMEM lanes)
 constexpr int BK = 32;             // fp32 elements per 128-byte swizzle row
-constexpr int STAGES = 4;
+constexpr int MAX_STAGES = 8;
 constexpr int A_TILE_BYTES = BM * BK * 4;          // 16 KB
-constexpr int B_TILE_BYTES_MAX = 256 * BK * 4;     // 32 KB
-constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES_MAX;
-constexpr int NUM_THREADS = 384;
+constexpr int EPI_WARPS = 16;                      // 4 per TMEM lane quarter, each a column quarter
+constexpr int NUM_THREADS = 128 + 32 * EPI_WARPS;  // 640
+constexpr int SMEM_LIMIT = 232448;                 // 227 KB opt-in maximum per CTA
 
 struct SmemCtl {
-    uint64_t full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2];
+    uint64_t full[MAX_STAGES], empty[MAX_STAGES], tmem_full[2], tmem_empty[2];
     uint32_t tmem_base;
     float ys[2][256];
 };
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + (int)sizeof(SmemCtl);
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
-template <int EPI>
+// LIK: 0 Bernoulli-logit, 1 Gaussian (EPI_GLM_FWD only)
+template <int EPI, int LIK>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    SmemCtl* ctl = reinterpret_cast<SmemCtl*>(tiles + STAGES * STAGE_BYTES);
+    const int NT = p.nt;
+    const int stage_bytes = A_TILE_BYTES + NT * BK * 4;
+    const int stages = p.stages;
+    SmemCtl* ctl = reinterpret_cast<SmemCtl*>(tiles + stages * stage_bytes);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
@@ -53,8 +56,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         tc::tma_prefetch_desc(&tmB);
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&ctl->full[s], 1); tc::mbar_init(&ctl->empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { tc::mbar_init(&ctl->tmem_full[s], 1); tc::mbar_init(&ctl->tmem_empty[s], 8); }
+        for (int s = 0; s < stages; ++s) { tc::mbar_init(&ctl->full[s], 1); tc::mbar_init(&ctl->empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { tc::mbar_init(&ctl->tmem_full[s], 1); tc::mbar_init(&ctl->tmem_empty[s], EPI_WARPS); }
         tc::mbar_fence_init();
     }
     if (warp == 2) tc::tmem_alloc(&ctl->tmem_base, 512);
@@ -63,9 +66,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     tc::fence_after_sync();
     const uint32_t tmem_base = ctl->tmem_base;
 
-    const int NT = p.nt;
     const int units = p.n_ablk * p.n_bchunk * p.n_ksplit;
-    const uint32_t stage_tx = (uint32_t)(A_TILE_BYTES + NT * BK * 4);
+    const uint32_t stage_tx = (uint32_t)stage_bytes;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -76,11 +78,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 const int kb0 = ks * p.kb_per_split, kb1 = min(p.n_kblk, kb0 + p.kb_per_split);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     tc::mbar_wait(&ctl->empty[stage], phase ^ 1);
-                    uint8_t* sa = tiles + stage * STAGE_BYTES;
+                    uint8_t* sa = tiles + stage * stage_bytes;
                     tc::mbar_arrive_expect_tx(&ctl->full[stage], stage_tx);
                     tc::tma_load_2d(sa, &tmA, &ctl->full[stage], kb * BK, ab * BM);
                     tc::tma_load_2d(sa + A_TILE_BYTES, &tmB, &ctl->full[stage], kb * BK, bc * NT);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -99,7 +101,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 for (int kb = kb0; kb < kb1; ++kb) {
                     tc::mbar_wait(&ctl->full[stage], phase);
                     tc::fence_after_sync();
-                    const uint32_t sa = tc::smem_u32(tiles + stage * STAGE_BYTES);
+                    const uint32_t sa = tc::smem_u32(tiles + stage * stage_bytes);
                     const uint64_t da = tc::smem_desc_k_sw128(sa);
                     const uint64_t db = tc::smem_desc_k_sw128(sa + A_TILE_BYTES);
 #pragma unroll
@@ -107,7 +109,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         tc::umma_tf32(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
                                       (kb > kb0 || k > 0) ? 1u : 0u);
                     tc::umma_commit(&ctl->empty[stage]);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
                 tc::umma_commit(&ctl->tmem_full[as]);
                 if (++as == 2) { as = 0; aphase ^= 1; }
@@ -115,9 +117,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
-        const int ew = warp - 4, quarter = warp & 3, half = ew >> 2;
-        const int et = threadIdx.x - 128;   // 0..255
-        const int c_begin = half * (NT / 2), c_end = c_begin + NT / 2;
+        // warp w may only touch TMEM lanes [32 (w % 4), +32); the 4 warps of a lane quarter split the
+        // NT columns into runs of 8-column groups
+        const int ew = warp - 4, quarter = warp & 3, cq = ew >> 2;
+        const int et = threadIdx.x - 128;   // 0..511
+        const int ngroups = NT / 8;
+        const int c_begin = 8 * ((ngroups * cq) / 4), c_end = 8 * ((ngroups * (cq + 1)) / 4);
         int as = 0; uint32_t aphase = 0;
         for (int u = blockIdx.x; u < units; u += gridDim.x) {
             const int ab = u % p.n_ablk, bc = (u / p.n_ablk) % p.n_bchunk, ks = u / (p.n_ablk * p.n_bchunk);
@@ -128,57 +133,78 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 if (et < NT) ctl->ys[as][et] = b < p.Nb ? __ldg(p.y + b) : 0.0f;
                 epi_bar_sync();
             }
-            tc::mbar_wait(&ctl->tmem_full[as], aphase);
-            tc::fence_after_sync();
-            const uint32_t tacc = tmem_base + (uint32_t)(as * 256) + ((uint32_t)(quarter * 32) << 16);
             float s1 = 0.0f, s2 = 0.0f;
-            for (int c = c_begin; c < c_end; c += 8) {
-                float v[8];
-                tc::tmem_ld8(tacc + (uint32_t)c, v);
-                const int b0 = bc * NT + c;
-                if (EPI == EPI_GLM_FWD) {
-                    float r[8];
+            const uint32_t tacc = tmem_base + (uint32_t)(as * 256) + ((uint32_t)(quarter * 32) << 16);
+            if (EPI == EPI_GLM_BWD) {
+                // eps[b][a] for this thread's columns, fetched while the MMAs are still running
+                const float* Ea = p.E + a;
+                int c = c_begin;
+                float e[32];
+                bool waited = false;
+                for (; c < c_end; c += 32) {
+                    const int nc = min(32, c_end - c);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int b = b0 + j;
-                        const float yv = ctl->ys[as][c + j];
-                        float lp, rr;
-                        if (p.likelihood == AVI_GLM_BERNOULLI_LOGIT) {
-                            const float l = v[j];
-                            const float e = __expf(-fabsf(l));
-                            const float inv = __fdividef(1.0f, 1.0f + e);
-                            const float sig = l >= 0.0f ? inv : e * inv;
-                            lp = yv * l - (fmaxf(l, 0.0f) - __logf(inv));   // y l - log1pexp(l)
-                            rr = yv - sig;
-                        } else {
-                            rr = yv - v[j];
-                            lp = -0.5f * AVI_LOG2PI - 0.5f * rr * rr;
-                        }
-                        const bool ok = b < p.Nb;
-                        s1 += ok ? lp : 0.0f;
-                        r[j] = ok ? tc::round_tf32(p.w * rr) : 0.0f;
+                    for (int j = 0; j < 32; ++j) {
+                        const int b = bc * NT + c + j;
+                        e[j] = (j < nc && a_ok && b < p.Nb) ? __ldg(Ea + (size_t)b * p.lde) : 0.0f;
                     }
-                    if (a_ok && b0 < p.ldc) {
-                        float4* dst = reinterpret_cast<float4*>(p.C + (size_t)a * p.ldc + b0);
-                        dst[0] = make_float4(r[0], r[1], r[2], r[3]);
-                        dst[1] = make_float4(r[4], r[5], r[6], r[7]);
-                    }
-                } else if (EPI == EPI_GLM_BWD) {
+                    if (!waited) { tc::mbar_wait(&ctl->tmem_full[as], aphase); tc::fence_after_sync(); waited = true; }
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int b = b0 + j;
-                        if (b < p.Nb && a_ok) {
-                            const float e = __ldg(p.E + (size_t)b * p.lde + a);
-                            s1 += v[j];
-                            s2 = fmaf(v[j], e, s2);
+                    for (int h = 0; h < 4; ++h) {
+                        if (h * 8 < nc) {
+                            float v[8];
+                            tc::tmem_ld8(tacc + (uint32_t)(c + h * 8), v);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const bool ok = bc * NT + c + h * 8 + j < p.Nb;
+                                s1 += ok ? v[j] : 0.0f;
+                                s2 = fmaf(v[j], e[h * 8 + j], s2);
+                            }
                         }
                     }
-                } else {
-                    float* Cs = p.C + (size_t)ks * p.slab_stride;
+                }
+                if (!waited) { tc::mbar_wait(&ctl->tmem_full[as], aphase); tc::fence_after_sync(); }
+            } else {
+                tc::mbar_wait(&ctl->tmem_full[as], aphase);
+                tc::fence_after_sync();
+                for (int c = c_begin; c < c_end; c += 8) {
+                    float v[8];
+                    tc::tmem_ld8(tacc + (uint32_t)c, v);
+                    const int b0 = bc * NT + c;
+                    if (EPI == EPI_GLM_FWD) {
+                        float r[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int b = b0 + j;
-                        if (b < p.Nb && a_ok) Cs[(size_t)b * p.ldc + a] = v[j];
+                        for (int j = 0; j < 8; ++j) {
+                            const float yv = ctl->ys[as][c + j];
+                            float lp, rr;
+                            if (LIK == 0) {
+                                const float l = v[j];
+                                const float e = exp2f(-1.4426950408889634f * fabsf(l));
+                                const float inv = __fdividef(1.0f, 1.0f + e);
+                                const float sig = l >= 0.0f ? inv : e * inv;
+                                // y l - log1pexp(l) = y l - max(l, 0) + ln(inv)
+                                lp = fmaf(yv, l, fmaf(0.6931471805599453f, __log2f(inv), -fmaxf(l, 0.0f)));
+                                rr = yv - sig;
+                            } else {
+                                rr = yv - v[j];
+                                lp = fmaf(-0.5f * rr, rr, -0.5f * AVI_LOG2PI);
+                            }
+                            const bool ok = b0 + j < p.Nb;
+                            s1 += ok ? lp : 0.0f;
+                            r[j] = ok ? tc::round_tf32(p.w * rr) : 0.0f;
+                        }
+                        if (a_ok && b0 < p.ldc) {
+                            float4* dst = reinterpret_cast<float4*>(p.C + (size_t)a * p.ldc + b0);
+                            dst[0] = make_float4(r[0], r[1], r[2], r[3]);
+                            dst[1] = make_float4(r[4], r[5], r[6], r[7]);
+                        }
+                    } else {
+                        float* Cs = p.C + (size_t)ks * p.slab_stride;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int b = b0 + j;
+                            if (b < p.Nb && a_ok) Cs[(size_t)b * p.ldc + a] = v[j];
+                        }
                     }
                 }
             }
@@ -187,10 +213,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&ctl->tmem_empty[as]);
             if (EPI == EPI_GLM_FWD) {
-                if (a_ok) p.part1[(size_t)(bc * 2 + half) * p.ldpart + a] = s1;
+                if (a_ok) p.part1[(size_t)(bc * 4 + cq) * p.ldpart + a] = s1;
             } else if (EPI == EPI_GLM_BWD) {
                 if (a_ok) {
-                    const size_t slab = (size_t)((ks * p.n_bchunk + bc) * 2 + half) * p.ldpart;
+                    const size_t slab = (size_t)((ks * p.n_bchunk + bc) * 4 + cq) * p.ldpart;
                     p.part1[slab + a] = s1;
                     p.part2[slab + a] = s2;
                 }
@@ -258,22 +284,33 @@ int avi_tc_pick_nt(int64_t Nb, int n_ablk, int n_ksplit, int sms, int nt_max) {
     return best;
 }
 
-int32_t avi_tc_launch(avi_ctx* ctx, int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p) {
+int32_t avi_tc_launch(avi_ctx* ctx, int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p_in) {
+    TcParams p = p_in;
     if (p.nt % 16 || p.nt < 16 || p.nt > 256) AVI_FAIL(ctx, AVI_ERR_INVALID, "bad b-chunk width");
     const int units = p.n_ablk * p.n_bchunk * p.n_ksplit;
     if (units <= 0) return AVI_OK;
+    // as many pipeline stages as fit: the contraction is bound by bytes in flight per SM
+    const int stage_bytes = A_TILE_BYTES + p.nt * BK * 4;
+    p.stages = std::min(MAX_STAGES, (SMEM_LIMIT - 1024 - (int)sizeof(SmemCtl)) / stage_bytes);
+    const int smem = p.stages * stage_bytes + 1024 + (int)sizeof(SmemCtl);
     static bool attr_done = false;
     if (!attr_done) {
-        AVI_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tc<EPI_GLM_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        AVI_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tc<EPI_GLM_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        AVI_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tc<EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        AVI_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tc<EPI_GLM_FWD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        AVI_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tc<EPI_GLM_FWD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        AVI_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tc<EPI_GLM_BWD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        AVI_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tc<EPI_STORE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         attr_done = true;
     }
     const unsigned grid = (unsigned)std::min(units, ctx->prop.multiProcessorCount);
     AviTimed timed(ctx, epi == EPI_GLM_FWD ? "glm_fwd" : epi == EPI_GLM_BWD ? "glm_bwd" : "gemm_store");
-    if (epi == EPI_GLM_FWD) k_gemm_tc<EPI_GLM_FWD><<<grid, NUM_THREADS, SMEM_BYTES, ctx->stream>>>(tmA, tmB, p);
-    else if (epi == EPI_GLM_BWD) k_gemm_tc<EPI_GLM_BWD><<<grid, NUM_THREADS, SMEM_BYTES, ctx->stream>>>(tmA, tmB, p);
-    else k_gemm_tc<EPI_STORE><<<grid, NUM_THREADS, SMEM_BYTES, ctx->stream>>>(tmA, tmB, p);
+    if (epi == EPI_GLM_FWD && p.likelihood == AVI_GLM_BERNOULLI_LOGIT)
+        k_gemm_tc<EPI_GLM_FWD, 0><<<grid, NUM_THREADS, smem, ctx->stream>>>(tmA, tmB, p);
+    else if (epi == EPI_GLM_FWD)
+        k_gemm_tc<EPI_GLM_FWD, 1><<<grid, NUM_THREADS, smem, ctx->stream>>>(tmA, tmB, p);
+    else if (epi == EPI_GLM_BWD)
+        k_gemm_tc<EPI_GLM_BWD, 0><<<grid, NUM_THREADS, smem, ctx->stream>>>(tmA, tmB, p);
+    else
+        k_gemm_tc<EPI_STORE, 0><<<grid, NUM_THREADS, smem, ctx->stream>>>(tmA, tmB, p);
     AVI_LAUNCHED(ctx);
     return AVI_OK;
 }

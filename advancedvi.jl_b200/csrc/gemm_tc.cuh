@@ -14,6 +14,7 @@ struct TcParams {
     int n_ablk, n_bchunk, n_ksplit;
     int n_kblk, kb_per_split;
     int nt;
+    int stages;          // filled by avi_tc_launch
     // epilogue operands
     float* C;            // FWD: R [a][ldc];  STORE: slabs [ks][b * ldc + a]
     int ldc;
@@ -23,7 +24,7 @@ struct TcParams {
     int likelihood;
     const float* E;      // BWD: eps [b][lde]
     int lde;
-    float* part1;        // FWD: partial log-lik [(bc*2+half)][ldpart];  BWD: sum g  [slab][ldpart]
+    float* part1;        // FWD: partial log-lik [(bc*4+cq)][ldpart];  BWD: sum g  [slab][ldpart]
     float* part2;        // BWD: sum g*eps
     int ldpart;
 };

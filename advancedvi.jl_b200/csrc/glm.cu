@@ -14,11 +14,10 @@
 #include "avi_internal.cuh"
 #include "device_utils.cuh"
 #include "gemm_tc.cuh"
+#include "glm_prior.cuh"
 #include "tc_common.cuh"
 
 namespace {
-
-constexpr float LOG3 = 1.0986122886681098f;
 
 // per-sample prior pieces: pre[m] = {prior_lp, 1/sigma^2, d logp / d eta, |beta|^2}
 __global__ void __launch_bounds__(256)
@@ -33,15 +32,7 @@ k_glm_pre(const float* __restrict__ Z, int ld, int d, int variant, int include_p
         if (Zt) Zt[(size_t)m * ld + i] = tc::round_tf32(z);
     }
     const float bsq = block_sum(part, sm);
-    if (threadIdx.x == 0) {
-        const float eta = Z[(size_t)m * ld + d];
-        const float s2 = expf(2.0f * eta), inv = 1.0f / s2;
-        float lp = -0.5f * (float)d * AVI_LOG2PI - (float)d * eta - 0.5f * bsq * inv - LOG3 - 0.5f * AVI_LOG2PI;
-        float ge = -(float)d + bsq * inv;
-        if (variant == AVI_GLM_SUBSAMPLING) { lp -= s2 / 18.0f; ge -= s2 / 9.0f; }
-        else { lp -= eta * eta / 18.0f; ge -= eta / 9.0f; }
-        pre[m] = include_prior ? make_float4(lp, inv, ge, bsq) : make_float4(0.f, 0.f, 0.f, bsq);
-    }
+    if (threadIdx.x == 0) pre[m] = glm_prior_terms(bsq, Z[(size_t)m * ld + d], d, variant, include_prior);
 }
 
 // SIMT mode: logits in R -> weighted residual in place, per-sample log-likelihood sum
@@ -72,24 +63,31 @@ k_glm_lik(float* __restrict__ R, int ldR, int n, const float* __restrict__ y, in
 // fused mean-field tail: a1[i] = sum_m G[m][i], a2[i] = sum_m G[m][i] eps[m][i] where
 // G = (split-K partial sums of X'R) - beta / sigma^2 for i < d and d logp / d eta for i == d;
 // the trailing CTAs assemble logp[m] = w * sum(partial log-lik) + prior.
+// CTA = 32 coordinates (or 32 samples) x 32 groups; every sum is combined in a fixed order.
 __global__ void __launch_bounds__(1024)
 k_glm_post_sums(const float* __restrict__ Z, const float* __restrict__ E, int ld, int M, int d,
                 const float4* __restrict__ pre, const float* __restrict__ a1p, const float* __restrict__ a2p,
                 int nslab, int ldslab, const float* __restrict__ llpart, int nparts, int ldpart, float w,
                 int ncoordblk, float* __restrict__ a1, float* __restrict__ a2, float* __restrict__ logp) {
+    __shared__ float sm[4][32][33];
+    const int tx = threadIdx.x, ty = threadIdx.y;
     if ((int)blockIdx.x >= ncoordblk) {
-        const int m = (blockIdx.x - ncoordblk) * 1024 + threadIdx.y * 32 + threadIdx.x;
-        if (m < M) {
-            float s = 0.f;
-            for (int q = 0; q < nparts; ++q) s += llpart[(size_t)q * ldpart + m];
-            logp[m] = fmaf(w, s, pre[m].x);
+        const int m = (blockIdx.x - ncoordblk) * 32 + tx;
+        float s = 0.f;
+        if (m < M)
+            for (int q = ty; q < nparts; q += 32) s += llpart[(size_t)q * ldpart + m];
+        sm[0][ty][tx] = s;
+        __syncthreads();
+        if (ty == 0 && m < M) {
+            float t = 0.f;
+#pragma unroll
+            for (int r = 0; r < 32; ++r) t += sm[0][r][tx];
+            logp[m] = fmaf(w, t, pre[m].x);
         }
         return;
     }
-    __shared__ float sm[2][32][33];
-    const int tx = threadIdx.x, ty = threadIdx.y;
     const int i = blockIdx.x * 32 + tx;
-    float t1 = 0.f, t2 = 0.f;
+    float t1 = 0.f, t2 = 0.f, p1 = 0.f, p2 = 0.f;
     if (i <= d) {
         for (int m = ty; m < M; m += 32) {
             const float4 pm = pre[m];
@@ -97,18 +95,19 @@ k_glm_post_sums(const float* __restrict__ Z, const float* __restrict__ E, int ld
             const float g = i < d ? -Z[(size_t)m * ld + i] * pm.y : pm.z;
             t1 += g; t2 = fmaf(g, e, t2);
         }
+        if (i < d)
+            for (int q = ty; q < nslab; q += 32) {
+                p1 += a1p[(size_t)q * ldslab + i];
+                p2 += a2p[(size_t)q * ldslab + i];
+            }
     }
-    sm[0][ty][tx] = t1; sm[1][ty][tx] = t2;
+    sm[0][ty][tx] = t1; sm[1][ty][tx] = t2; sm[2][ty][tx] = p1; sm[3][ty][tx] = p2;
     __syncthreads();
     if (ty < 2 && i <= d) {
-        float s = 0.f;
+        float s = 0.f, ps = 0.f;
 #pragma unroll
-        for (int r = 0; r < 32; ++r) s += sm[ty][r][tx];
-        if (i < d) {
-            const float* part = ty == 0 ? a1p : a2p;
-            for (int q = 0; q < nslab; ++q) s += part[(size_t)q * ldslab + i];
-        }
-        (ty == 0 ? a1 : a2)[i] = s;
+        for (int r = 0; r < 32; ++r) { s += sm[ty][r][tx]; ps += sm[ty + 2][r][tx]; }
+        (ty == 0 ? a1 : a2)[i] = s + ps;
     }
 }
 
@@ -211,7 +210,15 @@ struct Glm : avi_model {
         avi_free(idx_own); avi_free(R); avi_free(Zt); avi_free(llpart); avi_free(a1p);
         avi_free(slabs); avi_free(pre);
     }
+    bool hooked = false;
     bool tc_mode() const { return mode != AVI_GEMM_SIMT_FP32; }
+    bool sample_hook(int ld, int M, SampleHook* h) override {
+        if (M <= 0 || ensure(M, ld) != AVI_OK) return false;
+        h->kind = 1; h->d = d; h->variant = variant; h->include_prior = include_prior;
+        h->Zt = tc_mode() ? Zt : nullptr; h->pre = pre;
+        hooked = true;
+        return true;
+    }
     float likeadj() const {
         if (variant != AVI_GLM_SUBSAMPLING) return 1.0f;
         double rows = subsampled ? (double)n_act * nshards : (double)rows_global;
@@ -242,8 +249,12 @@ struct Glm : avi_model {
     // forward: R <- w * resid, llpart/nparts <- partial log-lik sums
     int32_t forward(const float* Z, int ld, int M, int* nparts) {
         const float w = likeadj();
-        k_glm_pre<<<M, 256, 0, ctx->stream>>>(Z, ld, d, variant, include_prior, tc_mode() ? Zt : nullptr, pre);
-        AVI_LAUNCHED(ctx);
+        if (hooked) {
+            hooked = false;   // the sampling kernel already produced Zt and pre for these samples
+        } else {
+            k_glm_pre<<<M, 256, 0, ctx->stream>>>(Z, ld, d, variant, include_prior, tc_mode() ? Zt : nullptr, pre);
+            AVI_LAUNCHED(ctx);
+        }
         if (!tc_mode()) {
             AVI_CHECK(ensure_buf(&llpart, &llpart_cap, capM));
             // logits[m][j] = sum_k Z[m][k] Xr[j][k]
@@ -260,13 +271,13 @@ struct Glm : avi_model {
         p.n_bchunk = (int)ceil_div(n_act, p.nt);
         p.n_ksplit = 1; p.n_kblk = (int)ceil_div(d, 32); p.kb_per_split = p.n_kblk;
         p.C = R; p.ldc = (int)ldR; p.y = y; p.w = w; p.likelihood = likelihood;
-        AVI_CHECK(ensure_buf(&llpart, &llpart_cap, (long long)p.n_bchunk * 2 * capM));
+        AVI_CHECK(ensure_buf(&llpart, &llpart_cap, (long long)p.n_bchunk * 4 * capM));
         p.part1 = llpart; p.ldpart = capM;
         CUtensorMap tmA, tmB;
         AVI_CHECK(avi_tc_make_tmap(ctx, &tmA, Zt, M, d, ld, 128));
         AVI_CHECK(avi_tc_make_tmap(ctx, &tmB, Xr, n_act, d, dK, p.nt));
         AVI_CHECK(avi_tc_launch(ctx, EPI_GLM_FWD, tmA, tmB, p));
-        *nparts = p.n_bchunk * 2;
+        *nparts = p.n_bchunk * 4;
         return AVI_OK;
     }
 
@@ -320,14 +331,14 @@ struct Glm : avi_model {
         AVI_CHECK(forward(Z, ld, M, &nparts));
         TcParams p{}; CUtensorMap tmA, tmB;
         AVI_CHECK(backward_setup(M, &p, &tmA, &tmB));
-        const int nslab = p.n_ksplit * p.n_bchunk * 2;
+        const int nslab = p.n_ksplit * p.n_bchunk * 4;
         const int ldslab = (int)round_up(d, 32);
         AVI_CHECK(ensure_buf(&a1p, &ap_cap, 2LL * nslab * ldslab));
         float* a2p = a1p + (size_t)nslab * ldslab;
         p.E = E; p.lde = ld; p.part1 = a1p; p.part2 = a2p; p.ldpart = ldslab;
         AVI_CHECK(avi_tc_launch(ctx, EPI_GLM_BWD, tmA, tmB, p));
         const int ncb = (int)ceil_div(d + 1, 32);
-        const unsigned grid = (unsigned)(ncb + ceil_div(M, 1024));
+        const unsigned grid = (unsigned)(ncb + ceil_div(M, 32));
         k_glm_post_sums<<<grid, dim3(32, 32), 0, ctx->stream>>>(Z, E, ld, M, d, pre, a1p, a2p, nslab, ldslab, llpart,
                                                                 nparts, capM, likeadj(), ncb, a1, a2, logp);
         AVI_LAUNCHED(ctx);

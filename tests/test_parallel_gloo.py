@@ -51,9 +51,12 @@ def _worker(rank, world, port, out):
     lp_part, G_part = w * ll, np.zeros_like(Zf)
     G_part[:d] = w * (sub.X.T @ resid)
     if rank == 0:
-        full_prior = Mo.LogReg(X[:0], y[:0], n_data=n)       # zero rows: prior terms only
-        lp0, G0 = full_prior.logdensity_and_gradient_batch(Zf)
-        lp_part, G_part = lp_part + lp0, G_part + G0
+        # prior terms only: full log-density minus its likelihood part
+        lpf, Gf = prob.logdensity_and_gradient_batch(Zf)
+        llf, resf = prob._loglik_and_resid(prob.X @ B)
+        G0 = Gf.copy()
+        G0[:d] -= prob.X.T @ resf
+        lp_part, G_part = lp_part + (lpf - llf), G_part + G0
     t = torch.from_numpy(np.concatenate([lp_part, G_part.reshape(-1)]))
     dist.all_reduce(t)
     lp_all, G_all = t.numpy()[:M], t.numpy()[M:].reshape(D, M)
