@@ -1,0 +1,106 @@
+"""Multi-rank parity check, run as `torchrun --nproc-per-node N tests/multigpu_check.py` (one rank per GPU).
+Sharded results (M-axis and n-axis, native NVLink exchange and the NCCL callback) must reproduce the
+single-rank result of the same library up to summation order, and must be bitwise identical across ranks."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    import advancedvi_jl_b200 as avi
+    from advancedvi_jl_b200 import parallel, _lib as L
+    from oracle import models as Mo
+
+    rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(lr)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    n, d, M, key = 2000, 96, 64, 11
+    X, y = Mo.synth_glm_data(n, d, seed=4)
+    D = d + 1
+    q = avi.MeanFieldGaussian(np.zeros(D, np.float32), np.full(D, 0.3, np.float32))
+    lam = q.destructure()
+    results = {}
+
+    def gather_equal(a, what):
+        t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+        allt = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        for r in range(world):
+            assert torch.equal(allt[0], allt[r]), f"{what}: rank {r} differs bitwise from rank 0"
+
+    # reference: unsharded, single rank
+    c0 = avi.Context(lr)
+    p0 = avi.LogReg(c0, X, y, gemm="tf32")
+    for kind in ("rep", "stl", "score"):
+        spec = {"rep": avi.RepGradELBO(M), "stl": avi.RepGradELBO(M, avi.StickingTheLandingEntropy()),
+                "score": avi.ScoreGradELBO(M)}[kind]
+        o0 = avi.Objective(key, spec, q, p0)
+        results[kind] = o0.estimate_gradient(lam)
+        o0.close()
+    alg = avi.KLMinRepGradDescent(optimizer=avi.Adam(1e-2), n_samples=M, operator=avi.ClipScale())
+    _, info0, st0 = avi.optimize(key, alg, 25, p0, q)
+    lam0, avg0, _ = st0.params()
+
+    for native in (True, False):
+        ctx = avi.Context(lr)
+        parallel.connect(ctx, max_floats=4 * 128 + 64, native=native)
+        # ---- M-axis ----
+        prob = avi.LogReg(ctx, X, y, gemm="tf32")
+        m0, ml = parallel.sample_shard(M, rank, world)
+        for kind in ("rep", "stl", "score"):
+            spec = {"rep": avi.RepGradELBO(M), "stl": avi.RepGradELBO(M, avi.StickingTheLandingEntropy()),
+                    "score": avi.ScoreGradELBO(M)}[kind]
+            o = avi.Objective(key, spec, q, prob)
+            o.set_sample_shard(m0, ml)
+            v, g, e = o.estimate_gradient(lam)
+            v0, g0, e0 = results[kind]
+            tol = 2e-3 if kind == "score" else 2e-5
+            assert abs(v - v0) <= tol * abs(v0) + 1e-6, (kind, v, v0)
+            assert np.linalg.norm(g - g0) <= tol * np.linalg.norm(g0), (kind, native)
+            gather_equal(g, f"grad {kind}")
+            o.close()
+        _, info, st = avi.optimize(key, alg, 25, prob, q, state=None) if False else (None, None, None)
+        obj = avi.Objective(key, alg.objective, q, prob)
+        obj.set_sample_shard(m0, ml)
+        from advancedvi_jl_b200.api import _OptState
+        import ctypes as C
+        st = _OptState(alg, obj, q)
+        vals, elbos, nd = np.empty(25, np.float32), np.empty(25, np.float32), C.c_int32()
+        L.check(L.lib.avi_opt_steps(st.h, 25, L.fptr(vals), L.fptr(elbos), C.byref(nd)), ctx.h)
+        assert nd.value == 25
+        lam1, avg1, _ = st.params()
+        assert np.linalg.norm(lam1 - lam0) <= 1e-4 * np.linalg.norm(lam0), np.linalg.norm(lam1 - lam0)
+        gather_equal(lam1, "lambda after 25 sharded steps")
+        st.close(); obj.close(); prob.close()
+        # ---- n-axis: every rank holds all samples and a slice of the rows ----
+        r0, nr = parallel.row_shard(n, rank, world, align=32)
+        probr = avi.LogReg(ctx, X[r0:r0 + nr], y[r0:r0 + nr], n_data=n, gemm="tf32")
+        probr.set_data_shard(world, n, include_prior=(rank == 0))
+        for kind in ("rep", "score"):
+            spec = avi.RepGradELBO(M) if kind == "rep" else avi.ScoreGradELBO(M)
+            o = avi.Objective(key, spec, q, probr)
+            o.set_shard_axis(L.SHARD_ROWS)
+            v, g, e = o.estimate_gradient(lam)
+            v0, g0, e0 = results[kind]
+            tol = 2e-3 if kind == "score" else 2e-5
+            assert abs(v - v0) <= tol * abs(v0) + 1e-6, (kind, v, v0)
+            assert np.linalg.norm(g - g0) <= tol * np.linalg.norm(g0), (kind, "rows", native)
+            gather_equal(g, f"row-sharded grad {kind}")
+            o.close()
+        probr.close()
+        ctx.close()
+        if rank == 0:
+            print(f"multigpu_check ok: world={world} native_exchange={native}", flush=True)
+    st0.close(); st0.obj.close(); p0.close(); c0.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
