@@ -133,8 +133,7 @@ struct avi_model {
     // Fused mean-field path: a1[i] = sum_m G[m][i], a2[i] = sum_m G[m][i] * E[m][i] without
     // materialising G (a1, a2 hold D floats and are overwritten).  Optional.
     virtual bool has_gradsums() const { return false; }
-    virtual int32_t eval_gradsums(const float* Z, const float* E, int ld, int M, float* logp,
-                                  float* a1, float* a2) {
+    virtual int32_t eval_gradsums(const float* Z, const float* E, int ld, int M, float* logp, float* a1, float* a2) {
         return AVI_ERR_UNSUPPORTED;
     }
     virtual int32_t subsample(const int32_t* idx_host, int64_t batch) {

@@ -10,6 +10,8 @@
 //   estimate_scoregradelbo_ad_forward    src/algorithms/scoregradelbo.jl:87-117
 // Gradients are the closed forms of SURVEY.md Appendix A (checked against finite differences of
 // the restated forward in tests/test_oracle_gradients.py).
+#include <cstdlib>
+
 #include "avi_internal.cuh"
 #include "device_utils.cuh"
 #include "glm_prior.cuh"

@@ -16,6 +16,9 @@
 //   warp 1      MMA issuer     (one elected thread: tcgen05.mma.kind::tf32, M = 128, N = NT)
 //   warp 2      TMEM allocator (512 columns = 2 accumulator stages of up to 256 columns)
 //   warps 4-19  epilogue       (tcgen05.ld 32x32b; warp w reads lanes 32*(w%4).., column quarter (w-4)/4)
+#include <cstdio>
+#include <cstdlib>
+
 #include "avi_internal.cuh"
 #include "device_utils.cuh"
 #include "gemm_tc.cuh"
@@ -51,37 +54,60 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     SmemCtl* ctl = reinterpret_cast<SmemCtl*>(tiles + stages * stage_bytes);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+    // thread-block cluster: CA a-blocks x CB b-chunks of one k-split.  The A tile of an a-block is needed
+    // by the CB CTAs of its row, the B tile of a b-chunk by the CA CTAs of its column: every CTA loads
+    // 1/CB of its A tile and 1/CA of its B tile and TMA-multicasts the slice to the CTAs that share it,
+    // so each operand byte crosses the L2 -> SM crossbar once per cluster instead of once per CTA.
+    const int CA = p.ca, CB = p.cb, CSZ = CA * CB;
+    const uint32_t crank = CSZ > 1 ? tc::cluster_ctarank() : 0u;
+    const int ra = (int)crank % CA, rb = (int)crank / CA;
+    uint32_t a_mask = 0, b_mask = 0;
+    for (int j = 0; j < CB; ++j) a_mask |= 1u << (ra + CA * j);
+    for (int j = 0; j < CA; ++j) b_mask |= 1u << (j + CA * rb);
+    const uint32_t peer_mask = a_mask | b_mask;   // CTAs that write into my stages == CTAs I write into
+    const int cluster_id = blockIdx.x / CSZ, n_clusters = gridDim.x / CSZ;
+
     if (warp == 0 && lane == 0) {
         tc::tma_prefetch_desc(&tmA);
         tc::tma_prefetch_desc(&tmB);
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < stages; ++s) { tc::mbar_init(&ctl->full[s], 1); tc::mbar_init(&ctl->empty[s], 1); }
+        for (int s = 0; s < stages; ++s) { tc::mbar_init(&ctl->full[s], 1); tc::mbar_init(&ctl->empty[s], CA + CB - 1); }
         for (int s = 0; s < 2; ++s) { tc::mbar_init(&ctl->tmem_full[s], 1); tc::mbar_init(&ctl->tmem_empty[s], EPI_WARPS); }
         tc::mbar_fence_init();
     }
     if (warp == 2) tc::tmem_alloc(&ctl->tmem_base, 512);
     tc::fence_before_sync();
     __syncthreads();
+    if (CSZ > 1) tc::cluster_sync();   // peers must see initialised barriers before any multicast lands
     tc::fence_after_sync();
     const uint32_t tmem_base = ctl->tmem_base;
 
-    const int units = p.n_ablk * p.n_bchunk * p.n_ksplit;
+    // cluster units: (a-group, b-group, k-split); this CTA's tile inside the unit is (ra, rb)
+    const int n_ag = (p.n_ablk + CA - 1) / CA, n_bg = (p.n_bchunk + CB - 1) / CB;
+    const int units = n_ag * n_bg * p.n_ksplit;
     const uint32_t stage_tx = (uint32_t)stage_bytes;
+    const int a_rows = BM / CB, b_rows = NT / CA;   // rows of the slices this CTA loads
+#define UNIT_COORDS(u)                                                                       \
+    const int ab = ((u) % n_ag) * CA + ra, bc = (((u) / n_ag) % n_bg) * CB + rb, ks = (u) / (n_ag * n_bg)
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int u = blockIdx.x; u < units; u += gridDim.x) {
-                const int ab = u % p.n_ablk, bc = (u / p.n_ablk) % p.n_bchunk, ks = u / (p.n_ablk * p.n_bchunk);
+            for (int u = cluster_id; u < units; u += n_clusters) {
+                UNIT_COORDS(u);
                 const int kb0 = ks * p.kb_per_split, kb1 = min(p.n_kblk, kb0 + p.kb_per_split);
                 for (int kb = kb0; kb < kb1; ++kb) {
-                    tc::mbar_wait(&ctl->empty[stage], phase ^ 1);
+                    tc::mbar_wait(&ctl->empty[stage], phase ^ 1);   // every CTA I write into has drained this stage
                     uint8_t* sa = tiles + stage * stage_bytes;
                     tc::mbar_arrive_expect_tx(&ctl->full[stage], stage_tx);
-                    tc::tma_load_2d(sa, &tmA, &ctl->full[stage], kb * BK, ab * BM);
-                    tc::tma_load_2d(sa + A_TILE_BYTES, &tmB, &ctl->full[stage], kb * BK, bc * NT);
+                    uint8_t* dst_a = sa + rb * a_rows * (BK * 4);
+                    uint8_t* dst_b = sa + A_TILE_BYTES + ra * b_rows * (BK * 4);
+                    if (CB > 1) tc::tma_load_2d_mc(dst_a, &tmA, &ctl->full[stage], kb * BK, ab * BM + rb * a_rows, (uint16_t)a_mask);
+                    else tc::tma_load_2d(dst_a, &tmA, &ctl->full[stage], kb * BK, ab * BM);
+                    if (CA > 1) tc::tma_load_2d_mc(dst_b, &tmB, &ctl->full[stage], kb * BK, bc * NT + ra * b_rows, (uint16_t)b_mask);
+                    else tc::tma_load_2d(dst_b, &tmB, &ctl->full[stage], kb * BK, bc * NT);
                     if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -92,8 +118,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             const uint32_t idesc = tc::idesc_tf32(BM, NT);
             int stage = 0; uint32_t phase = 0;
             int as = 0; uint32_t aphase = 0;
-            for (int u = blockIdx.x; u < units; u += gridDim.x) {
-                const int ks = u / (p.n_ablk * p.n_bchunk);
+            for (int u = cluster_id; u < units; u += n_clusters) {
+                const int ks = u / (n_ag * n_bg);
                 const int kb0 = ks * p.kb_per_split, kb1 = min(p.n_kblk, kb0 + p.kb_per_split);
                 tc::mbar_wait(&ctl->tmem_empty[as], aphase ^ 1);
                 tc::fence_after_sync();
@@ -108,7 +134,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     for (int k = 0; k < BK / 8; ++k)   // UMMA K = 8 tf32 = 32 bytes: +2 in 16-byte units
                         tc::umma_tf32(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
                                       (kb > kb0 || k > 0) ? 1u : 0u);
-                    tc::umma_commit(&ctl->empty[stage]);
+                    if (CSZ > 1) tc::umma_commit_mc(&ctl->empty[stage], (uint16_t)peer_mask);
+                    else tc::umma_commit(&ctl->empty[stage]);
                     if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
                 tc::umma_commit(&ctl->tmem_full[as]);
@@ -124,10 +151,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const int ngroups = NT / 8;
         const int c_begin = 8 * ((ngroups * cq) / 4), c_end = 8 * ((ngroups * (cq + 1)) / 4);
         int as = 0; uint32_t aphase = 0;
-        for (int u = blockIdx.x; u < units; u += gridDim.x) {
-            const int ab = u % p.n_ablk, bc = (u / p.n_ablk) % p.n_bchunk, ks = u / (p.n_ablk * p.n_bchunk);
+        for (int u = cluster_id; u < units; u += n_clusters) {
+            UNIT_COORDS(u);
             const int a = ab * BM + quarter * 32 + lane;   // this thread's accumulator row
-            const bool a_ok = a < p.Ma;
+            const bool a_ok = a < p.Ma && bc < p.n_bchunk;   // tiles past the edge of the unit grid only feed the pipeline
             if (EPI == EPI_GLM_FWD) {
                 int b = bc * NT + et;
                 if (et < NT) ctl->ys[as][et] = b < p.Nb ? __ldg(p.y + b) : 0.0f;
@@ -225,8 +252,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
     }
 
+#undef UNIT_COORDS
     tc::fence_before_sync();
     __syncthreads();
+    if (CSZ > 1) tc::cluster_sync();   // no peer may still signal my barriers / write my smem after I exit
     if (warp == 2) {
         tc::fence_after_sync();
         tc::tmem_dealloc(tmem_base, 512);
@@ -270,47 +299,124 @@ int32_t avi_tc_make_tmap(avi_ctx* ctx, CUtensorMap* map, const float* base, int6
     return AVI_OK;
 }
 
-// Pick the b-chunk width (multiple of 16, <= 256) that minimises the makespan of
-// n_ablk * ceil(Nb / nt) * n_ksplit units on `sms` CTAs.
-int avi_tc_pick_nt(int64_t Nb, int n_ablk, int n_ksplit, int sms, int nt_max) {
-    int best = 16; double best_cost = 1e300;
-    int hi = (int)std::min<int64_t>(nt_max, round_up(Nb, 16));
-    for (int nt = 16; nt <= hi; nt += 16) {
-        int64_t units = (int64_t)n_ablk * ceil_div(Nb, nt) * n_ksplit;
-        int64_t waves = ceil_div(units, sms);
-        double cost = (double)waves * (nt + 24.0);   // +24: per-unit pipeline fill / epilogue tail
-        if (cost < best_cost - 1e-9) { best_cost = cost; best = nt; }
+static int smem_bytes_for(int nt, int* stages_out) {
+    const int stage_bytes = A_TILE_BYTES + nt * BK * 4;
+    const int stages = std::min(MAX_STAGES, (SMEM_LIMIT - 1024 - (int)sizeof(SmemCtl)) / stage_bytes);
+    if (stages_out) *stages_out = stages;
+    return stages * stage_bytes + 1024 + (int)sizeof(SmemCtl);
+}
+
+static int32_t set_attrs(avi_ctx* ctx) {
+    static bool attr_done = false;
+    if (attr_done) return AVI_OK;
+    AVI_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tc<EPI_GLM_FWD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    AVI_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tc<EPI_GLM_FWD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    AVI_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tc<EPI_GLM_BWD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    AVI_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tc<EPI_STORE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    attr_done = true;
+    return AVI_OK;
+}
+
+// how many clusters of `csz` CTAs (one CTA per SM, full shared memory) can be resident at once
+static int max_active_clusters(avi_ctx* ctx, int csz) {
+    static int cache[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (csz <= 1) return ctx->prop.multiProcessorCount;
+    if (cache[csz]) return cache[csz];
+    if (set_attrs(ctx) != AVI_OK) return 0;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(csz * 64)); cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = smem_bytes_for(256, nullptr); cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = csz; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, (const void*)k_gemm_tc<EPI_GLM_BWD, 0>, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    cache[csz] = n > 0 ? n : -1;
+    return cache[csz];
+}
+
+// Tiling plan.  split_k = false: many b-chunks, full K per unit (the epilogue is non-linear: GLM forward);
+// split_k = true: few output tiles, K split across the chip (linear epilogues).
+// Cost model per 32-wide k-block: max(MMA time 2*nt cycles, bytes one SM must take in / 64 B per cycle).
+// Measured (profiles/): the fp32-sized operands make the mainloop SM-ingress-bound, and a multicast tile
+// still has to enter every SM that uses it, so clusters do not pay here; they stay available (force_cluster
+// = 2, AVI_TC_CLUSTER=2) and tested, and are what a cta_group::2 version would build on.
+int32_t avi_tc_plan(avi_ctx* ctx, int64_t Ma, int64_t Nb, int64_t K, bool split_k, int force_cluster, TcParams* p) {
+    const int sms = ctx->prop.multiProcessorCount;
+    p->Ma = (int)Ma; p->Nb = (int)Nb;
+    p->n_ablk = (int)ceil_div(Ma, BM);
+    p->n_kblk = (int)ceil_div(K, BK);
+    double best = 1e300;
+    const int nt_hi = (int)std::min<int64_t>(256, round_up(Nb, 16));
+    for (int ca = 1; ca <= 8; ca *= 2) {
+        if (ca > 1 && ca > p->n_ablk) break;
+        for (int cb = 1; ca * cb <= 8; cb *= 2) {
+            const int csz = ca * cb;
+            if (force_cluster == 0 && csz > 1) continue;
+            const int maxc = max_active_clusters(ctx, csz);
+            if (maxc <= 0) continue;
+            for (int nt = split_k ? nt_hi : 16; nt <= nt_hi; nt += 16) {
+                if (nt % (8 * ca)) continue;
+                const int n_bchunk = (int)ceil_div(Nb, nt);
+                if (cb > 1 && cb > n_bchunk) continue;
+                const int64_t tiles = ceil_div(p->n_ablk, ca) * ceil_div(n_bchunk, cb);
+                int n_ksplit = 1, kbps = p->n_kblk;
+                if (split_k) {
+                    int want = (int)std::max<int64_t>(1, maxc / tiles);
+                    want = std::min(want, p->n_kblk);
+                    kbps = (int)ceil_div(p->n_kblk, want);
+                    n_ksplit = (int)ceil_div(p->n_kblk, kbps);
+                }
+                const int64_t units = tiles * n_ksplit;
+                const int64_t waves = ceil_div(units, maxc);
+                const double bytes_sm = (double)A_TILE_BYTES + nt * BK * 4.0;
+                const double per_kb = std::max(2.0 * nt, bytes_sm / 64.0) + 20.0;
+                double cost = (double)waves * (per_kb * kbps + 6000.0) + (csz > 1 ? 500.0 : 0.0);
+                if (force_cluster == 2 && csz > 1) cost *= 0.25;   // testing / experiments: prefer clusters
+                if (cost < best) {
+                    best = cost;
+                    p->ca = ca; p->cb = cb; p->nt = nt; p->n_bchunk = n_bchunk; p->n_ksplit = n_ksplit;
+                    p->kb_per_split = kbps;
+                }
+            }
+        }
     }
-    return best;
+    if (best >= 1e300) AVI_FAIL(ctx, AVI_ERR_INVALID, "no valid tiling");
+    if (getenv("AVI_TC_DEBUG"))
+        fprintf(stderr, "[avi_tc_plan] Ma=%lld Nb=%lld K=%lld split_k=%d -> ca=%d cb=%d nt=%d n_ablk=%d n_bchunk=%d n_ksplit=%d kbps=%d "
+                "maxc(1,2,4,8)=%d,%d,%d,%d cost=%.0f\n", (long long)Ma, (long long)Nb, (long long)K, (int)split_k, p->ca, p->cb, p->nt,
+                p->n_ablk, p->n_bchunk, p->n_ksplit, p->kb_per_split, max_active_clusters(ctx, 1), max_active_clusters(ctx, 2),
+                max_active_clusters(ctx, 4), max_active_clusters(ctx, 8), best);
+    (void)sms;
+    return AVI_OK;
 }
 
 int32_t avi_tc_launch(avi_ctx* ctx, int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p_in) {
     TcParams p = p_in;
-    if (p.nt % 16 || p.nt < 16 || p.nt > 256) AVI_FAIL(ctx, AVI_ERR_INVALID, "bad b-chunk width");
-    const int units = p.n_ablk * p.n_bchunk * p.n_ksplit;
+    if (p.nt % 16 || p.nt < 16 || p.nt > 256 || p.ca < 1 || p.cb < 1 || p.ca * p.cb > 8 || p.nt % (8 * p.ca))
+        AVI_FAIL(ctx, AVI_ERR_INVALID, "bad tiling");
+    const int csz = p.ca * p.cb;
+    const int64_t units = ceil_div(p.n_ablk, p.ca) * ceil_div(p.n_bchunk, p.cb) * p.n_ksplit;
     if (units <= 0) return AVI_OK;
-    // as many pipeline stages as fit: the contraction is bound by bytes in flight per SM
-    const int stage_bytes = A_TILE_BYTES + p.nt * BK * 4;
-    p.stages = std::min(MAX_STAGES, (SMEM_LIMIT - 1024 - (int)sizeof(SmemCtl)) / stage_bytes);
-    const int smem = p.stages * stage_bytes + 1024 + (int)sizeof(SmemCtl);
-    static bool attr_done = false;
-    if (!attr_done) {
-        AVI_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tc<EPI_GLM_FWD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-        AVI_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tc<EPI_GLM_FWD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-        AVI_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tc<EPI_GLM_BWD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-        AVI_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tc<EPI_STORE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-        attr_done = true;
-    }
-    const unsigned grid = (unsigned)std::min(units, ctx->prop.multiProcessorCount);
+    AVI_CHECK(set_attrs(ctx));
+    const int smem = smem_bytes_for(p.nt, &p.stages);   // as many stages as fit: bytes in flight per SM
+    const int maxc = max_active_clusters(ctx, csz);
+    if (maxc <= 0) AVI_FAIL(ctx, AVI_ERR_CUDA, "cluster size not launchable");
+    const unsigned grid = (unsigned)(std::min<int64_t>(units, maxc) * csz);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = csz; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = csz > 1 ? 1 : 0;
     AviTimed timed(ctx, epi == EPI_GLM_FWD ? "glm_fwd" : epi == EPI_GLM_BWD ? "glm_bwd" : "gemm_store");
-    if (epi == EPI_GLM_FWD && p.likelihood == AVI_GLM_BERNOULLI_LOGIT)
-        k_gemm_tc<EPI_GLM_FWD, 0><<<grid, NUM_THREADS, smem, ctx->stream>>>(tmA, tmB, p);
-    else if (epi == EPI_GLM_FWD)
-        k_gemm_tc<EPI_GLM_FWD, 1><<<grid, NUM_THREADS, smem, ctx->stream>>>(tmA, tmB, p);
-    else if (epi == EPI_GLM_BWD)
-        k_gemm_tc<EPI_GLM_BWD, 0><<<grid, NUM_THREADS, smem, ctx->stream>>>(tmA, tmB, p);
-    else
-        k_gemm_tc<EPI_STORE, 0><<<grid, NUM_THREADS, smem, ctx->stream>>>(tmA, tmB, p);
+    cudaError_t e;
+    if (epi == EPI_GLM_FWD && p.likelihood == AVI_GLM_BERNOULLI_LOGIT) e = cudaLaunchKernelEx(&cfg, k_gemm_tc<EPI_GLM_FWD, 0>, tmA, tmB, p);
+    else if (epi == EPI_GLM_FWD) e = cudaLaunchKernelEx(&cfg, k_gemm_tc<EPI_GLM_FWD, 1>, tmA, tmB, p);
+    else if (epi == EPI_GLM_BWD) e = cudaLaunchKernelEx(&cfg, k_gemm_tc<EPI_GLM_BWD, 0>, tmA, tmB, p);
+    else e = cudaLaunchKernelEx(&cfg, k_gemm_tc<EPI_STORE, 0>, tmA, tmB, p);
+    if (e != cudaSuccess) AVI_FAIL(ctx, AVI_ERR_CUDA, std::string("tcgen05 kernel launch: ") + cudaGetErrorString(e));
     AVI_LAUNCHED(ctx);
     return AVI_OK;
 }

@@ -14,6 +14,7 @@ struct TcParams {
     int n_ablk, n_bchunk, n_ksplit;
     int n_kblk, kb_per_split;
     int nt;
+    int ca, cb;          // cluster shape: ca a-blocks x cb b-chunks share operands by TMA multicast
     int stages;          // filled by avi_tc_launch
     // epilogue operands
     float* C;            // FWD: R [a][ldc];  STORE: slabs [ks][b * ldc + a]
@@ -31,5 +32,6 @@ struct TcParams {
 
 int32_t avi_tc_make_tmap(avi_ctx* ctx, CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld,
                          int box_rows);
-int avi_tc_pick_nt(int64_t Nb, int n_ablk, int n_ksplit, int sms, int nt_max);
+// fills Ma, Nb, n_ablk, n_kblk, nt, n_bchunk, n_ksplit, kb_per_split, ca, cb.  force_cluster: 0 = never cluster
+int32_t avi_tc_plan(avi_ctx* ctx, int64_t Ma, int64_t Nb, int64_t K, bool split_k, int force_cluster, TcParams* p);
 int32_t avi_tc_launch(avi_ctx* ctx, int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p);

@@ -10,6 +10,7 @@
 // contraction) and Xc [d][nP] (rows contiguous, backward contraction).  In the TF32 modes the
 // stored X is rounded to TF32 once (round-to-nearest) so the tensor-core reads are exact.
 #include <cmath>
+#include <cstdlib>
 
 #include "avi_internal.cuh"
 #include "device_utils.cuh"
@@ -70,7 +71,7 @@ k_glm_post_sums(const float* __restrict__ Z, const float* __restrict__ E, int ld
                 int nslab, int ldslab, const float* __restrict__ llpart, int nparts, int ldpart, float w,
                 int ncoordblk, float* __restrict__ a1, float* __restrict__ a2, float* __restrict__ logp) {
     __shared__ float sm[4][32][33];
-    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     if ((int)blockIdx.x >= ncoordblk) {
         const int m = (blockIdx.x - ncoordblk) * 32 + tx;
         float s = 0.f;
@@ -84,30 +85,30 @@ k_glm_post_sums(const float* __restrict__ Z, const float* __restrict__ E, int ld
             for (int r = 0; r < 32; ++r) t += sm[0][r][tx];
             logp[m] = fmaf(w, t, pre[m].x);
         }
-        return;
-    }
-    const int i = blockIdx.x * 32 + tx;
-    float t1 = 0.f, t2 = 0.f, p1 = 0.f, p2 = 0.f;
-    if (i <= d) {
-        for (int m = ty; m < M; m += 32) {
-            const float4 pm = pre[m];
-            const float e = E[(size_t)m * ld + i];
-            const float g = i < d ? -Z[(size_t)m * ld + i] * pm.y : pm.z;
-            t1 += g; t2 = fmaf(g, e, t2);
-        }
-        if (i < d)
-            for (int q = ty; q < nslab; q += 32) {
-                p1 += a1p[(size_t)q * ldslab + i];
-                p2 += a2p[(size_t)q * ldslab + i];
+    } else {
+        const int i = blockIdx.x * 32 + tx;
+        float t1 = 0.f, t2 = 0.f, p1 = 0.f, p2 = 0.f;
+        if (i <= d) {
+            for (int m = ty; m < M; m += 32) {
+                const float4 pm = pre[m];
+                const float e = E[(size_t)m * ld + i];
+                const float g = i < d ? -Z[(size_t)m * ld + i] * pm.y : pm.z;
+                t1 += g; t2 = fmaf(g, e, t2);
             }
-    }
-    sm[0][ty][tx] = t1; sm[1][ty][tx] = t2; sm[2][ty][tx] = p1; sm[3][ty][tx] = p2;
-    __syncthreads();
-    if (ty < 2 && i <= d) {
-        float s = 0.f, ps = 0.f;
+            if (i < d)
+                for (int q = ty; q < nslab; q += 32) {
+                    p1 += a1p[(size_t)q * ldslab + i];
+                    p2 += a2p[(size_t)q * ldslab + i];
+                }
+        }
+        sm[0][ty][tx] = t1; sm[1][ty][tx] = t2; sm[2][ty][tx] = p1; sm[3][ty][tx] = p2;
+        __syncthreads();
+        if (ty < 2 && i <= d) {
+            float s = 0.f, ps = 0.f;
 #pragma unroll
-        for (int r = 0; r < 32; ++r) { s += sm[ty][r][tx]; ps += sm[ty + 2][r][tx]; }
-        (ty == 0 ? a1 : a2)[i] = s + ps;
+            for (int r = 0; r < 32; ++r) { s += sm[ty][r][tx]; ps += sm[ty + 2][r][tx]; }
+            (ty == 0 ? a1 : a2)[i] = s + ps;
+        }
     }
 }
 
@@ -211,6 +212,7 @@ struct Glm : avi_model {
         avi_free(slabs); avi_free(pre);
     }
     bool hooked = false;
+    int cluster_mode = 1;   // 0: never use thread-block clusters (AVI_TC_CLUSTER=0), 1: planner decides
     bool tc_mode() const { return mode != AVI_GEMM_SIMT_FP32; }
     bool sample_hook(int ld, int M, SampleHook* h) override {
         if (M <= 0 || ensure(M, ld) != AVI_OK) return false;
@@ -265,34 +267,22 @@ struct Glm : avi_model {
             return AVI_OK;
         }
         TcParams p{};
-        p.Ma = M; p.Nb = (int)n_act;
-        p.n_ablk = (int)ceil_div(M, 128);
-        p.nt = avi_tc_pick_nt(n_act, p.n_ablk, 1, ctx->prop.multiProcessorCount, 256);
-        p.n_bchunk = (int)ceil_div(n_act, p.nt);
-        p.n_ksplit = 1; p.n_kblk = (int)ceil_div(d, 32); p.kb_per_split = p.n_kblk;
+        AVI_CHECK(avi_tc_plan(ctx, M, n_act, d, false, cluster_mode, &p));
         p.C = R; p.ldc = (int)ldR; p.y = y; p.w = w; p.likelihood = likelihood;
         AVI_CHECK(ensure_buf(&llpart, &llpart_cap, (long long)p.n_bchunk * 4 * capM));
         p.part1 = llpart; p.ldpart = capM;
         CUtensorMap tmA, tmB;
-        AVI_CHECK(avi_tc_make_tmap(ctx, &tmA, Zt, M, d, ld, 128));
-        AVI_CHECK(avi_tc_make_tmap(ctx, &tmB, Xr, n_act, d, dK, p.nt));
+        AVI_CHECK(avi_tc_make_tmap(ctx, &tmA, Zt, M, d, ld, 128 / p.cb));
+        AVI_CHECK(avi_tc_make_tmap(ctx, &tmB, Xr, n_act, d, dK, p.nt / p.ca));
         AVI_CHECK(avi_tc_launch(ctx, EPI_GLM_FWD, tmA, tmB, p));
         *nparts = p.n_bchunk * 4;
         return AVI_OK;
     }
 
     int32_t backward_setup(int M, TcParams* p, CUtensorMap* tmA, CUtensorMap* tmB) {
-        p->Ma = d; p->Nb = M;
-        p->n_ablk = (int)ceil_div(d, 128);
-        p->nt = (int)std::min<int64_t>(256, round_up(M, 16));
-        p->n_bchunk = (int)ceil_div(M, p->nt);
-        p->n_kblk = (int)ceil_div(n_act, 32);
-        int want = std::max(1, ctx->prop.multiProcessorCount / (p->n_ablk * p->n_bchunk));
-        want = std::min(want, p->n_kblk);
-        p->kb_per_split = (int)ceil_div(p->n_kblk, want);
-        p->n_ksplit = (int)ceil_div(p->n_kblk, p->kb_per_split);
-        AVI_CHECK(avi_tc_make_tmap(ctx, tmA, Xc, d, n_act, nP, 128));
-        AVI_CHECK(avi_tc_make_tmap(ctx, tmB, R, M, n_act, ldR, p->nt));
+        AVI_CHECK(avi_tc_plan(ctx, d, M, n_act, true, cluster_mode, p));
+        AVI_CHECK(avi_tc_make_tmap(ctx, tmA, Xc, d, n_act, nP, 128 / p->cb));
+        AVI_CHECK(avi_tc_make_tmap(ctx, tmB, R, M, n_act, ldR, p->nt / p->ca));
         return AVI_OK;
     }
 
@@ -339,8 +329,8 @@ struct Glm : avi_model {
         AVI_CHECK(avi_tc_launch(ctx, EPI_GLM_BWD, tmA, tmB, p));
         const int ncb = (int)ceil_div(d + 1, 32);
         const unsigned grid = (unsigned)(ncb + ceil_div(M, 32));
-        k_glm_post_sums<<<grid, dim3(32, 32), 0, ctx->stream>>>(Z, E, ld, M, d, pre, a1p, a2p, nslab, ldslab, llpart,
-                                                                nparts, capM, likeadj(), ncb, a1, a2, logp);
+        k_glm_post_sums<<<grid, 1024, 0, ctx->stream>>>(Z, E, ld, M, d, pre, a1p, a2p, nslab, ldslab, llpart, nparts,
+                                                        capM, likeadj(), ncb, a1, a2, logp);
         AVI_LAUNCHED(ctx);
         return AVI_OK;
     }
@@ -405,6 +395,7 @@ int32_t avi_model_glm_make(avi_ctx* ctx, const float* X, const float* y, int64_t
     g->d = d; g->dK = (int)round_up(d, 4);
     g->n_full = n; g->nP_full = round_up(n, 32); g->n_data = n_data; g->rows_global = n;
     g->likelihood = likelihood; g->variant = variant; g->mode = gemm_mode;
+    if (const char* e = getenv("AVI_TC_CLUSTER")) g->cluster_mode = atoi(e);
     float* tmp = nullptr;
     int32_t rc = avi_alloc(ctx, &g->Xr_full, (size_t)n * g->dK);
     if (rc == AVI_OK) rc = avi_alloc(ctx, &g->Xc_full, (size_t)d * g->nP_full);

@@ -12,20 +12,9 @@
 #include "avi_internal.cuh"
 #include "device_utils.cuh"
 #include "mf_finalize.cuh"
+#include "mf_tail.cuh"
 
 namespace {
-
-// scalar state sc[]: 0 averaging t | 1 DoG v | 2 DoG r | 3 beta1^t | 4 beta2^t | 5 last step size
-enum { SC_T = 0, SC_V = 1, SC_R = 2, SC_B1T = 3, SC_B2T = 4, SC_ETA = 5, SC_N = 16 };
-
-struct UpdArgs {
-    int rule, op, averager;
-    float h0, h1, h2, h3;   // rule hyper-parameters
-    float op_param, avg_param;
-    int D, fullrank;
-    long long P;
-    int nparts;             // DoG/DoWG: number of partial norms
-};
 
 // DoG / DoWG partial norms: part[2b] = sum (x - x0)^2, part[2b+1] = sum g^2 over the CTA's slice
 __global__ void __launch_bounds__(256)
@@ -120,124 +109,10 @@ k_update(float* __restrict__ lam, const float* __restrict__ grad, float* __restr
     }
 }
 
-// Mean-field tail of one iteration in ONE launch (single CTA): finalize (sums -> gradient, value, elbo)
-// + finiteness check + rule + operator + averager + commit of the scalar state / trace / step counter.
-// Thread t owns coordinates t, t + 1024, ... (ITEMS of them): everything it needs is fetched up front
-// in one batch of independent loads, so the kernel pays the L2 latency once.
 template <int ITEMS>
 __global__ void __launch_bounds__(1024)
-k_mf_finalize_update(const float* __restrict__ acc, int accv, int M, int objective, int entropy,
-                     const float* __restrict__ logp, const float* __restrict__ esq, int Mloc, int deferred,
-                     float* __restrict__ lam, float* __restrict__ grad, float* __restrict__ m1,
-                     float* __restrict__ m2, float* __restrict__ avg, float* __restrict__ sc, float* __restrict__ out,
-                     ObjDeviceState* __restrict__ st, float* __restrict__ trace, int trace_cap, UpdArgs a) {
-    __shared__ float sm[33];
-    const int D = a.D;
-    const bool stl = entropy == AVI_ENT_STL || entropy == AVI_ENT_STL_ZEROGRAD;
-    const bool need23 = objective == AVI_SCOREGRAD || stl;
-    const bool adam = a.rule == AVI_RULE_ADAM, dog = a.rule == AVI_RULE_DOG || a.rule == AVI_RULE_DOWG;
-    const bool polyavg = a.averager == AVI_AVG_POLYNOMIAL;
-    float v[ITEMS][4], x[ITEMS][2], s1m[ITEMS][2], s2m[ITEMS][2], av[ITEMS][2];
-#pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-        const int i = threadIdx.x + k * 1024;
-        const bool ok = i < D;
-        v[k][0] = ok ? acc[i] : 0.f;
-        v[k][1] = ok ? acc[accv + i] : 0.f;
-        v[k][2] = ok && need23 ? acc[2 * (size_t)accv + i] : 0.f;
-        v[k][3] = ok && need23 ? acc[3 * (size_t)accv + i] : 0.f;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const size_t p = (size_t)h * D + i;
-            x[k][h] = ok ? lam[p] : 1.0f;
-            s1m[k][h] = ok && (adam || dog) ? m1[p] : 0.f;
-            s2m[k][h] = ok && adam ? m2[p] : 0.f;
-            av[k][h] = ok && polyavg ? avg[p] : 0.f;
-        }
-    }
-    float sl = 0.f, sq = 0.f;
-    if (deferred)
-        for (int m = threadIdx.x; m < Mloc; m += 1024) { sl += logp[m]; sq += esq[m]; }
-    const float* scal = acc + 4 * (size_t)accv;
-    const float c0 = scal[0], c1 = scal[1], c2 = scal[2], c3 = scal[3];
-    const float shift = out[3];
-    const int halted = st->halted;
-    const float b1t = sc[SC_B1T], b2t = sc[SC_B2T], t_avg = sc[SC_T], v_old = sc[SC_V], r_old = sc[SC_R];
-
-    MfSums S;
-    float part = 0.f;
-#pragma unroll
-    for (int k = 0; k < ITEMS; ++k) part += (threadIdx.x + k * 1024 < D) ? logf(x[k][1]) : 0.f;
-    S.logdet = block_sum(part, sm);
-    if (deferred) { S.s0 = block_sum(sl, sm); S.s1 = block_sum(sq, sm); S.s2 = 0.f; S.s3 = 0.f; }
-    else { S.s0 = c0; S.s1 = c1; S.s2 = c2; S.s3 = c3; }
-    float value, elbo, shift_next;
-    mf_outputs(D, M, objective, entropy, S, shift, value, elbo, shift_next);
-    const bool bad = !isfinite(value);
-
-    float g[ITEMS][2];
-    float dx2 = 0.f, g2 = 0.f;
-#pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-        const int i = threadIdx.x + k * 1024;
-        mf_grad_vals(v[k][0], v[k][1], v[k][2], v[k][3], x[k][1], M, objective, entropy, S, g[k][0], g[k][1]);
-        if (i < D) {
-            grad[i] = g[k][0]; grad[D + i] = g[k][1];
-            if (dog) {
-                const float d0 = x[k][0] - s1m[k][0], d1 = x[k][1] - s1m[k][1];
-                dx2 = fmaf(d0, d0, fmaf(d1, d1, dx2));
-                g2 = fmaf(g[k][0], g[k][0], fmaf(g[k][1], g[k][1], g2));
-            }
-        }
-    }
-    float eta = a.rule == AVI_RULE_DESCENT ? a.h0 : 0.f, v_new = 0.f, r_new = 0.f;
-    if (dog) {
-        dx2 = block_sum(dx2, sm); g2 = block_sum(g2, sm);
-        r_new = fmaxf(sqrtf(dx2), r_old);
-        if (a.rule == AVI_RULE_DOG) { v_new = v_old + g2; eta = r_new / sqrtf(v_new); }
-        else { const float r2 = r_new * r_new; v_new = v_old + r2 * g2; eta = r2 / sqrtf(v_new); }
-    }
-    if (!halted && !bad) {
-        const float w = (a.avg_param + 1.0f) / (t_avg + a.avg_param);
-#pragma unroll
-        for (int k = 0; k < ITEMS; ++k) {
-            const int i = threadIdx.x + k * 1024;
-            if (i >= D) continue;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const size_t p = (size_t)h * D + i;
-                float xx = x[k][h], dx;
-                if (adam) {
-                    const float mt = a.h1 * s1m[k][h] + (1.0f - a.h1) * g[k][h];
-                    const float vt = a.h2 * s2m[k][h] + (1.0f - a.h2) * g[k][h] * g[k][h];
-                    m1[p] = mt; m2[p] = vt;
-                    dx = mt / (1.0f - b1t) / (sqrtf(vt / (1.0f - b2t)) + a.h3) * a.h0;
-                } else {
-                    dx = eta * g[k][h];
-                }
-                xx -= dx;
-                if (h == 1 && a.op != AVI_OP_IDENTITY) {
-                    if (a.op == AVI_OP_CLIPSCALE) xx = fmaxf(xx, a.op_param);
-                    else xx = xx + (sqrtf(fmaf(xx, xx, 4.0f * eta)) - xx) * 0.5f;
-                }
-                lam[p] = xx;
-                if (polyavg) avg[p] = (1.0f - w) * av[k][h] + w * xx;
-            }
-        }
-    }
-    if (threadIdx.x == 0 && !halted) {
-        out[0] = value; out[1] = elbo; out[2] = S.logdet; out[3] = shift_next;
-        const int tp = st->trace_pos;
-        if (tp < trace_cap) { trace[2 * tp] = value; trace[2 * tp + 1] = elbo; }
-        st->trace_pos = tp + 1;
-        if (bad) { st->halted = 1; return; }
-        sc[SC_T] = t_avg + 1.0f;
-        sc[SC_ETA] = eta;
-        if (adam) { sc[SC_B1T] = b1t * a.h1; sc[SC_B2T] = b2t * a.h2; }
-        if (dog) { sc[SC_V] = v_new; sc[SC_R] = r_new; }
-        st->step += 1ull;
-        st->batch_cursor += 1;
-    }
+k_mf_finalize_update(MfTailArgs t) {
+    mf_finalize_update_body<ITEMS>(t);
 }
 
 __global__ void k_commit(float* __restrict__ sc, const float* __restrict__ out, ObjDeviceState* __restrict__ st,
@@ -283,15 +158,18 @@ int32_t enqueue_iteration(avi_opt* op, bool subsampled, int64_t batch) {
     avi_obj* o = op->obj;
     avi_ctx* ctx = op->ctx;
     if (subsampled) AVI_CHECK(o->model->subsample_dev(op->idx_dev, batch, o->d_state));
-    AVI_CHECK(avi_objective_local(o, op->lam));
     UpdArgs a = make_args(op);
+    MfTailArgs tail{};
+    tail.acc = o->acc; tail.accv = o->accv; tail.M = o->M; tail.objective = o->objective; tail.entropy = o->entropy;
+    tail.logp = o->logp; tail.esq = o->esq; tail.Mloc = o->Mloc; tail.deferred = avi_obj_defers_scalars(o) ? 1 : 0;
+    tail.lam = op->lam; tail.grad = o->grad; tail.m1 = op->m1; tail.m2 = op->m2; tail.avg = op->avg; tail.sc = op->sc;
+    tail.out = o->out; tail.st = o->d_state; tail.trace = op->trace; tail.trace_cap = op->trace_cap; tail.a = a;
+    AVI_CHECK(avi_objective_local(o, op->lam));
+    // (running this tail inside the last CTA of the target's final kernel was measured SLOWER than its own
+    // launch: profiles/README.md)
     if (o->family == AVI_MEANFIELD && o->D <= 8 * 1024) {
         const int items = (int)ceil_div(o->D, 1024);
-#define LAUNCH_TAIL(IT)                                                                                          \
-    k_mf_finalize_update<IT><<<1, 1024, 0, ctx->stream>>>(o->acc, o->accv, o->M, o->objective, o->entropy, o->logp, \
-                                                          o->esq, o->Mloc, avi_obj_defers_scalars(o) ? 1 : 0, op->lam, \
-                                                          o->grad, op->m1, op->m2, op->avg, op->sc, o->out,      \
-                                                          o->d_state, op->trace, op->trace_cap, a)
+#define LAUNCH_TAIL(IT) k_mf_finalize_update<IT><<<1, 1024, 0, ctx->stream>>>(tail)
         if (items <= 1) LAUNCH_TAIL(1);
         else if (items <= 2) LAUNCH_TAIL(2);
         else if (items <= 4) LAUNCH_TAIL(4);
