@@ -398,7 +398,7 @@ int32_t avi_obj_estimate_objective(avi_obj* o, const float* lambda_host, int64_t
     cudaSetDevice(ctx->device);
     std::memcpy(o->h_lambda, lambda_host, (size_t)P * sizeof(float));
     AVI_CUDA(ctx, cudaMemcpyAsync(o->d_lambda, o->h_lambda, (size_t)P * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    const int chunk = std::max(o->cap_M, std::min(n_samples, 8192));
+    const int chunk = std::max(o->cap_M, std::min(n_samples, 32768));
     AVI_CHECK(avi_obj_ensure_capacity(o, std::min(chunk, n_samples)));
     ObjDeviceState ov{};
     ov.key = key; ov.step = 0;

@@ -242,7 +242,7 @@ bool avi_obj_defers_scalars(const avi_obj* o);                                  
 // a < Ma, b < Nb, k < K; bounds-checked.
 int32_t avi_gemm_simt(avi_ctx* ctx, const float* A, long long sa_r, long long sa_k, const float* B,
                       long long sb_r, long long sb_k, float* C, long long sc_r, long long sc_c, int Ma,
-                      int Nb, int K, float alpha);
+                      int Nb, int K, float alpha, int tri_b = 0);
 // U = L^{-T} E for a column-major lower-triangular L (D x D): row m of U solves L' u = e_m.
 int32_t avi_trsm_lt(avi_ctx* ctx, const float* L, int D, const float* E, float* U, int ld, int M);
 

@@ -33,6 +33,26 @@ __device__ __forceinline__ float uniform23(uint32_t x) {
     return ((float)(x >> 9) + 0.5f) * 1.1920928955078125e-07f;   // 2^-23
 }
 
+// Box-Muller pair from two uniforms in (0,1), on the SFU pipes (MUFU lg2 / rsq / sin / cos) so that the
+// sampling kernel stays HBM-bound.  ln(u) loses absolute accuracy through cancellation as u -> 1
+// (lg2.approx has a fixed absolute error), so that range uses the series of ln(1 + t), t = u - 1.
+// Accuracy vs the fp64 oracle: |d eps| < 3e-6 (tests/test_gpu_parity.py::test_rand_matches_oracle).
+__device__ __forceinline__ void box_muller_fast(float u0, float u1, float& n0, float& n1) {
+    float ln_u;
+    if (u0 > 0.875f) {
+        const float t = u0 - 1.0f;   // exact
+        ln_u = t * (1.0f + t * (-0.5f + t * (0.33333334f + t * (-0.25f + t * (0.2f + t * (-0.16666667f +
+               t * (0.14285715f + t * (-0.125f))))))));
+    } else {
+        ln_u = 0.6931471805599453f * __log2f(u0);
+    }
+    const float r = sqrtf(-2.0f * ln_u);
+    // angle 2 pi u1 folded into (-pi, pi] where sin.approx / cos.approx are most accurate
+    const float th = 6.283185307179586f * (u1 - (u1 > 0.5f ? 1.0f : 0.0f));
+    n0 = r * __cosf(th);
+    n1 = r * __sinf(th);
+}
+
 // four standard normals for coordinates 4q .. 4q+3 of Monte-Carlo sample m at step `step`
 __device__ __forceinline__ float4 normal4(uint32_t q, uint32_t m, unsigned long long step, uint32_t stream,
                                           unsigned long long key) {
@@ -40,14 +60,8 @@ __device__ __forceinline__ float4 normal4(uint32_t q, uint32_t m, unsigned long 
     philox4x32_10(q, m, (uint32_t)step, (stream & 0xFFu) | ((uint32_t)((step >> 32) & 0xFFFFFFu) << 8),
                   (uint32_t)key, (uint32_t)(key >> 32), x);
     float4 e;
-    float r0 = sqrtf(-2.0f * logf(uniform23(x[0])));
-    float s0, c0;
-    sincospif(2.0f * uniform23(x[1]), &s0, &c0);
-    e.x = r0 * c0; e.y = r0 * s0;
-    float r1 = sqrtf(-2.0f * logf(uniform23(x[2])));
-    float s1, c1;
-    sincospif(2.0f * uniform23(x[3]), &s1, &c1);
-    e.z = r1 * c1; e.w = r1 * s1;
+    box_muller_fast(uniform23(x[0]), uniform23(x[1]), e.x, e.y);
+    box_muller_fast(uniform23(x[2]), uniform23(x[3]), e.z, e.w);
     return e;
 }
 

@@ -21,31 +21,48 @@
 namespace {
 
 // ------------------------------------------------------------------------------------------
-// K1: one CTA per Monte-Carlo sample; thread t owns coordinates 4q..4q+3 (one Philox block).
-// Writes Z = mu + s .* eps (mean-field), E = eps (both zero in the padding columns i >= D) and
-// |eps_m|^2.  FULLRANK writes only E (Z = L * eps + mu comes from k_fr_affine).
-template <bool FULLRANK, bool HOOK>
-__global__ void __launch_bounds__(256)
-k_sample(const float* __restrict__ lambda, int D, int ld, int m0, const ObjDeviceState* __restrict__ st,
+// K1: one WARP per Monte-Carlo sample; lane l owns the coordinate quads l, l + 32, ... (one Philox block
+// each; a warp instruction moves 512 contiguous bytes).  Writes Z = mu + s .* eps (mean-field), E = eps
+// (both zero in the padding columns i >= D) and |eps_m|^2 (fixed shuffle tree: no block barrier, no
+// atomics).  FULLRANK writes only E (Z = L * eps + mu comes from k_fr_affine).  HOOK: SampleHook.
+// SPLIT = warps cooperating on one sample: 1 for large M (no barrier at all), SAMPLE_WARPS for small M
+// (latency: the row is spread over the whole CTA, partial sums combined in a fixed order through smem).
+constexpr int SAMPLE_WARPS = 4;
+template <bool FULLRANK, bool HOOK, int SPLIT>
+__global__ void __launch_bounds__(32 * SAMPLE_WARPS)
+k_sample(const float* __restrict__ lambda, int D, int ld, int m0, int Mloc, const ObjDeviceState* __restrict__ st,
          ObjDeviceState st_val, int use_val, uint32_t stream_id, float* __restrict__ Z,
          float* __restrict__ E, float* __restrict__ esq, SampleHook hk) {
-    __shared__ float sm[33];
-    __shared__ float s_eta;
     const unsigned long long step = use_val ? st_val.step : st->step;
     const unsigned long long key = use_val ? st_val.key : st->key;
-    const int m = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int m = SPLIT == 1 ? blockIdx.x * SAMPLE_WARPS + warp : blockIdx.x;
+    if (m >= Mloc) return;   // warp-uniform (SPLIT > 1: CTA-uniform)
     const float* mu = lambda;
     const float* sc = lambda + D;
-    float part = 0.0f, bsq = 0.0f;
-    for (int q = threadIdx.x; q < ld / 4; q += blockDim.x) {
+    float part = 0.0f, bsq = 0.0f, eta = 0.0f;
+    for (int q = SPLIT == 1 ? lane : threadIdx.x; q < ld / 4; q += 32 * SPLIT) {
         float4 e = normal4((uint32_t)q, (uint32_t)(m0 + m), step, stream_id, key);
         const int i = 4 * q;
         float ev[4] = {e.x, e.y, e.z, e.w}, zv[4], zt[4];
+        float mv[4] = {0.f, 0.f, 0.f, 0.f}, sv[4] = {0.f, 0.f, 0.f, 0.f};
+        if (!FULLRANK) {
+            if (i + 3 < D) {   // D + ... : lambda + D is only 4-byte aligned in general
+                const float4 m4 = *reinterpret_cast<const float4*>(mu + i);
+                mv[0] = m4.x; mv[1] = m4.y; mv[2] = m4.z; mv[3] = m4.w;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) sv[c] = __ldg(sc + i + c);
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (i + c < D) { mv[c] = __ldg(mu + i + c); sv[c] = __ldg(sc + i + c); }
+            }
+        }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             if (i + c < D) {
                 part = fmaf(ev[c], ev[c], part);
-                zv[c] = FULLRANK ? 0.0f : fmaf(__ldg(sc + i + c), ev[c], __ldg(mu + i + c));
+                zv[c] = FULLRANK ? 0.0f : fmaf(sv[c], ev[c], mv[c]);
             } else {
                 ev[c] = 0.0f; zv[c] = 0.0f;
             }
@@ -53,7 +70,7 @@ k_sample(const float* __restrict__ lambda, int D, int ld, int m0, const ObjDevic
                 const bool is_beta = i + c < hk.d;
                 bsq = is_beta ? fmaf(zv[c], zv[c], bsq) : bsq;
                 zt[c] = is_beta ? tc::round_tf32(zv[c]) : 0.0f;
-                if (i + c == hk.d) s_eta = zv[c];
+                if (i + c == hk.d) eta = zv[c];
             }
         }
         *reinterpret_cast<float4*>(E + (size_t)m * ld + i) = make_float4(ev[0], ev[1], ev[2], ev[3]);
@@ -62,55 +79,29 @@ k_sample(const float* __restrict__ lambda, int D, int ld, int m0, const ObjDevic
         if (HOOK && hk.Zt)
             *reinterpret_cast<float4*>(hk.Zt + (size_t)m * ld + i) = make_float4(zt[0], zt[1], zt[2], zt[3]);
     }
-    float tot = block_sum(part, sm);
-    if (HOOK) bsq = block_sum(bsq, sm);   // the barriers inside also publish s_eta
-    if (threadIdx.x == 0) {
+    float tot = warp_sum(part);
+    if (HOOK) { bsq = warp_sum(bsq); eta = warp_sum(eta); }   // eta is non-zero in exactly one lane
+    if (SPLIT > 1) {
+        __shared__ float sm[3][SAMPLE_WARPS];
+        if (lane == 0) { sm[0][warp] = tot; sm[1][warp] = bsq; sm[2][warp] = eta; }
+        __syncthreads();
+        tot = 0.f; bsq = 0.f; eta = 0.f;
+#pragma unroll
+        for (int w = 0; w < SAMPLE_WARPS; ++w) { tot += sm[0][w]; bsq += sm[1][w]; eta += sm[2][w]; }
+        if (warp != 0) return;
+    }
+    if (lane == 0) {
         esq[m] = tot;
-        if (HOOK) hk.pre[m] = glm_prior_terms(bsq, s_eta, hk.d, hk.variant, hk.include_prior);
+        if (HOOK) hk.pre[m] = glm_prior_terms(bsq, eta, hk.d, hk.variant, hk.include_prior);
     }
 }
 
-// full-rank affine map: Z[m][i] = mu[i] + sum_{j <= i} L[i + D*j] * E[m][j].
-// CTA = 64 coordinates x 16 samples; L tile and eps tile staged through shared memory.
-constexpr int FA_TI = 64, FA_TM = 16, FA_TK = 32;
-__global__ void __launch_bounds__(256)
-k_fr_affine(const float* __restrict__ lambda, int D, int ld, int Mloc, const float* __restrict__ E,
-            float* __restrict__ Z) {
-    __shared__ float Ls[FA_TK][FA_TI + 1];   // Ls[k][i] = L[i0 + i][k0 + k]
-    __shared__ float Es[FA_TM][FA_TK + 1];   // Es[m][k]
-    const float* L = lambda + D;
-    const int i0 = blockIdx.x * FA_TI, mb = blockIdx.y * FA_TM;
-    const int ti = threadIdx.x & 63, tm = threadIdx.x >> 6;   // thread: coordinate ti, samples tm*4..+3
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    const int kmax = min(D, i0 + FA_TI);   // lower triangular: j <= i
-    for (int k0 = 0; k0 < kmax; k0 += FA_TK) {
-        for (int e = threadIdx.x; e < FA_TK * FA_TI; e += 256) {
-            int i = e & 63, k = e >> 6;
-            int gi = i0 + i, gk = k0 + k;
-            Ls[k][i] = (gi < D && gk <= gi) ? __ldg(L + (size_t)gk * D + gi) : 0.0f;
-        }
-        for (int e = threadIdx.x; e < FA_TM * FA_TK; e += 256) {
-            int k = e & 31, mm = e >> 5;
-            int gm = mb + mm, gk = k0 + k;
-            Es[mm][k] = (gm < Mloc && gk < D) ? E[(size_t)gm * ld + gk] : 0.0f;
-        }
-        __syncthreads();
-#pragma unroll 8
-        for (int k = 0; k < FA_TK; ++k) {
-            float l = Ls[k][ti];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) acc[c] = fmaf(l, Es[tm * 4 + c][k], acc[c]);
-        }
-        __syncthreads();
-    }
-    const int gi = i0 + ti;
-    if (gi < ld) {
-        float mu = gi < D ? __ldg(lambda + gi) : 0.0f;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            int gm = mb + tm * 4 + c;
-            if (gm < Mloc) Z[(size_t)gm * ld + gi] = gi < D ? acc[c] + mu : 0.0f;
-        }
+// full-rank: Z[m][i] += mu[i] after the L * eps contraction; zero the padding columns
+__global__ void k_fr_add_mu(const float* __restrict__ lambda, int D, int ld, float* __restrict__ Z) {
+    const int m = blockIdx.x;
+    for (int i = threadIdx.x; i < ld; i += blockDim.x) {
+        float* p = Z + (size_t)m * ld + i;
+        *p = i < D ? *p + __ldg(lambda + i) : 0.0f;
     }
 }
 
@@ -326,19 +317,28 @@ int32_t avi_family_sample(avi_obj* o, const float* lambda, float* Z, float* E, f
     int use_val = 0;
     if (ov) { sv = *ov; use_val = 1; }
     AviTimed timed(ctx, "sample");
+    const bool split = Mloc <= 8192;   // small batches: spread each sample over the whole CTA
+    const unsigned sgrid = split ? (unsigned)Mloc : (unsigned)ceil_div(Mloc, SAMPLE_WARPS);
+#define LAUNCH_SAMPLE(FR, HK, HOOKV)                                                                                 \
+    do {                                                                                                             \
+        if (split) k_sample<FR, HK, SAMPLE_WARPS><<<sgrid, 32 * SAMPLE_WARPS, 0, ctx->stream>>>(                      \
+            lambda, o->D, o->ld, m0, Mloc, st, sv, use_val, AVI_STREAM_EPS, Z, E, esq, HOOKV);                        \
+        else k_sample<FR, HK, 1><<<sgrid, 32 * SAMPLE_WARPS, 0, ctx->stream>>>(                                       \
+            lambda, o->D, o->ld, m0, Mloc, st, sv, use_val, AVI_STREAM_EPS, Z, E, esq, HOOKV);                        \
+    } while (0)
     if (o->family == AVI_MEANFIELD) {
-        if (hook && hook->kind == 1)
-            k_sample<false, true><<<Mloc, 256, 0, ctx->stream>>>(lambda, o->D, o->ld, m0, st, sv, use_val, AVI_STREAM_EPS, Z, E, esq, *hook);
-        else
-            k_sample<false, false><<<Mloc, 256, 0, ctx->stream>>>(lambda, o->D, o->ld, m0, st, sv, use_val, AVI_STREAM_EPS, Z, E, esq, SampleHook{});
+        if (hook && hook->kind == 1) LAUNCH_SAMPLE(false, true, *hook);
+        else LAUNCH_SAMPLE(false, false, SampleHook{});
         AVI_LAUNCHED(ctx);
     } else {
-        k_sample<true, false><<<Mloc, 256, 0, ctx->stream>>>(lambda, o->D, o->ld, m0, st, sv, use_val, AVI_STREAM_EPS, Z, E, esq, SampleHook{});
+        LAUNCH_SAMPLE(true, false, SampleHook{});
         AVI_LAUNCHED(ctx);
-        dim3 grid((unsigned)ceil_div(o->ld, FA_TI), (unsigned)ceil_div(Mloc, FA_TM));
-        k_fr_affine<<<grid, 256, 0, ctx->stream>>>(lambda, o->D, o->ld, Mloc, E, Z);
+        // Z[m][i] = sum_{j <= i} E[m][j] * L[i + D*j]  (scale * eps, location_scale.jl:76)
+        AVI_CHECK(avi_gemm_simt(ctx, E, o->ld, 1, lambda + o->D, 1, o->D, Z, o->ld, 1, Mloc, o->D, o->D, 1.0f, 1));
+        k_fr_add_mu<<<Mloc, 256, 0, ctx->stream>>>(lambda, o->D, o->ld, Z);
         AVI_LAUNCHED(ctx);
     }
+#undef LAUNCH_SAMPLE
     return AVI_OK;
 }
 

@@ -12,10 +12,12 @@ __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const float* __restrict__ A, long long sa_r, long long sa_k,
                  const float* __restrict__ B, long long sb_r, long long sb_k,
                  float* __restrict__ C, long long sc_r, long long sc_c,
-                 int Ma, int Nb, int K, float alpha) {
+                 int Ma, int Nb, int K_in, float alpha, int tri_b) {
     __shared__ __align__(16) float As[TK][TM + 4];
     __shared__ __align__(16) float Bs[TK][TN + 4];
     const int tile_a = blockIdx.y * TM, tile_b = blockIdx.x * TN;
+    // tri_b: B[b][k] == 0 for k > b (lower-triangular L): the contraction stops at the tile's last row
+    const int K = tri_b ? min(K_in, tile_b + TN) : K_in;
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
     float acc[4][4];
 #pragma unroll
@@ -144,13 +146,13 @@ int32_t launch_trsm(avi_ctx* ctx, const float* L, int D, const float* E, float* 
 
 int32_t avi_gemm_simt(avi_ctx* ctx, const float* A, long long sa_r, long long sa_k, const float* B,
                       long long sb_r, long long sb_k, float* C, long long sc_r, long long sc_c, int Ma,
-                      int Nb, int K, float alpha) {
+                      int Nb, int K, float alpha, int tri_b) {
     if (Ma <= 0 || Nb <= 0 || K <= 0) return AVI_OK;
     dim3 grid((unsigned)ceil_div(Nb, TN), (unsigned)ceil_div(Ma, TM));
     bool ak = (sa_k == 1), bk = (sb_k == 1);
 #define LAUNCH(AK, BK)                                                                              \
     gemm_simt_kernel<AK, BK><<<grid, 256, 0, ctx->stream>>>(A, sa_r, sa_k, B, sb_r, sb_k, C, sc_r, \
-                                                            sc_c, Ma, Nb, K, alpha)
+                                                            sc_c, Ma, Nb, K, alpha, tri_b)
     if (ak && bk) LAUNCH(true, true);
     else if (ak) LAUNCH(true, false);
     else if (bk) LAUNCH(false, true);

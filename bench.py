@@ -266,6 +266,25 @@ def main():
         ms, cnt = ctx.kernel_time(name)
         ktime[name] = ms / max(cnt, 1)
 
+    # the sample+transform kernel at a bandwidth-relevant size (outputs >> 126 MB L2): same kernel, M = 32768
+    sample_large = None
+    if world == 1:
+        M_big = 32768
+        qb = avi.MeanFieldGaussian(np.zeros(D, np.float32), np.ones(D, np.float32))
+        pb = avi.MvNormalDiag(ctx, np.zeros(D, np.float32), np.ones(D, np.float32))
+        ob = avi.Objective(SEED, avi.RepGradELBO(8), qb, pb)
+        ob.estimate_objective(SEED, qb, M_big)                      # sizes the buffers (untimed)
+        ctx.timing(True)
+        for _ in range(5):
+            ob.estimate_objective(SEED, qb, M_big)
+        ctx.timing(False)
+        ms_b, cnt_b = ctx.kernel_time("sample")
+        ld = (D + 3) // 4 * 4
+        bytes_b = 4 * (2 * D + 2 * ld * M_big)                      # read mu, s; write Z and eps (materialised)
+        sample_large = {"M": M_big, "bytes_per_launch": bytes_b, "ms": ms_b / max(cnt_b, 1),
+                        "achieved_gbs": bytes_b / (ms_b / max(cnt_b, 1) * 1e-3) / 1e9 if ms_b > 0 else None}
+        ob.close(); pb.close()
+
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -287,7 +306,10 @@ def main():
                 "sample_kernel_hbm": {"bytes_per_launch": 4 * (2 * D + 2 * D * m_loc),
                                       "achieved_gbs": (4 * (2 * D + 2 * D * m_loc) / (ktime["sample"] * 1e-3) / 1e9)
                                       if ktime["sample"] > 0 else None,
-                                      "peak_gbs": hbm, "note": "1 MB launch: latency-bound at this shape (SURVEY F8)"}}
+                                      "peak_gbs": hbm, "note": "2 MB launch: latency-bound at this shape (SURVEY F8)",
+                                      "large_shape": dict(sample_large, frac=(sample_large["achieved_gbs"] / hbm
+                                                          if sample_large and sample_large["achieved_gbs"] else None))
+                                      if sample_large else None}}
 
     line = {
         "metric": "ELBO grad-steps/sec", "value": K / (cold_ms * 1e-3), "unit": "steps/s", "n_gpus": world,
