@@ -1,6 +1,7 @@
 // extern "C" entry points of libavi_b200.so (include/avi.h): lifecycle, targets, objective.
 // The fused step lives in opt.cu.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -40,6 +41,11 @@ void avi_ktime_mark(avi_ctx* ctx, const char* name) {
     cudaEventCreate(&e);
     cudaEventRecord(e, ctx->stream);
     t->ev.push_back(e);
+}
+
+bool avi_pdl_enabled() {
+    static const bool on = !(getenv("AVI_PDL") && atoi(getenv("AVI_PDL")) == 0);
+    return on;
 }
 
 static void ktime_fold(avi_ctx* ctx) {

@@ -82,6 +82,23 @@ struct AviTimed {
     ~AviTimed() { if (c->timing) avi_ktime_mark(c, n); }
 };
 
+// Launch with programmatic dependent launch (PDL): the grid may start while its predecessor on the stream is
+// still draining; the kernel must execute pdl_wait() (device_utils.cuh) before touching anything the
+// predecessor wrote, and pdl_trigger() lets ITS successor start early.  Inside a captured graph this becomes
+// a programmatic edge.  AVI_PDL=0 turns it off (plain stream order).
+bool avi_pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t avi_launch_pdl(avi_ctx* ctx, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                         Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = avi_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // device allocation with error plumbing (zero-filled)
 int32_t avi_dev_alloc(avi_ctx* ctx, void** p, size_t bytes);
 template <typename T>

@@ -65,6 +65,10 @@ __device__ __forceinline__ float4 normal4(uint32_t q, uint32_t m, unsigned long 
     return e;
 }
 
+// programmatic dependent launch (see avi_launch_pdl): no-ops when the grid was launched without the attribute
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

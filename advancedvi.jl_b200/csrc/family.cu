@@ -33,6 +33,8 @@ __global__ void __launch_bounds__(32 * SAMPLE_WARPS)
 k_sample(const float* __restrict__ lambda, int D, int ld, int m0, int Mloc, const ObjDeviceState* __restrict__ st,
          ObjDeviceState st_val, int use_val, uint32_t stream_id, float* __restrict__ Z,
          float* __restrict__ E, float* __restrict__ esq, SampleHook hk) {
+    pdl_trigger();
+    pdl_wait();   // lambda and the step counter come from the previous iteration's tail
     const unsigned long long step = use_val ? st_val.step : st->step;
     const unsigned long long key = use_val ? st_val.key : st->key;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -321,10 +323,10 @@ int32_t avi_family_sample(avi_obj* o, const float* lambda, float* Z, float* E, f
     const unsigned sgrid = split ? (unsigned)Mloc : (unsigned)ceil_div(Mloc, SAMPLE_WARPS);
 #define LAUNCH_SAMPLE(FR, HK, HOOKV)                                                                                 \
     do {                                                                                                             \
-        if (split) k_sample<FR, HK, SAMPLE_WARPS><<<sgrid, 32 * SAMPLE_WARPS, 0, ctx->stream>>>(                      \
-            lambda, o->D, o->ld, m0, Mloc, st, sv, use_val, AVI_STREAM_EPS, Z, E, esq, HOOKV);                        \
-        else k_sample<FR, HK, 1><<<sgrid, 32 * SAMPLE_WARPS, 0, ctx->stream>>>(                                       \
-            lambda, o->D, o->ld, m0, Mloc, st, sv, use_val, AVI_STREAM_EPS, Z, E, esq, HOOKV);                        \
+        if (split) avi_launch_pdl(ctx, k_sample<FR, HK, SAMPLE_WARPS>, dim3(sgrid), dim3(32 * SAMPLE_WARPS), 0,       \
+            lambda, o->D, o->ld, m0, Mloc, st, sv, use_val, (uint32_t)AVI_STREAM_EPS, Z, E, esq, HOOKV);              \
+        else avi_launch_pdl(ctx, k_sample<FR, HK, 1>, dim3(sgrid), dim3(32 * SAMPLE_WARPS), 0,                        \
+            lambda, o->D, o->ld, m0, Mloc, st, sv, use_val, (uint32_t)AVI_STREAM_EPS, Z, E, esq, HOOKV);              \
     } while (0)
     if (o->family == AVI_MEANFIELD) {
         if (hook && hook->kind == 1) LAUNCH_SAMPLE(false, true, *hook);

@@ -40,7 +40,120 @@ struct SmemCtl {
     float ys[2][256];
 };
 
+__device__ __forceinline__ unsigned long long gtime_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// phase timestamps (ns, %globaltimer) per CTA when TcParams.prof != nullptr:
+// 0 kernel entry | 1 prologue done | 2 first operands landed | 3 last MMA committed (issue side)
+// 4 accumulator ready (epilogue side) | 5 epilogue math done | 6 kernel exit
+#define TC_STAMP(slot, cond) do { if (p.prof && (cond)) p.prof[(size_t)blockIdx.x * 8 + (slot)] = gtime_ns(); } while (0)
+
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+
+// Epilogue of one work unit for one thread: waits for the accumulator stage, consumes the thread's TMEM
+// row (lane) over its column range and returns the per-thread partial sums.
+template <int EPI, int LIK>
+__device__ __forceinline__ void epilogue_unit(const TcParams& p, SmemCtl* ctl, int as, uint32_t aphase,
+                                              uint32_t tacc, int NT, int a, bool a_ok, int bc, int ks, int c_begin,
+                                              int c_end, int et, float& s1, float& s2) {
+    s1 = 0.0f; s2 = 0.0f;
+    if (EPI == EPI_GLM_FWD) {
+        int b = bc * NT + et;
+        if (et < NT) ctl->ys[as][et] = b < p.Nb ? __ldg(p.y + b) : 0.0f;
+        epi_bar_sync();
+    }
+    if (EPI == EPI_GLM_BWD) {
+        // eps[b][a] for this thread's columns, fetched while the MMAs are still running
+        const float* Ea = p.E + a;
+        float e[32];
+        bool waited = false;
+        for (int c = c_begin; c < c_end; c += 32) {
+            const int nc = min(32, c_end - c);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int b = bc * NT + c + j;
+                e[j] = (j < nc && a_ok && b < p.Nb) ? __ldg(Ea + (size_t)b * p.lde) : 0.0f;
+            }
+            if (!waited) { tc::mbar_wait(&ctl->tmem_full[as], aphase); tc::fence_after_sync(); waited = true; TC_STAMP(4, et == 0); }
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                if (h * 8 < nc) {
+                    float v[8];
+                    tc::tmem_ld8(tacc + (uint32_t)(c + h * 8), v);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const bool ok = bc * NT + c + h * 8 + j < p.Nb;
+                        s1 += ok ? v[j] : 0.0f;
+                        s2 = fmaf(v[j], e[h * 8 + j], s2);
+                    }
+                }
+            }
+        }
+        if (!waited) { tc::mbar_wait(&ctl->tmem_full[as], aphase); tc::fence_after_sync(); }
+    } else {
+        tc::mbar_wait(&ctl->tmem_full[as], aphase);
+        tc::fence_after_sync();
+        TC_STAMP(4, et == 0);
+        for (int c = c_begin; c < c_end; c += 8) {
+            float v[8];
+            tc::tmem_ld8(tacc + (uint32_t)c, v);
+            const int b0 = bc * NT + c;
+            if (EPI == EPI_GLM_FWD) {
+                float r[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float yv = ctl->ys[as][c + j];
+                    float lp, rr;
+                    if (LIK == 0) {
+                        const float l = v[j];
+                        const float e = tc::ex2_approx(-1.4426950408889634f * fabsf(l));   // exp(-|l|) in (0, 1]
+                        const float inv = tc::rcp_approx(1.0f + e);                         // in [1/2, 1)
+                        const float sig = l >= 0.0f ? inv : e * inv;
+                        // y l - log1pexp(l) = y l - max(l, 0) + ln(inv)
+                        lp = fmaf(yv, l, fmaf(0.6931471805599453f, tc::lg2_approx(inv), -fmaxf(l, 0.0f)));
+                        rr = yv - sig;
+                    } else {
+                        rr = yv - v[j];
+                        lp = fmaf(-0.5f * rr, rr, -0.5f * AVI_LOG2PI);
+                    }
+                    const bool ok = b0 + j < p.Nb;
+                    s1 += ok ? lp : 0.0f;
+                    r[j] = ok ? tc::round_tf32(p.w * rr) : 0.0f;
+                }
+                // (staging this tile through shared memory for 128-byte row stores was measured slower: the
+                // extra STS + barrier cost more than the 32-byte-sector stores; profiles/README.md)
+                if (a_ok && b0 < p.ldc) {
+                    float4* dst = reinterpret_cast<float4*>(p.C + (size_t)a * p.ldc + b0);
+                    dst[0] = make_float4(r[0], r[1], r[2], r[3]);
+                    dst[1] = make_float4(r[4], r[5], r[6], r[7]);
+                }
+            } else {
+                float* Cs = p.C + (size_t)ks * p.slab_stride;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int b = b0 + j;
+                    if (b < p.Nb && a_ok) Cs[(size_t)b * p.ldc + a] = v[j];
+                }
+            }
+        }
+    }
+}
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_store_partials(const TcParams& p, bool a_ok, int a, int bc, int ks, int cq,
+                                                        float s1, float s2) {
+    if (EPI == EPI_GLM_FWD) {
+        if (a_ok) p.part1[(size_t)(bc * 4 + cq) * p.ldpart + a] = s1;
+    } else if (EPI == EPI_GLM_BWD) {
+        if (a_ok) {
+            const size_t slab = (size_t)((ks * p.n_bchunk + bc) * 4 + cq) * p.ldpart;
+            p.part1[slab + a] = s1;
+            p.part2[slab + a] = s2;
+        }
+    }
+}
 
 // LIK: 0 Bernoulli-logit, 1 Gaussian (EPI_GLM_FWD only)
 template <int EPI, int LIK>
@@ -53,6 +166,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int stages = p.stages;
     SmemCtl* ctl = reinterpret_cast<SmemCtl*>(tiles + stages * stage_bytes);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    TC_STAMP(0, threadIdx.x == 0);
 
     // thread-block cluster: CA a-blocks x CB b-chunks of one k-split.  The A tile of an a-block is needed
     // by the CB CTAs of its row, the B tile of a b-chunk by the CA CTAs of its column: every CTA loads
@@ -77,11 +191,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         tc::mbar_fence_init();
     }
     if (warp == 2) tc::tmem_alloc(&ctl->tmem_base, 512);
+    pdl_trigger();
     tc::fence_before_sync();
     __syncthreads();
     if (CSZ > 1) tc::cluster_sync();   // peers must see initialised barriers before any multicast lands
-    tc::fence_after_sync();
-    const uint32_t tmem_base = ctl->tmem_base;
 
     // cluster units: (a-group, b-group, k-split); this CTA's tile inside the unit is (ra, rb)
     const int n_ag = (p.n_ablk + CA - 1) / CA, n_bg = (p.n_bchunk + CB - 1) / CB;
@@ -91,16 +204,58 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #define UNIT_COORDS(u)                                                                       \
     const int ab = ((u) % n_ag) * CA + ra, bc = (((u) / n_ag) % n_bg) * CB + rb, ks = (u) / (n_ag * n_bg)
 
+    // One operand is static data (X): its tiles for the first ring fill are requested BEFORE waiting for the
+    // previous kernel (programmatic dependent launch), hiding the cold-pipeline latency behind that kernel.
+    // p.static_op: 1 = A is static, 2 = B is static, 0 = neither.  (single-CTA, non-multicast path only)
+    int pre_issued = 0;
+    if (p.static_op && CSZ == 1 && warp == 0 && lane == 0 && (int)blockIdx.x < units) {
+        const int u = cluster_id;
+        UNIT_COORDS(u);
+        const int kb0 = ks * p.kb_per_split, kb1 = min(p.n_kblk, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1 && pre_issued < stages; ++kb, ++pre_issued) {
+            uint8_t* sa = tiles + pre_issued * stage_bytes;
+            if (p.static_op == 1) {
+                tc::mbar_expect_tx(&ctl->full[pre_issued], (uint32_t)A_TILE_BYTES);
+                tc::tma_load_2d(sa, &tmA, &ctl->full[pre_issued], kb * BK, ab * BM);
+            } else {
+                tc::mbar_expect_tx(&ctl->full[pre_issued], (uint32_t)(NT * BK * 4));
+                tc::tma_load_2d(sa + A_TILE_BYTES, &tmB, &ctl->full[pre_issued], kb * BK, bc * NT);
+            }
+        }
+    }
+    pdl_wait();   // everything above overlapped the previous kernel's tail; dependent operands from here on
+    tc::fence_after_sync();
+    const uint32_t tmem_base = ctl->tmem_base;
+    TC_STAMP(1, threadIdx.x == 0);
+
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
+            int kcount = 0;   // k-blocks issued so far by this CTA
             for (int u = cluster_id; u < units; u += n_clusters) {
                 UNIT_COORDS(u);
                 const int kb0 = ks * p.kb_per_split, kb1 = min(p.n_kblk, kb0 + p.kb_per_split);
-                for (int kb = kb0; kb < kb1; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb, ++kcount) {
                     tc::mbar_wait(&ctl->empty[stage], phase ^ 1);   // every CTA I write into has drained this stage
                     uint8_t* sa = tiles + stage * stage_bytes;
+                    if (kcount < pre_issued) {
+                        // the static operand of this k-block is already in flight: add the dependent one
+                        if (p.static_op == 1) {
+                            tc::mbar_arrive_expect_tx(&ctl->full[stage], (uint32_t)(NT * BK * 4));
+                            tc::tma_load_2d(sa + A_TILE_BYTES, &tmB, &ctl->full[stage], kb * BK, bc * NT);
+                        } else {
+                            tc::mbar_arrive_expect_tx(&ctl->full[stage], (uint32_t)A_TILE_BYTES);
+                            tc::tma_load_2d(sa, &tmA, &ctl->full[stage], kb * BK, ab * BM);
+                        }
+                        if (++stage == stages) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
+                    if (p.dbg & 1) {   // timing experiment: no operand traffic (MMA + epilogue bound)
+                        tc::mbar_arrive(&ctl->full[stage]);
+                        if (++stage == stages) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     tc::mbar_arrive_expect_tx(&ctl->full[stage], stage_tx);
                     uint8_t* dst_a = sa + rb * a_rows * (BK * 4);
                     uint8_t* dst_b = sa + A_TILE_BYTES + ra * b_rows * (BK * 4);
@@ -127,18 +282,22 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 for (int kb = kb0; kb < kb1; ++kb) {
                     tc::mbar_wait(&ctl->full[stage], phase);
                     tc::fence_after_sync();
+                    TC_STAMP(2, kb == kb0 && u == cluster_id);
                     const uint32_t sa = tc::smem_u32(tiles + stage * stage_bytes);
                     const uint64_t da = tc::smem_desc_k_sw128(sa);
                     const uint64_t db = tc::smem_desc_k_sw128(sa + A_TILE_BYTES);
+                    if (!(p.dbg & 2) || kb == kb0) {   // dbg bit 1: timing experiment without the MMAs (TMA bound)
 #pragma unroll
                     for (int k = 0; k < BK / 8; ++k)   // UMMA K = 8 tf32 = 32 bytes: +2 in 16-byte units
                         tc::umma_tf32(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
                                       (kb > kb0 || k > 0) ? 1u : 0u);
+                    }
                     if (CSZ > 1) tc::umma_commit_mc(&ctl->empty[stage], (uint16_t)peer_mask);
                     else tc::umma_commit(&ctl->empty[stage]);
                     if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
                 tc::umma_commit(&ctl->tmem_full[as]);
+                TC_STAMP(3, true);
                 if (++as == 2) { as = 0; aphase ^= 1; }
             }
         }
@@ -155,99 +314,15 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             UNIT_COORDS(u);
             const int a = ab * BM + quarter * 32 + lane;   // this thread's accumulator row
             const bool a_ok = a < p.Ma && bc < p.n_bchunk;   // tiles past the edge of the unit grid only feed the pipeline
-            if (EPI == EPI_GLM_FWD) {
-                int b = bc * NT + et;
-                if (et < NT) ctl->ys[as][et] = b < p.Nb ? __ldg(p.y + b) : 0.0f;
-                epi_bar_sync();
-            }
-            float s1 = 0.0f, s2 = 0.0f;
             const uint32_t tacc = tmem_base + (uint32_t)(as * 256) + ((uint32_t)(quarter * 32) << 16);
-            if (EPI == EPI_GLM_BWD) {
-                // eps[b][a] for this thread's columns, fetched while the MMAs are still running
-                const float* Ea = p.E + a;
-                int c = c_begin;
-                float e[32];
-                bool waited = false;
-                for (; c < c_end; c += 32) {
-                    const int nc = min(32, c_end - c);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int b = bc * NT + c + j;
-                        e[j] = (j < nc && a_ok && b < p.Nb) ? __ldg(Ea + (size_t)b * p.lde) : 0.0f;
-                    }
-                    if (!waited) { tc::mbar_wait(&ctl->tmem_full[as], aphase); tc::fence_after_sync(); waited = true; }
-#pragma unroll
-                    for (int h = 0; h < 4; ++h) {
-                        if (h * 8 < nc) {
-                            float v[8];
-                            tc::tmem_ld8(tacc + (uint32_t)(c + h * 8), v);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const bool ok = bc * NT + c + h * 8 + j < p.Nb;
-                                s1 += ok ? v[j] : 0.0f;
-                                s2 = fmaf(v[j], e[h * 8 + j], s2);
-                            }
-                        }
-                    }
-                }
-                if (!waited) { tc::mbar_wait(&ctl->tmem_full[as], aphase); tc::fence_after_sync(); }
-            } else {
-                tc::mbar_wait(&ctl->tmem_full[as], aphase);
-                tc::fence_after_sync();
-                for (int c = c_begin; c < c_end; c += 8) {
-                    float v[8];
-                    tc::tmem_ld8(tacc + (uint32_t)c, v);
-                    const int b0 = bc * NT + c;
-                    if (EPI == EPI_GLM_FWD) {
-                        float r[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float yv = ctl->ys[as][c + j];
-                            float lp, rr;
-                            if (LIK == 0) {
-                                const float l = v[j];
-                                const float e = exp2f(-1.4426950408889634f * fabsf(l));
-                                const float inv = __fdividef(1.0f, 1.0f + e);
-                                const float sig = l >= 0.0f ? inv : e * inv;
-                                // y l - log1pexp(l) = y l - max(l, 0) + ln(inv)
-                                lp = fmaf(yv, l, fmaf(0.6931471805599453f, __log2f(inv), -fmaxf(l, 0.0f)));
-                                rr = yv - sig;
-                            } else {
-                                rr = yv - v[j];
-                                lp = fmaf(-0.5f * rr, rr, -0.5f * AVI_LOG2PI);
-                            }
-                            const bool ok = b0 + j < p.Nb;
-                            s1 += ok ? lp : 0.0f;
-                            r[j] = ok ? tc::round_tf32(p.w * rr) : 0.0f;
-                        }
-                        if (a_ok && b0 < p.ldc) {
-                            float4* dst = reinterpret_cast<float4*>(p.C + (size_t)a * p.ldc + b0);
-                            dst[0] = make_float4(r[0], r[1], r[2], r[3]);
-                            dst[1] = make_float4(r[4], r[5], r[6], r[7]);
-                        }
-                    } else {
-                        float* Cs = p.C + (size_t)ks * p.slab_stride;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int b = b0 + j;
-                            if (b < p.Nb && a_ok) Cs[(size_t)b * p.ldc + a] = v[j];
-                        }
-                    }
-                }
-            }
+            float s1, s2;
+            epilogue_unit<EPI, LIK>(p, ctl, as, aphase, tacc, NT, a, a_ok, bc, ks, c_begin, c_end, et, s1, s2);
+            TC_STAMP(5, et == 0);
             // accumulator stage drained: hand it back to the MMA warp
             tc::fence_before_sync();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&ctl->tmem_empty[as]);
-            if (EPI == EPI_GLM_FWD) {
-                if (a_ok) p.part1[(size_t)(bc * 4 + cq) * p.ldpart + a] = s1;
-            } else if (EPI == EPI_GLM_BWD) {
-                if (a_ok) {
-                    const size_t slab = (size_t)((ks * p.n_bchunk + bc) * 4 + cq) * p.ldpart;
-                    p.part1[slab + a] = s1;
-                    p.part2[slab + a] = s2;
-                }
-            }
+            epilogue_store_partials<EPI>(p, a_ok, a, bc, ks, cq, s1, s2);
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
     }
@@ -260,6 +335,134 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         tc::fence_after_sync();
         tc::tmem_dealloc(tmem_base, 512);
     }
+    TC_STAMP(6, threadIdx.x == 64);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05.mma.cta_group::2, UMMA M = 256): a cluster of 2 CTAs works on two a-blocks of one
+// (b-chunk, k-split).  Each CTA stages its own 128 x 32 A tile and HALF of the b-chunk (NT/2 rows); the leader
+// CTA's elected thread issues the MMAs for both tensor cores; accumulator rows of CTA r stay in CTA r's TMEM and
+// are drained by CTA r's epilogue warps.  Per SM and k-block this moves 16 KB + NT*64 B instead of
+// 16 KB + NT*128 B, which is what bounds the 1-CTA kernel (SM ingress).
+template <int EPI, int LIK>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+k_gemm_tc_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int NT = p.nt;
+    const int b_half_bytes = (NT / 2) * BK * 4;
+    const int stage_bytes = A_TILE_BYTES + b_half_bytes;
+    const int stages = p.stages;
+    SmemCtl* ctl = reinterpret_cast<SmemCtl*>(tiles + stages * stage_bytes);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = tc::cluster_ctarank();   // 0 = leader
+    const int pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    TC_STAMP(0, threadIdx.x == 0);
+
+    if (warp == 0 && lane == 0) {
+        tc::tma_prefetch_desc(&tmA);
+        tc::tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < stages; ++s) { tc::mbar_init(&ctl->full[s], 1); tc::mbar_init(&ctl->empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { tc::mbar_init(&ctl->tmem_full[s], 1); tc::mbar_init(&ctl->tmem_empty[s], 2 * EPI_WARPS); }
+        tc::mbar_fence_init();
+    }
+    if (warp == 2) tc::tmem_alloc_cg2(&ctl->tmem_base, 512);
+    pdl_trigger();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::cluster_sync();
+    pdl_wait();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = ctl->tmem_base;
+    TC_STAMP(1, threadIdx.x == 0);
+
+    const int n_ag = (p.n_ablk + 1) / 2;
+    const int units = n_ag * p.n_bchunk * p.n_ksplit;
+#define PAIR_COORDS(u) \
+    const int ab = ((u) % n_ag) * 2 + (int)rank, bc = ((u) / n_ag) % p.n_bchunk, ks = (u) / (n_ag * p.n_bchunk)
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int u = pair_id; u < units; u += n_pairs) {
+                PAIR_COORDS(u);
+                const int kb0 = ks * p.kb_per_split, kb1 = min(p.n_kblk, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    tc::mbar_wait(&ctl->empty[stage], phase ^ 1);   // released by the leader's commit (multicast)
+                    uint8_t* sa = tiles + stage * stage_bytes;
+                    const uint32_t leader_full = tc::mapa_u32(tc::smem_u32(&ctl->full[stage]), 0u);
+                    if (rank == 0) tc::mbar_arrive_expect_tx(&ctl->full[stage], 2u * (uint32_t)stage_bytes);
+                    tc::tma_load_2d_cg2(sa, &tmA, leader_full, kb * BK, ab * BM);
+                    tc::tma_load_2d_cg2(sa + A_TILE_BYTES, &tmB, leader_full, kb * BK, bc * NT + (int)rank * (NT / 2));
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (lane == 0 && rank == 0) {
+            const uint32_t idesc = tc::idesc_tf32(2 * BM, NT);
+            int stage = 0; uint32_t phase = 0;
+            int as = 0; uint32_t aphase = 0;
+            for (int u = pair_id; u < units; u += n_pairs) {
+                const int ks = u / (n_ag * p.n_bchunk);
+                const int kb0 = ks * p.kb_per_split, kb1 = min(p.n_kblk, kb0 + p.kb_per_split);
+                tc::mbar_wait(&ctl->tmem_empty[as], aphase ^ 1);   // both CTAs' epilogues drained this stage
+                tc::fence_after_sync();
+                const uint32_t tacc = tmem_base + (uint32_t)(as * 256);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    tc::mbar_wait(&ctl->full[stage], phase);       // both CTAs' tiles have landed
+                    tc::fence_after_sync();
+                    TC_STAMP(2, kb == kb0 && u == pair_id);
+                    const uint32_t sa = tc::smem_u32(tiles + stage * stage_bytes);
+                    const uint64_t da = tc::smem_desc_k_sw128(sa);
+                    const uint64_t db = tc::smem_desc_k_sw128(sa + A_TILE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 8; ++k)
+                        tc::umma_tf32_cg2(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                                          (kb > kb0 || k > 0) ? 1u : 0u);
+                    tc::umma_commit_cg2_mc(&ctl->empty[stage], (uint16_t)3);
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
+                }
+                tc::umma_commit_cg2_mc(&ctl->tmem_full[as], (uint16_t)3);
+                TC_STAMP(3, true);
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue (both CTAs, own accumulator rows) =====================
+        const int ew = warp - 4, quarter = warp & 3, cq = ew >> 2;
+        const int et = threadIdx.x - 128;
+        const int ngroups = NT / 8;
+        const int c_begin = 8 * ((ngroups * cq) / 4), c_end = 8 * ((ngroups * (cq + 1)) / 4);
+        int as = 0; uint32_t aphase = 0;
+        for (int u = pair_id; u < units; u += n_pairs) {
+            PAIR_COORDS(u);
+            const int a = ab * BM + quarter * 32 + lane;
+            const bool a_ok = a < p.Ma;
+            const uint32_t tacc = tmem_base + (uint32_t)(as * 256) + ((uint32_t)(quarter * 32) << 16);
+            float s1, s2;
+            epilogue_unit<EPI, LIK>(p, ctl, as, aphase, tacc, NT, a, a_ok, bc, ks, c_begin, c_end, et, s1, s2);
+            TC_STAMP(5, et == 0);
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive_cluster(tc::mapa_u32(tc::smem_u32(&ctl->tmem_empty[as]), 0u));
+            epilogue_store_partials<EPI>(p, a_ok, a, bc, ks, cq, s1, s2);
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+    }
+#undef PAIR_COORDS
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::cluster_sync();
+    if (warp == 2) {
+        tc::fence_after_sync();
+        tc::tmem_dealloc_cg2(tmem_base, 512);
+    }
+    TC_STAMP(6, threadIdx.x == 64);
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
@@ -299,11 +502,13 @@ int32_t avi_tc_make_tmap(avi_ctx* ctx, CUtensorMap* map, const float* base, int6
     return AVI_OK;
 }
 
-static int smem_bytes_for(int nt, int* stages_out) {
-    const int stage_bytes = A_TILE_BYTES + nt * BK * 4;
-    const int stages = std::min(MAX_STAGES, (SMEM_LIMIT - 1024 - (int)sizeof(SmemCtl)) / stage_bytes);
+static int smem_bytes_for(int nt, int* stages_out, bool pair = false, bool fwd = false) {
+    const int stage_bytes = A_TILE_BYTES + (pair ? nt / 2 : nt) * BK * 4;
+    const int extra = 1024 + (int)sizeof(SmemCtl);
+    (void)fwd;
+    const int stages = std::max(2, std::min(MAX_STAGES, (SMEM_LIMIT - extra) / stage_bytes));
     if (stages_out) *stages_out = stages;
-    return stages * stage_bytes + 1024 + (int)sizeof(SmemCtl);
+    return stages * stage_bytes + extra;
 }
 
 static int32_t set_attrs(avi_ctx* ctx) {
@@ -313,6 +518,10 @@ static int32_t set_attrs(avi_ctx* ctx) {
     AVI_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tc<EPI_GLM_FWD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     AVI_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tc<EPI_GLM_BWD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     AVI_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tc<EPI_STORE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    AVI_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tc_pair<EPI_GLM_FWD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    AVI_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tc_pair<EPI_GLM_FWD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    AVI_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tc_pair<EPI_GLM_BWD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    AVI_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tc_pair<EPI_STORE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     attr_done = true;
     return AVI_OK;
 }
@@ -356,8 +565,10 @@ int32_t avi_tc_plan(avi_ctx* ctx, int64_t Ma, int64_t Nb, int64_t K, bool split_
             if (force_cluster == 0 && csz > 1) continue;
             const int maxc = max_active_clusters(ctx, csz);
             if (maxc <= 0) continue;
+            static const int nt_env = getenv("AVI_TC_NT") ? atoi(getenv("AVI_TC_NT")) : 0;
             for (int nt = split_k ? nt_hi : 16; nt <= nt_hi; nt += 16) {
                 if (nt % (8 * ca)) continue;
+                if (nt_env && !split_k && nt != std::min(nt_env, nt_hi)) continue;
                 const int n_bchunk = (int)ceil_div(Nb, nt);
                 if (cb > 1 && cb > n_bchunk) continue;
                 const int64_t tiles = ceil_div(p->n_ablk, ca) * ceil_div(n_bchunk, cb);
@@ -382,10 +593,38 @@ int32_t avi_tc_plan(avi_ctx* ctx, int64_t Ma, int64_t Nb, int64_t K, bool split_
             }
         }
     }
+    // CTA pairs (cta_group::2): two a-blocks per unit, half of the b-chunk per SM
+    p->pair = 0;
+    static const int pair_env = getenv("AVI_TC_PAIR") ? atoi(getenv("AVI_TC_PAIR")) : 0;
+    if (pair_env && p->n_ablk >= 2) {
+        const int maxp = max_active_clusters(ctx, 2);
+        const int n_ag = (p->n_ablk + 1) / 2;
+        for (int nt = split_k ? nt_hi : 16; nt <= nt_hi && maxp > 0; nt += 16) {
+            const int n_bchunk = (int)ceil_div(Nb, nt);
+            const int64_t tiles = (int64_t)n_ag * n_bchunk;
+            int n_ksplit = 1, kbps = p->n_kblk;
+            if (split_k) {
+                int want = (int)std::max<int64_t>(1, maxp / tiles);
+                want = std::min(want, p->n_kblk);
+                kbps = (int)ceil_div(p->n_kblk, want);
+                n_ksplit = (int)ceil_div(p->n_kblk, kbps);
+            }
+            const int64_t waves = ceil_div(tiles * n_ksplit, maxp);
+            const double bytes_sm = (double)A_TILE_BYTES + (nt / 2) * BK * 4.0;
+            const double per_kb = std::max(2.0 * nt, bytes_sm / 64.0) + 20.0;
+            double cost = (double)waves * (per_kb * kbps + 6500.0);
+            if (pair_env == 2) cost *= 0.25;
+            if (cost < best) {
+                best = cost;
+                p->pair = 1; p->ca = 1; p->cb = 1; p->nt = nt; p->n_bchunk = n_bchunk; p->n_ksplit = n_ksplit;
+                p->kb_per_split = kbps;
+            }
+        }
+    }
     if (best >= 1e300) AVI_FAIL(ctx, AVI_ERR_INVALID, "no valid tiling");
     if (getenv("AVI_TC_DEBUG"))
-        fprintf(stderr, "[avi_tc_plan] Ma=%lld Nb=%lld K=%lld split_k=%d -> ca=%d cb=%d nt=%d n_ablk=%d n_bchunk=%d n_ksplit=%d kbps=%d "
-                "maxc(1,2,4,8)=%d,%d,%d,%d cost=%.0f\n", (long long)Ma, (long long)Nb, (long long)K, (int)split_k, p->ca, p->cb, p->nt,
+        fprintf(stderr, "[avi_tc_plan] Ma=%lld Nb=%lld K=%lld split_k=%d -> pair=%d ca=%d cb=%d nt=%d n_ablk=%d n_bchunk=%d n_ksplit=%d kbps=%d "
+                "maxc(1,2,4,8)=%d,%d,%d,%d cost=%.0f\n", (long long)Ma, (long long)Nb, (long long)K, (int)split_k, p->pair, p->ca, p->cb, p->nt,
                 p->n_ablk, p->n_bchunk, p->n_ksplit, p->kb_per_split, max_active_clusters(ctx, 1), max_active_clusters(ctx, 2),
                 max_active_clusters(ctx, 4), max_active_clusters(ctx, 8), best);
     (void)sms;
@@ -394,29 +633,72 @@ int32_t avi_tc_plan(avi_ctx* ctx, int64_t Ma, int64_t Nb, int64_t K, bool split_
 
 int32_t avi_tc_launch(avi_ctx* ctx, int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p_in) {
     TcParams p = p_in;
+    static const int dbg_env = getenv("AVI_TC_DBG") ? atoi(getenv("AVI_TC_DBG")) : 0;
+    p.dbg = dbg_env;
+    static const int prof_env = getenv("AVI_TC_PROF") ? atoi(getenv("AVI_TC_PROF")) : 0;
+    static unsigned long long* prof_buf = nullptr;
+    static int prof_calls = 0;
+    if (prof_env) {
+        if (!prof_buf) { cudaMalloc(&prof_buf, 148 * 8 * sizeof(unsigned long long)); }
+        cudaMemsetAsync(prof_buf, 0, 148 * 8 * sizeof(unsigned long long), ctx->stream);
+        p.prof = prof_buf;
+    }
     if (p.nt % 16 || p.nt < 16 || p.nt > 256 || p.ca < 1 || p.cb < 1 || p.ca * p.cb > 8 || p.nt % (8 * p.ca))
         AVI_FAIL(ctx, AVI_ERR_INVALID, "bad tiling");
-    const int csz = p.ca * p.cb;
-    const int64_t units = ceil_div(p.n_ablk, p.ca) * ceil_div(p.n_bchunk, p.cb) * p.n_ksplit;
+    const int csz = p.pair ? 2 : p.ca * p.cb;
+    const int64_t units = p.pair ? (int64_t)((p.n_ablk + 1) / 2) * p.n_bchunk * p.n_ksplit
+                                 : ceil_div(p.n_ablk, p.ca) * ceil_div(p.n_bchunk, p.cb) * p.n_ksplit;
     if (units <= 0) return AVI_OK;
     AVI_CHECK(set_attrs(ctx));
-    const int smem = smem_bytes_for(p.nt, &p.stages);   // as many stages as fit: bytes in flight per SM
+    const int smem = smem_bytes_for(p.nt, &p.stages, p.pair != 0, epi == EPI_GLM_FWD);   // as many stages as fit
+    if (smem > SMEM_LIMIT) AVI_FAIL(ctx, AVI_ERR_INVALID, "tile does not fit in shared memory");
     const int maxc = max_active_clusters(ctx, csz);
     if (maxc <= 0) AVI_FAIL(ctx, AVI_ERR_CUDA, "cluster size not launchable");
     const unsigned grid = (unsigned)(std::min<int64_t>(units, maxc) * csz);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = ctx->stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = csz; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = csz > 1 ? 1 : 0;
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    if (csz > 1) {
+        at[na].id = cudaLaunchAttributeClusterDimension;
+        at[na].val.clusterDim.x = csz; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (avi_pdl_enabled()) {
+        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = at; cfg.numAttrs = na;
     AviTimed timed(ctx, epi == EPI_GLM_FWD ? "glm_fwd" : epi == EPI_GLM_BWD ? "glm_bwd" : "gemm_store");
     cudaError_t e;
+    if (p.pair) {
+        if (epi == EPI_GLM_FWD && p.likelihood == AVI_GLM_BERNOULLI_LOGIT) e = cudaLaunchKernelEx(&cfg, k_gemm_tc_pair<EPI_GLM_FWD, 0>, tmA, tmB, p);
+        else if (epi == EPI_GLM_FWD) e = cudaLaunchKernelEx(&cfg, k_gemm_tc_pair<EPI_GLM_FWD, 1>, tmA, tmB, p);
+        else if (epi == EPI_GLM_BWD) e = cudaLaunchKernelEx(&cfg, k_gemm_tc_pair<EPI_GLM_BWD, 0>, tmA, tmB, p);
+        else e = cudaLaunchKernelEx(&cfg, k_gemm_tc_pair<EPI_STORE, 0>, tmA, tmB, p);
+    } else
     if (epi == EPI_GLM_FWD && p.likelihood == AVI_GLM_BERNOULLI_LOGIT) e = cudaLaunchKernelEx(&cfg, k_gemm_tc<EPI_GLM_FWD, 0>, tmA, tmB, p);
     else if (epi == EPI_GLM_FWD) e = cudaLaunchKernelEx(&cfg, k_gemm_tc<EPI_GLM_FWD, 1>, tmA, tmB, p);
     else if (epi == EPI_GLM_BWD) e = cudaLaunchKernelEx(&cfg, k_gemm_tc<EPI_GLM_BWD, 0>, tmA, tmB, p);
     else e = cudaLaunchKernelEx(&cfg, k_gemm_tc<EPI_STORE, 0>, tmA, tmB, p);
     if (e != cudaSuccess) AVI_FAIL(ctx, AVI_ERR_CUDA, std::string("tcgen05 kernel launch: ") + cudaGetErrorString(e));
     AVI_LAUNCHED(ctx);
+    if (p.prof && ++prof_calls > prof_env && !ctx->capturing) {   // AVI_TC_PROF=n: report launches after the n-th
+        std::vector<unsigned long long> h(148 * 8);
+        cudaStreamSynchronize(ctx->stream);
+        cudaMemcpy(h.data(), prof_buf, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+        unsigned long long t0 = ~0ull, t6 = 0;
+        for (unsigned b = 0; b < grid; ++b) { if (h[b * 8]) t0 = std::min(t0, h[b * 8]); t6 = std::max(t6, h[b * 8 + 6]); }
+        double avg[8] = {0};
+        int cnt[8] = {0};
+        for (unsigned b = 0; b < grid; ++b)
+            for (int k = 0; k < 7; ++k)
+                if (h[b * 8 + k]) { avg[k] += (double)(h[b * 8 + k] - t0); cnt[k]++; }
+        for (int k = 0; k < 7; ++k) avg[k] /= std::max(cnt[k], 1);
+        fprintf(stderr, "[tc_prof] epi=%d grid=%u total=%.2fus | avg ns since first CTA entry: entry %.0f prologue %.0f first-operands %.0f "
+                "mma-issued %.0f acc-ready %.0f epi-done %.0f exit %.0f\n", epi, grid, (t6 - t0) * 1e-3, avg[0], avg[1], avg[2], avg[3],
+                avg[4], avg[5], avg[6]);
+    }
     return AVI_OK;
 }

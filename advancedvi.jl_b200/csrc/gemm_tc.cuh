@@ -14,8 +14,12 @@ struct TcParams {
     int n_ablk, n_bchunk, n_ksplit;
     int n_kblk, kb_per_split;
     int nt;
+    int pair;            // 1: CTA-pair kernel (cta_group::2): A box = 128 rows, B box = nt/2 rows
     int ca, cb;          // cluster shape: ca a-blocks x cb b-chunks share operands by TMA multicast
     int stages;          // filled by avi_tc_launch
+    int static_op;       // 1: A is static data (not written by the previous kernel), 2: B is, 0: neither
+    unsigned long long* prof;   // AVI_TC_PROF: per-CTA phase timestamps
+    int dbg;             // AVI_TC_DBG timing experiments (results are then meaningless): 1 no operand loads, 2 no MMAs
     // epilogue operands
     float* C;            // FWD: R [a][ldc];  STORE: slabs [ks][b * ldc + a]
     int ldc;

@@ -72,11 +72,15 @@ k_glm_post_sums(const float* __restrict__ Z, const float* __restrict__ E, int ld
                 int ncoordblk, float* __restrict__ a1, float* __restrict__ a2, float* __restrict__ logp) {
     __shared__ float sm[4][32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    pdl_trigger();
+    pdl_wait();
     if ((int)blockIdx.x >= ncoordblk) {
         const int m = (blockIdx.x - ncoordblk) * 32 + tx;
         float s = 0.f;
-        if (m < M)
+        if (m < M) {
+#pragma unroll 8
             for (int q = ty; q < nparts; q += 32) s += llpart[(size_t)q * ldpart + m];
+        }
         sm[0][ty][tx] = s;
         __syncthreads();
         if (ty == 0 && m < M) {
@@ -89,6 +93,7 @@ k_glm_post_sums(const float* __restrict__ Z, const float* __restrict__ E, int ld
         const int i = blockIdx.x * 32 + tx;
         float t1 = 0.f, t2 = 0.f, p1 = 0.f, p2 = 0.f;
         if (i <= d) {
+#pragma unroll 8
             for (int m = ty; m < M; m += 32) {
                 const float4 pm = pre[m];
                 const float e = E[(size_t)m * ld + i];
@@ -96,6 +101,7 @@ k_glm_post_sums(const float* __restrict__ Z, const float* __restrict__ E, int ld
                 t1 += g; t2 = fmaf(g, e, t2);
             }
             if (i < d)
+#pragma unroll 4
                 for (int q = ty; q < nslab; q += 32) {
                     p1 += a1p[(size_t)q * ldslab + i];
                     p2 += a2p[(size_t)q * ldslab + i];
@@ -269,11 +275,12 @@ struct Glm : avi_model {
         TcParams p{};
         AVI_CHECK(avi_tc_plan(ctx, M, n_act, d, false, cluster_mode, &p));
         p.C = R; p.ldc = (int)ldR; p.y = y; p.w = w; p.likelihood = likelihood;
+        p.static_op = subsampled ? 0 : 2;   // B = X rows (a minibatch copy is rewritten every step: not static)
         AVI_CHECK(ensure_buf(&llpart, &llpart_cap, (long long)p.n_bchunk * 4 * capM));
         p.part1 = llpart; p.ldpart = capM;
         CUtensorMap tmA, tmB;
         AVI_CHECK(avi_tc_make_tmap(ctx, &tmA, Zt, M, d, ld, 128 / p.cb));
-        AVI_CHECK(avi_tc_make_tmap(ctx, &tmB, Xr, n_act, d, dK, p.nt / p.ca));
+        AVI_CHECK(avi_tc_make_tmap(ctx, &tmB, Xr, n_act, d, dK, p.pair ? p.nt / 2 : p.nt / p.ca));
         AVI_CHECK(avi_tc_launch(ctx, EPI_GLM_FWD, tmA, tmB, p));
         *nparts = p.n_bchunk * 4;
         return AVI_OK;
@@ -281,8 +288,9 @@ struct Glm : avi_model {
 
     int32_t backward_setup(int M, TcParams* p, CUtensorMap* tmA, CUtensorMap* tmB) {
         AVI_CHECK(avi_tc_plan(ctx, d, M, n_act, true, cluster_mode, p));
+        p->static_op = subsampled ? 0 : 1;   // A = X columns
         AVI_CHECK(avi_tc_make_tmap(ctx, tmA, Xc, d, n_act, nP, 128 / p->cb));
-        AVI_CHECK(avi_tc_make_tmap(ctx, tmB, R, M, n_act, ldR, p->nt / p->ca));
+        AVI_CHECK(avi_tc_make_tmap(ctx, tmB, R, M, n_act, ldR, p->pair ? p->nt / 2 : p->nt / p->ca));
         return AVI_OK;
     }
 
@@ -329,8 +337,12 @@ struct Glm : avi_model {
         AVI_CHECK(avi_tc_launch(ctx, EPI_GLM_BWD, tmA, tmB, p));
         const int ncb = (int)ceil_div(d + 1, 32);
         const unsigned grid = (unsigned)(ncb + ceil_div(M, 32));
-        k_glm_post_sums<<<grid, 1024, 0, ctx->stream>>>(Z, E, ld, M, d, pre, a1p, a2p, nslab, ldslab, llpart, nparts,
-                                                        capM, likeadj(), ncb, a1, a2, logp);
+        {
+            cudaError_t e = avi_launch_pdl(ctx, k_glm_post_sums, dim3(grid), dim3(1024), 0, Z, E, ld, M, d,
+                                           (const float4*)pre, (const float*)a1p, (const float*)a2p, nslab, ldslab,
+                                           (const float*)llpart, nparts, capM, likeadj(), ncb, a1, a2, logp);
+            if (e != cudaSuccess) AVI_FAIL(ctx, AVI_ERR_CUDA, std::string("post_sums launch: ") + cudaGetErrorString(e));
+        }
         AVI_LAUNCHED(ctx);
         return AVI_OK;
     }

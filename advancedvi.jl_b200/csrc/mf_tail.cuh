@@ -52,6 +52,8 @@ __device__ __forceinline__ float block_sum_1024(float v, float* sm) {
 template <int ITEMS>
 __device__ __forceinline__ void mf_finalize_update_body(const MfTailArgs& t) {
     __shared__ float sm[33];
+    pdl_trigger();
+    pdl_wait();
     const float* __restrict__ acc = t.acc; const int accv = t.accv, M = t.M, objective = t.objective, entropy = t.entropy;
     const float* __restrict__ logp = t.logp; const float* __restrict__ esq = t.esq;
     const int Mloc = t.Mloc, deferred = t.deferred, trace_cap = t.trace_cap;

@@ -7,6 +7,7 @@
 //   averaging  PolynomialAveraging / NoAveraging  src/optimization/averaging.jl:42-53
 //   non-finite value slot => the step is not applied  src/algorithms/common.jl:83-89
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "avi_internal.cuh"
@@ -169,7 +170,7 @@ int32_t enqueue_iteration(avi_opt* op, bool subsampled, int64_t batch) {
     // launch: profiles/README.md)
     if (o->family == AVI_MEANFIELD && o->D <= 8 * 1024) {
         const int items = (int)ceil_div(o->D, 1024);
-#define LAUNCH_TAIL(IT) k_mf_finalize_update<IT><<<1, 1024, 0, ctx->stream>>>(tail)
+#define LAUNCH_TAIL(IT) avi_launch_pdl(ctx, k_mf_finalize_update<IT>, dim3(1), dim3(1024), 0, tail)
         if (items <= 1) LAUNCH_TAIL(1);
         else if (items <= 2) LAUNCH_TAIL(2);
         else if (items <= 4) LAUNCH_TAIL(4);
@@ -238,7 +239,8 @@ int32_t run_steps(avi_opt* op, int32_t n, const int32_t* idx_host, int64_t batch
     k_begin_call<<<1, 1, 0, ctx->stream>>>(o->d_state);
     AVI_LAUNCHED(ctx);
 
-    const bool capturable = !ctx->timing && !o->model->needs_sync_eval() && !(ctx->nranks > 1 && !ctx->comm_capturable);
+    static const bool no_graph = getenv("AVI_NO_GRAPH") && atoi(getenv("AVI_NO_GRAPH")) != 0;
+    const bool capturable = !no_graph && !ctx->timing && !o->model->needs_sync_eval() && !(ctx->nranks > 1 && !ctx->comm_capturable);
     if (capturable) {
         const int64_t gen = o->generation * 1000003 + o->model->generation;
         if (op->graph_exec && (op->graph_gen != gen || op->graph_subsampled != subsampled || op->graph_batch != batch))

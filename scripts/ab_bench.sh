@@ -1,9 +1,8 @@
 #!/bin/bash
 # A/B of environment toggles inside ONE gpurun call (same box, same clocks): prints cold / warm / e2e steps per second
-run() { python bench.py --steps 300 --warmup 30 --no-cpu-baseline 2>/dev/null | python -c "
+run() { timeout 200 python bench.py --steps 300 --warmup 30 --no-cpu-baseline 2>/dev/null | python -c "
 import json,sys; d=json.loads(sys.stdin.read()); print('$1', round(d['value']), round(d['value_l2_resident']), round(d['e2e']['value']), d['roofline']['kernel_ms'], d['gpu_launches'])"; }
 for rep in 1 2; do
-  AVI_FUSE_TAIL=1 run "fuse=1"
-  AVI_FUSE_TAIL=0 run "fuse=0"
+  AVI_TC_PAIR=1 run "pair=1"
+  AVI_TC_PAIR=0 run "pair=0"
 done
-AVI_TC_DEBUG=1 python scripts/profile_steps.py 1 2>&1 | grep avi_tc_plan | sort | uniq -c
