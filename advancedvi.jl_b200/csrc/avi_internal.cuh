@@ -186,6 +186,7 @@ struct avi_obj {
     int D = 0, M = 0;         // M = global number of Monte-Carlo samples
     int m0 = 0, Mloc = 0;     // this rank's shard
     int shard_axis = 0;       // AVI_SHARD_*
+    bool fused_exchange = false;   // the caller's next kernel performs the sample-shard exchange of acc itself
     int64_t generation = 0;   // bumped when buffers / shard / target change (captured graphs go stale)
     int ld = 0, accv = 0;     // leading dimension of sample-major buffers; padded vector length
     int cap_M = 0;            // sample capacity of the buffers below
@@ -251,7 +252,9 @@ int32_t avi_objective_finalize(avi_obj* o, const float* lambda, float* grad, flo
 // forward-only chunk for estimate_objective: sums_dev = {sum logp, sum |eps|^2, logdet}
 int32_t avi_objective_forward_chunk(avi_obj* o, const float* lambda, int m0, int Mc, const ObjDeviceState* ov,
                                     float* sums_dev);
-int32_t avi_exchange(avi_ctx* ctx, float* buf, int64_t count);          // all-reduce (no-op single rank)
+int32_t avi_exchange(avi_ctx* ctx, float* buf, int64_t count);
+struct CommPeers;
+bool avi_comm_peers(avi_ctx* ctx, int64_t count, CommPeers* out);   // comm.cu          // all-reduce (no-op single rank)
 int32_t avi_obj_advance(avi_obj* o);
 bool avi_obj_defers_scalars(const avi_obj* o);                                    // step += 1 on the device
 

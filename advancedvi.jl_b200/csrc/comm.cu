@@ -15,20 +15,12 @@
 #include <cstring>
 
 #include "avi_internal.cuh"
+#include "comm_dev.cuh"
 
 namespace {
 
-constexpr int MAX_RANKS = 16;
-constexpr int FLAG_WORDS = 64;   // flag area: MAX_RANKS words used, padded to 256 B
-
-struct CommDev {
-    unsigned int seq, arrive, depart, pad;
-};
-
-struct PeerTable {
-    float* data[MAX_RANKS];
-    unsigned int* flags[MAX_RANKS];
-};
+constexpr int MAX_RANKS = AVI_MAX_RANKS;
+constexpr int FLAG_WORDS = AVI_FLAG_WORDS;
 
 struct CommState {
     int rank = 0, nranks = 1;
@@ -40,20 +32,6 @@ struct CommState {
     PeerTable table{};
     bool connected = false;
 };
-
-__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
-    unsigned int v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ float ld_relaxed_sys(const float* p) {
-    float v;
-    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
-    return v;
-}
 
 __global__ void __launch_bounds__(256)
 k_allreduce_oneshot(float* __restrict__ buf, long long count, long long slot_stride, PeerTable t, int rank,
@@ -105,6 +83,14 @@ int32_t finish_connect(avi_ctx* ctx, CommState* cs) {
 }
 
 }  // namespace
+
+// peers for a kernel that fuses the exchange (payload of up to max_floats floats); false when not connected
+bool avi_comm_peers(avi_ctx* ctx, int64_t count, CommPeers* out) {
+    CommState* cs = state(ctx);
+    if (!cs || !cs->connected || count > cs->max_floats) return false;
+    out->nranks = cs->nranks; out->rank = cs->rank; out->slot_stride = cs->max_floats; out->t = cs->table; out->dev = cs->dev;
+    return true;
+}
 
 int32_t avi_comm_exchange(avi_ctx* ctx, float* buf, int64_t count) {
     CommState* cs = state(ctx);

@@ -365,7 +365,8 @@ int32_t avi_objective_local(avi_obj* o, const float* lambda) {
     float* scal = o->acc + 4 * (size_t)accv;
     if (Mloc <= 0) {   // a rank without samples contributes zeros
         AVI_CUDA(ctx, cudaMemsetAsync(o->acc, 0, o->acc_len * sizeof(float), ctx->stream));
-        if (o->shard_axis == AVI_SHARD_SAMPLES && ctx->nranks > 1) AVI_CHECK(avi_exchange(ctx, o->acc, o->acc_len));
+        if (o->shard_axis == AVI_SHARD_SAMPLES && ctx->nranks > 1 && !o->fused_exchange)
+            AVI_CHECK(avi_exchange(ctx, o->acc, o->acc_len));
         return AVI_OK;
     }
     SampleHook hook;
@@ -423,7 +424,8 @@ int32_t avi_objective_local(avi_obj* o, const float* lambda) {
         }
     }
     // sample sharding: the partial sums are the exchange payload
-    if (o->shard_axis == AVI_SHARD_SAMPLES && ctx->nranks > 1) AVI_CHECK(avi_exchange(ctx, o->acc, o->acc_len));
+    if (o->shard_axis == AVI_SHARD_SAMPLES && ctx->nranks > 1 && !o->fused_exchange)
+        AVI_CHECK(avi_exchange(ctx, o->acc, o->acc_len));
     return AVI_OK;
 }
 

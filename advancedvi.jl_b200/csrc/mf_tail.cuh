@@ -5,6 +5,7 @@
 
 #include "avi_internal.cuh"
 #include "device_utils.cuh"
+#include "comm_dev.cuh"
 #include "mf_finalize.cuh"
 
 // scalar state sc[]: 0 averaging t | 1 DoG v | 2 DoG r | 3 beta1^t | 4 beta2^t | 5 last step size
@@ -27,6 +28,8 @@ struct MfTailArgs {
     ObjDeviceState* st;
     float* trace; int trace_cap;
     UpdArgs a;
+    CommPeers comm;    // comm.nranks > 1: the sample-sharded exchange of `acc` runs inside this kernel
+    long long acc_len;
 };
 
 // block sum for a 1024-thread CTA addressed by a linear thread id (any block shape); fixed tree
@@ -68,14 +71,41 @@ __device__ __forceinline__ void mf_finalize_update_body(const MfTailArgs& t) {
     const bool adam = a.rule == AVI_RULE_ADAM, dog = a.rule == AVI_RULE_DOG || a.rule == AVI_RULE_DOWG;
     const bool polyavg = a.averager == AVI_AVG_POLYNOMIAL;
     float v[ITEMS][4], x[ITEMS][2], s1m[ITEMS][2], s2m[ITEMS][2], av[ITEMS][2];
+    // Fused exchange (sample sharding): publish my partial sums in my symmetric slot, release-store the sequence
+    // number into every peer's flag word, acquire-wait for all peers, then take every needed entry as the sum
+    // over the ranks' slots IN RANK ORDER: identical bits on all ranks, no separate all-reduce launch.
+    const int NR = t.comm.nranks;
+    unsigned int seq = 0;
+    long long soff = 0;
+    if (NR > 1) {
+        seq = *reinterpret_cast<volatile unsigned int*>(&t.comm.dev->seq) + 1u;
+        soff = (long long)(seq & 1u) * t.comm.slot_stride;
+        float* mine = t.comm.t.data[t.comm.rank] + soff;
+        for (long long i = tid; i < t.acc_len; i += 1024) mine[i] = acc[i];
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0)
+            for (int r = 0; r < NR; ++r) st_release_sys(t.comm.t.flags[r] + t.comm.rank, seq);
+        if (tid < NR) {
+            const unsigned int* f = t.comm.t.flags[t.comm.rank] + tid;
+            while ((int)(ld_acquire_sys(f) - seq) < 0) { }
+        }
+        __syncthreads();
+    }
+    auto acc_at = [&](size_t idx) -> float {
+        if (NR <= 1) return acc[idx];
+        float s = 0.f;
+        for (int r = 0; r < NR; ++r) s += ld_relaxed_sys(t.comm.t.data[r] + soff + idx);
+        return s;
+    };
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
         const int i = tid + k * 1024;
         const bool ok = i < D;
-        v[k][0] = ok ? acc[i] : 0.f;
-        v[k][1] = ok ? acc[accv + i] : 0.f;
-        v[k][2] = ok && need23 ? acc[2 * (size_t)accv + i] : 0.f;
-        v[k][3] = ok && need23 ? acc[3 * (size_t)accv + i] : 0.f;
+        v[k][0] = ok ? acc_at(i) : 0.f;
+        v[k][1] = ok ? acc_at((size_t)accv + i) : 0.f;
+        v[k][2] = ok && need23 ? acc_at(2 * (size_t)accv + i) : 0.f;
+        v[k][3] = ok && need23 ? acc_at(3 * (size_t)accv + i) : 0.f;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const size_t p = (size_t)h * D + i;
@@ -88,8 +118,8 @@ __device__ __forceinline__ void mf_finalize_update_body(const MfTailArgs& t) {
     float sl = 0.f, sq = 0.f;
     if (deferred)
         for (int m = tid; m < Mloc; m += 1024) { sl += logp[m]; sq += esq[m]; }
-    const float* scal = acc + 4 * (size_t)accv;
-    const float c0 = scal[0], c1 = scal[1], c2 = scal[2], c3 = scal[3];
+    const size_t sbase = 4 * (size_t)accv;
+    const float c0 = acc_at(sbase), c1 = acc_at(sbase + 1), c2 = acc_at(sbase + 2), c3 = acc_at(sbase + 3);
     const float shift = out[3];
     const int halted = st->halted;
     const float b1t = sc[SC_B1T], b2t = sc[SC_B2T], t_avg = sc[SC_T], v_old = sc[SC_V], r_old = sc[SC_R];
@@ -155,6 +185,7 @@ __device__ __forceinline__ void mf_finalize_update_body(const MfTailArgs& t) {
             }
         }
     }
+    if (tid == 0 && NR > 1) *reinterpret_cast<volatile unsigned int*>(&t.comm.dev->seq) = seq;
     if (tid == 0 && !halted) {
         out[0] = value; out[1] = elbo; out[2] = S.logdet; out[3] = shift_next;
         const int tp = st->trace_pos;

@@ -165,7 +165,15 @@ int32_t enqueue_iteration(avi_opt* op, bool subsampled, int64_t batch) {
     tail.logp = o->logp; tail.esq = o->esq; tail.Mloc = o->Mloc; tail.deferred = avi_obj_defers_scalars(o) ? 1 : 0;
     tail.lam = op->lam; tail.grad = o->grad; tail.m1 = op->m1; tail.m2 = op->m2; tail.avg = op->avg; tail.sc = op->sc;
     tail.out = o->out; tail.st = o->d_state; tail.trace = op->trace; tail.trace_cap = op->trace_cap; tail.a = a;
-    AVI_CHECK(avi_objective_local(o, op->lam));
+    // sample sharding over the native NVLink exchange: the tail kernel performs the all-reduce itself
+    tail.comm.nranks = 1; tail.acc_len = o->acc_len;
+    const bool mf_tail = o->family == AVI_MEANFIELD && o->D <= 8 * 1024;
+    o->fused_exchange = mf_tail && o->shard_axis == AVI_SHARD_SAMPLES && ctx->nranks > 1 &&
+                        avi_comm_peers(ctx, o->acc_len, &tail.comm);
+    if (!o->fused_exchange) tail.comm.nranks = 1;
+    int32_t rc_local = avi_objective_local(o, op->lam);
+    o->fused_exchange = false;
+    AVI_CHECK(rc_local);
     // (running this tail inside the last CTA of the target's final kernel was measured SLOWER than its own
     // launch: profiles/README.md)
     if (o->family == AVI_MEANFIELD && o->D <= 8 * 1024) {

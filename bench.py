@@ -141,6 +141,9 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--gemm", default="tf32")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard", default="samples", choices=["rows", "samples"],
+                    help="multi-GPU axis: Monte-Carlo samples (M-axis, default, as north_star asks) "
+                         "or data rows (n-axis)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -156,21 +159,32 @@ def main():
 
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("AVI_NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     K, W = args.steps, max(args.warmup, 3)
 
     X, y = synth(N_ROWS, N_FEAT, SEED)
     ctx = avi.Context(local_rank)
-    prob = avi.LogReg(ctx, X, y, gemm=args.gemm)
     D = N_FEAT + 1
     P = 2 * D
     q0 = avi.MeanFieldGaussian(np.zeros(D, np.float32), np.ones(D, np.float32))
     alg = avi.KLMinRepGradDescent(optimizer=avi.Adam(1e-3), n_samples=N_MC, operator=avi.ClipScale())
+    rows_local = N_ROWS
+    if world > 1 and args.shard == "rows":
+        r0, rows_local = parallel.row_shard(N_ROWS, rank, world, align=32)
+        prob = avi.LogReg(ctx, X[r0:r0 + rows_local], y[r0:r0 + rows_local], n_data=N_ROWS, gemm=args.gemm)
+        prob.set_data_shard(world, N_ROWS, include_prior=(rank == 0))
+    else:
+        prob = avi.LogReg(ctx, X, y, gemm=args.gemm)
     obj = avi.Objective(SEED, alg.objective, q0, prob)
     if world > 1:
         parallel.connect(ctx, max_floats=4 * 1056 + 64, native=True)
-        m0, ml = parallel.sample_shard(N_MC, rank, world)
-        obj.set_sample_shard(m0, ml)
+        if args.shard == "rows":
+            from advancedvi_jl_b200 import _lib as _L
+            obj.set_shard_axis(_L.SHARD_ROWS)
+        else:
+            m0, ml = parallel.sample_shard(N_MC, rank, world)
+            obj.set_sample_shard(m0, ml)
     from advancedvi_jl_b200.api import _OptState
     from advancedvi_jl_b200 import _lib as L
     import ctypes as C
@@ -293,8 +307,8 @@ def main():
     bf16 = peaks.get("bf16_tflops", 1590.0)
     hbm = peaks.get("hbm_gbs", 6650.0)
     src = "measured" if peaks else "fallback"
-    m_loc = N_MC // world if world > 1 else N_MC
-    flops_fwd = 2.0 * N_ROWS * N_FEAT * m_loc
+    m_loc = N_MC // world if (world > 1 and args.shard == "samples") else N_MC
+    flops_fwd = 2.0 * rows_local * N_FEAT * m_loc
     dom = "glm_fwd" if ktime["glm_fwd"] >= ktime["glm_bwd"] else "glm_bwd"
     ach = flops_fwd / (ktime[dom] * 1e-3) / 1e12 if ktime[dom] > 0 else None
     roofline = {"bound": "tensor", "kernel": f"k_gemm_tc<{dom}>", "achieved": ach, "peak": bf16 / 2.0, "unit": "TFLOP/s",
@@ -317,7 +331,11 @@ def main():
         "vs_baseline": None, "dtype": "tf32" if args.gemm == "tf32" else "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "optimizer": "Adam(1e-3)+ClipScale+PolynomialAveraging",
                    "l2": "flushed between timed steps (256 MiB device write, untimed); per-step CUDA events",
-                   "sharding": "none" if world == 1 else f"M-axis: {m_loc} samples per rank, one-shot NVLink all-reduce",
+                   "sharding": "none" if world == 1 else
+                   (f"n-axis: {rows_local} data rows per rank, all {N_MC} samples on every rank; exchange = one-shot NVLink "
+                    f"all-reduce kernels of [sum g, sum g*eps] (2x1056 floats) and log pi ({N_MC} floats)"
+                    if args.shard == "rows" else
+                    f"M-axis: {m_loc} samples per rank; exchange = one-shot NVLink all-reduce of the partial sums"),
                    "contraction": "tcgen05 kind::tf32 (operands rounded to nearest TF32, fp32 accumulate)"
                    if args.gemm == "tf32" else "SIMT fp32"},
         "value_l2_resident": K / (warm_ms * 1e-3), "ms_per_step_l2_resident": warm_ms / K,
