@@ -311,8 +311,15 @@ def main():
     flops_fwd = 2.0 * rows_local * N_FEAT * m_loc
     dom = "glm_fwd" if ktime["glm_fwd"] >= ktime["glm_bwd"] else "glm_bwd"
     ach = flops_fwd / (ktime[dom] * 1e-3) / 1e12 if ktime[dom] > 0 else None
+    traffic = None
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["dram_bytes_per_launch"].get(dom)
+        if world > 1:
+            traffic = None   # captured at N = 1
+    except Exception:   # noqa: BLE001
+        pass
     roofline = {"bound": "tensor", "kernel": f"k_gemm_tc<{dom}>", "achieved": ach, "peak": bf16 / 2.0, "unit": "TFLOP/s",
-                "frac": (ach / (bf16 / 2.0)) if ach else None, "traffic": None,
+                "frac": (ach / (bf16 / 2.0)) if ach else None, "traffic": traffic,
                 "peak_note": f"kind::tf32 dense = 1/2 of the {src} bf16 cuBLAS peak ({bf16} TFLOP/s); "
                              f"frac of the bf16 figure itself: {ach / bf16 if ach else None}",
                 "flops_per_launch": flops_fwd,
