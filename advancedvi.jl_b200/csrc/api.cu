@@ -323,6 +323,7 @@ int32_t avi_obj_destroy(avi_obj* o) {
     if (!o) return AVI_OK;
     cudaStreamSynchronize(o->ctx->stream);
     obj_free_buffers(o);
+    avi_fr_free(o);
     avi_free(o->d_state); avi_free(o->d_lambda); avi_free(o->acc); avi_free(o->grad); avi_free(o->out);
     if (o->h_lambda) cudaFreeHost(o->h_lambda);
     if (o->h_grad) cudaFreeHost(o->h_grad);

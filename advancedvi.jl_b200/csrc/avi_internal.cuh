@@ -179,6 +179,12 @@ struct avi_model {
 // This vector is what the exchange step all-reduces when the samples are sharded.
 enum { ACC_NSCAL = 8 };
 
+// scratch of the tensor-core full-rank contractions (family_fr.cu)
+struct FrWork {
+    float *Lr3 = nullptr, *Er3 = nullptr, *Et3 = nullptr, *Wt3 = nullptr, *Ut3 = nullptr, *zslab = nullptr;
+    size_t Lr3_cap = 0, Er3_cap = 0, Et3_cap = 0, Wt3_cap = 0, Ut3_cap = 0, zslab_cap = 0;
+};
+
 struct avi_obj {
     avi_ctx* ctx = nullptr;
     avi_model* model = nullptr;
@@ -206,6 +212,7 @@ struct avi_obj {
     float* acc = nullptr;        // acc_len
     float* grad = nullptr;       // P
     float* out = nullptr;        // 4 : value, elbo, logdet, ScoreGrad centring shift
+    FrWork fr;
     // pinned host staging
     float* h_lambda = nullptr;   // P
     float* h_grad = nullptr;     // P + 4
@@ -248,7 +255,8 @@ int32_t avi_obj_ensure_capacity(avi_obj* o, int M);
 int32_t avi_family_sample(avi_obj* o, const float* lambda, float* Z, float* E, float* esq, int Mloc,
                           int m0, const ObjDeviceState* st, const ObjDeviceState* ov, const SampleHook* hook = nullptr);
 int32_t avi_objective_local(avi_obj* o, const float* lambda);          // sample + model + reduce -> acc
-int32_t avi_objective_finalize(avi_obj* o, const float* lambda, float* grad, float* out);  // acc -> grad
+// acc -> grad (skip_fr_matrix: leave the D x D block of a full-rank gradient to the caller's fused update)
+int32_t avi_objective_finalize(avi_obj* o, const float* lambda, float* grad, float* out, bool skip_fr_matrix = false);
 // forward-only chunk for estimate_objective: sums_dev = {sum logp, sum |eps|^2, logdet}
 int32_t avi_objective_forward_chunk(avi_obj* o, const float* lambda, int m0, int Mc, const ObjDeviceState* ov,
                                     float* sums_dev);
@@ -265,6 +273,12 @@ int32_t avi_gemm_simt(avi_ctx* ctx, const float* A, long long sa_r, long long sa
                       int Nb, int K, float alpha, int tri_b = 0);
 // U = L^{-T} E for a column-major lower-triangular L (D x D): row m of U solves L' u = e_m.
 int32_t avi_trsm_lt(avi_ctx* ctx, const float* L, int D, const float* E, float* U, int ld, int M);
+
+// full-rank family on the tensor cores (family_fr.cu)
+bool avi_fr_tc_ok(const avi_obj* o, int Mloc);
+int32_t avi_fr_affine_tc(avi_obj* o, const float* lambda, const float* E, float* Z, int Mloc);
+int32_t avi_fr_outer_tc(avi_obj* o, const float* W, const float* E, float* C, int Mloc, int which, bool reuse_E);
+void avi_fr_free(avi_obj* o);
 
 // models
 int32_t avi_model_mvnormal_diag_make(avi_ctx* ctx, const float* mu, const float* sigma, int D, avi_model** out);

@@ -15,6 +15,7 @@
 #include "avi_internal.cuh"
 #include "device_utils.cuh"
 #include "glm_prior.cuh"
+#include "fr_finalize.cuh"
 #include "mf_finalize.cuh"
 #include "tc_common.cuh"
 
@@ -239,21 +240,8 @@ __global__ void k_finalize_fr_mat(const float* __restrict__ C1, const float* __r
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (size_t)D * D) return;
     const int j = (int)(idx / D), i = (int)(idx % D);   // column-major: entry (i, j)
-    const float invM = 1.0f / (float)M;
     float g = 0.0f;
-    if (i >= j) {
-        if (objective == AVI_REPGRAD) {
-            g = -C1[idx] * invM;
-            if (i == j) {
-                float inv = 1.0f / __ldg(lambda + D + idx);
-                if (entropy == AVI_ENT_CLOSEDFORM || entropy == AVI_ENT_MONTECARLO) g -= inv;
-                else if (entropy == AVI_ENT_STL_ZEROGRAD) g += inv;
-            }
-        } else {
-            const float fbar = scal[2] * invM;
-            g = (C1[idx] - fbar * C2[idx]) * invM;
-        }
-    }
+    if (i >= j) g = fr_grad_entry(C1, C2, scal, __ldg(lambda + D + idx), idx, i, j, M, objective, entropy);
     grad[D + idx] = g;
 }
 
@@ -335,10 +323,14 @@ int32_t avi_family_sample(avi_obj* o, const float* lambda, float* Z, float* E, f
     } else {
         LAUNCH_SAMPLE(true, false, SampleHook{});
         AVI_LAUNCHED(ctx);
-        // Z[m][i] = sum_{j <= i} E[m][j] * L[i + D*j]  (scale * eps, location_scale.jl:76)
-        AVI_CHECK(avi_gemm_simt(ctx, E, o->ld, 1, lambda + o->D, 1, o->D, Z, o->ld, 1, Mloc, o->D, o->D, 1.0f, 1));
-        k_fr_add_mu<<<Mloc, 256, 0, ctx->stream>>>(lambda, o->D, o->ld, Z);
-        AVI_LAUNCHED(ctx);
+        // Z[m][i] = mu[i] + sum_{j <= i} E[m][j] * L[i + D*j]  (scale * eps, location_scale.jl:76)
+        if (avi_fr_tc_ok(o, Mloc)) {
+            AVI_CHECK(avi_fr_affine_tc(o, lambda, E, Z, Mloc));
+        } else {   // very large forward-only batches (estimate_objective): exact-fp32 SIMT contraction
+            AVI_CHECK(avi_gemm_simt(ctx, E, o->ld, 1, lambda + o->D, 1, o->D, Z, o->ld, 1, Mloc, o->D, o->D, 1.0f, 1));
+            k_fr_add_mu<<<Mloc, 256, 0, ctx->stream>>>(lambda, o->D, o->ld, Z);
+            AVI_LAUNCHED(ctx);
+        }
     }
 #undef LAUNCH_SAMPLE
     return AVI_OK;
@@ -415,12 +407,15 @@ int32_t avi_objective_local(avi_obj* o, const float* lambda) {
         k_colsum<<<(unsigned)ceil_div(D, 32), dim3(32, 32), 0, ctx->stream>>>(W, ld, Mloc, D, o->acc);
         AVI_LAUNCHED(ctx);
         // C1[j*D + i] = sum_m W[m][i] * E[m][j]: contraction over the samples
-        AVI_CHECK(avi_gemm_simt(ctx, o->E, 1, ld, W, 1, ld, C1, D, 1, D, D, Mloc, 1.0f));
+        const bool tc_ok = avi_fr_tc_ok(o, Mloc);
+        if (tc_ok) AVI_CHECK(avi_fr_outer_tc(o, W, o->E, C1, Mloc, 0, false));
+        else AVI_CHECK(avi_gemm_simt(ctx, o->E, 1, ld, W, 1, ld, C1, D, 1, D, D, Mloc, 1.0f));
         if (!rep) {
             k_colsum<<<(unsigned)ceil_div(D, 32), dim3(32, 32), 0, ctx->stream>>>(o->U, ld, Mloc, D,
                                                                                   o->acc + 2 * (size_t)accv);
             AVI_LAUNCHED(ctx);
-            AVI_CHECK(avi_gemm_simt(ctx, o->E, 1, ld, o->U, 1, ld, C2, D, 1, D, D, Mloc, 1.0f));
+            if (tc_ok) AVI_CHECK(avi_fr_outer_tc(o, o->U, o->E, C2, Mloc, 1, true));
+            else AVI_CHECK(avi_gemm_simt(ctx, o->E, 1, ld, o->U, 1, ld, C2, D, 1, D, D, Mloc, 1.0f));
         }
     }
     // sample sharding: the partial sums are the exchange payload
@@ -439,7 +434,7 @@ int32_t avi_objective_forward_chunk(avi_obj* o, const float* lambda, int m0, int
     return AVI_OK;
 }
 
-int32_t avi_objective_finalize(avi_obj* o, const float* lambda, float* grad, float* out) {
+int32_t avi_objective_finalize(avi_obj* o, const float* lambda, float* grad, float* out, bool skip_fr_matrix) {
     avi_ctx* ctx = o->ctx;
     const int D = o->D, accv = o->accv;
     if (o->family == AVI_MEANFIELD) {
@@ -453,9 +448,11 @@ int32_t avi_objective_finalize(avi_obj* o, const float* lambda, float* grad, flo
         const float* C2 = C1 + (size_t)D * D;
         size_t n = (size_t)D * D;
         // the matrix part reads fbar from scal before k_finalize_fr_vec rewrites out[3]
-        k_finalize_fr_mat<<<(unsigned)ceil_div(n, 256), 256, 0, ctx->stream>>>(C1, C2, scal, lambda, D, o->M,
-                                                                              o->objective, o->entropy, grad);
-        AVI_LAUNCHED(ctx);
+        if (!skip_fr_matrix) {   // (the fused update kernel computes these entries on the fly)
+            k_finalize_fr_mat<<<(unsigned)ceil_div(n, 256), 256, 0, ctx->stream>>>(C1, C2, scal, lambda, D, o->M,
+                                                                                  o->objective, o->entropy, grad);
+            AVI_LAUNCHED(ctx);
+        }
         k_finalize_fr_vec<<<1, 1024, 0, ctx->stream>>>(o->acc, accv, lambda, D, o->M, o->objective, o->entropy, grad, out);
         AVI_LAUNCHED(ctx);
     }

@@ -547,10 +547,10 @@ static int max_active_clusters(avi_ctx* ctx, int csz) {
 
 // Tiling plan.  split_k = false: many b-chunks, full K per unit (the epilogue is non-linear: GLM forward);
 // split_k = true: few output tiles, K split across the chip (linear epilogues).
-// Cost model per 32-wide k-block: max(MMA time 2*nt cycles, bytes one SM must take in / 64 B per cycle).
-// Measured (profiles/): the fp32-sized operands make the mainloop SM-ingress-bound, and a multicast tile
-// still has to enter every SM that uses it, so clusters do not pay here; they stay available (force_cluster
-// = 2, AVI_TC_CLUSTER=2) and tested, and are what a cta_group::2 version would build on.
+// Cost model (cycles, from profiles/r1_phase_timeline.txt): a kind::tf32 M=128 MMA costs ~145 cycles whatever
+// nt <= 256 is, i.e. 580 per 32-wide k-block; the epilogue costs ~58 cycles per column; ~6000 fixed per wave.
+// Operand traffic is not the limit, so cluster multicast / CTA pairs do not pay at these sizes; they stay
+// available (force_cluster = 2 / AVI_TC_CLUSTER=2, AVI_TC_PAIR) and tested.
 int32_t avi_tc_plan(avi_ctx* ctx, int64_t Ma, int64_t Nb, int64_t K, bool split_k, int force_cluster, TcParams* p) {
     const int sms = ctx->prop.multiProcessorCount;
     p->Ma = (int)Ma; p->Nb = (int)Nb;
@@ -581,9 +581,8 @@ int32_t avi_tc_plan(avi_ctx* ctx, int64_t Ma, int64_t Nb, int64_t K, bool split_
                 }
                 const int64_t units = tiles * n_ksplit;
                 const int64_t waves = ceil_div(units, maxc);
-                const double bytes_sm = (double)A_TILE_BYTES + nt * BK * 4.0;
-                const double per_kb = std::max(2.0 * nt, bytes_sm / 64.0) + 20.0;
-                double cost = (double)waves * (per_kb * kbps + 6000.0) + (csz > 1 ? 500.0 : 0.0);
+                const double per_kb = 580.0;
+                double cost = (double)waves * (per_kb * kbps + 58.0 * nt + 6000.0) + (csz > 1 ? 500.0 : 0.0);
                 if (force_cluster == 2 && csz > 1) cost *= 0.25;   // testing / experiments: prefer clusters
                 if (cost < best) {
                     best = cost;
@@ -610,9 +609,8 @@ int32_t avi_tc_plan(avi_ctx* ctx, int64_t Ma, int64_t Nb, int64_t K, bool split_
                 n_ksplit = (int)ceil_div(p->n_kblk, kbps);
             }
             const int64_t waves = ceil_div(tiles * n_ksplit, maxp);
-            const double bytes_sm = (double)A_TILE_BYTES + (nt / 2) * BK * 4.0;
-            const double per_kb = std::max(2.0 * nt, bytes_sm / 64.0) + 20.0;
-            double cost = (double)waves * (per_kb * kbps + 6500.0);
+            const double per_kb = 520.0;
+            double cost = (double)waves * (per_kb * kbps + 58.0 * nt + 8000.0);
             if (pair_env == 2) cost *= 0.25;
             if (cost < best) {
                 best = cost;
@@ -700,5 +698,25 @@ int32_t avi_tc_launch(avi_ctx* ctx, int epi, const CUtensorMap& tmA, const CUten
                 "mma-issued %.0f acc-ready %.0f epi-done %.0f exit %.0f\n", epi, grid, (t6 - t0) * 1e-3, avg[0], avg[1], avg[2], avg[3],
                 avg[4], avg[5], avg[6]);
     }
+    return AVI_OK;
+}
+
+// C[ks][b * ldc + a] = sum_k A[a, k] B[b, k] over k-split ks (EPI_STORE).  split_k = false: one slab (C itself).
+// Returns the number of slabs written; slab s starts at C + s * slab_stride.
+int32_t avi_tc_gemm_store(avi_ctx* ctx, const float* A, int64_t Ma, int64_t lda, const float* B, int64_t Nb, int64_t ldb,
+                          int64_t K, float* C, int64_t ldc, int64_t slab_stride, int max_slabs, int* n_slabs) {
+    TcParams p{};
+    AVI_CHECK(avi_tc_plan(ctx, Ma, Nb, K, max_slabs > 1, 0, &p));
+    if (p.n_ksplit > max_slabs) {   // the caller's slab buffer bounds the split
+        p.n_ksplit = max_slabs;
+        p.kb_per_split = (int)ceil_div(p.n_kblk, p.n_ksplit);
+        p.n_ksplit = (int)ceil_div(p.n_kblk, p.kb_per_split);
+    }
+    CUtensorMap tmA, tmB;
+    AVI_CHECK(avi_tc_make_tmap(ctx, &tmA, A, Ma, K, lda, 128 / p.cb));
+    AVI_CHECK(avi_tc_make_tmap(ctx, &tmB, B, Nb, K, ldb, p.pair ? p.nt / 2 : p.nt / p.ca));
+    p.C = C; p.ldc = (int)ldc; p.slab_stride = slab_stride;
+    AVI_CHECK(avi_tc_launch(ctx, EPI_STORE, tmA, tmB, p));
+    if (n_slabs) *n_slabs = p.n_ksplit;
     return AVI_OK;
 }

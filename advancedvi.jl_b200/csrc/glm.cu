@@ -118,7 +118,9 @@ k_glm_post_sums(const float* __restrict__ Z, const float* __restrict__ E, int ld
     }
 }
 
-// full gradient tail: G[m][i] = sum_s slab[s][m][i] - beta_i / sigma^2, G[m][d] = dlogp/deta, logp[m]
+// full gradient tail: G[m][i] = sum_s slab[s][m][i] - beta_i / sigma^2, G[m][d] = dlogp/deta, logp[m].
+// One CTA per sample, a thread per coordinate quad: the nslab partial sums are fetched as independent 16-byte
+// loads (ld % 4 == 0 and every buffer is 16-byte aligned).
 __global__ void __launch_bounds__(256)
 k_glm_post_full(const float* __restrict__ Z, int ld, int d, const float4* __restrict__ pre,
                 const float* __restrict__ slabs, int nslab, long long slab_stride,
@@ -127,21 +129,30 @@ k_glm_post_full(const float* __restrict__ Z, int ld, int d, const float4* __rest
     const int m = blockIdx.x;
     const float4 pm = pre[m];
     if (G) {
-        for (int i = threadIdx.x; i < ld; i += blockDim.x) {
-            float g = 0.0f;
-            if (i < d) {
-                for (int s = 0; s < nslab; ++s) g += slabs[(size_t)s * slab_stride + (size_t)m * ld + i];
-                g = fmaf(-Z[(size_t)m * ld + i], pm.y, g);
-            } else if (i == d) {
-                g = pm.z;
+        for (int q = threadIdx.x; q < ld / 4; q += blockDim.x) {
+            const size_t base = (size_t)m * ld + 4 * q;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 6
+            for (int s = 0; s < nslab; ++s) {
+                const float4 v = *reinterpret_cast<const float4*>(slabs + (size_t)s * slab_stride + base);
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
             }
-            G[(size_t)m * ld + i] = g;
+            const float4 z = *reinterpret_cast<const float4*>(Z + base);
+            float gv[4] = {acc.x, acc.y, acc.z, acc.w};
+            const float zv[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int i = 4 * q + c;
+                gv[c] = i < d ? fmaf(-zv[c], pm.y, gv[c]) : (i == d ? pm.z : 0.0f);
+            }
+            *reinterpret_cast<float4*>(G + base) = make_float4(gv[0], gv[1], gv[2], gv[3]);
         }
     }
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {   // fixed shuffle tree over the partial log-likelihood sums
         float s = 0.f;
-        for (int q = 0; q < nparts; ++q) s += llpart[(size_t)q * ldpart + m];
-        logp[m] = fmaf(w, s, pm.x);
+        for (int q = threadIdx.x; q < nparts; q += 32) s += llpart[(size_t)q * ldpart + m];
+        s = warp_sum(s);
+        if (threadIdx.x == 0) logp[m] = fmaf(w, s, pm.x);
     }
 }
 

@@ -12,6 +12,7 @@
 
 #include "avi_internal.cuh"
 #include "device_utils.cuh"
+#include "fr_finalize.cuh"
 #include "mf_finalize.cuh"
 #include "mf_tail.cuh"
 
@@ -116,6 +117,34 @@ k_mf_finalize_update(MfTailArgs t) {
     mf_finalize_update_body<ITEMS>(t);
 }
 
+// Full-rank: gradient of the scale block computed on the fly from the reduced sums (no D x D gradient pass of its
+// own) + rule + operator + averager.  Only the lower triangle is touched: the strict upper triangle of L, of its
+// gradient and of the Adam moments is identically zero.  Scalars / trace / step are committed by k_commit.
+__global__ void __launch_bounds__(256)
+k_fr_update(float* __restrict__ lam, float* __restrict__ grad, float* __restrict__ m1, float* __restrict__ m2,
+            float* __restrict__ avg, const float* __restrict__ sc, const float* __restrict__ out,
+            const ObjDeviceState* __restrict__ st, const float* __restrict__ C1, const float* __restrict__ C2,
+            const float* __restrict__ scal, int M, int objective, int entropy, UpdArgs a) {
+    if (st->halted || !isfinite(out[0])) return;
+    const int D = a.D;
+    const float eta = a.rule == AVI_RULE_DESCENT ? a.h0 : 0.f;
+    const float b1t = sc[SC_B1T], b2t = sc[SC_B2T], w = (a.avg_param + 1.0f) / (sc[SC_T] + a.avg_param);
+    const long long n = (long long)D + (long long)D * D;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
+        float g;
+        if (p < D) {
+            g = grad[p];   // location block: written by k_finalize_fr_vec
+        } else {
+            const size_t idx = (size_t)(p - D);
+            const int j = (int)(idx / D), i = (int)(idx % D);
+            if (i < j) continue;
+            g = fr_grad_entry(C1, C2, scal, lam[p], idx, i, j, M, objective, entropy);
+            grad[p] = g;
+        }
+        update_entry(p, g, lam, m1, m2, avg, a, eta, b1t, b2t, w);
+    }
+}
+
 __global__ void k_commit(float* __restrict__ sc, const float* __restrict__ out, ObjDeviceState* __restrict__ st,
                          float* __restrict__ trace, int trace_cap, const float* __restrict__ norm_part, UpdArgs a) {
     if (threadIdx.x != 0) return;
@@ -184,6 +213,20 @@ int32_t enqueue_iteration(avi_opt* op, bool subsampled, int64_t batch) {
         else if (items <= 4) LAUNCH_TAIL(4);
         else LAUNCH_TAIL(8);
 #undef LAUNCH_TAIL
+        AVI_LAUNCHED(ctx);
+        return AVI_OK;
+    }
+    const bool dog_rule = op->rule == AVI_RULE_DOG || op->rule == AVI_RULE_DOWG;
+    if (o->family == AVI_FULLRANK && !dog_rule) {
+        AVI_CHECK(avi_objective_finalize(o, op->lam, o->grad, o->out, /*skip_fr_matrix=*/true));
+        const float* scal = o->acc + 4 * (size_t)o->accv;
+        const float* C1 = scal + ACC_NSCAL;
+        const float* C2 = C1 + (size_t)o->D * o->D;
+        const int nb = (int)std::min<int64_t>(ceil_div(op->P, 256 * 4), 8 * ctx->prop.multiProcessorCount);
+        k_fr_update<<<nb, 256, 0, ctx->stream>>>(op->lam, o->grad, op->m1, op->m2, op->avg, op->sc, o->out, o->d_state, C1,
+                                                 C2, scal, o->M, o->objective, o->entropy, a);
+        AVI_LAUNCHED(ctx);
+        k_commit<<<1, 32, 0, ctx->stream>>>(op->sc, o->out, o->d_state, op->trace, op->trace_cap, op->norm_part, a);
         AVI_LAUNCHED(ctx);
         return AVI_OK;
     }
