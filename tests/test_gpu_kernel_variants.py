@@ -1,0 +1,27 @@
+"""The optional code paths of the tcgen05 kernel -- cluster TMA multicast, CTA pairs (cta_group::2), no PDL,
+no CUDA graph -- are selected by environment variables read when the library is first used, so each variant
+runs a subset of the parity tests in its own process."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SUBSET = ["tests/test_gpu_parity.py::test_glm_logdensity_and_gradient",
+          "tests/test_gpu_parity.py::test_repgrad_logreg_matches_oracle",
+          "tests/test_gpu_parity.py::test_fused_step_trajectory_matches_oracle",
+          "tests/test_gpu_parity.py::test_determinism_and_warm_start",
+          "tests/test_gpu_parity.py::test_c2_full_size_properties"]
+
+
+@pytest.mark.parametrize("env", [{"AVI_TC_CLUSTER": "2"}, {"AVI_TC_PAIR": "2"}, {"AVI_PDL": "0"}, {"AVI_NO_GRAPH": "1"}],
+                         ids=["cluster_multicast", "cta_pair", "no_pdl", "no_graph"])
+def test_variant(env):
+    e = dict(os.environ)
+    e.update(env)
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider"] + SUBSET,
+                       cwd=ROOT, env=e, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
