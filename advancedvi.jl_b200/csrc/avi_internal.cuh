@@ -134,6 +134,7 @@ struct SampleHook {
     int kind = 0;
     int d = 0, variant = 0, include_prior = 1;
     float* Zt = nullptr;
+    int zt_ld = 0, zt_seg = 0;   // row pitch of Zt; zt_seg > 0: 3xTF32 split [hi | hi | lo] in segments of zt_seg
     float4* pre = nullptr;
 };
 

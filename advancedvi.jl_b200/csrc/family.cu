@@ -72,15 +72,26 @@ k_sample(const float* __restrict__ lambda, int D, int ld, int m0, int Mloc, cons
             if (HOOK) {
                 const bool is_beta = i + c < hk.d;
                 bsq = is_beta ? fmaf(zv[c], zv[c], bsq) : bsq;
-                zt[c] = is_beta ? tc::round_tf32(zv[c]) : 0.0f;
+                zt[c] = is_beta ? zv[c] : 0.0f;
                 if (i + c == hk.d) eta = zv[c];
             }
         }
         *reinterpret_cast<float4*>(E + (size_t)m * ld + i) = make_float4(ev[0], ev[1], ev[2], ev[3]);
         if (!FULLRANK)
             *reinterpret_cast<float4*>(Z + (size_t)m * ld + i) = make_float4(zv[0], zv[1], zv[2], zv[3]);
-        if (HOOK && hk.Zt)
-            *reinterpret_cast<float4*>(hk.Zt + (size_t)m * ld + i) = make_float4(zt[0], zt[1], zt[2], zt[3]);
+        if (HOOK && hk.Zt) {
+            float hi[4], lo[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { hi[c] = tc::round_tf32(zt[c]); lo[c] = tc::round_tf32(zt[c] - hi[c]); }
+            float* row = hk.Zt + (size_t)m * hk.zt_ld + i;
+            if (hk.zt_seg == 0) {
+                *reinterpret_cast<float4*>(row) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            } else if (i < hk.zt_seg) {   // 3xTF32: [hi | hi | lo]
+                *reinterpret_cast<float4*>(row) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<float4*>(row + hk.zt_seg) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<float4*>(row + 2 * hk.zt_seg) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            }
+        }
     }
     float tot = warp_sum(part);
     if (HOOK) { bsq = warp_sum(bsq); eta = warp_sum(eta); }   // eta is non-zero in exactly one lane

@@ -120,14 +120,29 @@ __device__ __forceinline__ void epilogue_unit(const TcParams& p, SmemCtl* ctl, i
                     }
                     const bool ok = b0 + j < p.Nb;
                     s1 += ok ? lp : 0.0f;
-                    r[j] = ok ? tc::round_tf32(p.w * rr) : 0.0f;
+                    r[j] = ok ? p.w * rr : 0.0f;
+                }
+                float rlo[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float hi = tc::round_tf32(r[j]);
+                    rlo[j] = tc::round_tf32(r[j] - hi);
+                    r[j] = hi;
                 }
                 // (staging this tile through shared memory for 128-byte row stores was measured slower: the
                 // extra STS + barrier cost more than the 32-byte-sector stores; profiles/README.md)
-                if (a_ok && b0 < p.ldc) {
+                if (a_ok && b0 < (p.r_seg ? p.r_seg : p.ldc)) {
                     float4* dst = reinterpret_cast<float4*>(p.C + (size_t)a * p.ldc + b0);
                     dst[0] = make_float4(r[0], r[1], r[2], r[3]);
                     dst[1] = make_float4(r[4], r[5], r[6], r[7]);
+                    if (p.r_seg) {   // 3xTF32: R is the B operand of the backward contraction: [hi | lo | hi]
+                        float4* dl = reinterpret_cast<float4*>(p.C + (size_t)a * p.ldc + p.r_seg + b0);
+                        dl[0] = make_float4(rlo[0], rlo[1], rlo[2], rlo[3]);
+                        dl[1] = make_float4(rlo[4], rlo[5], rlo[6], rlo[7]);
+                        float4* dh = reinterpret_cast<float4*>(p.C + (size_t)a * p.ldc + 2 * (size_t)p.r_seg + b0);
+                        dh[0] = make_float4(r[0], r[1], r[2], r[3]);
+                        dh[1] = make_float4(r[4], r[5], r[6], r[7]);
+                    }
                 }
             } else {
                 float* Cs = p.C + (size_t)ks * p.slab_stride;

@@ -26,6 +26,7 @@ struct TcParams {
     long long slab_stride;
     const float* y;      // FWD: response per data row (b)
     float w;             // FWD: likelihood adjustment folded into R
+    int r_seg;           // FWD, 3xTF32: R rows hold [hi | lo | hi] in segments of r_seg floats (0: plain TF32)
     int likelihood;
     const float* E;      // BWD: eps [b][lde]
     int lde;

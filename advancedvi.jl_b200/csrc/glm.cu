@@ -20,17 +20,31 @@
 
 namespace {
 
+// split x = hi + lo (both TF32, round to nearest) for the 3xTF32 mode; see family_fr.cu for the K-concatenation
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+    hi = tc::round_tf32(x);
+    lo = tc::round_tf32(x - hi);
+}
+
 // per-sample prior pieces: pre[m] = {prior_lp, 1/sigma^2, d logp / d eta, |beta|^2}
 __global__ void __launch_bounds__(256)
 k_glm_pre(const float* __restrict__ Z, int ld, int d, int variant, int include_prior, float* __restrict__ Zt,
-          float4* __restrict__ pre) {
+          int zt_ld, int zt_seg, float4* __restrict__ pre) {
     __shared__ float sm[33];
     const int m = blockIdx.x;
     float part = 0.f;
-    for (int i = threadIdx.x; i < ld; i += blockDim.x) {
+    const int iend = zt_seg > 0 ? max(ld, zt_seg) : ld;
+    for (int i = threadIdx.x; i < iend; i += blockDim.x) {
         float z = i < d ? Z[(size_t)m * ld + i] : 0.0f;
         part = fmaf(z, z, part);
-        if (Zt) Zt[(size_t)m * ld + i] = tc::round_tf32(z);
+        if (Zt) {
+            if (zt_seg == 0) { if (i < zt_ld) Zt[(size_t)m * zt_ld + i] = tc::round_tf32(z); }
+            else if (i < zt_seg) {   // 3xTF32: [hi | hi | lo]
+                float hi, lo; split_tf32(z, hi, lo);
+                float* row = Zt + (size_t)m * zt_ld;
+                row[i] = hi; row[zt_seg + i] = hi; row[2 * zt_seg + i] = lo;
+            }
+        }
     }
     const float bsq = block_sum(part, sm);
     if (threadIdx.x == 0) pre[m] = glm_prior_terms(bsq, Z[(size_t)m * ld + d], d, variant, include_prior);
@@ -156,32 +170,53 @@ k_glm_post_full(const float* __restrict__ Z, int ld, int d, const float4* __rest
     }
 }
 
-// column-major host layout (n x d, ldsrc = n) -> Xr [n][dK] and Xc [d][nP], optionally TF32-rounded
-__global__ void k_glm_layout(const float* __restrict__ src, long long n, int d, int dK, long long nP, int round,
-                             float* __restrict__ Xr, float* __restrict__ Xc) {
+// column-major host layout (n x d, ldsrc = n) -> Xr [n][dK] and Xc [d][nP].
+// mode 0: exact copy; 1: TF32-rounded; 2 (3xTF32): Xr rows hold [hi | lo | hi] in segments of segd (B-operand
+// pattern), Xc rows hold [hi | hi | lo] in segments of segn (A-operand pattern).
+__global__ void k_glm_layout(const float* __restrict__ src, long long n, int d, int dK, long long nP, int mode,
+                             int segd, long long segn, float* __restrict__ Xr, float* __restrict__ Xc) {
     __shared__ float t[32][33];
     const long long r0 = (long long)blockIdx.x * 32;
     const int c0 = blockIdx.y * 32;
-    // read src[(c0+ty) * n + r0 + tx] (coalesced along rows)
     for (int yy = threadIdx.y; yy < 32; yy += blockDim.y) {
         long long r = r0 + threadIdx.x; int c = c0 + yy;
         float v = (r < n && c < d) ? src[(size_t)c * n + r] : 0.0f;
-        if (round) v = tc::round_tf32(v);
         t[yy][threadIdx.x] = v;
-        if (r < nP && c < d) Xc[(size_t)c * nP + r] = v;
+        if (c < d) {
+            if (mode == 2) {
+                if (r < segn) {
+                    float hi, lo; split_tf32(v, hi, lo);
+                    float* row = Xc + (size_t)c * nP;
+                    row[r] = hi; row[segn + r] = hi; row[2 * segn + r] = lo;
+                }
+            } else if (r < nP) {
+                Xc[(size_t)c * nP + r] = mode == 1 ? tc::round_tf32(v) : v;
+            }
+        }
     }
     __syncthreads();
     for (int yy = threadIdx.y; yy < 32; yy += blockDim.y) {
         long long r = r0 + yy; int c = c0 + threadIdx.x;
-        if (r < n && c < dK) Xr[(size_t)r * dK + c] = t[threadIdx.x][yy];
+        if (r >= n) continue;
+        const float v = t[threadIdx.x][yy];
+        if (mode == 2) {
+            if (c < segd) {
+                float hi, lo; split_tf32(v, hi, lo);
+                float* row = Xr + (size_t)r * dK;
+                row[c] = hi; row[segd + c] = lo; row[2 * segd + c] = hi;
+            }
+        } else if (c < dK) {
+            Xr[(size_t)r * dK + c] = mode == 1 ? tc::round_tf32(v) : v;
+        }
     }
 }
 
-// minibatch gather: rows idx[cursor*batch + j] of the full data -> contiguous batch buffers
+// minibatch gather: rows idx[cursor*batch + j] of the full data -> contiguous batch buffers (both layouts).
+// 3xTF32 (segd > 0): the source row is [hi | lo | hi]; Xc_b rows are rebuilt as [hi | hi | lo] in segments of segnb.
 __global__ void k_glm_gather(const float* __restrict__ Xr_full, const float* __restrict__ y_full, int dK, int d,
                              const int32_t* __restrict__ idx, const ObjDeviceState* __restrict__ st, long long batch,
-                             long long nPb, float* __restrict__ Xr_b, float* __restrict__ Xc_b,
-                             float* __restrict__ y_b) {
+                             long long nPb, int segd, long long segnb, float* __restrict__ Xr_b,
+                             float* __restrict__ Xc_b, float* __restrict__ y_b) {
     __shared__ float t[32][33];
     const int32_t* ix = idx + (st ? st->batch_cursor * batch : 0);
     const long long j0 = (long long)blockIdx.x * 32;
@@ -199,12 +234,24 @@ __global__ void k_glm_gather(const float* __restrict__ Xr_full, const float* __r
     __syncthreads();
     for (int yy = threadIdx.y; yy < 32; yy += blockDim.y) {
         long long j = j0 + threadIdx.x; int c = c0 + yy;
-        if (j < nPb && c < d) Xc_b[(size_t)c * nPb + j] = j < batch ? t[threadIdx.x][yy] : 0.0f;
+        const float v = j < batch ? t[threadIdx.x][yy] : 0.0f;
+        if (segd == 0) {
+            if (j < nPb && c < d) Xc_b[(size_t)c * nPb + j] = v;
+        } else if (j < segnb) {
+            if (c < segd) {                       // hi segment of the source row
+                if (c < d) { Xc_b[(size_t)c * nPb + j] = v; Xc_b[(size_t)c * nPb + segnb + j] = v; }
+            } else if (c < 2 * segd) {            // lo segment
+                if (c - segd < d) Xc_b[(size_t)(c - segd) * nPb + 2 * segnb + j] = v;
+            }
+        }
     }
 }
 
 struct Glm : avi_model {
     int d = 0, dK = 0;
+    int x3 = 0, segd = 0;             // 3xTF32: operands stored as three K segments (see k_glm_layout)
+    long long segn_full = 0, segn_b = 0, segn = 0;
+    int zt_ld = 0;
     long long n_full = 0, nP_full = 0, n_data = 0;
     int likelihood = 0, variant = 0, mode = 0;
     int nshards = 1; long long rows_global = 0; int include_prior = 1;
@@ -234,7 +281,7 @@ struct Glm : avi_model {
     bool sample_hook(int ld, int M, SampleHook* h) override {
         if (M <= 0 || ensure(M, ld) != AVI_OK) return false;
         h->kind = 1; h->d = d; h->variant = variant; h->include_prior = include_prior;
-        h->Zt = tc_mode() ? Zt : nullptr; h->pre = pre;
+        h->Zt = tc_mode() ? Zt : nullptr; h->pre = pre; h->zt_ld = zt_ld; h->zt_seg = x3 ? segd : 0;
         hooked = true;
         return true;
     }
@@ -243,16 +290,19 @@ struct Glm : avi_model {
         double rows = subsampled ? (double)n_act * nshards : (double)rows_global;
         return (float)((double)n_data / rows);
     }
-    void view_full() { Xr = Xr_full; Xc = Xc_full; y = y_full; n_act = n_full; nP = nP_full; subsampled = false; }
+    void view_full() { Xr = Xr_full; Xc = Xc_full; y = y_full; n_act = n_full; nP = nP_full; segn = segn_full; subsampled = false; }
+    long long kf() const { return x3 ? 3LL * segd : d; }        // K extent of the forward contraction
+    long long kb() const { return x3 ? 3LL * segn : n_act; }    // K extent of the backward contraction
 
     int32_t ensure(int M, int ld) {
         if (M <= capM && ld == cap_ld && n_act <= cap_n) return AVI_OK;
         avi_free(R); avi_free(Zt); avi_free(pre);
         generation++;
         capM = std::max(M, capM); cap_ld = ld; cap_n = std::max(cap_n, n_act);
-        ldR = round_up(cap_n, 32);
+        ldR = (x3 ? 3 : 1) * round_up(cap_n, 32);
+        zt_ld = x3 ? 3 * segd : ld;
         AVI_CHECK(avi_alloc(ctx, &R, (size_t)capM * ldR));
-        AVI_CHECK(avi_alloc(ctx, &Zt, (size_t)capM * ld));
+        AVI_CHECK(avi_alloc(ctx, &Zt, (size_t)capM * zt_ld));
         AVI_CHECK(avi_alloc(ctx, &pre, (size_t)capM));
         return AVI_OK;
     }
@@ -271,7 +321,8 @@ struct Glm : avi_model {
         if (hooked) {
             hooked = false;   // the sampling kernel already produced Zt and pre for these samples
         } else {
-            k_glm_pre<<<M, 256, 0, ctx->stream>>>(Z, ld, d, variant, include_prior, tc_mode() ? Zt : nullptr, pre);
+            k_glm_pre<<<M, 256, 0, ctx->stream>>>(Z, ld, d, variant, include_prior, tc_mode() ? Zt : nullptr, zt_ld,
+                                                  x3 ? segd : 0, pre);
             AVI_LAUNCHED(ctx);
         }
         if (!tc_mode()) {
@@ -284,24 +335,25 @@ struct Glm : avi_model {
             return AVI_OK;
         }
         TcParams p{};
-        AVI_CHECK(avi_tc_plan(ctx, M, n_act, d, false, cluster_mode, &p));
+        AVI_CHECK(avi_tc_plan(ctx, M, n_act, kf(), false, cluster_mode, &p));
         p.C = R; p.ldc = (int)ldR; p.y = y; p.w = w; p.likelihood = likelihood;
+        p.r_seg = x3 ? (int)segn : 0;
         p.static_op = subsampled ? 0 : 2;   // B = X rows (a minibatch copy is rewritten every step: not static)
         AVI_CHECK(ensure_buf(&llpart, &llpart_cap, (long long)p.n_bchunk * 4 * capM));
         p.part1 = llpart; p.ldpart = capM;
         CUtensorMap tmA, tmB;
-        AVI_CHECK(avi_tc_make_tmap(ctx, &tmA, Zt, M, d, ld, 128 / p.cb));
-        AVI_CHECK(avi_tc_make_tmap(ctx, &tmB, Xr, n_act, d, dK, p.pair ? p.nt / 2 : p.nt / p.ca));
+        AVI_CHECK(avi_tc_make_tmap(ctx, &tmA, Zt, M, kf(), zt_ld, 128 / p.cb));
+        AVI_CHECK(avi_tc_make_tmap(ctx, &tmB, Xr, n_act, kf(), dK, p.pair ? p.nt / 2 : p.nt / p.ca));
         AVI_CHECK(avi_tc_launch(ctx, EPI_GLM_FWD, tmA, tmB, p));
         *nparts = p.n_bchunk * 4;
         return AVI_OK;
     }
 
     int32_t backward_setup(int M, TcParams* p, CUtensorMap* tmA, CUtensorMap* tmB) {
-        AVI_CHECK(avi_tc_plan(ctx, d, M, n_act, true, cluster_mode, p));
+        AVI_CHECK(avi_tc_plan(ctx, d, M, kb(), true, cluster_mode, p));
         p->static_op = subsampled ? 0 : 1;   // A = X columns
-        AVI_CHECK(avi_tc_make_tmap(ctx, tmA, Xc, d, n_act, nP, 128 / p->cb));
-        AVI_CHECK(avi_tc_make_tmap(ctx, tmB, R, M, n_act, ldR, p->pair ? p->nt / 2 : p->nt / p->ca));
+        AVI_CHECK(avi_tc_make_tmap(ctx, tmA, Xc, d, kb(), nP, 128 / p->cb));
+        AVI_CHECK(avi_tc_make_tmap(ctx, tmB, R, M, kb(), ldR, p->pair ? p->nt / 2 : p->nt / p->ca));
         return AVI_OK;
     }
 
@@ -362,7 +414,7 @@ struct Glm : avi_model {
         if (batch <= batch_cap) return AVI_OK;
         avi_free(Xr_b); avi_free(Xc_b); avi_free(y_b);
         generation++;
-        batch_cap = batch; nP_b = round_up(batch, 32);
+        batch_cap = batch; segn_b = round_up(batch, 32); nP_b = (x3 ? 3 : 1) * segn_b;
         AVI_CHECK(avi_alloc(ctx, &Xr_b, (size_t)batch_cap * dK));
         AVI_CHECK(avi_alloc(ctx, &Xc_b, (size_t)d * nP_b));
         AVI_CHECK(avi_alloc(ctx, &y_b, (size_t)batch_cap));
@@ -371,11 +423,11 @@ struct Glm : avi_model {
     int32_t gather(const int32_t* idx_dev, long long batch, const ObjDeviceState* st) {
         AVI_CHECK(ensure_batch(batch));
         // the pitch of Xc_b follows the allocated capacity so that captured tensor maps stay valid
-        dim3 grid((unsigned)ceil_div(nP_b, 32), (unsigned)ceil_div(dK, 32));
-        k_glm_gather<<<grid, dim3(32, 8), 0, ctx->stream>>>(Xr_full, y_full, dK, d, idx_dev, st, batch, nP_b, Xr_b,
-                                                            Xc_b, y_b);
+        dim3 grid((unsigned)ceil_div(segn_b, 32), (unsigned)ceil_div(dK, 32));
+        k_glm_gather<<<grid, dim3(32, 8), 0, ctx->stream>>>(Xr_full, y_full, dK, d, idx_dev, st, batch, nP_b,
+                                                            x3 ? segd : 0, segn_b, Xr_b, Xc_b, y_b);
         AVI_LAUNCHED(ctx);
-        Xr = Xr_b; Xc = Xc_b; y = y_b; n_act = batch; nP = nP_b; subsampled = true;
+        Xr = Xr_b; Xc = Xc_b; y = y_b; n_act = batch; nP = nP_b; segn = segn_b; subsampled = true;
         return AVI_OK;
     }
     int32_t subsample(const int32_t* idx_host, int64_t batch) override {
@@ -411,12 +463,14 @@ int32_t avi_model_glm_make(avi_ctx* ctx, const float* X, const float* y, int64_t
     if (n > 0x7fffffffLL) AVI_FAIL(ctx, AVI_ERR_UNSUPPORTED, "more than 2^31-1 rows per device");
     if (likelihood != AVI_GLM_BERNOULLI_LOGIT && likelihood != AVI_GLM_GAUSSIAN) AVI_FAIL(ctx, AVI_ERR_INVALID, "likelihood");
     if (variant != AVI_GLM_SUBSAMPLING && variant != AVI_GLM_BASIC) AVI_FAIL(ctx, AVI_ERR_INVALID, "variant");
-    if (gemm_mode == AVI_GEMM_TF32X3) AVI_FAIL(ctx, AVI_ERR_UNSUPPORTED, "AVI_GEMM_TF32X3 is not implemented yet");
-    if (gemm_mode != AVI_GEMM_SIMT_FP32 && gemm_mode != AVI_GEMM_TF32) AVI_FAIL(ctx, AVI_ERR_INVALID, "gemm_mode");
+    if (gemm_mode != AVI_GEMM_SIMT_FP32 && gemm_mode != AVI_GEMM_TF32 && gemm_mode != AVI_GEMM_TF32X3)
+        AVI_FAIL(ctx, AVI_ERR_INVALID, "gemm_mode");
     Glm* g = new Glm();
     g->ctx = ctx; g->D = d + 1; g->capability = 1;
-    g->d = d; g->dK = (int)round_up(d, 4);
-    g->n_full = n; g->nP_full = round_up(n, 32); g->n_data = n_data; g->rows_global = n;
+    g->x3 = gemm_mode == AVI_GEMM_TF32X3 ? 1 : 0;
+    g->segd = (int)round_up(d, 32); g->segn_full = round_up(n, 32);
+    g->d = d; g->dK = g->x3 ? 3 * g->segd : (int)round_up(d, 4);
+    g->n_full = n; g->nP_full = (g->x3 ? 3 : 1) * g->segn_full; g->n_data = n_data; g->rows_global = n;
     g->likelihood = likelihood; g->variant = variant; g->mode = gemm_mode;
     if (const char* e = getenv("AVI_TC_CLUSTER")) g->cluster_mode = atoi(e);
     float* tmp = nullptr;
@@ -428,9 +482,9 @@ int32_t avi_model_glm_make(avi_ctx* ctx, const float* X, const float* y, int64_t
     cudaError_t e = avi_copy(ctx, tmp, X, (size_t)n * d * sizeof(float), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = avi_copy(ctx, g->y_full, y, (size_t)n * sizeof(float), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {
-        dim3 grid((unsigned)ceil_div(g->nP_full, 32), (unsigned)ceil_div(g->dK, 32));
-        k_glm_layout<<<grid, dim3(32, 8), 0, ctx->stream>>>(tmp, n, d, g->dK, g->nP_full, g->tc_mode() ? 1 : 0,
-                                                            g->Xr_full, g->Xc_full);
+        dim3 grid((unsigned)ceil_div(g->segn_full, 32), (unsigned)ceil_div(g->segd, 32));
+        k_glm_layout<<<grid, dim3(32, 8), 0, ctx->stream>>>(tmp, n, d, g->dK, g->nP_full, g->x3 ? 2 : (g->tc_mode() ? 1 : 0),
+                                                            g->segd, g->segn_full, g->Xr_full, g->Xc_full);
         ctx->launches++;
         e = cudaStreamSynchronize(ctx->stream);
     }

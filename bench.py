@@ -353,6 +353,22 @@ def main():
         "clocks": sampler.summary(), "roofline": roofline,
     }
 
+    # the fp32-grade tensor-core mode (3xTF32 by K-concatenation) on the same workload, L2-resident replays
+    if world == 1 and args.gemm == "tf32":
+        p3 = avi.LogReg(ctx, X, y, gemm="tf32x3")
+        o3 = avi.Objective(SEED, alg.objective, q0, p3)
+        s3 = _OptState(alg, o3, q0)
+        L.check(L.lib.avi_opt_steps(s3.h, W, L.fptr(vals), L.fptr(elbos), C.byref(nd)), ctx.h)
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(ext)
+        L.check(L.lib.avi_opt_steps(s3.h, K, L.fptr(vals), L.fptr(elbos), C.byref(nd)), ctx.h)
+        a1.record(ext)
+        barrier()
+        line["alt_precision"] = {"mode": "tf32x3 (hi/lo split operands, 3 tensor-core products, fp32-grade)",
+                                 "value_l2_resident": K / (a0.elapsed_time(a1) * 1e-3), "unit": "steps/s"}
+        s3.close(); o3.close(); p3.close()
+
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import family as F, models as Mo, objectives as O, philox as Ph
         probo = Mo.LogReg(X, y)

@@ -107,7 +107,7 @@ def glm_pair(avi, ctx, name, n, d, gemm, n_data=None):
 
 
 @pytest.mark.parametrize("name", ["logreg_subsampling", "logreg_basic", "gaussglm"])
-@pytest.mark.parametrize("gemm,tol_l,tol_g", [("fp32", 2e-6, 2e-5), ("tf32", 5e-4, 2e-3)])
+@pytest.mark.parametrize("gemm,tol_l,tol_g", [("fp32", 2e-6, 2e-5), ("tf32", 5e-4, 2e-3), ("tf32x3", 4e-6, 4e-5)])
 @pytest.mark.parametrize("n,d,M", [(40, 4, 3), (300, 37, 17), (1000, 160, 130)])
 def test_glm_logdensity_and_gradient(avi, ctx, name, gemm, tol_l, tol_g, n, d, M):
     prob, probo = glm_pair(avi, ctx, name, n, d, gemm, n_data=3 * n)
@@ -119,7 +119,7 @@ def test_glm_logdensity_and_gradient(avi, ctx, name, gemm, tol_l, tol_g, n, d, M
     prob.close()
 
 
-@pytest.mark.parametrize("gemm,tol_v,tol_g", [("fp32", 1e-5, 5e-5), ("tf32", 5e-4, 2e-3)])
+@pytest.mark.parametrize("gemm,tol_v,tol_g", [("fp32", 1e-5, 5e-5), ("tf32", 5e-4, 2e-3), ("tf32x3", 1e-5, 5e-5)])
 @pytest.mark.parametrize("kind", ["meanfield", "fullrank"])
 @pytest.mark.parametrize("entropy", ["ClosedFormEntropy", "StickingTheLandingEntropy"])
 def test_repgrad_logreg_matches_oracle(avi, ctx, gemm, tol_v, tol_g, kind, entropy):
@@ -168,6 +168,11 @@ def test_subsample_matches_oracle(avi, ctx):
     lp2, _ = prob.subsample(None).logdensity_and_gradient(Z)
     assert np.abs(lp2 - probo.logdensity_batch(Z.astype(np.float64))).max() <= 5e-4 * np.abs(lp2).max()
     prob.close()
+    # the 3xTF32 mode rebuilds the split operands of the batch (minibatch gather of [hi | lo | hi] rows)
+    prob3 = avi.LogReg(ctx, probo.X.astype(np.float32), probo.y.astype(np.float32), gemm="tf32x3")
+    lp3, G3 = prob3.subsample(idx).logdensity_and_gradient(Z)
+    assert np.abs(lp3 - lpo).max() <= 4e-6 * np.abs(lpo).max() and relerr(G3, Go) < 4e-5
+    prob3.close()
 
 
 def test_hostcallback_target(avi, ctx):
@@ -420,7 +425,7 @@ def test_c2_full_size_properties(avi, ctx):
     q = avi.MeanFieldGaussian(np.zeros(D, np.float32), np.ones(D, np.float32) * 0.1)
     lam = q.destructure()
     res = {}
-    for gemm in ("tf32", "fp32"):
+    for gemm in ("tf32", "fp32", "tf32x3"):
         prob = avi.LogReg(ctx, X, y, gemm=gemm)
         obj = avi.Objective(1, avi.RepGradELBO(M), q, prob)
         res[gemm] = obj.estimate_gradient(lam)
@@ -429,9 +434,10 @@ def test_c2_full_size_properties(avi, ctx):
             again = obj.estimate_gradient(lam)
             assert again[0] == res[gemm][0] and np.array_equal(again[1], res[gemm][1])     # bitwise repeatable
         obj.close(); prob.close()
-    (v1, g1, _), (v0, g0, _) = res["tf32"], res["fp32"]
+    (v1, g1, _), (v0, g0, _), (v3, g3, _) = res["tf32"], res["fp32"], res["tf32x3"]
     assert abs(v1 - v0) <= 5e-4 * abs(v0)
     assert relerr(g1, g0) < 2e-3
+    assert abs(v3 - v0) <= 1e-5 * abs(v0) and relerr(g3, g0) < 5e-5      # 3xTF32 == fp32-grade
     # oracle on a bounded slice of the same workload: 16 samples
     probo = Mo.LogReg(X, y)
     prob = avi.LogReg(ctx, X, y, gemm="tf32")
