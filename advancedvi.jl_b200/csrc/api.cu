@@ -322,6 +322,8 @@ int32_t avi_obj_create(avi_ctx* ctx, avi_model* model, int32_t family, int32_t o
 int32_t avi_obj_destroy(avi_obj* o) {
     if (!o) return AVI_OK;
     cudaStreamSynchronize(o->ctx->stream);
+    if (o->eg_exec) cudaGraphExecDestroy(o->eg_exec);
+    if (o->eg_graph) cudaGraphDestroy(o->eg_graph);
     obj_free_buffers(o);
     avi_fr_free(o);
     avi_free(o->d_state); avi_free(o->d_lambda); avi_free(o->acc); avi_free(o->grad); avi_free(o->out);
@@ -383,12 +385,54 @@ int32_t avi_obj_estimate_gradient(avi_obj* o, const float* lambda_host, int64_t 
     AVI_CHECK(check_lambda(o, lambda_host, P));
     cudaSetDevice(ctx->device);
     std::memcpy(o->h_lambda, lambda_host, (size_t)P * sizeof(float));
-    AVI_CUDA(ctx, cudaMemcpyAsync(o->d_lambda, o->h_lambda, (size_t)P * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    AVI_CHECK(avi_objective_local(o, o->d_lambda));
-    AVI_CHECK(avi_objective_finalize(o, o->d_lambda, o->grad, o->out));
-    AVI_CHECK(avi_obj_advance(o));
-    AVI_CUDA(ctx, cudaMemcpyAsync(o->h_grad, o->grad, (size_t)P * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-    AVI_CUDA(ctx, cudaMemcpyAsync(o->h_grad + P, o->out, 4 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    auto enqueue = [&]() -> int32_t {
+        AVI_CUDA(ctx, cudaMemcpyAsync(o->d_lambda, o->h_lambda, (size_t)P * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        AVI_CHECK(avi_objective_local(o, o->d_lambda));
+        AVI_CHECK(avi_objective_finalize(o, o->d_lambda, o->grad, o->out));
+        AVI_CHECK(avi_obj_advance(o));
+        AVI_CUDA(ctx, cudaMemcpyAsync(o->h_grad, o->grad, (size_t)P * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        AVI_CUDA(ctx, cudaMemcpyAsync(o->h_grad + P, o->out, 4 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        return AVI_OK;
+    };
+    // The whole call (copies included: the staging buffers are pinned and fixed) is captured as a CUDA graph
+    // on its second use and replayed afterwards; anything that invalidates device pointers bumps `generation`.
+    static const bool no_graph = getenv("AVI_NO_GRAPH") && atoi(getenv("AVI_NO_GRAPH")) != 0;
+    const bool capturable = !no_graph && !ctx->timing && !o->model->needs_sync_eval() &&
+                            !(ctx->nranks > 1 && !ctx->comm_capturable);
+    const int64_t gen = o->generation * 1000003 + o->model->generation;
+    if (o->eg_exec && o->eg_gen != gen) {
+        cudaGraphExecDestroy(o->eg_exec); cudaGraphDestroy(o->eg_graph);
+        o->eg_exec = nullptr; o->eg_graph = nullptr; o->eg_calls = 0;
+    }
+    if (capturable && o->eg_exec) {
+        AVI_CUDA(ctx, cudaGraphLaunch(o->eg_exec, ctx->stream));
+        ctx->launches += o->eg_launches;
+        o->step += 1;
+    } else if (capturable && o->eg_calls >= 1 && o->eg_gen == gen) {
+        const int64_t l0 = ctx->launches;
+        const unsigned long long step0 = o->step;
+        AVI_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        ctx->capturing = true;
+        int32_t rc = enqueue();
+        ctx->capturing = false;
+        cudaGraph_t g = nullptr;
+        cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+        o->eg_launches = ctx->launches - l0;
+        ctx->launches = l0;
+        o->step = step0;
+        if (rc != AVI_OK) { if (g) cudaGraphDestroy(g); return rc; }
+        if (e != cudaSuccess) AVI_FAIL(ctx, AVI_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+        o->eg_graph = g;
+        AVI_CUDA(ctx, cudaGraphInstantiate(&o->eg_exec, o->eg_graph, 0));
+        o->eg_gen = o->generation * 1000003 + o->model->generation;
+        AVI_CUDA(ctx, cudaGraphLaunch(o->eg_exec, ctx->stream));
+        ctx->launches += o->eg_launches;
+        o->step += 1;
+    } else {
+        AVI_CHECK(enqueue());   // first call: also sizes every lazily allocated buffer
+        o->eg_calls++;
+        o->eg_gen = o->generation * 1000003 + o->model->generation;
+    }
     AVI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (grad_host) std::memcpy(grad_host, o->h_grad, (size_t)P * sizeof(float));
     if (value) *value = o->h_grad[P];

@@ -217,6 +217,12 @@ struct avi_obj {
     // pinned host staging
     float* h_lambda = nullptr;   // P
     float* h_grad = nullptr;     // P + 4
+    // captured estimate_gradient! (H2D lambda -> kernels -> D2H gradient): one graph launch per call
+    cudaGraph_t eg_graph = nullptr;
+    cudaGraphExec_t eg_exec = nullptr;
+    int64_t eg_gen = -1;
+    int64_t eg_launches = 0;
+    int eg_calls = 0;
 };
 
 struct avi_opt {

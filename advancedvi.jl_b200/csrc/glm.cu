@@ -428,10 +428,11 @@ struct Glm : avi_model {
                                                             x3 ? segd : 0, segn_b, Xr_b, Xc_b, y_b);
         AVI_LAUNCHED(ctx);
         Xr = Xr_b; Xc = Xc_b; y = y_b; n_act = batch; nP = nP_b; segn = segn_b; subsampled = true;
+        generation++;   // the active view changed: graphs captured on the previous view are stale
         return AVI_OK;
     }
     int32_t subsample(const int32_t* idx_host, int64_t batch) override {
-        if (!idx_host) { view_full(); return AVI_OK; }
+        if (!idx_host) { view_full(); generation++; return AVI_OK; }
         if (batch <= 0) AVI_FAIL(ctx, AVI_ERR_INVALID, "empty batch");
         for (int64_t j = 0; j < batch; ++j)
             if (idx_host[j] < 0 || idx_host[j] >= n_full) AVI_FAIL(ctx, AVI_ERR_INVALID, "batch index out of range");
