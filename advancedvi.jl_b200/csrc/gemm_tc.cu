@@ -37,7 +37,8 @@ constexpr int SMEM_LIMIT = 232448;                 // 227 KB opt-in maximum per 
 struct SmemCtl {
     uint64_t full[MAX_STAGES], empty[MAX_STAGES], tmem_full[2], tmem_empty[2];
     uint32_t tmem_base;
-    float ys[2][256];
+    int flag;
+    float ys[2][512];   // FWD: y per accumulator stage (<= 256 used); BWD: reduction scratch
 };
 
 __device__ __forceinline__ unsigned long long gtime_ns() {
@@ -67,6 +68,63 @@ __device__ __forceinline__ void epilogue_unit(const TcParams& p, SmemCtl* ctl, i
     if (EPI == EPI_GLM_BWD) {
         // eps[b][a] for this thread's columns, fetched while the MMAs are still running
         const float* Ea = p.E + a;
+        float pr1 = 0.0f, pr2 = 0.0f;
+        if (p.post_on) {
+            // Work that does not depend on this kernel's MMAs, done while they run (the epilogue warps would
+            // otherwise sleep on the accumulator barrier):
+            // (1) log pi(z_m) = w * sum(partial log-lik of the forward kernel) + log prior, by the a-block-0 CTAs
+            const int ab0 = a / BM;
+            if (ab0 == 0) {
+                float* red = &ctl->ys[0][0];   // 16 warps x 32 lanes
+                const int ew = et >> 5, ln = et & 31;
+                for (int m0 = (ks * p.n_bchunk + bc) * 32; m0 < p.Nb; m0 += p.n_ksplit * p.n_bchunk * 32) {
+                    const int m = m0 + ln;
+                    float sll = 0.0f;
+                    if (m < p.Nb) {
+#pragma unroll 6
+                        for (int q = ew; q < p.post_nparts; q += EPI_WARPS) sll += p.post_llpart[(size_t)q * p.post_ldll + m];
+                    }
+                    red[ew * 32 + ln] = sll;
+                    epi_bar_sync();
+                    if (ew == 0 && m < p.Nb) {
+                        float t = 0.0f;
+#pragma unroll
+                        for (int w2 = 0; w2 < EPI_WARPS; ++w2) t += red[w2 * 32 + ln];
+                        p.post_logp[m] = fmaf(p.post_w, t, __ldg(p.post_pre + 4 * (size_t)m));
+                    }
+                    epi_bar_sync();
+                }
+            }
+            // (1b) eta = theta[d]: sum over ALL samples of d log pi / d eta and of its product with eps
+            if (ab0 == 0 && ks == 0 && bc == 0 && (et >> 5) == EPI_WARPS - 1) {
+                const int ln = et & 31;
+                float t1 = 0.0f, t2 = 0.0f;
+#pragma unroll 8
+                for (int m = ln; m < p.Nb; m += 32) {
+                    const float ge = __ldg(p.post_pre + 4 * (size_t)m + 2);
+                    t1 += ge;
+                    t2 = fmaf(ge, __ldg(p.E + (size_t)m * p.lde + p.Ma), t2);
+                }
+                t1 = warp_sum(t1); t2 = warp_sum(t2);
+                if (ln == 0) { p.post_a1[p.Ma] = t1; p.post_a2[p.Ma] = t2; }
+            }
+            // (2) the prior part of grad_beta, -beta / sigma^2: the samples of this thread's column range are dealt
+            // round-robin to the k-split CTAs of the a-block (the sum is linear: any fixed partition is exact), so
+            // each thread issues only a handful of independent loads
+            if (a_ok) {
+                const float* Za = p.post_Z + a;
+                const int first = c_begin + ((ks - c_begin) % p.n_ksplit + p.n_ksplit) % p.n_ksplit;
+#pragma unroll 4
+                for (int c = first; c < c_end; c += p.n_ksplit) {
+                    const int b = bc * NT + c;
+                    if (b < p.Nb) {
+                        const float gz = -__ldg(Za + (size_t)b * p.lde) * __ldg(p.post_pre + 4 * (size_t)b + 1);
+                        pr1 += gz;
+                        pr2 = fmaf(gz, __ldg(Ea + (size_t)b * p.lde), pr2);
+                    }
+                }
+            }
+        }
         float e[32];
         bool waited = false;
         for (int c = c_begin; c < c_end; c += 32) {
@@ -92,6 +150,7 @@ __device__ __forceinline__ void epilogue_unit(const TcParams& p, SmemCtl* ctl, i
             }
         }
         if (!waited) { tc::mbar_wait(&ctl->tmem_full[as], aphase); tc::fence_after_sync(); }
+        s1 += pr1; s2 += pr2;
     } else {
         tc::mbar_wait(&ctl->tmem_full[as], aphase);
         tc::fence_after_sync();
@@ -156,18 +215,66 @@ __device__ __forceinline__ void epilogue_unit(const TcParams& p, SmemCtl* ctl, i
     }
 }
 
+// EPI_GLM_BWD with post_on: the last CTA to finish an a-block (all k-splits and b-chunks) adds up the partial
+// slabs of its 128 coordinates in a fixed order and writes the final sum_m g / sum_m g*eps; the last CTA of
+// a-block 0 also produces the eta coordinate.  Replaces the separate k_glm_post_sums launch.
+__device__ __forceinline__ void epilogue_bwd_combine(const TcParams& p, SmemCtl* ctl, int ab, int et) {
+    // (called right after epilogue_bwd_store: slab rows written, fenced, barrier passed)
+    if (et == 0) {
+        const unsigned int total = (unsigned int)(p.n_bchunk * p.n_ksplit);
+        const unsigned int t = atomicAdd(p.post_tickets + ab, 1u);
+        ctl->flag = (t == total - 1u);
+        if (t == total - 1u) p.post_tickets[ab] = 0u;   // re-arm for the next launch
+    }
+    epi_bar_sync();
+    if (!ctl->flag) return;
+    __threadfence();
+    float* red1 = &ctl->ys[0][0];   // 4 groups x 128 coordinates, per array
+    float* red2 = &ctl->ys[1][0];
+    const int lc = et & 127, g = et >> 7, coord = ab * BM + lc;
+    const int nslab = p.n_ksplit * p.n_bchunk;
+    float t1 = 0.0f, t2 = 0.0f;
+    if (coord < p.Ma) {
+#pragma unroll 6
+        for (int q = g; q < nslab; q += 4) {
+            t1 += p.part1[(size_t)q * p.ldpart + coord];
+            t2 += p.part2[(size_t)q * p.ldpart + coord];
+        }
+    }
+    red1[g * 128 + lc] = t1; red2[g * 128 + lc] = t2;
+    epi_bar_sync();
+    if (g == 0 && coord < p.Ma) {
+        p.post_a1[coord] = ((red1[lc] + red1[128 + lc]) + red1[256 + lc]) + red1[384 + lc];
+        p.post_a2[coord] = ((red2[lc] + red2[128 + lc]) + red2[256 + lc]) + red2[384 + lc];
+    }
+    epi_bar_sync();
+}
+
 template <int EPI>
 __device__ __forceinline__ void epilogue_store_partials(const TcParams& p, bool a_ok, int a, int bc, int ks, int cq,
                                                         float s1, float s2) {
     if (EPI == EPI_GLM_FWD) {
         if (a_ok) p.part1[(size_t)(bc * 4 + cq) * p.ldpart + a] = s1;
-    } else if (EPI == EPI_GLM_BWD) {
-        if (a_ok) {
-            const size_t slab = (size_t)((ks * p.n_bchunk + bc) * 4 + cq) * p.ldpart;
-            p.part1[slab + a] = s1;
-            p.part2[slab + a] = s2;
-        }
     }
+}
+
+// EPI_GLM_BWD: the four column-quarter warps of a TMEM lane combine their partial sums through shared memory
+// (fixed order) so that a unit contributes ONE slab row per coordinate.  Ends with the slab rows written and
+// fenced and all 512 epilogue threads past a barrier (which epilogue_bwd_combine relies on).
+__device__ __forceinline__ void epilogue_bwd_store(const TcParams& p, SmemCtl* ctl, bool a_ok, int a, int bc, int ks,
+                                                   int cq, int et, float s1, float s2) {
+    float* red1 = &ctl->ys[0][0];           // [4 quarters][128 rows]
+    float* red2 = &ctl->ys[1][0];
+    const int row = a & (BM - 1);
+    red1[cq * BM + row] = s1; red2[cq * BM + row] = s2;
+    epi_bar_sync();
+    if (cq == 0 && a_ok) {
+        const size_t slab = (size_t)(ks * p.n_bchunk + bc) * p.ldpart;
+        p.part1[slab + a] = ((red1[row] + red1[BM + row]) + red1[2 * BM + row]) + red1[3 * BM + row];
+        p.part2[slab + a] = ((red2[row] + red2[BM + row]) + red2[2 * BM + row]) + red2[3 * BM + row];
+    }
+    __threadfence();
+    epi_bar_sync();
 }
 
 // LIK: 0 Bernoulli-logit, 1 Gaussian (EPI_GLM_FWD only)
@@ -338,6 +445,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&ctl->tmem_empty[as]);
             epilogue_store_partials<EPI>(p, a_ok, a, bc, ks, cq, s1, s2);
+            if (EPI == EPI_GLM_BWD) epilogue_bwd_store(p, ctl, a_ok, a, bc, ks, cq, et, s1, s2);
+            if (EPI == EPI_GLM_BWD && p.post_on) epilogue_bwd_combine(p, ctl, ab, et);
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
     }
@@ -466,6 +575,7 @@ k_gemm_tc_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             __syncwarp();
             if (lane == 0) tc::mbar_arrive_cluster(tc::mapa_u32(tc::smem_u32(&ctl->tmem_empty[as]), 0u));
             epilogue_store_partials<EPI>(p, a_ok, a, bc, ks, cq, s1, s2);
+            if (EPI == EPI_GLM_BWD) epilogue_bwd_store(p, ctl, a_ok, a, bc, ks, cq, et, s1, s2);
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
     }

@@ -30,9 +30,19 @@ struct TcParams {
     int likelihood;
     const float* E;      // BWD: eps [b][lde]
     int lde;
-    float* part1;        // FWD: partial log-lik [(bc*4+cq)][ldpart];  BWD: sum g  [slab][ldpart]
+    float* part1;        // FWD: partial log-lik [(bc*4+cq)][ldpart];  BWD: sum g  [ks*n_bchunk+bc][ldpart]
     float* part2;        // BWD: sum g*eps
     int ldpart;
+    // BWD, fused post-processing (replaces k_glm_post_sums): prior gradient, log pi assembly, slab combine
+    int post_on;
+    const float* post_Z;       // z [b][lde]
+    const float* post_pre;     // float4 per sample: {log prior, 1/sigma^2, d log pi / d eta, |beta|^2}
+    const float* post_llpart;  // partial log-likelihood sums of the forward kernel [post_nparts][post_ldll]
+    int post_nparts, post_ldll;
+    float post_w;
+    float* post_logp;          // [Nb]
+    float *post_a1, *post_a2;  // final sum_m g, sum_m g*eps  [Ma + 1]
+    unsigned int* post_tickets;   // [n_ablk], zero between launches
 };
 
 int32_t avi_tc_make_tmap(avi_ctx* ctx, CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld,

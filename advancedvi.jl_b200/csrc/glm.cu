@@ -273,9 +273,10 @@ struct Glm : avi_model {
     ~Glm() override {
         avi_free(Xr_full); avi_free(Xc_full); avi_free(y_full); avi_free(Xr_b); avi_free(Xc_b); avi_free(y_b);
         avi_free(idx_own); avi_free(R); avi_free(Zt); avi_free(llpart); avi_free(a1p);
-        avi_free(slabs); avi_free(pre);
+        avi_free(slabs); avi_free(pre); avi_free(tickets);
     }
     bool hooked = false;
+    unsigned int* tickets = nullptr;   // last-CTA election per coordinate block (fused backward post-processing)
     int cluster_mode = 1;   // 0: never use thread-block clusters (AVI_TC_CLUSTER=0), 1: planner decides
     bool tc_mode() const { return mode != AVI_GEMM_SIMT_FP32; }
     bool sample_hook(int ld, int M, SampleHook* h) override {
@@ -392,11 +393,20 @@ struct Glm : avi_model {
         AVI_CHECK(forward(Z, ld, M, &nparts));
         TcParams p{}; CUtensorMap tmA, tmB;
         AVI_CHECK(backward_setup(M, &p, &tmA, &tmB));
-        const int nslab = p.n_ksplit * p.n_bchunk * 4;
+        const int nslab = p.n_ksplit * p.n_bchunk;
         const int ldslab = (int)round_up(d, 32);
         AVI_CHECK(ensure_buf(&a1p, &ap_cap, 2LL * nslab * ldslab));
         float* a2p = a1p + (size_t)nslab * ldslab;
         p.E = E; p.lde = ld; p.part1 = a1p; p.part2 = a2p; p.ldpart = ldslab;
+        // fold the whole post-processing into the backward kernel's epilogue (one launch less per step)
+        static const bool fuse_post = !(getenv("AVI_FUSE_POST") && atoi(getenv("AVI_FUSE_POST")) == 0);
+        if (fuse_post && !p.pair && p.ca == 1 && p.cb == 1) {
+            p.post_on = 1; p.post_Z = Z; p.post_pre = reinterpret_cast<const float*>(pre);
+            p.post_llpart = llpart; p.post_nparts = nparts; p.post_ldll = capM; p.post_w = likeadj();
+            p.post_logp = logp; p.post_a1 = a1; p.post_a2 = a2; p.post_tickets = tickets;
+            AVI_CHECK(avi_tc_launch(ctx, EPI_GLM_BWD, tmA, tmB, p));
+            return AVI_OK;
+        }
         AVI_CHECK(avi_tc_launch(ctx, EPI_GLM_BWD, tmA, tmB, p));
         const int ncb = (int)ceil_div(d + 1, 32);
         const unsigned grid = (unsigned)(ncb + ceil_div(M, 32));
@@ -478,6 +488,7 @@ int32_t avi_model_glm_make(avi_ctx* ctx, const float* X, const float* y, int64_t
     int32_t rc = avi_alloc(ctx, &g->Xr_full, (size_t)n * g->dK);
     if (rc == AVI_OK) rc = avi_alloc(ctx, &g->Xc_full, (size_t)d * g->nP_full);
     if (rc == AVI_OK) rc = avi_alloc(ctx, &g->y_full, (size_t)n);
+    if (rc == AVI_OK) rc = avi_alloc(ctx, &g->tickets, (size_t)ceil_div(d, 128) + 1);
     if (rc == AVI_OK) rc = avi_alloc(ctx, &tmp, (size_t)n * d);
     if (rc != AVI_OK) { avi_free(tmp); delete g; return rc; }
     cudaError_t e = avi_copy(ctx, tmp, X, (size_t)n * d * sizeof(float), cudaMemcpyHostToDevice);
