@@ -28,41 +28,83 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1,
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-// uint32 -> (0,1), exactly representable in fp32 (oracle/philox.py: uniform23)
+// uint32 -> (0,1), exactly representable in fp32 (oracle/philox.py: uniform23): (v + 0.5) * 2^-23 has 24
+// significant bits, so the single fma is exact
 __device__ __forceinline__ float uniform23(uint32_t x) {
-    return ((float)(x >> 9) + 0.5f) * 1.1920928955078125e-07f;   // 2^-23
+    return fmaf((float)(x >> 9), 1.1920928955078125e-07f, 5.9604644775390625e-08f);
 }
 
-// Box-Muller pair from two uniforms in (0,1), on the SFU pipes (MUFU lg2 / rsq / sin / cos) so that the
-// sampling kernel stays HBM-bound.  ln(u) loses absolute accuracy through cancellation as u -> 1
-// (lg2.approx has a fixed absolute error), so that range uses the series of ln(1 + t), t = u - 1.
+// Box-Muller pair from two Philox words, on the SFU pipes (MUFU lg2 / sqrt / sin / cos) and branch-free so
+// that the sampling kernel stays HBM-bound (the first version, with a divergent series branch, the IEEE sqrtf
+// and a compare/select angle fold, was issue-bound at 49 % of HBM peak: profiles/README.md).
+//   radius: r = sqrt(-2 ln u0).  lg2.approx has a fixed ABSOLUTE error, so ln(u) loses relative accuracy
+//           through cancellation as u -> 1; above 1 - 2^-5 the series of ln(1 + t), t = u0 - 1 (exact), is
+//           selected instead (5 terms: relative error < 5e-9).
+//   angle : 2 pi u1 folded into (-pi, pi), where sin.approx / cos.approx are most accurate.  u1 > 1/2 is the
+//           top bit of the 23-bit integer, so the fold u1 - 1 is the SIGNED reading of the same bits and
+//           th = fl(2 pi) * (vs + 0.5) * 2^-23 is one exact-product fma (bit-identical to 2 pi * (u1 - [u1 > 1/2])).
 // Accuracy vs the fp64 oracle: |d eps| < 3e-6 (tests/test_gpu_parity.py::test_rand_matches_oracle).
-__device__ __forceinline__ void box_muller_fast(float u0, float u1, float& n0, float& n1) {
-    float ln_u;
-    if (u0 > 0.875f) {
-        const float t = u0 - 1.0f;   // exact
-        ln_u = t * (1.0f + t * (-0.5f + t * (0.33333334f + t * (-0.25f + t * (0.2f + t * (-0.16666667f +
-               t * (0.14285715f + t * (-0.125f))))))));
-    } else {
-        ln_u = 0.6931471805599453f * __log2f(u0);
-    }
-    const float r = sqrtf(-2.0f * ln_u);
-    // angle 2 pi u1 folded into (-pi, pi] where sin.approx / cos.approx are most accurate
-    const float th = 6.283185307179586f * (u1 - (u1 > 0.5f ? 1.0f : 0.0f));
+__device__ __forceinline__ void box_muller_fast(uint32_t x0, uint32_t x1, float& n0, float& n1) {
+    const float u0 = uniform23(x0);
+    const float t = u0 - 1.0f;   // exact
+    const float a_series = t * (-2.0f + t * (1.0f + t * (-0.66666669f + t * (0.5f + t * (-0.4f)))));
+    float l2;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u0));   // u0 >= 2^-24: never subnormal
+    const float a_lg2 = -1.3862943611198906f * l2;
+    const float a = u0 > 0.96875f ? a_series : a_lg2;   // -2 ln u0 > 0
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+    const float th = fmaf((float)((int32_t)x1 >> 9), 6.283185307179586f * 1.1920928955078125e-07f,
+                          6.283185307179586f * 5.9604644775390625e-08f);
     n0 = r * __cosf(th);
     n1 = r * __sinf(th);
 }
 
+// Philox round keys (k + r * Weyl constant): warp-uniform, hoisted out of the per-quad loop
+struct PhiloxKeys {
+    uint32_t k0[10], k1[10];
+    __device__ __forceinline__ explicit PhiloxKeys(unsigned long long key) {
+        uint32_t a = (uint32_t)key, b = (uint32_t)(key >> 32);
+#pragma unroll
+        for (int r = 0; r < 10; ++r) { k0[r] = a; k1[r] = b; a += 0x9E3779B9u; b += 0xBB67AE85u; }
+    }
+};
+
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              const PhiloxKeys& pk, uint32_t out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t lo0, hi0, lo1, hi1;   // one IMAD.WIDE each
+        asm("{\n\t.reg .b64 p;\n\tmul.wide.u32 p, %2, %3;\n\tmov.b64 {%0, %1}, p;\n\t}"
+            : "=r"(lo0), "=r"(hi0) : "r"(c0), "r"(0xD2511F53u));
+        asm("{\n\t.reg .b64 p;\n\tmul.wide.u32 p, %2, %3;\n\tmov.b64 {%0, %1}, p;\n\t}"
+            : "=r"(lo1), "=r"(hi1) : "r"(c2), "r"(0xCD9E8D57u));
+        c0 = hi1 ^ c1 ^ pk.k0[r];
+        c2 = hi0 ^ c3 ^ pk.k1[r];
+        c1 = lo1;
+        c3 = lo0;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// counter words 2 and 3 of the eps stream (oracle/philox.py): step low word, stream id | step high bits
+__device__ __forceinline__ uint32_t eps_ctr3(unsigned long long step, uint32_t stream) {
+    return (stream & 0xFFu) | ((uint32_t)((step >> 32) & 0xFFFFFFu) << 8);
+}
+
 // four standard normals for coordinates 4q .. 4q+3 of Monte-Carlo sample m at step `step`
+__device__ __forceinline__ float4 normal4(uint32_t q, uint32_t m, uint32_t c2, uint32_t c3, const PhiloxKeys& pk) {
+    uint32_t x[4];
+    philox4x32_10(q, m, c2, c3, pk, x);
+    float4 e;
+    box_muller_fast(x[0], x[1], e.x, e.y);
+    box_muller_fast(x[2], x[3], e.z, e.w);
+    return e;
+}
 __device__ __forceinline__ float4 normal4(uint32_t q, uint32_t m, unsigned long long step, uint32_t stream,
                                           unsigned long long key) {
-    uint32_t x[4];
-    philox4x32_10(q, m, (uint32_t)step, (stream & 0xFFu) | ((uint32_t)((step >> 32) & 0xFFFFFFu) << 8),
-                  (uint32_t)key, (uint32_t)(key >> 32), x);
-    float4 e;
-    box_muller_fast(uniform23(x[0]), uniform23(x[1]), e.x, e.y);
-    box_muller_fast(uniform23(x[2]), uniform23(x[3]), e.z, e.w);
-    return e;
+    const PhiloxKeys pk(key);
+    return normal4(q, m, (uint32_t)step, eps_ctr3(step, stream), pk);
 }
 
 // programmatic dependent launch (see avi_launch_pdl): no-ops when the grid was launched without the attribute

@@ -26,87 +26,107 @@ namespace {
 // each; a warp instruction moves 512 contiguous bytes).  Writes Z = mu + s .* eps (mean-field), E = eps
 // (both zero in the padding columns i >= D) and |eps_m|^2 (fixed shuffle tree: no block barrier, no
 // atomics).  FULLRANK writes only E (Z = L * eps + mu comes from k_fr_affine).  HOOK: SampleHook.
-// SPLIT = warps cooperating on one sample: 1 for large M (no barrier at all), SAMPLE_WARPS for small M
-// (latency: the row is spread over the whole CTA, partial sums combined in a fixed order through smem).
+// SPLIT = warps cooperating on one sample: 1 for large M, SAMPLE_WARPS for small M (latency: the row is
+// spread over the whole CTA, partial sums combined in a fixed order through smem).
+// SPLIT == 1 is the bandwidth shape: CTAs stride over groups of SAMPLE_WARPS samples and (mean-field) keep
+// mu and s zero-padded in shared memory, so the per-quad work is Philox + Box-Muller + 2 LDS.128 + 2 STG.128.
 constexpr int SAMPLE_WARPS = 4;
 template <bool FULLRANK, bool HOOK, int SPLIT>
 __global__ void __launch_bounds__(32 * SAMPLE_WARPS)
 k_sample(const float* __restrict__ lambda, int D, int ld, int m0, int Mloc, const ObjDeviceState* __restrict__ st,
          ObjDeviceState st_val, int use_val, uint32_t stream_id, float* __restrict__ Z,
          float* __restrict__ E, float* __restrict__ esq, SampleHook hk) {
+    extern __shared__ __align__(16) float s_ms[];   // STAGE: [ld] mu, [ld] s
+    constexpr bool STAGE = !FULLRANK && SPLIT == 1;
     pdl_trigger();
     pdl_wait();   // lambda and the step counter come from the previous iteration's tail
     const unsigned long long step = use_val ? st_val.step : st->step;
-    const unsigned long long key = use_val ? st_val.key : st->key;
+    const PhiloxKeys pk(use_val ? st_val.key : st->key);
+    const uint32_t c2 = (uint32_t)step, c3 = eps_ctr3(step, stream_id);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int m = SPLIT == 1 ? blockIdx.x * SAMPLE_WARPS + warp : blockIdx.x;
-    if (m >= Mloc) return;   // warp-uniform (SPLIT > 1: CTA-uniform)
     const float* mu = lambda;
-    const float* sc = lambda + D;
-    float part = 0.0f, bsq = 0.0f, eta = 0.0f;
-    for (int q = SPLIT == 1 ? lane : threadIdx.x; q < ld / 4; q += 32 * SPLIT) {
-        float4 e = normal4((uint32_t)q, (uint32_t)(m0 + m), step, stream_id, key);
-        const int i = 4 * q;
-        float ev[4] = {e.x, e.y, e.z, e.w}, zv[4], zt[4];
-        float mv[4] = {0.f, 0.f, 0.f, 0.f}, sv[4] = {0.f, 0.f, 0.f, 0.f};
-        if (!FULLRANK) {
-            if (i + 3 < D) {   // D + ... : lambda + D is only 4-byte aligned in general
-                const float4 m4 = *reinterpret_cast<const float4*>(mu + i);
-                mv[0] = m4.x; mv[1] = m4.y; mv[2] = m4.z; mv[3] = m4.w;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) sv[c] = __ldg(sc + i + c);
-            } else {
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    if (i + c < D) { mv[c] = __ldg(mu + i + c); sv[c] = __ldg(sc + i + c); }
-            }
+    const float* sc = lambda + D;   // only 4-byte aligned in general
+    if (STAGE) {
+        for (int i = threadIdx.x; i < ld; i += 32 * SAMPLE_WARPS) {
+            s_ms[i] = i < D ? __ldg(mu + i) : 0.0f;
+            s_ms[ld + i] = i < D ? __ldg(sc + i) : 0.0f;
         }
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            if (i + c < D) {
-                part = fmaf(ev[c], ev[c], part);
-                zv[c] = FULLRANK ? 0.0f : fmaf(sv[c], ev[c], mv[c]);
-            } else {
-                ev[c] = 0.0f; zv[c] = 0.0f;
-            }
-            if (HOOK) {
-                const bool is_beta = i + c < hk.d;
-                bsq = is_beta ? fmaf(zv[c], zv[c], bsq) : bsq;
-                zt[c] = is_beta ? zv[c] : 0.0f;
-                if (i + c == hk.d) eta = zv[c];
-            }
-        }
-        *reinterpret_cast<float4*>(E + (size_t)m * ld + i) = make_float4(ev[0], ev[1], ev[2], ev[3]);
-        if (!FULLRANK)
-            *reinterpret_cast<float4*>(Z + (size_t)m * ld + i) = make_float4(zv[0], zv[1], zv[2], zv[3]);
-        if (HOOK && hk.Zt) {
-            float hi[4], lo[4];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) { hi[c] = tc::round_tf32(zt[c]); lo[c] = tc::round_tf32(zt[c] - hi[c]); }
-            float* row = hk.Zt + (size_t)m * hk.zt_ld + i;
-            if (hk.zt_seg == 0) {
-                *reinterpret_cast<float4*>(row) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-            } else if (i < hk.zt_seg) {   // 3xTF32: [hi | hi | lo]
-                *reinterpret_cast<float4*>(row) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<float4*>(row + hk.zt_seg) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<float4*>(row + 2 * hk.zt_seg) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-            }
-        }
-    }
-    float tot = warp_sum(part);
-    if (HOOK) { bsq = warp_sum(bsq); eta = warp_sum(eta); }   // eta is non-zero in exactly one lane
-    if (SPLIT > 1) {
-        __shared__ float sm[3][SAMPLE_WARPS];
-        if (lane == 0) { sm[0][warp] = tot; sm[1][warp] = bsq; sm[2][warp] = eta; }
         __syncthreads();
-        tot = 0.f; bsq = 0.f; eta = 0.f;
-#pragma unroll
-        for (int w = 0; w < SAMPLE_WARPS; ++w) { tot += sm[0][w]; bsq += sm[1][w]; eta += sm[2][w]; }
-        if (warp != 0) return;
     }
-    if (lane == 0) {
-        esq[m] = tot;
-        if (HOOK) hk.pre[m] = glm_prior_terms(bsq, eta, hk.d, hk.variant, hk.include_prior);
+    const int m_step = SPLIT == 1 ? (int)gridDim.x * SAMPLE_WARPS : Mloc;
+    for (int m = SPLIT == 1 ? blockIdx.x * SAMPLE_WARPS + warp : blockIdx.x; m < Mloc; m += m_step) {
+        float part = 0.0f, bsq = 0.0f, eta = 0.0f;
+        float* Erow = E + (size_t)m * ld;
+        float* Zrow = FULLRANK ? nullptr : Z + (size_t)m * ld;
+        for (int q = SPLIT == 1 ? lane : threadIdx.x; q < ld / 4; q += 32 * SPLIT) {
+            const float4 e = normal4((uint32_t)q, (uint32_t)(m0 + m), c2, c3, pk);
+            const int i = 4 * q;
+            float ev[4] = {e.x, e.y, e.z, e.w}, zv[4] = {0.f, 0.f, 0.f, 0.f}, zt[4];
+            if (i + 3 >= D) {   // the row's last quad: zero the padding columns
+#pragma unroll
+                for (int c = 0; c < 4; ++c) ev[c] = i + c < D ? ev[c] : 0.0f;
+            }
+            if (!FULLRANK) {
+                float mv[4] = {0.f, 0.f, 0.f, 0.f}, sv[4] = {0.f, 0.f, 0.f, 0.f};
+                if (STAGE) {
+                    const float4 m4 = *reinterpret_cast<const float4*>(s_ms + i);
+                    const float4 s4 = *reinterpret_cast<const float4*>(s_ms + ld + i);
+                    mv[0] = m4.x; mv[1] = m4.y; mv[2] = m4.z; mv[3] = m4.w;
+                    sv[0] = s4.x; sv[1] = s4.y; sv[2] = s4.z; sv[3] = s4.w;
+                } else if (i + 3 < D) {
+                    const float4 m4 = *reinterpret_cast<const float4*>(mu + i);
+                    mv[0] = m4.x; mv[1] = m4.y; mv[2] = m4.z; mv[3] = m4.w;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) sv[c] = __ldg(sc + i + c);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if (i + c < D) { mv[c] = __ldg(mu + i + c); sv[c] = __ldg(sc + i + c); }
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) zv[c] = fmaf(sv[c], ev[c], mv[c]);   // padding: 0 * 0 + 0
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) part = fmaf(ev[c], ev[c], part);
+            if (HOOK) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const bool is_beta = i + c < hk.d;
+                    bsq = is_beta ? fmaf(zv[c], zv[c], bsq) : bsq;
+                    zt[c] = is_beta ? zv[c] : 0.0f;
+                    if (i + c == hk.d) eta = zv[c];
+                }
+            }
+            *reinterpret_cast<float4*>(Erow + i) = make_float4(ev[0], ev[1], ev[2], ev[3]);
+            if (!FULLRANK) *reinterpret_cast<float4*>(Zrow + i) = make_float4(zv[0], zv[1], zv[2], zv[3]);
+            if (HOOK && hk.Zt) {
+                float hi[4], lo[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { hi[c] = tc::round_tf32(zt[c]); lo[c] = tc::round_tf32(zt[c] - hi[c]); }
+                float* row = hk.Zt + (size_t)m * hk.zt_ld + i;
+                if (hk.zt_seg == 0) {
+                    *reinterpret_cast<float4*>(row) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                } else if (i < hk.zt_seg) {   // 3xTF32: [hi | hi | lo]
+                    *reinterpret_cast<float4*>(row) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<float4*>(row + hk.zt_seg) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<float4*>(row + 2 * hk.zt_seg) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                }
+            }
+        }
+        float tot = warp_sum(part);
+        if (HOOK) { bsq = warp_sum(bsq); eta = warp_sum(eta); }   // eta is non-zero in exactly one lane
+        if (SPLIT > 1) {
+            __shared__ float sm[3][SAMPLE_WARPS];
+            if (lane == 0) { sm[0][warp] = tot; sm[1][warp] = bsq; sm[2][warp] = eta; }
+            __syncthreads();
+            tot = 0.f; bsq = 0.f; eta = 0.f;
+#pragma unroll
+            for (int w = 0; w < SAMPLE_WARPS; ++w) { tot += sm[0][w]; bsq += sm[1][w]; eta += sm[2][w]; }
+        }
+        if (lane == 0 && (SPLIT == 1 || warp == 0)) {
+            esq[m] = tot;
+            if (HOOK) hk.pre[m] = glm_prior_terms(bsq, eta, hk.d, hk.variant, hk.include_prior);
+        }
     }
 }
 
@@ -318,13 +338,17 @@ int32_t avi_family_sample(avi_obj* o, const float* lambda, float* Z, float* E, f
     int use_val = 0;
     if (ov) { sv = *ov; use_val = 1; }
     AviTimed timed(ctx, "sample");
-    const bool split = Mloc <= 8192;   // small batches: spread each sample over the whole CTA
-    const unsigned sgrid = split ? (unsigned)Mloc : (unsigned)ceil_div(Mloc, SAMPLE_WARPS);
+    // small batches: spread each sample over the whole CTA.  Large batches: warp per sample, CTAs stride over
+    // the samples with mu / s staged in shared memory (needs 8 * ld bytes; wider families keep the CTA shape)
+    const size_t stage_bytes = o->family == AVI_MEANFIELD ? 2 * (size_t)o->ld * sizeof(float) : 0;
+    const bool split = Mloc <= 8192 || stage_bytes > 48 * 1024;
+    const unsigned sgrid = split ? (unsigned)Mloc
+                                 : (unsigned)std::min<int64_t>(ceil_div(Mloc, SAMPLE_WARPS), (int64_t)ctx->prop.multiProcessorCount * 12);
 #define LAUNCH_SAMPLE(FR, HK, HOOKV)                                                                                 \
     do {                                                                                                             \
         if (split) avi_launch_pdl(ctx, k_sample<FR, HK, SAMPLE_WARPS>, dim3(sgrid), dim3(32 * SAMPLE_WARPS), 0,       \
             lambda, o->D, o->ld, m0, Mloc, st, sv, use_val, (uint32_t)AVI_STREAM_EPS, Z, E, esq, HOOKV);              \
-        else avi_launch_pdl(ctx, k_sample<FR, HK, 1>, dim3(sgrid), dim3(32 * SAMPLE_WARPS), 0,                        \
+        else avi_launch_pdl(ctx, k_sample<FR, HK, 1>, dim3(sgrid), dim3(32 * SAMPLE_WARPS), stage_bytes,              \
             lambda, o->D, o->ld, m0, Mloc, st, sv, use_val, (uint32_t)AVI_STREAM_EPS, Z, E, esq, HOOKV);              \
     } while (0)
     if (o->family == AVI_MEANFIELD) {
