@@ -596,6 +596,20 @@ class _OptState:
         L.check(L.lib.avi_opt_get(self.h, L.fptr(lam), L.fptr(avg), L.fptr(grad)), self.obj.ctx.h)
         return lam, avg, grad
 
+    # avi_opt_steps in three phases (no host round trip between iterations; see include/avi.h)
+    def steps_begin(self, capacity: int):
+        L.check(L.lib.avi_opt_steps_begin(self.h, int(capacity)), self.obj.ctx.h)
+        self._cap = int(capacity)
+
+    def steps_enqueue(self, n: int = 1):
+        L.check(L.lib.avi_opt_steps_enqueue(self.h, int(n)), self.obj.ctx.h)
+
+    def steps_end(self):
+        """-> (value slots, elbos, iterations completed); raises like `step` when the objective diverged."""
+        vals, elbos, nd = np.empty(self._cap, np.float32), np.empty(self._cap, np.float32), C.c_int32()
+        L.check(L.lib.avi_opt_steps_end(self.h, L.fptr(vals), L.fptr(elbos), C.byref(nd)), self.obj.ctx.h)
+        return vals, elbos, nd.value
+
     def export_bytes(self) -> bytes:
         n = int(L.lib.avi_opt_state_nbytes(self.h))
         buf = C.create_string_buffer(n)

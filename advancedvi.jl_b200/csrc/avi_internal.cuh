@@ -136,6 +136,8 @@ struct SampleHook {
     float* Zt = nullptr;
     int zt_ld = 0, zt_seg = 0;   // row pitch of Zt; zt_seg > 0: 3xTF32 split [hi | hi | lo] in segments of zt_seg
     float4* pre = nullptr;
+    const void* pf_ptr = nullptr;         // static operand of the next kernel to pull into L2 meanwhile (may be null)
+    unsigned long long pf_bytes = 0;
 };
 
 // Layout shared by every sample-major buffer: row m (one Monte-Carlo sample) holds `ld` floats,
@@ -252,6 +254,10 @@ struct avi_opt {
     int64_t graph_batch = 0;
     int64_t graph_gen = -1;
     int64_t graph_launches = 0;   // kernels per captured iteration
+    // open avi_opt_steps call (begin / enqueue / end)
+    int call_cap = 0, call_enqueued = 0;
+    bool call_subsampled = false, use_graph = false;
+    int64_t call_batch = 0;
 };
 
 // ---------------------------------------------------------------------------------------------

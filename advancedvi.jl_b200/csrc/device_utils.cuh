@@ -109,6 +109,22 @@ __device__ __forceinline__ float4 normal4(uint32_t q, uint32_t m, unsigned long 
 
 // programmatic dependent launch (see avi_launch_pdl): no-ops when the grid was launched without the attribute
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Ask the memory system to pull [base, base + bytes) into L2 (cp.async.bulk.prefetch.L2, a per-warp instruction with
+// a uniform address): warp `widx` of `nwarps` issues every nwarps-th chunk of `chunk` bytes.  Used to stream the NEXT
+// kernel's static operand from HBM while the current kernel computes (an L2 hit costs a tag lookup).  base must be
+// 16-byte aligned, chunk a multiple of 16.  Call with the whole warp.
+__device__ __forceinline__ void l2_prefetch_span(const void* base, unsigned long long bytes, unsigned widx,
+                                                 unsigned nwarps, unsigned chunk, unsigned pace_ns = 0) {
+    const char* p = static_cast<const char*>(base);
+    if ((threadIdx.x & 31) == 0) {
+        for (unsigned long long off = (unsigned long long)widx * chunk; off < bytes; off += (unsigned long long)nwarps * chunk) {
+            const unsigned long long left = bytes - off;
+            const unsigned sz = (unsigned)(left < chunk ? left : chunk) & ~15u;
+            if (sz) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p + off), "r"(sz) : "memory");
+            if (pace_ns) __nanosleep(pace_ns);   // spread the requests so they do not queue ahead of demand loads
+        }
+    }
+}
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -39,6 +39,8 @@ k_sample(const float* __restrict__ lambda, int D, int ld, int m0, int Mloc, cons
     extern __shared__ __align__(16) float s_ms[];   // STAGE: [ld] mu, [ld] s
     constexpr bool STAGE = !FULLRANK && SPLIT == 1;
     pdl_trigger();
+    if (HOOK && hk.pf_bytes)   // stream the forward kernel's X into L2 while this kernel runs (static data: before the wait)
+        l2_prefetch_span(hk.pf_ptr, hk.pf_bytes, blockIdx.x * SAMPLE_WARPS + (threadIdx.x >> 5), gridDim.x * SAMPLE_WARPS, 8192);
     pdl_wait();   // lambda and the step counter come from the previous iteration's tail
     const unsigned long long step = use_val ? st_val.step : st->step;
     const PhiloxKeys pk(use_val ? st_val.key : st->key);

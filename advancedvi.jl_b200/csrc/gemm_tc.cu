@@ -152,7 +152,8 @@ __device__ __forceinline__ void epilogue_unit(const TcParams& p, SmemCtl* ctl, i
         if (!waited) { tc::mbar_wait(&ctl->tmem_full[as], aphase); tc::fence_after_sync(); }
         s1 += pr1; s2 += pr2;
     } else {
-        tc::mbar_wait(&ctl->tmem_full[as], aphase);
+        if (p.dbg & 4) { while (!tc::mbar_try_wait(&ctl->tmem_full[as], aphase)) __nanosleep(500); }   // experiment: sleeping waiters
+        else tc::mbar_wait(&ctl->tmem_full[as], aphase);
         tc::fence_after_sync();
         TC_STAMP(4, et == 0);
         for (int c = c_begin; c < c_end; c += 8) {
@@ -352,7 +353,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        if (tc::elect_one()) {   // elect.sync: the compiler then treats the whole region as warp-uniform
             int stage = 0; uint32_t phase = 0;
             int kcount = 0;   // k-blocks issued so far by this CTA
             for (int u = cluster_id; u < units; u += n_clusters) {
@@ -391,10 +392,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (tc::elect_one()) {   // elect.sync: the compiler then treats the whole region as warp-uniform
             const uint32_t idesc = tc::idesc_tf32(BM, NT);
             int stage = 0; uint32_t phase = 0;
             int as = 0; uint32_t aphase = 0;
+            long long prof_wait = 0, prof_t0 = 0;   // AVI_TC_PROF: cycles stalled on full[] / first operands seen
             for (int u = cluster_id; u < units; u += n_clusters) {
                 const int ks = u / (n_ag * n_bg);
                 const int kb0 = ks * p.kb_per_split, kb1 = min(p.n_kblk, kb0 + p.kb_per_split);
@@ -402,7 +404,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 tc::fence_after_sync();
                 const uint32_t tacc = tmem_base + (uint32_t)(as * 256);
                 for (int kb = kb0; kb < kb1; ++kb) {
-                    tc::mbar_wait(&ctl->full[stage], phase);
+                    const long long c0 = p.prof ? clock64() : 0;
+                    if (!(p.dbg & 8)) tc::mbar_wait(&ctl->full[stage], phase);   // dbg 8: free-running issue (garbage operands)
+                    if (p.prof) { const long long c1 = clock64(); if (prof_t0) prof_wait += c1 - c0; else prof_t0 = c1; }
                     tc::fence_after_sync();
                     TC_STAMP(2, kb == kb0 && u == cluster_id);
                     const uint32_t sa = tc::smem_u32(tiles + stage * stage_bytes);
@@ -422,7 +426,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 TC_STAMP(3, true);
                 if (++as == 2) { as = 0; aphase ^= 1; }
             }
+            // slot 7: (cycles stalled on operands after the first k-block) << 32 | mainloop cycles
+            if (p.prof) p.prof[(size_t)blockIdx.x * 8 + 7] = ((unsigned long long)prof_wait << 32) |
+                                                            (unsigned long long)(uint32_t)(clock64() - prof_t0);
         }
+    } else if (warp == 3) {
+        if (p.pf_bytes) l2_prefetch_span(p.pf_ptr, p.pf_bytes, blockIdx.x, gridDim.x, 16384, p.pf_pace_ns);
     } else if (warp >= 4) {
         // ===================== epilogue =====================
         // warp w may only touch TMEM lanes [32 (w % 4), +32); the 4 warps of a lane quarter split the
@@ -509,7 +518,7 @@ k_gemm_tc_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (warp == 0) {
         // ===================== TMA producer (both CTAs) =====================
-        if (lane == 0) {
+        if (tc::elect_one()) {   // elect.sync: the compiler then treats the whole region as warp-uniform
             int stage = 0; uint32_t phase = 0;
             for (int u = pair_id; u < units; u += n_pairs) {
                 PAIR_COORDS(u);
@@ -527,7 +536,7 @@ k_gemm_tc_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA only) =====================
-        if (lane == 0 && rank == 0) {
+        if (rank == 0 && tc::elect_one()) {
             const uint32_t idesc = tc::idesc_tf32(2 * BM, NT);
             int stage = 0; uint32_t phase = 0;
             int as = 0; uint32_t aphase = 0;
@@ -651,6 +660,11 @@ static int32_t set_attrs(avi_ctx* ctx) {
     return AVI_OK;
 }
 
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
 // how many clusters of `csz` CTAs (one CTA per SM, full shared memory) can be resident at once
 static int max_active_clusters(avi_ctx* ctx, int csz) {
     static int cache[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -690,7 +704,11 @@ int32_t avi_tc_plan(avi_ctx* ctx, int64_t Ma, int64_t Nb, int64_t K, bool split_
             if (force_cluster == 0 && csz > 1) continue;
             const int maxc = max_active_clusters(ctx, csz);
             if (maxc <= 0) continue;
-            static const int nt_env = getenv("AVI_TC_NT") ? atoi(getenv("AVI_TC_NT")) : 0;
+            // experiment overrides (read per call): AVI_TC_NT = forward tile width, AVI_TC_CA / AVI_TC_CB = cluster shape of
+            // the forward (no split-K) plan, AVI_TC_BCA / AVI_TC_BCB = of the split-K plan
+            const int nt_env = env_int("AVI_TC_NT", 0);
+            const int ca_env = env_int(split_k ? "AVI_TC_BCA" : "AVI_TC_CA", 0), cb_env = env_int(split_k ? "AVI_TC_BCB" : "AVI_TC_CB", 0);
+            if ((ca_env && ca != ca_env) || (cb_env && cb != cb_env)) continue;
             for (int nt = split_k ? nt_hi : 16; nt <= nt_hi; nt += 16) {
                 if (nt % (8 * ca)) continue;
                 if (nt_env && !split_k && nt != std::min(nt_env, nt_hi)) continue;
@@ -719,7 +737,7 @@ int32_t avi_tc_plan(avi_ctx* ctx, int64_t Ma, int64_t Nb, int64_t K, bool split_
     }
     // CTA pairs (cta_group::2): two a-blocks per unit, half of the b-chunk per SM
     p->pair = 0;
-    static const int pair_env = getenv("AVI_TC_PAIR") ? atoi(getenv("AVI_TC_PAIR")) : 0;
+    const int pair_env = env_int("AVI_TC_PAIR", 0);
     if (pair_env && p->n_ablk >= 2) {
         const int maxp = max_active_clusters(ctx, 2);
         const int n_ag = (p->n_ablk + 1) / 2;
@@ -756,9 +774,9 @@ int32_t avi_tc_plan(avi_ctx* ctx, int64_t Ma, int64_t Nb, int64_t K, bool split_
 
 int32_t avi_tc_launch(avi_ctx* ctx, int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p_in) {
     TcParams p = p_in;
-    static const int dbg_env = getenv("AVI_TC_DBG") ? atoi(getenv("AVI_TC_DBG")) : 0;
+    const int dbg_env = env_int("AVI_TC_DBG", 0);
     p.dbg = dbg_env;
-    static const int prof_env = getenv("AVI_TC_PROF") ? atoi(getenv("AVI_TC_PROF")) : 0;
+    const int prof_env = env_int("AVI_TC_PROF", 0);
     static unsigned long long* prof_buf = nullptr;
     static int prof_calls = 0;
     if (prof_env) {
@@ -819,9 +837,12 @@ int32_t avi_tc_launch(avi_ctx* ctx, int epi, const CUtensorMap& tmA, const CUten
             for (int k = 0; k < 7; ++k)
                 if (h[b * 8 + k]) { avg[k] += (double)(h[b * 8 + k] - t0); cnt[k]++; }
         for (int k = 0; k < 7; ++k) avg[k] /= std::max(cnt[k], 1);
-        fprintf(stderr, "[tc_prof] epi=%d grid=%u total=%.2fus | avg ns since first CTA entry: entry %.0f prologue %.0f first-operands %.0f "
-                "mma-issued %.0f acc-ready %.0f epi-done %.0f exit %.0f\n", epi, grid, (t6 - t0) * 1e-3, avg[0], avg[1], avg[2], avg[3],
-                avg[4], avg[5], avg[6]);
+        double wait_c = 0, loop_c = 0;
+        for (unsigned b = 0; b < grid; ++b) { wait_c += (double)(h[b * 8 + 7] >> 32); loop_c += (double)(h[b * 8 + 7] & 0xffffffffull); }
+        fprintf(stderr, "[tc_prof] epi=%d grid=%u nt=%d total=%.2fus | avg ns since first CTA entry: entry %.0f prologue %.0f first-operands %.0f "
+                "mma-issued %.0f acc-ready %.0f epi-done %.0f exit %.0f | issuer: mainloop %.0f cyc, of which stalled on operands %.0f cyc "
+                "(after the first k-block)\n", epi, grid, p.nt, (t6 - t0) * 1e-3, avg[0], avg[1], avg[2], avg[3],
+                avg[4], avg[5], avg[6], loop_c / grid, wait_c / grid);
     }
     return AVI_OK;
 }

@@ -18,6 +18,9 @@ struct TcParams {
     int ca, cb;          // cluster shape: ca a-blocks x cb b-chunks share operands by TMA multicast
     int stages;          // filled by avi_tc_launch
     int static_op;       // 1: A is static data (not written by the previous kernel), 2: B is, 0: neither
+    const void* pf_ptr;  // static operand of the NEXT kernel, pulled into L2 by the idle warp 3 while this one computes
+    unsigned long long pf_bytes;
+    unsigned pf_pace_ns;
     unsigned long long* prof;   // AVI_TC_PROF: per-CTA phase timestamps
     int dbg;             // AVI_TC_DBG timing experiments (results are then meaningless): 1 no operand loads, 2 no MMAs
     // epilogue operands

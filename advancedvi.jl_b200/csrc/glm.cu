@@ -279,10 +279,20 @@ struct Glm : avi_model {
     unsigned int* tickets = nullptr;   // last-CTA election per coordinate block (fused backward post-processing)
     int cluster_mode = 1;   // 0: never use thread-block clusters (AVI_TC_CLUSTER=0), 1: planner decides
     bool tc_mode() const { return mode != AVI_GEMM_SIMT_FP32; }
+    // Both layouts of X fit the 126 MB L2 together with R: each kernel then pulls the next kernel's copy of X
+    // into L2 while it computes, so a step that starts with a cold L2 streams X from HBM behind the math.
+    // AVI_L2_STREAM bits: 1 the sampling kernel pulls Xr, 2 the forward kernel pulls Xc (all requests up front),
+    // 4 the forward kernel pulls Xc paced over its mainloop.  Default 0: measured slower on C2 (profiles/README.md).
+    int l2_stream() const {
+        static const int mode = getenv("AVI_L2_STREAM") ? atoi(getenv("AVI_L2_STREAM")) : 0;
+        const double bytes = 4.0 * ((double)n_act * dK + (double)d * nP + (double)capM * ldR);
+        return (tc_mode() && !subsampled && bytes < 100e6) ? mode : 0;
+    }
     bool sample_hook(int ld, int M, SampleHook* h) override {
         if (M <= 0 || ensure(M, ld) != AVI_OK) return false;
         h->kind = 1; h->d = d; h->variant = variant; h->include_prior = include_prior;
         h->Zt = tc_mode() ? Zt : nullptr; h->pre = pre; h->zt_ld = zt_ld; h->zt_seg = x3 ? segd : 0;
+        if (l2_stream() & 1) { h->pf_ptr = Xr; h->pf_bytes = (unsigned long long)n_act * dK * sizeof(float); }
         hooked = true;
         return true;
     }
@@ -317,7 +327,7 @@ struct Glm : avi_model {
     }
 
     // forward: R <- w * resid, llpart/nparts <- partial log-lik sums
-    int32_t forward(const float* Z, int ld, int M, int* nparts) {
+    int32_t forward(const float* Z, int ld, int M, int* nparts, bool want_backward) {
         const float w = likeadj();
         if (hooked) {
             hooked = false;   // the sampling kernel already produced Zt and pre for these samples
@@ -340,6 +350,10 @@ struct Glm : avi_model {
         p.C = R; p.ldc = (int)ldR; p.y = y; p.w = w; p.likelihood = likelihood;
         p.r_seg = x3 ? (int)segn : 0;
         p.static_op = subsampled ? 0 : 2;   // B = X rows (a minibatch copy is rewritten every step: not static)
+        if ((l2_stream() & 6) && want_backward) {
+            p.pf_ptr = Xc; p.pf_bytes = (unsigned long long)d * nP * sizeof(float);
+            p.pf_pace_ns = (l2_stream() & 4) ? 600u : 0u;
+        }
         AVI_CHECK(ensure_buf(&llpart, &llpart_cap, (long long)p.n_bchunk * 4 * capM));
         p.part1 = llpart; p.ldpart = capM;
         CUtensorMap tmA, tmB;
@@ -362,7 +376,7 @@ struct Glm : avi_model {
         if (M <= 0) return AVI_OK;
         AVI_CHECK(ensure(M, ld));
         int nparts = 0;
-        AVI_CHECK(forward(Z, ld, M, &nparts));
+        AVI_CHECK(forward(Z, ld, M, &nparts, G != nullptr));
         const float w = likeadj();
         const float* sl = nullptr; int nslab = 0; long long sstride = 0;
         if (G) {
@@ -390,7 +404,7 @@ struct Glm : avi_model {
         if (M <= 0) return AVI_OK;
         AVI_CHECK(ensure(M, ld));
         int nparts = 0;
-        AVI_CHECK(forward(Z, ld, M, &nparts));
+        AVI_CHECK(forward(Z, ld, M, &nparts, true));
         TcParams p{}; CUtensorMap tmA, tmB;
         AVI_CHECK(backward_setup(M, &p, &tmA, &tmB));
         const int nslab = p.n_ksplit * p.n_bchunk;

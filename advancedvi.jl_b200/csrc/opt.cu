@@ -258,12 +258,13 @@ void drop_graph(avi_opt* op) {
     op->graph_exec = nullptr; op->graph = nullptr;
 }
 
-int32_t run_steps(avi_opt* op, int32_t n, const int32_t* idx_host, int64_t batch, float* value_host, float* elbo_host,
-                  int32_t* n_done) {
+// One avi_opt_steps call = prepare (size the trace, upload minibatch indices, reset the per-call device counters,
+// capture the iteration graph if needed) + launch (n graph replays, no host synchronisation) + finish (copy the
+// trace back, synchronise once, bookkeeping).  The three phases are also exported separately
+// (avi_opt_steps_begin / _enqueue / _end) so that a caller can keep the device queue full.
+int32_t steps_prepare(avi_opt* op, int32_t n, const int32_t* idx_host, int64_t batch) {
     avi_obj* o = op->obj;
     avi_ctx* ctx = op->ctx;
-    if (n_done) *n_done = 0;
-    if (n <= 0) return AVI_OK;
     cudaSetDevice(ctx->device);
     const bool subsampled = idx_host != nullptr;
     if (n > op->trace_cap) {
@@ -291,8 +292,8 @@ int32_t run_steps(avi_opt* op, int32_t n, const int32_t* idx_host, int64_t batch
     AVI_LAUNCHED(ctx);
 
     static const bool no_graph = getenv("AVI_NO_GRAPH") && atoi(getenv("AVI_NO_GRAPH")) != 0;
-    const bool capturable = !no_graph && !ctx->timing && !o->model->needs_sync_eval() && !(ctx->nranks > 1 && !ctx->comm_capturable);
-    if (capturable) {
+    op->use_graph = !no_graph && !ctx->timing && !o->model->needs_sync_eval() && !(ctx->nranks > 1 && !ctx->comm_capturable);
+    if (op->use_graph) {
         const int64_t gen = o->generation * 1000003 + o->model->generation;
         if (op->graph_exec && (op->graph_gen != gen || op->graph_subsampled != subsampled || op->graph_batch != batch))
             drop_graph(op);
@@ -317,11 +318,31 @@ int32_t run_steps(avi_opt* op, int32_t n, const int32_t* idx_host, int64_t batch
             op->graph_gen = o->generation * 1000003 + o->model->generation;
             op->graph_subsampled = subsampled; op->graph_batch = batch;
         }
+    }
+    op->call_cap = n; op->call_enqueued = 0; op->call_subsampled = subsampled; op->call_batch = batch;
+    return AVI_OK;
+}
+
+int32_t steps_launch(avi_opt* op, int32_t n) {
+    avi_ctx* ctx = op->ctx;
+    if (op->call_enqueued + n > op->call_cap) AVI_FAIL(ctx, AVI_ERR_INVALID, "more iterations enqueued than avi_opt_steps_begin reserved");
+    if (op->use_graph) {
         for (int32_t it = 0; it < n; ++it) AVI_CUDA(ctx, cudaGraphLaunch(op->graph_exec, ctx->stream));
         ctx->launches += (int64_t)n * op->graph_launches;
     } else {
-        for (int32_t it = 0; it < n; ++it) AVI_CHECK(enqueue_iteration(op, subsampled, batch));
+        for (int32_t it = 0; it < n; ++it) AVI_CHECK(enqueue_iteration(op, op->call_subsampled, op->call_batch));
     }
+    op->call_enqueued += n;
+    return AVI_OK;
+}
+
+int32_t steps_finish(avi_opt* op, float* value_host, float* elbo_host, int32_t* n_done) {
+    avi_obj* o = op->obj;
+    avi_ctx* ctx = op->ctx;
+    const int n = op->call_enqueued;
+    op->call_cap = 0; op->call_enqueued = 0;
+    if (n_done) *n_done = 0;
+    if (n <= 0) return AVI_OK;
     ObjDeviceState hs{};
     AVI_CUDA(ctx, cudaMemcpyAsync(op->h_trace, op->trace, 2 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     AVI_CUDA(ctx, cudaMemcpyAsync(&hs, o->d_state, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
@@ -336,6 +357,17 @@ int32_t run_steps(avi_opt* op, int32_t n, const int32_t* idx_host, int64_t batch
     op->iteration += done;
     if (n_done) *n_done = done;
     return AVI_OK;
+}
+
+int32_t run_steps(avi_opt* op, int32_t n, const int32_t* idx_host, int64_t batch, float* value_host, float* elbo_host,
+                  int32_t* n_done) {
+    if (n_done) *n_done = 0;
+    if (n <= 0) return AVI_OK;
+    if (op->call_cap) AVI_FAIL(op->ctx, AVI_ERR_STATE, "avi_opt_steps_begin is open: call avi_opt_steps_end first");
+    AVI_CHECK(steps_prepare(op, n, idx_host, batch));
+    int32_t rc = steps_launch(op, n);
+    if (rc != AVI_OK) { op->call_cap = 0; op->call_enqueued = 0; return rc; }
+    return steps_finish(op, value_host, elbo_host, n_done);
 }
 
 }  // namespace
@@ -400,6 +432,26 @@ int32_t avi_opt_destroy(avi_opt* op) {
 int32_t avi_opt_steps(avi_opt* op, int32_t n, float* value_host, float* elbo_host, int32_t* n_done) {
     if (!op) return AVI_ERR_INVALID;
     return run_steps(op, n, nullptr, 0, value_host, elbo_host, n_done);
+}
+
+int32_t avi_opt_steps_begin(avi_opt* op, int32_t capacity) {
+    if (!op) return AVI_ERR_INVALID;
+    if (capacity <= 0) AVI_FAIL(op->ctx, AVI_ERR_INVALID, "capacity must be positive");
+    if (op->call_cap) AVI_FAIL(op->ctx, AVI_ERR_STATE, "avi_opt_steps_begin is already open");
+    return steps_prepare(op, capacity, nullptr, 0);
+}
+
+int32_t avi_opt_steps_enqueue(avi_opt* op, int32_t n) {
+    if (!op) return AVI_ERR_INVALID;
+    if (!op->call_cap) AVI_FAIL(op->ctx, AVI_ERR_STATE, "avi_opt_steps_enqueue without avi_opt_steps_begin");
+    if (n <= 0) return AVI_OK;
+    return steps_launch(op, n);
+}
+
+int32_t avi_opt_steps_end(avi_opt* op, float* value_host, float* elbo_host, int32_t* n_done) {
+    if (!op) return AVI_ERR_INVALID;
+    if (!op->call_cap) AVI_FAIL(op->ctx, AVI_ERR_STATE, "avi_opt_steps_end without avi_opt_steps_begin");
+    return steps_finish(op, value_host, elbo_host, n_done);
 }
 
 int32_t avi_opt_steps_subsampled(avi_opt* op, int32_t n, const int32_t* idx_host, int64_t batch, float* value_host,

@@ -214,12 +214,17 @@ def main():
     barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     l0 = ctx.launch_count()
+    # the K iterations are enqueued without a host round trip (avi_opt_steps_begin / _enqueue / _end), so the event
+    # pairs bracket device work only: flush | ev0 | one captured iteration | ev1
+    state.steps_begin(K)
     for k in range(K):
         with torch.cuda.stream(ext):
             flush.zero_()                                   # evict X, R, Z from L2 (untimed)
             ev[k][0].record(ext)
-        L.check(L.lib.avi_opt_steps(state.h, 1, L.fptr(vals), L.fptr(elbos), C.byref(nd)), ctx.h)
+        state.steps_enqueue(1)
         ev[k][1].record(ext)
+    _, cold_elbos, n_cold = state.steps_end()
+    assert n_cold == K, "objective diverged"
     barrier()
     launches = ctx.launch_count() - l0
     cold_ms = sum(a.elapsed_time(b) for a, b in ev)

@@ -184,6 +184,13 @@ int32_t avi_opt_create(avi_obj* obj, int32_t rule, const float* hyper, int32_t n
  * AVI_OK with *n_done < n when the value slot is not finite (the caller raises).  One stream
  * synchronisation at the end. */
 int32_t avi_opt_steps(avi_opt* opt, int32_t n, float* value_host, float* elbo_host, int32_t* n_done);
+/* The same call in three phases, for callers that keep the device queue full (no host round trip between
+ * iterations): _begin reserves trace space for `capacity` iterations and does every piece of setup (graph capture
+ * included); _enqueue launches n more iterations and returns WITHOUT synchronising (sum of n <= capacity);
+ * _end copies the trace back, synchronises once and reports like avi_opt_steps.  Full-batch objectives only. */
+int32_t avi_opt_steps_begin(avi_opt* opt, int32_t capacity);
+int32_t avi_opt_steps_enqueue(avi_opt* opt, int32_t n);
+int32_t avi_opt_steps_end(avi_opt* opt, float* value_host, float* elbo_host, int32_t* n_done);
 /* same, with the minibatch of every iteration given up front: idx_host holds n * batch row
  * indices (SubsampledObjective, src/algorithms/subsampledobjective.jl:64-90) */
 int32_t avi_opt_steps_subsampled(avi_opt* opt, int32_t n, const int32_t* idx_host, int64_t batch,

@@ -114,3 +114,34 @@ def test_many_handles_and_reuse(avi, ctx):
     obj.close()
     for p in probs:
         p.close()
+
+
+def test_steps_begin_enqueue_end_matches_blocking_call(avi, ctx):
+    """avi_opt_steps_begin / _enqueue / _end (no host round trip between iterations) == avi_opt_steps, bitwise;
+    misuse is reported as a state error."""
+    from advancedvi_jl_b200 import api as A
+    X, y = Mo.synth_glm_data(200, 12, seed=4)
+    prob = avi.LogReg(ctx, X, y, gemm="tf32")
+    D = 13
+    q = avi.MeanFieldGaussian(np.zeros(D, np.float32), np.full(D, 0.5, np.float32))
+    alg = avi.KLMinRepGradDescent(optimizer=avi.Adam(1e-2), n_samples=16, operator=avi.ClipScale())
+    _, info, st_ref = avi.optimize(KEY, alg, 10, prob, q)
+    lam_ref, avg_ref, _ = st_ref.params()
+
+    obj = avi.Objective(KEY, alg.objective, q, prob)
+    st = A._OptState(alg, obj, q)
+    with pytest.raises(avi.AviError, match="without avi_opt_steps_begin"):
+        st.steps_enqueue(1)
+    st.steps_begin(10)
+    with pytest.raises(avi.AviError, match="already open"):
+        st.steps_begin(10)
+    st.steps_enqueue(3)
+    st.steps_enqueue(7)
+    with pytest.raises(avi.AviError, match="reserved"):
+        st.steps_enqueue(1)
+    vals, elbos, done = st.steps_end()
+    assert done == 10 and st.iteration == 10
+    assert np.array_equal(elbos[:10], np.array([i["elbo"] for i in info], np.float32))
+    lam, avg, _ = st.params()
+    assert np.array_equal(lam, lam_ref) and np.array_equal(avg, avg_ref)
+    st.close(); obj.close(); st_ref.close(); st_ref.obj.close(); prob.close()
