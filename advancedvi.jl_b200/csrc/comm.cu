@@ -25,13 +25,37 @@ constexpr int FLAG_WORDS = AVI_FLAG_WORDS;
 struct CommState {
     int rank = 0, nranks = 1;
     int64_t max_floats = 0;
-    void* base = nullptr;        // my symmetric allocation: [flags (256 B) | slot 0 | slot 1]
+    int64_t ll_cap = 0;          // floats per LL lane
+    void* base = nullptr;        // my symmetric allocation: [flags (256 B) | slot 0 | slot 1 | LL area]
     void* peer_base[MAX_RANKS] = {nullptr};
     bool opened[MAX_RANKS] = {false};
     CommDev* dev = nullptr;
     PeerTable table{};
     bool connected = false;
 };
+
+// Small payloads: the low-latency push protocol (comm_dev.cuh).  Every thread pushes its elements to all peers, then
+// sums the ranks' values in rank order as they arrive; the last CTA to finish advances the sequence number.
+__global__ void __launch_bounds__(256)
+k_allreduce_ll(float* __restrict__ buf, long long count, CommPeers c) {
+    const unsigned int seq = *reinterpret_cast<volatile unsigned int*>(&c.dev->seq) + 1u;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (long long i = i0; i < count; i += stride) ll_push(c, seq, i, buf[i]);
+    for (long long i = i0; i < count; i += stride) {
+        const long long idx[1] = {i}; const bool need[1] = {true}; const float own[1] = {buf[i]};
+        float out[1];
+        ll_gather<1>(c, seq, idx, need, own, out);
+        buf[i] = out[0];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(&c.dev->depart, 1u) == gridDim.x - 1) {
+            c.dev->depart = 0;
+            *reinterpret_cast<volatile unsigned int*>(&c.dev->seq) = seq;
+        }
+    }
+}
 
 __global__ void __launch_bounds__(256)
 k_allreduce_oneshot(float* __restrict__ buf, long long count, long long slot_stride, PeerTable t, int rank,
@@ -75,6 +99,8 @@ int32_t finish_connect(avi_ctx* ctx, CommState* cs) {
     for (int r = 0; r < cs->nranks; ++r) {
         cs->table.flags[r] = static_cast<unsigned int*>(cs->peer_base[r]);
         cs->table.data[r] = reinterpret_cast<float*>(static_cast<char*>(cs->peer_base[r]) + FLAG_WORDS * 4);
+        cs->table.ll[r] = reinterpret_cast<LLWord*>(static_cast<char*>(cs->peer_base[r]) + FLAG_WORDS * 4 +
+                                                    2 * (size_t)cs->max_floats * sizeof(float));
     }
     cs->connected = true;
     ctx->rank = cs->rank; ctx->nranks = cs->nranks;
@@ -89,6 +115,8 @@ bool avi_comm_peers(avi_ctx* ctx, int64_t count, CommPeers* out) {
     CommState* cs = state(ctx);
     if (!cs || !cs->connected || count > cs->max_floats) return false;
     out->nranks = cs->nranks; out->rank = cs->rank; out->slot_stride = cs->max_floats; out->t = cs->table; out->dev = cs->dev;
+    static const bool ll_off = getenv("AVI_COMM_LL") && atoi(getenv("AVI_COMM_LL")) == 0;
+    out->ll_cap = ll_off ? 0 : cs->ll_cap;
     return true;
 }
 
@@ -98,6 +126,12 @@ int32_t avi_comm_exchange(avi_ctx* ctx, float* buf, int64_t count) {
     if (count > cs->max_floats) AVI_FAIL(ctx, AVI_ERR_COMM, "exchange payload larger than the symmetric buffer");
     int grid = (int)std::min<int64_t>(ceil_div(count, 256 * 8), 64);
     if (grid < 1) grid = 1;
+    CommPeers peers;
+    if (avi_comm_peers(ctx, count, &peers) && peers.ll_cap >= count) {
+        k_allreduce_ll<<<(int)std::min<int64_t>(ceil_div(count, 256), 32), 256, 0, ctx->stream>>>(buf, count, peers);
+        AVI_LAUNCHED(ctx);
+        return AVI_OK;
+    }
     k_allreduce_oneshot<<<grid, 256, 0, ctx->stream>>>(buf, count, cs->max_floats, cs->table, cs->rank, cs->nranks, cs->dev);
     AVI_LAUNCHED(ctx);
     return AVI_OK;
@@ -125,8 +159,13 @@ int32_t avi_comm_buffer(avi_ctx* ctx, int64_t max_floats, char* handle_out) {
     CommState* cs = new CommState();
     ctx->comm = cs;
     cs->max_floats = round_up(max_floats, 64);
-    const size_t bytes = FLAG_WORDS * 4 + 2 * (size_t)cs->max_floats * sizeof(float);
+    cs->ll_cap = std::min<int64_t>(cs->max_floats, 16384);   // LL lanes for payloads of up to 64 KB
+    const size_t ll_bytes = 2 * (size_t)MAX_RANKS * (size_t)cs->ll_cap * sizeof(LLWord);
+    const size_t bytes = FLAG_WORDS * 4 + 2 * (size_t)cs->max_floats * sizeof(float) + ll_bytes;
     AVI_CHECK(avi_dev_alloc(ctx, &cs->base, bytes));
+    // avi_dev_alloc zero-fills on the stream (sequence numbers start at 1: zero = nothing yet); the fill must have
+    // happened before any peer can push into the buffer, i.e. before the handle leaves this call
+    AVI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     AVI_CHECK(avi_alloc(ctx, &cs->dev, 1));
     cudaIpcMemHandle_t h;
     AVI_CUDA(ctx, cudaIpcGetMemHandle(&h, cs->base));

@@ -71,26 +71,34 @@ __device__ __forceinline__ void mf_finalize_update_body(const MfTailArgs& t) {
     const bool adam = a.rule == AVI_RULE_ADAM, dog = a.rule == AVI_RULE_DOG || a.rule == AVI_RULE_DOWG;
     const bool polyavg = a.averager == AVI_AVG_POLYNOMIAL;
     float v[ITEMS][4], x[ITEMS][2], s1m[ITEMS][2], s2m[ITEMS][2], av[ITEMS][2];
-    // Fused exchange (sample sharding): publish my partial sums in my symmetric slot, release-store the sequence
-    // number into every peer's flag word, acquire-wait for all peers, then take every needed entry as the sum
-    // over the ranks' slots IN RANK ORDER: identical bits on all ranks, no separate all-reduce launch.
+    // Fused exchange (sample sharding), low-latency protocol: every rank PUSHES its partial sums into each peer's
+    // receive lane as 8-byte {value, sequence number} words (one NVLink store latency, no fence, no flag round trip),
+    // then takes every entry it needs as the sum over the ranks' lanes IN RANK ORDER (own values from `acc`):
+    // identical bits on all ranks, no separate all-reduce launch.  Lanes alternate with the parity of the sequence
+    // number; a peer can only overwrite a lane at seq + 2 after it consumed my seq + 1 push, which I issue after
+    // these reads.  Without an LL area (payload too large) the pull protocol of comm.cu runs here instead.
     const int NR = t.comm.nranks;
+    const bool ll = ITEMS <= 2 && NR > 1 && t.comm.ll_cap >= t.acc_len;   // (ITEMS > 2: too many registers)
     unsigned int seq = 0;
     long long soff = 0;
     if (NR > 1) {
         seq = *reinterpret_cast<volatile unsigned int*>(&t.comm.dev->seq) + 1u;
-        soff = (long long)(seq & 1u) * t.comm.slot_stride;
-        float* mine = t.comm.t.data[t.comm.rank] + soff;
-        for (long long i = tid; i < t.acc_len; i += 1024) mine[i] = acc[i];
-        __threadfence_system();
-        __syncthreads();
-        if (tid == 0)
-            for (int r = 0; r < NR; ++r) st_release_sys(t.comm.t.flags[r] + t.comm.rank, seq);
-        if (tid < NR) {
-            const unsigned int* f = t.comm.t.flags[t.comm.rank] + tid;
-            while ((int)(ld_acquire_sys(f) - seq) < 0) { }
+        if (ll) {
+            for (long long i = tid; i < t.acc_len; i += 1024) ll_push(t.comm, seq, i, acc[i]);
+        } else {
+            soff = (long long)(seq & 1u) * t.comm.slot_stride;
+            float* mine = t.comm.t.data[t.comm.rank] + soff;
+            for (long long i = tid; i < t.acc_len; i += 1024) mine[i] = acc[i];
+            __threadfence_system();
+            __syncthreads();
+            if (tid == 0)
+                for (int r = 0; r < NR; ++r) st_release_sys(t.comm.t.flags[r] + t.comm.rank, seq);
+            if (tid < NR) {
+                const unsigned int* f = t.comm.t.flags[t.comm.rank] + tid;
+                while ((int)(ld_acquire_sys(f) - seq) < 0) { }
+            }
+            __syncthreads();
         }
-        __syncthreads();
     }
     auto acc_at = [&](size_t idx) -> float {
         if (NR <= 1) return acc[idx];
@@ -98,14 +106,49 @@ __device__ __forceinline__ void mf_finalize_update_body(const MfTailArgs& t) {
         for (int r = 0; r < NR; ++r) s += ld_relaxed_sys(t.comm.t.data[r] + soff + idx);
         return s;
     };
+    const size_t sbase = 4 * (size_t)accv;
+    float c0, c1, c2, c3;
+    if constexpr (ITEMS <= 2) { if (ll) {
+        // all the entries this thread needs, gathered together: ITEMS x 4 vector entries + the 4 scalars
+        constexpr int NG = 4 * ITEMS + 4;
+        long long gi[NG]; bool gn[NG]; float go[NG], gv[NG];
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            const int i = tid + k * 1024;
+            const bool ok = i < D;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                gi[4 * k + c] = (long long)c * accv + i;
+                gn[4 * k + c] = ok && (c < 2 || need23);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { gi[4 * ITEMS + c] = (long long)sbase + c; gn[4 * ITEMS + c] = true; }
+#pragma unroll
+        for (int n = 0; n < NG; ++n) go[n] = gn[n] ? acc[gi[n]] : 0.f;
+        ll_gather<NG>(t.comm, seq, gi, gn, go, gv);
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) v[k][c] = gv[4 * k + c];
+        c0 = gv[4 * ITEMS]; c1 = gv[4 * ITEMS + 1]; c2 = gv[4 * ITEMS + 2]; c3 = gv[4 * ITEMS + 3];
+    } }
+    if (!ll) {
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            const int i = tid + k * 1024;
+            const bool ok = i < D;
+            v[k][0] = ok ? acc_at(i) : 0.f;
+            v[k][1] = ok ? acc_at((size_t)accv + i) : 0.f;
+            v[k][2] = ok && need23 ? acc_at(2 * (size_t)accv + i) : 0.f;
+            v[k][3] = ok && need23 ? acc_at(3 * (size_t)accv + i) : 0.f;
+        }
+        c0 = acc_at(sbase); c1 = acc_at(sbase + 1); c2 = acc_at(sbase + 2); c3 = acc_at(sbase + 3);
+    }
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
         const int i = tid + k * 1024;
         const bool ok = i < D;
-        v[k][0] = ok ? acc_at(i) : 0.f;
-        v[k][1] = ok ? acc_at((size_t)accv + i) : 0.f;
-        v[k][2] = ok && need23 ? acc_at(2 * (size_t)accv + i) : 0.f;
-        v[k][3] = ok && need23 ? acc_at(3 * (size_t)accv + i) : 0.f;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const size_t p = (size_t)h * D + i;
@@ -118,8 +161,6 @@ __device__ __forceinline__ void mf_finalize_update_body(const MfTailArgs& t) {
     float sl = 0.f, sq = 0.f;
     if (deferred)
         for (int m = tid; m < Mloc; m += 1024) { sl += logp[m]; sq += esq[m]; }
-    const size_t sbase = 4 * (size_t)accv;
-    const float c0 = acc_at(sbase), c1 = acc_at(sbase + 1), c2 = acc_at(sbase + 2), c3 = acc_at(sbase + 3);
     const float shift = out[3];
     const int halted = st->halted;
     const float b1t = sc[SC_B1T], b2t = sc[SC_B2T], t_avg = sc[SC_T], v_old = sc[SC_V], r_old = sc[SC_R];
