@@ -43,6 +43,18 @@ void avi_ktime_mark(avi_ctx* ctx, const char* name) {
     t->ev.push_back(e);
 }
 
+cudaError_t avi_stream_wait(avi_ctx* ctx) {
+    static const bool spin = !(getenv("AVI_SPIN_SYNC") && atoi(getenv("AVI_SPIN_SYNC")) == 0);
+    if (!spin) return cudaStreamSynchronize(ctx->stream);
+    cudaError_t e;
+    while ((e = cudaStreamQuery(ctx->stream)) == cudaErrorNotReady) {
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    return e;
+}
+
 bool avi_pdl_enabled() {
     static const bool on = !(getenv("AVI_PDL") && atoi(getenv("AVI_PDL")) == 0);
     return on;
@@ -100,7 +112,19 @@ int32_t avi_ctx_create(int32_t device, avi_ctx** out) {
         delete ctx;
         return AVI_ERR_CUDA;
     }
+    if (getenv("AVI_TIMELINE") && atoi(getenv("AVI_TIMELINE")) != 0) {
+        avi_dev_alloc(ctx, reinterpret_cast<void**>(&ctx->tl), 32 * sizeof(unsigned long long));
+        avi_dev_alloc(ctx, reinterpret_cast<void**>(&ctx->tl_hist), 64 * 32 * sizeof(unsigned long long));
+    }
     *out = ctx;
+    return AVI_OK;
+}
+
+int32_t avi_ctx_timeline_get(avi_ctx* ctx, uint64_t* hist_host) {
+    if (!ctx || !hist_host) return AVI_ERR_INVALID;
+    if (!ctx->tl_hist) AVI_FAIL(ctx, AVI_ERR_STATE, "timeline disabled (set AVI_TIMELINE=1 before avi_ctx_create)");
+    AVI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    AVI_CUDA(ctx, cudaMemcpy(hist_host, ctx->tl_hist, 64 * 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return AVI_OK;
 }
 
@@ -109,6 +133,8 @@ int32_t avi_ctx_destroy(avi_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     avi_comm_destroy(ctx);
+    if (ctx->tl) cudaFree(ctx->tl);
+    if (ctx->tl_hist) cudaFree(ctx->tl_hist);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return AVI_OK;
@@ -433,7 +459,7 @@ int32_t avi_obj_estimate_gradient(avi_obj* o, const float* lambda_host, int64_t 
         o->eg_calls++;
         o->eg_gen = o->generation * 1000003 + o->model->generation;
     }
-    AVI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    AVI_CUDA(ctx, avi_stream_wait(ctx));
     if (grad_host) std::memcpy(grad_host, o->h_grad, (size_t)P * sizeof(float));
     if (value) *value = o->h_grad[P];
     if (elbo) *elbo = o->h_grad[P + 1];

@@ -71,6 +71,9 @@ struct avi_ctx {
         int64_t count = 0;
     };
     std::vector<KTimer> timers;
+    // AVI_TIMELINE=1: per-kernel %globaltimer stamps of the fused iteration (device_utils.cuh), history of 64 steps
+    unsigned long long* tl = nullptr;
+    unsigned long long* tl_hist = nullptr;
     bool comm_capturable = false;   // the exchange is a kernel of ours (comm.cu), safe inside a graph
     void* comm = nullptr;           // struct CommState* (comm.cu)
 };
@@ -87,6 +90,9 @@ struct AviTimed {
 // predecessor wrote, and pdl_trigger() lets ITS successor start early.  Inside a captured graph this becomes
 // a programmatic edge.  AVI_PDL=0 turns it off (plain stream order).
 bool avi_pdl_enabled();
+// Wait for the ctx stream on the hot blocking calls (estimate_gradient!, avi_opt_steps): polls cudaStreamQuery instead of
+// sleeping in cudaStreamSynchronize, which returns ~10 us after the work is done.  AVI_SPIN_SYNC=0: plain synchronise.
+cudaError_t avi_stream_wait(avi_ctx* ctx);
 template <typename... KArgs, typename... Args>
 static inline cudaError_t avi_launch_pdl(avi_ctx* ctx, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
                                          Args... args) {
@@ -136,6 +142,7 @@ struct SampleHook {
     float* Zt = nullptr;
     int zt_ld = 0, zt_seg = 0;   // row pitch of Zt; zt_seg > 0: 3xTF32 split [hi | hi | lo] in segments of zt_seg
     float4* pre = nullptr;
+    unsigned long long* tl = nullptr;     // step timeline (diagnostic)
     const void* pf_ptr = nullptr;         // static operand of the next kernel to pull into L2 meanwhile (may be null)
     unsigned long long pf_bytes = 0;
 };
@@ -250,6 +257,9 @@ struct avi_opt {
     // captured iteration
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
+    cudaGraph_t graph_u = nullptr;          // graph_unroll iterations in one graph
+    cudaGraphExec_t graph_u_exec = nullptr;
+    int graph_unroll = 1;
     bool graph_subsampled = false;
     int64_t graph_batch = 0;
     int64_t graph_gen = -1;

@@ -109,6 +109,21 @@ __device__ __forceinline__ float4 normal4(uint32_t q, uint32_t m, unsigned long 
 
 // programmatic dependent launch (see avi_launch_pdl): no-ops when the grid was launched without the attribute
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Step timeline (AVI_TIMELINE=1, diagnostic): every kernel of the fused iteration stamps %globaltimer into
+// tl[16]: [id] first CTA entered, [4 + id] first CTA past its dependency wait, [8 + id] last CTA done
+// (id: 0 sample, 1 forward, 2 backward, 3 tail).  Null pointer: nothing happens.
+__device__ __forceinline__ unsigned long long tl_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void tl_min(unsigned long long* tl, int slot) {
+    if (tl && threadIdx.x == 0 && threadIdx.y == 0) atomicMin(tl + slot, tl_now());
+}
+__device__ __forceinline__ void tl_max(unsigned long long* tl, int slot) {
+    if (tl && threadIdx.x == 0 && threadIdx.y == 0) atomicMax(tl + slot, tl_now());
+}
+
 // Ask the memory system to pull [base, base + bytes) into L2 (cp.async.bulk.prefetch.L2, a per-warp instruction with
 // a uniform address): warp `widx` of `nwarps` issues every nwarps-th chunk of `chunk` bytes.  Used to stream the NEXT
 // kernel's static operand from HBM while the current kernel computes (an L2 hit costs a tag lookup).  base must be

@@ -38,10 +38,12 @@ k_sample(const float* __restrict__ lambda, int D, int ld, int m0, int Mloc, cons
          float* __restrict__ E, float* __restrict__ esq, SampleHook hk) {
     extern __shared__ __align__(16) float s_ms[];   // STAGE: [ld] mu, [ld] s
     constexpr bool STAGE = !FULLRANK && SPLIT == 1;
+    if (HOOK) tl_min(hk.tl, 0);
     pdl_trigger();
     if (HOOK && hk.pf_bytes)   // stream the forward kernel's X into L2 while this kernel runs (static data: before the wait)
         l2_prefetch_span(hk.pf_ptr, hk.pf_bytes, blockIdx.x * SAMPLE_WARPS + (threadIdx.x >> 5), gridDim.x * SAMPLE_WARPS, 8192);
     pdl_wait();   // lambda and the step counter come from the previous iteration's tail
+    if (HOOK) tl_min(hk.tl, 4);
     const unsigned long long step = use_val ? st_val.step : st->step;
     const PhiloxKeys pk(use_val ? st_val.key : st->key);
     const uint32_t c2 = (uint32_t)step, c3 = eps_ctr3(step, stream_id);
@@ -130,6 +132,7 @@ k_sample(const float* __restrict__ lambda, int D, int ld, int m0, int Mloc, cons
             if (HOOK) hk.pre[m] = glm_prior_terms(bsq, eta, hk.d, hk.variant, hk.include_prior);
         }
     }
+    if (HOOK) tl_max(hk.tl, 8);
 }
 
 // full-rank: Z[m][i] += mu[i] after the L * eps contraction; zero the padding columns

@@ -38,7 +38,7 @@ struct SmemCtl {
     uint64_t full[MAX_STAGES], empty[MAX_STAGES], tmem_full[2], tmem_empty[2];
     uint32_t tmem_base;
     int flag;
-    float ys[2][512];   // FWD: y per accumulator stage (<= 256 used); BWD: reduction scratch
+    alignas(16) float ys[2][512];   // FWD: y per accumulator stage (<= 256 used); BWD: reduction scratch
 };
 
 __device__ __forceinline__ unsigned long long gtime_ns() {
@@ -161,10 +161,16 @@ __device__ __forceinline__ void epilogue_unit(const TcParams& p, SmemCtl* ctl, i
             tc::tmem_ld8(tacc + (uint32_t)c, v);
             const int b0 = bc * NT + c;
             if (EPI == EPI_GLM_FWD) {
-                float r[8];
+                float r[8], yv[8];
+                {   // c is a multiple of 8 and ys is 16-byte aligned: two LDS.128
+                    const float4 y0 = *reinterpret_cast<const float4*>(&ctl->ys[as][c]);
+                    const float4 y1 = *reinterpret_cast<const float4*>(&ctl->ys[as][c + 4]);
+                    yv[0] = y0.x; yv[1] = y0.y; yv[2] = y0.z; yv[3] = y0.w; yv[4] = y1.x; yv[5] = y1.y; yv[6] = y1.z; yv[7] = y1.w;
+                }
+                const bool full = b0 + 8 <= p.Nb;   // only the last chunk of the data rows needs per-element masks
+                float lpv[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float yv = ctl->ys[as][c + j];
                     float lp, rr;
                     if (LIK == 0) {
                         const float l = v[j];
@@ -172,22 +178,32 @@ __device__ __forceinline__ void epilogue_unit(const TcParams& p, SmemCtl* ctl, i
                         const float inv = tc::rcp_approx(1.0f + e);                         // in [1/2, 1)
                         const float sig = l >= 0.0f ? inv : e * inv;
                         // y l - log1pexp(l) = y l - max(l, 0) + ln(inv)
-                        lp = fmaf(yv, l, fmaf(0.6931471805599453f, tc::lg2_approx(inv), -fmaxf(l, 0.0f)));
-                        rr = yv - sig;
+                        lp = fmaf(yv[j], l, fmaf(0.6931471805599453f, tc::lg2_approx(inv), -fmaxf(l, 0.0f)));
+                        rr = yv[j] - sig;
                     } else {
-                        rr = yv - v[j];
+                        rr = yv[j] - v[j];
                         lp = fmaf(-0.5f * rr, rr, -0.5f * AVI_LOG2PI);
                     }
-                    const bool ok = b0 + j < p.Nb;
-                    s1 += ok ? lp : 0.0f;
-                    r[j] = ok ? p.w * rr : 0.0f;
+                    lpv[j] = lp; r[j] = p.w * rr;
                 }
-                float rlo[8];
+                if (!full) {   // warp-uniform, rare
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float hi = tc::round_tf32(r[j]);
-                    rlo[j] = tc::round_tf32(r[j] - hi);
-                    r[j] = hi;
+                    for (int j = 0; j < 8; ++j)
+                        if (b0 + j >= p.Nb) { lpv[j] = 0.0f; r[j] = 0.0f; }
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s1 += lpv[j];
+                float rlo[8];
+                if (p.r_seg) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float hi = tc::round_tf32(r[j]);
+                        rlo[j] = tc::round_tf32(r[j] - hi);
+                        r[j] = hi;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { r[j] = tc::round_tf32(r[j]); rlo[j] = 0.0f; }
                 }
                 // (staging this tile through shared memory for 128-byte row stores was measured slower: the
                 // extra STS + barrier cost more than the 32-byte-sector stores; profiles/README.md)
@@ -290,6 +306,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     SmemCtl* ctl = reinterpret_cast<SmemCtl*>(tiles + stages * stage_bytes);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     TC_STAMP(0, threadIdx.x == 0);
+    tl_min(p.tl, p.tl_id);
 
     // thread-block cluster: CA a-blocks x CB b-chunks of one k-split.  The A tile of an a-block is needed
     // by the CB CTAs of its row, the B tile of a b-chunk by the CA CTAs of its column: every CTA loads
@@ -347,6 +364,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
     }
     pdl_wait();   // everything above overlapped the previous kernel's tail; dependent operands from here on
+    tl_min(p.tl, 4 + p.tl_id);
     tc::fence_after_sync();
     const uint32_t tmem_base = ctl->tmem_base;
     TC_STAMP(1, threadIdx.x == 0);
@@ -469,6 +487,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         tc::tmem_dealloc(tmem_base, 512);
     }
     TC_STAMP(6, threadIdx.x == 64);
+    tl_max(p.tl, 8 + p.tl_id);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -686,10 +705,12 @@ static int max_active_clusters(avi_ctx* ctx, int csz) {
 
 // Tiling plan.  split_k = false: many b-chunks, full K per unit (the epilogue is non-linear: GLM forward);
 // split_k = true: few output tiles, K split across the chip (linear epilogues).
-// Cost model (cycles, from profiles/r1_phase_timeline.txt): a kind::tf32 M=128 MMA costs ~145 cycles whatever
-// nt <= 256 is, i.e. 580 per 32-wide k-block; the epilogue costs ~58 cycles per column; ~6000 fixed per wave.
-// Operand traffic is not the limit, so cluster multicast / CTA pairs do not pay at these sizes; they stay
-// available (force_cluster = 2 / AVI_TC_CLUSTER=2, AVI_TC_PAIR) and tested.
+// Cost model (cycles; scripts/ubench/mma_rate.cu and profiles/r2_tc_sweep.txt): a kind::tf32 M=128 MMA (K = 8) costs
+// max(48, nt / 2) cycles on the tensor pipe, but an SM ingests TMA operand bytes at only ~71 B/cycle, so a 32-wide
+// k-block of a 128 x nt tile costs max(4 * max(48, nt / 2), (128 + nt) * 128 / 71): every single-CTA TF32 tile is
+// ingest-bound ((128 + nt) * 128 B per 2 * nt MMA cycles > 71 B/cycle for all nt <= 256).  The epilogue costs ~58
+// cycles per column; ~6000 fixed per wave.  Multicast does not reduce what an SM ingests, so clusters only pay when
+// L2 bandwidth is the limit; they stay available (force_cluster = 2 / AVI_TC_CLUSTER=2, AVI_TC_CA/CB) and tested.
 int32_t avi_tc_plan(avi_ctx* ctx, int64_t Ma, int64_t Nb, int64_t K, bool split_k, int force_cluster, TcParams* p) {
     const int sms = ctx->prop.multiProcessorCount;
     p->Ma = (int)Ma; p->Nb = (int)Nb;
@@ -724,7 +745,7 @@ int32_t avi_tc_plan(avi_ctx* ctx, int64_t Ma, int64_t Nb, int64_t K, bool split_
                 }
                 const int64_t units = tiles * n_ksplit;
                 const int64_t waves = ceil_div(units, maxc);
-                const double per_kb = 580.0;
+                const double per_kb = std::max(4.0 * std::max(48.0, nt / 2.0), (128.0 + nt) * 128.0 / 71.0) + 30.0;
                 double cost = (double)waves * (per_kb * kbps + 58.0 * nt + 6000.0) + (csz > 1 ? 500.0 : 0.0);
                 if (force_cluster == 2 && csz > 1) cost *= 0.25;   // testing / experiments: prefer clusters
                 if (cost < best) {
@@ -752,7 +773,8 @@ int32_t avi_tc_plan(avi_ctx* ctx, int64_t Ma, int64_t Nb, int64_t K, bool split_
                 n_ksplit = (int)ceil_div(p->n_kblk, kbps);
             }
             const int64_t waves = ceil_div(tiles * n_ksplit, maxp);
-            const double per_kb = 520.0;
+            // per SM: 128 rows of A and nt / 2 rows of B; measured ~25 % above the ingest model (pair handshakes)
+            const double per_kb = 1.25 * std::max(4.0 * std::max(48.0, nt / 2.0), (128.0 + nt / 2.0) * 128.0 / 71.0) + 30.0;
             double cost = (double)waves * (per_kb * kbps + 58.0 * nt + 8000.0);
             if (pair_env == 2) cost *= 0.25;
             if (cost < best) {

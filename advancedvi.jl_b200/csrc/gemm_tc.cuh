@@ -21,6 +21,8 @@ struct TcParams {
     const void* pf_ptr;  // static operand of the NEXT kernel, pulled into L2 by the idle warp 3 while this one computes
     unsigned long long pf_bytes;
     unsigned pf_pace_ns;
+    unsigned long long* tl;     // step timeline (diagnostic), slot id tl_id
+    int tl_id;
     unsigned long long* prof;   // AVI_TC_PROF: per-CTA phase timestamps
     int dbg;             // AVI_TC_DBG timing experiments (results are then meaningless): 1 no operand loads, 2 no MMAs
     // epilogue operands

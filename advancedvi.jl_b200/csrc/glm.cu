@@ -292,6 +292,7 @@ struct Glm : avi_model {
         if (M <= 0 || ensure(M, ld) != AVI_OK) return false;
         h->kind = 1; h->d = d; h->variant = variant; h->include_prior = include_prior;
         h->Zt = tc_mode() ? Zt : nullptr; h->pre = pre; h->zt_ld = zt_ld; h->zt_seg = x3 ? segd : 0;
+        h->tl = ctx->tl;
         if (l2_stream() & 1) { h->pf_ptr = Xr; h->pf_bytes = (unsigned long long)n_act * dK * sizeof(float); }
         hooked = true;
         return true;
@@ -350,6 +351,7 @@ struct Glm : avi_model {
         p.C = R; p.ldc = (int)ldR; p.y = y; p.w = w; p.likelihood = likelihood;
         p.r_seg = x3 ? (int)segn : 0;
         p.static_op = subsampled ? 0 : 2;   // B = X rows (a minibatch copy is rewritten every step: not static)
+        p.tl = ctx->tl; p.tl_id = 1;
         if ((l2_stream() & 6) && want_backward) {
             p.pf_ptr = Xc; p.pf_bytes = (unsigned long long)d * nP * sizeof(float);
             p.pf_pace_ns = (l2_stream() & 4) ? 600u : 0u;
@@ -367,6 +369,7 @@ struct Glm : avi_model {
     int32_t backward_setup(int M, TcParams* p, CUtensorMap* tmA, CUtensorMap* tmB) {
         AVI_CHECK(avi_tc_plan(ctx, d, M, kb(), true, cluster_mode, p));
         p->static_op = subsampled ? 0 : 1;   // A = X columns
+        p->tl = ctx->tl; p->tl_id = 2;
         AVI_CHECK(avi_tc_make_tmap(ctx, tmA, Xc, d, kb(), nP, 128 / p->cb));
         AVI_CHECK(avi_tc_make_tmap(ctx, tmB, R, M, kb(), ldR, p->pair ? p->nt / 2 : p->nt / p->ca));
         return AVI_OK;

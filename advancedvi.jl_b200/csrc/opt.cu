@@ -15,6 +15,7 @@
 #include "fr_finalize.cuh"
 #include "mf_finalize.cuh"
 #include "mf_tail.cuh"
+#include <chrono>
 
 namespace {
 
@@ -111,10 +112,21 @@ k_update(float* __restrict__ lam, const float* __restrict__ grad, float* __restr
     }
 }
 
+// diagnostic: file this iteration's stamps under (step - 1) % 64 (the tail has already advanced the counter)
+__global__ void k_tl_commit(const unsigned long long* tl, unsigned long long* hist, const ObjDeviceState* st) {
+    hist[((st->step + 63ull) % 64ull) * 32 + threadIdx.x] = tl[threadIdx.x];
+}
+
 template <int ITEMS>
 __global__ void __launch_bounds__(1024)
 k_mf_finalize_update(MfTailArgs t) {
-    mf_finalize_update_body<ITEMS>(t);
+    mf_finalize_update_body<ITEMS, false>(t);
+}
+// the same tail spread over one thread-block cluster of 8 CTAs (mf_tail.cuh)
+template <int ITEMS>
+__global__ void __cluster_dims__(TAIL_CLUSTER, 1, 1) __launch_bounds__(TAIL_CL_THREADS)
+k_mf_finalize_update_cl(MfTailArgs t) {
+    mf_finalize_update_body<ITEMS, true>(t);
 }
 
 // Full-rank: gradient of the scale block computed on the fly from the reduced sums (no D x D gradient pass of its
@@ -188,8 +200,15 @@ int32_t enqueue_iteration(avi_opt* op, bool subsampled, int64_t batch) {
     avi_obj* o = op->obj;
     avi_ctx* ctx = op->ctx;
     if (subsampled) AVI_CHECK(o->model->subsample_dev(op->idx_dev, batch, o->d_state));
+    if (ctx->tl) {   // diagnostic: reset the min slots (all ones) and max slots (zero) of this iteration's stamps
+        for (int half = 0; half < 2; ++half) {
+            AVI_CUDA(ctx, cudaMemsetAsync(ctx->tl + 16 * half, 0xFF, 8 * sizeof(unsigned long long), ctx->stream));
+            AVI_CUDA(ctx, cudaMemsetAsync(ctx->tl + 16 * half + 8, 0, 8 * sizeof(unsigned long long), ctx->stream));
+        }
+    }
     UpdArgs a = make_args(op);
     MfTailArgs tail{};
+    tail.tl = ctx->tl; tail.tl_s = 3;
     tail.acc = o->acc; tail.accv = o->accv; tail.M = o->M; tail.objective = o->objective; tail.entropy = o->entropy;
     tail.logp = o->logp; tail.esq = o->esq; tail.Mloc = o->Mloc; tail.deferred = avi_obj_defers_scalars(o) ? 1 : 0;
     tail.lam = op->lam; tail.grad = o->grad; tail.m1 = op->m1; tail.m2 = op->m2; tail.avg = op->avg; tail.sc = op->sc;
@@ -206,14 +225,22 @@ int32_t enqueue_iteration(avi_opt* op, bool subsampled, int64_t batch) {
     // (running this tail inside the last CTA of the target's final kernel was measured SLOWER than its own
     // launch: profiles/README.md)
     if (o->family == AVI_MEANFIELD && o->D <= 8 * 1024) {
-        const int items = (int)ceil_div(o->D, 1024);
-#define LAUNCH_TAIL(IT) avi_launch_pdl(ctx, k_mf_finalize_update<IT>, dim3(1), dim3(1024), 0, tail)
+        static const bool tail_cluster = !(getenv("AVI_TAIL_CLUSTER") && atoi(getenv("AVI_TAIL_CLUSTER")) == 0);
+        const int items = (int)ceil_div(o->D, tail_cluster ? TAIL_CLUSTER * TAIL_CL_THREADS : 1024);
+#define LAUNCH_TAIL(IT) (tail_cluster ? avi_launch_pdl(ctx, k_mf_finalize_update_cl<IT>, dim3(TAIL_CLUSTER), dim3(TAIL_CL_THREADS), 0, tail) \
+                                      : avi_launch_pdl(ctx, k_mf_finalize_update<IT>, dim3(1), dim3(1024), 0, tail))
         if (items <= 1) LAUNCH_TAIL(1);
         else if (items <= 2) LAUNCH_TAIL(2);
         else if (items <= 4) LAUNCH_TAIL(4);
         else LAUNCH_TAIL(8);
+        static const bool dbg_tail2 = getenv("AVI_DBG_TAIL2") && atoi(getenv("AVI_DBG_TAIL2")) != 0;
+        if (dbg_tail2 && ctx->tl) {   // timing experiment (results meaningless): the same kernel again, warm instruction cache
+            tail.tl = ctx->tl + 16; tail.tl_s = 3;   // second half of the stamp array
+            if (items <= 1) LAUNCH_TAIL(1); else if (items <= 2) LAUNCH_TAIL(2); else if (items <= 4) LAUNCH_TAIL(4); else LAUNCH_TAIL(8);
+        }
 #undef LAUNCH_TAIL
         AVI_LAUNCHED(ctx);
+        if (ctx->tl) k_tl_commit<<<1, 32, 0, ctx->stream>>>(ctx->tl, ctx->tl_hist, o->d_state);
         return AVI_OK;
     }
     const bool dog_rule = op->rule == AVI_RULE_DOG || op->rule == AVI_RULE_DOWG;
@@ -255,7 +282,9 @@ int32_t enqueue_iteration(avi_opt* op, bool subsampled, int64_t batch) {
 void drop_graph(avi_opt* op) {
     if (op->graph_exec) cudaGraphExecDestroy(op->graph_exec);
     if (op->graph) cudaGraphDestroy(op->graph);
-    op->graph_exec = nullptr; op->graph = nullptr;
+    if (op->graph_u_exec) cudaGraphExecDestroy(op->graph_u_exec);
+    if (op->graph_u) cudaGraphDestroy(op->graph_u);
+    op->graph_exec = nullptr; op->graph = nullptr; op->graph_u_exec = nullptr; op->graph_u = nullptr;
 }
 
 // One avi_opt_steps call = prepare (size the trace, upload minibatch indices, reset the per-call device counters,
@@ -302,19 +331,32 @@ int32_t steps_prepare(avi_opt* op, int32_t n, const int32_t* idx_host, int64_t b
             // lazily sized buffer exists.  It only writes scratch (no optimiser state, no step counter).
             if (subsampled) AVI_CHECK(o->model->subsample_dev(op->idx_dev, batch, o->d_state));
             AVI_CHECK(avi_objective_local(o, op->lam));
-            const int64_t launches0 = ctx->launches;
-            AVI_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-            ctx->capturing = true;
-            int32_t rc = enqueue_iteration(op, subsampled, batch);
-            ctx->capturing = false;
-            cudaGraph_t g = nullptr;
-            cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
-            op->graph_launches = ctx->launches - launches0;
-            ctx->launches = launches0;
-            if (rc != AVI_OK) { if (g) cudaGraphDestroy(g); return rc; }
-            if (e != cudaSuccess) AVI_FAIL(ctx, AVI_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
-            op->graph = g;
-            AVI_CUDA(ctx, cudaGraphInstantiate(&op->graph_exec, op->graph, 0));
+            auto capture = [&](int iters, cudaGraph_t* graph, cudaGraphExec_t* exec) -> int32_t {
+                const int64_t launches0 = ctx->launches;
+                AVI_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+                ctx->capturing = true;
+                int32_t rc = AVI_OK;
+                for (int it = 0; it < iters && rc == AVI_OK; ++it) rc = enqueue_iteration(op, subsampled, batch);
+                ctx->capturing = false;
+                cudaGraph_t g = nullptr;
+                cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+                op->graph_launches = (ctx->launches - launches0) / iters;
+                ctx->launches = launches0;
+                if (rc != AVI_OK) { if (g) cudaGraphDestroy(g); return rc; }
+                if (e != cudaSuccess) AVI_FAIL(ctx, AVI_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+                *graph = g;
+                AVI_CUDA(ctx, cudaGraphInstantiate(exec, g, 0));
+                return AVI_OK;
+            };
+            AVI_CHECK(capture(1, &op->graph, &op->graph_exec));
+            // several iterations per graph launch (AVI_GRAPH_UNROLL, default 8): inside one graph the tail -> sampling
+            // edge of consecutive iterations is a programmatic dependent launch too, which saves the ~2.5 us that a
+            // graph boundary costs (measured +6 % steps/s on C2).  Full-batch objectives only (a minibatch iteration
+            // reads its indices at a per-iteration offset that the device state already tracks, but keep the simple
+            // path there).
+            static const int unroll = getenv("AVI_GRAPH_UNROLL") ? std::max(1, atoi(getenv("AVI_GRAPH_UNROLL"))) : 8;
+            op->graph_unroll = subsampled ? 1 : unroll;
+            if (op->graph_unroll > 1) AVI_CHECK(capture(op->graph_unroll, &op->graph_u, &op->graph_u_exec));
             op->graph_gen = o->generation * 1000003 + o->model->generation;
             op->graph_subsampled = subsampled; op->graph_batch = batch;
         }
@@ -327,7 +369,10 @@ int32_t steps_launch(avi_opt* op, int32_t n) {
     avi_ctx* ctx = op->ctx;
     if (op->call_enqueued + n > op->call_cap) AVI_FAIL(ctx, AVI_ERR_INVALID, "more iterations enqueued than avi_opt_steps_begin reserved");
     if (op->use_graph) {
-        for (int32_t it = 0; it < n; ++it) AVI_CUDA(ctx, cudaGraphLaunch(op->graph_exec, ctx->stream));
+        int32_t left = n;
+        if (op->graph_u_exec)
+            for (; left >= op->graph_unroll; left -= op->graph_unroll) AVI_CUDA(ctx, cudaGraphLaunch(op->graph_u_exec, ctx->stream));
+        for (; left > 0; --left) AVI_CUDA(ctx, cudaGraphLaunch(op->graph_exec, ctx->stream));
         ctx->launches += (int64_t)n * op->graph_launches;
     } else {
         for (int32_t it = 0; it < n; ++it) AVI_CHECK(enqueue_iteration(op, op->call_subsampled, op->call_batch));
@@ -346,7 +391,7 @@ int32_t steps_finish(avi_opt* op, float* value_host, float* elbo_host, int32_t* 
     ObjDeviceState hs{};
     AVI_CUDA(ctx, cudaMemcpyAsync(op->h_trace, op->trace, 2 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     AVI_CUDA(ctx, cudaMemcpyAsync(&hs, o->d_state, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
-    AVI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    AVI_CUDA(ctx, avi_stream_wait(ctx));
     const int recorded = std::min(hs.trace_pos, n);
     const int done = hs.halted ? recorded - 1 : recorded;
     for (int i = 0; i < recorded; ++i) {
@@ -365,9 +410,19 @@ int32_t run_steps(avi_opt* op, int32_t n, const int32_t* idx_host, int64_t batch
     if (n <= 0) return AVI_OK;
     if (op->call_cap) AVI_FAIL(op->ctx, AVI_ERR_STATE, "avi_opt_steps_begin is open: call avi_opt_steps_end first");
     AVI_CHECK(steps_prepare(op, n, idx_host, batch));
+    static const bool dbg_launch = getenv("AVI_DEBUG_LAUNCH") && atoi(getenv("AVI_DEBUG_LAUNCH")) != 0;
+    const auto t0 = std::chrono::steady_clock::now();
     int32_t rc = steps_launch(op, n);
+    const auto t1 = std::chrono::steady_clock::now();
     if (rc != AVI_OK) { op->call_cap = 0; op->call_enqueued = 0; return rc; }
-    return steps_finish(op, value_host, elbo_host, n_done);
+    rc = steps_finish(op, value_host, elbo_host, n_done);
+    if (dbg_launch) {   // is the host's launch loop or the device the limit?
+        const auto t2 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[avi_opt_steps] n=%d: host launch loop %.1f us/iteration, launch + wait %.1f us/iteration\n", n,
+                std::chrono::duration<double, std::micro>(t1 - t0).count() / n,
+                std::chrono::duration<double, std::micro>(t2 - t0).count() / n);
+    }
+    return rc;
 }
 
 }  // namespace

@@ -74,6 +74,10 @@ int64_t avi_ctx_launch_count(const avi_ctx* ctx);
 /* Device timing of the named hot kernels ("sample", "glm_fwd", "glm_bwd", "gemm_store") with CUDA events
  * on the ctx stream, for roofline reporting.  While enabled, avi_opt_steps launches eagerly (no graph). */
 int32_t avi_ctx_timing(avi_ctx* ctx, int32_t enable);
+/* Diagnostic step timeline (AVI_TIMELINE=1 in the environment at avi_ctx_create): %globaltimer stamps (ns) of the
+ * last 64 fused iterations, hist[(step % 64) * 32 + slot]; slot id / 4 + id / 8 + id = first CTA entered / first CTA
+ * past its dependency wait / last CTA done, id 0 sample, 1 forward, 2 backward, 3 tail (slots 16.. : experiments).  hist_host: 2048 uint64. */
+int32_t avi_ctx_timeline_get(avi_ctx* ctx, uint64_t* hist_host);
 int32_t avi_ctx_timing_get(avi_ctx* ctx, const char* name, double* total_ms, int64_t* count);
 
 /* Multi-rank plumbing.  The exchange step of the path is ONE sum-all-reduce of the partial
