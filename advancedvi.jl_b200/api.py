@@ -35,7 +35,7 @@ __all__ = [
     "Descent", "Adam", "DoG", "DoWG", "IdentityOperator", "ClipScale", "ProximalLocationScaleEntropy",
     "NoAveraging", "PolynomialAveraging",
     "KLMinRepGradDescent", "KLMinRepGradProxDescent", "KLMinScoreGradDescent", "ADVI", "BBVI",
-    "optimize", "estimate_objective", "Objective", "AviError",
+    "optimize", "estimate_objective", "Objective", "AviError", "HostUpdate",
 ]
 
 AviError = L.AviError
@@ -537,10 +537,17 @@ class Objective:
     def set_shard_axis(self, axis: int):
         L.check(L.lib.avi_obj_set_shard_axis(self.h, axis), self.ctx.h)
 
-    def estimate_gradient(self, params):
-        """-> (value, gradient, elbo): value = -ELBO (RepGrad) or the VarGrad value (ScoreGrad)."""
+    def estimate_gradient(self, params, out=None):
+        """-> (value, gradient, elbo): value = -ELBO (RepGrad) or the VarGrad value (ScoreGrad).
+        `out`: caller-owned float32 gradient buffer of P entries, written in place like the DiffResults buffer of
+        estimate_gradient! (abstractobjective.jl:67-86)."""
         params = _f32(params, "params")
-        grad = np.empty(self.P, np.float32)
+        if out is None:
+            grad = np.empty(self.P, np.float32)
+        else:
+            grad = out
+            if grad.dtype != np.float32 or grad.size != self.P or not grad.flags.c_contiguous:
+                raise ValueError("out must be a contiguous float32 array of num_params entries")
         v, e = C.c_float(), C.c_float()
         L.check(L.lib.avi_obj_estimate_gradient(self.h, L.fptr(params), len(params), L.fptr(grad), C.byref(v),
                                                 C.byref(e)), self.ctx.h)
@@ -569,6 +576,33 @@ class Objective:
         if self.h:
             L.lib.avi_obj_destroy(self.h)
             self.h = None
+
+
+class HostUpdate:
+    """Host-side `Optimisers.update!` + operator + averager (src/algorithms/common.jl:91-94) for callers that stay on
+    the estimate_gradient! boundary with the parameters in host memory: Descent / Adam, ClipScale on the scale entries
+    of a mean-field lambda, PolynomialAveraging.  Compiled (avi_host_update in the library), no device work."""
+
+    def __init__(self, optimizer, operator, averager, lambda0, scale_offset: int):
+        if optimizer.code not in (L.RULE_DESCENT, L.RULE_ADAM):
+            raise ValueError("HostUpdate supports Descent and Adam")
+        self.rule, self.op, self.avg = optimizer, operator, averager
+        self.hyper = np.asarray(optimizer.hyper, np.float32)
+        self.lam = np.ascontiguousarray(lambda0, np.float32).copy()
+        self.m1, self.m2 = np.zeros_like(self.lam), np.zeros_like(self.lam)
+        self.lam_avg = self.lam.copy()
+        self.state = np.zeros(16, np.float32)
+        self.scale_offset = int(scale_offset)
+
+    def update(self, grad):
+        g = np.ascontiguousarray(grad, np.float32)
+        rc = L.lib.avi_host_update(self.rule.code, L.fptr(self.hyper), len(self.hyper), self.op.code,
+                                   getattr(self.op, "param", 0.0), self.avg.code, getattr(self.avg, "param", 0.0),
+                                   self.lam.size, self.scale_offset, L.fptr(self.lam), L.fptr(g), L.fptr(self.m1),
+                                   L.fptr(self.m2), L.fptr(self.lam_avg), L.fptr(self.state))
+        if rc != 0:
+            raise AviError(rc, "avi_host_update: unsupported rule / operator or missing state arrays")
+        return self.lam
 
 
 class _OptState:

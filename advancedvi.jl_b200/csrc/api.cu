@@ -2,6 +2,7 @@
 // The fused step lives in opt.cu.
 #include <cmath>
 #include <cstdlib>
+#include <atomic>
 #include <cstring>
 #include <mutex>
 
@@ -331,12 +332,13 @@ int32_t avi_obj_create(avi_ctx* ctx, avi_model* model, int32_t family, int32_t o
     int32_t rc = avi_alloc(ctx, &o->d_state, 1);
     if (rc == AVI_OK) rc = avi_alloc(ctx, &o->d_lambda, (size_t)o->P);
     if (rc == AVI_OK) rc = avi_alloc(ctx, &o->acc, (size_t)o->acc_len);
-    if (rc == AVI_OK) rc = avi_alloc(ctx, &o->grad, (size_t)o->P);
+    if (rc == AVI_OK) rc = avi_alloc(ctx, &o->grad, (size_t)o->P + 4);   // + {value, elbo, logdet, shift} (estimate_gradient!)
     if (rc == AVI_OK) rc = avi_alloc(ctx, &o->out, 4);
     if (rc == AVI_OK) rc = avi_obj_ensure_capacity(o, M);
     if (rc == AVI_OK) {
         cudaError_t e = cudaMallocHost(&o->h_lambda, (size_t)o->P * sizeof(float));
-        if (e == cudaSuccess) e = cudaMallocHost(&o->h_grad, ((size_t)o->P + 4) * sizeof(float));
+        if (e == cudaSuccess) e = cudaMallocHost(&o->h_grad, ((size_t)o->P + 8) * sizeof(float));
+        if (e == cudaSuccess) std::memset(o->h_grad, 0, ((size_t)o->P + 8) * sizeof(float));
         if (e != cudaSuccess) { avi_set_error(ctx, std::string("pinned allocation: ") + cudaGetErrorString(e)); rc = AVI_ERR_CUDA; }
     }
     if (rc == AVI_OK) rc = obj_push_state(o);
@@ -411,7 +413,19 @@ int32_t avi_obj_estimate_gradient(avi_obj* o, const float* lambda_host, int64_t 
     AVI_CHECK(check_lambda(o, lambda_host, P));
     cudaSetDevice(ctx->device);
     std::memcpy(o->h_lambda, lambda_host, (size_t)P * sizeof(float));
+    // Mean-field: no copy-engine node in the chain.  lambda is staged in by a kernel reading the pinned buffer, and the
+    // finalize kernel writes gradient + scalars + a completion flag (the new step counter) straight into pinned host
+    // memory; the host spins on that flag.  (AVI_ZERO_COPY=0: copy nodes + stream wait, as for the full-rank family.)
+    static const bool zc_env = !(getenv("AVI_ZERO_COPY") && atoi(getenv("AVI_ZERO_COPY")) == 0);
+    const bool zero_copy = zc_env && o->family == AVI_MEANFIELD && P <= (1 << 16);
     auto enqueue = [&]() -> int32_t {
+        if (zero_copy) {
+            AVI_CHECK(avi_obj_stage_lambda(o));
+            AVI_CHECK(avi_objective_local(o, o->d_lambda));
+            AVI_CHECK(avi_objective_finalize(o, o->d_lambda, o->grad, o->out, false, /*fuse_advance=*/true));
+            o->step += 1;
+            return AVI_OK;
+        }
         AVI_CUDA(ctx, cudaMemcpyAsync(o->d_lambda, o->h_lambda, (size_t)P * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
         AVI_CHECK(avi_objective_local(o, o->d_lambda));
         AVI_CHECK(avi_objective_finalize(o, o->d_lambda, o->grad, o->out));
@@ -430,6 +444,8 @@ int32_t avi_obj_estimate_gradient(avi_obj* o, const float* lambda_host, int64_t 
         cudaGraphExecDestroy(o->eg_exec); cudaGraphDestroy(o->eg_graph);
         o->eg_exec = nullptr; o->eg_graph = nullptr; o->eg_calls = 0;
     }
+    if (zero_copy)   // arm the completion flag: anything but the value this call will publish (o->step + 1)
+        *reinterpret_cast<volatile unsigned int*>(o->h_grad + P + 4) = ~(unsigned int)(o->step + 1);
     if (capturable && o->eg_exec) {
         AVI_CUDA(ctx, cudaGraphLaunch(o->eg_exec, ctx->stream));
         ctx->launches += o->eg_launches;
@@ -459,7 +475,26 @@ int32_t avi_obj_estimate_gradient(avi_obj* o, const float* lambda_host, int64_t 
         o->eg_calls++;
         o->eg_gen = o->generation * 1000003 + o->model->generation;
     }
-    AVI_CUDA(ctx, avi_stream_wait(ctx));
+    if (zero_copy) {
+        // completion flag = low 32 bits of the device step counter after this call (== the host mirror o->step)
+        volatile unsigned int* flag = reinterpret_cast<volatile unsigned int*>(o->h_grad + P + 4);
+        const unsigned int want = (unsigned int)o->step;
+        for (unsigned long long spins = 0; *flag != want; ++spins) {
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+            if ((spins & 0xFFFFull) == 0xFFFFull) {   // every ~64k polls: has the stream failed or finished without the flag?
+                cudaError_t qe = cudaStreamQuery(ctx->stream);
+                if (qe != cudaErrorNotReady) {
+                    AVI_CUDA(ctx, qe);
+                    if (*flag != want) AVI_FAIL(ctx, AVI_ERR_STATE, "estimate_gradient: stream finished without the completion flag");
+                }
+            }
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+    } else {
+        AVI_CUDA(ctx, avi_stream_wait(ctx));
+    }
     if (grad_host) std::memcpy(grad_host, o->h_grad, (size_t)P * sizeof(float));
     if (value) *value = o->h_grad[P];
     if (elbo) *elbo = o->h_grad[P + 1];

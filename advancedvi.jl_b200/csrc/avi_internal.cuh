@@ -225,7 +225,7 @@ struct avi_obj {
     FrWork fr;
     // pinned host staging
     float* h_lambda = nullptr;   // P
-    float* h_grad = nullptr;     // P + 4
+    float* h_grad = nullptr;     // P + 8: gradient | value, elbo, logdet, shift | completion flag (u32)
     // captured estimate_gradient! (H2D lambda -> kernels -> D2H gradient): one graph launch per call
     cudaGraph_t eg_graph = nullptr;
     cudaGraphExec_t eg_exec = nullptr;
@@ -277,9 +277,11 @@ int32_t avi_obj_ensure_capacity(avi_obj* o, int M);
 // (or in *ov when ov != nullptr, a host value).  E, esq always written.
 int32_t avi_family_sample(avi_obj* o, const float* lambda, float* Z, float* E, float* esq, int Mloc,
                           int m0, const ObjDeviceState* st, const ObjDeviceState* ov, const SampleHook* hook = nullptr);
+int32_t avi_obj_stage_lambda(avi_obj* o);   // o->h_lambda (pinned, mapped) -> o->d_lambda by a kernel
 int32_t avi_objective_local(avi_obj* o, const float* lambda);          // sample + model + reduce -> acc
 // acc -> grad (skip_fr_matrix: leave the D x D block of a full-rank gradient to the caller's fused update)
-int32_t avi_objective_finalize(avi_obj* o, const float* lambda, float* grad, float* out, bool skip_fr_matrix = false);
+int32_t avi_objective_finalize(avi_obj* o, const float* lambda, float* grad, float* out, bool skip_fr_matrix = false,
+                               bool fuse_advance = false);
 // forward-only chunk for estimate_objective: sums_dev = {sum logp, sum |eps|^2, logdet}
 int32_t avi_objective_forward_chunk(avi_obj* o, const float* lambda, int m0, int Mc, const ObjDeviceState* ov,
                                     float* sums_dev);

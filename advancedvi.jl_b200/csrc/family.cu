@@ -218,22 +218,47 @@ k_reduce_mf(const float* __restrict__ G, const float* __restrict__ E, const floa
 // finalize, mean-field: global sums -> gradient of the value slot, value, elbo.
 // Gradient entries are independent; the scalars are recomputed by every CTA in the same fixed
 // order (CTA 0 writes them), so the grid size does not change any result.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 k_finalize_mf(const float* __restrict__ acc, int accv, const float* __restrict__ lambda, int D, int M,
               int objective, int entropy, const float* __restrict__ logp, const float* __restrict__ esq, int Mloc,
-              int deferred, float* __restrict__ grad, float* __restrict__ out) {
+              int deferred, float* __restrict__ grad, float* __restrict__ out, float* __restrict__ host_out,
+              ObjDeviceState* __restrict__ advance_st) {
     __shared__ float sm[33];
+    pdl_trigger();
+    pdl_wait();
     const float* s = lambda + D;
     const MfSums S = mf_collect_sums(lambda, D, acc + 4 * (size_t)accv, logp, esq, Mloc, deferred, sm);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < D; i += gridDim.x * blockDim.x) {
         float gm, gs;
         mf_grad_entry(acc, accv, __ldg(s + i), i, M, objective, entropy, S, gm, gs);
         grad[i] = gm; grad[D + i] = gs;
+        if (host_out) { host_out[i] = gm; host_out[D + i] = gs; }   // posted writes into mapped pinned host memory
+    }
+    if (host_out) {
+        // estimate_gradient! boundary (launched as ONE CTA): the gradient went straight to the caller-visible pinned
+        // buffer [grad (2 D) | value, elbo, logdet, shift | done flag]; once every thread's stores are fenced, thread 0
+        // adds the scalars, advances the step counter and release-stores the new counter value as the completion flag
+        // the host spins on -- no device-to-host copy node, no stream query round trip
+        __threadfence_system();
+        __syncthreads();
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         float value, elbo, shift_next;
         mf_outputs(D, M, objective, entropy, S, out[3], value, elbo, shift_next);
         out[0] = value; out[1] = elbo; out[2] = S.logdet; out[3] = shift_next;
+        // estimate_gradient! boundary: the scalars also go right behind the gradient (one device-to-host copy) and
+        // the step counter advances here instead of in a launch of its own
+        if (advance_st) {
+            const unsigned long long step_next = advance_st->step + 1ull;
+            advance_st->step = step_next;
+            if (host_out) {
+                float* tail = host_out + 2 * (size_t)D;
+                tail[0] = value; tail[1] = elbo; tail[2] = S.logdet; tail[3] = shift_next;
+                __threadfence_system();
+                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(reinterpret_cast<unsigned int*>(tail + 4)),
+                             "r"((unsigned int)step_next) : "memory");
+            }
+        }
     }
 }
 
@@ -315,6 +340,15 @@ k_finalize_fr_vec(const float* __restrict__ acc, int accv, const float* __restri
 
 __global__ void k_advance(ObjDeviceState* st) { st->step += 1ull; }
 
+// estimate_gradient! boundary: lambda from the caller's pinned (mapped) host buffer into device memory by a kernel
+// (a few KB: one PCIe read round trip) instead of a copy-engine node in front of the compute chain
+__global__ void __launch_bounds__(256)
+k_stage_in(const float* __restrict__ host_src, float* __restrict__ dst, long long n) {
+    pdl_trigger();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = host_src[i];
+}
+
 // forward-only chunk sums for estimate_objective: out = {sum logp, sum |eps|^2, logdet}
 __global__ void __launch_bounds__(1024)
 k_forward_sums(const float* __restrict__ lambda, int D, int fullrank, const float* __restrict__ logp,
@@ -381,6 +415,15 @@ int32_t avi_family_sample(avi_obj* o, const float* lambda, float* Z, float* E, f
 bool avi_obj_defers_scalars(const avi_obj* o) {
     return o->family == AVI_MEANFIELD && o->objective == AVI_REPGRAD && o->Mloc > 0 &&
            !(o->shard_axis == AVI_SHARD_SAMPLES && o->ctx->nranks > 1);
+}
+
+int32_t avi_obj_stage_lambda(avi_obj* o) {
+    avi_ctx* ctx = o->ctx;
+    cudaError_t e = avi_launch_pdl(ctx, k_stage_in, dim3((unsigned)ceil_div(o->P, 256)), dim3(256), 0, (const float*)o->h_lambda,
+                                   o->d_lambda, (long long)o->P);
+    if (e != cudaSuccess) AVI_FAIL(ctx, AVI_ERR_CUDA, std::string("stage-in launch: ") + cudaGetErrorString(e));
+    AVI_LAUNCHED(ctx);
+    return AVI_OK;
 }
 
 int32_t avi_obj_advance(avi_obj* o) {
@@ -474,13 +517,21 @@ int32_t avi_objective_forward_chunk(avi_obj* o, const float* lambda, int m0, int
     return AVI_OK;
 }
 
-int32_t avi_objective_finalize(avi_obj* o, const float* lambda, float* grad, float* out, bool skip_fr_matrix) {
+int32_t avi_objective_finalize(avi_obj* o, const float* lambda, float* grad, float* out, bool skip_fr_matrix,
+                               bool fuse_advance) {
     avi_ctx* ctx = o->ctx;
     const int D = o->D, accv = o->accv;
     if (o->family == AVI_MEANFIELD) {
         unsigned nb = (unsigned)std::min<int64_t>(ceil_div(D, 256), 64);
-        k_finalize_mf<<<nb, 256, 0, ctx->stream>>>(o->acc, accv, lambda, D, o->M, o->objective, o->entropy, o->logp,
-                                                   o->esq, o->Mloc, avi_obj_defers_scalars(o) ? 1 : 0, grad, out);
+        // fuse_advance (estimate_gradient!): one CTA; gradient, scalars and completion flag written straight into the
+        // pinned host buffer o->h_grad, step counter advanced by this kernel
+        cudaError_t e = avi_launch_pdl(ctx, k_finalize_mf, dim3(fuse_advance ? 1u : nb), dim3(fuse_advance ? 1024u : 256u), 0,
+                                       (const float*)o->acc, accv, lambda, D, o->M,
+                                       o->objective, o->entropy, (const float*)o->logp, (const float*)o->esq, o->Mloc,
+                                       avi_obj_defers_scalars(o) ? 1 : 0, grad, out,
+                                       fuse_advance ? o->h_grad : (float*)nullptr,
+                                       fuse_advance ? o->d_state : (ObjDeviceState*)nullptr);
+        if (e != cudaSuccess) AVI_FAIL(ctx, AVI_ERR_CUDA, std::string("finalize launch: ") + cudaGetErrorString(e));
         AVI_LAUNCHED(ctx);
     } else {
         const float* scal = o->acc + 4 * (size_t)accv;

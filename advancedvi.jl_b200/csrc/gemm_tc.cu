@@ -758,7 +758,8 @@ int32_t avi_tc_plan(avi_ctx* ctx, int64_t Ma, int64_t Nb, int64_t K, bool split_
     }
     // CTA pairs (cta_group::2): two a-blocks per unit, half of the b-chunk per SM
     p->pair = 0;
-    const int pair_env = env_int("AVI_TC_PAIR", 0);
+    // AVI_TC_PAIR: 0 never, 1 (default) when the cost model prefers it (large problems: C4 +17 %), 2 always
+    const int pair_env = env_int("AVI_TC_PAIR", 1);
     if (pair_env && p->n_ablk >= 2) {
         const int maxp = max_active_clusters(ctx, 2);
         const int n_ag = (p->n_ablk + 1) / 2;

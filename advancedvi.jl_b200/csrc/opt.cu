@@ -516,6 +516,40 @@ int32_t avi_opt_steps_subsampled(avi_opt* op, int32_t n, const int32_t* idx_host
     return run_steps(op, n, idx_host, batch, value_host, elbo_host, n_done);
 }
 
+int32_t avi_host_update(int32_t rule, const float* hyper, int32_t n_hyper, int32_t op_kind, float op_param,
+                        int32_t averager, float avg_param, int64_t P, int64_t scale_offset, float* lambda,
+                        const float* grad, float* m1, float* m2, float* lambda_avg, float* st) {
+    if (!lambda || !grad || !st || P <= 0) return AVI_ERR_INVALID;
+    if (rule != AVI_RULE_DESCENT && rule != AVI_RULE_ADAM) return AVI_ERR_UNSUPPORTED;
+    if (op_kind != AVI_OP_IDENTITY && op_kind != AVI_OP_CLIPSCALE) return AVI_ERR_UNSUPPORTED;
+    if (rule == AVI_RULE_ADAM && (!m1 || !m2)) return AVI_ERR_INVALID;
+    if (averager == AVI_AVG_POLYNOMIAL && !lambda_avg) return AVI_ERR_INVALID;
+    const float dflt[2][4] = {{0.1f, 0, 0, 0}, {1e-3f, 0.9f, 0.999f, 1e-8f}};
+    float h[4];
+    for (int i = 0; i < 4; ++i) h[i] = (hyper && i < n_hyper) ? hyper[i] : dflt[rule][i];
+    if (st[SC_T] == 0.0f) { st[SC_T] = 1.0f; st[SC_B1T] = h[1]; st[SC_B2T] = h[2]; }   // first call (averaging.jl:42)
+    const float b1t = st[SC_B1T], b2t = st[SC_B2T];
+    const float w = (avg_param + 1.0f) / (st[SC_T] + avg_param);
+    for (int64_t p = 0; p < P; ++p) {
+        float dx;
+        if (rule == AVI_RULE_ADAM) {
+            const float mt = h[1] * m1[p] + (1.0f - h[1]) * grad[p];
+            const float vt = h[2] * m2[p] + (1.0f - h[2]) * grad[p] * grad[p];
+            m1[p] = mt; m2[p] = vt;
+            dx = mt / (1.0f - b1t) / (std::sqrt(vt / (1.0f - b2t)) + h[3]) * h[0];
+        } else {
+            dx = h[0] * grad[p];
+        }
+        float x = lambda[p] - dx;
+        if (op_kind == AVI_OP_CLIPSCALE && scale_offset >= 0 && p >= scale_offset) x = std::max(x, op_param);
+        lambda[p] = x;
+        if (averager == AVI_AVG_POLYNOMIAL) lambda_avg[p] = (1.0f - w) * lambda_avg[p] + w * x;
+    }
+    st[SC_T] += 1.0f;
+    if (rule == AVI_RULE_ADAM) { st[SC_B1T] = b1t * h[1]; st[SC_B2T] = b2t * h[2]; }
+    return AVI_OK;
+}
+
 int32_t avi_opt_get(avi_opt* op, float* lambda_host, float* lambda_avg_host, float* grad_host) {
     if (!op) return AVI_ERR_INVALID;
     avi_ctx* ctx = op->ctx;

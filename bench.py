@@ -244,10 +244,11 @@ def main():
         cold_ms, warm_ms = t.tolist()
     final_elbo = float(elbos[K - 1])
 
-    # ---- end-to-end through the reference-facing call: estimate_gradient! with HOST buffers + host Adam ----
-    lam = q0.destructure().copy()
-    m1, m2, lam_avg = np.zeros_like(lam), np.zeros_like(lam), lam.copy()
-    b1, b2, eta, eps_adam, b1t, b2t, t_avg = 0.9, 0.999, 1e-3, 1e-8, 0.9, 0.999, 1.0
+    # ---- end-to-end through the reference-facing call: estimate_gradient! with HOST buffers, then the host-side
+    # Optimisers.update! + ClipScale + PolynomialAveraging of `step` (common.jl:91-94) as compiled host code
+    # (avi_host_update; a numpy version of the same update costs ~45 us per step and would dominate) ----
+    host = avi.HostUpdate(alg.optimizer, alg.operator, alg.averager, q0.destructure(), scale_offset=D)
+    gbuf = np.empty(P, np.float32)
     obj.seed(SEED, 0)
     e2e_s = 0.0
     for k in range(W + K):
@@ -255,16 +256,8 @@ def main():
             flush.zero_()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        v, g, e = obj.estimate_gradient(lam)                # H2D lambda, kernels, D2H gradient + value
-        m1 = b1 * m1 + (1 - b1) * g
-        m2 = b2 * m2 + (1 - b2) * g * g
-        lam = lam - m1 / (1 - b1t) / (np.sqrt(m2 / (1 - b2t)) + eps_adam) * eta
-        b1t *= b1; b2t *= b2
-        lam[D:] = np.maximum(lam[D:], 1e-5)
-        w = 9.0 / (t_avg + 8.0)
-        lam_avg = (1 - w) * lam_avg + w * lam
-        t_avg += 1.0
-        lam = lam.astype(np.float32)
+        v, g, e = obj.estimate_gradient(host.lam, out=gbuf)  # H2D lambda, kernels, D2H gradient + value
+        host.update(g)
         dt = time.perf_counter() - t0
         if k >= W:
             e2e_s += dt
@@ -353,7 +346,7 @@ def main():
         "value_l2_resident": K / (warm_ms * 1e-3), "ms_per_step_l2_resident": warm_ms / K,
         "e2e": {"value": K / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": 4 * P, "d2h_bytes_per_step": 4 * (P + 4),
                 "path": "avi_obj_estimate_gradient (estimate_gradient! boundary, host lambda in / host gradient out) "
-                        "+ host Adam/ClipScale/averaging, L2 flushed between steps"},
+                        "+ host Adam/ClipScale/averaging (avi_host_update), L2 flushed between steps"},
         "gpu_launches": int(launches), "final_elbo": final_elbo,
         "clocks": sampler.summary(), "roofline": roofline,
     }

@@ -199,6 +199,15 @@ int32_t avi_opt_steps_end(avi_opt* opt, float* value_host, float* elbo_host, int
  * indices (SubsampledObjective, src/algorithms/subsampledobjective.jl:64-90) */
 int32_t avi_opt_steps_subsampled(avi_opt* opt, int32_t n, const int32_t* idx_host, int64_t batch,
                                  float* value_host, float* elbo_host, int32_t* n_done);
+/* Host-side counterpart of the fused update, for callers that stay on the estimate_gradient! boundary and keep the
+ * parameters on the host (what Optimisers.update! + the operator + the averager do in `step`, common.jl:91-94, on
+ * Julia arrays): Descent / Adam on a mean-field lambda = [mu (D); diag scale (D)] of P = 2 D entries (or any flat
+ * vector with scale_offset = -1: no operator), ClipScale on the scale entries, PolynomialAveraging.  state16 holds the
+ * scalar state between calls (zero-initialise it; entries: 0 t of the averager, 3 beta1^t, 4 beta2^t).  m1 / m2 /
+ * lambda_avg may be NULL when the rule / averager does not use them.  No device work. */
+int32_t avi_host_update(int32_t rule, const float* hyper, int32_t n_hyper, int32_t op, float op_param, int32_t averager,
+                        float avg_param, int64_t P, int64_t scale_offset, float* lambda, const float* grad, float* m1,
+                        float* m2, float* lambda_avg, float* state16);
 /* current iterate, averaged iterate (output(), common.jl:63-67) and last gradient */
 int32_t avi_opt_get(avi_opt* opt, float* lambda_host, float* lambda_avg_host, float* grad_host);
 int64_t avi_opt_iteration(const avi_opt* opt);

@@ -97,3 +97,28 @@ def test_algorithm_constructors(avi):
     s = avi.KLMinScoreGradDescent(n_samples=7, subsampling=avi.ReshufflingBatchSubsampling(np.arange(10), 2))
     assert isinstance(s.objective, avi.SubsampledObjective) and s.objective.n_samples == 7
     assert avi.ADVI is avi.KLMinRepGradDescent and avi.BBVI is avi.KLMinScoreGradDescent
+
+
+def test_host_update_matches_oracle_adam_clip_polyavg():
+    """avi_host_update (host-side Optimisers.update! + ClipScale + PolynomialAveraging, no device work) against the
+    oracle's restatement of src/algorithms/common.jl:91-94 over 50 steps in fp32."""
+    import numpy as np
+    import advancedvi_jl_b200 as avi
+    from oracle import optim as Oo
+    D = 37
+    rng = np.random.default_rng(0)
+    lam0 = np.concatenate([rng.normal(size=D), np.abs(rng.normal(size=D)) + 0.1]).astype(np.float32)
+    for rule_a, rule_o in ((avi.Adam(1e-2), Oo.Adam(1e-2)), (avi.Descent(0.05), Oo.Descent(0.05))):
+        hu = avi.HostUpdate(rule_a, avi.ClipScale(0.3), avi.PolynomialAveraging(8), lam0, scale_offset=D)
+        x = lam0.copy(); st = rule_o.init(x); avg_o = Oo.PolynomialAveraging(8); ast = avg_o.init(x)
+        clip = Oo.ClipScale(0.3)
+        for t in range(50):
+            g = rng.normal(size=2 * D).astype(np.float32)
+            hu.update(g)
+            st, dx = rule_o.apply(st, x, g)
+            x = (x - dx).astype(np.float32)
+            x[D:] = np.maximum(x[D:], np.float32(0.3))        # clip_scale.jl:18-29 on a mean-field lambda
+            ast = avg_o.apply(ast, x)
+        assert np.allclose(hu.lam, x, rtol=2e-6, atol=1e-7)
+        assert np.allclose(hu.lam_avg, avg_o.value(ast), rtol=1e-5, atol=1e-6)
+        assert (hu.lam[D:] >= 0.3).all()

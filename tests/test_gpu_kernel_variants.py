@@ -1,5 +1,5 @@
-"""The optional code paths of the tcgen05 kernel -- cluster TMA multicast, CTA pairs (cta_group::2), no PDL,
-no CUDA graph -- are selected by environment variables read when the library is first used, so each variant
+"""The optional code paths -- cluster TMA multicast, CTA pairs (cta_group::2), no PDL, no CUDA graph, and the
+single-CTA tail / one-iteration graphs / copy-node boundary that the defaults replaced -- are selected by environment variables read when the library is first used, so each variant
 runs a subset of the parity tests in its own process."""
 import os
 import subprocess
@@ -17,8 +17,11 @@ SUBSET = ["tests/test_gpu_parity.py::test_glm_logdensity_and_gradient",
           "tests/test_gpu_parity.py::test_c2_full_size_properties"]
 
 
-@pytest.mark.parametrize("env", [{"AVI_TC_CLUSTER": "2"}, {"AVI_TC_PAIR": "2"}, {"AVI_PDL": "0"}, {"AVI_NO_GRAPH": "1"}],
-                         ids=["cluster_multicast", "cta_pair", "no_pdl", "no_graph"])
+LEGACY = {"AVI_TAIL_CLUSTER": "0", "AVI_GRAPH_UNROLL": "1", "AVI_ZERO_COPY": "0", "AVI_SPIN_SYNC": "0", "AVI_TC_PAIR": "0"}
+
+
+@pytest.mark.parametrize("env", [{"AVI_TC_CLUSTER": "2"}, {"AVI_TC_PAIR": "2"}, {"AVI_PDL": "0"}, {"AVI_NO_GRAPH": "1"}, LEGACY],
+                         ids=["cluster_multicast", "cta_pair", "no_pdl", "no_graph", "single_cta_tail_copy_nodes"])
 def test_variant(env):
     e = dict(os.environ)
     e.update(env)
