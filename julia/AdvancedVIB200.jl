@@ -158,5 +158,68 @@ function estimate_objective_b200(rng, st::B200ObjState, params::Vector{Float32},
     return r[]
 end
 
+# ---- optional fast path: the whole `step` on the device (src/algorithms/common.jl:40-120) ------------------
+# `init`/`step`/`output` methods for the three ParamSpaceSGD algorithm types when their adtype is AutoB200 and the
+# objective is not subsampled: parameters, optimiser state and the averaged iterate stay on the GPU (avi_opt_*),
+# one call runs `chunk` iterations without the callback; with a callback `chunk = 1` reproduces the reference loop.
+const B200Alg = Union{KLMinRepGradDescent{<:Union{RepGradELBO},AutoB200},
+                      KLMinRepGradProxDescent{<:Any,AutoB200},
+                      KLMinScoreGradDescent{<:Union{ScoreGradELBO},AutoB200}}
+rule_code(o::Optimisers.Descent) = (0, Float32[o.eta])
+rule_code(o::Optimisers.Adam) = (1, Float32[o.eta, o.beta[1], o.beta[2], o.epsilon])
+rule_code(o::AdvancedVI.DoG) = (2, Float32[o.alpha])
+rule_code(o::AdvancedVI.DoWG) = (3, Float32[o.alpha])
+op_code(::AdvancedVI.IdentityOperator) = (0, 0.0f0)
+op_code(o::AdvancedVI.ClipScale) = (1, Float32(o.epsilon))
+op_code(::AdvancedVI.ProximalLocationScaleEntropy) = (2, 0.0f0)
+avg_code(::AdvancedVI.NoAveraging) = (0, 0.0f0)
+avg_code(a::AdvancedVI.PolynomialAveraging) = (1, Float32(a.eta))
+
+mutable struct B200OptState
+    h::Ptr{Cvoid}
+    obj_st::B200ObjState
+end
+
+function AdvancedVI.init(rng::Random.AbstractRNG, alg::B200Alg, q_init, prob)
+    params, re = Optimisers.destructure(q_init)
+    obj_st = AdvancedVI.init(rng, alg.objective, alg.adtype, q_init, prob, params, re)
+    (rule, hyper), (op, op_param), (avg, avg_param) = rule_code(alg.optimizer), op_code(alg.operator), avg_code(alg.averager)
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    check(@ccall(libavi.avi_opt_create(obj_st.h::Ptr{Cvoid}, rule::Int32, hyper::Ptr{Float32}, length(hyper)::Int32,
+                 op::Int32, op_param::Float32, avg::Int32, avg_param::Float32, params::Ptr{Float32},
+                 length(params)::Int64, r::Ptr{Ptr{Cvoid}})::Int32), obj_st.prob.c.h)
+    st = B200OptState(r[], obj_st)
+    finalizer(s -> @ccall(libavi.avi_opt_destroy(s.h::Ptr{Cvoid})::Int32), st)
+    return (prob=prob, q=q_init, iteration=0, opt=st, re=re)
+end
+
+function AdvancedVI.step(rng::Random.AbstractRNG, alg::B200Alg, state, callback, objargs...; kwargs...)
+    v, e, nd = Ref{Float32}(0), Ref{Float32}(0), Ref{Int32}(0)
+    c = state.opt.obj_st.prob.c.h
+    check(@ccall(libavi.avi_opt_steps(state.opt.h::Ptr{Cvoid}, 1::Int32, v::Ptr{Float32}, e::Ptr{Float32},
+                 nd::Ptr{Int32})::Int32), c)
+    nd[] == 1 || throw(ErrorException("The objective value is $(v[]). This indicates that the optimization run diverged."))  # common.jl:83-89
+    info = (elbo=e[],)
+    state = merge(state, (iteration=state.iteration + 1,))
+    if !isnothing(callback)
+        P = length(first(Optimisers.destructure(state.q)))
+        lam, lam_avg, grad = (Vector{Float32}(undef, P) for _ in 1:3)
+        check(@ccall(libavi.avi_opt_get(state.opt.h::Ptr{Cvoid}, lam::Ptr{Float32}, lam_avg::Ptr{Float32},
+                     grad::Ptr{Float32})::Int32), c)
+        info′ = callback(; rng, iteration=state.iteration, restructure=state.re, params=lam, averaged_params=lam_avg,
+                         gradient=grad, state=state)
+        info = !isnothing(info′) ? merge(info′, info) : info
+    end
+    return state, false, info
+end
+
+function AdvancedVI.output(alg::B200Alg, state)   # common.jl:63-67: re(value(averager, avg_st))
+    P = length(first(Optimisers.destructure(state.q)))
+    lam_avg = Vector{Float32}(undef, P)
+    check(@ccall(libavi.avi_opt_get(state.opt.h::Ptr{Cvoid}, C_NULL::Ptr{Float32}, lam_avg::Ptr{Float32},
+                 C_NULL::Ptr{Float32})::Int32), state.opt.obj_st.prob.c.h)
+    return state.re(lam_avg)
+end
+
 export AutoB200, LogReg, NativeProblem
 end # module
