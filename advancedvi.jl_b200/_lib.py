@@ -86,6 +86,7 @@ SIGNATURES = {
                                    C.c_float, c_float_p, C.c_int64, C.POINTER(vp)]),
     "avi_opt_steps": (C.c_int32, [vp, C.c_int32, c_float_p, c_float_p, c_i32_p]),
     "avi_ctx_timeline_get": (C.c_int32, [vp, C.POINTER(C.c_uint64)]),
+    "avi_obj_gauss_expected_grad_hess": (C.c_int32, [vp, c_float_p, C.c_int64, C.c_int32, c_float_p, c_float_p, c_float_p]),
     "avi_host_update": (C.c_int32, [C.c_int32, c_float_p, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_float, C.c_int64,
                                     C.c_int64, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p]),
     "avi_opt_steps_begin": (C.c_int32, [vp, C.c_int32]),

@@ -36,6 +36,7 @@ __all__ = [
     "NoAveraging", "PolynomialAveraging",
     "KLMinRepGradDescent", "KLMinRepGradProxDescent", "KLMinScoreGradDescent", "ADVI", "BBVI",
     "optimize", "estimate_objective", "Objective", "AviError", "HostUpdate",
+    "gaussian_expectation_gradient_and_hessian",
 ]
 
 AviError = L.AviError
@@ -572,10 +573,34 @@ class Objective:
         L.check(L.lib.avi_obj_rand(self.h, L.fptr(params), len(params), L.fptr(Z), L.fptr(E)), self.ctx.h)
         return np.ascontiguousarray(Z.T), np.ascontiguousarray(E.T)
 
+    def gaussian_expectation_gradient_and_hessian(self, q: MvLocationScale, n_samples: int):
+        """gaussian_expectation_gradient_and_hessian!(rng, q, n_samples, grad_buf, hess_buf, prob), first-order (Stein)
+        branch of src/algorithms/gauss_expected_grad_hess.jl:20-58 -> (logpi_avg, grad (D), hess (D, D)); the draws
+        are the objective's Philox stream at its current step (which then advances)."""
+        params = q.destructure()
+        D = len(q)
+        grad, hess, lp = np.empty(D, np.float32), np.empty(D * D, np.float32), C.c_float()
+        L.check(L.lib.avi_obj_gauss_expected_grad_hess(self.h, L.fptr(params), len(params), int(n_samples), C.byref(lp),
+                                                       L.fptr(grad), L.fptr(hess)), self.ctx.h)
+        return lp.value, grad, hess.reshape(D, D, order="F")
+
     def close(self):
         if self.h:
             L.lib.avi_obj_destroy(self.h)
             self.h = None
+
+
+def gaussian_expectation_gradient_and_hessian(rng, q: MvLocationScale, n_samples: int, grad_buf, hess_buf, prob: _Problem):
+    """Same name and argument order as the reference (gauss_expected_grad_hess.jl:20-27): fills grad_buf (D) and
+    hess_buf (D, D) in place and returns (logpi_avg, grad_buf, hess_buf).  `rng` provides the Philox key."""
+    o = Objective(rng, RepGradELBO(1), q, prob)
+    try:
+        lp, g, H = o.gaussian_expectation_gradient_and_hessian(q, n_samples)
+    finally:
+        o.close()
+    grad_buf[...] = g
+    hess_buf[...] = H
+    return lp, grad_buf, hess_buf
 
 
 class HostUpdate:

@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "avi_internal.cuh"
 #include "device_utils.cuh"
@@ -550,6 +551,63 @@ int32_t avi_obj_rand(avi_obj* o, const float* lambda_host, int64_t P, float* Z_h
     if (Z_host) AVI_CUDA(ctx, cudaMemcpy2DAsync(Z_host, w, o->Z, pitch, w, o->Mloc, cudaMemcpyDeviceToHost, ctx->stream));
     if (eps_host) AVI_CUDA(ctx, cudaMemcpy2DAsync(eps_host, w, o->E, pitch, w, o->Mloc, cudaMemcpyDeviceToHost, ctx->stream));
     AVI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return AVI_OK;
+}
+
+// gaussian_expectation_gradient_and_hessian! (src/algorithms/gauss_expected_grad_hess.jl:20-58), first-order branch
+// (Stein / Price identity, :33-58): u ~ N(0, I), z = C u + m, then
+//   log pi_avg = mean log pi(z_b),  grad = mean grad log pi(z_b),  hess = C' \ mean(u_b grad log pi(z_b)').
+// Device path: the full-rank sampling kernels, the target's batched log-density + gradient, column sums, the
+// sample contraction U' G on the tensor cores (3xTF32, as the full-rank gradient) accumulated over chunks of
+// <= 4096 samples, and one triangular solve with D right-hand sides.  The 1 / n_samples is applied on the host.
+int32_t avi_obj_gauss_expected_grad_hess(avi_obj* o, const float* lambda_host, int64_t P, int32_t n_samples,
+                                         float* logpi_avg, float* grad_host, float* hess_host) {
+    if (!o || !logpi_avg || !grad_host || !hess_host) return AVI_ERR_INVALID;
+    avi_ctx* ctx = o->ctx;
+    if (o->family != AVI_FULLRANK)
+        AVI_FAIL(ctx, AVI_ERR_INVALID, "gaussian_expectation_gradient_and_hessian needs a full-rank (triangular scale) Gaussian");
+    if (o->model->capability < 1)
+        AVI_FAIL(ctx, AVI_ERR_UNSUPPORTED, "the target must provide logdensity_and_gradient (capability >= 1)");
+    AVI_CHECK(check_lambda(o, lambda_host, P));
+    if (n_samples < 1) AVI_FAIL(ctx, AVI_ERR_INVALID, "n_samples must be >= 1");
+    if (ctx->nranks > 1 && o->shard_axis == AVI_SHARD_ROWS) AVI_FAIL(ctx, AVI_ERR_UNSUPPORTED, "row-sharded targets are not supported here");
+    cudaSetDevice(ctx->device);
+    const int D = o->D, ld = o->ld, accv = o->accv;
+    const int chunk = std::min(n_samples, 4096);
+    AVI_CHECK(avi_obj_ensure_capacity(o, chunk));
+    std::memcpy(o->h_lambda, lambda_host, (size_t)P * sizeof(float));
+    AVI_CUDA(ctx, cudaMemcpyAsync(o->d_lambda, o->h_lambda, (size_t)P * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    float* scal = o->acc + 4 * (size_t)accv;
+    float* C1 = scal + ACC_NSCAL;              // per-chunk contraction, then the solved Hessian
+    float* C2 = C1 + (size_t)D * D;            // running sum of u g' over the chunks
+    float* gsum = o->acc + accv;               // running sum of g
+    AVI_CUDA(ctx, cudaMemsetAsync(C2, 0, (size_t)D * D * sizeof(float), ctx->stream));
+    AVI_CUDA(ctx, cudaMemsetAsync(gsum, 0, (size_t)accv * sizeof(float), ctx->stream));
+    std::vector<float> lp((size_t)chunk);
+    double s_logp = 0.0;
+    for (int m0 = 0; m0 < n_samples; m0 += chunk) {
+        const int Mc = std::min(chunk, n_samples - m0);
+        AVI_CHECK(avi_family_sample(o, o->d_lambda, o->Z, o->E, o->esq, Mc, m0, o->d_state, nullptr));
+        AVI_CHECK(o->model->eval(o->Z, ld, Mc, o->logp, o->G));
+        AVI_CHECK(avi_colsum_add(ctx, o->G, ld, Mc, D, o->acc, gsum));
+        // C1[j * D + i] = sum_b U[b][i] G[b][j]  (column-major D x D)
+        if (avi_fr_tc_ok(o, Mc)) AVI_CHECK(avi_fr_outer_tc(o, o->E, o->G, C1, Mc, 0, false));
+        else AVI_CHECK(avi_gemm_simt(ctx, o->G, 1, ld, o->E, 1, ld, C1, D, 1, D, D, Mc, 1.0f));
+        AVI_CHECK(avi_axpy(ctx, C1, C2, (int64_t)D * D));
+        AVI_CUDA(ctx, cudaMemcpyAsync(lp.data(), o->logp, (size_t)Mc * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        AVI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int b = 0; b < Mc; ++b) s_logp += lp[(size_t)b];
+    }
+    // hess = C' \ A: column j of A is a right-hand side (A is column-major: "row" j of a [D][D] sample-major buffer)
+    AVI_CHECK(avi_trsm_lt(ctx, o->d_lambda + D, D, C2, C1, D, D));
+    AVI_CHECK(avi_obj_advance(o));
+    AVI_CUDA(ctx, cudaMemcpyAsync(grad_host, gsum, (size_t)D * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    AVI_CUDA(ctx, cudaMemcpyAsync(hess_host, C1, (size_t)D * D * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    AVI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const float inv = 1.0f / (float)n_samples;
+    for (int i = 0; i < D; ++i) grad_host[i] *= inv;
+    for (size_t e = 0; e < (size_t)D * D; ++e) hess_host[e] *= inv;
+    *logpi_avg = (float)(s_logp / n_samples);
     return AVI_OK;
 }
 

@@ -277,6 +277,8 @@ int32_t avi_obj_ensure_capacity(avi_obj* o, int M);
 // (or in *ov when ov != nullptr, a host value).  E, esq always written.
 int32_t avi_family_sample(avi_obj* o, const float* lambda, float* Z, float* E, float* esq, int Mloc,
                           int m0, const ObjDeviceState* st, const ObjDeviceState* ov, const SampleHook* hook = nullptr);
+int32_t avi_axpy(avi_ctx* ctx, const float* x, float* y, int64_t n);                                   // y += x
+int32_t avi_colsum_add(avi_ctx* ctx, const float* W, int ld, int Mloc, int D, float* tmp, float* dst);  // dst += column sums
 int32_t avi_obj_stage_lambda(avi_obj* o);   // o->h_lambda (pinned, mapped) -> o->d_lambda by a kernel
 int32_t avi_objective_local(avi_obj* o, const float* lambda);          // sample + model + reduce -> acc
 // acc -> grad (skip_fr_matrix: leave the D x D block of a full-rank gradient to the caller's fused update)

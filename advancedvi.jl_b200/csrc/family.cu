@@ -417,6 +417,22 @@ bool avi_obj_defers_scalars(const avi_obj* o) {
            !(o->shard_axis == AVI_SHARD_SAMPLES && o->ctx->nranks > 1);
 }
 
+// dst[i] += sum_m W[m][i] (tmp receives the plain column sums) and y += x: small helpers of the Stein estimator
+__global__ void k_axpy(const float* __restrict__ x, float* __restrict__ y, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] += x[i];
+}
+int32_t avi_axpy(avi_ctx* ctx, const float* x, float* y, int64_t n) {
+    if (n <= 0) return AVI_OK;
+    k_axpy<<<(unsigned)std::min<int64_t>(ceil_div(n, 256), 1184), 256, 0, ctx->stream>>>(x, y, (long long)n);
+    AVI_LAUNCHED(ctx);
+    return AVI_OK;
+}
+int32_t avi_colsum_add(avi_ctx* ctx, const float* W, int ld, int Mloc, int D, float* tmp, float* dst) {
+    k_colsum<<<(unsigned)ceil_div(D, 32), dim3(32, 32), 0, ctx->stream>>>(W, ld, Mloc, D, tmp);
+    AVI_LAUNCHED(ctx);
+    return avi_axpy(ctx, tmp, dst, D);
+}
+
 int32_t avi_obj_stage_lambda(avi_obj* o) {
     avi_ctx* ctx = o->ctx;
     cudaError_t e = avi_launch_pdl(ctx, k_stage_in, dim3((unsigned)ceil_div(o->P, 256)), dim3(256), 0, (const float*)o->h_lambda,

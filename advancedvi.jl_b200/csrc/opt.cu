@@ -233,11 +233,6 @@ int32_t enqueue_iteration(avi_opt* op, bool subsampled, int64_t batch) {
         else if (items <= 2) LAUNCH_TAIL(2);
         else if (items <= 4) LAUNCH_TAIL(4);
         else LAUNCH_TAIL(8);
-        static const bool dbg_tail2 = getenv("AVI_DBG_TAIL2") && atoi(getenv("AVI_DBG_TAIL2")) != 0;
-        if (dbg_tail2 && ctx->tl) {   // timing experiment (results meaningless): the same kernel again, warm instruction cache
-            tail.tl = ctx->tl + 16; tail.tl_s = 3;   // second half of the stamp array
-            if (items <= 1) LAUNCH_TAIL(1); else if (items <= 2) LAUNCH_TAIL(2); else if (items <= 4) LAUNCH_TAIL(4); else LAUNCH_TAIL(8);
-        }
 #undef LAUNCH_TAIL
         AVI_LAUNCHED(ctx);
         if (ctx->tl) k_tl_commit<<<1, 32, 0, ctx->stream>>>(ctx->tl, ctx->tl_hist, o->d_state);

@@ -169,6 +169,14 @@ int32_t avi_obj_estimate_objective(avi_obj* obj, const float* lambda_host, int64
 /* rand(rng, q, M) (src/families/location_scale.jl:71-87): Z_host and eps_host (either may be
  * NULL) receive D x M column-major draws of the current step WITHOUT advancing it. */
 int32_t avi_obj_rand(avi_obj* obj, const float* lambda_host, int64_t P, float* Z_host, float* eps_host);
+/* gaussian_expectation_gradient_and_hessian!(rng, q, n_samples, grad_buf, hess_buf, prob), first-order (Stein / Price)
+ * branch -- src/algorithms/gauss_expected_grad_hess.jl:20-58: with u ~ N(0, I), z = C u + m,
+ * *logpi_avg = mean log pi(z), grad_host (D) = mean grad log pi(z), hess_host (D x D, column-major, not symmetrised)
+ * = C' \ mean(u grad log pi(z)').  obj must be a full-rank objective (lambda = [m; vec(C)]); draws come from the
+ * objective's Philox stream at its current step, which then advances.  The sampling stage of KLMinWassFwdBwd,
+ * KLMinNaturalGradDescent and KLMinSqrtNaturalGradDescent (klminwassfwdbwd.jl:101, klminnaturalgraddescent.jl:120). */
+int32_t avi_obj_gauss_expected_grad_hess(avi_obj* obj, const float* lambda_host, int64_t P, int32_t n_samples,
+                                         float* logpi_avg, float* grad_host, float* hess_host);
 int32_t avi_obj_destroy(avi_obj* obj);
 
 /* ---- minibatch order: ReshufflingBatchSubsampling (src/reshuffling.jl:27-32) --------------------

@@ -158,6 +158,22 @@ function estimate_objective_b200(rng, st::B200ObjState, params::Vector{Float32},
     return r[]
 end
 
+# ---- gaussian_expectation_gradient_and_hessian! (src/algorithms/gauss_expected_grad_hess.jl:20-58) -------------
+# Method for native targets: the sampling stage of KLMinWassFwdBwd / KLMinNaturalGradDescent /
+# KLMinSqrtNaturalGradDescent (first-order Stein branch) runs on the device; the d x d updates stay in Julia.
+function AdvancedVI.gaussian_expectation_gradient_and_hessian!(rng::Random.AbstractRNG,
+        q::MvLocationScale{<:LinearAlgebra.AbstractTriangular,<:Normal}, n_samples::Int,
+        grad_buf::AbstractVector{Float32}, hess_buf::AbstractMatrix{Float32}, prob::NativeProblem)
+    params, _ = Optimisers.destructure(q)
+    st = make_state(rng, 0, 0, 1, AutoB200(prob.c.device), q, prob, params)
+    lp = Ref{Float32}(0)
+    g, H = Vector{Float32}(undef, length(grad_buf)), Matrix{Float32}(undef, size(hess_buf)...)
+    check(@ccall(libavi.avi_obj_gauss_expected_grad_hess(st.h::Ptr{Cvoid}, params::Ptr{Float32}, length(params)::Int64,
+                 n_samples::Int32, lp::Ptr{Float32}, g::Ptr{Float32}, H::Ptr{Float32})::Int32), prob.c.h)
+    grad_buf .= g; hess_buf .= H
+    return lp[], grad_buf, hess_buf
+end
+
 # ---- optional fast path: the whole `step` on the device (src/algorithms/common.jl:40-120) ------------------
 # `init`/`step`/`output` methods for the three ParamSpaceSGD algorithm types when their adtype is AutoB200 and the
 # objective is not subsampled: parameters, optimiser state and the averaged iterate stay on the GPU (avi_opt_*),

@@ -156,3 +156,23 @@ def estimate_objective(q: MvLocationScale, prob, eps, entropy="MonteCarloEntropy
     """estimate_objective(rng, alg::ParamSpaceSGD, q, prob; n_samples, entropy): always a
     fresh RepGradELBO with MonteCarloEntropy by default, ignoring subsampling."""
     return repgrad_estimate_objective(q, prob, eps, entropy)
+
+
+def gaussian_expectation_gradient_and_hessian(q: MvLocationScale, prob, u):
+    """gaussian_expectation_gradient_and_hessian! (src/algorithms/gauss_expected_grad_hess.jl:20-58) for given standard
+    normal draws u (D x n).  First-order targets (:33-58, Stein / Price identity): z = C u + m,
+    hess = C' \\ mean_b(u_b grad log pi(z_b)').  Targets that also provide `hessian_batch` (second order, :59-80):
+    plain sample average of the Hessians.  Returns (logpi_avg, grad, hess)."""
+    from scipy.linalg import solve_triangular
+    n = u.shape[1]
+    m, Cs = q.location, (np.diag(q.scale) if q.is_meanfield else q.scale)
+    z = Cs @ u + m[:, None]                                             # :44-45
+    logp, G = prob.logdensity_and_gradient_batch(z)
+    logpi_avg = float(np.sum(logp / n))                                 # :49
+    grad = np.sum(G / n, axis=1)                                        # :51-54
+    if getattr(prob, "capability", 1) >= 2 and hasattr(prob, "hessian_batch"):
+        hess = np.sum(prob.hessian_batch(z) / n, axis=0)                # :62-77
+        return logpi_avg, grad, hess
+    A = u @ (G / n).T                                                   # :55  sum_b u_b (grad_b / n)'
+    hess = solve_triangular(Cs.T, A, lower=False)                       # :57  C' \\ A
+    return logpi_avg, grad, hess

@@ -34,8 +34,6 @@ for s in range(done - 6, done):
         line += f"{nm} [{h[k] - t0:6d} {h[4 + k] - t0:6d} {h[8 + k] - t0:6d}]  "
     if 0 < h[16] < (1 << 62):
         line += f"tail phases: loaded+logdet {h[16] - t0}, value {h[17] - t0}, updated {h[18] - t0}  "
-    if h[19] > 0 and h[19] < (1 << 62):
-        line += f"tail#2 [{h[19] - t0:6d} {h[23] - t0:6d} {h[27] - t0:6d}]  "
     if prev0 is not None:
         line += f"period {t0 - prev0} ns"
     prev0 = t0

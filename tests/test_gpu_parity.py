@@ -446,3 +446,45 @@ def test_c2_full_size_properties(avi, ctx):
     lpo, Go = probo.logdensity_and_gradient_batch(Z.astype(np.float64))
     assert np.abs(lp - lpo).max() <= 5e-4 * np.abs(lpo).max() and relerr(G, Go) < 2e-3
     prob.close()
+
+
+# --- gaussian_expectation_gradient_and_hessian! (src/algorithms/gauss_expected_grad_hess.jl) ---------------------
+@pytest.mark.parametrize("n_samples", [64, 5000])      # one chunk / several chunks of 4096 (+ SIMT tail path)
+def test_gauss_expected_grad_hess_matches_oracle(avi, ctx, n_samples):
+    """Stein branch on the device vs the oracle on the same Philox draws: logistic-regression target, dense scale."""
+    n, d = 300, 11
+    X, y = Mo.synth_glm_data(n, d, seed=9)
+    D = d + 1
+    prob, probo = avi.LogReg(ctx, X, y, gemm="tf32x3"), Mo.LogReg(X, y)
+    mu = 0.1 * P.normal_matrix(5, 0, D, 1)[:, 0]
+    Lm = np.tril(0.05 * P.normal_matrix(6, 0, D, D)) + 0.4 * np.eye(D)
+    q = avi.FullRankGaussian(mu.astype(np.float32), Lm.astype(np.float32))
+    qo = F.FullRankGaussian(mu.astype(np.float32).astype(np.float64), Lm.astype(np.float32).astype(np.float64))
+    obj = avi.Objective(KEY, avi.RepGradELBO(8), q, prob)
+    lp, g, H = obj.gaussian_expectation_gradient_and_hessian(q, n_samples)
+    lpo, go, Ho = O.gaussian_expectation_gradient_and_hessian(qo, probo, P.normal_matrix(KEY, 0, D, n_samples))
+    assert abs(lp - lpo) <= 2e-5 * abs(lpo)
+    assert relerr(g, go) < 5e-5 and relerr(H, Ho) < 2e-4
+    # the call advanced the step: a second call uses fresh draws
+    lp2, g2, H2 = obj.gaussian_expectation_gradient_and_hessian(q, n_samples)
+    lpo2, go2, Ho2 = O.gaussian_expectation_gradient_and_hessian(qo, probo, P.normal_matrix(KEY, 1, D, n_samples))
+    assert relerr(g2, go2) < 5e-5 and relerr(H2, Ho2) < 2e-4 and not np.array_equal(g, g2)
+    obj.close(); prob.close()
+
+
+def test_gauss_expected_grad_hess_known_answer(avi, ctx):
+    """test/general/gauss_expected_grad_hess.jl:29-56 on the device (first-order capability): q = N(1, 0.1^2 I); for a
+    Gaussian target N(mu_t, diag sigma_t^2): E grad = -(m - mu_t) / sigma_t^2, E Hessian = -diag(1 / sigma_t^2), atol 1e-1."""
+    D = 3
+    mu_t, sg_t = np.array([0.5, -0.2, 1.5]), np.array([0.8, 1.0, 0.7])
+    prob = avi.MvNormalDiag(ctx, mu_t, sg_t)
+    q = avi.FullRankGaussian(np.ones(D, np.float32), (0.1 * np.eye(D)).astype(np.float32))
+    g, H = np.zeros(D, np.float32), np.zeros((D, D), np.float32)
+    lp, g, H = avi.gaussian_expectation_gradient_and_hessian(KEY, q, 10 ** 6, g, H, prob)
+    assert np.allclose(g, -(1.0 - mu_t) / sg_t ** 2, atol=1e-1)
+    assert np.allclose(H, -np.diag(1.0 / sg_t ** 2), atol=1e-1)
+    # a mean-field family has no triangular scale: rejected like the reference's method signature (:20-27)
+    qm = avi.MeanFieldGaussian(np.ones(D, np.float32), np.full(D, 0.1, np.float32))
+    with pytest.raises(avi.AviError, match="full-rank"):
+        avi.gaussian_expectation_gradient_and_hessian(KEY, qm, 16, g, H, prob)
+    prob.close()

@@ -253,3 +253,30 @@ def test_nonfinite_objective_raises():
     st = Op.sgd_init(q0, Op.Descent(1e-3), Op.NoAveraging())
     with pytest.raises(RuntimeError, match="diverged"):
         Op.sgd_step(st, q0, lambda p, t: (np.nan, np.zeros(4), {}), Op.Descent(1e-3), Op.ClipScale(), Op.NoAveraging())
+
+
+# --- test/general/gauss_expected_grad_hess.jl ----------------------------------------------------
+class _TestQuad:
+    """TestQuad of the reference test (:1-27): log pi(x) = -x' S x / 2, gradient -S x, Hessian -S."""
+
+    def __init__(self, S, capability):
+        self.S, self.capability = np.asarray(S, float), capability
+
+    def logdensity_and_gradient_batch(self, Z):
+        return -0.5 * np.sum(Z * (self.S @ Z), axis=0), -(self.S @ Z)
+
+    def hessian_batch(self, Z):
+        return np.broadcast_to(-self.S, (Z.shape[1],) + self.S.shape)
+
+
+@pytest.mark.parametrize("capability", [1, 2])
+def test_gauss_expected_grad_hess_known_answer(capability):
+    """gauss_expected_grad_hess.jl (test) :29-56: d = 2, Sigma = [2 -0.1; -0.1 2], q = N(1, 0.1^2 I), n = 10^6:
+    E grad = -Sigma mu and E Hessian = -Sigma within atol 1e-1, for first- and second-order targets."""
+    S = np.array([[2.0, -0.1], [-0.1, 2.0]])
+    q = F.FullRankGaussian(np.ones(2), 0.1 * np.eye(2))
+    u = P.normal_matrix(77, 0, 2, 10 ** 6)
+    lp, g, H = O.gaussian_expectation_gradient_and_hessian(q, _TestQuad(S, capability), u)
+    assert np.allclose(g, -S @ q.location, atol=1e-1)
+    assert np.allclose(H, -S, atol=1e-1)
+    assert np.isfinite(lp)
