@@ -13,9 +13,14 @@
 //
 // Structure (one CTA per SM, persistent over work units = (a-block, b-chunk, k-split)):
 //   warp 0      TMA producer   (cp.async.bulk.tensor, 128B swizzle, mbarrier ring as deep as shared memory allows)
-//   warp 1      MMA issuer     (one elected thread: tcgen05.mma.kind::tf32, M = 128, N = NT)
+//   warp 1      MMA issuer     (one thread chosen by elect.sync -- NOT by `lane == 0`, which makes nvcc wrap every
+//                               tcgen05.mma in a divergence loop: tcgen05.mma.kind::tf32, M = 128, N = NT)
 //   warp 2      TMEM allocator (512 columns = 2 accumulator stages of up to 256 columns)
+//   warp 3      idle (optionally pulls the next kernel's static operand into L2: TcParams.pf_*)
 //   warps 4-19  epilogue       (tcgen05.ld 32x32b; warp w reads lanes 32*(w%4).., column quarter (w-4)/4)
+// k_gemm_tc_pair is the cta_group::2 variant (UMMA M = 256 over two CTAs).  What bounds the mainloop (tensor pipe
+// max(48, NT/2) cycles per MMA vs ~71 B/cycle of TMA ingest per SM) is measured in profiles/README.md and is the
+// cost model of avi_tc_plan.
 #include <cstdio>
 #include <cstdlib>
 

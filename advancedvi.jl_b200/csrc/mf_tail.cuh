@@ -1,6 +1,7 @@
 // The mean-field tail of one iteration -- finalize (sums -> gradient, value, elbo), finiteness check,
-// rule + operator + averager, commit -- as a device function, so that it can run as its own one-CTA kernel
-// (opt.cu).
+// rule + operator + averager, commit, and with several ranks the NVLink exchange of the partial sums -- as a device
+// function with two launch shapes (opt.cu): one thread-block cluster of 8 CTAs x 256 threads (default) or one CTA of
+// 1024 threads (AVI_TAIL_CLUSTER=0).
 #pragma once
 
 #include "avi_internal.cuh"

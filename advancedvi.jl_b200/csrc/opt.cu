@@ -1,11 +1,13 @@
 // K4: the fused SGD step -- Optimisers.update! + operator + averager of
 // src/algorithms/common.jl:91-94 with the parameters resident on the device -- and the
-// multi-iteration driver that replays one captured iteration as a CUDA graph.
+// multi-iteration driver that replays captured iterations (graphs of 1 and of AVI_GRAPH_UNROLL = 8 iterations),
+// blocking (avi_opt_steps) or without a host round trip (avi_opt_steps_begin / _enqueue / _end).
 //   rules      Optimisers.Descent / Adam (third-party), DoG / DoWG  src/optimization/rules.jl:17-64
 //   operators  ClipScale  src/optimization/clip_scale.jl:18-29
 //              ProximalLocationScaleEntropy  src/optimization/proximal_location_scale_entropy.jl:32-61
 //   averaging  PolynomialAveraging / NoAveraging  src/optimization/averaging.jl:42-53
 //   non-finite value slot => the step is not applied  src/algorithms/common.jl:83-89
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -15,7 +17,6 @@
 #include "fr_finalize.cuh"
 #include "mf_finalize.cuh"
 #include "mf_tail.cuh"
-#include <chrono>
 
 namespace {
 
