@@ -138,23 +138,44 @@ k_fr_update(float* __restrict__ lam, float* __restrict__ grad, float* __restrict
             float* __restrict__ avg, const float* __restrict__ sc, const float* __restrict__ out,
             const ObjDeviceState* __restrict__ st, const float* __restrict__ C1, const float* __restrict__ C2,
             const float* __restrict__ scal, int M, int objective, int entropy, UpdArgs a) {
+    // CTA 0: the location block; CTA 1 + j: column j of L, rows i >= j only (contiguous in the column-major layout:
+    // coalesced, no index divisions, nothing above the diagonal is touched)
     if (st->halted || !isfinite(out[0])) return;
     const int D = a.D;
     const float eta = a.rule == AVI_RULE_DESCENT ? a.h0 : 0.f;
     const float b1t = sc[SC_B1T], b2t = sc[SC_B2T], w = (a.avg_param + 1.0f) / (sc[SC_T] + a.avg_param);
-    const long long n = (long long)D + (long long)D * D;
-    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
+    const float bc1 = 1.0f / (1.0f - b1t), bc2 = 1.0f / (1.0f - b2t);   // Adam bias corrections as reciprocals
+    const int j = (int)blockIdx.x - 1;
+    const int i0 = j < 0 ? 0 : j;
+    for (int i = (i0 & ~31) + (int)threadIdx.x; i < D; i += 256) {
+        if (i < i0) continue;
+        size_t p;
         float g;
-        if (p < D) {
+        if (j < 0) {
+            p = (size_t)i;
             g = grad[p];   // location block: written by k_finalize_fr_vec
         } else {
-            const size_t idx = (size_t)(p - D);
-            const int j = (int)(idx / D), i = (int)(idx % D);
-            if (i < j) continue;
+            const size_t idx = (size_t)j * D + i;
+            p = (size_t)D + idx;
             g = fr_grad_entry(C1, C2, scal, lam[p], idx, i, j, M, objective, entropy);
             grad[p] = g;
         }
-        update_entry(p, g, lam, m1, m2, avg, a, eta, b1t, b2t, w);
+        float x = lam[p], dx;
+        if (a.rule == AVI_RULE_ADAM) {
+            const float mt = a.h1 * m1[p] + (1.0f - a.h1) * g;
+            const float vt = a.h2 * m2[p] + (1.0f - a.h2) * g * g;
+            m1[p] = mt; m2[p] = vt;
+            dx = __fdividef(mt * bc1, sqrtf(vt * bc2) + a.h3) * a.h0;
+        } else {
+            dx = eta * g;
+        }
+        x -= dx;
+        if (a.op != AVI_OP_IDENTITY && i == j) {   // diagonal of the scale
+            if (a.op == AVI_OP_CLIPSCALE) x = fmaxf(x, a.op_param);
+            else x = x + (sqrtf(fmaf(x, x, 4.0f * eta)) - x) * 0.5f;
+        }
+        lam[p] = x;
+        if (a.averager == AVI_AVG_POLYNOMIAL) avg[p] = (1.0f - w) * avg[p] + w * x;
     }
 }
 
@@ -245,8 +266,7 @@ int32_t enqueue_iteration(avi_opt* op, bool subsampled, int64_t batch) {
         const float* scal = o->acc + 4 * (size_t)o->accv;
         const float* C1 = scal + ACC_NSCAL;
         const float* C2 = C1 + (size_t)o->D * o->D;
-        const int nb = (int)std::min<int64_t>(ceil_div(op->P, 256 * 4), 8 * ctx->prop.multiProcessorCount);
-        k_fr_update<<<nb, 256, 0, ctx->stream>>>(op->lam, o->grad, op->m1, op->m2, op->avg, op->sc, o->out, o->d_state, C1,
+        k_fr_update<<<(unsigned)o->D + 1u, 256, 0, ctx->stream>>>(op->lam, o->grad, op->m1, op->m2, op->avg, op->sc, o->out, o->d_state, C1,
                                                  C2, scal, o->M, o->objective, o->entropy, a);
         AVI_LAUNCHED(ctx);
         k_commit<<<1, 32, 0, ctx->stream>>>(op->sc, o->out, o->d_state, op->trace, op->trace_cap, op->norm_part, a);
