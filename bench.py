@@ -344,7 +344,7 @@ def main():
                    "contraction": "tcgen05 kind::tf32 (operands rounded to nearest TF32, fp32 accumulate)"
                    if args.gemm == "tf32" else "SIMT fp32"},
         "value_l2_resident": K / (warm_ms * 1e-3), "ms_per_step_l2_resident": warm_ms / K,
-        "e2e": {"value": K / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": 4 * P, "d2h_bytes_per_step": 4 * (P + 4),
+        "e2e": {"value": K / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": 4 * P, "d2h_bytes_per_step": 4 * (P + 5),   # lambda in; gradient + 4 scalars + flag out
                 "path": "avi_obj_estimate_gradient (estimate_gradient! boundary, host lambda in / host gradient out) "
                         "+ host Adam/ClipScale/averaging (avi_host_update), L2 flushed between steps"},
         "gpu_launches": int(launches), "final_elbo": final_elbo,
