@@ -115,3 +115,77 @@ def FullRankGaussian(mu, L) -> MvLocationScale:
     L = np.asarray(L)
     assert L.ndim == 2 and np.allclose(L, np.tril(L))
     return MvLocationScale(mu, L)
+
+
+class MvLocationScaleLowRank:
+    """src/families/location_scale_low_rank.jl:16-24 with dist = Normal(0, 1) (`LowRankGaussian`, :132-135):
+    z = scale_diag .* u_diag + scale_factors * u_fact + location, covariance diag(scale_diag^2) + U U'.
+    Groundwork for SURVEY 8f rank 4: no device kernels use it yet."""
+
+    def __init__(self, location, scale_diag, scale_factors):
+        self.location = np.array(location, copy=True)
+        self.scale_diag = np.array(scale_diag, copy=True)
+        self.scale_factors = np.array(scale_factors, copy=True)
+        d = len(self.location)
+        assert self.scale_diag.shape == (d,) and self.scale_factors.ndim == 2 and self.scale_factors.shape[0] == d
+
+    def __len__(self):                                   # :28
+        return len(self.location)
+
+    @property
+    def rank(self) -> int:
+        return self.scale_factors.shape[1]
+
+    # Functors.@functor order (location, scale_diag, scale_factors) (:26); matrices flatten column-major
+    def destructure(self) -> np.ndarray:
+        return np.concatenate([self.location, self.scale_diag, self.scale_factors.reshape(-1, order="F")])
+
+    def restructure(self, flat) -> "MvLocationScaleLowRank":
+        d, r = len(self.location), self.rank
+        flat = np.asarray(flat)
+        assert flat.shape == (2 * d + d * r,)
+        return MvLocationScaleLowRank(flat[:d], flat[d:2 * d], flat[2 * d:].reshape(d, r, order="F"))
+
+    def entropy(self):                                   # :34-43
+        d = len(self.location)
+        D2 = self.scale_diag * self.scale_diag
+        UtDinvU = self.scale_factors.T @ (self.scale_factors / D2[:, None])
+        logdet_sigma = 2.0 * np.sum(np.log(self.scale_diag)) + np.linalg.slogdet(np.eye(self.rank) + UtDinvU)[1]
+        return d * H0 + logdet_sigma / 2.0
+
+    def logpdf(self, z: np.ndarray):                     # :45-70 (differentiable O(d^3) path; mean(dist) = 0)
+        from scipy.linalg import cholesky, solve_triangular
+        scale2 = np.diag(self.scale_diag ** 2) + self.scale_factors @ self.scale_factors.T
+        Lc = cholesky(scale2, lower=True)
+        r = z - (self.location if z.ndim == 1 else self.location[:, None])
+        u = solve_triangular(Lc, r, lower=True)
+        return np.sum(-0.5 * (u * u + LOG2PI), axis=0) - np.sum(np.log(np.diag(Lc)))
+
+    def rand_from_eps(self, u_diag: np.ndarray, u_fact: np.ndarray) -> np.ndarray:   # :79-86
+        """u_diag: (d, M), u_fact: (r, M) independent standard normal draws."""
+        return self.scale_diag[:, None] * u_diag + self.scale_factors @ u_fact + self.location[:, None]
+
+    def mean(self):                                      # :99-105
+        return self.location.copy()
+
+    def var(self):                                       # :107-111
+        return self.scale_diag ** 2 + np.sum(self.scale_factors ** 2, axis=1)
+
+    def cov(self):                                       # :113-117
+        return np.diag(self.scale_diag ** 2) + self.scale_factors @ self.scale_factors.T
+
+    def entropy_gradient(self):
+        """d entropy / d (scale_diag, scale_factors): with W = D^-2 U and B = I + U' W,
+        dH/dU = W B^-1 and dH/dD_i = 1 / D_i - (U B^-1 U')_ii / D_i^3 (the r x r capacitance matrix is all a
+        device kernel would have to factor)."""
+        D = self.scale_diag
+        W = self.scale_factors / (D * D)[:, None]
+        Binv = np.linalg.inv(np.eye(self.rank) + self.scale_factors.T @ W)
+        gU = W @ Binv
+        gD = 1.0 / D - np.einsum("ik,kl,il->i", self.scale_factors, Binv, self.scale_factors) / D ** 3
+        return gD, gU
+
+
+def LowRankGaussian(mu, D, U) -> MvLocationScaleLowRank:
+    """location_scale_low_rank.jl:119-135."""
+    return MvLocationScaleLowRank(mu, D, U)

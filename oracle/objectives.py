@@ -176,3 +176,21 @@ def gaussian_expectation_gradient_and_hessian(q: MvLocationScale, prob, u):
     A = u @ (G / n).T                                                   # :55  sum_b u_b (grad_b / n)'
     hess = solve_triangular(Cs.T, A, lower=False)                       # :57  C' \\ A
     return logpi_avg, grad, hess
+
+
+def repgrad_lowrank_value_and_gradient(params, q_template, prob, u_diag, u_fact):
+    """estimate_gradient! for RepGradELBO + ClosedFormEntropy over MvLocationScaleLowRank
+    (repgradelbo.jl:142-177 with the sampling path of location_scale_low_rank.jl:79-86), closed form:
+    with g_m = grad log pi(z_m): d/d location = -mean g, d/d scale_diag = -mean(g .* u_diag) - dH/dD,
+    d/d scale_factors = -mean(g u_fact') - dH/dU (dH: MvLocationScaleLowRank.entropy_gradient).
+    Returns (value = -ELBO, gradient in destructure order, elbo).  Groundwork for SURVEY 8f rank 4."""
+    q = q_template.restructure(params)
+    M = u_diag.shape[1]
+    Z = q.rand_from_eps(u_diag, u_fact)
+    logp, G = prob.logdensity_and_gradient_batch(Z)
+    elbo = float(np.mean(logp) + q.entropy())
+    gD_H, gU_H = q.entropy_gradient()
+    g_loc = -np.mean(G, axis=1)
+    g_diag = -np.mean(G * u_diag, axis=1) - gD_H
+    g_fact = -(G @ u_fact.T) / M - gU_H
+    return -elbo, np.concatenate([g_loc, g_diag, g_fact.reshape(-1, order="F")]), elbo

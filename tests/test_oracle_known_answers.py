@@ -280,3 +280,45 @@ def test_gauss_expected_grad_hess_known_answer(capability):
     assert np.allclose(g, -S @ q.location, atol=1e-1)
     assert np.allclose(H, -S, atol=1e-1)
     assert np.isfinite(lp)
+
+
+# --- test/families/location_scale_low_rank.jl (groundwork for SURVEY 8f rank 4: oracle only) ----------------
+@pytest.mark.parametrize("rank", [1, 2])
+def test_lowrank_family_logpdf_entropy_moments(rank):
+    """location_scale_low_rank.jl (test) :3-90, basedist = :gaussian: logpdf / entropy / mean / var / cov vs
+    MvNormal(location, Diagonal(scale_diag^2) + U U'), sample moments within 1e-2."""
+    d = 10
+    loc = P.normal_matrix(41, 0, d, 1)[:, 0]
+    U = P.normal_matrix(42, 0, d, rank)
+    q = F.LowRankGaussian(loc, np.ones(d), U)
+    Sigma = np.eye(d) + U @ U.T
+    ref = stats.multivariate_normal(loc, Sigma)
+    z = q.rand_from_eps(P.normal_matrix(43, 0, d, 5), P.normal_matrix(44, 0, rank, 5))
+    assert np.allclose(q.logpdf(z), ref.logpdf(z.T), rtol=1e-10)
+    assert np.isclose(q.entropy(), ref.entropy(), rtol=1e-12)
+    assert len(q) == d and np.allclose(q.mean(), loc) and np.allclose(q.var(), np.diag(Sigma)) and np.allclose(q.cov(), Sigma)
+    Z = q.rand_from_eps(P.normal_matrix(45, 0, d, 10 ** 6), P.normal_matrix(46, 0, rank, 10 ** 6))
+    assert np.allclose(Z.mean(axis=1), loc, rtol=1e-2, atol=1e-2)
+    assert np.allclose(Z.var(axis=1), np.diag(Sigma), rtol=1e-2)
+    lam = q.destructure()
+    assert lam.shape == (2 * d + d * rank,)
+    q2 = q.restructure(lam)
+    assert np.array_equal(q2.scale_factors, q.scale_factors) and np.array_equal(q2.scale_diag, q.scale_diag)
+
+
+def test_lowrank_repgrad_closed_form_vs_finite_differences():
+    """The closed-form RepGradELBO + ClosedFormEntropy gradient over the low-rank family equals central finite
+    differences of the forward closure (what the reference's AD backend returns)."""
+    d, r, M = 6, 2, 5
+    prob = Mo.NormalDiag(np.linspace(-1, 1, d), np.linspace(0.5, 1.5, d))
+    q = F.LowRankGaussian(0.1 * np.arange(d), 0.5 + 0.1 * np.arange(d), 0.3 * P.normal_matrix(51, 0, d, r))
+    u1, u2 = P.normal_matrix(52, 0, d, M), P.normal_matrix(53, 0, r, M)
+    lam = q.destructure()
+    v, g, e = O.repgrad_lowrank_value_and_gradient(lam, q, prob, u1, u2)
+
+    def f(x):
+        return O.repgrad_lowrank_value_and_gradient(x, q, prob, u1, u2)[0]
+    h = 1e-6
+    fd = np.array([(f(lam + h * np.eye(len(lam))[k]) - f(lam - h * np.eye(len(lam))[k])) / (2 * h) for k in range(len(lam))])
+    assert np.allclose(g, fd, rtol=1e-6, atol=1e-7)
+    assert np.isclose(v, -e)
