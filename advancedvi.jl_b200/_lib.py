@@ -22,7 +22,7 @@ lib = C.CDLL(LIB_PATH)
 
 # status codes / enums (include/avi.h)
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_COMM, ERR_STATE, ERR_CALLBACK = range(7)
-MEANFIELD, FULLRANK = 0, 1
+MEANFIELD, FULLRANK, LOWRANK = 0, 1, 2
 REPGRAD, SCOREGRAD = 0, 1
 ENT_CLOSEDFORM, ENT_MONTECARLO, ENT_STL, ENT_CLOSEDFORM_ZEROGRAD, ENT_STL_ZEROGRAD = range(5)
 RULE_DESCENT, RULE_ADAM, RULE_DOG, RULE_DOWG = range(4)
@@ -86,6 +86,7 @@ SIGNATURES = {
                                    C.c_float, c_float_p, C.c_int64, C.POINTER(vp)]),
     "avi_opt_steps": (C.c_int32, [vp, C.c_int32, c_float_p, c_float_p, c_i32_p]),
     "avi_ctx_timeline_get": (C.c_int32, [vp, C.POINTER(C.c_uint64)]),
+    "avi_obj_create_lowrank": (C.c_int32, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(vp)]),
     "avi_obj_gauss_expected_grad_hess": (C.c_int32, [vp, c_float_p, C.c_int64, C.c_int32, c_float_p, c_float_p, c_float_p]),
     "avi_host_update": (C.c_int32, [C.c_int32, c_float_p, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_float, C.c_int64,
                                     C.c_int64, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p]),

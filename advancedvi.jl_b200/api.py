@@ -28,7 +28,7 @@ from . import _lib as L
 
 __all__ = [
     "Context", "MvNormalDiag", "LogReg", "GaussGLM", "HostCallbackProblem",
-    "MvLocationScale", "MeanFieldGaussian", "FullRankGaussian",
+    "MvLocationScale", "MeanFieldGaussian", "FullRankGaussian", "MvLocationScaleLowRank", "LowRankGaussian",
     "ClosedFormEntropy", "MonteCarloEntropy", "StickingTheLandingEntropy",
     "ClosedFormEntropyZeroGradient", "StickingTheLandingEntropyZeroGradient",
     "RepGradELBO", "ScoreGradELBO", "SubsampledObjective", "ReshufflingBatchSubsampling",
@@ -283,6 +283,49 @@ class MvLocationScale:
         return MvLocationScale(flat[:D].copy(), flat[D:].reshape(D, D, order="F").copy())
 
 
+class MvLocationScaleLowRank:
+    """src/families/location_scale_low_rank.jl:16-24 with dist = Normal(0, 1) (`LowRankGaussian`): covariance
+    diag(scale_diag^2) + scale_factors scale_factors'; float32 only.  Flat parameters follow the Functors order
+    (location, scale_diag, scale_factors) with the factor matrix column-major."""
+
+    family = L.LOWRANK
+
+    def __init__(self, location, scale_diag, scale_factors):
+        for a in (location, scale_diag, scale_factors):
+            if np.asarray(a).dtype not in (np.float32,):
+                raise TypeError("MvLocationScaleLowRank: the B200 path supports Float32 only "
+                                f"(got {np.asarray(a).dtype}); convert with .astype(np.float32)")
+        self.location = np.array(location, dtype=np.float32)
+        self.scale_diag = np.array(scale_diag, dtype=np.float32)
+        self.scale_factors = np.array(scale_factors, dtype=np.float32)
+        d = len(self.location)
+        if self.scale_diag.shape != (d,) or self.scale_factors.ndim != 2 or self.scale_factors.shape[0] != d:
+            raise ValueError("scale_diag must have D entries and scale_factors must be D x rank")
+
+    @property
+    def rank(self):
+        return self.scale_factors.shape[1]
+
+    def __len__(self):
+        return len(self.location)
+
+    def destructure(self):
+        return np.concatenate([self.location, self.scale_diag, self.scale_factors.reshape(-1, order="F")])
+
+    def restructure(self, flat):
+        d, r = len(self.location), self.rank
+        flat = np.asarray(flat, dtype=np.float32)
+        return MvLocationScaleLowRank(flat[:d].copy(), flat[d:2 * d].copy(), flat[2 * d:].reshape(d, r, order="F").copy())
+
+    def cov(self):                                   # location_scale_low_rank.jl:113-117
+        return np.diag(self.scale_diag.astype(np.float64) ** 2) + self.scale_factors.astype(np.float64) @ self.scale_factors.T
+
+
+def LowRankGaussian(mu, D, U):
+    """location_scale_low_rank.jl:119-135."""
+    return MvLocationScaleLowRank(mu, D, U)
+
+
 def MeanFieldGaussian(mu, diag_scale):
     """location_scale.jl:139-141."""
     if np.asarray(diag_scale).ndim != 1:
@@ -512,8 +555,12 @@ class Objective:
         if len(q) != prob.dimension():
             raise ValueError("q and the target have different dimensions")
         h = L.vp()
-        L.check(L.lib.avi_obj_create(self.ctx.h, prob.h, q.family, base.kind, base.entropy.code, base.n_samples,
-                                     C.byref(h)), self.ctx.h)
+        if q.family == L.LOWRANK:
+            L.check(L.lib.avi_obj_create_lowrank(self.ctx.h, prob.h, q.rank, base.kind, base.entropy.code, base.n_samples,
+                                                 C.byref(h)), self.ctx.h)
+        else:
+            L.check(L.lib.avi_obj_create(self.ctx.h, prob.h, q.family, base.kind, base.entropy.code, base.n_samples,
+                                         C.byref(h)), self.ctx.h)
         self.h = h
         self.P = int(L.lib.avi_obj_num_params(h))
         self.key = _key_from(rng)

@@ -276,7 +276,7 @@ int32_t avi_model_destroy(avi_model* model) {
 
 // ---- objective ---------------------------------------------------------------------------------
 static void obj_free_buffers(avi_obj* o) {
-    avi_free(o->Z); avi_free(o->E); avi_free(o->G); avi_free(o->U);
+    avi_free(o->Z); avi_free(o->E); avi_free(o->G); avi_free(o->U); avi_free(o->E2);
     avi_free(o->logp); avi_free(o->esq); avi_free(o->fbuf);
 }
 
@@ -294,6 +294,7 @@ int32_t avi_obj_ensure_capacity(avi_obj* o, int M) {
     AVI_CHECK(avi_alloc(ctx, &o->E, n));
     AVI_CHECK(avi_alloc(ctx, &o->G, n));
     if (o->family == AVI_FULLRANK) AVI_CHECK(avi_alloc(ctx, &o->U, n));
+    if (o->family == AVI_LOWRANK) AVI_CHECK(avi_alloc(ctx, &o->E2, (size_t)M * o->ldr));
     AVI_CHECK(avi_alloc(ctx, &o->logp, (size_t)M));
     AVI_CHECK(avi_alloc(ctx, &o->esq, (size_t)M));
     AVI_CHECK(avi_alloc(ctx, &o->fbuf, (size_t)M));
@@ -310,11 +311,30 @@ static int32_t obj_push_state(avi_obj* o) {
     return AVI_OK;
 }
 
+static int32_t obj_create(avi_ctx* ctx, avi_model* model, int32_t family, int32_t rank, int32_t objective,
+                          int32_t entropy, int32_t M, avi_obj** out);
+
 int32_t avi_obj_create(avi_ctx* ctx, avi_model* model, int32_t family, int32_t objective, int32_t entropy,
                        int32_t M, avi_obj** out) {
     if (!ctx || !model || !out) return AVI_ERR_INVALID;
     *out = nullptr;
-    if (family != AVI_MEANFIELD && family != AVI_FULLRANK) AVI_FAIL(ctx, AVI_ERR_INVALID, "family");
+    if (family != AVI_MEANFIELD && family != AVI_FULLRANK)
+        AVI_FAIL(ctx, AVI_ERR_INVALID, "family (the low-rank family is created with avi_obj_create_lowrank)");
+    return obj_create(ctx, model, family, 0, objective, entropy, M, out);
+}
+
+int32_t avi_obj_create_lowrank(avi_ctx* ctx, avi_model* model, int32_t rank, int32_t objective, int32_t entropy,
+                               int32_t M, avi_obj** out) {
+    if (!ctx || !model || !out) return AVI_ERR_INVALID;
+    *out = nullptr;
+    if (rank < 1 || rank > avi_lr_max_rank()) AVI_FAIL(ctx, AVI_ERR_INVALID, "rank must be in 1..32");
+    if (objective != AVI_REPGRAD || entropy != AVI_ENT_CLOSEDFORM)
+        AVI_FAIL(ctx, AVI_ERR_UNSUPPORTED, "the low-rank family supports RepGradELBO with ClosedFormEntropy only");
+    return obj_create(ctx, model, AVI_LOWRANK, rank, objective, entropy, M, out);
+}
+
+static int32_t obj_create(avi_ctx* ctx, avi_model* model, int32_t family, int32_t rank, int32_t objective,
+                          int32_t entropy, int32_t M, avi_obj** out) {
     if (objective != AVI_REPGRAD && objective != AVI_SCOREGRAD) AVI_FAIL(ctx, AVI_ERR_INVALID, "objective");
     if (entropy < AVI_ENT_CLOSEDFORM || entropy > AVI_ENT_STL_ZEROGRAD) AVI_FAIL(ctx, AVI_ERR_INVALID, "entropy");
     if (M < 1) AVI_FAIL(ctx, AVI_ERR_INVALID, "n_samples must be >= 1");
@@ -328,9 +348,15 @@ int32_t avi_obj_create(avi_ctx* ctx, avi_model* model, int32_t family, int32_t o
     o->D = model->D; o->M = M; o->m0 = 0; o->Mloc = M;
     o->ld = (int)round_up(o->D, 4);
     o->accv = (int)round_up(o->D, 32);
-    o->P = family == AVI_MEANFIELD ? 2LL * o->D : (int64_t)o->D + (int64_t)o->D * o->D;
-    o->acc_len = 4LL * o->accv + ACC_NSCAL + (family == AVI_FULLRANK ? 2LL * o->D * o->D : 0);
+    o->rank = rank; o->ldr = (int)round_up(std::max(rank, 1), 4);
+    o->P = family == AVI_MEANFIELD ? 2LL * o->D
+           : family == AVI_FULLRANK ? (int64_t)o->D + (int64_t)o->D * o->D
+                                    : 2LL * o->D + (int64_t)o->D * rank;
+    // payload of the exchange: vector sums | scalars | full-rank: two D x D blocks / low-rank: sum_m g u_fact' (D x r)
+    o->acc_len = 4LL * o->accv + ACC_NSCAL +
+                 (family == AVI_FULLRANK ? 2LL * o->D * o->D : family == AVI_LOWRANK ? (int64_t)o->D * rank : 0);
     int32_t rc = avi_alloc(ctx, &o->d_state, 1);
+    if (rc == AVI_OK && family == AVI_LOWRANK) rc = avi_alloc(ctx, &o->lr_ent, 1 + (size_t)o->D + (size_t)o->D * rank);
     if (rc == AVI_OK) rc = avi_alloc(ctx, &o->d_lambda, (size_t)o->P);
     if (rc == AVI_OK) rc = avi_alloc(ctx, &o->acc, (size_t)o->acc_len);
     if (rc == AVI_OK) rc = avi_alloc(ctx, &o->grad, (size_t)o->P + 4);   // + {value, elbo, logdet, shift} (estimate_gradient!)
@@ -356,6 +382,7 @@ int32_t avi_obj_destroy(avi_obj* o) {
     obj_free_buffers(o);
     avi_fr_free(o);
     avi_free(o->d_state); avi_free(o->d_lambda); avi_free(o->acc); avi_free(o->grad); avi_free(o->out);
+    avi_free(o->lr_ent);
     if (o->h_lambda) cudaFreeHost(o->h_lambda);
     if (o->h_grad) cudaFreeHost(o->h_grad);
     delete o;
@@ -508,6 +535,9 @@ int32_t avi_obj_estimate_objective(avi_obj* o, const float* lambda_host, int64_t
     avi_ctx* ctx = o->ctx;
     AVI_CHECK(check_lambda(o, lambda_host, P));
     if (n_samples < 1) AVI_FAIL(ctx, AVI_ERR_INVALID, "n_samples must be >= 1");
+    if (o->family == AVI_LOWRANK)
+        AVI_FAIL(ctx, AVI_ERR_UNSUPPORTED, "estimate_objective is not implemented for the low-rank family (its Monte-Carlo "
+                                           "entropy needs logpdf through the capacitance matrix)");
     cudaSetDevice(ctx->device);
     std::memcpy(o->h_lambda, lambda_host, (size_t)P * sizeof(float));
     AVI_CUDA(ctx, cudaMemcpyAsync(o->d_lambda, o->h_lambda, (size_t)P * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));

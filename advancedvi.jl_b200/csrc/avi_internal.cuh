@@ -216,6 +216,10 @@ struct avi_obj {
     float* E = nullptr;          // cap_M x ld
     float* G = nullptr;          // cap_M x ld
     float* U = nullptr;          // cap_M x ld (full-rank: L^{-T} eps)
+    // low-rank family (family_lr.cu): rank, pitch of the factor draws, u_fact draws, [H | dH/dD | dH/dU]
+    int rank = 0, ldr = 0;
+    float* E2 = nullptr;         // cap_M x ldr
+    float* lr_ent = nullptr;     // 1 + D + D * rank
     float* logp = nullptr;       // cap_M
     float* esq = nullptr;        // cap_M : |eps_m|^2
     float* fbuf = nullptr;       // cap_M : ScoreGrad f_m
@@ -277,6 +281,10 @@ int32_t avi_obj_ensure_capacity(avi_obj* o, int M);
 // (or in *ov when ov != nullptr, a host value).  E, esq always written.
 int32_t avi_family_sample(avi_obj* o, const float* lambda, float* Z, float* E, float* esq, int Mloc,
                           int m0, const ObjDeviceState* st, const ObjDeviceState* ov, const SampleHook* hook = nullptr);
+int avi_lr_max_rank();                                                                                 // family_lr.cu
+int32_t avi_lr_affine(avi_obj* o, const float* lambda, const float* E1, const float* E2, float* Z, int Mloc);
+int32_t avi_lr_entropy(avi_obj* o, const float* lambda);      // -> o->lr_ent
+int32_t avi_lr_finalize(avi_obj* o, float* grad, float* out); // acc, lr_ent -> gradient, value, elbo
 int32_t avi_axpy(avi_ctx* ctx, const float* x, float* y, int64_t n);                                   // y += x
 int32_t avi_colsum_add(avi_ctx* ctx, const float* W, int ld, int Mloc, int D, float* tmp, float* dst);  // dst += column sums
 int32_t avi_obj_stage_lambda(avi_obj* o);   // o->h_lambda (pinned, mapped) -> o->d_lambda by a kernel

@@ -7,7 +7,7 @@
 #define AVI_LOG2PI 1.8378770664093453f
 #define AVI_H0 1.4189385332046727f   // entropy(Normal(0,1)) = (log 2pi + 1) / 2
 
-enum { AVI_STREAM_EPS = 0, AVI_STREAM_SHUFFLE = 1, AVI_STREAM_DATA = 2 };
+enum { AVI_STREAM_EPS = 0, AVI_STREAM_SHUFFLE = 1, AVI_STREAM_DATA = 2, AVI_STREAM_EPS_FACTORS = 3 };
 
 // Philox4x32-10 (Salmon et al., SC'11).  Same counter/key convention as oracle/philox.py.
 __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,

@@ -394,6 +394,16 @@ int32_t avi_family_sample(avi_obj* o, const float* lambda, float* Z, float* E, f
         if (hook && hook->kind == 1) LAUNCH_SAMPLE(false, true, *hook);
         else LAUNCH_SAMPLE(false, false, SampleHook{});
         AVI_LAUNCHED(ctx);
+    } else if (o->family == AVI_LOWRANK) {
+        // u_diag -> E (D per sample, eps stream), u_fact -> E2 (rank per sample, its own Philox stream), then
+        // z = scale_diag .* u_diag + scale_factors * u_fact + location (location_scale_low_rank.jl:79-86)
+        LAUNCH_SAMPLE(true, false, SampleHook{});
+        AVI_LAUNCHED(ctx);
+        avi_launch_pdl(ctx, k_sample<true, false, SAMPLE_WARPS>, dim3((unsigned)Mloc), dim3(32 * SAMPLE_WARPS), 0, lambda,
+                       o->rank, o->ldr, m0, Mloc, st, sv, use_val, (uint32_t)AVI_STREAM_EPS_FACTORS, (float*)nullptr, o->E2,
+                       o->fbuf, SampleHook{});
+        AVI_LAUNCHED(ctx);
+        AVI_CHECK(avi_lr_affine(o, lambda, E, o->E2, Z, Mloc));
     } else {
         LAUNCH_SAMPLE(true, false, SampleHook{});
         AVI_LAUNCHED(ctx);
@@ -487,7 +497,13 @@ int32_t avi_objective_local(avi_obj* o, const float* lambda) {
                                                Mloc, o->out, o->fbuf, scal);
         AVI_LAUNCHED(ctx);
     }
-    if (o->family == AVI_MEANFIELD) {
+    if (o->family == AVI_LOWRANK) {
+        // v0 = sum_m g, v1 = sum_m g .* u_diag (the mean-field reduction), CU[k * D + i] = sum_m g[m][i] u_fact[m][k]
+        k_reduce_mf<<<(unsigned)ceil_div(D, 32), dim3(32, 32), 0, ctx->stream>>>(o->G, o->E, o->fbuf, ld, Mloc, D, accv,
+                                                                               o->objective, 0, o->acc);
+        AVI_LAUNCHED(ctx);
+        AVI_CHECK(avi_gemm_simt(ctx, o->E2, 1, o->ldr, o->G, 1, ld, scal + ACC_NSCAL, D, 1, o->rank, D, Mloc, 1.0f));
+    } else if (o->family == AVI_MEANFIELD) {
         // with a fused target and a closed-form entropy nothing else is needed (v2, v3 unused)
         if (!(skip_g && !stl)) {
             k_reduce_mf<<<(unsigned)ceil_div(D, 32), dim3(32, 32), 0, ctx->stream>>>(
@@ -537,6 +553,10 @@ int32_t avi_objective_finalize(avi_obj* o, const float* lambda, float* grad, flo
                                bool fuse_advance) {
     avi_ctx* ctx = o->ctx;
     const int D = o->D, accv = o->accv;
+    if (o->family == AVI_LOWRANK) {
+        AVI_CHECK(avi_lr_entropy(o, lambda));
+        return avi_lr_finalize(o, grad, out);
+    }
     if (o->family == AVI_MEANFIELD) {
         unsigned nb = (unsigned)std::min<int64_t>(ceil_div(D, 256), 64);
         // fuse_advance (estimate_gradient!): one CTA; gradient, scalars and completion flag written straight into the

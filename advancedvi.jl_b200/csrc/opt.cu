@@ -37,7 +37,8 @@ k_norms(const float* __restrict__ lam, const float* __restrict__ x0, const float
 __device__ __forceinline__ bool is_scale_diag(long long p, int D, int fullrank) {
     if (p < D) return false;
     long long q = p - D;
-    return fullrank ? (q % (D + 1) == 0) : true;
+    // mean-field: [D, 2 D) is all there is; low-rank: the factor entries behind scale_diag are not scale diagonals
+    return fullrank ? (q % (D + 1) == 0) : q < D;
 }
 
 // one parameter entry of Optimisers.update! + operator + averager (common.jl:91-94)
@@ -455,6 +456,10 @@ int32_t avi_opt_create(avi_obj* obj, int32_t rule, const float* hyper, int32_t n
     if (rule < AVI_RULE_DESCENT || rule > AVI_RULE_DOWG) AVI_FAIL(ctx, AVI_ERR_INVALID, "rule");
     if (op_kind < AVI_OP_IDENTITY || op_kind > AVI_OP_PROXENTROPY) AVI_FAIL(ctx, AVI_ERR_INVALID, "operator");
     if (averager != AVI_AVG_NONE && averager != AVI_AVG_POLYNOMIAL) AVI_FAIL(ctx, AVI_ERR_INVALID, "averager");
+    if (op_kind == AVI_OP_PROXENTROPY && obj->family == AVI_LOWRANK)
+        AVI_FAIL(ctx, AVI_ERR_UNSUPPORTED,
+                 "ProximalLocationScaleEntropy is defined for MvLocationScale only "
+                 "(src/optimization/proximal_location_scale_entropy.jl:46-61)");
     if (op_kind == AVI_OP_PROXENTROPY && rule == AVI_RULE_ADAM)
         AVI_FAIL(ctx, AVI_ERR_UNSUPPORTED,
                  "ProximalLocationScaleEntropy only supports Descent, DoG and DoWG "

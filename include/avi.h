@@ -38,7 +38,7 @@ enum { AVI_OK = 0, AVI_ERR_INVALID = 1, AVI_ERR_CUDA = 2, AVI_ERR_UNSUPPORTED = 
        AVI_ERR_COMM = 4, AVI_ERR_STATE = 5, AVI_ERR_CALLBACK = 6 };
 
 /* MeanFieldGaussian / FullRankGaussian (src/families/location_scale.jl:124-141) */
-enum { AVI_MEANFIELD = 0, AVI_FULLRANK = 1 };
+enum { AVI_MEANFIELD = 0, AVI_FULLRANK = 1, AVI_LOWRANK = 2 };
 /* RepGradELBO (src/algorithms/repgradelbo.jl:21-24) / ScoreGradELBO (scoregradelbo.jl:15-17) */
 enum { AVI_REPGRAD = 0, AVI_SCOREGRAD = 1 };
 /* entropy estimators, src/algorithms/entropy.jl:11-15, 25-29, 40-46, 57-65, 78-90 */
@@ -142,6 +142,14 @@ int32_t avi_model_destroy(avi_model* model);
  *      (src/algorithms/abstractobjective.jl:25-86) ----------------------------------------- */
 int32_t avi_obj_create(avi_ctx* ctx, avi_model* model, int32_t family, int32_t objective,
                        int32_t entropy, int32_t M, avi_obj** out);
+/* MvLocationScaleLowRank / LowRankGaussian (src/families/location_scale_low_rank.jl:16-24, :119-135): covariance
+ * diag(scale_diag^2) + scale_factors scale_factors', lambda = [location (D); scale_diag (D); vec(scale_factors)
+ * (D x rank, column-major)] (Functors order, :26), P = 2 D + D rank.  rank <= 32.  Supported: RepGradELBO with
+ * ClosedFormEntropy (what KLMinRepGradDescent uses by default, docs/src/families.md:185-190), estimate_gradient!,
+ * rand and the fused step with Descent / Adam / DoG / DoWG, IdentityOperator / ClipScale (on scale_diag,
+ * clip_scale.jl:31-41) and both averagers; everything else reports AVI_ERR_UNSUPPORTED. */
+int32_t avi_obj_create_lowrank(avi_ctx* ctx, avi_model* model, int32_t rank, int32_t objective, int32_t entropy,
+                               int32_t M, avi_obj** out);
 /* set_objective_state_problem (repgradelbo.jl:31-39, scoregradelbo.jl:24-32) */
 int32_t avi_obj_set_model(avi_obj* obj, avi_model* model);
 /* eps[i, m] at step t is a pure function of (key, t, m, i) (Philox4x32-10 + Box-Muller);

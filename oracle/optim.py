@@ -105,6 +105,9 @@ class ClipScale:
     def apply(self, q_template: MvLocationScale, opt_rule, opt_state, params):
         q = q_template.restructure(params)
         eps = params.dtype.type(self.epsilon)
+        if hasattr(q, "scale_factors"):                 # MvLocationScaleLowRank, clip_scale.jl:31-41
+            q.scale_diag = np.maximum(q.scale_diag, eps)
+            return q.destructure()
         if q.is_meanfield:
             q.scale = np.maximum(q.scale, eps)
         else:

@@ -31,6 +31,7 @@ MASK32 = np.uint64(0xFFFFFFFF)
 STREAM_EPS = 0        # epsilon draws of the variational family
 STREAM_SHUFFLE = 1    # minibatch reshuffling (oracle/reshuffling.py)
 STREAM_DATA = 2       # synthetic benchmark data (bench.py / tests)
+STREAM_EPS_FACTORS = 3   # u_fact draws of the low-rank family (location_scale_low_rank.jl:84)
 
 
 def philox4x32_10(ctr: np.ndarray, key) -> np.ndarray:

@@ -488,3 +488,88 @@ def test_gauss_expected_grad_hess_known_answer(avi, ctx):
     with pytest.raises(avi.AviError, match="full-rank"):
         avi.gaussian_expectation_gradient_and_hessian(KEY, qm, 16, g, H, prob)
     prob.close()
+
+
+# --- MvLocationScaleLowRank / LowRankGaussian (src/families/location_scale_low_rank.jl) ---------
+def _lowrank_pair(avi, D, r, zero_factors=False):
+    mu = (0.1 * np.arange(D) - 0.2)
+    sd = 0.5 + 0.05 * np.arange(D)
+    U = np.zeros((D, r)) if zero_factors else 0.3 * P.normal_matrix(91, 0, D, r)
+    mu32, sd32, U32 = mu.astype(np.float32), sd.astype(np.float32), U.astype(np.float32)
+    return (avi.LowRankGaussian(mu32, sd32, U32),
+            F.LowRankGaussian(mu32.astype(np.float64), sd32.astype(np.float64), U32.astype(np.float64)))
+
+
+def _lowrank_draws(D, r, M, step=0):
+    return P.normal_matrix(KEY, step, D, M), P.normal_matrix(KEY, step, r, M, stream=P.STREAM_EPS_FACTORS)
+
+
+@pytest.mark.parametrize("D,r,M", [(5, 1, 7), (33, 3, 70), (130, 32, 16)])
+def test_lowrank_rand_and_gradient_match_oracle(avi, ctx, D, r, M):
+    """rand (location_scale_low_rank.jl:79-86) and estimate_gradient! for RepGradELBO + ClosedFormEntropy over the
+    low-rank family vs the oracle on the same two Philox streams (u_diag, u_fact)."""
+    mu_t, sg_t = np.linspace(-1, 1, D), np.linspace(0.5, 1.5, D)
+    prob, probo = avi.MvNormalDiag(ctx, mu_t, sg_t), Mo.NormalDiag(mu_t, sg_t)
+    q, qo = _lowrank_pair(avi, D, r)
+    obj = avi.Objective(KEY, avi.RepGradELBO(M), q, prob)
+    assert obj.P == 2 * D + D * r
+    u1, u2 = _lowrank_draws(D, r, M)
+    Z, E = obj.rand(q)
+    assert np.abs(E - u1).max() < 5e-6
+    assert relerr(Z, qo.rand_from_eps(u1, u2)) < 2e-6
+    v, g, e = obj.estimate_gradient(q.destructure())
+    vo, go, eo = O.repgrad_lowrank_value_and_gradient(qo.destructure(), qo, probo, u1, u2)
+    assert abs(v - vo) <= 2e-5 * max(1.0, abs(vo)) and abs(e - eo) <= 2e-5 * max(1.0, abs(eo))
+    assert relerr(g, go) < 5e-5
+    # blocks separately: location / scale_diag / scale_factors
+    assert relerr(g[:D], go[:D]) < 5e-5 and relerr(g[D:2 * D], go[D:2 * D]) < 5e-5 and relerr(g[2 * D:], go[2 * D:]) < 1e-4
+    obj.close(); prob.close()
+
+
+def test_lowrank_logreg_gradient_matches_oracle(avi, ctx):
+    n, d, r, M = 200, 20, 4, 32
+    X, y = Mo.synth_glm_data(n, d, seed=8)
+    D = d + 1
+    prob, probo = avi.LogReg(ctx, X, y, gemm="tf32x3"), Mo.LogReg(X, y)
+    q, qo = _lowrank_pair(avi, D, r)
+    obj = avi.Objective(KEY, avi.RepGradELBO(M), q, prob)
+    v, g, e = obj.estimate_gradient(q.destructure())
+    u1, u2 = _lowrank_draws(D, r, M)
+    vo, go, eo = O.repgrad_lowrank_value_and_gradient(qo.destructure(), qo, probo, u1, u2)
+    assert abs(v - vo) <= 2e-5 * abs(vo) and relerr(g, go) < 5e-5
+    obj.close(); prob.close()
+
+
+def test_lowrank_fused_trajectory_and_unsupported_combinations(avi, ctx):
+    """docs/src/families.md:185-190: LowRankGaussian(mu, ones, zeros(d, 3)) with KLMinRepGradDescent, Adam and
+    ClipScale: 20 fused iterations follow the fp64 oracle; everything outside RepGrad + ClosedFormEntropy is
+    reported as unsupported."""
+    D, r, M, T = 6, 3, 8, 20
+    mu_t, sg_t = np.linspace(-1, 1, D), np.linspace(0.5, 1.5, D)
+    prob, probo = avi.MvNormalDiag(ctx, mu_t, sg_t), Mo.NormalDiag(mu_t, sg_t)
+    q, qo = _lowrank_pair(avi, D, r, zero_factors=True)
+    alg = avi.KLMinRepGradDescent(optimizer=avi.Adam(1e-2), n_samples=M, operator=avi.ClipScale())
+    qa, info, state = avi.optimize(KEY, alg, T, prob, q)
+    rule, op, avg = Op.Adam(1e-2), Op.ClipScale(), Op.PolynomialAveraging()
+    st = Op.sgd_init(qo, rule, avg)
+
+    def grad_fn(params, t):
+        u1, u2 = _lowrank_draws(D, r, M, step=t - 1)
+        v, g, e = O.repgrad_lowrank_value_and_gradient(params, qo, probo, u1, u2)
+        return v, g, dict(elbo=e)
+    elbos = [Op.sgd_step(st, qo, grad_fn, rule, op, avg)["elbo"] for _ in range(T)]
+    lam, lam_avg, _ = state.params()
+    assert np.allclose([i["elbo"] for i in info], elbos, rtol=2e-4, atol=2e-4)
+    assert relerr(lam, st.params) < 1e-4 and relerr(lam_avg, st.avg_st[0]) < 1e-4
+    assert isinstance(qa, avi.MvLocationScaleLowRank) and qa.scale_factors.shape == (D, r)
+    state.close(); state.obj.close()
+    for spec in (avi.ScoreGradELBO(M), avi.RepGradELBO(M, avi.StickingTheLandingEntropy())):
+        with pytest.raises(avi.AviError, match="low-rank"):
+            avi.Objective(KEY, spec, q, prob)
+    with pytest.raises(avi.AviError, match="rank"):
+        avi.Objective(KEY, avi.RepGradELBO(M), avi.LowRankGaussian(q.location, q.scale_diag, np.zeros((D, 33), np.float32)), prob)
+    with pytest.raises(avi.AviError, match="low-rank"):      # (its zero-gradient entropy is rejected first)
+        avi.optimize(KEY, avi.KLMinRepGradProxDescent(optimizer=avi.DoWG(), n_samples=M), 1, prob, q)
+    with pytest.raises(avi.AviError, match="low-rank"):
+        avi.estimate_objective(KEY, alg, q, prob, n_samples=16)
+    prob.close()
