@@ -105,6 +105,7 @@ mutable struct B200ObjState
 end
 family_code(q::MvLocationScale{<:Diagonal}) = 0
 family_code(q::MvLocationScale{<:LowerTriangular}) = 1
+family_code(q::MvLocationScaleLowRank) = 2
 entropy_code(::ClosedFormEntropy) = 0
 entropy_code(::MonteCarloEntropy) = 1
 entropy_code(::StickingTheLandingEntropy) = 2
@@ -115,8 +116,13 @@ function make_state(rng, kind, entropy, n_samples, adtype::AutoB200, q, prob, pa
     eltype(params) === Float32 || throw(ArgumentError("AutoB200 supports Float32 only (got $(eltype(params)))"))
     p, keep = native(prob, adtype.device)
     r = Ref{Ptr{Cvoid}}(C_NULL)
-    check(@ccall(libavi.avi_obj_create(p.c.h::Ptr{Cvoid}, p.h::Ptr{Cvoid}, family_code(q)::Int32, kind::Int32,
-                 entropy::Int32, n_samples::Int32, r::Ptr{Ptr{Cvoid}})::Int32), p.c.h)
+    if q isa MvLocationScaleLowRank   # location_scale_low_rank.jl: lambda = [location; scale_diag; vec(scale_factors)]
+        check(@ccall(libavi.avi_obj_create_lowrank(p.c.h::Ptr{Cvoid}, p.h::Ptr{Cvoid}, size(q.scale_factors, 2)::Int32,
+                     kind::Int32, entropy::Int32, n_samples::Int32, r::Ptr{Ptr{Cvoid}})::Int32), p.c.h)
+    else
+        check(@ccall(libavi.avi_obj_create(p.c.h::Ptr{Cvoid}, p.h::Ptr{Cvoid}, family_code(q)::Int32, kind::Int32,
+                     entropy::Int32, n_samples::Int32, r::Ptr{Ptr{Cvoid}})::Int32), p.c.h)
+    end
     st = B200ObjState(r[], p, keep)
     finalizer(s -> @ccall(libavi.avi_obj_destroy(s.h::Ptr{Cvoid})::Int32), st)
     # the Julia rng is used only to draw the Philox key: same seed => identical run (klminrepgraddescent.jl:40-57)
