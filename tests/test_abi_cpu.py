@@ -122,3 +122,27 @@ def test_host_update_matches_oracle_adam_clip_polyavg():
         assert np.allclose(hu.lam, x, rtol=2e-6, atol=1e-7)
         assert np.allclose(hu.lam_avg, avg_o.value(ast), rtol=1e-5, atol=1e-6)
         assert (hu.lam[D:] >= 0.3).all()
+
+
+def test_lowrank_host_container_matches_oracle_layout():
+    """The host-side MvLocationScaleLowRank container flattens exactly like the oracle's restatement of the Functors
+    order (location, scale_diag, scale_factors column-major; location_scale_low_rank.jl:26) and round-trips."""
+    import numpy as np
+    import advancedvi_jl_b200 as avi
+    from oracle import family as F
+    d, r = 7, 3
+    rng = np.random.default_rng(1)
+    mu, sd, U = (rng.normal(size=d).astype(np.float32), (np.abs(rng.normal(size=d)) + 0.1).astype(np.float32),
+                 rng.normal(size=(d, r)).astype(np.float32))
+    q, qo = avi.LowRankGaussian(mu, sd, U), F.LowRankGaussian(mu, sd, U)
+    lam = q.destructure()
+    assert lam.dtype == np.float32 and lam.shape == (2 * d + d * r,)
+    assert np.array_equal(lam, qo.destructure().astype(np.float32))
+    q2 = q.restructure(lam)
+    assert np.array_equal(q2.location, mu) and np.array_equal(q2.scale_diag, sd) and np.array_equal(q2.scale_factors, U)
+    assert q.rank == r and len(q) == d and np.allclose(q.cov(), qo.cov(), rtol=1e-6)
+    import pytest
+    with pytest.raises(TypeError):
+        avi.LowRankGaussian(mu.astype(np.float64), sd, U)
+    with pytest.raises(ValueError):
+        avi.LowRankGaussian(mu, sd[:-1], U)
