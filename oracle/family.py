@@ -186,6 +186,25 @@ class MvLocationScaleLowRank:
         return gD, gU
 
 
+    # -- Woodbury pieces a device kernel needs for logpdf-based estimators (only r x r systems are solved) --
+    def _capacitance_inv(self):
+        W = self.scale_factors / (self.scale_diag ** 2)[:, None]
+        return W, np.linalg.inv(np.eye(self.rank) + self.scale_factors.T @ W)
+
+    def cov_solve(self, R: np.ndarray) -> np.ndarray:
+        """Sigma^-1 R for columns R (d, M): D^-2 R - W B^-1 U' D^-2 R with W = D^-2 U, B = I + U' W."""
+        W, Binv = self._capacitance_inv()
+        DR = R / (self.scale_diag ** 2)[:, None]
+        return DR - W @ (Binv @ (self.scale_factors.T @ DR))
+
+    def cov_inv_diag_and_factor(self):
+        """diag(Sigma^-1) and Sigma^-1 U (= W B^-1): what d log q / d scale_diag, d scale_factors need."""
+        W, Binv = self._capacitance_inv()
+        SinvU = W @ Binv
+        diag = 1.0 / self.scale_diag ** 2 - np.einsum("ik,ik->i", SinvU, W)
+        return diag, SinvU
+
+
 def LowRankGaussian(mu, D, U) -> MvLocationScaleLowRank:
     """location_scale_low_rank.jl:119-135."""
     return MvLocationScaleLowRank(mu, D, U)

@@ -178,19 +178,64 @@ def gaussian_expectation_gradient_and_hessian(q: MvLocationScale, prob, u):
     return logpi_avg, grad, hess
 
 
-def repgrad_lowrank_value_and_gradient(params, q_template, prob, u_diag, u_fact):
-    """estimate_gradient! for RepGradELBO + ClosedFormEntropy over MvLocationScaleLowRank
-    (repgradelbo.jl:142-177 with the sampling path of location_scale_low_rank.jl:79-86), closed form:
-    with g_m = grad log pi(z_m): d/d location = -mean g, d/d scale_diag = -mean(g .* u_diag) - dH/dD,
-    d/d scale_factors = -mean(g u_fact') - dH/dU (dH: MvLocationScaleLowRank.entropy_gradient).
-    Returns (value = -ELBO, gradient in destructure order, elbo).  Groundwork for SURVEY 8f rank 4."""
+def _lowrank_logq_param_grads(q, Z):
+    """Per-sample gradients of log q_lambda(z) w.r.t. lambda at FIXED z for the low-rank Gaussian:
+    w = Sigma^-1 (z - mu);  d/d mu = w,  d/d D_i = D_i (w_i^2 - (Sigma^-1)_ii),  d/d U = w (w' U) - Sigma^-1 U.
+    Returns (w (d, M), gD (d, M), gU (d, r, M))."""
+    w = q.cov_solve(Z - q.location[:, None])
+    sinv_diag, sinv_U = q.cov_inv_diag_and_factor()
+    gD = q.scale_diag[:, None] * (w * w - sinv_diag[:, None])
+    gU = w[:, None, :] * (q.scale_factors.T @ w)[None, :, :] - sinv_U[:, :, None]
+    return w, gD, gU
+
+
+def repgrad_lowrank_value_and_gradient(params, q_template, prob, u_diag, u_fact, entropy="ClosedFormEntropy"):
+    """estimate_gradient! for RepGradELBO over MvLocationScaleLowRank (repgradelbo.jl:142-177 with the sampling
+    path of location_scale_low_rank.jl:79-86), closed forms.  With g_m = grad log pi(z_m) and the path Jacobian
+    dz/d(location, scale_diag, scale_factors) = (I, diag(u_diag), . u_fact'):
+      ClosedFormEntropy          d = -mean J' g - dH          (dH: MvLocationScaleLowRank.entropy_gradient)
+      StickingTheLandingEntropy  d = -mean J' (g + w),  w = Sigma^-1 (z - mu)   (q frozen inside log q, entropy.jl:59-65)
+      MonteCarloEntropy          the STL path term plus mean d log q / d lambda at fixed z (entropy.jl:42-46)
+    Returns (value = -ELBO estimate, gradient in destructure order, elbo).  The device path implements the first
+    (family_lr.cu); the other two are groundwork."""
     q = q_template.restructure(params)
     M = u_diag.shape[1]
     Z = q.rand_from_eps(u_diag, u_fact)
     logp, G = prob.logdensity_and_gradient_batch(Z)
-    elbo = float(np.mean(logp) + q.entropy())
-    gD_H, gU_H = q.entropy_gradient()
-    g_loc = -np.mean(G, axis=1)
-    g_diag = -np.mean(G * u_diag, axis=1) - gD_H
-    g_fact = -(G @ u_fact.T) / M - gU_H
+    if entropy == "ClosedFormEntropy":
+        ent = q.entropy()
+        gD_H, gU_H = q.entropy_gradient()
+        Wg = G
+        g_loc_x, g_diag_x, g_fact_x = 0.0, -gD_H, -gU_H
+    elif entropy in ("StickingTheLandingEntropy", "MonteCarloEntropy"):
+        ent = -float(np.mean(q.logpdf(Z)))
+        w, gD, gU = _lowrank_logq_param_grads(q, Z)
+        Wg = G + w
+        if entropy == "MonteCarloEntropy":   # + d/d lambda of mean log q_lambda(z) at fixed z (the value has -H_MC = +mean log q)
+            g_loc_x, g_diag_x, g_fact_x = np.mean(w, axis=1), np.mean(gD, axis=1), np.mean(gU, axis=2)
+        else:
+            g_loc_x, g_diag_x, g_fact_x = 0.0, 0.0, 0.0
+    else:
+        raise ValueError(entropy)
+    elbo = float(np.mean(logp) + ent)
+    g_loc = -np.mean(Wg, axis=1) + g_loc_x
+    g_diag = -np.mean(Wg * u_diag, axis=1) + g_diag_x
+    g_fact = -(Wg @ u_fact.T) / M + g_fact_x
     return -elbo, np.concatenate([g_loc, g_diag, g_fact.reshape(-1, order="F")]), elbo
+
+
+def scoregrad_lowrank_value_and_gradient(params, q_template, prob, u_diag, u_fact):
+    """estimate_gradient! for ScoreGradELBO (VarGrad, scoregradelbo.jl:87-117) over MvLocationScaleLowRank:
+    f_m = log q_lambda(z_m) - log pi(z_m) with z, log pi constants; value = (mean f^2 - (mean f)^2) / 2,
+    gradient = mean (f_m - fbar) d log q_lambda(z_m) / d lambda.  Returns (value, gradient, elbo).  Groundwork."""
+    q = q_template.restructure(params)
+    Z = q.rand_from_eps(u_diag, u_fact)
+    logp = prob.logdensity_batch(Z) if hasattr(prob, "logdensity_batch") else prob.logdensity_and_gradient_batch(Z)[0]
+    f = q.logpdf(Z) - logp
+    c = f - np.mean(f)
+    w, gD, gU = _lowrank_logq_param_grads(q, Z)
+    g_loc = np.mean(c[None, :] * w, axis=1)
+    g_diag = np.mean(c[None, :] * gD, axis=1)
+    g_fact = np.mean(c[None, None, :] * gU, axis=2)
+    value = (np.mean(f * f) - np.mean(f) ** 2) / 2
+    return value, np.concatenate([g_loc, g_diag, g_fact.reshape(-1, order="F")]), float(np.mean(logp - q.logpdf(Z)))

@@ -103,3 +103,61 @@ def test_per_sample_and_batched_evaluation_agree():
     a = O.repgrad_value_and_gradient(q.destructure(), q, prob, eps, "ClosedFormEntropy", per_sample=True)
     b = O.repgrad_value_and_gradient(q.destructure(), q, prob, eps, "ClosedFormEntropy", per_sample=False)
     assert np.isclose(a[0], b[0], rtol=1e-13) and np.allclose(a[1], b[1], rtol=1e-12)
+
+
+# --- low-rank family: logpdf-based estimators (groundwork) ---------------------------------------
+def _lowrank_setup():
+    from oracle import family as F, models as Mo, philox as P
+    d, r, M = 6, 2, 5
+    prob = Mo.NormalDiag(np.linspace(-1, 1, d), np.linspace(0.5, 1.5, d))
+    q = F.LowRankGaussian(0.1 * np.arange(d), 0.5 + 0.1 * np.arange(d), 0.3 * P.normal_matrix(61, 0, d, r))
+    return q, prob, P.normal_matrix(62, 0, d, M), P.normal_matrix(63, 0, r, M)
+
+
+def _fd(f, x, h=1e-6):
+    return np.array([(f(x + h * e) - f(x - h * e)) / (2 * h) for e in np.eye(len(x))])
+
+
+def test_lowrank_woodbury_pieces():
+    q, _, u1, u2 = _lowrank_setup()
+    Sigma = q.cov()
+    R = q.rand_from_eps(u1, u2) - q.location[:, None]
+    assert np.allclose(q.cov_solve(R), np.linalg.solve(Sigma, R), rtol=1e-10)
+    diag, SinvU = q.cov_inv_diag_and_factor()
+    assert np.allclose(diag, np.diag(np.linalg.inv(Sigma)), rtol=1e-10)
+    assert np.allclose(SinvU, np.linalg.solve(Sigma, q.scale_factors), rtol=1e-10)
+
+
+@pytest.mark.parametrize("entropy", ["StickingTheLandingEntropy", "MonteCarloEntropy"])
+def test_lowrank_repgrad_logpdf_entropies_vs_fd(entropy):
+    """Closed forms vs central differences of the forward closure the reference differentiates
+    (repgradelbo.jl:142-149 with entropy.jl:42-46 / :59-65: q frozen inside log q for STL)."""
+    from oracle import objectives as O
+    q, prob, u1, u2 = _lowrank_setup()
+    lam = q.destructure()
+    v, g, e = O.repgrad_lowrank_value_and_gradient(lam, q, prob, u1, u2, entropy)
+
+    def forward(x):
+        qx = q.restructure(x)
+        Z = qx.rand_from_eps(u1, u2)
+        logp, _ = prob.logdensity_and_gradient_batch(Z)
+        q_in_logpdf = q if entropy == "StickingTheLandingEntropy" else qx    # q_stop vs live q
+        return -(np.mean(logp) - np.mean(q_in_logpdf.logpdf(Z)))
+    assert np.isclose(v, forward(lam))
+    assert np.allclose(g, _fd(forward, lam), rtol=2e-6, atol=2e-7)
+
+
+def test_lowrank_scoregrad_vs_fd():
+    from oracle import objectives as O
+    q, prob, u1, u2 = _lowrank_setup()
+    lam = q.destructure()
+    v, g, e = O.scoregrad_lowrank_value_and_gradient(lam, q, prob, u1, u2)
+    Z = q.rand_from_eps(u1, u2)
+    logp, _ = prob.logdensity_and_gradient_batch(Z)
+
+    def forward(x):                       # scoregradelbo.jl:87-94: samples and log pi are constants
+        f = q.restructure(x).logpdf(Z) - logp
+        return (np.mean(f * f) - np.mean(f) ** 2) / 2
+    assert np.isclose(v, forward(lam))
+    assert np.allclose(g, _fd(forward, lam), rtol=2e-6, atol=2e-7)
+    assert np.isclose(e, np.mean(logp - q.logpdf(Z)))
