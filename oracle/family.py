@@ -14,16 +14,92 @@ LOG2PI = float(np.log(2.0 * np.pi))
 H0 = 0.5 * (LOG2PI + 1.0)   # entropy(Normal(0,1)), Appendix B of SURVEY.md
 
 
+class StdNormal:
+    """Normal(0, 1): the base distribution of MeanFieldGaussian / FullRankGaussian / LowRankGaussian."""
+    name = "Normal(0,1)"
+
+    def mean(self): return 0.0
+    def var(self): return 1.0
+    def entropy(self): return H0
+    def logpdf(self, u): return -0.5 * (u * u + LOG2PI)
+    def score(self, u): return -u                      # d/du logpdf
+    def from_normal(self, eps): return eps             # sampling transform of standard normal draws
+
+
+class NormalDist(StdNormal):
+    """Normal(m, s) base (the :gaussian_nonstd case of test/families/location_scale.jl:22-25)."""
+
+    def __init__(self, m, s):
+        self.m, self.s, self.name = float(m), float(s), f"Normal({m},{s})"
+
+    def mean(self): return self.m
+    def var(self): return self.s ** 2
+    def entropy(self): return H0 + float(np.log(self.s))
+    def logpdf(self, u): return -0.5 * (((u - self.m) / self.s) ** 2 + LOG2PI) - np.log(self.s)
+    def score(self, u): return -(u - self.m) / self.s ** 2
+    def from_normal(self, eps): return self.m + self.s * eps
+
+
+class LaplaceDist(StdNormal):
+    """Laplace(0, 1) base (docs/src/families.md:88-101): density exp(-|u|) / 2."""
+    name = "Laplace(0,1)"
+
+    def mean(self): return 0.0
+    def var(self): return 2.0
+    def entropy(self): return 1.0 + float(np.log(2.0))
+    def logpdf(self, u): return -np.abs(u) - np.log(2.0)
+    def score(self, u): return -np.sign(u)
+
+    def from_normal(self, eps):
+        """Inverse-CDF transform of the uniform Phi(eps) (a device sampler would start from the Philox uniform)."""
+        from scipy.special import ndtr
+        p = ndtr(eps) - 0.5
+        return -np.sign(p) * np.log1p(-2.0 * np.abs(p))
+
+
+class TDistBase(StdNormal):
+    """TDist(nu) base (docs/src/families.md:72-86)."""
+
+    def __init__(self, nu):
+        self.nu, self.name = float(nu), f"TDist({nu})"
+
+    def mean(self): return 0.0
+    def var(self): return self.nu / (self.nu - 2.0) if self.nu > 2 else np.inf
+
+    def entropy(self):
+        from scipy.special import betaln, digamma
+        nu = self.nu
+        return float((nu + 1) / 2 * (digamma((nu + 1) / 2) - digamma(nu / 2)) + 0.5 * np.log(nu) + betaln(nu / 2, 0.5))
+
+    def logpdf(self, u):
+        from scipy.special import gammaln
+        nu = self.nu
+        c = gammaln((nu + 1) / 2) - gammaln(nu / 2) - 0.5 * np.log(nu * np.pi)
+        return c - (nu + 1) / 2 * np.log1p(u * u / nu)
+
+    def score(self, u): return -(self.nu + 1.0) * u / (self.nu + u * u)
+
+    def from_normal(self, eps):
+        from scipy.special import ndtr
+        from scipy.stats import t as student_t
+        return student_t.ppf(ndtr(eps), self.nu)
+
+
+STD_NORMAL = StdNormal()
+
+
 class MvLocationScale:
-    """src/families/location_scale.jl:15-19 with dist = Normal(0, 1).
+    """src/families/location_scale.jl:15-19; dist = Normal(0, 1) unless another base distribution is given
+    (`MvLocationScale(location, scale, dist)`; the device path implements Normal(0, 1) only).
 
     `scale` is a 1-D array (Diagonal -> MeanFieldGaussian, :139-141) or a 2-D lower
     triangular array (LowerTriangular -> FullRankGaussian, :124-128).
     """
 
-    def __init__(self, location, scale):
+    def __init__(self, location, scale, dist=STD_NORMAL):
         self.location = np.array(location, copy=True)
         self.scale = np.array(scale, copy=True)
+        self.dist = dist
         assert self.scale.ndim in (1, 2)
         if self.scale.ndim == 2:
             assert self.scale.shape == (len(self.location),) * 2
@@ -58,14 +134,14 @@ class MvLocationScale:
         flat = np.asarray(flat)
         if self.is_meanfield:
             assert flat.shape == (2 * D,)
-            return MvLocationScale(flat[:D], flat[D:])
+            return MvLocationScale(flat[:D], flat[D:], self.dist)
         assert flat.shape == (D + D * D,)
-        return MvLocationScale(flat[:D], flat[D:].reshape(D, D, order="F"))
+        return MvLocationScale(flat[:D], flat[D:].reshape(D, D, order="F"), self.dist)
 
     # -- StatsBase.entropy (location_scale.jl:52-57) -------------------------------
     def entropy(self):
         D = len(self.location)
-        return D * self.dtype.type(H0) + np.sum(np.log(self.scale_diag()))
+        return D * self.dtype.type(self.dist.entropy()) + np.sum(np.log(self.scale_diag()))
 
     # -- Distributions.logpdf (location_scale.jl:59-63) ----------------------------
     def standardize(self, z: np.ndarray) -> np.ndarray:
@@ -79,7 +155,7 @@ class MvLocationScale:
     def logpdf(self, z: np.ndarray):
         """sum(logpdf(Normal(0,1), z_std)) - logdet(scale); vectorised over columns."""
         u = self.standardize(z)
-        return np.sum(-0.5 * (u * u + LOG2PI), axis=0) - np.sum(np.log(self.scale_diag()))
+        return np.sum(self.dist.logpdf(u), axis=0) - np.sum(np.log(self.scale_diag()))
 
     # -- Distributions.rand (location_scale.jl:71-87) ------------------------------
     def rand_from_eps(self, eps: np.ndarray) -> np.ndarray:
@@ -90,17 +166,20 @@ class MvLocationScale:
 
     # -- mean / var / cov (location_scale.jl:98-113), mean(Normal(0,1)) = 0, var = 1 --
     def mean(self):
-        return self.location.copy()
+        if self.dist.mean() == 0.0:
+            return self.location.copy()
+        m = np.full(len(self.location), self.dist.mean())
+        return self.location + (self.scale * m if self.is_meanfield else self.scale @ m)   # :98-101
 
     def var(self):
         if self.is_meanfield:
-            return self.scale ** 2
-        return np.sum(self.scale ** 2, axis=1)          # diag(C C')
+            return self.dist.var() * self.scale ** 2
+        return self.dist.var() * np.sum(self.scale ** 2, axis=1)          # var(dist) diag(C C')
 
     def cov(self):
         if self.is_meanfield:
-            return np.diag(self.scale ** 2)
-        return self.scale @ self.scale.T
+            return self.dist.var() * np.diag(self.scale ** 2)
+        return self.dist.var() * (self.scale @ self.scale.T)
 
 
 def MeanFieldGaussian(mu, diag_scale) -> MvLocationScale:

@@ -239,3 +239,39 @@ def scoregrad_lowrank_value_and_gradient(params, q_template, prob, u_diag, u_fac
     g_fact = np.mean(c[None, None, :] * gU, axis=2)
     value = (np.mean(f * f) - np.mean(f) ** 2) / 2
     return value, np.concatenate([g_loc, g_diag, g_fact.reshape(-1, order="F")]), float(np.mean(logp - q.logpdf(Z)))
+
+
+def repgrad_general_base_value_and_gradient(params, q_template: MvLocationScale, prob, u: np.ndarray, entropy: str):
+    """RepGradELBO over MvLocationScale(location, scale, dist) with a NON-Gaussian base distribution
+    (docs/src/families.md:72-101: TDist, Laplace): u are draws of the base distribution, z = scale u + location.
+    Closed forms: the energy part is A.1 with eps -> u; ClosedFormEntropy adds -grad logdet(scale);
+    StickingTheLandingEntropy replaces g by g - grad_z log q_stop(z) = g - scale^-T score(u), score = d log phi / du
+    (for Normal(0, 1): score = -u, i.e. the g + L^-T eps of A.3).  Groundwork: no device path."""
+    q = q_template.restructure(params)
+    M = u.shape[1]
+    Z = q.rand_from_eps(u)
+    logp, G = prob.logdensity_and_gradient_batch(Z)
+    sd = q.scale_diag()
+    if entropy == "ClosedFormEntropy":
+        ent, W = q.entropy(), G
+    elif entropy == "StickingTheLandingEntropy":
+        ent = -float(np.mean(q.logpdf(Z)))
+        sc = q.dist.score(u)
+        if q.is_meanfield:
+            W = G - sc / sd[:, None]
+        else:
+            from scipy.linalg import solve_triangular
+            W = G - solve_triangular(q.scale.T, sc, lower=False)
+    else:
+        raise ValueError(entropy)
+    value = -(np.mean(logp) + ent)
+    g_mu = -np.mean(W, axis=1)
+    if q.is_meanfield:
+        g_sc = -np.mean(W * u, axis=1)
+        inv = 1.0 / sd
+    else:
+        g_sc = -np.tril(W @ u.T) / M
+        inv = np.diag(1.0 / sd)
+    if entropy == "ClosedFormEntropy":
+        g_sc = g_sc - inv
+    return value, _scale_grad_pack(q, g_mu, g_sc), -value

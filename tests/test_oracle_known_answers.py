@@ -322,3 +322,66 @@ def test_lowrank_repgrad_closed_form_vs_finite_differences():
     fd = np.array([(f(lam + h * np.eye(len(lam))[k]) - f(lam - h * np.eye(len(lam))[k])) / (2 * h) for k in range(len(lam))])
     assert np.allclose(g, fd, rtol=1e-6, atol=1e-7)
     assert np.isclose(v, -e)
+
+
+# --- non-standard / non-Gaussian base distributions (groundwork for SURVEY 8f rank 4: oracle only) -----------------
+@pytest.mark.parametrize("covtype", ["meanfield", "fullrank"])
+def test_family_nonstandard_gaussian_base(covtype):
+    """location_scale.jl (test) :22-31, basedist = :gaussian_nonstd: MvLocationScale(location, scale, Normal(3, 3))
+    equals MvNormal(location + scale * fill(3, d), 9 scale scale')."""
+    d = 10
+    loc = P.normal_matrix(71, 0, d, 1)[:, 0]
+    Ld = np.tril(np.eye(d) + np.ones((d, d)) / 2)
+    scale = np.ones(d) if covtype == "meanfield" else Ld
+    q = F.MvLocationScale(loc, scale, F.NormalDist(3.0, 3.0))
+    C = np.diag(scale) if covtype == "meanfield" else scale
+    ref = stats.multivariate_normal(loc + C @ np.full(d, 3.0), 9.0 * C @ C.T)
+    z = q.rand_from_eps(q.dist.from_normal(P.normal_matrix(72, 0, d, 6)))
+    assert np.allclose(q.logpdf(z), ref.logpdf(z.T), rtol=1e-10)
+    assert np.isclose(q.entropy(), ref.entropy(), rtol=1e-12)
+    assert np.allclose(q.mean(), ref.mean) and np.allclose(q.cov(), ref.cov) and np.allclose(q.var(), np.diag(ref.cov))
+
+
+@pytest.mark.parametrize("dist,ref", [(F.LaplaceDist(), stats.laplace()), (F.TDistBase(5.0), stats.t(5.0))])
+def test_base_distributions_against_scipy(dist, ref):
+    """Laplace() and TDist(nu) bases (docs/src/families.md:72-101): logpdf, entropy, variance, score and the
+    sampling transform against scipy."""
+    u = np.linspace(-4, 4, 41)
+    assert np.allclose(dist.logpdf(u), ref.logpdf(u), rtol=1e-12)
+    assert np.isclose(dist.entropy(), ref.entropy(), rtol=1e-12) and np.isclose(dist.var(), ref.var())
+    h = 1e-6
+    mid = u[np.abs(u) > 1e-3]
+    assert np.allclose(dist.score(mid), (dist.logpdf(mid + h) - dist.logpdf(mid - h)) / (2 * h), rtol=1e-5, atol=1e-7)
+    x = dist.from_normal(P.normal_matrix(73, 0, 1, 10 ** 6)[0])
+    assert abs(x.mean()) < 1e-2 and np.isclose(x.var(), ref.var(), rtol=3e-2)
+    assert stats.kstest(x[:20000], ref.cdf).pvalue > 1e-3
+
+
+@pytest.mark.parametrize("covtype", ["meanfield", "fullrank"])
+@pytest.mark.parametrize("dist", [F.LaplaceDist(), F.TDistBase(5.0)], ids=["laplace", "tdist5"])
+@pytest.mark.parametrize("entropy", ["ClosedFormEntropy", "StickingTheLandingEntropy"])
+def test_nongaussian_base_repgrad_closed_form_vs_fd(covtype, dist, entropy):
+    """Closed-form RepGradELBO gradient for Student-t / Laplace location-scale families vs central differences of
+    the forward closure (q frozen inside log q for STL)."""
+    d, M = 5, 6
+    prob = Mo.NormalDiag(np.linspace(-1, 1, d), np.linspace(0.5, 1.5, d))
+    scale = 0.5 + 0.1 * np.arange(d) if covtype == "meanfield" else np.tril(0.05 * np.ones((d, d))) + np.diag(0.5 + 0.1 * np.arange(d))
+    q = F.MvLocationScale(0.1 * np.arange(d), scale, dist)
+    u = dist.from_normal(P.normal_matrix(74, 0, d, M))
+    lam = q.destructure()
+    v, g, e = O.repgrad_general_base_value_and_gradient(lam, q, prob, u, entropy)
+
+    def forward(x):
+        qx = q.restructure(x)
+        Z = qx.rand_from_eps(u)
+        logp, _ = prob.logdensity_and_gradient_batch(Z)
+        ent = qx.entropy() if entropy == "ClosedFormEntropy" else -np.mean(q.logpdf(Z))
+        return -(np.mean(logp) + ent)
+    hh = 1e-6
+    fd = np.array([(forward(lam + hh * ek) - forward(lam - hh * ek)) / (2 * hh) for ek in np.eye(len(lam))])
+    if covtype == "fullrank":   # the strict upper triangle is not a parameter of a LowerTriangular scale
+        D = d
+        mask = np.concatenate([np.ones(D, bool), np.tril(np.ones((D, D), bool)).reshape(-1, order="F")])
+        fd = fd * mask
+    assert np.isclose(v, forward(lam))
+    assert np.allclose(g, fd, rtol=5e-6, atol=5e-7)
