@@ -808,11 +808,32 @@ def estimate_objective(rng, alg_or_obj, q: MvLocationScale, prob: _Problem, *, n
     """estimate_objective(rng, alg, q, prob; n_samples, entropy) -> -ELBO estimate.
     For an algorithm this is always a fresh RepGradELBO with MonteCarloEntropy, ignoring subsampling
     (src/algorithms/common.jl:29-38); for an objective it is that objective's own estimate
-    (repgradelbo.jl:112-118, scoregradelbo.jl:58-65)."""
+    (repgradelbo.jl:112-118, scoregradelbo.jl:58-65); for a SubsampledObjective the mean of the inner objective's
+    estimates over all length(subsampling) minibatches of one freshly shuffled epoch, short trailing batch included
+    (subsampledobjective.jl:47-58).  Minibatch k draws its samples with key + 1 + k (the reference's rng stream moves
+    on between batches); the target is back on its full data afterwards."""
+    if isinstance(alg_or_obj, SubsampledObjective):
+        sub, inner = alg_or_obj.subsampling, alg_or_obj.objective
+        key = _key_from(rng)
+        st = _sub_init(sub, key)                                           # :51
+        n = n_samples or inner.n_samples
+        spec = inner if entropy is None else RepGradELBO(inner.n_samples, entropy)
+        o = Objective(0, spec if (spec.kind != L.REPGRAD or prob.capability >= 1) else ScoreGradELBO(spec.n_samples), q, prob)
+        total = 0.0
+        try:
+            for k in range(len(sub)):                                      # :52
+                batch, st, _ = _sub_step(sub, st)                          # :53
+                prob.subsample(batch)                                      # :54
+                total += o.estimate_objective((key + 1 + k) & 0xFFFFFFFFFFFFFFFF, q, n, kind=spec.kind,
+                                              entropy=spec.entropy) / len(sub)   # :56
+        finally:
+            prob.subsample(None)
+            o.close()
+        return total
     if isinstance(alg_or_obj, _ParamSpaceSGD):
         spec = RepGradELBO(n_samples or alg_or_obj.objective.n_samples, entropy or MonteCarloEntropy())
     else:
-        spec = alg_or_obj.objective if isinstance(alg_or_obj, SubsampledObjective) else alg_or_obj
+        spec = alg_or_obj
         if entropy is not None:
             spec = RepGradELBO(spec.n_samples, entropy)
     if spec.kind == L.REPGRAD and prob.capability < 1:

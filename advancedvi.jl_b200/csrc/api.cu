@@ -231,12 +231,14 @@ int32_t avi_model_set_gemm_mode(avi_model* model, int32_t gemm_mode) {
 
 int32_t avi_model_logdensity(avi_model* model, const float* Z_dev, int32_t ldz, int32_t M, float* logp_dev) {
     if (!model || !Z_dev || !logp_dev || ldz < model->D || (ldz % 4)) return AVI_ERR_INVALID;
+    model->clear_hook();
     return model->eval(Z_dev, ldz, M, logp_dev, nullptr);
 }
 
 int32_t avi_model_logdensity_and_gradient(avi_model* model, const float* Z_dev, int32_t ldz, int32_t M,
                                           float* logp_dev, float* G_dev) {
     if (!model || !Z_dev || !logp_dev || ldz < model->D || (ldz % 4)) return AVI_ERR_INVALID;
+    model->clear_hook();
     return model->eval(Z_dev, ldz, M, logp_dev, G_dev);
 }
 
@@ -254,6 +256,7 @@ int32_t avi_model_logdensity_and_gradient_host(avi_model* model, const float* Z_
                                           cudaMemcpyHostToDevice, ctx->stream);
         if (e != cudaSuccess) { avi_set_error(ctx, cudaGetErrorString(e)); rc = AVI_ERR_CUDA; }
     }
+    model->clear_hook();
     if (rc == AVI_OK) rc = model->eval(Z, ld, M, lp, G);
     if (rc == AVI_OK) {
         cudaError_t e = cudaMemcpyAsync(logp_host, lp, M * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
@@ -467,7 +470,7 @@ int32_t avi_obj_estimate_gradient(avi_obj* o, const float* lambda_host, int64_t 
     static const bool no_graph = getenv("AVI_NO_GRAPH") && atoi(getenv("AVI_NO_GRAPH")) != 0;
     const bool capturable = !no_graph && !ctx->timing && !o->model->needs_sync_eval() &&
                             !(ctx->nranks > 1 && !ctx->comm_capturable);
-    const int64_t gen = o->generation * 1000003 + o->model->generation;
+    const int64_t gen = avi_graph_key(o, true);
     if (o->eg_exec && o->eg_gen != gen) {
         cudaGraphExecDestroy(o->eg_exec); cudaGraphDestroy(o->eg_graph);
         o->eg_exec = nullptr; o->eg_graph = nullptr; o->eg_calls = 0;
@@ -494,14 +497,14 @@ int32_t avi_obj_estimate_gradient(avi_obj* o, const float* lambda_host, int64_t 
         if (e != cudaSuccess) AVI_FAIL(ctx, AVI_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
         o->eg_graph = g;
         AVI_CUDA(ctx, cudaGraphInstantiate(&o->eg_exec, o->eg_graph, 0));
-        o->eg_gen = o->generation * 1000003 + o->model->generation;
+        o->eg_gen = avi_graph_key(o, true);
         AVI_CUDA(ctx, cudaGraphLaunch(o->eg_exec, ctx->stream));
         ctx->launches += o->eg_launches;
         o->step += 1;
     } else {
         AVI_CHECK(enqueue());   // first call: also sizes every lazily allocated buffer
         o->eg_calls++;
-        o->eg_gen = o->generation * 1000003 + o->model->generation;
+        o->eg_gen = avi_graph_key(o, true);
     }
     if (zero_copy) {
         // completion flag = low 32 bits of the device step counter after this call (== the host mirror o->step)

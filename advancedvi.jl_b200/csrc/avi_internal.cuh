@@ -155,6 +155,10 @@ struct avi_model {
     int capability = 1;
     int64_t generation = 0;   // bumped whenever device buffers are reallocated (captured graphs go stale)
     virtual ~avi_model() {}
+    // identifies the active data view (full data or a minibatch of some size) for captured graphs: switching between
+    // views of the same shape keeps pointers and tensor maps, so graphs are keyed on (generation, view_key)
+    virtual int64_t view_key() const { return -1; }
+    virtual int64_t rows_full() const { return -1; }   // number of data rows minibatch indices may address (-1: n/a)
     // logp[m] = log pi(z_m); G (nullable) = grad log pi(z_m), same layout as Z.
     virtual int32_t eval(const float* Z, int ld, int M, float* logp, float* G) = 0;
     // Fused mean-field path: a1[i] = sum_m G[m][i], a2[i] = sum_m G[m][i] * E[m][i] without
@@ -168,7 +172,9 @@ struct avi_model {
     }
     virtual int32_t set_gemm_mode(int mode) { return AVI_OK; }
     // fills *h and returns true when the next eval / eval_gradsums on these samples may skip its own pass
-    virtual bool sample_hook(int ld, int M, SampleHook* h) { return false; }
+    // (the promise is bound to these samples: Z pointer and count; any other eval ignores and clears it)
+    virtual bool sample_hook(const float* Z, int ld, int M, SampleHook* h) { return false; }
+    virtual void clear_hook() {}
     // Device-side minibatch selection for the fused multi-step loop: the rows of iteration k are
     // idx_dev[k * batch .. (k+1) * batch) with k = st->batch_cursor read ON THE DEVICE.
     virtual int32_t subsample_dev(const int32_t* idx_dev, int64_t batch, const ObjDeviceState* st) {
@@ -273,6 +279,12 @@ struct avi_opt {
     bool call_subsampled = false, use_graph = false;
     int64_t call_batch = 0;
 };
+
+// validity key of a captured graph: buffers of the objective, buffers of the target and (unless the captured work
+// selects its own minibatch view) the active data view
+static inline int64_t avi_graph_key(const avi_obj* o, bool with_view) {
+    return (o->generation * 1000003 + o->model->generation) * 1000003 + (with_view ? o->model->view_key() : -7);
+}
 
 // ---------------------------------------------------------------------------------------------
 // entry points implemented across the .cu files (all enqueue on ctx->stream)

@@ -471,8 +471,11 @@ int32_t avi_objective_local(avi_obj* o, const float* lambda) {
         return AVI_OK;
     }
     SampleHook hook;
-    const bool hooked = o->family == AVI_MEANFIELD && o->model->sample_hook(ld, Mloc, &hook);
-    AVI_CHECK(avi_family_sample(o, lambda, o->Z, o->E, o->esq, Mloc, o->m0, o->d_state, nullptr, hooked ? &hook : nullptr));
+    const bool hooked = o->family == AVI_MEANFIELD && o->model->sample_hook(o->Z, ld, Mloc, &hook);
+    {
+        const int32_t rc_s = avi_family_sample(o, lambda, o->Z, o->E, o->esq, Mloc, o->m0, o->d_state, nullptr, hooked ? &hook : nullptr);
+        if (rc_s != AVI_OK) { o->model->clear_hook(); return rc_s; }
+    }
     const bool rep = o->objective == AVI_REPGRAD;
     const bool stl = o->entropy == AVI_ENT_STL || o->entropy == AVI_ENT_STL_ZEROGRAD;
     const bool rows = o->shard_axis == AVI_SHARD_ROWS && ctx->nranks > 1;

@@ -275,7 +275,8 @@ struct Glm : avi_model {
         avi_free(idx_own); avi_free(R); avi_free(Zt); avi_free(llpart); avi_free(a1p);
         avi_free(slabs); avi_free(pre); avi_free(tickets);
     }
-    bool hooked = false;
+    bool hooked = false;               // the sampling kernel produced Zt / pre for exactly (hooked_Z, hooked_M)
+    const float* hooked_Z = nullptr; int hooked_M = 0;
     unsigned int* tickets = nullptr;   // last-CTA election per coordinate block (fused backward post-processing)
     int cluster_mode = 1;   // 0: never use thread-block clusters (AVI_TC_CLUSTER=0), 1: planner decides
     bool tc_mode() const { return mode != AVI_GEMM_SIMT_FP32; }
@@ -288,13 +289,17 @@ struct Glm : avi_model {
         const double bytes = 4.0 * ((double)n_act * dK + (double)d * nP + (double)capM * ldR);
         return (tc_mode() && !subsampled && bytes < 100e6) ? mode : 0;
     }
-    bool sample_hook(int ld, int M, SampleHook* h) override {
+    int64_t view_key() const override { return subsampled ? (int64_t)n_act : -1; }
+    int64_t rows_full() const override { return n_full; }
+    void clear_hook() override { hooked = false; hooked_Z = nullptr; hooked_M = 0; }
+    bool sample_hook(const float* Z, int ld, int M, SampleHook* h) override {
+        clear_hook();
         if (M <= 0 || ensure(M, ld) != AVI_OK) return false;
         h->kind = 1; h->d = d; h->variant = variant; h->include_prior = include_prior;
         h->Zt = tc_mode() ? Zt : nullptr; h->pre = pre; h->zt_ld = zt_ld; h->zt_seg = x3 ? segd : 0;
         h->tl = ctx->tl;
         if (l2_stream() & 1) { h->pf_ptr = Xr; h->pf_bytes = (unsigned long long)n_act * dK * sizeof(float); }
-        hooked = true;
+        hooked = true; hooked_Z = Z; hooked_M = M;
         return true;
     }
     float likeadj() const {
@@ -330,8 +335,10 @@ struct Glm : avi_model {
     // forward: R <- w * resid, llpart/nparts <- partial log-lik sums
     int32_t forward(const float* Z, int ld, int M, int* nparts, bool want_backward) {
         const float w = likeadj();
-        if (hooked) {
-            hooked = false;   // the sampling kernel already produced Zt and pre for these samples
+        const bool pre_done = hooked && hooked_Z == Z && hooked_M == M;
+        clear_hook();
+        if (pre_done) {
+            // the sampling kernel already produced Zt and pre for exactly these samples
         } else {
             k_glm_pre<<<M, 256, 0, ctx->stream>>>(Z, ld, d, variant, include_prior, tc_mode() ? Zt : nullptr, zt_ld,
                                                   x3 ? segd : 0, pre);
@@ -454,12 +461,13 @@ struct Glm : avi_model {
         k_glm_gather<<<grid, dim3(32, 8), 0, ctx->stream>>>(Xr_full, y_full, dK, d, idx_dev, st, batch, nP_b,
                                                             x3 ? segd : 0, segn_b, Xr_b, Xc_b, y_b);
         AVI_LAUNCHED(ctx);
+        // (buffers and pitches follow the allocated capacity: graphs captured on a view of this shape stay valid; a
+        // different shape is a different view_key())
         Xr = Xr_b; Xc = Xc_b; y = y_b; n_act = batch; nP = nP_b; segn = segn_b; subsampled = true;
-        generation++;   // the active view changed: graphs captured on the previous view are stale
         return AVI_OK;
     }
     int32_t subsample(const int32_t* idx_host, int64_t batch) override {
-        if (!idx_host) { view_full(); generation++; return AVI_OK; }
+        if (!idx_host) { view_full(); return AVI_OK; }
         if (batch <= 0) AVI_FAIL(ctx, AVI_ERR_INVALID, "empty batch");
         for (int64_t j = 0; j < batch; ++j)
             if (idx_host[j] < 0 || idx_host[j] >= n_full) AVI_FAIL(ctx, AVI_ERR_INVALID, "batch index out of range");

@@ -325,6 +325,16 @@ int32_t steps_prepare(avi_opt* op, int32_t n, const int32_t* idx_host, int64_t b
     }
     if (subsampled) {
         const int64_t need = (int64_t)n * batch;
+        // the gather kernel trusts these indices: reject anything outside [0, rows) here (0-based; a Julia caller's
+        // 1:n must be shifted by the glue)
+        const int64_t rows = o->model->rows_full();
+        if (rows >= 0) {
+            if (batch > rows) AVI_FAIL(ctx, AVI_ERR_INVALID, "minibatch larger than the data set");
+            for (int64_t j = 0; j < need; ++j)
+                if (idx_host[j] < 0 || idx_host[j] >= rows)
+                    AVI_FAIL(ctx, AVI_ERR_INVALID, "minibatch index " + std::to_string(idx_host[j]) + " outside [0, " +
+                                                       std::to_string(rows) + ")");
+        }
         if (need > op->idx_cap) {
             AVI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             avi_free(op->idx_dev);
@@ -340,7 +350,7 @@ int32_t steps_prepare(avi_opt* op, int32_t n, const int32_t* idx_host, int64_t b
     static const bool no_graph = getenv("AVI_NO_GRAPH") && atoi(getenv("AVI_NO_GRAPH")) != 0;
     op->use_graph = !no_graph && !ctx->timing && !o->model->needs_sync_eval() && !(ctx->nranks > 1 && !ctx->comm_capturable);
     if (op->use_graph) {
-        const int64_t gen = o->generation * 1000003 + o->model->generation;
+        const int64_t gen = avi_graph_key(o, !subsampled);
         if (op->graph_exec && (op->graph_gen != gen || op->graph_subsampled != subsampled || op->graph_batch != batch))
             drop_graph(op);
         if (!op->graph_exec) {
@@ -374,7 +384,7 @@ int32_t steps_prepare(avi_opt* op, int32_t n, const int32_t* idx_host, int64_t b
             static const int unroll = getenv("AVI_GRAPH_UNROLL") ? std::max(1, atoi(getenv("AVI_GRAPH_UNROLL"))) : 8;
             op->graph_unroll = subsampled ? 1 : unroll;
             if (op->graph_unroll > 1) AVI_CHECK(capture(op->graph_unroll, &op->graph_u, &op->graph_u_exec));
-            op->graph_gen = o->generation * 1000003 + o->model->generation;
+            op->graph_gen = avi_graph_key(o, !subsampled);
             op->graph_subsampled = subsampled; op->graph_batch = batch;
         }
     }
@@ -402,8 +412,13 @@ int32_t steps_finish(avi_opt* op, float* value_host, float* elbo_host, int32_t* 
     avi_obj* o = op->obj;
     avi_ctx* ctx = op->ctx;
     const int n = op->call_enqueued;
-    op->call_cap = 0; op->call_enqueued = 0;
+    const bool was_subsampled = op->call_subsampled;
+    op->call_cap = 0; op->call_enqueued = 0; op->call_subsampled = false;
     if (n_done) *n_done = 0;
+    // AdvancedVI.subsample(prob, batch) returns a NEW problem and never alters `prob` (src/AdvancedVI.jl:303-313):
+    // after a subsampled run the target is back on its full data (host-side view switch only; the enqueued work
+    // carries its own pointers)
+    if (was_subsampled) AVI_CHECK(o->model->subsample(nullptr, 0));
     if (n <= 0) return AVI_OK;
     ObjDeviceState hs{};
     AVI_CUDA(ctx, cudaMemcpyAsync(op->h_trace, op->trace, 2 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
@@ -485,11 +500,18 @@ int32_t avi_opt_create(avi_obj* obj, int32_t rule, const float* hyper, int32_t n
         double nrm = 0.0;
         for (int64_t p = 0; p < P; ++p) nrm += (double)lambda0_host[p] * lambda0_host[p];
         sc[SC_R] = op->hyper[0] * (1.0f + (float)std::sqrt(nrm));   // rules.jl:21-23, :52-54
-        avi_copy(ctx, op->m1, lambda0_host, (size_t)P * sizeof(float), cudaMemcpyHostToDevice);   // x0
     }
-    avi_copy(ctx, op->lam, lambda0_host, (size_t)P * sizeof(float), cudaMemcpyHostToDevice);
-    avi_copy(ctx, op->avg, lambda0_host, (size_t)P * sizeof(float), cudaMemcpyHostToDevice);
-    avi_copy(ctx, op->sc, sc, sizeof(sc), cudaMemcpyHostToDevice);
+    cudaError_t ce = cudaSuccess;
+    if (rule == AVI_RULE_DOG || rule == AVI_RULE_DOWG)
+        ce = avi_copy(ctx, op->m1, lambda0_host, (size_t)P * sizeof(float), cudaMemcpyHostToDevice);   // x0
+    if (ce == cudaSuccess) ce = avi_copy(ctx, op->lam, lambda0_host, (size_t)P * sizeof(float), cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) ce = avi_copy(ctx, op->avg, lambda0_host, (size_t)P * sizeof(float), cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) ce = avi_copy(ctx, op->sc, sc, sizeof(sc), cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) {
+        avi_set_error(ctx, std::string("avi_opt_create: initial state upload: ") + cudaGetErrorString(ce));
+        avi_opt_destroy(op);
+        return AVI_ERR_CUDA;
+    }
     *out = op;
     return AVI_OK;
 }
