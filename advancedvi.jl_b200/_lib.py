@@ -56,6 +56,7 @@ SIGNATURES = {
     "avi_ctx_timing_get": (C.c_int32, [vp, C.c_char_p, C.POINTER(C.c_double), c_i64_p]),
     "avi_comm_buffer": (C.c_int32, [vp, C.c_int64, C.c_char_p]),
     "avi_comm_connect": (C.c_int32, [vp, C.c_int32, C.c_int32, C.c_char_p]),
+    "avi_comm_disconnect": (C.c_int32, [vp]),
     "avi_model_mvnormal_diag_create": (C.c_int32, [vp, c_float_p, c_float_p, C.c_int32, C.POINTER(vp)]),
     "avi_model_glm_create": (C.c_int32, [vp, c_float_p, c_float_p, C.c_int64, C.c_int32, C.c_int64, C.c_int32,
                                          C.c_int32, C.c_int32, C.POINTER(vp)]),
@@ -65,6 +66,7 @@ SIGNATURES = {
     "avi_model_dimension": (C.c_int32, [vp]),
     "avi_model_capability": (C.c_int32, [vp]),
     "avi_model_set_gemm_mode": (C.c_int32, [vp, C.c_int32]),
+    "avi_model_set_fused_step": (C.c_int32, [vp, C.c_int32]),
     "avi_model_logdensity": (C.c_int32, [vp, vp, C.c_int32, C.c_int32, vp]),
     "avi_model_logdensity_and_gradient": (C.c_int32, [vp, vp, C.c_int32, C.c_int32, vp, vp]),
     "avi_model_logdensity_and_gradient_host": (C.c_int32, [vp, c_float_p, C.c_int32, c_float_p, c_float_p]),

@@ -118,6 +118,11 @@ class Context:
         L.check(L.lib.avi_comm_connect(self.h, rank, nranks, b"".join(handles)), self.h)
         self.rank, self.nranks = rank, nranks
 
+    def disconnect_peers(self):
+        """Unmap the peers' exchange buffers; call on every rank and synchronise the ranks before re-connecting."""
+        L.check(L.lib.avi_comm_disconnect(self.h), self.h)
+        self.rank, self.nranks = 0, 1
+
     def close(self):
         if self.h:
             L.lib.avi_ctx_destroy(self.h)
@@ -209,6 +214,10 @@ class LogReg(_Problem):
 
     def set_data_shard(self, nshards: int, rows_global: int, include_prior: bool):
         L.check(L.lib.avi_model_set_data_shard(self.h, nshards, rows_global, int(include_prior)), self.ctx.h)
+
+    def set_fused_step(self, mode: int):
+        """0: one kernel per stage, 1: library default, 2: always the single whole-iteration kernel."""
+        L.check(L.lib.avi_model_set_fused_step(self.h, int(mode)), self.ctx.h)
 
 
 class GaussGLM(LogReg):

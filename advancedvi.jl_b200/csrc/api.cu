@@ -9,6 +9,7 @@
 
 #include "avi_internal.cuh"
 #include "device_utils.cuh"
+#include "step_fused.cuh"
 
 static thread_local std::string g_create_error;
 
@@ -227,6 +228,12 @@ int32_t avi_model_dimension(const avi_model* model) { return model ? model->D : 
 int32_t avi_model_capability(const avi_model* model) { return model ? model->capability : -1; }
 int32_t avi_model_set_gemm_mode(avi_model* model, int32_t gemm_mode) {
     return model ? model->set_gemm_mode(gemm_mode) : AVI_ERR_INVALID;
+}
+int32_t avi_model_set_fused_step(avi_model* model, int32_t mode) {
+    if (!model) return AVI_ERR_INVALID;
+    const int32_t rc = model->set_fused_step(mode);
+    if (rc != AVI_OK) avi_set_error(model->ctx, "avi_model_set_fused_step: unsupported target or mode");
+    return rc;
 }
 
 int32_t avi_model_logdensity(avi_model* model, const float* Z_dev, int32_t ldz, int32_t M, float* logp_dev) {
@@ -452,6 +459,14 @@ int32_t avi_obj_estimate_gradient(avi_obj* o, const float* lambda_host, int64_t 
     auto enqueue = [&]() -> int32_t {
         if (zero_copy) {
             AVI_CHECK(avi_obj_stage_lambda(o));
+            {   // sample -> contractions -> gradient + completion flag in pinned host memory: one launch (step_fused.cu)
+                StepTail ft{};
+                ft.mode = STEP_TAIL_GRAD_OUT;
+                ft.lam = o->d_lambda; ft.host_out = o->h_grad;
+                bool taken = false;
+                AVI_CHECK(avi_objective_fused(o, o->d_lambda, ft, &taken));
+                if (taken) { o->step += 1; return AVI_OK; }
+            }
             AVI_CHECK(avi_objective_local(o, o->d_lambda));
             AVI_CHECK(avi_objective_finalize(o, o->d_lambda, o->grad, o->out, false, /*fuse_advance=*/true));
             o->step += 1;

@@ -147,6 +147,8 @@ struct SampleHook {
     unsigned long long pf_bytes = 0;
 };
 
+struct FusedStepArgs;   // step_fused.cuh
+
 // Layout shared by every sample-major buffer: row m (one Monte-Carlo sample) holds `ld` floats,
 // coordinate i at [m * ld + i]  ==  a D x M column-major matrix with leading dimension ld.
 struct avi_model {
@@ -183,6 +185,11 @@ struct avi_model {
     // restrict the target to the data rows [r0, r0 + nr) (multi-rank row sharding)
     virtual int32_t set_row_shard(int64_t r0, int64_t nr) { return AVI_ERR_UNSUPPORTED; }
     virtual bool needs_sync_eval() const { return false; }   // host callback: not graph-capturable
+    // The whole mean-field RepGradELBO iteration (sample -> log-density + gradient sums -> [exchange] -> finalize +
+    // update) as ONE kernel launch (step_fused.cuh).  Optional.
+    virtual bool fused_step_ok(int Mloc) const { return false; }
+    virtual int32_t set_fused_step(int mode) { return AVI_ERR_UNSUPPORTED; }
+    virtual int32_t fused_step(const FusedStepArgs& a) { return AVI_ERR_UNSUPPORTED; }
 };
 
 // accumulator layout (floats): 4 vectors of `accv` entries + ACC_NSCAL scalars
@@ -301,6 +308,11 @@ int32_t avi_axpy(avi_ctx* ctx, const float* x, float* y, int64_t n);            
 int32_t avi_colsum_add(avi_ctx* ctx, const float* W, int ld, int Mloc, int D, float* tmp, float* dst);  // dst += column sums
 int32_t avi_obj_stage_lambda(avi_obj* o);   // o->h_lambda (pinned, mapped) -> o->d_lambda by a kernel
 int32_t avi_objective_local(avi_obj* o, const float* lambda);          // sample + model + reduce -> acc
+// The whole iteration as one launch when objective, target and sharding allow it (step_fused.cuh): `tail` carries the
+// mode and the optimiser / host-output pointers, the rest is filled here.  *taken = false: nothing was enqueued, use
+// the multi-kernel path.
+struct StepTail;
+int32_t avi_objective_fused(avi_obj* o, const float* lambda, const StepTail& tail, bool* taken);
 // acc -> grad (skip_fr_matrix: leave the D x D block of a full-rank gradient to the caller's fused update)
 int32_t avi_objective_finalize(avi_obj* o, const float* lambda, float* grad, float* out, bool skip_fr_matrix = false,
                                bool fuse_advance = false);

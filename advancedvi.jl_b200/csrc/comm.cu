@@ -174,6 +174,22 @@ int32_t avi_comm_buffer(avi_ctx* ctx, int64_t max_floats, char* handle_out) {
     return AVI_OK;
 }
 
+// Unmap every peer's buffer (this rank's own allocation stays).  Ranks call this -- and then synchronise among
+// themselves -- before any of them frees or re-creates its buffer, so that no exporter frees memory a peer still maps.
+int32_t avi_comm_disconnect(avi_ctx* ctx) {
+    if (!ctx) return AVI_ERR_INVALID;
+    CommState* cs = state(ctx);
+    if (!cs) return AVI_OK;
+    cudaSetDevice(ctx->device);
+    AVI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int r = 0; r < MAX_RANKS; ++r)
+        if (cs->opened[r]) { cudaIpcCloseMemHandle(cs->peer_base[r]); cs->opened[r] = false; cs->peer_base[r] = nullptr; }
+    cs->connected = false;
+    ctx->comm_capturable = false;
+    ctx->rank = 0; ctx->nranks = 1;
+    return AVI_OK;
+}
+
 // handles: nranks x 64 bytes, entry r exported by rank r (all-gathered by the host: torch.distributed
 // in the Python mirror, MPI.jl / Distributed from Julia).  Entry `rank` is this rank's own.
 int32_t avi_comm_connect(avi_ctx* ctx, int32_t rank, int32_t nranks, const char* handles) {

@@ -18,6 +18,7 @@
 #include "fr_finalize.cuh"
 #include "mf_finalize.cuh"
 #include "tc_common.cuh"
+#include "step_fused.cuh"
 
 namespace {
 
@@ -539,6 +540,31 @@ int32_t avi_objective_local(avi_obj* o, const float* lambda) {
     // sample sharding: the partial sums are the exchange payload
     if (o->shard_axis == AVI_SHARD_SAMPLES && ctx->nranks > 1 && !o->fused_exchange)
         AVI_CHECK(avi_exchange(ctx, o->acc, o->acc_len));
+    return AVI_OK;
+}
+
+int32_t avi_objective_fused(avi_obj* o, const float* lambda, const StepTail& tail, bool* taken) {
+    avi_ctx* ctx = o->ctx;
+    *taken = false;
+    if (o->family != AVI_MEANFIELD || o->objective != AVI_REPGRAD || o->Mloc <= 0) return AVI_OK;
+    if (!o->model->fused_step_ok(o->Mloc)) return AVI_OK;
+    StepTail t = tail;
+    t.acc = o->acc; t.accv = o->accv; t.M = o->M; t.objective = o->objective; t.entropy = o->entropy;
+    t.logp = o->logp; t.grad = o->grad; t.out = o->out; t.acc_len = o->acc_len;
+    t.a.D = o->D;
+    t.comm.nranks = 1; t.xmask = 0;
+    if (ctx->nranks > 1 && o->shard_axis != AVI_SHARD_NONE) {
+        // the exchange runs inside the kernel's tail phase: needs the peer-mapped low-latency lanes of comm.cu
+        if (!avi_comm_peers(ctx, o->acc_len, &t.comm) || t.comm.ll_cap < o->acc_len) return AVI_OK;
+        t.xmask = o->shard_axis == AVI_SHARD_ROWS ? (STEP_X_V01 | STEP_X_S0)
+                                                  : (STEP_X_V01 | STEP_X_V23 | STEP_X_S0 | STEP_X_S1);
+    }
+    if (ceil_div(o->D, ctx->prop.multiProcessorCount) > avi_step_fused_max_per_cta()) return AVI_OK;
+    FusedStepArgs fa{};
+    fa.lambda = lambda; fa.D = o->D; fa.ld = o->ld; fa.m0 = o->m0; fa.Mloc = o->Mloc; fa.st = o->d_state;
+    fa.Z = o->Z; fa.E = o->E; fa.esq = o->esq; fa.logp = o->logp; fa.t = t;
+    AVI_CHECK(o->model->fused_step(fa));
+    *taken = true;
     return AVI_OK;
 }
 

@@ -15,6 +15,7 @@
 #include "avi_internal.cuh"
 #include "device_utils.cuh"
 #include "gemm_tc.cuh"
+#include "step_fused.cuh"
 #include "glm_prior.cuh"
 #include "tc_common.cuh"
 
@@ -273,11 +274,12 @@ struct Glm : avi_model {
     ~Glm() override {
         avi_free(Xr_full); avi_free(Xc_full); avi_free(y_full); avi_free(Xr_b); avi_free(Xc_b); avi_free(y_b);
         avi_free(idx_own); avi_free(R); avi_free(Zt); avi_free(llpart); avi_free(a1p);
-        avi_free(slabs); avi_free(pre); avi_free(tickets);
+        avi_free(slabs); avi_free(pre); avi_free(tickets); avi_free(gbar);
     }
     bool hooked = false;               // the sampling kernel produced Zt / pre for exactly (hooked_Z, hooked_M)
     const float* hooked_Z = nullptr; int hooked_M = 0;
     unsigned int* tickets = nullptr;   // last-CTA election per coordinate block (fused backward post-processing)
+    unsigned long long* gbar = nullptr;   // grid barrier of the fused iteration kernel: [counter, base] (+ [2]: done ticket)
     int cluster_mode = 1;   // 0: never use thread-block clusters (AVI_TC_CLUSTER=0), 1: planner decides
     bool tc_mode() const { return mode != AVI_GEMM_SIMT_FP32; }
     // Both layouts of X fit the 126 MB L2 together with R: each kernel then pulls the next kernel's copy of X
@@ -444,6 +446,60 @@ struct Glm : avi_model {
         return AVI_OK;
     }
 
+    // ---- the whole iteration in one launch (step_fused.cu) ----
+    // AVI_FUSED_STEP: 0 never, 1 (default) for problems where the per-launch fixed costs matter (the large ones keep the
+    // CTA-pair tiles of the stand-alone kernels), 2 always
+    int fused_mode = getenv("AVI_FUSED_STEP") ? atoi(getenv("AVI_FUSED_STEP")) : 1;
+    int32_t set_fused_step(int m) override {
+        if (m < 0 || m > 2) return AVI_ERR_INVALID;
+        if (m != fused_mode) generation++;   // captured iterations were built for the other launch shape
+        fused_mode = m;
+        return AVI_OK;
+    }
+    bool fused_step_ok(int Mloc) const override {
+        if (!fused_mode || !tc_mode() || Mloc <= 0) return false;
+        const double flops = 4.0 * (double)n_act * d * Mloc * (x3 ? 3.0 : 1.0);
+        return fused_mode >= 2 || flops <= 2e11;
+    }
+    int32_t fused_step(const FusedStepArgs& fa) override {
+        const int M = fa.Mloc, ld = fa.ld;
+        AVI_CHECK(ensure(M, ld));
+        clear_hook();
+        StepParams sp{};
+        const float w = likeadj();
+        // forward: logits[m][j] = sum_k Zt[m][k] Xr[j][k]
+        AVI_CHECK(avi_tc_plan(ctx, M, n_act, kf(), false, 0, &sp.f, 0));
+        sp.f.C = R; sp.f.ldc = (int)ldR; sp.f.y = y; sp.f.w = w; sp.f.likelihood = likelihood;
+        sp.f.r_seg = x3 ? (int)segn : 0;
+        sp.f.static_op = subsampled ? 0 : 2;
+        AVI_CHECK(ensure_buf(&llpart, &llpart_cap, (long long)sp.f.n_bchunk * 4 * capM));
+        sp.f.part1 = llpart; sp.f.ldpart = capM;
+        // backward: G[i][m] = sum_j Xc[i][j] R[m][j], reduced against eps in the epilogue
+        AVI_CHECK(avi_tc_plan(ctx, d, M, kb(), true, 0, &sp.b, 0));
+        sp.b.static_op = subsampled ? 0 : 1;
+        const int nslab = sp.b.n_ksplit * sp.b.n_bchunk;
+        const int ldslab = (int)round_up(d, 32);
+        AVI_CHECK(ensure_buf(&a1p, &ap_cap, 2LL * nslab * ldslab));
+        sp.b.E = fa.E; sp.b.lde = ld; sp.b.part1 = a1p; sp.b.part2 = a1p + (size_t)nslab * ldslab; sp.b.ldpart = ldslab;
+        sp.b.post_on = 1; sp.b.post_Z = fa.Z; sp.b.post_pre = reinterpret_cast<const float*>(pre);
+        sp.b.post_llpart = llpart; sp.b.post_nparts = sp.f.n_bchunk * 4; sp.b.post_ldll = capM; sp.b.post_w = w;
+        sp.b.post_logp = fa.logp; sp.b.post_a1 = fa.t.acc; sp.b.post_a2 = fa.t.acc + fa.t.accv; sp.b.post_tickets = tickets;
+        CUtensorMap tmZ, tmXr, tmXc, tmR;
+        AVI_CHECK(avi_tc_make_tmap(ctx, &tmZ, Zt, M, kf(), zt_ld, 128));
+        AVI_CHECK(avi_tc_make_tmap(ctx, &tmXr, Xr, n_act, kf(), dK, sp.f.nt));
+        AVI_CHECK(avi_tc_make_tmap(ctx, &tmXc, Xc, d, kb(), nP, 128));
+        AVI_CHECK(avi_tc_make_tmap(ctx, &tmR, R, M, kb(), ldR, sp.b.nt));
+        sp.do_sample = 1;
+        sp.lambda = fa.lambda; sp.D = fa.D; sp.ld = ld; sp.m0 = fa.m0; sp.Mloc = M; sp.st = fa.st;
+        sp.Z = fa.Z; sp.E = fa.E; sp.esq = fa.esq;
+        sp.d = d; sp.variant = variant; sp.include_prior = include_prior;
+        sp.Zt = Zt; sp.zt_ld = zt_ld; sp.zt_seg = x3 ? segd : 0; sp.pre = reinterpret_cast<float*>(pre);
+        sp.t = fa.t;
+        sp.t.done_ticket = reinterpret_cast<unsigned int*>(gbar + 2);
+        sp.gbar = gbar;
+        return avi_step_fused_launch(ctx, tmZ, tmXr, tmXc, tmR, sp);
+    }
+
     int32_t ensure_batch(long long batch) {
         if (batch <= batch_cap) return AVI_OK;
         avi_free(Xr_b); avi_free(Xc_b); avi_free(y_b);
@@ -514,6 +570,7 @@ int32_t avi_model_glm_make(avi_ctx* ctx, const float* X, const float* y, int64_t
     if (rc == AVI_OK) rc = avi_alloc(ctx, &g->Xc_full, (size_t)d * g->nP_full);
     if (rc == AVI_OK) rc = avi_alloc(ctx, &g->y_full, (size_t)n);
     if (rc == AVI_OK) rc = avi_alloc(ctx, &g->tickets, (size_t)ceil_div(d, 128) + 1);
+    if (rc == AVI_OK) rc = avi_alloc(ctx, &g->gbar, 4);
     if (rc == AVI_OK) rc = avi_alloc(ctx, &tmp, (size_t)n * d);
     if (rc != AVI_OK) { avi_free(tmp); delete g; return rc; }
     cudaError_t e = avi_copy(ctx, tmp, X, (size_t)n * d * sizeof(float), cudaMemcpyHostToDevice);

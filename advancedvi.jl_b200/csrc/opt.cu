@@ -17,6 +17,7 @@
 #include "fr_finalize.cuh"
 #include "mf_finalize.cuh"
 #include "mf_tail.cuh"
+#include "step_fused.cuh"
 
 namespace {
 
@@ -230,6 +231,18 @@ int32_t enqueue_iteration(avi_opt* op, bool subsampled, int64_t batch) {
         }
     }
     UpdArgs a = make_args(op);
+    {   // one launch for the whole iteration when the objective / target / sharding allow it (step_fused.cu)
+        StepTail ft{};
+        ft.mode = STEP_TAIL_UPDATE;
+        ft.lam = op->lam; ft.m1 = op->m1; ft.m2 = op->m2; ft.avg = op->avg; ft.sc = op->sc;
+        ft.trace = op->trace; ft.trace_cap = op->trace_cap; ft.a = a; ft.norm_part = op->norm_part;
+        bool taken = false;
+        AVI_CHECK(avi_objective_fused(o, op->lam, ft, &taken));
+        if (taken) {
+            if (ctx->tl) k_tl_commit<<<1, 32, 0, ctx->stream>>>(ctx->tl, ctx->tl_hist, o->d_state);
+            return AVI_OK;
+        }
+    }
     MfTailArgs tail{};
     tail.tl = ctx->tl; tail.tl_s = 3;
     tail.acc = o->acc; tail.accv = o->accv; tail.M = o->M; tail.objective = o->objective; tail.entropy = o->entropy;

@@ -1,0 +1,643 @@
+// The fused whole-iteration kernel (interface and phase list: step_fused.cuh).
+//
+// One persistent CTA per SM, 640 threads, the warp roles of gemm_tc.cu inside the two contraction phases
+// (warp 0 TMA producer, warp 1 tcgen05.mma issuer, warp 2 TMEM allocator, warps 4-19 epilogue); every warp works in the
+// sample and tail phases.  Phases are separated by grid barriers (monotonic 64-bit counters in global memory; all CTAs
+// are co-resident by construction: grid <= #SMs and the shared-memory footprint admits one CTA per SM).
+//
+// Memory-model notes (each one is load-bearing):
+//  * data produced by generic stores in one phase and consumed by TMA (async proxy) in the next -- Zt after the sample
+//    phase, R after the forward phase -- is published with fence.proxy.async.global by every writer before the barrier
+//    and by the consuming producer thread after it, on top of the barrier's release / acquire at gpu scope;
+//  * data produced in-kernel and consumed by ordinary loads (eps, z, the per-sample prior terms, the partial
+//    log-likelihood sums) is read with ld.global.cg (`COH` in gemm_tc_dev.cuh): never through the read-only path;
+//  * everything a later phase OVERWRITES at the end of the iteration (step counter, optimiser scalars, exchange
+//    sequence number, lambda for log det) is read by every CTA at kernel entry, i.e. before the first barrier, so the
+//    committing CTA cannot race with a CTA that is still reading;
+//  * the mbarrier ring is invalidated and re-initialised between the contraction phases (their stage geometry differs),
+//    after a CTA-wide barrier that follows the last accumulator hand-over of the phase.
+#include <cstdio>
+#include <cstdlib>
+
+#include "step_fused.cuh"
+#include "gemm_tc_dev.cuh"
+#include "glm_prior.cuh"
+#include "mf_finalize.cuh"
+
+namespace {
+
+constexpr int NW = NUM_THREADS / 32;            // 20 warps
+constexpr int TAIL_MAX_PER_CTA = 120;           // coordinates per CTA in the tail (scratch: 4 floats each in ys[0])
+
+__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+__device__ __forceinline__ void mbar_inval(uint64_t* bar) {
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+
+// All threads of all CTAs.  Arrival: every thread publishes its generic global writes to the async proxy, the CTA
+// barrier orders them before thread 0, whose gpu-scope fence + atomic makes them visible (cumulativity) to whoever
+// acquires the counter.  gbar[0] is a counter that only grows; gbar[1] holds its value at the start of the launch
+// (written by CTA 0 at the very end of the previous launch, read by every CTA at entry): the k-th barrier of a launch
+// of n CTAs completes at base + k * n, whatever the grid sizes of earlier launches were.
+struct GridBar {
+    unsigned long long* ctr;
+    unsigned long long base;
+    int k;
+};
+__device__ __forceinline__ void grid_barrier(GridBar& gb) {
+    fence_proxy_async_global();
+    __syncthreads();
+    gb.k += 1;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned long long target = gb.base + (unsigned long long)gb.k * gridDim.x;
+        atomicAdd(gb.ctr, 1ull);
+        while (ld_acquire_gpu_u64(gb.ctr) < target) { }
+        __threadfence();
+        fence_proxy_async_global();
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void stamp_min(unsigned long long* tl, int slot) {
+    if (tl && threadIdx.x == 0) atomicMin(tl + slot, gtime_ns());
+}
+__device__ __forceinline__ void stamp_max(unsigned long long* tl, int slot) {
+    if (tl && threadIdx.x == 0) atomicMax(tl + slot, gtime_ns());
+}
+
+// pipeline barriers for a phase with `stages` ring slots (one thread)
+__device__ __forceinline__ void init_pipeline(SmemCtl* ctl, int stages, int stages_prev) {
+    for (int s = 0; s < stages_prev; ++s) { mbar_inval(&ctl->full[s]); mbar_inval(&ctl->empty[s]); }
+    if (stages_prev > 0)
+        for (int s = 0; s < 2; ++s) { mbar_inval(&ctl->tmem_full[s]); mbar_inval(&ctl->tmem_empty[s]); }
+    for (int s = 0; s < stages; ++s) { tc::mbar_init(&ctl->full[s], 1); tc::mbar_init(&ctl->empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { tc::mbar_init(&ctl->tmem_full[s], 1); tc::mbar_init(&ctl->tmem_empty[s], EPI_WARPS); }
+    tc::mbar_fence_init();
+}
+
+#define FUNIT_COORDS(u) \
+    const int ab = (u) % p.n_ablk, bc = ((u) / p.n_ablk) % p.n_bchunk, ks = (u) / (p.n_ablk * p.n_bchunk)
+
+// The operand that does not depend on the previous phase (X; early_op 1 = A, 2 = B) of this CTA's first unit is
+// requested before the phase's dependency is satisfied: expect_tx without arrive; the producer adds the dependent
+// operand (and the arrive) later.  One thread.  Returns the number of ring slots armed.
+__device__ __forceinline__ int preissue_early(const CUtensorMap* tmA, const CUtensorMap* tmB, const TcParams& p,
+                                              SmemCtl* ctl, uint8_t* tiles, int stages, int early_op) {
+    const int units = p.n_ablk * p.n_bchunk * p.n_ksplit;
+    if ((int)blockIdx.x >= units) return 0;
+    const int NT = p.nt, stage_bytes = A_TILE_BYTES + NT * BK * 4;
+    const int u = blockIdx.x;
+    FUNIT_COORDS(u);
+    const int kb0 = ks * p.kb_per_split, kb1 = min(p.n_kblk, kb0 + p.kb_per_split);
+    int n = 0;
+    for (int kb = kb0; kb < kb1 && n < stages; ++kb, ++n) {
+        uint8_t* sa = tiles + n * stage_bytes;
+        if (early_op == 1) {
+            tc::mbar_expect_tx(&ctl->full[n], (uint32_t)A_TILE_BYTES);
+            tc::tma_load_2d(sa, tmA, &ctl->full[n], kb * BK, ab * BM);
+        } else {
+            tc::mbar_expect_tx(&ctl->full[n], (uint32_t)(NT * BK * 4));
+            tc::tma_load_2d(sa + A_TILE_BYTES, tmB, &ctl->full[n], kb * BK, bc * NT);
+        }
+    }
+    return n;
+}
+
+// One contraction phase: the single-CTA pipeline of k_gemm_tc (gemm_tc.cu) over the units u = blockIdx.x,
+// blockIdx.x + gridDim.x, ...; the ring and the accumulator stages start from their initial state.
+template <int EPI, int LIK>
+__device__ __forceinline__ void tc_phase(const CUtensorMap* tmA, const CUtensorMap* tmB, const TcParams& p, SmemCtl* ctl,
+                                         uint8_t* tiles, uint32_t tmem_base, int stages, int pre_issued, int early_op) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int NT = p.nt;
+    const int stage_bytes = A_TILE_BYTES + NT * BK * 4;
+    const int units = p.n_ablk * p.n_bchunk * p.n_ksplit;
+    const int first = blockIdx.x, stride = gridDim.x;
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (tc::elect_one()) {
+            fence_proxy_async_global();   // operands written by generic stores of the previous phase (other CTAs)
+            int stage = 0; uint32_t phase = 0;
+            int kcount = 0;
+            for (int u = first; u < units; u += stride) {
+                FUNIT_COORDS(u);
+                const int kb0 = ks * p.kb_per_split, kb1 = min(p.n_kblk, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb, ++kcount) {
+                    tc::mbar_wait(&ctl->empty[stage], phase ^ 1);
+                    uint8_t* sa = tiles + stage * stage_bytes;
+                    if (kcount < pre_issued) {
+                        if (early_op == 1) {
+                            tc::mbar_arrive_expect_tx(&ctl->full[stage], (uint32_t)(NT * BK * 4));
+                            tc::tma_load_2d(sa + A_TILE_BYTES, tmB, &ctl->full[stage], kb * BK, bc * NT);
+                        } else {
+                            tc::mbar_arrive_expect_tx(&ctl->full[stage], (uint32_t)A_TILE_BYTES);
+                            tc::tma_load_2d(sa, tmA, &ctl->full[stage], kb * BK, ab * BM);
+                        }
+                    } else {
+                        tc::mbar_arrive_expect_tx(&ctl->full[stage], (uint32_t)stage_bytes);
+                        tc::tma_load_2d(sa, tmA, &ctl->full[stage], kb * BK, ab * BM);
+                        tc::tma_load_2d(sa + A_TILE_BYTES, tmB, &ctl->full[stage], kb * BK, bc * NT);
+                    }
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (tc::elect_one()) {
+            const uint32_t idesc = tc::idesc_tf32(BM, NT);
+            int stage = 0; uint32_t phase = 0;
+            int as = 0; uint32_t aphase = 0;
+            for (int u = first; u < units; u += stride) {
+                const int ks = u / (p.n_ablk * p.n_bchunk);
+                const int kb0 = ks * p.kb_per_split, kb1 = min(p.n_kblk, kb0 + p.kb_per_split);
+                tc::mbar_wait(&ctl->tmem_empty[as], aphase ^ 1);
+                tc::fence_after_sync();
+                const uint32_t tacc = tmem_base + (uint32_t)(as * 256);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    tc::mbar_wait(&ctl->full[stage], phase);
+                    tc::fence_after_sync();
+                    const uint32_t sa = tc::smem_u32(tiles + stage * stage_bytes);
+                    const uint64_t da = tc::smem_desc_k_sw128(sa);
+                    const uint64_t db = tc::smem_desc_k_sw128(sa + A_TILE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 8; ++k)
+                        tc::umma_tf32(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                                      (kb > kb0 || k > 0) ? 1u : 0u);
+                    tc::umma_commit(&ctl->empty[stage]);
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
+                }
+                tc::umma_commit(&ctl->tmem_full[as]);
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int ew = warp - 4, quarter = warp & 3, cq = ew >> 2;
+        const int et = threadIdx.x - 128;
+        const int ngroups = NT / 8;
+        const int c_begin = 8 * ((ngroups * cq) / 4), c_end = 8 * ((ngroups * (cq + 1)) / 4);
+        int as = 0; uint32_t aphase = 0;
+        for (int u = first; u < units; u += stride) {
+            FUNIT_COORDS(u);
+            const int a = ab * BM + quarter * 32 + lane;
+            const bool a_ok = a < p.Ma;
+            const uint32_t tacc = tmem_base + (uint32_t)(as * 256) + ((uint32_t)(quarter * 32) << 16);
+            float s1, s2;
+            epilogue_unit<EPI, LIK, true>(p, ctl, as, aphase, tacc, NT, a, a_ok, bc, ks, c_begin, c_end, et, s1, s2);
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&ctl->tmem_empty[as]);
+            epilogue_store_partials<EPI>(p, a_ok, a, bc, ks, cq, s1, s2);
+            if (EPI == EPI_GLM_BWD) epilogue_bwd_store(p, ctl, a_ok, a, bc, ks, cq, et, s1, s2);
+            if (EPI == EPI_GLM_BWD && p.post_on) epilogue_bwd_combine(p, ctl, ab, et);
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Sample phase: z = mu + s .* eps for this rank's samples, eps from Philox (global sample index), plus what the
+// sampling kernel's GLM hook produces (family.cu: k_sample<.., HOOK>): the TF32-rounded beta block Zt (A operand of the
+// forward contraction), |eps_m|^2 and the per-sample prior terms.  Samples are dealt to CTAs in contiguous groups of
+// S = ceil(Mloc / grid); inside a CTA W = 20 / S warps share one sample (fixed-order combine through shared memory).
+__device__ __forceinline__ void sample_phase(const StepParams& sp, SmemCtl* ctl, unsigned long long step,
+                                             unsigned long long key) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int S = (sp.Mloc + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int W = S <= NW ? NW / S : 1;
+    const int slots = NW / W;
+    const PhiloxKeys pk(key);
+    const uint32_t c2 = (uint32_t)step, c3 = eps_ctr3(step, (uint32_t)AVI_STREAM_EPS);
+    const int D = sp.D, ld = sp.ld, nq = ld / 4;
+    const float* mu = sp.lambda;
+    const float* sc = sp.lambda + D;   // only 4-byte aligned in general
+    float* red = &ctl->ys[0][0];       // [warp][3]
+    const int slot = warp / W, wi = warp - slot * W;
+    for (int j0 = 0; j0 < S; j0 += slots) {
+        const int j = j0 + slot;
+        const int m = (int)blockIdx.x * S + j;
+        const bool active = slot < slots && j < S && m < sp.Mloc;
+        float part = 0.f, bsq = 0.f, eta = 0.f;
+        if (active) {
+            float* Erow = sp.E + (size_t)m * ld;
+            float* Zrow = sp.Z + (size_t)m * ld;
+            for (int q = wi * 32 + lane; q < nq; q += 32 * W) {
+                const float4 e = normal4((uint32_t)q, (uint32_t)(sp.m0 + m), c2, c3, pk);
+                const int i = 4 * q;
+                float ev[4] = {e.x, e.y, e.z, e.w}, zv[4], zt[4], mv[4] = {0.f, 0.f, 0.f, 0.f}, sv[4] = {0.f, 0.f, 0.f, 0.f};
+                if (i + 3 >= D) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) ev[c] = i + c < D ? ev[c] : 0.0f;
+                }
+                if (i + 3 < D) {
+                    const float4 m4 = *reinterpret_cast<const float4*>(mu + i);
+                    mv[0] = m4.x; mv[1] = m4.y; mv[2] = m4.z; mv[3] = m4.w;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) sv[c] = sc[i + c];
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if (i + c < D) { mv[c] = mu[i + c]; sv[c] = sc[i + c]; }
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    zv[c] = fmaf(sv[c], ev[c], mv[c]);
+                    part = fmaf(ev[c], ev[c], part);
+                    const bool is_beta = i + c < sp.d;
+                    bsq = is_beta ? fmaf(zv[c], zv[c], bsq) : bsq;
+                    zt[c] = is_beta ? zv[c] : 0.0f;
+                    if (i + c == sp.d) eta = zv[c];
+                }
+                *reinterpret_cast<float4*>(Erow + i) = make_float4(ev[0], ev[1], ev[2], ev[3]);
+                *reinterpret_cast<float4*>(Zrow + i) = make_float4(zv[0], zv[1], zv[2], zv[3]);
+                float hi[4], lo[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { hi[c] = tc::round_tf32(zt[c]); lo[c] = tc::round_tf32(zt[c] - hi[c]); }
+                float* row = sp.Zt + (size_t)m * sp.zt_ld + i;
+                if (sp.zt_seg == 0) {
+                    if (i < sp.zt_ld) *reinterpret_cast<float4*>(row) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                } else if (i < sp.zt_seg) {   // 3xTF32: [hi | hi | lo]
+                    *reinterpret_cast<float4*>(row) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<float4*>(row + sp.zt_seg) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<float4*>(row + 2 * sp.zt_seg) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                }
+            }
+        }
+        part = warp_sum(part); bsq = warp_sum(bsq); eta = warp_sum(eta);   // eta is non-zero in exactly one lane
+        if (W > 1) {
+            if (lane == 0) { red[warp * 3] = part; red[warp * 3 + 1] = bsq; red[warp * 3 + 2] = eta; }
+            __syncthreads();
+            if (wi == 0 && lane == 0 && slot < slots) {
+                part = 0.f; bsq = 0.f; eta = 0.f;
+                for (int w2 = 0; w2 < W; ++w2) {
+                    part += red[(slot * W + w2) * 3]; bsq += red[(slot * W + w2) * 3 + 1]; eta += red[(slot * W + w2) * 3 + 2];
+                }
+            }
+            __syncthreads();
+        }
+        if (active && wi == 0 && lane == 0) {
+            sp.esq[m] = part;
+            reinterpret_cast<float4*>(sp.pre)[m] = glm_prior_terms(bsq, eta, sp.d, sp.variant, sp.include_prior);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// State read by every CTA at kernel entry (see the memory-model notes at the top).
+struct Snap {
+    unsigned long long step, key;
+    long long cursor;
+    int halted, tp;
+    float b1t, b2t, t_avg, v_old, r_old, shift, logdet;
+    unsigned int seq;
+};
+
+// Tail phase, all CTAs: CTA c owns coordinates [c * per, (c + 1) * per) of mu and of s.
+//   local scalars (every CTA, same order => same bits) -> [exchange] -> value / ELBO / finiteness ->
+//   gradient entries of the slice -> [DoG / DoWG: partial norms + one more grid barrier] -> update of the slice ->
+//   commit (CTA 0) or, on the estimate_gradient! boundary, gradient to pinned host memory + last-CTA completion flag.
+__device__ __forceinline__ void tail_phase(const StepParams& sp, SmemCtl* ctl, const Snap& sn, GridBar& gb) {
+    const StepTail& t = sp.t;
+    const UpdArgs a = t.a;
+    const int D = sp.D, accv = t.accv, M = t.M, objective = t.objective, entropy = t.entropy;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float* vals = &ctl->ys[0][0];      // [per][4]
+    float* sm = &ctl->ys[1][0];        // block_sum scratch (33) | [64..] broadcast slots
+    const bool stl = entropy == AVI_ENT_STL || entropy == AVI_ENT_STL_ZEROGRAD;
+    const bool adam = a.rule == AVI_RULE_ADAM, dog = a.rule == AVI_RULE_DOG || a.rule == AVI_RULE_DOWG;
+    const bool polyavg = a.averager == AVI_AVG_POLYNOMIAL;
+    const int per = (D + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int c0 = min(D, (int)blockIdx.x * per), c1 = min(D, c0 + per), nc = c1 - c0;
+    const int NR = t.comm.nranks;
+
+    // ---- local scalars: sum_m log pi(z_m), sum_m |eps_m|^2 over this rank's samples / rows
+    float sl = 0.f, sq = 0.f;
+    for (int m = tid; m < sp.Mloc; m += NUM_THREADS) { sl += __ldcg(t.logp + m); sq += __ldcg(sp.esq + m); }
+    sl = block_sum(sl, sm); sq = block_sum(sq, sm);
+
+    // ---- per-coordinate sums of the slice (v2, v3 only where the gradient needs them: sticking the landing)
+    for (int j = warp; j < nc; j += NW) {
+        const int i = c0 + j;
+        float v2 = 0.f, v3 = 0.f;
+        if (stl) {
+            for (int m = lane; m < sp.Mloc; m += 32) {
+                const float e = __ldcg(sp.E + (size_t)m * sp.ld + i);
+                v2 += e; v3 = fmaf(e, e, v3);
+            }
+            v2 = warp_sum(v2); v3 = warp_sum(v3);
+        }
+        if (lane == 0) {
+            vals[4 * j] = __ldcg(t.acc + i); vals[4 * j + 1] = __ldcg(t.acc + accv + i);
+            vals[4 * j + 2] = v2; vals[4 * j + 3] = v3;
+        }
+    }
+    __syncthreads();
+
+    // ---- exchange over NVLink (low-latency push protocol of comm_dev.cuh): entry (class c, coordinate i) travels as
+    //      element c * accv + i, the scalars as elements 4 * accv + {0, 1}; sums are taken in rank order
+    if (NR > 1) {
+        const unsigned int seq = sn.seq;
+        const int nent = 4 * nc;
+        const long long sbase = 4ll * accv;
+        for (int k = tid; k < nent; k += NUM_THREADS) {
+            const int c = k & 3, j = k >> 2;
+            const bool x = (c < 2) ? (t.xmask & STEP_X_V01) != 0 : ((t.xmask & STEP_X_V23) != 0 && stl);
+            if (x) ll_push(t.comm, seq, (long long)c * accv + c0 + j, vals[k]);
+        }
+        if (blockIdx.x == 0 && tid == NUM_THREADS - 1) {
+            if (t.xmask & STEP_X_S0) ll_push(t.comm, seq, sbase, sl);
+            if (t.xmask & STEP_X_S1) ll_push(t.comm, seq, sbase + 1, sq);
+        }
+        for (int k = tid; k < nent; k += NUM_THREADS) {
+            const int c = k & 3, j = k >> 2;
+            const bool x = (c < 2) ? (t.xmask & STEP_X_V01) != 0 : ((t.xmask & STEP_X_V23) != 0 && stl);
+            if (x) {
+                const long long idx[1] = {(long long)c * accv + c0 + j}; const bool need[1] = {true};
+                const float own[1] = {vals[k]};
+                float out[1];
+                ll_gather<1>(t.comm, seq, idx, need, own, out);
+                vals[k] = out[0];
+            }
+        }
+        if (tid == NUM_THREADS - 1) {
+            const long long idx[2] = {sbase, sbase + 1};
+            const bool need[2] = {(t.xmask & STEP_X_S0) != 0, (t.xmask & STEP_X_S1) != 0};
+            const float own[2] = {sl, sq};
+            float out[2];
+            ll_gather<2>(t.comm, seq, idx, need, own, out);
+            sm[64] = need[0] ? out[0] : sl; sm[65] = need[1] ? out[1] : sq;
+        }
+        __syncthreads();
+        sl = sm[64]; sq = sm[65];
+    }
+
+    MfSums S;
+    S.s0 = sl; S.s1 = sq; S.s2 = 0.f; S.s3 = 0.f; S.logdet = sn.logdet;
+    float value, elbo, shift_next;
+    mf_outputs(D, M, objective, entropy, S, sn.shift, value, elbo, shift_next);
+    const bool bad = !isfinite(value);
+
+    // ---- gradient entries of the slice: thread j < nc owns coordinate c0 + j (mu_i and s_i)
+    const bool mine = tid < nc;
+    const int i = c0 + (mine ? tid : 0);
+    float x0 = 0.f, x1 = 1.f, g0 = 0.f, g1 = 0.f;
+    if (mine) {
+        x0 = t.lam[i]; x1 = t.lam[D + i];
+        mf_grad_vals(vals[4 * tid], vals[4 * tid + 1], vals[4 * tid + 2], vals[4 * tid + 3], x1, M, objective, entropy, S, g0, g1);
+        t.grad[i] = g0; t.grad[D + i] = g1;
+    }
+
+    if (t.mode == STEP_TAIL_GRAD_OUT) {
+        // estimate_gradient! boundary: the gradient goes straight to the caller-visible pinned buffer (posted writes);
+        // the last CTA to finish adds the scalars, advances the step counter and release-stores the completion flag
+        if (mine && t.host_out) { t.host_out[i] = g0; t.host_out[D + i] = g1; }
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned int tk = atomicAdd(t.done_ticket, 1u);
+            if (tk == gridDim.x - 1) {
+                *t.done_ticket = 0u;
+                __threadfence();
+                t.out[0] = value; t.out[1] = elbo; t.out[2] = S.logdet; t.out[3] = shift_next;
+                const unsigned long long step_next = sn.step + 1ull;
+                sp.st->step = step_next;
+                if (NR > 1) *reinterpret_cast<volatile unsigned int*>(&t.comm.dev->seq) = sn.seq;
+                if (t.host_out) {
+                    float* tail = t.host_out + 2 * (size_t)D;
+                    tail[0] = value; tail[1] = elbo; tail[2] = S.logdet; tail[3] = shift_next;
+                    __threadfence_system();
+                    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(reinterpret_cast<unsigned int*>(tail + 4)),
+                                 "r"((unsigned int)step_next) : "memory");
+                }
+            }
+        }
+        return;
+    }
+
+    // ---- optimiser step (common.jl:91-94)
+    float s1m0 = 0.f, s1m1 = 0.f, s2m0 = 0.f, s2m1 = 0.f, av0 = 0.f, av1 = 0.f;
+    if (mine) {
+        if (adam || dog) { s1m0 = t.m1[i]; s1m1 = t.m1[D + i]; }
+        if (adam) { s2m0 = t.m2[i]; s2m1 = t.m2[D + i]; }
+        if (polyavg) { av0 = t.avg[i]; av1 = t.avg[D + i]; }
+    }
+    float eta = a.rule == AVI_RULE_DESCENT ? a.h0 : 0.f, v_new = 0.f, r_new = 0.f;
+    if (dog) {
+        // two global norms (rules.jl:21-34, :52-64): per-CTA partials, one more grid barrier, fixed-order sum
+        float dx2 = 0.f, g2 = 0.f;
+        if (mine) {
+            const float d0 = x0 - s1m0, d1 = x1 - s1m1;
+            dx2 = fmaf(d0, d0, d1 * d1);
+            g2 = fmaf(g0, g0, g1 * g1);
+        }
+        dx2 = block_sum(dx2, sm); g2 = block_sum(g2, sm);
+        if (tid == 0) { t.norm_part[2 * blockIdx.x] = dx2; t.norm_part[2 * blockIdx.x + 1] = g2; }
+        grid_barrier(gb);
+        dx2 = 0.f; g2 = 0.f;
+        for (int q = tid; q < (int)gridDim.x; q += NUM_THREADS) { dx2 += __ldcg(t.norm_part + 2 * q); g2 += __ldcg(t.norm_part + 2 * q + 1); }
+        dx2 = block_sum(dx2, sm); g2 = block_sum(g2, sm);
+        r_new = fmaxf(sqrtf(dx2), sn.r_old);
+        if (a.rule == AVI_RULE_DOG) { v_new = sn.v_old + g2; eta = r_new / sqrtf(v_new); }
+        else { const float r2 = r_new * r_new; v_new = sn.v_old + r2 * g2; eta = r2 / sqrtf(v_new); }
+    }
+    if (!sn.halted && !bad && mine) {
+        const float w = (a.avg_param + 1.0f) / (sn.t_avg + a.avg_param);
+        const float bc1 = 1.0f / (1.0f - sn.b1t), bc2 = 1.0f / (1.0f - sn.b2t);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const size_t p = (size_t)h * D + i;
+            const float g = h ? g1 : g0;
+            float xx = h ? x1 : x0, dx;
+            if (adam) {
+                const float mt = a.h1 * (h ? s1m1 : s1m0) + (1.0f - a.h1) * g;
+                const float vt = a.h2 * (h ? s2m1 : s2m0) + (1.0f - a.h2) * g * g;
+                t.m1[p] = mt; t.m2[p] = vt;
+                dx = __fdividef(mt * bc1, sqrtf(vt * bc2) + a.h3) * a.h0;
+            } else {
+                dx = eta * g;
+            }
+            xx -= dx;
+            if (h == 1 && a.op != AVI_OP_IDENTITY) {
+                if (a.op == AVI_OP_CLIPSCALE) xx = fmaxf(xx, a.op_param);
+                else xx = xx + (sqrtf(fmaf(xx, xx, 4.0f * eta)) - xx) * 0.5f;
+            }
+            t.lam[p] = xx;
+            if (polyavg) t.avg[p] = (1.0f - w) * (h ? av1 : av0) + w * xx;
+        }
+    }
+    if (blockIdx.x == 0 && tid == 0) {
+        if (NR > 1) *reinterpret_cast<volatile unsigned int*>(&t.comm.dev->seq) = sn.seq;
+        if (!sn.halted) {
+            t.out[0] = value; t.out[1] = elbo; t.out[2] = S.logdet; t.out[3] = shift_next;
+            if (sn.tp < t.trace_cap) { t.trace[2 * sn.tp] = value; t.trace[2 * sn.tp + 1] = elbo; }
+            sp.st->trace_pos = sn.tp + 1;
+            if (bad) {
+                sp.st->halted = 1;
+            } else {
+                t.sc[SC_T] = sn.t_avg + 1.0f;
+                t.sc[SC_ETA] = eta;
+                if (adam) { t.sc[SC_B1T] = sn.b1t * a.h1; t.sc[SC_B2T] = sn.b2t * a.h2; }
+                if (dog) { t.sc[SC_V] = v_new; t.sc[SC_R] = r_new; }
+                sp.st->step = sn.step + 1ull;
+                sp.st->batch_cursor = sn.cursor + 1;
+            }
+        }
+    }
+}
+
+// timeline slots (AVI_TIMELINE; atomicMin in 0..7, atomicMax in 8..15): first CTA 0 entered | 1 past the dependency wait |
+// 2 past barrier 0 (forward starts) | 3 past barrier 1 (backward starts) | 4 past barrier 2 (tail starts);
+// last CTA 8 left the sample phase | 9 left the forward phase | 10 left the backward phase | 11 done
+template <int LIK>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+k_glm_mf_step(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmXr,
+              const __grid_constant__ CUtensorMap tmXc, const __grid_constant__ CUtensorMap tmR, const StepParams sp) {
+    extern __shared__ uint8_t smem_raw[];
+    SmemCtl* ctl = reinterpret_cast<SmemCtl*>((reinterpret_cast<uintptr_t>(smem_raw) + 15) & ~(uintptr_t)15);
+    uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ctl) + sizeof(SmemCtl) + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    stamp_min(sp.tl, 0);
+
+    if (warp == 0 && lane == 0) {
+        tc::tma_prefetch_desc(&tmZ); tc::tma_prefetch_desc(&tmXr); tc::tma_prefetch_desc(&tmXc); tc::tma_prefetch_desc(&tmR);
+    }
+    if (warp == 1 && lane == 0) init_pipeline(ctl, sp.stages_f, 0);
+    if (warp == 2) tc::tmem_alloc(&ctl->tmem_base, 512);
+    pdl_trigger();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = ctl->tmem_base;
+
+    // forward phase: A = Zt (dependent), B = X rows.  A full-data X is static: request it before waiting for the
+    // previous kernel; a minibatch copy is rewritten by the gather kernel of this iteration: request it after the wait.
+    int pre = 0;
+    if (warp == 0 && sp.f.static_op == 2) {
+        if (lane == 0) pre = preissue_early(&tmZ, &tmXr, sp.f, ctl, tiles, sp.stages_f, 2);
+        pre = __shfl_sync(0xffffffffu, pre, 0);
+    }
+    pdl_wait();
+    stamp_min(sp.tl, 1);
+    if (warp == 0 && sp.f.static_op != 2) {   // minibatch copy of X: final once the gather kernel has completed
+        if (lane == 0) pre = preissue_early(&tmZ, &tmXr, sp.f, ctl, tiles, sp.stages_f, 2);
+        pre = __shfl_sync(0xffffffffu, pre, 0);
+    }
+
+    // ---- snapshot of everything the end of this iteration overwrites
+    GridBar gb;
+    gb.ctr = sp.gbar; gb.base = __ldcg(sp.gbar + 1); gb.k = 0;
+    Snap sn;
+    sn.step = sp.st->step; sn.key = sp.st->key; sn.cursor = sp.st->batch_cursor; sn.halted = sp.st->halted; sn.tp = sp.st->trace_pos;
+    sn.b1t = sn.b2t = sn.t_avg = sn.v_old = sn.r_old = sn.shift = sn.logdet = 0.f; sn.seq = 0;
+    if (sp.t.mode != STEP_TAIL_NONE) {
+        if (sp.t.mode == STEP_TAIL_UPDATE) {
+            sn.b1t = sp.t.sc[SC_B1T]; sn.b2t = sp.t.sc[SC_B2T]; sn.t_avg = sp.t.sc[SC_T]; sn.v_old = sp.t.sc[SC_V]; sn.r_old = sp.t.sc[SC_R];
+        }
+        sn.shift = sp.t.out[3];
+        if (sp.t.comm.nranks > 1) sn.seq = *reinterpret_cast<volatile unsigned int*>(&sp.t.comm.dev->seq) + 1u;
+        float part = 0.f;
+        for (int i = threadIdx.x; i < sp.D; i += NUM_THREADS) part += __logf(sp.lambda[sp.D + i]);
+        sn.logdet = block_sum(part, &ctl->ys[1][0]);
+    }
+
+    if (sp.do_sample) {
+        sample_phase(sp, ctl, sn.step, sn.key);
+        stamp_max(sp.tl, 8);
+        grid_barrier(gb);
+        stamp_min(sp.tl, 2);
+    }
+
+    tc_phase<EPI_GLM_FWD, LIK>(&tmZ, &tmXr, sp.f, ctl, tiles, tmem_base, sp.stages_f, pre, 2);
+    stamp_max(sp.tl, 9);
+
+    // ---- drain, re-carve the ring for the backward geometry, request its static operand (X columns) while the
+    //      other CTAs finish, then the barrier that publishes R
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 1 && lane == 0) init_pipeline(ctl, sp.stages_b, sp.stages_f);
+    __syncthreads();
+    pre = 0;
+    if (warp == 0) {
+        if (lane == 0) pre = preissue_early(&tmXc, &tmR, sp.b, ctl, tiles, sp.stages_b, 1);
+        pre = __shfl_sync(0xffffffffu, pre, 0);
+    }
+    grid_barrier(gb);
+    stamp_min(sp.tl, 3);
+    tc::fence_after_sync();
+
+    tc_phase<EPI_GLM_BWD, 0>(&tmXc, &tmR, sp.b, ctl, tiles, tmem_base, sp.stages_b, pre, 1);
+    stamp_max(sp.tl, 10);
+
+    if (sp.t.mode != STEP_TAIL_NONE) {
+        grid_barrier(gb);
+        stamp_min(sp.tl, 4);
+        tail_phase(sp, ctl, sn, gb);
+    }
+
+    // (CTA 0 has passed the last barrier of the launch: every CTA has read the old base)
+    if (blockIdx.x == 0 && threadIdx.x == 0) sp.gbar[1] = gb.base + (unsigned long long)gb.k * gridDim.x;
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 2) {
+        tc::fence_after_sync();
+        tc::tmem_dealloc(tmem_base, 512);
+    }
+    stamp_max(sp.tl, 11);
+}
+
+}  // namespace
+
+int avi_step_fused_max_per_cta() { return TAIL_MAX_PER_CTA; }
+
+int32_t avi_step_fused_launch(avi_ctx* ctx, const CUtensorMap& tmZ, const CUtensorMap& tmXr, const CUtensorMap& tmXc,
+                              const CUtensorMap& tmR, StepParams& sp) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        AVI_CUDA(ctx, cudaFuncSetAttribute(k_glm_mf_step<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        AVI_CUDA(ctx, cudaFuncSetAttribute(k_glm_mf_step<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        attr_done = true;
+    }
+    const int extra = 16 + (int)sizeof(SmemCtl) + 1024;
+    auto stages_for = [&](int nt) {
+        const int stage_bytes = A_TILE_BYTES + nt * BK * 4;
+        return std::max(2, std::min(MAX_STAGES, (SMEM_LIMIT - extra) / stage_bytes));
+    };
+    sp.stages_f = stages_for(sp.f.nt); sp.stages_b = stages_for(sp.b.nt);
+    const int smem = extra + std::max(sp.stages_f * (A_TILE_BYTES + sp.f.nt * BK * 4), sp.stages_b * (A_TILE_BYTES + sp.b.nt * BK * 4));
+    if (smem > SMEM_LIMIT) AVI_FAIL(ctx, AVI_ERR_INVALID, "tiles do not fit in shared memory");
+    if (sp.f.pair || sp.b.pair || sp.f.ca * sp.f.cb != 1 || sp.b.ca * sp.b.cb != 1)
+        AVI_FAIL(ctx, AVI_ERR_INVALID, "the fused iteration runs single-CTA tiles only");
+    const int sms = ctx->prop.multiProcessorCount;
+    const int64_t units_f = (int64_t)sp.f.n_ablk * sp.f.n_bchunk * sp.f.n_ksplit;
+    const int64_t units_b = (int64_t)sp.b.n_ablk * sp.b.n_bchunk * sp.b.n_ksplit;
+    int grid = (int)std::min<int64_t>(sms, std::max<int64_t>(units_f, units_b));
+    // the tail deals D coordinates to the CTAs, at most TAIL_MAX_PER_CTA each
+    if (sp.t.mode != STEP_TAIL_NONE) grid = std::max(grid, std::min(sms, (int)ceil_div(sp.D, TAIL_MAX_PER_CTA)));
+    if (sp.t.mode != STEP_TAIL_NONE && ceil_div(sp.D, grid) > TAIL_MAX_PER_CTA)
+        AVI_FAIL(ctx, AVI_ERR_UNSUPPORTED, "too many coordinates for the fused tail");
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    int na = 0;
+    if (avi_pdl_enabled()) {
+        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = at; cfg.numAttrs = na;
+    sp.tl = ctx->tl;
+    AviTimed timed(ctx, "glm_step");
+    cudaError_t e = sp.f.likelihood == AVI_GLM_BERNOULLI_LOGIT
+                        ? cudaLaunchKernelEx(&cfg, k_glm_mf_step<0>, tmZ, tmXr, tmXc, tmR, sp)
+                        : cudaLaunchKernelEx(&cfg, k_glm_mf_step<1>, tmZ, tmXr, tmXc, tmR, sp);
+    if (e != cudaSuccess) AVI_FAIL(ctx, AVI_ERR_CUDA, std::string("fused step launch: ") + cudaGetErrorString(e));
+    AVI_LAUNCHED(ctx);
+    return AVI_OK;
+}

@@ -1,0 +1,68 @@
+// Host-side interface of the fused whole-iteration kernel (step_fused.cu): ONE launch per `step`
+// (src/algorithms/common.jl:75-104 minus the callback) for the mean-field family over a hierarchical GLM target:
+//   sample phase   rand(rng, q, M)                               src/families/location_scale.jl:80-87
+//   -- grid barrier --
+//   forward phase  X * beta + log-likelihood + weighted residual  docs/src/tutorials/subsampling.md:35-36 for all M samples
+//   -- grid barrier --
+//   backward phase X' R reduced against eps (mean-field pullback) src/families/location_scale.jl:86, repgradelbo.jl:142-149
+//   -- grid barrier --
+//   tail phase     [NVLink exchange of the partial sums] + closed-form gradient + value / ELBO + finiteness check +
+//                  Optimisers rule + operator + averager + commit src/algorithms/common.jl:83-94
+// The contraction phases are the tcgen05 pipelines of gemm_tc.cu; what the fusion removes is three kernel boundaries
+// (prologue, first-operand latency, teardown: ~8 us per contraction launch at the benchmark shape) and it lets the
+// static operand of the NEXT phase stream in while the current one drains.
+#pragma once
+
+#include <cuda.h>
+#include <stdint.h>
+
+#include "avi_internal.cuh"
+#include "comm_dev.cuh"
+#include "gemm_tc.cuh"
+#include "mf_tail.cuh"
+
+enum { STEP_TAIL_NONE = 0, STEP_TAIL_UPDATE = 1, STEP_TAIL_GRAD_OUT = 2 };
+// which classes of partial sums are summed over the ranks by the fused exchange
+enum { STEP_X_V01 = 1, STEP_X_V23 = 2, STEP_X_S0 = 4, STEP_X_S1 = 8 };
+
+struct StepTail {
+    int mode;                      // STEP_TAIL_*
+    float* acc; int accv;          // [v0 | v1 | v2 | v3] as in avi_internal.cuh (v0, v1 written by the backward phase)
+    int M, objective, entropy;
+    float* logp;                   // [Mloc] log pi(z_m) (this rank's rows)
+    float *lam, *grad, *m1, *m2, *avg, *sc, *out;
+    float* trace; int trace_cap;
+    UpdArgs a;
+    float* norm_part;              // DoG / DoWG: [2 * grid] partial norms
+    float* host_out;               // STEP_TAIL_GRAD_OUT: mapped pinned [grad (2 D) | value, elbo, logdet, shift | flag]
+    unsigned int* done_ticket;     // STEP_TAIL_GRAD_OUT: last-CTA election
+    CommPeers comm; int xmask; long long acc_len;
+};
+
+struct StepParams {
+    TcParams f, b;                 // forward / backward contraction plans (no clusters, no CTA pairs)
+    int stages_f, stages_b;
+    // sample phase
+    int do_sample;                 // 0: Z, Zt, E, esq, pre come from the stand-alone sampling kernel
+    const float* lambda; int D, ld, m0, Mloc;
+    ObjDeviceState* st;
+    float *Z, *E, *esq;
+    int d, variant, include_prior;
+    float* Zt; int zt_ld, zt_seg;
+    float* pre;                    // float4 per sample
+    StepTail t;
+    unsigned long long* gbar;      // [2] grid barrier: monotonic arrival counter | its value at the start of the launch
+    unsigned long long* tl;        // AVI_TIMELINE: %globaltimer stamps per phase (diagnostic)
+};
+
+// what the objective layer hands to a target that can run the fused iteration (avi_model::fused_step)
+struct FusedStepArgs {
+    const float* lambda; int D, ld, m0, Mloc;
+    ObjDeviceState* st;
+    float *Z, *E, *esq, *logp;
+    StepTail t;
+};
+
+int avi_step_fused_max_per_cta();   // coordinates of the tail one CTA can take
+int32_t avi_step_fused_launch(avi_ctx* ctx, const CUtensorMap& tmZ, const CUtensorMap& tmXr, const CUtensorMap& tmXc,
+                              const CUtensorMap& tmR, StepParams& sp);

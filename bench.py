@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""bench.py -- ELBO grad-steps/sec on BASELINE.json config 2 (configs[1]):
+"""bench.py -- ELBO grad-steps/sec on the configs of BASELINE.json; headline = config 2 (configs[1]):
 RepGradELBO + ClosedFormEntropy, MeanFieldGaussian, hierarchical logistic regression
 n = 10000, d = 1024 (D = 1025), M = 256 Monte-Carlo samples, Adam(1e-3) + ClipScale + PolynomialAveraging.
 
@@ -7,10 +7,16 @@ One "step" = everything `step` does per iteration except the callback (src/algor
 sample -> log-density + gradient on M samples -> entropy -> reduce to grad lambda and ELBO -> (exchange)
 -> optimiser + operator + averaging.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config c2|c3|c4a|c4b|c5]
+                  [--shard rows|samples] [--extras / --no-extras]
 
-N > 1 (under torchrun): the M samples are sharded over the ranks (strong scaling) and the
-partial gradient sums are exchanged by the library's one-shot NVLink all-reduce kernel.
+The printed JSON line is the --config workload (default c2).  With c2 at default settings the line also carries a
+compact `configs` dict with the other BASELINE.json configs measured in the same process (bounded step counts).
+
+N > 1 (under torchrun): default n-axis sharding -- every rank holds all M samples and n / N data rows, so each rank
+ingests X / N; the partial gradient sums and sum_m log pi are exchanged over NVLink inside the iteration kernel's tail
+phase.  --shard samples = M-axis (every rank streams all of X).  c5 is weak scaling: a fixed minibatch
+per rank out of one reshuffled epoch, likeadj on the global batch.
 """
 import argparse
 import json
@@ -30,25 +36,49 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_ROWS, N_FEAT, N_MC = 10000, 1024, 256
-SEED = 1
-WORKLOAD = "C2: RepGradELBO+ClosedFormEntropy, MeanFieldGaussian, hier. logistic regression n=10000 d=1024 (D=1025), M=256"
 L2_FLUSH_BYTES = 256 << 20
 
+CONFIGS = {
+    "c2": dict(n=10000, d=1024, M=256, family="meanfield", objective="rep", entropy="ClosedFormEntropy", model="logreg",
+               opt=("adam", 1e-3), seed=1, scaling="strong",
+               workload="C2: RepGradELBO+ClosedFormEntropy, MeanFieldGaussian, hier. logistic regression n=10000 d=1024 (D=1025), M=256"),
+    "c3": dict(n=10000, d=1024, M=256, family="fullrank", objective="rep", entropy="ClosedFormEntropy", model="logreg",
+               opt=("adam", 1e-3), seed=1, scaling="strong",
+               workload="C3: RepGradELBO+ClosedFormEntropy, FullRankGaussian (lambda in R^1051650), hier. logistic regression n=10000 d=1024, M=256"),
+    "c4a": dict(n=100000, d=4096, M=1024, family="meanfield", objective="score", entropy="ClosedFormEntropy", model="gaussglm",
+                opt=("dog", 1e-6), seed=2, scaling="strong",
+                workload="C4a: ScoreGradELBO (VarGrad), MeanFieldGaussian, Gaussian GLM n=100000 d=4096 (D=4097), M=1024, DoG"),
+    "c4b": dict(n=100000, d=4096, M=1024, family="meanfield", objective="rep", entropy="StickingTheLandingEntropy", model="gaussglm",
+                opt=("dog", 1e-6), seed=2, scaling="strong",
+                workload="C4b: RepGradELBO+StickingTheLanding, MeanFieldGaussian, Gaussian GLM n=100000 d=4096 (D=4097), M=1024, DoG"),
+    "c5": dict(n=1000000, d=512, M=512, family="meanfield", objective="rep", entropy="ClosedFormEntropy", model="logreg",
+               opt=("adam", 1e-3), seed=3, batch=4096, scaling="weak",
+               workload="C5: Subsampled RepGradELBO+ClosedFormEntropy (ReshufflingBatchSubsampling, batch 4096 rows per GPU), "
+                        "MeanFieldGaussian, hier. logistic regression n=1000000 d=512 (D=513), M=512"),
+}
+OPT_DESC = {"adam": "Adam(1e-3)+ClipScale+PolynomialAveraging", "dog": "DoG+ClipScale+PolynomialAveraging"}
 
-def synth(n, d, seed, gaussian=False):
+
+def synth(n, d, seed, gaussian=False, rows=None):
     """SURVEY.md 8(d) recipe: X_ij ~ N(0,1)/sqrt(d), last column == 1 (intercept), beta* ~ N(0,1),
     y ~ Bernoulli(sigmoid(X beta*)) or X beta* + N(0,1).  Plain numpy generator: nothing under oracle/ is needed
-    to produce the inputs of either arm."""
-    rng = np.random.default_rng(seed)
-    X = rng.standard_normal((n, d), dtype=np.float32) / np.float32(np.sqrt(d))
-    X[:, d - 1] = 1.0
-    beta = rng.standard_normal(d).astype(np.float32)
-    logits = X @ beta
-    if gaussian:
-        y = (logits + rng.standard_normal(n).astype(np.float32)).astype(np.float32)
-    else:
-        y = (rng.random(n) < 1.0 / (1.0 + np.exp(-logits))).astype(np.float32)
+    to produce the inputs of either arm.  rows = (r0, nr): only that slice (generated block-wise so that every rank
+    of a sharded run sees the same global data set without materialising all of it)."""
+    beta = np.random.default_rng([seed, 1]).standard_normal(d).astype(np.float32)
+    r0, nr = (0, n) if rows is None else rows
+    blk = 8192
+    X = np.empty((nr, d), np.float32)
+    y = np.empty(nr, np.float32)
+    for b0 in range((r0 // blk) * blk, r0 + nr, blk):
+        rng = np.random.default_rng([seed, 2, b0 // blk])
+        Xb = rng.standard_normal((min(blk, n - b0), d), dtype=np.float32) / np.float32(np.sqrt(d))
+        Xb[:, d - 1] = 1.0
+        lg = Xb @ beta
+        yb = (lg + rng.standard_normal(len(lg)).astype(np.float32)).astype(np.float32) if gaussian else \
+            (rng.random(len(lg)) < 1.0 / (1.0 + np.exp(-lg))).astype(np.float32)
+        lo, hi = max(b0, r0), min(b0 + len(lg), r0 + nr)
+        X[lo - r0:hi - r0] = Xb[lo - b0:hi - b0]
+        y[lo - r0:hi - r0] = yb[lo - b0:hi - b0]
     return X, y
 
 
@@ -105,7 +135,9 @@ def reference_arm(args, rank, world):
     `cpu_baseline.reference_shaped_steps_per_s` = the same whole step run the way the reference is structured
     (one logdensity_and_gradient call per Monte-Carlo sample, src/algorithms/repgradelbo.jl:84-86: M GEMVs over X,
     Float64), timed on a few whole steps (it is ~4x slower, so it gets a smaller step count, never an
-    extrapolation from a fraction of a step)."""
+    extrapolation from a fraction of a step).
+    Configs other than c2 are too large for whole CPU steps (c4: 8e11 FLOP per step): they run on a stated row / sample
+    slice and the time is scaled linearly (said so in `sample`)."""
     if rank != 0:
         return
     try:
@@ -114,18 +146,30 @@ def reference_arm(args, rank, world):
     except Exception:   # noqa: BLE001
         pass
     from oracle import family as F, models as Mo, objectives as O, optim as Op, philox as P
-    X, y = synth(N_ROWS, N_FEAT, SEED)
-    prob = Mo.LogReg(X, y)
-    D = N_FEAT + 1
-    q0 = F.MeanFieldGaussian(np.zeros(D), np.ones(D))
-    rule, op, avg = Op.Adam(1e-3), Op.ClipScale(), Op.PolynomialAveraging()
+    cfg = CONFIGS[args.config]
+    n, d, M = cfg["n"], cfg["d"], cfg["M"]
+    scale = 1.0
+    if args.config in ("c4a", "c4b"):
+        n, M, scale = n // 16, M // 16, 256.0
+    if args.config == "c5":
+        n = cfg["batch"]          # one minibatch per step; the gather is a row slice on the CPU
+    X, y = synth(n, d, cfg["seed"], gaussian=cfg["model"] == "gaussglm")
+    prob = (Mo.GaussGLM if cfg["model"] == "gaussglm" else Mo.LogReg)(X, y, n_data=cfg["n"])
+    D = d + 1
+    q0 = F.MeanFieldGaussian(np.zeros(D), np.ones(D)) if cfg["family"] == "meanfield" else \
+        F.FullRankGaussian(np.zeros(D), 0.6 * np.eye(D))
+    rule = Op.Adam(1e-3) if cfg["opt"][0] == "adam" else Op.DoG()
+    op, avg = Op.ClipScale(), Op.PolynomialAveraging()
 
     def run(per_sample, steps, warm):
         st = Op.sgd_init(q0, rule, avg)
 
         def grad_fn(params, t):
-            eps = P.normal_matrix(SEED, t - 1, D, N_MC)
-            v, g, e = O.repgrad_value_and_gradient(params, q0, prob, eps, "ClosedFormEntropy", per_sample=per_sample)
+            eps = P.normal_matrix(cfg["seed"], t - 1, D, M)
+            if cfg["objective"] == "score":
+                v, g, e = O.scoregrad_value_and_gradient(params, q0, prob, eps)
+            else:
+                v, g, e = O.repgrad_value_and_gradient(params, q0, prob, eps, cfg["entropy"], per_sample=per_sample)
             return v, g, dict(elbo=e)
         for _ in range(warm):
             Op.sgd_step(st, q0, grad_fn, rule, op, avg)
@@ -135,23 +179,25 @@ def reference_arm(args, rank, world):
         return (time.perf_counter() - t0) / steps
 
     K, W = max(1, args.steps), max(0, args.warmup)
-    batched_s = run(False, K, W)
-    k_ps = max(2, min(K, int(20.0 / max(4.0 * batched_s, 1e-3))))   # ~20 s of per-sample steps, whole steps only
-    per_sample_s = run(True, k_ps, 1)
+    batched_s = run(False, K, W) * scale
     cores = os.cpu_count()
     val = 1.0 / batched_s
+    cb = {"value": val, "unit": "steps/s", "cores": cores, "kind": "port",
+          "sample": f"{K} whole grad-steps (all {M} samples, one batched GEMM per pass, Float64 numpy/OpenBLAS, {cores} "
+                    f"threads) after {W} warm-ups: best-effort CPU, the conservative denominator"
+                    + (f"; run on n/16 rows x M/16 samples, time scaled by {scale:g}" if scale != 1.0 else "")}
+    if args.config == "c2":
+        k_ps = max(2, min(K, int(20.0 / max(4.0 * batched_s, 1e-3))))   # ~20 s of per-sample steps, whole steps only
+        per_sample_s = run(True, k_ps, 1)
+        cb["reference_shaped_steps_per_s"] = 1.0 / per_sample_s
+        cb["reference_shaped_sample"] = (f"{k_ps} whole grad-steps of {M} per-sample logdensity_and_gradient calls "
+                                         "(M GEMVs over X), no extrapolation")
     line = {
         "impl": "reference", "metric": "ELBO grad-steps/sec", "value": val, "unit": "steps/s", "n_gpus": args.gpus,
         "steps": K, "warmup": W, "ms_per_step": batched_s * 1e3, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "optimizer": "Adam(1e-3)+ClipScale+PolynomialAveraging"},
-        "cpu_baseline": {"value": val, "unit": "steps/s", "cores": cores, "kind": "port",
-                         "sample": f"{K} whole grad-steps (all {N_MC} samples, one batched GEMM per pass, Float64 "
-                                   f"numpy/OpenBLAS, {cores} threads) after {W} warm-ups: best-effort CPU, the conservative "
-                                   "denominator",
-                         "reference_shaped_steps_per_s": 1.0 / per_sample_s,
-                         "reference_shaped_sample": f"{k_ps} whole grad-steps of {N_MC} per-sample logdensity_and_gradient "
-                                                    "calls (M GEMVs over X), no extrapolation"},
+        "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": cfg["workload"], "optimizer": OPT_DESC[cfg["opt"][0]]},
+        "cpu_baseline": cb,
         "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "CPU restatement (oracle/) of AdvancedVI.jl's path; the Julia package itself cannot run here",
     }
@@ -159,14 +205,253 @@ def reference_arm(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------------
+class Bench:
+    """One config on this rank: data, target, objective, fused optimiser state."""
+
+    _bpos = 0
+
+    def __init__(self, name, args, ctx, rank, world, local_rank, gemm):
+        import advancedvi_jl_b200 as avi
+        from advancedvi_jl_b200 import parallel, _lib as L
+        from advancedvi_jl_b200.api import _OptState
+        self.avi, self.L, self.name, self.cfg = avi, L, name, CONFIGS[name]
+        cfg = self.cfg
+        self.ctx, self.rank, self.world, self.gemm = ctx, rank, world, gemm
+        n, d, M = cfg["n"], cfg["d"], cfg["M"]
+        self.D = D = d + 1
+        gaussian = cfg["model"] == "gaussglm"
+        cls = avi.GaussGLM if gaussian else avi.LogReg
+        self.shard = args.shard if world > 1 else "none"
+        self.subsampled = "batch" in cfg
+        self.rows_local = n
+        if self.subsampled or world == 1 or self.shard == "samples":
+            X, y = synth(n, d, cfg["seed"], gaussian)
+            self.prob = cls(ctx, X, y, gemm=gemm)
+            if self.subsampled and world > 1:
+                self.prob.set_data_shard(world, n, include_prior=(rank == 0))
+        else:
+            r0, nr = parallel.row_shard(n, rank, world, align=32)
+            X, y = synth(n, d, cfg["seed"], gaussian, rows=(r0, nr))
+            self.prob = cls(ctx, X, y, n_data=n, gemm=gemm)
+            self.prob.set_data_shard(world, n, include_prior=(rank == 0))
+            self.rows_local = nr
+        self.X, self.y = (X, y) if name == "c2" else (None, None)
+        if cfg["family"] == "meanfield":
+            self.q0 = avi.MeanFieldGaussian(np.zeros(D, np.float32), np.ones(D, np.float32))
+        else:
+            self.q0 = avi.FullRankGaussian(np.zeros(D, np.float32), (0.6 * np.eye(D)).astype(np.float32))
+        opt = avi.Adam(cfg["opt"][1]) if cfg["opt"][0] == "adam" else avi.DoG(cfg["opt"][1])
+        ent = getattr(avi, cfg["entropy"])()
+        if cfg["objective"] == "score":
+            self.alg = avi.KLMinScoreGradDescent(optimizer=opt, n_samples=M, operator=avi.ClipScale())
+        else:
+            self.alg = avi.KLMinRepGradDescent(optimizer=opt, entropy=ent, n_samples=M, operator=avi.ClipScale())
+        self.obj = avi.Objective(cfg["seed"], self.alg.objective, self.q0, self.prob)
+        self.m_loc = M
+        if world > 1:
+            P = self.obj.P
+            parallel.connect(ctx, max_floats=(4 * ((D + 31) // 32 * 32) + 64) if cfg["family"] == "meanfield" else P + 4 * D + 4096,
+                             native=True)
+            if self.subsampled or self.shard == "rows":
+                self.obj.set_shard_axis(L.SHARD_ROWS)
+            else:
+                m0, ml = parallel.sample_shard(M, rank, world)
+                self.obj.set_sample_shard(m0, ml)
+                self.m_loc = ml
+        self.state = _OptState(self.alg, self.obj, self.q0)
+        self.batches = None
+        if self.subsampled:
+            # one reshuffled epoch, dealt round-robin to the ranks (reshuffling.jl:27-32; SURVEY.md 8e C5)
+            sub = avi.ReshufflingBatchSubsampling(np.arange(n), cfg["batch"])
+            allb = [bb for _, bb in sub.reshuffle_batches(cfg["seed"], 0)]
+            allb = [bb for bb in allb if len(bb) == cfg["batch"]]
+            self.batches = parallel.rank_batches(allb, rank, world)
+
+    def run_steps(self, n, vals, elbos):
+        import ctypes as C
+        L, nd = self.L, C.c_int32()
+        if self.subsampled:
+            idx = np.ascontiguousarray(np.stack([self.batches[(self._bpos + k) % len(self.batches)] for k in range(n)]), dtype=np.int32)
+            self._bpos += n
+            L.check(L.lib.avi_opt_steps_subsampled(self.state.h, n, L.iptr(idx), idx.shape[1], L.fptr(vals), L.fptr(elbos),
+                                                   C.byref(nd)), self.ctx.h)
+        else:
+            L.check(L.lib.avi_opt_steps(self.state.h, n, L.fptr(vals), L.fptr(elbos), C.byref(nd)), self.ctx.h)
+        assert nd.value == n, f"{self.name}: objective diverged"
+
+    def sharding_desc(self):
+        cfg = self.cfg
+        if self.world == 1:
+            return "none"
+        if self.subsampled:
+            return (f"weak scaling: {cfg['batch']} minibatch rows per rank per step (global batch {cfg['batch'] * self.world}), every "
+                    f"rank holds all {cfg['M']} samples; exchange = [sum g, sum g*eps, sum log pi] over NVLink inside the iteration kernel")
+        if self.shard == "rows":
+            return (f"n-axis: {self.rows_local} data rows per rank, all {cfg['M']} samples on every rank; exchange = partial "
+                    "gradient sums + sum_m log pi over NVLink (peer-memory low-latency push), fused into the iteration kernel's tail phase")
+        return f"M-axis: {self.m_loc} samples per rank, every rank streams all of X; exchange = one-shot NVLink all-reduce of the partial sums"
+
+    def close(self):
+        self.state.close(); self.obj.close(); self.prob.close()
+        if self.world > 1:
+            import torch.distributed as dist
+            self.ctx.disconnect_peers()
+            dist.barrier()
+
+
+def device_loop(b, K, W, torch, dist, ext, flush, barrier, sampler_index=None):
+    """K timed iterations of the fused device loop.  Returns (cold_ms, warm_ms, launches, final_elbo, clocks).
+    cold: L2 flushed (256 MiB write, untimed) before every step, per-step CUDA events on the library stream, the steps
+    enqueued without a host round trip.  warm: K back-to-back replays, one event pair."""
+    vals = np.empty(max(K, W), np.float32)
+    elbos = np.empty_like(vals)
+    b.run_steps(W, vals, elbos)
+    sampler = ClockSampler(sampler_index) if sampler_index is not None else None
+    if sampler:
+        sampler.start()
+    barrier()
+    l0 = b.ctx.launch_count()
+    if b.subsampled:
+        # minibatch indices travel with the call: one blocking call of K steps between two events (X = 2 GB >> L2, the
+        # gathered batch is produced inside the step: no flush needed)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        b.run_steps(K, vals, elbos)
+        e1.record(ext)
+        barrier()
+        cold_ms = e0.elapsed_time(e1)
+        launches = b.ctx.launch_count() - l0
+        warm_ms = cold_ms
+    else:
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        b.state.steps_begin(K)
+        for k in range(K):
+            with torch.cuda.stream(ext):
+                flush.zero_()                                   # evict X, R, Z from L2 (untimed)
+                ev[k][0].record(ext)
+            b.state.steps_enqueue(1)
+            ev[k][1].record(ext)
+        _, cold_elbos, n_cold = b.state.steps_end()
+        assert n_cold == K, f"{b.name}: objective diverged"
+        barrier()
+        launches = b.ctx.launch_count() - l0
+        cold_ms = sum(x.elapsed_time(z) for x, z in ev)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        b.run_steps(K, vals, elbos)
+        e1.record(ext)
+        barrier()
+        warm_ms = e0.elapsed_time(e1)
+    clocks = None
+    if sampler:
+        sampler.stop_flag = True
+        sampler.join()
+        clocks = sampler.summary()
+    if b.world > 1:
+        t = torch.tensor([cold_ms, warm_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        cold_ms, warm_ms = t.tolist()
+    return cold_ms, warm_ms, int(launches), float(elbos[K - 1]), clocks
+
+
+def e2e_estimate_gradient(b, K, W, torch, dist, ext, flush):
+    """End to end through the reference-facing call: estimate_gradient! with HOST buffers (lambda in, gradient +
+    value out: both transfers inside the timed region), then the host-side Optimisers.update! + ClipScale +
+    PolynomialAveraging of `step` (common.jl:91-94) as compiled host code (avi_host_update).  Wall clock, L2 flushed and
+    the device idle before every step.  Returns (seconds for K steps, breakdown dict)."""
+    avi = b.avi
+    host = avi.HostUpdate(b.alg.optimizer, b.alg.operator, b.alg.averager, b.q0.destructure(), scale_offset=b.D)
+    gbuf = np.empty(b.obj.P, np.float32)
+    b.obj.seed(b.cfg["seed"], 0)
+    tot, t_call, t_upd = 0.0, 0.0, 0.0
+    for k in range(W + K):
+        with torch.cuda.stream(ext):
+            flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        v, g, e = b.obj.estimate_gradient(host.lam, out=gbuf)
+        t1 = time.perf_counter()
+        host.update(g)
+        t2 = time.perf_counter()
+        if k >= W:
+            tot += t2 - t0; t_call += t1 - t0; t_upd += t2 - t1
+    if b.world > 1:
+        t = torch.tensor([tot], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        tot = t.item()
+    return tot, {"estimate_gradient_call_us": 1e6 * t_call / K, "host_update_us": 1e6 * t_upd / K}
+
+
+def kernel_times(b, torch, ext, flush, names, reps=5):
+    """Per-kernel device times: eager launches, CUDA events inside the library around the named kernels, L2 flushed."""
+    vals, elbos = np.empty(4, np.float32), np.empty(4, np.float32)
+    b.ctx.timing(True)
+    for _ in range(reps):
+        with torch.cuda.stream(ext):
+            flush.zero_()
+        b.run_steps(1, vals, elbos)
+    b.ctx.timing(False)
+    out = {}
+    for name in names:
+        ms, cnt = b.ctx.kernel_time(name)
+        if cnt:
+            out[name] = ms / cnt
+    return out
+
+
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:   # noqa: BLE001
+        return {}, "fallback (B200_PROFILING.md)"
+
+
+def roofline_for(b, ktime, peaks, src, x3=False):
+    """Dominant kernel of the step against the tensor roofline.  achieved = ALGORITHMIC FLOPs per launch (SURVEY.md 8d:
+    4 n d M for the forward + backward contraction pair, 2 n d M for a single contraction kernel; the 3xTF32 mode issues
+    3x the tensor work for the same algorithmic figure) / the kernel's average launch duration (CUDA events around the
+    eager launch on the library stream, L2 flushed: includes the launch overhead, i.e. conservative)."""
+    cfg = b.cfg
+    bf16 = peaks.get("bf16_tflops", 1590.0)
+    n_loc, d, m_loc = (b.rows_local if not b.subsampled else cfg["batch"]), cfg["d"], b.m_loc
+    if "glm_step" in ktime:
+        dom, flops, kname = "glm_step", 4.0 * n_loc * d * m_loc, "k_glm_mf_step (sample + forward + backward + tail, one launch)"
+    else:
+        cands = {k: v for k, v in ktime.items() if k in ("glm_fwd", "glm_bwd")}
+        if not cands:
+            return None
+        dom = max(cands, key=cands.get)
+        flops, kname = 2.0 * n_loc * d * m_loc, f"k_gemm_tc<{dom}>"
+    ach = flops / (ktime[dom] * 1e-3) / 1e12
+    peak = bf16 / 2.0 / (3.0 if x3 else 1.0)
+    traffic = None
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of this kernel
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+        if b.world == 1 and b.name == "c2" and not x3:
+            traffic = tr["dram_bytes_per_launch"].get(dom)
+    except Exception:   # noqa: BLE001
+        pass
+    return {"bound": "tensor", "kernel": kname, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+            "traffic": traffic,
+            "peak_note": f"kind::tf32 dense = 1/2 of the {src} bf16 cuBLAS peak ({bf16} TFLOP/s)"
+                         + (", / 3 for the 3xTF32 mode (three tensor products per algorithmic product)" if x3 else "")
+                         + f"; frac of the bf16 figure itself: {ach / bf16:.4f}",
+            "flops_per_launch": flops, "kernel_ms": {k: round(v, 5) for k, v in ktime.items()}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200")
+    ap.add_argument("--config", default="c2", choices=list(CONFIGS))
     ap.add_argument("--gemm", default="tf32")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--extras", dest="extras", action="store_true", default=None,
+                    help="also measure the other BASELINE.json configs (default: on for c2)")
+    ap.add_argument("--no-extras", dest="extras", action="store_false")
     ap.add_argument("--shard", default="rows", choices=["rows", "samples"],
                     help="multi-GPU axis: data rows (n-axis, default: every rank ingests X/N) or Monte-Carlo samples "
                          "(M-axis: every rank streams all of X)")
@@ -181,49 +466,17 @@ def main():
     import torch
     import torch.distributed as dist
     import advancedvi_jl_b200 as avi
-    from advancedvi_jl_b200 import parallel
 
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     K, W = args.steps, max(args.warmup, 3)
-
-    X, y = synth(N_ROWS, N_FEAT, SEED)
+    cfg = CONFIGS[args.config]
     ctx = avi.Context(local_rank)
-    D = N_FEAT + 1
-    P = 2 * D
-    q0 = avi.MeanFieldGaussian(np.zeros(D, np.float32), np.ones(D, np.float32))
-    alg = avi.KLMinRepGradDescent(optimizer=avi.Adam(1e-3), n_samples=N_MC, operator=avi.ClipScale())
-    rows_local = N_ROWS
-    if world > 1 and args.shard == "rows":
-        r0, rows_local = parallel.row_shard(N_ROWS, rank, world, align=32)
-        prob = avi.LogReg(ctx, X[r0:r0 + rows_local], y[r0:r0 + rows_local], n_data=N_ROWS, gemm=args.gemm)
-        prob.set_data_shard(world, N_ROWS, include_prior=(rank == 0))
-    else:
-        prob = avi.LogReg(ctx, X, y, gemm=args.gemm)
-    obj = avi.Objective(SEED, alg.objective, q0, prob)
-    if world > 1:
-        parallel.connect(ctx, max_floats=4 * 1056 + 64, native=True)
-        if args.shard == "rows":
-            from advancedvi_jl_b200 import _lib as _L
-            obj.set_shard_axis(_L.SHARD_ROWS)
-        else:
-            m0, ml = parallel.sample_shard(N_MC, rank, world)
-            obj.set_sample_shard(m0, ml)
-    from advancedvi_jl_b200.api import _OptState
-    from advancedvi_jl_b200 import _lib as L
-    import ctypes as C
-    state = _OptState(alg, obj, q0)
-
     ext = torch.cuda.ExternalStream(ctx.stream(), device=local_rank)
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
-    vals = np.empty(max(K, W), np.float32)
-    elbos = np.empty_like(vals)
-    nd = C.c_int32()
-
-    def run_steps(n):
-        L.check(L.lib.avi_opt_steps(state.h, n, L.fptr(vals), L.fptr(elbos), C.byref(nd)), ctx.h)
-        assert nd.value == n, "objective diverged"
+    peaks, src = load_peaks()
+    hbm = peaks.get("hbm_gbs", 6650.0)
 
     def barrier():
         torch.cuda.synchronize()
@@ -231,196 +484,163 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    # ---- device-resident steps: (a) L2 flushed between timed steps, (b) back-to-back graph replays ----
-    run_steps(W)
-    launches_per_step = None
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    barrier()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    l0 = ctx.launch_count()
-    # the K iterations are enqueued without a host round trip (avi_opt_steps_begin / _enqueue / _end), so the event
-    # pairs bracket device work only: flush | ev0 | one captured iteration | ev1
-    state.steps_begin(K)
-    for k in range(K):
-        with torch.cuda.stream(ext):
-            flush.zero_()                                   # evict X, R, Z from L2 (untimed)
-            ev[k][0].record(ext)
-        state.steps_enqueue(1)
-        ev[k][1].record(ext)
-    _, cold_elbos, n_cold = state.steps_end()
-    assert n_cold == K, "objective diverged"
-    barrier()
-    launches = ctx.launch_count() - l0
-    cold_ms = sum(a.elapsed_time(b) for a, b in ev)
-    # back-to-back (L2-resident) replays of the captured iteration, one sync for all K
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(ext)
-    run_steps(K)
-    e1.record(ext)
-    barrier()
-    warm_ms = e0.elapsed_time(e1)
-    sampler.stop_flag = True
-    sampler.join()
-    if world > 1:
-        t = torch.tensor([cold_ms, warm_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        cold_ms, warm_ms = t.tolist()
-    final_elbo = float(elbos[K - 1])
-
-    # ---- end-to-end through the reference-facing call: estimate_gradient! with HOST buffers, then the host-side
-    # Optimisers.update! + ClipScale + PolynomialAveraging of `step` (common.jl:91-94) as compiled host code
-    # (avi_host_update; a numpy version of the same update costs ~45 us per step and would dominate) ----
-    host = avi.HostUpdate(alg.optimizer, alg.operator, alg.averager, q0.destructure(), scale_offset=D)
-    gbuf = np.empty(P, np.float32)
-    obj.seed(SEED, 0)
-    e2e_s = 0.0
-    for k in range(W + K):
-        with torch.cuda.stream(ext):
-            flush.zero_()
-        torch.cuda.synchronize()
+    b = Bench(args.config, args, ctx, rank, world, local_rank, args.gemm)
+    D, P = b.D, b.obj.P
+    cold_ms, warm_ms, launches, final_elbo, clocks = device_loop(b, K, W, torch, dist, ext, flush, barrier, local_rank)
+    meanfield = cfg["family"] == "meanfield"
+    if meanfield and cfg["objective"] == "rep" and not b.subsampled:
+        e2e_s, e2e_parts = e2e_estimate_gradient(b, K, W, torch, dist, ext, flush)
+        e2e = {"value": K / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": 4 * P, "d2h_bytes_per_step": 4 * (P + 5),
+               "path": "avi_obj_estimate_gradient (estimate_gradient! boundary: host lambda in, host gradient + value + "
+                       "completion flag out) + host Adam/ClipScale/averaging (avi_host_update); wall clock, L2 flushed "
+                       "and device idle before every step", "breakdown": e2e_parts}
+    else:
+        # the call a user makes for these configs is optimize(): one blocking call per chunk of iterations with the
+        # minibatch indices (c5) going host -> device and the ELBO trace coming back
+        vals, elbos = np.empty(K, np.float32), np.empty(K, np.float32)
+        barrier()
         t0 = time.perf_counter()
-        v, g, e = obj.estimate_gradient(host.lam, out=gbuf)  # H2D lambda, kernels, D2H gradient + value
-        host.update(g)
+        b.run_steps(K, vals, elbos)
         dt = time.perf_counter() - t0
-        if k >= W:
-            e2e_s += dt
-    if world > 1:
-        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = t.item()
-
-    # ---- per-kernel device times (eager launches, CUDA events inside the library) -> roofline ----
-    ctx.timing(True)
-    for _ in range(3):
-        with torch.cuda.stream(ext):
-            flush.zero_()
-        run_steps(1)
-    ctx.timing(False)
-    ktime = {}
-    for name in ("sample", "glm_fwd", "glm_bwd"):
-        ms, cnt = ctx.kernel_time(name)
-        ktime[name] = ms / max(cnt, 1)
+        if world > 1:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = t.item()
+        e2e = {"value": K / dt, "unit": "steps/s", "h2d_bytes_per_step": 4 * cfg.get("batch", 0), "d2h_bytes_per_step": 8,
+               "path": "avi_opt_steps[_subsampled] (the optimize() loop: minibatch indices host -> device, (value, elbo) trace "
+                       "device -> host, one synchronisation per call of K iterations); wall clock"}
+    ktime = kernel_times(b, torch, ext, flush, ("glm_step", "sample", "glm_fwd", "glm_bwd", "gemm_store"))
+    roofline = roofline_for(b, ktime, peaks, src, x3=args.gemm == "tf32x3")
 
     # the sample+transform kernel at a bandwidth-relevant size (outputs >> 126 MB L2): same kernel, M = 32768
     sample_large = None
-    if world == 1:
+    if world == 1 and args.config == "c2":
         M_big = 32768
         qb = avi.MeanFieldGaussian(np.zeros(D, np.float32), np.ones(D, np.float32))
         pb = avi.MvNormalDiag(ctx, np.zeros(D, np.float32), np.ones(D, np.float32))
-        ob = avi.Objective(SEED, avi.RepGradELBO(8), qb, pb)
-        ob.estimate_objective(SEED, qb, M_big)                      # sizes the buffers (untimed)
+        ob = avi.Objective(cfg["seed"], avi.RepGradELBO(8), qb, pb)
+        ob.estimate_objective(cfg["seed"], qb, M_big)                      # sizes the buffers (untimed)
         ctx.timing(True)
         for _ in range(5):
-            ob.estimate_objective(SEED, qb, M_big)
+            ob.estimate_objective(cfg["seed"], qb, M_big)
         ctx.timing(False)
         ms_b, cnt_b = ctx.kernel_time("sample")
         ld = (D + 3) // 4 * 4
-        bytes_b = 4 * (2 * D + 2 * ld * M_big)                      # read mu, s; write Z and eps (materialised)
-        sample_large = {"M": M_big, "bytes_per_launch": bytes_b, "ms": ms_b / max(cnt_b, 1),
-                        "achieved_gbs": bytes_b / (ms_b / max(cnt_b, 1) * 1e-3) / 1e9 if ms_b > 0 else None}
+        per = ms_b / max(cnt_b, 1)
+        alg_bytes = 4 * (2 * D + D * M_big)                                # read mu, s; write Z
+        moved_bytes = 4 * (2 * D + 2 * ld * M_big)                         # + eps materialised for the reduction kernels
+        sample_large = {"M": M_big, "ms": per, "algorithmic_bytes": alg_bytes, "moved_bytes": moved_bytes,
+                        "achieved_gbs_algorithmic": alg_bytes / (per * 1e-3) / 1e9 if per > 0 else None,
+                        "achieved_gbs_moved": moved_bytes / (per * 1e-3) / 1e9 if per > 0 else None,
+                        "frac_algorithmic": alg_bytes / (per * 1e-3) / 1e9 / hbm if per > 0 else None,
+                        "frac_moved": moved_bytes / (per * 1e-3) / 1e9 / hbm if per > 0 else None, "peak_gbs": hbm}
         ob.close(); pb.close()
-
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:   # noqa: BLE001
-        pass
-    bf16 = peaks.get("bf16_tflops", 1590.0)
-    hbm = peaks.get("hbm_gbs", 6650.0)
-    src = "measured" if peaks else "fallback"
-    m_loc = N_MC // world if (world > 1 and args.shard == "samples") else N_MC
-    flops_fwd = 2.0 * rows_local * N_FEAT * m_loc
-    dom = "glm_fwd" if ktime["glm_fwd"] >= ktime["glm_bwd"] else "glm_bwd"
-    ach = flops_fwd / (ktime[dom] * 1e-3) / 1e12 if ktime[dom] > 0 else None
-    traffic = None
-    try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["dram_bytes_per_launch"].get(dom)
-        if world > 1:
-            traffic = None   # captured at N = 1
-    except Exception:   # noqa: BLE001
-        pass
-    roofline = {"bound": "tensor", "kernel": f"k_gemm_tc<{dom}>", "achieved": ach, "peak": bf16 / 2.0, "unit": "TFLOP/s",
-                "frac": (ach / (bf16 / 2.0)) if ach else None, "traffic": traffic,
-                "peak_note": f"kind::tf32 dense = 1/2 of the {src} bf16 cuBLAS peak ({bf16} TFLOP/s); "
-                             f"frac of the bf16 figure itself: {ach / bf16 if ach else None}",
-                "flops_per_launch": flops_fwd,
-                "kernel_ms": {k: round(v, 5) for k, v in ktime.items()},
-                "sample_kernel_hbm": {"bytes_per_launch": 4 * (2 * D + 2 * D * m_loc),
-                                      "achieved_gbs": (4 * (2 * D + 2 * D * m_loc) / (ktime["sample"] * 1e-3) / 1e9)
-                                      if ktime["sample"] > 0 else None,
-                                      "peak_gbs": hbm, "note": "2 MB launch: latency-bound at this shape (SURVEY F8)",
-                                      "large_shape": dict(sample_large, frac=(sample_large["achieved_gbs"] / hbm
-                                                          if sample_large and sample_large["achieved_gbs"] else None))
-                                      if sample_large else None}}
+    if roofline is not None and sample_large is not None:
+        roofline["sample_kernel_hbm"] = sample_large
 
     line = {
         "metric": "ELBO grad-steps/sec", "value": K / (cold_ms * 1e-3), "unit": "steps/s", "n_gpus": world,
-        "steps": K, "warmup": W, "ms_per_step": cold_ms / K, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "tf32" if args.gemm == "tf32" else "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "optimizer": "Adam(1e-3)+ClipScale+PolynomialAveraging",
-                   "l2": "flushed between timed steps (256 MiB device write, untimed); per-step CUDA events",
-                   "sharding": "none" if world == 1 else
-                   (f"n-axis: {rows_local} data rows per rank, all {N_MC} samples on every rank; exchange = one-shot NVLink "
-                    f"all-reduce kernels of [sum g, sum g*eps] (2x1056 floats) and log pi ({N_MC} floats)"
-                    if args.shard == "rows" else
-                    f"M-axis: {m_loc} samples per rank; exchange = one-shot NVLink all-reduce of the partial sums"),
-                   "contraction": "tcgen05 kind::tf32 (operands rounded to nearest TF32, fp32 accumulate)"
-                   if args.gemm == "tf32" else "SIMT fp32"},
+        "steps": K, "warmup": W, "ms_per_step": cold_ms / K, "higher_is_better": True, "scaling": cfg["scaling"],
+        "vs_baseline": None, "dtype": {"tf32": "tf32", "tf32x3": "tf32x3", "fp32": "f32"}.get(args.gemm, args.gemm),
+        "data": "synthetic",
+        "config": {"workload": cfg["workload"], "optimizer": OPT_DESC[cfg["opt"][0]],
+                   "l2": ("inputs larger than L2 (X = 2 GB; the gathered minibatch is produced inside the step); one event pair around K steps"
+                          if b.subsampled else
+                          "flushed between timed steps (256 MiB device write, untimed); per-step CUDA events"),
+                   "sharding": b.sharding_desc(),
+                   "contraction": {"tf32": "tcgen05 kind::tf32 (operands rounded to nearest TF32, fp32 accumulate)",
+                                   "tf32x3": "tcgen05 kind::tf32, 3xTF32 split operands (fp32-grade)",
+                                   "fp32": "SIMT fp32"}.get(args.gemm)},
         "value_l2_resident": K / (warm_ms * 1e-3), "ms_per_step_l2_resident": warm_ms / K,
-        "e2e": {"value": K / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": 4 * P, "d2h_bytes_per_step": 4 * (P + 5),   # lambda in; gradient + 4 scalars + flag out
-                "path": "avi_obj_estimate_gradient (estimate_gradient! boundary, host lambda in / host gradient out) "
-                        "+ host Adam/ClipScale/averaging (avi_host_update), L2 flushed between steps"},
-        "gpu_launches": int(launches), "final_elbo": final_elbo,
-        "clocks": sampler.summary(), "roofline": roofline,
+        "e2e": e2e, "gpu_launches": launches, "launches_per_step": launches / K, "final_elbo": final_elbo,
+        "clocks": clocks, "roofline": roofline,
     }
 
-    # the fp32-grade tensor-core mode (3xTF32 by K-concatenation) on the same workload, L2-resident replays
-    if world == 1 and args.gemm == "tf32":
-        p3 = avi.LogReg(ctx, X, y, gemm="tf32x3")
-        o3 = avi.Objective(SEED, alg.objective, q0, p3)
-        s3 = _OptState(alg, o3, q0)
-        L.check(L.lib.avi_opt_steps(s3.h, W, L.fptr(vals), L.fptr(elbos), C.byref(nd)), ctx.h)
-        barrier()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record(ext)
-        L.check(L.lib.avi_opt_steps(s3.h, K, L.fptr(vals), L.fptr(elbos), C.byref(nd)), ctx.h)
-        a1.record(ext)
-        barrier()
-        line["alt_precision"] = {"mode": "tf32x3 (hi/lo split operands, 3 tensor-core products, fp32-grade)",
-                                 "value_l2_resident": K / (a0.elapsed_time(a1) * 1e-3), "unit": "steps/s"}
-        s3.close(); o3.close(); p3.close()
+    # ---- the fp32-grade tensor-core mode (3xTF32 by K-concatenation) as a complete second record ----
+    b3 = None
+    if world == 1 and args.config == "c2" and args.gemm == "tf32":
+        try:
+            b3 = Bench("c2", args, ctx, rank, world, local_rank, "tf32x3")
+            c3_ms, w3_ms, l3, fe3, _ = device_loop(b3, K, W, torch, dist, ext, flush, barrier)
+            e3_s, e3_parts = e2e_estimate_gradient(b3, K, W, torch, dist, ext, flush)
+            k3 = kernel_times(b3, torch, ext, flush, ("glm_step", "glm_fwd", "glm_bwd"))
+            line["alt_precision"] = {
+                "mode": "tf32x3 (hi/lo split operands, 3 tensor-core products per algorithmic product, fp32-grade)",
+                "value": K / (c3_ms * 1e-3), "ms_per_step": c3_ms / K, "value_l2_resident": K / (w3_ms * 1e-3),
+                "unit": "steps/s", "e2e": {"value": K / e3_s, "unit": "steps/s", "breakdown": e3_parts},
+                "gpu_launches": l3, "final_elbo": fe3, "roofline": roofline_for(b3, k3, peaks, src, x3=True)}
+        except Exception as ex:   # noqa: BLE001
+            line["alt_precision"] = {"error": repr(ex)}
 
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    # ---- CPU baseline (bounded sample of the same workload) and parity of the timed configuration ----
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.config == "c2":
         from oracle import family as F, models as Mo, objectives as O, philox as Ph
-        probo = Mo.LogReg(X, y)
+        probo = Mo.LogReg(b.X, b.y)
         qo = F.MeanFieldGaussian(np.zeros(D), np.ones(D))
-        ms = 8
-        eps = Ph.normal_matrix(SEED, 0, D, ms)
-        O.repgrad_value_and_gradient(qo.destructure(), qo, probo, eps[:, :2], "ClosedFormEntropy", per_sample=True)
+        M = cfg["M"]
+        epsf = Ph.normal_matrix(cfg["seed"], 0, D, M)
+        O.repgrad_value_and_gradient(qo.destructure(), qo, probo, epsf, "ClosedFormEntropy")
         t0 = time.perf_counter()
-        reps = 4
+        reps = 10
         for _ in range(reps):
-            vo, go, eo = O.repgrad_value_and_gradient(qo.destructure(), qo, probo, eps, "ClosedFormEntropy", per_sample=True)
-        dt = (time.perf_counter() - t0) / reps * (N_MC / ms)
-        epsf = Ph.normal_matrix(SEED, 0, D, N_MC)
+            vo, go, eo = O.repgrad_value_and_gradient(qo.destructure(), qo, probo, epsf, "ClosedFormEntropy")
+        bt = (time.perf_counter() - t0) / reps
         t0 = time.perf_counter()
-        vo, go, eo = O.repgrad_value_and_gradient(qo.destructure(), qo, probo, epsf, "ClosedFormEntropy")
-        bt = time.perf_counter() - t0
-        # parity of the timed configuration against the fp64 oracle on the same eps (step 0)
-        obj.seed(SEED, 0)
-        v, g, e = obj.estimate_gradient(q0.destructure())
-        line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "steps/s", "cores": os.cpu_count(), "kind": "port",
-                                "sample": f"{reps} x {ms}/{N_MC} per-sample logdensity_and_gradient calls (M GEMVs over X, "
-                                          f"Float64, numpy/OpenBLAS), scaled by {N_MC // ms}",
-                                "batched_gemm_steps_per_s": 1.0 / bt}
+        reps_ps = 4
+        for _ in range(reps_ps):
+            O.repgrad_value_and_gradient(qo.destructure(), qo, probo, epsf, "ClosedFormEntropy", per_sample=True)
+        pt = (time.perf_counter() - t0) / reps_ps
+        line["cpu_baseline"] = {"value": 1.0 / bt, "unit": "steps/s", "cores": os.cpu_count(), "kind": "port",
+                                "sample": f"{reps} whole value-and-gradient evaluations (all {M} samples, one batched GEMM per pass, "
+                                          "Float64 numpy/OpenBLAS, all cores): best-effort CPU, the conservative denominator",
+                                "reference_shaped_steps_per_s": 1.0 / pt,
+                                "reference_shaped_sample": f"{reps_ps} whole evaluations as {M} per-sample logdensity_and_gradient calls"}
+        # parity of the timed configurations against the fp64 oracle on the same eps (step 0)
+        b.obj.seed(cfg["seed"], 0)
+        v, g, e = b.obj.estimate_gradient(b.q0.destructure())
         line["parity"] = {"elbo_rel_err_vs_fp64_oracle": abs(v - vo) / abs(vo),
                           "grad_rel_err_vs_fp64_oracle": float(np.linalg.norm(g - go) / np.linalg.norm(go)),
                           "tolerance": {"elbo": 5e-4, "grad": 2e-3}}
+        if b3 is not None and "error" not in line.get("alt_precision", {}):
+            b3.obj.seed(cfg["seed"], 0)
+            v3, g3, e3 = b3.obj.estimate_gradient(b3.q0.destructure())
+            line["alt_precision"]["parity"] = {"elbo_rel_err_vs_fp64_oracle": abs(v3 - vo) / abs(vo),
+                                               "grad_rel_err_vs_fp64_oracle": float(np.linalg.norm(g3 - go) / np.linalg.norm(go)),
+                                               "tolerance": {"elbo": 1e-5, "grad": 5e-5}}
+    if b3 is not None:
+        b3.close()
+
+    # ---- the other BASELINE.json configs, compact (bounded step counts; same timing rules) ----
+    extras = args.extras if args.extras is not None else (args.config == "c2")
+    if extras:
+        line["configs"] = {}
+        b.close()
+        b = None
+        for name, (k2, w2) in (("c3", (40, 5)), ("c4a", (10, 3)), ("c4b", (10, 3)), ("c5", (100, 10))):
+            if name == args.config:
+                continue
+            try:
+                t_setup = time.perf_counter()
+                bx = Bench(name, args, ctx, rank, world, local_rank, args.gemm)
+                setup_s = time.perf_counter() - t_setup
+                cm, wm, ln, fe, _ = device_loop(bx, k2, w2, torch, dist, ext, flush, barrier)
+                kt = kernel_times(bx, torch, ext, flush, ("glm_step", "glm_fwd", "glm_bwd"), reps=3)
+                rf = roofline_for(bx, kt, peaks, src)
+                line["configs"][name] = {"workload": CONFIGS[name]["workload"], "value": k2 / (cm * 1e-3), "unit": "steps/s",
+                                         "ms_per_step": cm / k2, "value_l2_resident": k2 / (wm * 1e-3), "steps": k2, "warmup": w2,
+                                         "scaling": CONFIGS[name]["scaling"], "sharding": bx.sharding_desc(),
+                                         "launches_per_step": ln / k2, "final_elbo": fe, "setup_s": round(setup_s, 1),
+                                         "roofline": None if rf is None else {k: rf[k] for k in ("kernel", "achieved", "peak", "frac", "unit")},
+                                         "parity": "tests/test_gpu_objective_parity.py (one-step oracle parity at this config's width)"}
+                bx.close()
+                del bx
+            except Exception as ex:   # noqa: BLE001
+                line["configs"][name] = {"error": repr(ex)}
     if rank == 0:
         print(json.dumps(line), flush=True)
-    state.close(); obj.close(); prob.close(); ctx.close()
+    if b is not None:
+        b.close()
+    ctx.close()
     if world > 1:
         dist.destroy_process_group()
 

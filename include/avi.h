@@ -94,6 +94,9 @@ int32_t avi_ctx_set_allreduce(avi_ctx* ctx, avi_allreduce_fn fn, void* user, int
  * then avi_comm_connect with the nranks x 64-byte table. */
 int32_t avi_comm_buffer(avi_ctx* ctx, int64_t max_floats, char* handle_out_64);
 int32_t avi_comm_connect(avi_ctx* ctx, int32_t rank, int32_t nranks, const char* handles);
+/* Unmap the peers' buffers (collective by convention: every rank calls it, then the ranks synchronise, before any
+ * rank destroys its context or calls avi_comm_buffer again). */
+int32_t avi_comm_disconnect(avi_ctx* ctx);
 /* the cudaStream_t every call on this ctx enqueues on (for hosts that order their own work after it) */
 void* avi_ctx_stream(avi_ctx* ctx);
 
@@ -127,6 +130,11 @@ int32_t avi_model_set_data_shard(avi_model* model, int32_t nshards, int64_t rows
 int32_t avi_model_dimension(const avi_model* model);      /* LogDensityProblems.dimension    */
 int32_t avi_model_capability(const avi_model* model);     /* LogDensityProblems.capabilities */
 int32_t avi_model_set_gemm_mode(avi_model* model, int32_t gemm_mode);
+/* How iterations over this target are launched: 0 = one kernel per stage (sample / forward / backward / tail),
+ * 1 = (default; env AVI_FUSED_STEP) the whole iteration as ONE persistent kernel where the fixed per-launch costs
+ * matter, 2 = always the single kernel.  Results agree up to summation order.  AVI_ERR_UNSUPPORTED for targets
+ * without a fused path. */
+int32_t avi_model_set_fused_step(avi_model* model, int32_t mode);
 /* Batched LogDensityProblems.logdensity / logdensity_and_gradient on device data:
  * Z_dev is D x M column-major with leading dimension ldz; logp_dev has M entries; G_dev is
  * D x M with leading dimension ldz. */

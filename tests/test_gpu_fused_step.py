@@ -1,0 +1,262 @@
+"""The whole-iteration kernel (csrc/step_fused.cu: sample -> forward contraction -> backward contraction -> [exchange] ->
+finalize + update in ONE launch) against the fp64 oracle on identical Philox eps, and against the one-kernel-per-stage
+path of the same library.  Every call goes through the C ABI; `launch_count` deltas prove which path ran.
+
+Tolerances: TF32 contractions 5e-4 on the value slot / ELBO and 2e-3 on the gradient norm;
+3xTF32 (fp32-grade) 1e-5 / 5e-5; optimiser trajectories 2e-3 (TF32) over the stated number of steps.
+"""
+import numpy as np
+import pytest
+
+from oracle import family as F, models as Mo, objectives as O, optim as Op, philox as P, reshuffling as R
+
+pytestmark = pytest.mark.gpu
+
+KEY = 0x38BEF07CF9CC549D
+
+
+@pytest.fixture(scope="module")
+def ctx(avi):
+    c = avi.Context(0)
+    yield c
+    c.close()
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)
+
+
+def make_pair(avi, ctx, name, n, d, gemm, seed=5, n_data=None):
+    fam = "gaussian" if name == "gaussglm" else "bernoulli_logit"
+    X, y = Mo.synth_glm_data(n, d, seed=seed, family=fam)
+    if name == "gaussglm":
+        return avi.GaussGLM(ctx, X, y, n_data=n_data, gemm=gemm), Mo.GaussGLM(X, y, n_data=n_data)
+    variant = "basic" if name == "logreg_basic" else "subsampling"
+    return (avi.LogReg(ctx, X, y, n_data=n_data, variant=variant, gemm=gemm), Mo.LogReg(X, y, n_data=n_data, variant=variant))
+
+
+def make_q(avi, D):
+    mu = (0.05 * np.cos(np.arange(D))).astype(np.float32)
+    s = (0.2 + 0.02 * (np.arange(D) % 5)).astype(np.float32)
+    return avi.MeanFieldGaussian(mu, s), F.MeanFieldGaussian(mu.astype(np.float64), s.astype(np.float64))
+
+
+ENT = ["ClosedFormEntropy", "MonteCarloEntropy", "StickingTheLandingEntropy", "ClosedFormEntropyZeroGradient",
+       "StickingTheLandingEntropyZeroGradient"]
+
+
+# ragged shapes on purpose: n not a multiple of 32, d not a multiple of 4 (D = d + 1 odd or even), M below / above one
+# 128-row accumulator block, M above the CTA count (several samples per CTA in the sample phase)
+@pytest.mark.parametrize("n,d,M", [(40, 4, 3), (300, 37, 17), (1000, 160, 130), (513, 95, 300), (2000, 64, 700)])
+@pytest.mark.parametrize("gemm,tol_v,tol_g", [("tf32", 5e-4, 2e-3), ("tf32x3", 1e-5, 5e-5)])
+def test_fused_estimate_gradient_matches_oracle(avi, ctx, n, d, M, gemm, tol_v, tol_g):
+    """estimate_gradient! boundary (host lambda in, host gradient out) through the single kernel, all five entropy
+    estimators of src/algorithms/entropy.jl, two consecutive calls (the step counter moves eps)."""
+    prob, probo = make_pair(avi, ctx, "logreg_subsampling", n, d, gemm, n_data=3 * n)
+    prob.set_fused_step(2)
+    D = d + 1
+    q, qo = make_q(avi, D)
+    for ent in ENT:
+        obj = avi.Objective(KEY, avi.RepGradELBO(M, getattr(avi, ent)()), q, prob)
+        obj.estimate_gradient(q.destructure())                    # first call sizes buffers (eager)
+        l0 = ctx.launch_count()
+        obj.seed(KEY, 0)
+        for step in range(2):
+            v, g, e = obj.estimate_gradient(q.destructure())
+            vo, go, eo = O.repgrad_value_and_gradient(qo.destructure(), qo, probo, P.normal_matrix(KEY, step, D, M), ent)
+            assert abs(v - vo) <= tol_v * abs(vo), (ent, step, v, vo)
+            assert abs(e - eo) <= tol_v * abs(eo)
+            assert relerr(g, go) < tol_g, (ent, step, relerr(g, go))
+        assert ctx.launch_count() - l0 == 2 * 2          # stage-in + ONE kernel per call
+        assert obj.step_counter() == 2
+        obj.close()
+    prob.close()
+
+
+@pytest.mark.parametrize("name", ["logreg_basic", "gaussglm"])
+def test_fused_other_targets(avi, ctx, name):
+    n, d, M = 700, 96, 64
+    prob, probo = make_pair(avi, ctx, name, n, d, "tf32")
+    prob.set_fused_step(2)
+    q, qo = make_q(avi, d + 1)
+    obj = avi.Objective(KEY, avi.RepGradELBO(M), q, prob)
+    v, g, e = obj.estimate_gradient(q.destructure())
+    vo, go, eo = O.repgrad_value_and_gradient(qo.destructure(), qo, probo, P.normal_matrix(KEY, 0, d + 1, M), "ClosedFormEntropy")
+    assert abs(v - vo) <= 5e-4 * abs(vo) and relerr(g, go) < 2e-3
+    obj.close(); prob.close()
+
+
+def test_fused_agrees_with_staged_path(avi, ctx):
+    """Same library, same inputs: one kernel per stage (mode 0) vs the single kernel (mode 2).  The contraction plans
+    and epilogues are shared, so the gradient sums agree to fp32 summation order."""
+    n, d, M = 1500, 200, 256
+    X, y = Mo.synth_glm_data(n, d, seed=8)
+    q, _ = make_q(avi, d + 1)
+    res = {}
+    for mode in (0, 2):
+        prob = avi.LogReg(ctx, X, y, gemm="tf32")
+        prob.set_fused_step(mode)
+        obj = avi.Objective(KEY, avi.RepGradELBO(M, avi.StickingTheLandingEntropy()), q, prob)
+        res[mode] = obj.estimate_gradient(q.destructure())
+        obj.close(); prob.close()
+    (v0, g0, e0), (v2, g2, e2) = res[0], res[2]
+    assert abs(v0 - v2) <= 2e-6 * abs(v0) and relerr(g2, g0) < 2e-5
+
+
+RULES = {
+    "descent": (lambda a: a.Descent(1e-2), lambda: Op.Descent(1e-2)),
+    "adam": (lambda a: a.Adam(1e-2), lambda: Op.Adam(1e-2)),
+    "dog": (lambda a: a.DoG(1e-2), lambda: Op.DoG(1e-2)),
+    "dowg": (lambda a: a.DoWG(1e-2), lambda: Op.DoWG(1e-2)),
+}
+
+
+def oracle_run(qo, probo, T, M, rule, op, avg, entropy, key):
+    st = Op.sgd_init(qo, rule, avg)
+
+    def grad_fn(params, t):
+        v, g, e = O.repgrad_value_and_gradient(params, qo, probo, P.normal_matrix(key, t - 1, len(qo), M), entropy)
+        return v, g, dict(elbo=e)
+    elbos = [Op.sgd_step(st, qo, grad_fn, rule, op, avg)["elbo"] for _ in range(T)]
+    return st, np.array(elbos)
+
+
+@pytest.mark.parametrize("rule", list(RULES))
+@pytest.mark.parametrize("entropy", ["ClosedFormEntropy", "StickingTheLandingEntropy"])
+def test_fused_optimize_trajectory_matches_oracle(avi, ctx, rule, entropy):
+    """12 iterations of `step` (common.jl:75-104) in 12 launches: rule + ClipScale + PolynomialAveraging follow the
+    fp64 oracle trajectory on the same eps; the fp32-grade contraction keeps lambda within 2e-4."""
+    n, d, M, T = 400, 30, 48, 12
+    prob, probo = make_pair(avi, ctx, "logreg_subsampling", n, d, "tf32x3")
+    prob.set_fused_step(2)
+    q, qo = make_q(avi, d + 1)
+    alg = avi.KLMinRepGradDescent(optimizer=RULES[rule][0](avi), entropy=getattr(avi, entropy)(), n_samples=M,
+                                  operator=avi.ClipScale())
+    _, _, warm = avi.optimize(KEY, alg, 1, prob, q)            # sizes buffers, captures the iteration
+    warm.close(); warm.obj.close()
+    l0 = ctx.launch_count()
+    qa, info, state = avi.optimize(KEY, alg, T, prob, q)
+    launches = ctx.launch_count() - l0
+    st, elbos = oracle_run(qo, probo, T, M, RULES[rule][1](), Op.ClipScale(), Op.PolynomialAveraging(), entropy, KEY)
+    lam, avg, _ = state.params()
+    assert np.allclose([i["elbo"] for i in info], elbos, rtol=2e-4, atol=2e-4)
+    assert relerr(lam, st.params) < 2e-4 and relerr(avg, st.avg_st[0]) < 2e-4
+    assert relerr(qa.destructure(), st.avg_st[0]) < 2e-4
+    # T launches of the iteration kernel + the per-call bookkeeping (begin-call kernel, buffer-sizing eager pass)
+    assert launches <= T + 8, launches
+    state.close(); state.obj.close(); prob.close()
+
+
+def test_fused_prox_descent_trajectory(avi, ctx):
+    """KLMinRepGradProxDescent (constructors.jl:122-157): zero-gradient entropy + proximal operator in the tail phase."""
+    n, d, M, T = 300, 20, 32, 10
+    prob, probo = make_pair(avi, ctx, "logreg_subsampling", n, d, "tf32x3")
+    prob.set_fused_step(2)
+    q, qo = make_q(avi, d + 1)
+    alg = avi.KLMinRepGradProxDescent(optimizer=avi.DoWG(1e-2), n_samples=M)
+    _, info, state = avi.optimize(KEY, alg, T, prob, q)
+    st, elbos = oracle_run(qo, probo, T, M, Op.DoWG(1e-2), Op.ProximalLocationScaleEntropy(), Op.PolynomialAveraging(),
+                           "ClosedFormEntropyZeroGradient", KEY)
+    lam, avg, _ = state.params()
+    assert relerr(lam, st.params) < 3e-4 and relerr(avg, st.avg_st[0]) < 3e-4
+    state.close(); state.obj.close(); prob.close()
+
+
+def test_fused_determinism_and_warm_start(avi, ctx):
+    """Same seed => bitwise identical run (klminrepgraddescent.jl:40-57); T/2 + T/2 through `state=` == T
+    (optimize.jl:30-40), on the single-kernel path with TF32 contractions."""
+    n, d, M, T = 900, 128, 256, 16
+    prob, _ = make_pair(avi, ctx, "logreg_subsampling", n, d, "tf32")
+    prob.set_fused_step(2)
+    q, _ = make_q(avi, d + 1)
+    alg = avi.KLMinRepGradDescent(optimizer=avi.Adam(1e-2), n_samples=M, operator=avi.ClipScale())
+    qa, info_a, sa = avi.optimize(KEY, alg, T, prob, q)
+    qb, info_b, sb = avi.optimize(KEY, alg, T, prob, q)
+    assert [i["elbo"] for i in info_a] == [i["elbo"] for i in info_b]
+    assert np.array_equal(qa.destructure(), qb.destructure())
+    _, info_h, sh = avi.optimize(KEY, alg, T // 2, prob, q)
+    qc, info_h2, sh = avi.optimize(KEY, alg, T // 2, prob, q, state=sh)
+    assert [i["elbo"] for i in info_h + info_h2] == [i["elbo"] for i in info_a]
+    assert np.array_equal(qc.destructure(), qa.destructure())
+    for s in (sa, sb, sh):
+        s.close(); s.obj.close()
+    prob.close()
+
+
+def test_fused_divergence_is_reported(avi, ctx):
+    """A non-finite value slot stops the run without applying the step (common.jl:83-89)."""
+    n, d, M = 200, 12, 16
+    prob, _ = make_pair(avi, ctx, "logreg_subsampling", n, d, "tf32")
+    prob.set_fused_step(2)
+    D = d + 1
+    mu = np.zeros(D, np.float32); mu[-1] = 60.0       # sigma = exp(60): sigma^2 overflows fp32 in the prior
+    q = avi.MeanFieldGaussian(mu, np.full(D, 0.1, np.float32))
+    alg = avi.KLMinRepGradDescent(optimizer=avi.Adam(1e-2), n_samples=M, operator=avi.ClipScale())
+    with pytest.raises(RuntimeError, match="diverged"):
+        avi.optimize(KEY, alg, 5, prob, q)
+    prob.close()
+
+
+def test_fused_subsampled_optimize_matches_oracle(avi, ctx):
+    """SubsampledObjective + ReshufflingBatchSubsampling: gather kernel + the single iteration kernel per step against
+    the oracle state machine fed the same Philox permutation (config 5 in miniature, drop-trailing swap included)."""
+    n, d, M, bs, T = 210, 24, 40, 32, 15            # 210 % 32 != 0
+    X, y = Mo.synth_glm_data(n, d, seed=11)
+    prob, probo = avi.LogReg(ctx, X, y, gemm="tf32x3"), Mo.LogReg(X, y)
+    prob.set_fused_step(2)
+    D = d + 1
+    q, qo = make_q(avi, D)
+    alg = avi.KLMinRepGradDescent(optimizer=avi.Adam(1e-2), n_samples=M, operator=avi.ClipScale(),
+                                  subsampling=avi.ReshufflingBatchSubsampling(np.arange(n), bs))
+    _, info, state = avi.optimize(KEY, alg, T, prob, q)
+    sub = R.ReshufflingBatchSubsampling(np.arange(n), bs)
+    sst = R.subsampled_init(sub, KEY)
+    rule, op, avg = Op.Adam(1e-2), Op.ClipScale(), Op.PolynomialAveraging()
+    st = Op.sgd_init(qo, rule, avg)
+    infos = []
+    for t in range(T):
+        def grad_fn(params, it):
+            nonlocal sst
+
+            def inner(ps):
+                return O.repgrad_value_and_gradient(params, qo, ps, P.normal_matrix(KEY, it - 1, D, M), "ClosedFormEntropy")[:2] + (dict(),)
+            v, g, sst, inf = R.subsampled_estimate_gradient(sub, sst, probo, inner)
+            return v, g, inf
+        infos.append(Op.sgd_step(st, qo, grad_fn, rule, op, avg))
+    assert [(i["epoch"], i["step"]) for i in info] == [(i["epoch"], i["step"]) for i in infos]
+    lam, avgp, _ = state.params()
+    assert relerr(lam, st.params) < 2e-4 and relerr(avgp, st.avg_st[0]) < 2e-4
+    state.close(); state.obj.close(); prob.close()
+
+
+def test_fused_c2_full_size(avi, ctx):
+    """BASELINE.json config 2 at full size (n = 10000, d = 1024, M = 256) through the single kernel: oracle parity of the
+    first step (TF32 tolerances) and agreement with the staged path over 5 optimiser steps."""
+    n, d, M = 10000, 1024, 256
+    rng = np.random.default_rng(1)
+    X = rng.standard_normal((n, d), dtype=np.float32) / np.float32(np.sqrt(d))
+    X[:, d - 1] = 1.0
+    beta = rng.standard_normal(d).astype(np.float32)
+    y = (rng.random(n) < 1.0 / (1.0 + np.exp(-(X @ beta)))).astype(np.float32)
+    D = d + 1
+    q = avi.MeanFieldGaussian(np.zeros(D, np.float32), np.ones(D, np.float32))
+    qo = F.MeanFieldGaussian(np.zeros(D), np.ones(D))
+    alg = avi.KLMinRepGradDescent(optimizer=avi.Adam(1e-3), n_samples=M, operator=avi.ClipScale())
+    out = {}
+    for mode in (0, 2):
+        prob = avi.LogReg(ctx, X, y, gemm="tf32")
+        prob.set_fused_step(mode)
+        obj = avi.Objective(1, avi.RepGradELBO(M), q, prob)
+        vg = obj.estimate_gradient(q.destructure())
+        obj.close()
+        _, info, state = avi.optimize(1, alg, 5, prob, q)
+        out[mode] = (vg, [i["elbo"] for i in info], state.params()[0])
+        state.close(); state.obj.close(); prob.close()
+    (v, g, e), elbos2, lam2 = out[2]
+    vo, go, eo = O.repgrad_value_and_gradient(qo.destructure(), qo, Mo.LogReg(X, y), P.normal_matrix(1, 0, D, M), "ClosedFormEntropy")
+    assert abs(v - vo) <= 5e-4 * abs(vo), (v, vo)
+    assert relerr(g, go) < 2e-3
+    (v0, g0, e0), elbos0, lam0 = out[0]
+    assert abs(v - v0) <= 2e-6 * abs(v0) and relerr(g, g0) < 2e-5
+    assert np.allclose(elbos2, elbos0, rtol=2e-6) and relerr(lam2, lam0) < 2e-5
