@@ -26,6 +26,7 @@ struct SmemCtl {
     uint64_t full[MAX_STAGES], empty[MAX_STAGES], tmem_full[2], tmem_empty[2];
     uint32_t tmem_base;
     int flag;
+    float scratch[8];               // fused iteration kernel: values handed from one phase to a later one
     alignas(16) float ys[2][512];   // FWD: y per accumulator stage (<= 256 used); BWD: reduction scratch
 };
 

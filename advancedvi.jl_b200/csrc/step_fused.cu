@@ -71,6 +71,9 @@ __device__ __forceinline__ void stamp_max(unsigned long long* tl, int slot) {
     if (tl && threadIdx.x == 0) atomicMax(tl + slot, gtime_ns());
 }
 
+// AVI_STEP_PROF: per-CTA %globaltimer stamps (StepParams.prof[blockIdx.x][32]); slot list in scripts/step_prof.py
+#define PSTAMP(prof, slot) do { if (prof) (prof)[(size_t)blockIdx.x * 32 + (slot)] = gtime_ns(); } while (0)
+
 // pipeline barriers for a phase with `stages` ring slots (one thread)
 __device__ __forceinline__ void init_pipeline(SmemCtl* ctl, int stages, int stages_prev) {
     for (int s = 0; s < stages_prev; ++s) { mbar_inval(&ctl->full[s]); mbar_inval(&ctl->empty[s]); }
@@ -111,9 +114,10 @@ __device__ __forceinline__ int preissue_early(const CUtensorMap* tmA, const CUte
 
 // One contraction phase: the single-CTA pipeline of k_gemm_tc (gemm_tc.cu) over the units u = blockIdx.x,
 // blockIdx.x + gridDim.x, ...; the ring and the accumulator stages start from their initial state.
-template <int EPI, int LIK>
+template <int EPI, int LIK, bool COH>
 __device__ __forceinline__ void tc_phase(const CUtensorMap* tmA, const CUtensorMap* tmB, const TcParams& p, SmemCtl* ctl,
-                                         uint8_t* tiles, uint32_t tmem_base, int stages, int pre_issued, int early_op) {
+                                         uint8_t* tiles, uint32_t tmem_base, int stages, int pre_issued, int early_op,
+                                         unsigned long long* prof, int ps) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NT = p.nt;
     const int stage_bytes = A_TILE_BYTES + NT * BK * 4;
@@ -147,6 +151,7 @@ __device__ __forceinline__ void tc_phase(const CUtensorMap* tmA, const CUtensorM
                     if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
             }
+            PSTAMP(prof, ps + 0);   // last operand request issued
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
@@ -163,6 +168,7 @@ __device__ __forceinline__ void tc_phase(const CUtensorMap* tmA, const CUtensorM
                 for (int kb = kb0; kb < kb1; ++kb) {
                     tc::mbar_wait(&ctl->full[stage], phase);
                     tc::fence_after_sync();
+                    if (kb == kb0 && u == first) PSTAMP(prof, ps + 1);   // first operands landed
                     const uint32_t sa = tc::smem_u32(tiles + stage * stage_bytes);
                     const uint64_t da = tc::smem_desc_k_sw128(sa);
                     const uint64_t db = tc::smem_desc_k_sw128(sa + A_TILE_BYTES);
@@ -174,6 +180,7 @@ __device__ __forceinline__ void tc_phase(const CUtensorMap* tmA, const CUtensorM
                     if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
                 tc::umma_commit(&ctl->tmem_full[as]);
+                PSTAMP(prof, ps + 2);   // last MMA of the (last) unit issued
                 if (++as == 2) { as = 0; aphase ^= 1; }
             }
         }
@@ -190,13 +197,16 @@ __device__ __forceinline__ void tc_phase(const CUtensorMap* tmA, const CUtensorM
             const bool a_ok = a < p.Ma;
             const uint32_t tacc = tmem_base + (uint32_t)(as * 256) + ((uint32_t)(quarter * 32) << 16);
             float s1, s2;
-            epilogue_unit<EPI, LIK, true>(p, ctl, as, aphase, tacc, NT, a, a_ok, bc, ks, c_begin, c_end, et, s1, s2);
+            epilogue_unit<EPI, LIK, COH>(p, ctl, as, aphase, tacc, NT, a, a_ok, bc, ks, c_begin, c_end, et, s1, s2);
+            if (et == 0) PSTAMP(prof, ps + 3);   // accumulator consumed (epilogue math of the unit done)
             tc::fence_before_sync();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&ctl->tmem_empty[as]);
             epilogue_store_partials<EPI>(p, a_ok, a, bc, ks, cq, s1, s2);
             if (EPI == EPI_GLM_BWD) epilogue_bwd_store(p, ctl, a_ok, a, bc, ks, cq, et, s1, s2);
+            if (EPI == EPI_GLM_BWD && et == 0) PSTAMP(prof, ps + 4);   // slab rows stored
             if (EPI == EPI_GLM_BWD && p.post_on) epilogue_bwd_combine(p, ctl, ab, et);
+            if (et == 0) PSTAMP(prof, ps + 5);   // unit complete
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
     }
@@ -379,7 +389,7 @@ __device__ __forceinline__ void tail_phase(const StepParams& sp, SmemCtl* ctl, c
     }
 
     MfSums S;
-    S.s0 = sl; S.s1 = sq; S.s2 = 0.f; S.s3 = 0.f; S.logdet = sn.logdet;
+    S.s0 = sl; S.s1 = sq; S.s2 = 0.f; S.s3 = 0.f; S.logdet = ctl->scratch[0];
     float value, elbo, shift_next;
     mf_outputs(D, M, objective, entropy, S, sn.shift, value, elbo, shift_next);
     const bool bad = !isfinite(value);
@@ -495,7 +505,7 @@ __device__ __forceinline__ void tail_phase(const StepParams& sp, SmemCtl* ctl, c
 // timeline slots (AVI_TIMELINE; atomicMin in 0..7, atomicMax in 8..15): first CTA 0 entered | 1 past the dependency wait |
 // 2 past barrier 0 (forward starts) | 3 past barrier 1 (backward starts) | 4 past barrier 2 (tail starts);
 // last CTA 8 left the sample phase | 9 left the forward phase | 10 left the backward phase | 11 done
-template <int LIK>
+template <int LIK, bool COH>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_glm_mf_step(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmXr,
               const __grid_constant__ CUtensorMap tmXc, const __grid_constant__ CUtensorMap tmR, const StepParams sp) {
@@ -504,6 +514,8 @@ k_glm_mf_step(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ C
     uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ctl) + sizeof(SmemCtl) + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     stamp_min(sp.tl, 0);
+    unsigned long long* const prof = sp.prof;
+    if (threadIdx.x == 0) PSTAMP(prof, 0);
 
     if (warp == 0 && lane == 0) {
         tc::tma_prefetch_desc(&tmZ); tc::tma_prefetch_desc(&tmXr); tc::tma_prefetch_desc(&tmXc); tc::tma_prefetch_desc(&tmR);
@@ -523,8 +535,10 @@ k_glm_mf_step(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ C
         if (lane == 0) pre = preissue_early(&tmZ, &tmXr, sp.f, ctl, tiles, sp.stages_f, 2);
         pre = __shfl_sync(0xffffffffu, pre, 0);
     }
+    if (threadIdx.x == 0) PSTAMP(prof, 1);
     pdl_wait();
     stamp_min(sp.tl, 1);
+    if (threadIdx.x == 0) PSTAMP(prof, 2);
     if (warp == 0 && sp.f.static_op != 2) {   // minibatch copy of X: final once the gather kernel has completed
         if (lane == 0) pre = preissue_early(&tmZ, &tmXr, sp.f, ctl, tiles, sp.stages_f, 2);
         pre = __shfl_sync(0xffffffffu, pre, 0);
@@ -542,19 +556,27 @@ k_glm_mf_step(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ C
         }
         sn.shift = sp.t.out[3];
         if (sp.t.comm.nranks > 1) sn.seq = *reinterpret_cast<volatile unsigned int*>(&sp.t.comm.dev->seq) + 1u;
-        float part = 0.f;
-        for (int i = threadIdx.x; i < sp.D; i += NUM_THREADS) part += __logf(sp.lambda[sp.D + i]);
-        sn.logdet = block_sum(part, &ctl->ys[1][0]);
     }
 
+    if (threadIdx.x == 0) PSTAMP(prof, 3);
     if (sp.do_sample) {
         sample_phase(sp, ctl, sn.step, sn.key);
         stamp_max(sp.tl, 8);
+        if (threadIdx.x == 0) PSTAMP(prof, 4);
         grid_barrier(gb);
         stamp_min(sp.tl, 2);
     }
+    if (threadIdx.x == 0) PSTAMP(prof, 5);
+    // log det of the scale (sum_i log s_i) is only needed by the tail: the otherwise idle warp 2 takes it while the
+    // forward contraction runs (lambda is not overwritten before the tail phase of this launch)
+    if (warp == 2 && sp.t.mode != STEP_TAIL_NONE) {
+        float part = 0.f;
+        for (int i = lane; i < sp.D; i += 32) part += __logf(sp.lambda[sp.D + i]);
+        part = warp_sum(part);
+        if (lane == 0) ctl->scratch[0] = part;
+    }
 
-    tc_phase<EPI_GLM_FWD, LIK>(&tmZ, &tmXr, sp.f, ctl, tiles, tmem_base, sp.stages_f, pre, 2);
+    tc_phase<EPI_GLM_FWD, LIK, COH>(&tmZ, &tmXr, sp.f, ctl, tiles, tmem_base, sp.stages_f, pre, 2, prof, 6);
     stamp_max(sp.tl, 9);
 
     // ---- drain, re-carve the ring for the backward geometry, request its static operand (X columns) while the
@@ -568,17 +590,22 @@ k_glm_mf_step(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ C
         if (lane == 0) pre = preissue_early(&tmXc, &tmR, sp.b, ctl, tiles, sp.stages_b, 1);
         pre = __shfl_sync(0xffffffffu, pre, 0);
     }
+    if (threadIdx.x == 0) PSTAMP(prof, 12);   // arriving at barrier 1 (ring re-carved, X columns requested)
     grid_barrier(gb);
     stamp_min(sp.tl, 3);
     tc::fence_after_sync();
+    if (threadIdx.x == 0) PSTAMP(prof, 13);
 
-    tc_phase<EPI_GLM_BWD, 0>(&tmXc, &tmR, sp.b, ctl, tiles, tmem_base, sp.stages_b, pre, 1);
+    tc_phase<EPI_GLM_BWD, 0, COH>(&tmXc, &tmR, sp.b, ctl, tiles, tmem_base, sp.stages_b, pre, 1, prof, 14);
     stamp_max(sp.tl, 10);
 
     if (sp.t.mode != STEP_TAIL_NONE) {
+        if (threadIdx.x == 0) PSTAMP(prof, 20);   // arriving at barrier 2
         grid_barrier(gb);
         stamp_min(sp.tl, 4);
+        if (threadIdx.x == 0) PSTAMP(prof, 21);
         tail_phase(sp, ctl, sn, gb);
+        if (threadIdx.x == 0) PSTAMP(prof, 22);
     }
 
     // (CTA 0 has passed the last barrier of the launch: every CTA has read the old base)
@@ -590,18 +617,31 @@ k_glm_mf_step(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ C
         tc::tmem_dealloc(tmem_base, 512);
     }
     stamp_max(sp.tl, 11);
+    if (threadIdx.x == 0) PSTAMP(prof, 23);
 }
 
 }  // namespace
 
+static unsigned long long* g_prof = nullptr;
+static int g_prof_grid = 0;
+
 int avi_step_fused_max_per_cta() { return TAIL_MAX_PER_CTA; }
+
+// diagnostic (AVI_STEP_PROF=1): stamps of the most recent fused launch, [grid][32] u64; returns the grid size (0: off)
+extern "C" int32_t avi_step_fused_prof_get(avi_ctx* ctx, uint64_t* out, int32_t max_ctas) {
+    if (!g_prof || !out || max_ctas < g_prof_grid) return 0;
+    cudaStreamSynchronize(ctx->stream);
+    cudaMemcpy(out, g_prof, (size_t)g_prof_grid * 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    return g_prof_grid;
+}
 
 int32_t avi_step_fused_launch(avi_ctx* ctx, const CUtensorMap& tmZ, const CUtensorMap& tmXr, const CUtensorMap& tmXc,
                               const CUtensorMap& tmR, StepParams& sp) {
     static bool attr_done = false;
     if (!attr_done) {
-        AVI_CUDA(ctx, cudaFuncSetAttribute(k_glm_mf_step<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-        AVI_CUDA(ctx, cudaFuncSetAttribute(k_glm_mf_step<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        AVI_CUDA(ctx, cudaFuncSetAttribute(k_glm_mf_step<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        AVI_CUDA(ctx, cudaFuncSetAttribute(k_glm_mf_step<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        AVI_CUDA(ctx, cudaFuncSetAttribute(k_glm_mf_step<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         attr_done = true;
     }
     const int extra = 16 + (int)sizeof(SmemCtl) + 1024;
@@ -633,10 +673,20 @@ int32_t avi_step_fused_launch(avi_ctx* ctx, const CUtensorMap& tmZ, const CUtens
     }
     cfg.attrs = at; cfg.numAttrs = na;
     sp.tl = ctx->tl;
+    // AVI_STEP_PROF=1: per-CTA phase stamps, copied out by avi_step_fused_prof_get
+    static const bool prof_on = getenv("AVI_STEP_PROF") && atoi(getenv("AVI_STEP_PROF")) != 0;
+    if (prof_on) {
+        if (!g_prof) { if (cudaMalloc(&g_prof, 160 * 32 * sizeof(unsigned long long)) != cudaSuccess) g_prof = nullptr; }
+        if (g_prof && !ctx->capturing) cudaMemsetAsync(g_prof, 0, 160 * 32 * sizeof(unsigned long long), ctx->stream);
+        sp.prof = g_prof; g_prof_grid = grid;
+    }
     AviTimed timed(ctx, "glm_step");
-    cudaError_t e = sp.f.likelihood == AVI_GLM_BERNOULLI_LOGIT
-                        ? cudaLaunchKernelEx(&cfg, k_glm_mf_step<0>, tmZ, tmXr, tmXc, tmR, sp)
-                        : cudaLaunchKernelEx(&cfg, k_glm_mf_step<1>, tmZ, tmXr, tmXc, tmR, sp);
+    // AVI_STEP_NC=1: TIMING EXPERIMENT ONLY -- in-kernel-produced epilogue inputs through the read-only path (results may
+    // be stale): measures what the coherent ld.global.cg loads cost
+    static const bool nc_exp = getenv("AVI_STEP_NC") && atoi(getenv("AVI_STEP_NC")) != 0;
+    cudaError_t e = sp.f.likelihood != AVI_GLM_BERNOULLI_LOGIT ? cudaLaunchKernelEx(&cfg, k_glm_mf_step<1, true>, tmZ, tmXr, tmXc, tmR, sp)
+                    : nc_exp ? cudaLaunchKernelEx(&cfg, k_glm_mf_step<0, false>, tmZ, tmXr, tmXc, tmR, sp)
+                             : cudaLaunchKernelEx(&cfg, k_glm_mf_step<0, true>, tmZ, tmXr, tmXc, tmR, sp);
     if (e != cudaSuccess) AVI_FAIL(ctx, AVI_ERR_CUDA, std::string("fused step launch: ") + cudaGetErrorString(e));
     AVI_LAUNCHED(ctx);
     return AVI_OK;

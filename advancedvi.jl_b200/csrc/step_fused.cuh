@@ -53,6 +53,7 @@ struct StepParams {
     StepTail t;
     unsigned long long* gbar;      // [2] grid barrier: monotonic arrival counter | its value at the start of the launch
     unsigned long long* tl;        // AVI_TIMELINE: %globaltimer stamps per phase (diagnostic)
+    unsigned long long* prof;      // AVI_STEP_PROF: per-CTA stamps [grid][32] (diagnostic)
 };
 
 // what the objective layer hands to a target that can run the fused iteration (avi_model::fused_step)
