@@ -377,7 +377,7 @@ EncodeTiledFn get_encode() {
 // rows x cols fp32 matrix with row pitch ld (floats); box = box_rows x 32 floats, 128B swizzle,
 // out-of-bounds elements read as zero.
 int32_t avi_tc_make_tmap(avi_ctx* ctx, CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld,
-                         int box_rows) {
+                         int box_rows, int atom32) {
     EncodeTiledFn enc = get_encode();
     if (!enc) AVI_FAIL(ctx, AVI_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
     if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld % 4) || box_rows < 1 || box_rows > 256 || rows < 1 || cols < 1)
@@ -387,7 +387,8 @@ int32_t avi_tc_make_tmap(avi_ctx* ctx, CUtensorMap* map, const float* base, int6
     cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) AVI_FAIL(ctx, AVI_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
     return AVI_OK;

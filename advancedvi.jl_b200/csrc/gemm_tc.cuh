@@ -18,6 +18,11 @@ struct TcParams {
     int ca, cb;          // cluster shape: ca a-blocks x cb b-chunks share operands by TMA multicast
     int stages;          // filled by avi_tc_launch
     int static_op;       // 1: A is static data (not written by the previous kernel), 2: B is, 0: neither
+    // fused iteration kernel only: A is read MN-major, i.e. from a matrix stored [k][a] (a contiguous): the backward
+    // contraction then takes X from the SAME row-major copy the forward contraction uses (X is read once per iteration).
+    // The A tensor map has box {32 a-elements, 32 k-rows} and the 32-byte-atom swizzle; a 128 x 32 tile is four boxes.  3xTF32: the k range consists
+    // of three segments of a_seg_kb blocks [hi | hi | lo]; the lo part of the source sits a_seg_off elements further.
+    int a_mn, a_seg_kb, a_seg_off;
     const void* pf_ptr;  // static operand of the NEXT kernel, pulled into L2 by the idle warp 3 while this one computes
     unsigned long long pf_bytes;
     unsigned pf_pace_ns;
@@ -50,8 +55,9 @@ struct TcParams {
     unsigned int* post_tickets;   // [n_ablk], zero between launches
 };
 
+// atom32 = 1: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B (MN-major TF32 operand, tc_common.cuh) instead of the 128-byte swizzle
 int32_t avi_tc_make_tmap(avi_ctx* ctx, CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld,
-                         int box_rows);
+                         int box_rows, int atom32 = 0);
 // fills Ma, Nb, n_ablk, n_kblk, nt, n_bchunk, n_ksplit, kb_per_split, ca, cb.  force_cluster: 0 = never cluster
 // allow_pair = 0: single-CTA tiles only (the fused iteration kernel)
 int32_t avi_tc_plan(avi_ctx* ctx, int64_t Ma, int64_t Nb, int64_t K, bool split_k, int force_cluster, TcParams* p,

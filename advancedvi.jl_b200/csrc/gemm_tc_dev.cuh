@@ -27,6 +27,8 @@ struct SmemCtl {
     uint32_t tmem_base;
     int flag;
     float scratch[8];               // fused iteration kernel: values handed from one phase to a later one
+    float red16[2][16];             // fused iteration kernel: per-warp partials of a unit's log-likelihood total
+    float tail[1024 + 256];         // fused iteration kernel, tail phase: slab staging + per-coordinate sums
     alignas(16) float ys[2][512];   // FWD: y per accumulator stage (<= 256 used); BWD: reduction scratch
 };
 
@@ -63,7 +65,7 @@ __device__ __forceinline__ void epilogue_unit(const TcParams& p, SmemCtl* ctl, i
             // otherwise sleep on the accumulator barrier):
             // (1) log pi(z_m) = w * sum(partial log-lik of the forward kernel) + log prior, by the a-block-0 CTAs
             const int ab0 = a / BM;
-            if (ab0 == 0) {
+            if (ab0 == 0 && p.post_on == 1) {   // (post_on == 2, fused iteration: the tail phase takes sum_m log pi itself)
                 float* red = &ctl->ys[0][0];   // 16 warps x 32 lanes
                 const int ew = et >> 5, ln = et & 31;
                 for (int m0 = (ks * p.n_bchunk + bc) * 32; m0 < p.Nb; m0 += p.n_ksplit * p.n_bchunk * 32) {
@@ -279,8 +281,23 @@ __device__ __forceinline__ void epilogue_bwd_store(const TcParams& p, SmemCtl* c
         p.part1[slab + a] = ((red1[row] + red1[BM + row]) + red1[2 * BM + row]) + red1[3 * BM + row];
         p.part2[slab + a] = ((red2[row] + red2[BM + row]) + red2[2 * BM + row]) + red2[3 * BM + row];
     }
-    __threadfence();
+    if (p.post_on != 2) __threadfence();   // (fused iteration: the grid barrier before the tail phase publishes the slabs)
     epi_bar_sync();
+}
+
+// EPI_GLM_FWD in the fused iteration (post_on == 2): RepGradELBO only needs sum_m log pi(z_m), so a unit contributes
+// ONE number -- the log-likelihood summed over its 128 samples x NT rows, fixed order -- instead of per-sample partials.
+__device__ __forceinline__ void epilogue_fwd_unit_total(const TcParams& p, SmemCtl* ctl, int as, int u, int et, float s1) {
+    const int ew = et >> 5, ln = et & 31;
+    s1 = warp_sum(s1);
+    if (ln == 0) ctl->red16[as][ew] = s1;
+    epi_bar_sync();
+    if (et == 0) {
+        float t = 0.0f;
+#pragma unroll
+        for (int w2 = 0; w2 < EPI_WARPS; ++w2) t += ctl->red16[as][w2];
+        p.part1[u] = t;
+    }
 }
 
 }  // namespace

@@ -472,8 +472,10 @@ struct Glm : avi_model {
         sp.f.C = R; sp.f.ldc = (int)ldR; sp.f.y = y; sp.f.w = w; sp.f.likelihood = likelihood;
         sp.f.r_seg = x3 ? (int)segn : 0;
         sp.f.static_op = subsampled ? 0 : 2;
-        AVI_CHECK(ensure_buf(&llpart, &llpart_cap, (long long)sp.f.n_bchunk * 4 * capM));
+        const long long units_f = (long long)sp.f.n_ablk * sp.f.n_bchunk * sp.f.n_ksplit;
+        AVI_CHECK(ensure_buf(&llpart, &llpart_cap, std::max<long long>(units_f, (long long)sp.f.n_bchunk * 4 * capM)));
         sp.f.part1 = llpart; sp.f.ldpart = capM;
+        sp.f.post_on = 2;   // one log-likelihood total per unit (the tail phase only needs sum_m log pi)
         // backward: G[i][m] = sum_j Xc[i][j] R[m][j], reduced against eps in the epilogue
         AVI_CHECK(avi_tc_plan(ctx, d, M, kb(), true, 0, &sp.b, 0));
         sp.b.static_op = subsampled ? 0 : 1;
@@ -481,13 +483,21 @@ struct Glm : avi_model {
         const int ldslab = (int)round_up(d, 32);
         AVI_CHECK(ensure_buf(&a1p, &ap_cap, 2LL * nslab * ldslab));
         sp.b.E = fa.E; sp.b.lde = ld; sp.b.part1 = a1p; sp.b.part2 = a1p + (size_t)nslab * ldslab; sp.b.ldpart = ldslab;
-        sp.b.post_on = 1; sp.b.post_Z = fa.Z; sp.b.post_pre = reinterpret_cast<const float*>(pre);
-        sp.b.post_llpart = llpart; sp.b.post_nparts = sp.f.n_bchunk * 4; sp.b.post_ldll = capM; sp.b.post_w = w;
-        sp.b.post_logp = fa.logp; sp.b.post_a1 = fa.t.acc; sp.b.post_a2 = fa.t.acc + fa.t.accv; sp.b.post_tickets = tickets;
+        // post_on = 2: prior gradient and the eta coordinate in the epilogue, slab rows left for the tail phase
+        sp.b.post_on = 2; sp.b.post_Z = fa.Z; sp.b.post_pre = reinterpret_cast<const float*>(pre);
+        sp.b.post_a1 = fa.t.acc; sp.b.post_a2 = fa.t.acc + fa.t.accv;
         CUtensorMap tmZ, tmXr, tmXc, tmR;
         AVI_CHECK(avi_tc_make_tmap(ctx, &tmZ, Zt, M, kf(), zt_ld, 128));
         AVI_CHECK(avi_tc_make_tmap(ctx, &tmXr, Xr, n_act, kf(), dK, sp.f.nt));
-        AVI_CHECK(avi_tc_make_tmap(ctx, &tmXc, Xc, d, kb(), nP, 128));
+        // backward A operand: X columns from the transposed copy Xc (K-major) or, default, MN-major straight from the
+        // row-major copy the forward phase has just pulled through L2 (AVI_TC_AMN=0 selects the former)
+        static const bool a_mn = !(getenv("AVI_TC_AMN") && atoi(getenv("AVI_TC_AMN")) == 0);
+        if (a_mn) {
+            sp.b.a_mn = 1; sp.b.a_seg_kb = x3 ? (int)(segn / 32) : 0; sp.b.a_seg_off = x3 ? segd : 0;
+            AVI_CHECK(avi_tc_make_tmap(ctx, &tmXc, Xr, n_act, x3 ? 3LL * segd : d, dK, 32, /*atom32=*/1));
+        } else {
+            AVI_CHECK(avi_tc_make_tmap(ctx, &tmXc, Xc, d, kb(), nP, 128));
+        }
         AVI_CHECK(avi_tc_make_tmap(ctx, &tmR, R, M, kb(), ldR, sp.b.nt));
         sp.do_sample = 1;
         sp.lambda = fa.lambda; sp.D = fa.D; sp.ld = ld; sp.m0 = fa.m0; sp.Mloc = M; sp.st = fa.st;
@@ -495,6 +505,8 @@ struct Glm : avi_model {
         sp.d = d; sp.variant = variant; sp.include_prior = include_prior;
         sp.Zt = Zt; sp.zt_ld = zt_ld; sp.zt_seg = x3 ? segd : 0; sp.pre = reinterpret_cast<float*>(pre);
         sp.t = fa.t;
+        sp.t.unit_ll = llpart; sp.t.n_units_f = (int)units_f; sp.t.w_lik = w;
+        sp.t.part1 = sp.b.part1; sp.t.part2 = sp.b.part2; sp.t.nslab = nslab; sp.t.ldslab = ldslab;
         sp.t.done_ticket = reinterpret_cast<unsigned int*>(gbar + 2);
         sp.gbar = gbar;
         return avi_step_fused_launch(ctx, tmZ, tmXr, tmXc, tmR, sp);

@@ -27,7 +27,8 @@
 namespace {
 
 constexpr int NW = NUM_THREADS / 32;            // 20 warps
-constexpr int TAIL_MAX_PER_CTA = 120;           // coordinates per CTA in the tail (scratch: 4 floats each in ys[0])
+constexpr int TAIL_MAX_PER_CTA = 120;           // coordinates per CTA in the tail (SmemCtl::tail: 2 floats each behind the staging area)
+constexpr int TAIL_STAGE = 1024;                // floats of the tail's slab staging area
 
 __device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
     unsigned long long v;
@@ -40,7 +41,7 @@ __device__ __forceinline__ void mbar_inval(uint64_t* bar) {
 }
 
 // All threads of all CTAs.  Arrival: every thread publishes its generic global writes to the async proxy, the CTA
-// barrier orders them before thread 0, whose gpu-scope fence + atomic makes them visible (cumulativity) to whoever
+// barrier orders them before thread 0, whose gpu-scope release-add makes them visible (cumulativity) to whoever
 // acquires the counter.  gbar[0] is a counter that only grows; gbar[1] holds its value at the start of the launch
 // (written by CTA 0 at the very end of the previous launch, read by every CTA at entry): the k-th barrier of a launch
 // of n CTAs completes at base + k * n, whatever the grid sizes of earlier launches were.
@@ -54,11 +55,11 @@ __device__ __forceinline__ void grid_barrier(GridBar& gb) {
     __syncthreads();
     gb.k += 1;
     if (threadIdx.x == 0) {
-        __threadfence();
+        // release-add (no return value, no separate membar) / acquire-poll: the CTA barrier above makes the release
+        // cumulative over the other threads' writes, the one below extends the acquire to them
         const unsigned long long target = gb.base + (unsigned long long)gb.k * gridDim.x;
-        atomicAdd(gb.ctr, 1ull);
+        asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(gb.ctr), "l"(1ull) : "memory");
         while (ld_acquire_gpu_u64(gb.ctr) < target) { }
-        __threadfence();
         fence_proxy_async_global();
     }
     __syncthreads();
@@ -87,6 +88,16 @@ __device__ __forceinline__ void init_pipeline(SmemCtl* ctl, int stages, int stag
 #define FUNIT_COORDS(u) \
     const int ab = (u) % p.n_ablk, bc = ((u) / p.n_ablk) % p.n_bchunk, ks = (u) / (p.n_ablk * p.n_bchunk)
 
+// A tile (128 a-rows x 32 k) of k-block kb into `sa`.  K-major: one box.  MN-major (TcParams.a_mn): four boxes of
+// {32 a-elements, 32 k-rows}, 4 KB apart (the LBO of smem_desc_mn_sw128).
+__device__ __forceinline__ void load_a_tile(uint8_t* sa, const CUtensorMap* tmA, uint64_t* bar, const TcParams& p, int kb, int ab) {
+    if (!p.a_mn) { tc::tma_load_2d(sa, tmA, bar, kb * BK, ab * BM); return; }
+    const int seg = p.a_seg_kb ? kb / p.a_seg_kb : 0, rb = p.a_seg_kb ? kb - seg * p.a_seg_kb : kb;
+    const int a0 = ab * BM + (seg == 2 ? p.a_seg_off : 0);
+#pragma unroll
+    for (int fb = 0; fb < BM / 32; ++fb) tc::tma_load_2d(sa + fb * 4096, tmA, bar, a0 + fb * 32, rb * BK);
+}
+
 // The operand that does not depend on the previous phase (X; early_op 1 = A, 2 = B) of this CTA's first unit is
 // requested before the phase's dependency is satisfied: expect_tx without arrive; the producer adds the dependent
 // operand (and the arrive) later.  One thread.  Returns the number of ring slots armed.
@@ -103,7 +114,7 @@ __device__ __forceinline__ int preissue_early(const CUtensorMap* tmA, const CUte
         uint8_t* sa = tiles + n * stage_bytes;
         if (early_op == 1) {
             tc::mbar_expect_tx(&ctl->full[n], (uint32_t)A_TILE_BYTES);
-            tc::tma_load_2d(sa, tmA, &ctl->full[n], kb * BK, ab * BM);
+            load_a_tile(sa, tmA, &ctl->full[n], p, kb, ab);
         } else {
             tc::mbar_expect_tx(&ctl->full[n], (uint32_t)(NT * BK * 4));
             tc::tma_load_2d(sa + A_TILE_BYTES, tmB, &ctl->full[n], kb * BK, bc * NT);
@@ -141,11 +152,11 @@ __device__ __forceinline__ void tc_phase(const CUtensorMap* tmA, const CUtensorM
                             tc::tma_load_2d(sa + A_TILE_BYTES, tmB, &ctl->full[stage], kb * BK, bc * NT);
                         } else {
                             tc::mbar_arrive_expect_tx(&ctl->full[stage], (uint32_t)A_TILE_BYTES);
-                            tc::tma_load_2d(sa, tmA, &ctl->full[stage], kb * BK, ab * BM);
+                            load_a_tile(sa, tmA, &ctl->full[stage], p, kb, ab);
                         }
                     } else {
                         tc::mbar_arrive_expect_tx(&ctl->full[stage], (uint32_t)stage_bytes);
-                        tc::tma_load_2d(sa, tmA, &ctl->full[stage], kb * BK, ab * BM);
+                        load_a_tile(sa, tmA, &ctl->full[stage], p, kb, ab);
                         tc::tma_load_2d(sa + A_TILE_BYTES, tmB, &ctl->full[stage], kb * BK, bc * NT);
                     }
                     if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -156,7 +167,8 @@ __device__ __forceinline__ void tc_phase(const CUtensorMap* tmA, const CUtensorM
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (tc::elect_one()) {
-            const uint32_t idesc = tc::idesc_tf32(BM, NT);
+            const uint32_t idesc = tc::idesc_tf32(BM, NT, p.a_mn);
+            const uint64_t a_step = p.a_mn ? 64u : 2u;   // per K = 8 MMA, in 16-byte units: 8 k-rows of 128 B | 32 B along the row
             int stage = 0; uint32_t phase = 0;
             int as = 0; uint32_t aphase = 0;
             for (int u = first; u < units; u += stride) {
@@ -170,11 +182,11 @@ __device__ __forceinline__ void tc_phase(const CUtensorMap* tmA, const CUtensorM
                     tc::fence_after_sync();
                     if (kb == kb0 && u == first) PSTAMP(prof, ps + 1);   // first operands landed
                     const uint32_t sa = tc::smem_u32(tiles + stage * stage_bytes);
-                    const uint64_t da = tc::smem_desc_k_sw128(sa);
+                    const uint64_t da = p.a_mn ? tc::smem_desc_mn_sw128(sa, 4096u) : tc::smem_desc_k_sw128(sa);
                     const uint64_t db = tc::smem_desc_k_sw128(sa + A_TILE_BYTES);
 #pragma unroll
                     for (int k = 0; k < BK / 8; ++k)
-                        tc::umma_tf32(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                        tc::umma_tf32(tacc, da + a_step * (uint64_t)k, db + (uint64_t)(2 * k), idesc,
                                       (kb > kb0 || k > 0) ? 1u : 0u);
                     tc::umma_commit(&ctl->empty[stage]);
                     if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -202,10 +214,13 @@ __device__ __forceinline__ void tc_phase(const CUtensorMap* tmA, const CUtensorM
             tc::fence_before_sync();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&ctl->tmem_empty[as]);
-            epilogue_store_partials<EPI>(p, a_ok, a, bc, ks, cq, s1, s2);
+            if (EPI == EPI_GLM_FWD) {
+                if (p.post_on == 2) epilogue_fwd_unit_total(p, ctl, as, u, et, a_ok ? s1 : 0.0f);
+                else epilogue_store_partials<EPI>(p, a_ok, a, bc, ks, cq, s1, s2);
+            }
             if (EPI == EPI_GLM_BWD) epilogue_bwd_store(p, ctl, a_ok, a, bc, ks, cq, et, s1, s2);
             if (EPI == EPI_GLM_BWD && et == 0) PSTAMP(prof, ps + 4);   // slab rows stored
-            if (EPI == EPI_GLM_BWD && p.post_on) epilogue_bwd_combine(p, ctl, ab, et);
+            if (EPI == EPI_GLM_BWD && p.post_on == 1) epilogue_bwd_combine(p, ctl, ab, et);
             if (et == 0) PSTAMP(prof, ps + 5);   // unit complete
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
@@ -318,7 +333,8 @@ __device__ __forceinline__ void tail_phase(const StepParams& sp, SmemCtl* ctl, c
     const UpdArgs a = t.a;
     const int D = sp.D, accv = t.accv, M = t.M, objective = t.objective, entropy = t.entropy;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float* vals = &ctl->ys[0][0];      // [per][4]
+    float* stage = &ctl->tail[0];      // [2][nc * nslab] slab partials of the slice (TAIL_STAGE floats)
+    float* vals = &ctl->tail[TAIL_STAGE];          // [per][2]: sticking-the-landing sums of the slice
     float* sm = &ctl->ys[1][0];        // block_sum scratch (33) | [64..] broadcast slots
     const bool stl = entropy == AVI_ENT_STL || entropy == AVI_ENT_STL_ZEROGRAD;
     const bool adam = a.rule == AVI_RULE_ADAM, dog = a.rule == AVI_RULE_DOG || a.rule == AVI_RULE_DOWG;
@@ -327,54 +343,94 @@ __device__ __forceinline__ void tail_phase(const StepParams& sp, SmemCtl* ctl, c
     const int c0 = min(D, (int)blockIdx.x * per), c1 = min(D, c0 + per), nc = c1 - c0;
     const int NR = t.comm.nranks;
 
-    // ---- local scalars: sum_m log pi(z_m), sum_m |eps_m|^2 over this rank's samples / rows
-    float sl = 0.f, sq = 0.f;
-    for (int m = tid; m < sp.Mloc; m += NUM_THREADS) { sl += __ldcg(t.logp + m); sq += __ldcg(sp.esq + m); }
-    sl = block_sum(sl, sm); sq = block_sum(sq, sm);
-
-    // ---- per-coordinate sums of the slice (v2, v3 only where the gradient needs them: sticking the landing)
-    for (int j = warp; j < nc; j += NW) {
-        const int i = c0 + j;
-        float v2 = 0.f, v3 = 0.f;
-        if (stl) {
-            for (int m = lane; m < sp.Mloc; m += 32) {
-                const float e = __ldcg(sp.E + (size_t)m * sp.ld + i);
-                v2 += e; v3 = fmaf(e, e, v3);
-            }
-            v2 = warp_sum(v2); v3 = warp_sum(v3);
-        }
-        if (lane == 0) {
-            vals[4 * j] = __ldcg(t.acc + i); vals[4 * j + 1] = __ldcg(t.acc + accv + i);
-            vals[4 * j + 2] = v2; vals[4 * j + 3] = v3;
+    // ---- every load this CTA needs is requested up front (one L2 round trip), the reductions follow
+    //  scalars: sum_m log pi(z_m) = w * (sum of the forward units' log-likelihood totals) + sum_m log prior(z_m);
+    //           sum_m |eps_m|^2
+    float sl = 0.f, spr = 0.f, sq = 0.f;
+    for (int u = tid; u < t.n_units_f; u += NUM_THREADS) sl += __ldcg(t.unit_ll + u);
+    for (int m = tid; m < sp.Mloc; m += NUM_THREADS) { spr += __ldcg(sp.pre + 4 * (size_t)m); sq += __ldcg(sp.esq + m); }
+    //  this thread's coordinate (j = tid < nc): the split-K slab partials of sum_m g and sum_m g*eps (the eta coordinate
+    //  i == d comes complete from the backward epilogue), lambda and the optimiser state
+    const bool mine = tid < nc;
+    const int i = c0 + (mine ? tid : 0);
+    float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+    float x0 = 0.f, x1 = 1.f, s1m0 = 0.f, s1m1 = 0.f, s2m0 = 0.f, s2m1 = 0.f, av0 = 0.f, av1 = 0.f;
+    // (all threads fetch the nc x nslab partials of the slice at once -- one round trip -- and stage them in shared
+    // memory; the coordinate's owner adds them up in slab order.  Slices too large for the staging area: owner loop.)
+    const int tot = nc * t.nslab;
+    const bool staged = 2 * tot <= TAIL_STAGE;
+    if (staged) {
+        for (int idx = tid; idx < tot; idx += NUM_THREADS) {
+            const int j = idx / t.nslab, q = idx - j * t.nslab, ii = c0 + j;
+            const bool beta = ii < sp.d;
+            stage[idx] = beta ? __ldcg(t.part1 + (size_t)q * t.ldslab + ii) : 0.f;
+            stage[tot + idx] = beta ? __ldcg(t.part2 + (size_t)q * t.ldslab + ii) : 0.f;
         }
     }
+    if (mine) {
+        if (i >= sp.d) {
+            v0 = __ldcg(t.acc + i); v1 = __ldcg(t.acc + accv + i);
+        } else if (!staged) {
+#pragma unroll 8
+            for (int q = 0; q < t.nslab; ++q) {
+                v0 += __ldcg(t.part1 + (size_t)q * t.ldslab + i);
+                v1 += __ldcg(t.part2 + (size_t)q * t.ldslab + i);
+            }
+        }
+        x0 = t.lam[i]; x1 = t.lam[D + i];
+        if (t.mode == STEP_TAIL_UPDATE) {
+            if (adam || dog) { s1m0 = t.m1[i]; s1m1 = t.m1[D + i]; }
+            if (adam) { s2m0 = t.m2[i]; s2m1 = t.m2[D + i]; }
+            if (polyavg) { av0 = t.avg[i]; av1 = t.avg[D + i]; }
+        }
+    }
+    //  sticking the landing: sum_m eps and sum_m eps^2 of the slice (warp per coordinate, lanes over the samples)
+    if (stl) {
+        for (int j = warp; j < nc; j += NW) {
+            float a2 = 0.f, a3 = 0.f;
+            for (int m = lane; m < sp.Mloc; m += 32) {
+                const float e = __ldcg(sp.E + (size_t)m * sp.ld + c0 + j);
+                a2 += e; a3 = fmaf(e, e, a3);
+            }
+            a2 = warp_sum(a2); a3 = warp_sum(a3);
+            if (lane == 0) { vals[2 * j] = a2; vals[2 * j + 1] = a3; }
+        }
+    }
+    // one fixed-order reduction for the three scalars (20 warp partials each through shared memory)
+    sl = warp_sum(sl); spr = warp_sum(spr); sq = warp_sum(sq);
+    if (lane == 0) { sm[3 * warp] = sl; sm[3 * warp + 1] = spr; sm[3 * warp + 2] = sq; }
     __syncthreads();
+    sl = 0.f; spr = 0.f; sq = 0.f;
+#pragma unroll
+    for (int w2 = 0; w2 < NW; ++w2) { sl += sm[3 * w2]; spr += sm[3 * w2 + 1]; sq += sm[3 * w2 + 2]; }
+    sl = fmaf(t.w_lik, sl, spr);
+    if (stl && mine) { v2 = vals[2 * tid]; v3 = vals[2 * tid + 1]; }
+    if (staged && mine && i < sp.d) {
+        for (int q = 0; q < t.nslab; ++q) { v0 += stage[tid * t.nslab + q]; v1 += stage[tot + tid * t.nslab + q]; }
+    }
 
     // ---- exchange over NVLink (low-latency push protocol of comm_dev.cuh): entry (class c, coordinate i) travels as
     //      element c * accv + i, the scalars as elements 4 * accv + {0, 1}; sums are taken in rank order
     if (NR > 1) {
         const unsigned int seq = sn.seq;
-        const int nent = 4 * nc;
         const long long sbase = 4ll * accv;
-        for (int k = tid; k < nent; k += NUM_THREADS) {
-            const int c = k & 3, j = k >> 2;
-            const bool x = (c < 2) ? (t.xmask & STEP_X_V01) != 0 : ((t.xmask & STEP_X_V23) != 0 && stl);
-            if (x) ll_push(t.comm, seq, (long long)c * accv + c0 + j, vals[k]);
+        const bool x01 = (t.xmask & STEP_X_V01) != 0, x23 = (t.xmask & STEP_X_V23) != 0 && stl;
+        if (mine) {
+            if (x01) { ll_push(t.comm, seq, (long long)i, v0); ll_push(t.comm, seq, (long long)accv + i, v1); }
+            if (x23) { ll_push(t.comm, seq, 2ll * accv + i, v2); ll_push(t.comm, seq, 3ll * accv + i, v3); }
         }
         if (blockIdx.x == 0 && tid == NUM_THREADS - 1) {
             if (t.xmask & STEP_X_S0) ll_push(t.comm, seq, sbase, sl);
             if (t.xmask & STEP_X_S1) ll_push(t.comm, seq, sbase + 1, sq);
         }
-        for (int k = tid; k < nent; k += NUM_THREADS) {
-            const int c = k & 3, j = k >> 2;
-            const bool x = (c < 2) ? (t.xmask & STEP_X_V01) != 0 : ((t.xmask & STEP_X_V23) != 0 && stl);
-            if (x) {
-                const long long idx[1] = {(long long)c * accv + c0 + j}; const bool need[1] = {true};
-                const float own[1] = {vals[k]};
-                float out[1];
-                ll_gather<1>(t.comm, seq, idx, need, own, out);
-                vals[k] = out[0];
-            }
+        if (mine) {
+            const long long idx[4] = {(long long)i, (long long)accv + i, 2ll * accv + i, 3ll * accv + i};
+            const bool need[4] = {x01, x01, x23, x23};
+            const float own[4] = {v0, v1, v2, v3};
+            float out[4];
+            ll_gather<4>(t.comm, seq, idx, need, own, out);
+            if (x01) { v0 = out[0]; v1 = out[1]; }
+            if (x23) { v2 = out[2]; v3 = out[3]; }
         }
         if (tid == NUM_THREADS - 1) {
             const long long idx[2] = {sbase, sbase + 1};
@@ -395,12 +451,9 @@ __device__ __forceinline__ void tail_phase(const StepParams& sp, SmemCtl* ctl, c
     const bool bad = !isfinite(value);
 
     // ---- gradient entries of the slice: thread j < nc owns coordinate c0 + j (mu_i and s_i)
-    const bool mine = tid < nc;
-    const int i = c0 + (mine ? tid : 0);
-    float x0 = 0.f, x1 = 1.f, g0 = 0.f, g1 = 0.f;
+    float g0 = 0.f, g1 = 0.f;
     if (mine) {
-        x0 = t.lam[i]; x1 = t.lam[D + i];
-        mf_grad_vals(vals[4 * tid], vals[4 * tid + 1], vals[4 * tid + 2], vals[4 * tid + 3], x1, M, objective, entropy, S, g0, g1);
+        mf_grad_vals(v0, v1, v2, v3, x1, M, objective, entropy, S, g0, g1);
         t.grad[i] = g0; t.grad[D + i] = g1;
     }
 
@@ -432,12 +485,6 @@ __device__ __forceinline__ void tail_phase(const StepParams& sp, SmemCtl* ctl, c
     }
 
     // ---- optimiser step (common.jl:91-94)
-    float s1m0 = 0.f, s1m1 = 0.f, s2m0 = 0.f, s2m1 = 0.f, av0 = 0.f, av1 = 0.f;
-    if (mine) {
-        if (adam || dog) { s1m0 = t.m1[i]; s1m1 = t.m1[D + i]; }
-        if (adam) { s2m0 = t.m2[i]; s2m1 = t.m2[D + i]; }
-        if (polyavg) { av0 = t.avg[i]; av1 = t.avg[D + i]; }
-    }
     float eta = a.rule == AVI_RULE_DESCENT ? a.h0 : 0.f, v_new = 0.f, r_new = 0.f;
     if (dog) {
         // two global norms (rules.jl:21-34, :52-64): per-CTA partials, one more grid barrier, fixed-order sum

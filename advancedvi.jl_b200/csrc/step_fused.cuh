@@ -29,7 +29,9 @@ struct StepTail {
     int mode;                      // STEP_TAIL_*
     float* acc; int accv;          // [v0 | v1 | v2 | v3] as in avi_internal.cuh (v0, v1 written by the backward phase)
     int M, objective, entropy;
-    float* logp;                   // [Mloc] log pi(z_m) (this rank's rows)
+    float* logp;                   // [Mloc] log pi(z_m) (unused by the kernel: the tail takes sum_m log pi from unit_ll and pre)
+    const float* unit_ll; int n_units_f; float w_lik;   // per forward unit: log-likelihood total; likelihood adjustment
+    const float *part1, *part2; int nslab, ldslab;      // split-K slabs of sum_m g, sum_m g*eps (backward phase)
     float *lam, *grad, *m1, *m2, *avg, *sc, *out;
     float* trace; int trace_cap;
     UpdArgs a;

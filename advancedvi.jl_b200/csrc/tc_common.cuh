@@ -210,10 +210,21 @@ __device__ __forceinline__ uint64_t smem_desc_k_sw128(uint32_t smem_addr) {
     return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
            (2ull << 61);
 }
+// Shared-memory operand descriptor, MN-major TF32.  The only layout the tensor core accepts for a 32-bit MN-major
+// operand is SWIZZLE_128B_BASE32B (layout type 1): rows of 128 B holding 32 consecutive MN elements, 32-byte chunks
+// swizzled with the row index modulo 4 (Swizzle<2,5,2>) -- what a TMA box of {32 floats, R rows} with
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B writes.  Canonical form in 16-byte units ((8, m), (4, k)) : ((1, LBO), (8, SBO)):
+// groups of 4 K-rows are SBO = 512 B apart (consecutive rows of the box), blocks of 32 MN elements are lbo_bytes apart
+// (one TMA box each).  One kind::tf32 MMA (K = 8) consumes 8 rows: advance the start address by 1024 B per MMA.
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (1ull << 61);
+}
 // Instruction descriptor kind::tf32: D = F32 (bits 4-5 = 1), A = B = TF32 (bits 7-9, 10-12 = 2),
-// both K-major (bits 15, 16 = 0), N >> 3 at bits 17-22, M >> 4 at bits 24-28.
-__host__ __device__ __forceinline__ uint32_t idesc_tf32(int M, int N) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// A / B major at bits 15 / 16 (0 = K-major, 1 = MN-major), N >> 3 at bits 17-22, M >> 4 at bits 24-28.
+__host__ __device__ __forceinline__ uint32_t idesc_tf32(int M, int N, int a_mn = 0) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a_mn ? 1 : 0) << 15) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
 }
 
 // SFU approximations without the denormal fix-up code the libdevice wrappers add

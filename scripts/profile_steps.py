@@ -3,12 +3,13 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import advancedvi_jl_b200 as avi
-from oracle import models as Mo
 
 n, d, M = 10000, 1024, 256
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 5
 family = sys.argv[2] if len(sys.argv) > 2 else "meanfield"
-X, y = Mo.synth_glm_data(n, d, 1)
+rng = np.random.default_rng(1)
+X = rng.standard_normal((n, d), dtype=np.float32) / np.float32(np.sqrt(d)); X[:, d - 1] = 1.0
+y = (rng.random(n) < 0.5).astype(np.float32)
 ctx = avi.Context(0)
 prob = avi.LogReg(ctx, X, y, gemm="tf32")
 D = d + 1

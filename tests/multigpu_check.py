@@ -16,6 +16,8 @@ def main():
     import advancedvi_jl_b200 as avi
     from advancedvi_jl_b200 import parallel, _lib as L
     from oracle import models as Mo
+    from advancedvi_jl_b200.api import _OptState
+    import ctypes as C
 
     rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(lr)
@@ -93,6 +95,17 @@ def main():
             assert np.linalg.norm(g - g0) <= tol * np.linalg.norm(g0), (kind, "rows", native)
             gather_equal(g, f"row-sharded grad {kind}")
             o.close()
+        # n-axis inside the fused optimiser loop (the bench default): 25 steps, rows sharded, exchange in the tail phase
+        objr = avi.Objective(key, alg.objective, q, probr)
+        objr.set_shard_axis(L.SHARD_ROWS)
+        str_ = _OptState(alg, objr, q)
+        L.check(L.lib.avi_opt_steps(str_.h, 25, L.fptr(vals), L.fptr(elbos), C.byref(nd)), ctx.h)
+        assert nd.value == 25
+        lam2, avg2, _ = str_.params()
+        assert np.linalg.norm(lam2 - lam0) <= 1e-4 * np.linalg.norm(lam0), ("rows", np.linalg.norm(lam2 - lam0))
+        assert abs(elbos[24] - info0[24]["elbo"]) <= 1e-4 * abs(info0[24]["elbo"])
+        gather_equal(lam2, "lambda after 25 row-sharded steps")
+        str_.close(); objr.close()
         probr.close()
         ctx.close()
         if rank == 0:
