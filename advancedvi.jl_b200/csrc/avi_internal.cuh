@@ -312,7 +312,7 @@ int32_t avi_objective_local(avi_obj* o, const float* lambda);          // sample
 // mode and the optimiser / host-output pointers, the rest is filled here.  *taken = false: nothing was enqueued, use
 // the multi-kernel path.
 struct StepTail;
-int32_t avi_objective_fused(avi_obj* o, const float* lambda, const StepTail& tail, bool* taken);
+int32_t avi_objective_fused(avi_obj* o, const float* lambda, const StepTail& tail, bool* taken, bool dry_run = false);
 // acc -> grad (skip_fr_matrix: leave the D x D block of a full-rank gradient to the caller's fused update)
 int32_t avi_objective_finalize(avi_obj* o, const float* lambda, float* grad, float* out, bool skip_fr_matrix = false,
                                bool fuse_advance = false);

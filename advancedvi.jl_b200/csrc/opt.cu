@@ -370,7 +370,13 @@ int32_t steps_prepare(avi_opt* op, int32_t n, const int32_t* idx_host, int64_t b
             // Allocation inside a capture is illegal: run the objective once eagerly so that every
             // lazily sized buffer exists.  It only writes scratch (no optimiser state, no step counter).
             if (subsampled) AVI_CHECK(o->model->subsample_dev(op->idx_dev, batch, o->d_state));
-            AVI_CHECK(avi_objective_local(o, op->lam));
+            {
+                bool fused = false;   // the single-kernel path sizes its own buffers without launching anything
+                StepTail ft{};
+                ft.mode = STEP_TAIL_UPDATE;
+                AVI_CHECK(avi_objective_fused(o, op->lam, ft, &fused, /*dry_run=*/true));
+                if (!fused) AVI_CHECK(avi_objective_local(o, op->lam));
+            }
             auto capture = [&](int iters, cudaGraph_t* graph, cudaGraphExec_t* exec) -> int32_t {
                 const int64_t launches0 = ctx->launches;
                 AVI_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));

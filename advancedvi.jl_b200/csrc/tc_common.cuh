@@ -40,7 +40,29 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity);
+#ifdef AVI_WATCHDOG
+// Debug build (make EXTRA=-DAVI_WATCHDOG): a wait that does not complete within ~2^24 polls records which barrier it
+// was ([1] shared-memory address, [2] parity, [3] block, [4] thread) and returns, so that a protocol bug shows up as a
+// report (avi_step_fused_hang_get) instead of a hung GPU.  Every later wait then returns at once.
+static __device__ unsigned int avi_hang_report[8];
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {   // (try_wait itself blocks for a hardware-defined time: bound the loop by wall clock, 0.2 s)
+        if (mbar_try_wait(bar, parity)) return;
+        if (*(volatile unsigned int*)&avi_hang_report[0]) return;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 200000000ull) break;
+    }
+    if (atomicCAS(&avi_hang_report[0], 0u, 1u) == 0u) {
+        avi_hang_report[1] = smem_u32(bar); avi_hang_report[2] = parity; avi_hang_report[3] = blockIdx.x; avi_hang_report[4] = threadIdx.x;
+    }
+}
+__device__ __forceinline__ void mbar_wait_release_unused(uint64_t* bar, uint32_t parity) {
+#else
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#endif
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "WAIT_LOOP:\n\t"
