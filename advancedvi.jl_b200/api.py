@@ -51,6 +51,25 @@ def _f32(a, name="array"):
     return np.ascontiguousarray(a)
 
 
+class _PtrCache:
+    """float* of caller-owned arrays that come back call after call (the parameter vector and the gradient buffer of an
+    optimisation loop): building a ctypes pointer costs ~5 us, as much as the device-side staging of the call.  The
+    cache holds a reference to the array, so an id() cannot be recycled while its entry is alive."""
+
+    def __init__(self, limit=8):
+        self.d, self.limit = {}, limit
+
+    def __call__(self, a):
+        k = id(a)
+        c = self.d.get(k)
+        if c is None or c[0] is not a or c[2] != a.__array_interface__["data"][0]:
+            if len(self.d) >= self.limit:
+                self.d.clear()
+            c = (a, a.ctypes.data_as(L.c_float_p), a.__array_interface__["data"][0])
+            self.d[k] = c
+        return c[1]
+
+
 def _key_from(rng):
     """The host rng is used only to draw the 64-bit Philox key (include/avi.h: avi_obj_seed)."""
     if isinstance(rng, (int, np.integer)):
@@ -572,6 +591,8 @@ class Objective:
                                          C.byref(h)), self.ctx.h)
         self.h = h
         self.P = int(L.lib.avi_obj_num_params(h))
+        self._ptr = _PtrCache()
+        self._v, self._e = C.c_float(), C.c_float()
         self.key = _key_from(rng)
         L.check(L.lib.avi_obj_seed(h, self.key, 0), self.ctx.h)
 
@@ -598,16 +619,18 @@ class Objective:
         """-> (value, gradient, elbo): value = -ELBO (RepGrad) or the VarGrad value (ScoreGrad).
         `out`: caller-owned float32 gradient buffer of P entries, written in place like the DiffResults buffer of
         estimate_gradient! (abstractobjective.jl:67-86)."""
-        params = _f32(params, "params")
+        if not (type(params) is np.ndarray and params.dtype == np.float32 and params.flags.c_contiguous):
+            params = _f32(params, "params")
         if out is None:
             grad = np.empty(self.P, np.float32)
         else:
             grad = out
             if grad.dtype != np.float32 or grad.size != self.P or not grad.flags.c_contiguous:
                 raise ValueError("out must be a contiguous float32 array of num_params entries")
-        v, e = C.c_float(), C.c_float()
-        L.check(L.lib.avi_obj_estimate_gradient(self.h, L.fptr(params), len(params), L.fptr(grad), C.byref(v),
-                                                C.byref(e)), self.ctx.h)
+        v, e = self._v, self._e
+        rc = L.lib.avi_obj_estimate_gradient(self.h, self._ptr(params), params.size, self._ptr(grad), C.byref(v), C.byref(e))
+        if rc:
+            L.check(rc, self.ctx.h)
         return v.value, grad, e.value
 
     def estimate_objective(self, rng, q: MvLocationScale, n_samples: int, kind=None, entropy=None):
@@ -674,13 +697,17 @@ class HostUpdate:
         self.lam_avg = self.lam.copy()
         self.state = np.zeros(16, np.float32)
         self.scale_offset = int(scale_offset)
+        self._ptr = _PtrCache()
+        # the state arrays live as long as this object: their pointers are built once
+        self._fixed = (self.rule.code, L.fptr(self.hyper), len(self.hyper), self.op.code,
+                       C.c_float(getattr(self.op, "param", 0.0)), self.avg.code, C.c_float(getattr(self.avg, "param", 0.0)),
+                       self.lam.size, self.scale_offset, L.fptr(self.lam))
+        self._tail = (L.fptr(self.m1), L.fptr(self.m2), L.fptr(self.lam_avg), L.fptr(self.state))
 
     def update(self, grad):
-        g = np.ascontiguousarray(grad, np.float32)
-        rc = L.lib.avi_host_update(self.rule.code, L.fptr(self.hyper), len(self.hyper), self.op.code,
-                                   getattr(self.op, "param", 0.0), self.avg.code, getattr(self.avg, "param", 0.0),
-                                   self.lam.size, self.scale_offset, L.fptr(self.lam), L.fptr(g), L.fptr(self.m1),
-                                   L.fptr(self.m2), L.fptr(self.lam_avg), L.fptr(self.state))
+        g = grad if (type(grad) is np.ndarray and grad.dtype == np.float32 and grad.flags.c_contiguous) else \
+            np.ascontiguousarray(grad, np.float32)
+        rc = L.lib.avi_host_update(*self._fixed, self._ptr(g), *self._tail)
         if rc != 0:
             raise AviError(rc, "avi_host_update: unsupported rule / operator or missing state arrays")
         return self.lam

@@ -131,6 +131,12 @@ struct ObjDeviceState {
     long long batch_cursor;    // index of the minibatch used by the next subsampled step
     int halted;                // set when the value slot was not finite: later steps are no-ops
     int trace_pos;             // next slot of the per-call (value, elbo) trace
+    // Samples drawn AHEAD by the fused iteration kernel (step_fused.cu): the tail phase of iteration t writes z, eps and
+    // the tensor-core copy of z for iteration t + 1 (it holds the new lambda and eps does not depend on lambda), so the
+    // next launch starts its forward contraction at once.  zt_kind == 1: the sample buffers hold exactly the draws of
+    // (zt_step, zt_key) under the current lambda, as zt_nparts per-sample partial sums; any other sampler resets it.
+    int zt_kind, zt_nparts, zt_mloc, zt_pad;
+    unsigned long long zt_step, zt_key;
 };
 
 // A target may ask the mean-field sampling kernel to produce its per-sample preprocessing in the same
@@ -143,6 +149,7 @@ struct SampleHook {
     int zt_ld = 0, zt_seg = 0;   // row pitch of Zt; zt_seg > 0: 3xTF32 split [hi | hi | lo] in segments of zt_seg
     float4* pre = nullptr;
     unsigned long long* tl = nullptr;     // step timeline (diagnostic)
+    unsigned long long* zt_owner = nullptr;   // cleared by whoever rewrites the target's sample-derived buffers (step_fused.cu)
     const void* pf_ptr = nullptr;         // static operand of the next kernel to pull into L2 meanwhile (may be null)
     unsigned long long pf_bytes = 0;
 };

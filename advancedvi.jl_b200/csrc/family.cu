@@ -40,6 +40,7 @@ k_sample(const float* __restrict__ lambda, int D, int ld, int m0, int Mloc, cons
     extern __shared__ __align__(16) float s_ms[];   // STAGE: [ld] mu, [ld] s
     constexpr bool STAGE = !FULLRANK && SPLIT == 1;
     if (HOOK) tl_min(hk.tl, 0);
+    if (HOOK && hk.zt_owner && blockIdx.x == 0 && threadIdx.x == 0) *hk.zt_owner = 0ull;
     pdl_trigger();
     if (HOOK && hk.pf_bytes)   // stream the forward kernel's X into L2 while this kernel runs (static data: before the wait)
         l2_prefetch_span(hk.pf_ptr, hk.pf_bytes, blockIdx.x * SAMPLE_WARPS + (threadIdx.x >> 5), gridDim.x * SAMPLE_WARPS, 8192);
@@ -47,6 +48,8 @@ k_sample(const float* __restrict__ lambda, int D, int ld, int m0, int Mloc, cons
     if (HOOK) tl_min(hk.tl, 4);
     const unsigned long long step = use_val ? st_val.step : st->step;
     const PhiloxKeys pk(use_val ? st_val.key : st->key);
+    // these draws overwrite whatever the fused iteration kernel may have drawn ahead (ObjDeviceState::zt_kind)
+    if (blockIdx.x == 0 && threadIdx.x == 0 && st) const_cast<ObjDeviceState*>(st)->zt_kind = 0;
     const uint32_t c2 = (uint32_t)step, c3 = eps_ctr3(step, stream_id);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float* mu = lambda;

@@ -23,7 +23,6 @@ struct TcParams {
     // The A tensor map has box {32 a-elements, 32 k-rows} and the 32-byte-atom swizzle; a 128 x 32 tile is four boxes.  3xTF32: the k range consists
     // of three segments of a_seg_kb blocks [hi | hi | lo]; the lo part of the source sits a_seg_off elements further.
     int a_mn, a_seg_kb, a_seg_off;
-    int r_to_smem;       // forward epilogue: the residual tile goes to SmemCtl::r_tile instead of C (row-stationary kernel)
     const void* pf_ptr;  // static operand of the NEXT kernel, pulled into L2 by the idle warp 3 while this one computes
     unsigned long long pf_bytes;
     unsigned pf_pace_ns;

@@ -28,10 +28,7 @@ struct SmemCtl {
     int flag;
     float scratch[8];               // fused iteration kernel: values handed from one phase to a later one
     float red16[2][16];             // fused iteration kernel: per-warp partials of a unit's log-likelihood total
-    float tail[2560 + 512];         // fused iteration kernel, tail phase: slab staging + per-coordinate sums
-    uint64_t r_ready;               // row-stationary iteration kernel: the unit's residual tile is in shared memory
-    uint8_t* r_tile;                // row-stationary iteration kernel: [4 k-blocks of 32 samples][NT rows][128 B], 128B swizzle
-    float rs[256];                  // row-stationary iteration kernel: sum over the unit's samples of R, per data row
+    float tail[1024 + 512];         // fused iteration kernel, tail phase: slab staging + per-coordinate sums
     alignas(16) float ys[2][512];   // FWD: y per accumulator stage (<= 256 used); BWD: reduction scratch
 };
 
@@ -199,18 +196,6 @@ __device__ __forceinline__ void epilogue_unit(const TcParams& p, SmemCtl* ctl, i
 #pragma unroll
                     for (int j = 0; j < 8; ++j) { r[j] = tc::round_tf32(r[j]); rlo[j] = 0.0f; }
                 }
-                if (p.r_to_smem) {
-                    // row-stationary iteration kernel: R stays on the SM as the K-major B operand of the backward
-                    // contraction, [n = data row][k = sample], 128-byte swizzle (16-byte chunk index ^ row % 8).
-                    // A warp's 32 lanes are 32 consecutive samples = one 128-byte row: conflict-free stores.
-                    const int kk = a & (BM - 1), k32 = kk & 31;
-                    uint8_t* rt = ctl->r_tile + (size_t)(kk >> 5) * ((size_t)NT * 128);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int n = c + j;
-                        *reinterpret_cast<float*>(rt + n * 128 + ((((k32 >> 2) ^ (n & 7)) << 4) | ((k32 & 3) << 2))) = a_ok ? r[j] : 0.0f;
-                    }
-                } else
                 // (staging this tile through shared memory for 128-byte row stores was measured slower: the
                 // extra STS + barrier cost more than the 32-byte-sector stores; profiles/README.md)
                 if (a_ok && b0 < (p.r_seg ? p.r_seg : p.ldc)) {

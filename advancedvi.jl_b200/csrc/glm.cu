@@ -30,9 +30,10 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 // per-sample prior pieces: pre[m] = {prior_lp, 1/sigma^2, d logp / d eta, |beta|^2}
 __global__ void __launch_bounds__(256)
 k_glm_pre(const float* __restrict__ Z, int ld, int d, int variant, int include_prior, float* __restrict__ Zt,
-          int zt_ld, int zt_seg, float4* __restrict__ pre) {
+          int zt_ld, int zt_seg, float4* __restrict__ pre, unsigned long long* __restrict__ zt_owner) {
     __shared__ float sm[33];
     const int m = blockIdx.x;
+    if (m == 0 && threadIdx.x == 0) *zt_owner = 0ull;   // Zt / pre no longer hold what the fused iteration kernel drew ahead
     float part = 0.f;
     const int iend = zt_seg > 0 ? max(ld, zt_seg) : ld;
     for (int i = threadIdx.x; i < iend; i += blockDim.x) {
@@ -267,13 +268,13 @@ struct Glm : avi_model {
     // work buffers
     int capM = 0, cap_ld = 0; long long cap_n = 0;
     long long ldR = 0;
-    float *R = nullptr, *Zt = nullptr, *Et = nullptr, *llpart = nullptr, *a1p = nullptr, *slabs = nullptr;
+    float *R = nullptr, *Zt = nullptr, *llpart = nullptr, *a1p = nullptr, *slabs = nullptr, *spart = nullptr;
     float4* pre = nullptr;
     long long llpart_cap = 0, ap_cap = 0, slab_cap = 0;
 
     ~Glm() override {
         avi_free(Xr_full); avi_free(Xc_full); avi_free(y_full); avi_free(Xr_b); avi_free(Xc_b); avi_free(y_b);
-        avi_free(idx_own); avi_free(R); avi_free(Zt); avi_free(Et); avi_free(llpart); avi_free(a1p);
+        avi_free(idx_own); avi_free(R); avi_free(Zt); avi_free(llpart); avi_free(a1p); avi_free(spart);
         avi_free(slabs); avi_free(pre); avi_free(tickets); avi_free(gbar);
     }
     bool hooked = false;               // the sampling kernel produced Zt / pre for exactly (hooked_Z, hooked_M)
@@ -299,7 +300,7 @@ struct Glm : avi_model {
         if (M <= 0 || ensure(M, ld) != AVI_OK) return false;
         h->kind = 1; h->d = d; h->variant = variant; h->include_prior = include_prior;
         h->Zt = tc_mode() ? Zt : nullptr; h->pre = pre; h->zt_ld = zt_ld; h->zt_seg = x3 ? segd : 0;
-        h->tl = ctx->tl;
+        h->tl = ctx->tl; h->zt_owner = gbar + 3;
         if (l2_stream() & 1) { h->pf_ptr = Xr; h->pf_bytes = (unsigned long long)n_act * dK * sizeof(float); }
         hooked = true; hooked_Z = Z; hooked_M = M;
         return true;
@@ -315,14 +316,14 @@ struct Glm : avi_model {
 
     int32_t ensure(int M, int ld) {
         if (M <= capM && ld == cap_ld && n_act <= cap_n) return AVI_OK;
-        avi_free(R); avi_free(Zt); avi_free(Et); avi_free(pre);
+        avi_free(R); avi_free(Zt); avi_free(pre); avi_free(spart);
         generation++;
         capM = std::max(M, capM); cap_ld = ld; cap_n = std::max(cap_n, n_act);
         ldR = (x3 ? 3 : 1) * round_up(cap_n, 32);
         zt_ld = x3 ? 3 * segd : ld;
         AVI_CHECK(avi_alloc(ctx, &R, (size_t)capM * ldR));
         AVI_CHECK(avi_alloc(ctx, &Zt, (size_t)capM * zt_ld));
-        if (!x3 && tc_mode()) AVI_CHECK(avi_alloc(ctx, &Et, (size_t)capM * ld));   // row-stationary iteration kernel
+        AVI_CHECK(avi_alloc(ctx, &spart, (size_t)capM * (2 * (size_t)ctx->prop.multiProcessorCount + 1)));   // step_fused.cu: draw_slice
         AVI_CHECK(avi_alloc(ctx, &pre, (size_t)capM));
         return AVI_OK;
     }
@@ -344,7 +345,7 @@ struct Glm : avi_model {
             // the sampling kernel already produced Zt and pre for exactly these samples
         } else {
             k_glm_pre<<<M, 256, 0, ctx->stream>>>(Z, ld, d, variant, include_prior, tc_mode() ? Zt : nullptr, zt_ld,
-                                                  x3 ? segd : 0, pre);
+                                                  x3 ? segd : 0, pre, gbar + 3);
             AVI_LAUNCHED(ctx);
         }
         if (!tc_mode()) {
@@ -462,55 +463,10 @@ struct Glm : avi_model {
         const double flops = 4.0 * (double)n_act * d * Mloc * (x3 ? 3.0 : 1.0);
         return fused_mode >= 2 || flops <= 2e11;
     }
-    // Row-stationary variant (step_fused.cu: k_glm_mf_step2): units = (128 samples) x (NT data rows), both contractions
-    // of a unit on the same CTA.  AVI_FUSED_KERNEL=1 selects the two-phase kernel instead.
-    bool fused2_ok(int M) const {
-        static const int kern = getenv("AVI_FUSED_KERNEL") ? atoi(getenv("AVI_FUSED_KERNEL")) : 1;
-        return kern == 2 && !x3 && Et != nullptr && M > 0;
-    }
-    int32_t fused_step2(const FusedStepArgs& fa) {
-        const int M = fa.Mloc, ld = fa.ld;
-        StepParams sp{};
-        const float w = likeadj();
-        const int sms = ctx->prop.multiProcessorCount;
-        TcParams& f = sp.f;
-        f.Ma = M; f.Nb = (int)n_act; f.n_ablk = (int)ceil_div(M, 128); f.n_kblk = (int)ceil_div(d, 32);
-        f.n_ksplit = 1; f.kb_per_split = f.n_kblk; f.ca = 1; f.cb = 1;
-        const int chunks = std::max(1, sms / f.n_ablk);
-        f.nt = (int)std::min<int64_t>(avi_step_fused2_max_nt(), std::max<int64_t>(32, round_up(ceil_div(n_act, chunks), 16)));
-        f.n_bchunk = (int)ceil_div(n_act, f.nt);
-        f.y = y; f.w = w; f.likelihood = likelihood; f.static_op = subsampled ? 0 : 2;
-        f.post_on = 2; f.r_to_smem = 1;
-        const long long units = (long long)f.n_ablk * f.n_bchunk;
-        AVI_CHECK(ensure_buf(&llpart, &llpart_cap, std::max<long long>(units, 4)));
-        f.part1 = llpart; f.ldpart = capM;
-        const int ldslab = (int)round_up(d, 32);
-        AVI_CHECK(ensure_buf(&a1p, &ap_cap, 2LL * units * ldslab));
-        CUtensorMap tmZ, tmXr, tmEt;
-        AVI_CHECK(avi_tc_make_tmap(ctx, &tmZ, Zt, M, d, zt_ld, 128));
-        AVI_CHECK(avi_tc_make_tmap(ctx, &tmXr, Xr, n_act, d, dK, f.nt));
-        AVI_CHECK(avi_tc_make_tmap(ctx, &tmEt, Et, M, (int64_t)d + 1, ld, 32, /*atom32=*/1));
-        sp.do_sample = 1;
-        sp.lambda = fa.lambda; sp.D = fa.D; sp.ld = ld; sp.m0 = fa.m0; sp.Mloc = M; sp.st = fa.st;
-        sp.Z = fa.Z; sp.E = fa.E; sp.esq = fa.esq;
-        sp.d = d; sp.variant = variant; sp.include_prior = include_prior;
-        sp.Zt = Zt; sp.zt_ld = zt_ld; sp.zt_seg = 0; sp.pre = reinterpret_cast<float*>(pre);
-        sp.Et = Et; sp.n_fblk = (int)ceil_div((int64_t)d + 1, 128); sp.Xr = Xr; sp.dK = dK; sp.n_rows = (int)n_act;
-        sp.bpart1 = a1p; sp.bpart2 = a1p + (size_t)units * ldslab; sp.ldslab = ldslab;
-        sp.t = fa.t;
-        sp.t.unit_ll = llpart; sp.t.n_units_f = (int)units; sp.t.w_lik = w;
-        sp.t.part1 = sp.bpart1; sp.t.part2 = sp.bpart2; sp.t.nslab = (int)units; sp.t.ldslab = ldslab;
-        sp.t.tail_prior = 1;
-        sp.t.done_ticket = reinterpret_cast<unsigned int*>(gbar + 2);
-        sp.gbar = gbar;
-        if (fa.dry_run) return AVI_OK;
-        return avi_step_fused2_launch(ctx, tmZ, tmXr, tmEt, sp);
-    }
     int32_t fused_step(const FusedStepArgs& fa) override {
         const int M = fa.Mloc, ld = fa.ld;
         AVI_CHECK(ensure(M, ld));
         clear_hook();
-        if (fused2_ok(M)) return fused_step2(fa);
         StepParams sp{};
         const float w = likeadj();
         // forward: logits[m][j] = sum_k Zt[m][k] Xr[j][k]
@@ -550,6 +506,10 @@ struct Glm : avi_model {
         sp.Z = fa.Z; sp.E = fa.E; sp.esq = fa.esq;
         sp.d = d; sp.variant = variant; sp.include_prior = include_prior;
         sp.Zt = Zt; sp.zt_ld = zt_ld; sp.zt_seg = x3 ? segd : 0; sp.pre = reinterpret_cast<float*>(pre);
+        // draw the next iteration's samples in the tail phase (AVI_DRAW_AHEAD=0: sample phase at the start of every launch)
+        static const bool ahead = !(getenv("AVI_DRAW_AHEAD") && atoi(getenv("AVI_DRAW_AHEAD")) == 0);
+        sp.draw_ahead = (ahead && fa.t.mode == STEP_TAIL_UPDATE && !x3) ? 1 : 0;
+        sp.spart = spart; sp.spart_stride = ctx->prop.multiProcessorCount;
         sp.t = fa.t;
         sp.t.unit_ll = llpart; sp.t.n_units_f = (int)units_f; sp.t.w_lik = w;
         sp.t.part1 = sp.b.part1; sp.t.part2 = sp.b.part2; sp.t.nslab = nslab; sp.t.ldslab = ldslab;

@@ -478,6 +478,38 @@ int32_t run_steps(avi_opt* op, int32_t n, const int32_t* idx_host, int64_t batch
 
 }  // namespace
 
+// The element loop of avi_host_update, written so that the host compiler vectorises it (restrict-qualified streams,
+// branch-free body per rule) and cloned for AVX2 / AVX-512 hosts: at P = 2050 the scalar loop cost 25 us per call,
+// a quarter of the whole estimate_gradient! + update round trip.
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+#define AVI_HOST_CLONES __attribute__((target_clones("avx512f", "avx2", "default")))
+#else
+#define AVI_HOST_CLONES
+#endif
+AVI_HOST_CLONES
+static void host_update_loop(int rule, const float* h, int op_kind, float op_param, int averager, float w, float b1t, float b2t,
+                             int64_t P, int64_t scale_offset, float* __restrict__ lambda, const float* __restrict__ grad,
+                             float* __restrict__ m1, float* __restrict__ m2, float* __restrict__ lambda_avg) {
+    const int64_t clip_from = (op_kind == AVI_OP_CLIPSCALE && scale_offset >= 0) ? scale_offset : P;
+    if (rule == AVI_RULE_ADAM) {
+        const float c1 = 1.0f / (1.0f - b1t), c2 = 1.0f / (1.0f - b2t);
+        const float be1 = h[1], be2 = h[2], eps = h[3], eta = h[0];
+        for (int64_t p = 0; p < P; ++p) {
+            const float g = grad[p];
+            const float mt = be1 * m1[p] + (1.0f - be1) * g;
+            const float vt = be2 * m2[p] + (1.0f - be2) * g * g;
+            m1[p] = mt; m2[p] = vt;
+            lambda[p] -= (mt * c1) / (std::sqrt(vt * c2) + eps) * eta;
+        }
+    } else {
+        const float eta = h[0];
+        for (int64_t p = 0; p < P; ++p) lambda[p] -= eta * grad[p];
+    }
+    for (int64_t p = clip_from; p < P; ++p) lambda[p] = lambda[p] > op_param ? lambda[p] : op_param;
+    if (averager == AVI_AVG_POLYNOMIAL)
+        for (int64_t p = 0; p < P; ++p) lambda_avg[p] = (1.0f - w) * lambda_avg[p] + w * lambda[p];
+}
+
 extern "C" {
 
 int32_t avi_opt_create(avi_obj* obj, int32_t rule, const float* hyper, int32_t n_hyper, int32_t op_kind,
@@ -592,21 +624,7 @@ int32_t avi_host_update(int32_t rule, const float* hyper, int32_t n_hyper, int32
     if (st[SC_T] == 0.0f) { st[SC_T] = 1.0f; st[SC_B1T] = h[1]; st[SC_B2T] = h[2]; }   // first call (averaging.jl:42)
     const float b1t = st[SC_B1T], b2t = st[SC_B2T];
     const float w = (avg_param + 1.0f) / (st[SC_T] + avg_param);
-    for (int64_t p = 0; p < P; ++p) {
-        float dx;
-        if (rule == AVI_RULE_ADAM) {
-            const float mt = h[1] * m1[p] + (1.0f - h[1]) * grad[p];
-            const float vt = h[2] * m2[p] + (1.0f - h[2]) * grad[p] * grad[p];
-            m1[p] = mt; m2[p] = vt;
-            dx = mt / (1.0f - b1t) / (std::sqrt(vt / (1.0f - b2t)) + h[3]) * h[0];
-        } else {
-            dx = h[0] * grad[p];
-        }
-        float x = lambda[p] - dx;
-        if (op_kind == AVI_OP_CLIPSCALE && scale_offset >= 0 && p >= scale_offset) x = std::max(x, op_param);
-        lambda[p] = x;
-        if (averager == AVI_AVG_POLYNOMIAL) lambda_avg[p] = (1.0f - w) * lambda_avg[p] + w * x;
-    }
+    host_update_loop(rule, h, op_kind, op_param, averager, w, b1t, b2t, P, scale_offset, lambda, grad, m1, m2, lambda_avg);
     st[SC_T] += 1.0f;
     if (rule == AVI_RULE_ADAM) { st[SC_B1T] = b1t * h[1]; st[SC_B2T] = b2t * h[2]; }
     return AVI_OK;

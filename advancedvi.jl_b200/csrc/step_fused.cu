@@ -28,7 +28,7 @@ namespace {
 
 constexpr int NW = NUM_THREADS / 32;            // 20 warps
 constexpr int TAIL_MAX_PER_CTA = 120;           // coordinates per CTA in the tail (SmemCtl::tail: 2 floats each behind the staging area)
-constexpr int TAIL_STAGE = 2560;                // floats of the tail's slab staging area
+constexpr int TAIL_STAGE = 1024;                // floats of the tail's slab staging area
 
 __device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
     unsigned long long v;
@@ -293,12 +293,6 @@ __device__ __forceinline__ void sample_phase(const StepParams& sp, SmemCtl* ctl,
                 }
                 *reinterpret_cast<float4*>(Erow + i) = make_float4(ev[0], ev[1], ev[2], ev[3]);
                 *reinterpret_cast<float4*>(Zrow + i) = make_float4(zv[0], zv[1], zv[2], zv[3]);
-                if (sp.Et) {   // rounded eps for the tensor cores; column d carries 1 (gives sum_m R in the same contraction)
-                    float et4[4];
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) et4[c] = i + c < sp.d ? tc::round_tf32(ev[c]) : (i + c == sp.d ? 1.0f : 0.0f);
-                    *reinterpret_cast<float4*>(sp.Et + (size_t)m * ld + i) = make_float4(et4[0], et4[1], et4[2], et4[3]);
-                }
                 float hi[4], lo[4];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) { hi[c] = tc::round_tf32(zt[c]); lo[c] = tc::round_tf32(zt[c] - hi[c]); }
@@ -337,9 +331,79 @@ struct Snap {
     unsigned long long step, key;
     long long cursor;
     int halted, tp;
+    int zt_ok, zt_nparts;      // the sample buffers already hold this iteration's draws (drawn ahead by the previous tail)
     float b1t, b2t, t_avg, v_old, r_old, shift, logdet;
     unsigned int seq;
 };
+
+// Coordinate slice of a CTA in the tail phase and in the slice-major sampler: `per` coordinates, a multiple of 4 so
+// that a slice is a whole number of Philox quads / 16-byte columns of the sample-major buffers.
+__device__ __forceinline__ int slice_per(int D) {
+    return (((D + (int)gridDim.x - 1) / (int)gridDim.x) + 3) & ~3;
+}
+
+// Slice-major sampler: this CTA draws, for ALL local samples, the coordinates of its slice for iteration `step` with the
+// slice's (mu, s) taken from shared memory (lam2[2 j], lam2[2 j + 1]), writes z, eps and the TF32 copy of z, and leaves
+// per-sample partial sums over the slice (|eps|^2, |beta|^2; the slice holding eta also stores eta_m).  Used by the
+// tail phase to draw the NEXT iteration's samples under the lambda it has just computed, and at kernel entry when
+// nothing was drawn ahead (same code, same bits either way).
+__device__ __forceinline__ void draw_slice(const StepParams& sp, const float* lam2, unsigned long long step, unsigned long long key) {
+    const int D = sp.D, ld = sp.ld;
+    const int per = slice_per(D);
+    const int c0 = (int)blockIdx.x * per;
+    if (c0 >= D) return;
+    const int nq = (min(ld, c0 + per) - c0) / 4;
+    const PhiloxKeys pk(key);
+    const uint32_t c2 = (uint32_t)step, c3 = eps_ctr3(step, (uint32_t)AVI_STREAM_EPS);
+    for (int m = threadIdx.x; m < sp.Mloc; m += NUM_THREADS) {
+        float e2 = 0.f, b2 = 0.f, eta = 0.f;
+        for (int qq = 0; qq < nq; ++qq) {
+            const int i = c0 + 4 * qq;
+            const float4 e = normal4((uint32_t)(i >> 2), (uint32_t)(sp.m0 + m), c2, c3, pk);
+            float ev[4] = {e.x, e.y, e.z, e.w}, zv[4], zt[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const bool in = i + c < D;
+                ev[c] = in ? ev[c] : 0.0f;
+                zv[c] = in ? fmaf(lam2[2 * (4 * qq + c) + 1], ev[c], lam2[2 * (4 * qq + c)]) : 0.0f;
+                e2 = fmaf(ev[c], ev[c], e2);
+                const bool is_beta = i + c < sp.d;
+                b2 = is_beta ? fmaf(zv[c], zv[c], b2) : b2;
+                zt[c] = is_beta ? tc::round_tf32(zv[c]) : 0.0f;
+                if (i + c == sp.d) eta = zv[c];
+            }
+            *reinterpret_cast<float4*>(sp.E + (size_t)m * ld + i) = make_float4(ev[0], ev[1], ev[2], ev[3]);
+            *reinterpret_cast<float4*>(sp.Z + (size_t)m * ld + i) = make_float4(zv[0], zv[1], zv[2], zv[3]);
+            if (i < sp.zt_ld) *reinterpret_cast<float4*>(sp.Zt + (size_t)m * sp.zt_ld + i) = make_float4(zt[0], zt[1], zt[2], zt[3]);
+        }
+        sp.spart[(size_t)blockIdx.x * sp.Mloc + m] = e2;
+        sp.spart[(size_t)(sp.spart_stride + blockIdx.x) * sp.Mloc + m] = b2;
+        if (c0 <= sp.d && sp.d < c0 + per) sp.spart[(size_t)2 * sp.spart_stride * sp.Mloc + m] = eta;
+    }
+}
+
+// Per-sample totals from the slice partials of draw_slice: |eps_m|^2 and the prior terms of the GLM (family.cu:
+// k_sample<.., HOOK> produces the same pair in the sample-major sampler).  Warps 2 and 3, which have no role in the
+// contraction phases, run this while the forward contraction proceeds; consumers come after the next grid barrier.
+__device__ __forceinline__ void finalize_samples(const StepParams& sp, int nparts) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int S = (sp.Mloc + (int)gridDim.x - 1) / (int)gridDim.x;
+    for (int j = warp - 2; j < S; j += 2) {
+        const int m = (int)blockIdx.x * S + j;
+        if (m >= sp.Mloc) break;
+        float e2 = 0.f, b2 = 0.f;
+        for (int c = lane; c < nparts; c += 32) {
+            e2 += __ldcg(sp.spart + (size_t)c * sp.Mloc + m);
+            b2 += __ldcg(sp.spart + (size_t)(sp.spart_stride + c) * sp.Mloc + m);
+        }
+        e2 = warp_sum(e2); b2 = warp_sum(b2);
+        if (lane == 0) {
+            sp.esq[m] = e2;
+            reinterpret_cast<float4*>(sp.pre)[m] =
+                glm_prior_terms(b2, __ldcg(sp.spart + (size_t)2 * sp.spart_stride * sp.Mloc + m), sp.d, sp.variant, sp.include_prior);
+        }
+    }
+}
 
 // Tail phase, all CTAs: CTA c owns coordinates [c * per, (c + 1) * per) of mu and of s.
 //   local scalars (every CTA, same order => same bits) -> [exchange] -> value / ELBO / finiteness ->
@@ -351,13 +415,14 @@ __device__ __forceinline__ void tail_phase(const StepParams& sp, SmemCtl* ctl, c
     const int D = sp.D, accv = t.accv, M = t.M, objective = t.objective, entropy = t.entropy;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float* stage = &ctl->tail[0];      // [2][nc * nslab] slab partials of the slice (TAIL_STAGE floats)
-    float* vals = &ctl->tail[TAIL_STAGE];          // [per][4]: per-coordinate sums over the samples taken here
+    float* vals = &ctl->tail[TAIL_STAGE];          // [per][2]: sticking-the-landing sums of the slice
     float* sm = &ctl->ys[1][0];        // block_sum scratch (33) | [64..] broadcast slots
     const bool stl = entropy == AVI_ENT_STL || entropy == AVI_ENT_STL_ZEROGRAD;
     const bool adam = a.rule == AVI_RULE_ADAM, dog = a.rule == AVI_RULE_DOG || a.rule == AVI_RULE_DOWG;
     const bool polyavg = a.averager == AVI_AVG_POLYNOMIAL;
-    const int per = (D + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int per = slice_per(D);
     const int c0 = min(D, (int)blockIdx.x * per), c1 = min(D, c0 + per), nc = c1 - c0;
+    float* lam2 = &ctl->tail[TAIL_STAGE + 2 * TAIL_MAX_PER_CTA];   // [per][2]: new (mu, s) of the slice for draw_slice
     const int NR = t.comm.nranks;
 
     // ---- every load this CTA needs is requested up front (one L2 round trip), the reductions follow
@@ -386,7 +451,7 @@ __device__ __forceinline__ void tail_phase(const StepParams& sp, SmemCtl* ctl, c
     }
     if (mine) {
         if (i >= sp.d) {
-            if (!t.tail_prior) { v0 = __ldcg(t.acc + i); v1 = __ldcg(t.acc + accv + i); }
+            v0 = __ldcg(t.acc + i); v1 = __ldcg(t.acc + accv + i);
         } else if (!staged) {
 #pragma unroll 8
             for (int q = 0; q < t.nslab; ++q) {
@@ -401,24 +466,16 @@ __device__ __forceinline__ void tail_phase(const StepParams& sp, SmemCtl* ctl, c
             if (polyavg) { av0 = t.avg[i]; av1 = t.avg[D + i]; }
         }
     }
-    //  sums over the samples of the slice's coordinates (warp per coordinate, lanes over the samples):
-    //  sticking the landing: sum_m eps, sum_m eps^2; t.tail_prior (row-stationary kernel, whose backward epilogue runs
-    //  over data rows, not samples): the prior part of the gradient sums, -beta / sigma^2 (d log pi / d eta for i == d)
-    if (stl || t.tail_prior) {
+    //  sticking the landing: sum_m eps and sum_m eps^2 of the slice (warp per coordinate, lanes over the samples)
+    if (stl) {
         for (int j = warp; j < nc; j += NW) {
-            const int ii = c0 + j;
-            float a2 = 0.f, a3 = 0.f, p1 = 0.f, p2 = 0.f;
+            float a2 = 0.f, a3 = 0.f;
             for (int m = lane; m < sp.Mloc; m += 32) {
-                const float e = __ldcg(sp.E + (size_t)m * sp.ld + ii);
+                const float e = __ldcg(sp.E + (size_t)m * sp.ld + c0 + j);
                 a2 += e; a3 = fmaf(e, e, a3);
-                if (t.tail_prior) {
-                    const float g = ii < sp.d ? -__ldcg(sp.Z + (size_t)m * sp.ld + ii) * __ldcg(sp.pre + 4 * (size_t)m + 1)
-                                              : __ldcg(sp.pre + 4 * (size_t)m + 2);
-                    p1 += g; p2 = fmaf(g, e, p2);
-                }
             }
-            a2 = warp_sum(a2); a3 = warp_sum(a3); p1 = warp_sum(p1); p2 = warp_sum(p2);
-            if (lane == 0) { vals[4 * j] = a2; vals[4 * j + 1] = a3; vals[4 * j + 2] = p1; vals[4 * j + 3] = p2; }
+            a2 = warp_sum(a2); a3 = warp_sum(a3);
+            if (lane == 0) { vals[2 * j] = a2; vals[2 * j + 1] = a3; }
         }
     }
     // one fixed-order reduction for the three scalars (20 warp partials each through shared memory)
@@ -429,8 +486,7 @@ __device__ __forceinline__ void tail_phase(const StepParams& sp, SmemCtl* ctl, c
 #pragma unroll
     for (int w2 = 0; w2 < NW; ++w2) { sl += sm[3 * w2]; spr += sm[3 * w2 + 1]; sq += sm[3 * w2 + 2]; }
     sl = fmaf(t.w_lik, sl, spr);
-    if (stl && mine) { v2 = vals[4 * tid]; v3 = vals[4 * tid + 1]; }
-    if (t.tail_prior && mine) { v0 += vals[4 * tid + 2]; v1 += vals[4 * tid + 3]; }
+    if (stl && mine) { v2 = vals[2 * tid]; v3 = vals[2 * tid + 1]; }
     if (staged && mine && i < sp.d) {
         for (int q = 0; q < t.nslab; ++q) { v0 += stage[tid * t.nslab + q]; v1 += stage[tot + tid * t.nslab + q]; }
     }
@@ -497,6 +553,8 @@ __device__ __forceinline__ void tail_phase(const StepParams& sp, SmemCtl* ctl, c
                 t.out[0] = value; t.out[1] = elbo; t.out[2] = S.logdet; t.out[3] = shift_next;
                 const unsigned long long step_next = sn.step + 1ull;
                 sp.st->step = step_next;
+                sp.st->zt_kind = 0;   // the sample buffers hold this call's draws
+                sp.gbar[3] = 0ull;
                 if (NR > 1) *reinterpret_cast<volatile unsigned int*>(&t.comm.dev->seq) = sn.seq;
                 if (t.host_out) {
                     float* tail = t.host_out + 2 * (size_t)D;
@@ -552,8 +610,16 @@ __device__ __forceinline__ void tail_phase(const StepParams& sp, SmemCtl* ctl, c
                 else xx = xx + (sqrtf(fmaf(xx, xx, 4.0f * eta)) - xx) * 0.5f;
             }
             t.lam[p] = xx;
+            lam2[2 * tid + h] = xx;
             if (polyavg) t.avg[p] = (1.0f - w) * (h ? av1 : av0) + w * xx;
         }
+    }
+    // ---- draw the NEXT iteration's samples for this CTA's slice under the lambda just computed
+    const bool ahead = sp.draw_ahead && !sn.halted && !bad;
+    if (ahead) {
+        if (tid >= nc && tid < per) { lam2[2 * tid] = 0.f; lam2[2 * tid + 1] = 0.f; }   // padding coordinates of the last quad
+        __syncthreads();
+        draw_slice(sp, lam2, sn.step + 1ull, sn.key);
     }
     if (blockIdx.x == 0 && tid == 0) {
         if (NR > 1) *reinterpret_cast<volatile unsigned int*>(&t.comm.dev->seq) = sn.seq;
@@ -572,6 +638,11 @@ __device__ __forceinline__ void tail_phase(const StepParams& sp, SmemCtl* ctl, c
                 sp.st->batch_cursor = sn.cursor + 1;
             }
         }
+        // (draw_slice's stores are complete for every CTA when this launch ends; the tag is read by the next launch)
+        sp.st->zt_kind = ahead ? 1 : 0;
+        sp.st->zt_step = sn.step + 1ull; sp.st->zt_key = sn.key;
+        sp.st->zt_nparts = (D + per - 1) / per; sp.st->zt_mloc = sp.Mloc;
+        sp.gbar[3] = ahead ? (unsigned long long)(uintptr_t)sp.st : 0ull;
     }
 }
 
@@ -623,6 +694,11 @@ k_glm_mf_step(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ C
     Snap sn;
     sn.step = sp.st->step; sn.key = sp.st->key; sn.cursor = sp.st->batch_cursor; sn.halted = sp.st->halted; sn.tp = sp.st->trace_pos;
     sn.b1t = sn.b2t = sn.t_avg = sn.v_old = sn.r_old = sn.shift = sn.logdet = 0.f; sn.seq = 0;
+    sn.zt_nparts = sp.st->zt_nparts;
+    // (both tags: the objective's -- z, eps are its buffers -- and the target's -- Zt and the partial sums are shared by
+    // every objective over that target)
+    sn.zt_ok = sp.draw_ahead && sp.st->zt_kind == 1 && sp.st->zt_step == sn.step && sp.st->zt_key == sn.key &&
+               sp.st->zt_mloc == sp.Mloc && __ldcg(sp.gbar + 3) == (unsigned long long)(uintptr_t)sp.st;
     if (sp.t.mode != STEP_TAIL_NONE) {
         if (sp.t.mode == STEP_TAIL_UPDATE) {
             sn.b1t = sp.t.sc[SC_B1T]; sn.b2t = sp.t.sc[SC_B2T]; sn.t_avg = sp.t.sc[SC_T]; sn.v_old = sp.t.sc[SC_V]; sn.r_old = sp.t.sc[SC_R];
@@ -632,7 +708,25 @@ k_glm_mf_step(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ C
     }
 
     if (threadIdx.x == 0) PSTAMP(prof, 3);
-    if (sp.do_sample) {
+    if (sp.draw_ahead) {
+        // optimiser loop: samples come slice-major, normally drawn ahead by the previous launch's tail phase
+        if (!sn.zt_ok) {
+            float* lam2 = &ctl->tail[TAIL_STAGE + 2 * TAIL_MAX_PER_CTA];
+            const int per = slice_per(sp.D), c0 = (int)blockIdx.x * per;
+            for (int j = threadIdx.x; j < per; j += NUM_THREADS) {
+                const bool in = c0 + j < sp.D;
+                lam2[2 * j] = in ? sp.lambda[c0 + j] : 0.f;
+                lam2[2 * j + 1] = in ? sp.lambda[sp.D + c0 + j] : 0.f;
+            }
+            __syncthreads();
+            draw_slice(sp, lam2, sn.step, sn.key);
+            sn.zt_nparts = (sp.D + per - 1) / per;
+            stamp_max(sp.tl, 8);
+            if (threadIdx.x == 0) PSTAMP(prof, 4);
+            grid_barrier(gb);
+            stamp_min(sp.tl, 2);
+        }
+    } else if (sp.do_sample) {
         sample_phase(sp, ctl, sn.step, sn.key);
         stamp_max(sp.tl, 8);
         if (threadIdx.x == 0) PSTAMP(prof, 4);
@@ -640,6 +734,7 @@ k_glm_mf_step(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ C
         stamp_min(sp.tl, 2);
     }
     if (threadIdx.x == 0) PSTAMP(prof, 5);
+    if (sp.draw_ahead && warp >= 2 && warp < 4) finalize_samples(sp, sn.zt_nparts);
     // log det of the scale (sum_i log s_i) is only needed by the tail: the otherwise idle warp 2 takes it while the
     // forward contraction runs (lambda is not overwritten before the tail phase of this launch)
     if (warp == 2 && sp.t.mode != STEP_TAIL_NONE) {
@@ -693,307 +788,6 @@ k_glm_mf_step(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ C
     if (threadIdx.x == 0) PSTAMP(prof, 23);
 }
 
-
-// =========================================================================================================
-// Row-stationary variant.  A work unit is (block of 128 samples) x (chunk of NT data rows), as in the forward phase
-// above, but the CTA that owns a unit runs BOTH contractions on it:
-//   forward   logits[sample, row] = Zt . X'   (K = d)           -> epilogue: log-lik total, R = w (y - sigmoid) as a
-//                                                                   TF32 tile in SHARED memory, K-major over the samples
-//   backward  T[f, row] = sum_{m in block} eps[m, f] R[m, row]   (K = 128 samples; A = eps MN-major from the TF32 copy Et,
-//                                                                   B = the shared-memory R tile: no operand traffic for B)
-//             epilogue (a thread owns a feature, its columns are data rows, double-buffered against the next block's
-//             MMAs):  sum_m g eps  += sum_row X[row, f] T[f, row]      (linearity: sum_m eps g = sum_row X (sum_m eps R))
-//                     sum_m g      += sum_row X[row, f] rs[row],  rs[row] = sum_m R[m, row] = T[d, row]: column d of Et is 1
-// so there is no grid barrier between the contractions, R never reaches global memory, the backward epilogues overlap
-// the tensor work, and the backward contraction is tensor-bound instead of ingest-bound (its B operand is resident).
-// The prior part of the gradient sums moves to the tail phase (StepTail::tail_prior).  TF32 mode only.
-constexpr int V2_KB = BM / BK;   // k-blocks of the backward contraction: 128 samples / 32
-
-template <int LIK>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-k_glm_mf_step2(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmXr,
-               const __grid_constant__ CUtensorMap tmEt, const StepParams sp) {
-    extern __shared__ uint8_t smem_raw[];
-    SmemCtl* ctl = reinterpret_cast<SmemCtl*>((reinterpret_cast<uintptr_t>(smem_raw) + 15) & ~(uintptr_t)15);
-    const TcParams& p = sp.f;
-    const int NT = p.nt, stages = sp.stages_f;
-    const int slot_bytes = A_TILE_BYTES + NT * BK * 4;
-    const int rk_bytes = NT * BK * 4;                       // one k-block (32 samples) of the R tile
-    uint8_t* r_tile = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ctl) + sizeof(SmemCtl) + 1023) & ~(uintptr_t)1023);
-    uint8_t* tiles = r_tile + (size_t)V2_KB * rk_bytes;     // NT % 8 == 0: still 1024-aligned
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned long long* const prof = sp.prof;
-    stamp_min(sp.tl, 0);
-    if (threadIdx.x == 0) PSTAMP(prof, 0);
-
-    if (warp == 0 && lane == 0) { tc::tma_prefetch_desc(&tmZ); tc::tma_prefetch_desc(&tmXr); tc::tma_prefetch_desc(&tmEt); }
-    if (warp == 1 && lane == 0) {
-        init_pipeline(ctl, stages, 0);
-        tc::mbar_init(&ctl->r_ready, EPI_WARPS);
-        tc::mbar_fence_init();
-        ctl->r_tile = r_tile;
-#ifdef AVI_WATCHDOG
-        if (blockIdx.x == 0) { tc::avi_hang_report[5] = tc::smem_u32(ctl); tc::avi_hang_report[6] = tc::smem_u32(&ctl->r_ready); }
-#endif
-    }
-    if (warp == 2) tc::tmem_alloc(&ctl->tmem_base, 512);
-    pdl_trigger();
-    tc::fence_before_sync();
-    __syncthreads();
-    tc::fence_after_sync();
-    const uint32_t tmem_base = ctl->tmem_base;
-
-    int pre = 0;
-    if (warp == 0 && p.static_op == 2) {
-        if (lane == 0) pre = preissue_early(&tmZ, &tmXr, p, ctl, tiles, stages, 2);
-        pre = __shfl_sync(0xffffffffu, pre, 0);
-    }
-    if (threadIdx.x == 0) PSTAMP(prof, 1);
-    pdl_wait();
-    stamp_min(sp.tl, 1);
-    if (threadIdx.x == 0) PSTAMP(prof, 2);
-    if (warp == 0 && p.static_op != 2) {
-        if (lane == 0) pre = preissue_early(&tmZ, &tmXr, p, ctl, tiles, stages, 2);
-        pre = __shfl_sync(0xffffffffu, pre, 0);
-    }
-
-    GridBar gb;
-    gb.ctr = sp.gbar; gb.base = __ldcg(sp.gbar + 1); gb.k = 0;
-    Snap sn;
-    sn.step = sp.st->step; sn.key = sp.st->key; sn.cursor = sp.st->batch_cursor; sn.halted = sp.st->halted; sn.tp = sp.st->trace_pos;
-    sn.b1t = sn.b2t = sn.t_avg = sn.v_old = sn.r_old = sn.shift = sn.logdet = 0.f; sn.seq = 0;
-    if (sp.t.mode == STEP_TAIL_UPDATE) {
-        sn.b1t = sp.t.sc[SC_B1T]; sn.b2t = sp.t.sc[SC_B2T]; sn.t_avg = sp.t.sc[SC_T]; sn.v_old = sp.t.sc[SC_V]; sn.r_old = sp.t.sc[SC_R];
-    }
-    sn.shift = sp.t.out[3];
-    if (sp.t.comm.nranks > 1) sn.seq = *reinterpret_cast<volatile unsigned int*>(&sp.t.comm.dev->seq) + 1u;
-    if (threadIdx.x == 0) PSTAMP(prof, 3);
-
-    sample_phase(sp, ctl, sn.step, sn.key);
-    stamp_max(sp.tl, 8);
-    if (threadIdx.x == 0) PSTAMP(prof, 4);
-    grid_barrier(gb);
-    stamp_min(sp.tl, 2);
-    if (threadIdx.x == 0) PSTAMP(prof, 5);
-    if (warp == 2) {   // log det of the scale for the tail (lambda is overwritten only after the last barrier)
-        float part = 0.f;
-        for (int i = lane; i < sp.D; i += 32) part += __logf(sp.lambda[sp.D + i]);
-        part = warp_sum(part);
-        if (lane == 0) ctl->scratch[0] = part;
-    }
-
-    const int units = p.n_ablk * p.n_bchunk;
-    const int first = blockIdx.x, stride = gridDim.x;
-    const int n_fblk = sp.n_fblk, fb_first = sp.d / BM;     // the block holding column d (the ones column) goes first
-    if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (tc::elect_one()) {
-            fence_proxy_async_global();
-            int stage = 0; uint32_t phase = 0;
-            int kcount = 0;
-            for (int u = first; u < units; u += stride) {
-                const int ab = u % p.n_ablk, bc = u / p.n_ablk;
-                for (int kb = 0; kb < p.n_kblk; ++kb, ++kcount) {            // forward: A = Zt block, B = X rows
-                    tc::mbar_wait(&ctl->empty[stage], phase ^ 1);
-                    uint8_t* sa = tiles + stage * slot_bytes;
-                    if (kcount < pre) {
-                        tc::mbar_arrive_expect_tx(&ctl->full[stage], (uint32_t)A_TILE_BYTES);
-                        tc::tma_load_2d(sa, &tmZ, &ctl->full[stage], kb * BK, ab * BM);
-                    } else {
-                        tc::mbar_arrive_expect_tx(&ctl->full[stage], (uint32_t)slot_bytes);
-                        tc::tma_load_2d(sa, &tmZ, &ctl->full[stage], kb * BK, ab * BM);
-                        tc::tma_load_2d(sa + A_TILE_BYTES, &tmXr, &ctl->full[stage], kb * BK, bc * NT);
-                    }
-                    if (++stage == stages) { stage = 0; phase ^= 1; }
-                }
-                for (int j = 0; j < n_fblk; ++j) {                           // backward: A = eps (MN-major), B resident
-                    const int fb = j == 0 ? fb_first : (j <= fb_first ? j - 1 : j);
-                    for (int kb = 0; kb < V2_KB; ++kb) {
-                        tc::mbar_wait(&ctl->empty[stage], phase ^ 1);
-                        uint8_t* sa = tiles + stage * slot_bytes;
-                        tc::mbar_arrive_expect_tx(&ctl->full[stage], (uint32_t)A_TILE_BYTES);
-#pragma unroll
-                        for (int q = 0; q < BM / 32; ++q)
-                            tc::tma_load_2d(sa + q * 4096, &tmEt, &ctl->full[stage], fb * BM + q * 32, ab * BM + kb * BK);
-                        if (++stage == stages) { stage = 0; phase ^= 1; }
-                    }
-                }
-            }
-            PSTAMP(prof, 6);
-        }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (tc::elect_one()) {
-            const uint32_t idesc_f = tc::idesc_tf32(BM, NT, 0), idesc_b = tc::idesc_tf32(BM, NT, 1);
-            int stage = 0; uint32_t phase = 0;
-            int as = 0; uint32_t aphase = 0;
-            uint32_t rphase = 0;
-            const uint32_t r_addr = tc::smem_u32(r_tile);
-            for (int u = first; u < units; u += stride) {
-                tc::mbar_wait(&ctl->tmem_empty[as], aphase ^ 1);
-                tc::fence_after_sync();
-                uint32_t tacc = tmem_base + (uint32_t)(as * 256);
-                for (int kb = 0; kb < p.n_kblk; ++kb) {
-                    tc::mbar_wait(&ctl->full[stage], phase);
-                    tc::fence_after_sync();
-                    if (kb == 0 && u == first) PSTAMP(prof, 7);
-                    const uint32_t sa = tc::smem_u32(tiles + stage * slot_bytes);
-                    const uint64_t da = tc::smem_desc_k_sw128(sa);
-                    const uint64_t db = tc::smem_desc_k_sw128(sa + A_TILE_BYTES);
-#pragma unroll
-                    for (int k = 0; k < BK / 8; ++k)
-                        tc::umma_tf32(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_f, (kb > 0 || k > 0) ? 1u : 0u);
-                    tc::umma_commit(&ctl->empty[stage]);
-                    if (++stage == stages) { stage = 0; phase ^= 1; }
-                }
-                tc::umma_commit(&ctl->tmem_full[as]);
-                PSTAMP(prof, 8);
-                if (++as == 2) { as = 0; aphase ^= 1; }
-                // the unit's residual tile (written by the forward epilogue through the generic proxy, fenced there)
-                tc::mbar_wait(&ctl->r_ready, rphase);
-                rphase ^= 1;
-                tc::fence_after_sync();
-                PSTAMP(prof, 14);
-                for (int j = 0; j < n_fblk; ++j) {
-                    tc::mbar_wait(&ctl->tmem_empty[as], aphase ^ 1);
-                    tc::fence_after_sync();
-                    tacc = tmem_base + (uint32_t)(as * 256);
-                    for (int kb = 0; kb < V2_KB; ++kb) {
-                        tc::mbar_wait(&ctl->full[stage], phase);
-                        tc::fence_after_sync();
-                        const uint32_t sa = tc::smem_u32(tiles + stage * slot_bytes);
-                        const uint64_t da = tc::smem_desc_mn_sw128(sa, 4096u);
-                        const uint64_t db = tc::smem_desc_k_sw128(r_addr + (uint32_t)(kb * rk_bytes));
-#pragma unroll
-                        for (int k = 0; k < BK / 8; ++k)
-                            tc::umma_tf32(tacc, da + (uint64_t)(64 * k), db + (uint64_t)(2 * k), idesc_b, (kb > 0 || k > 0) ? 1u : 0u);
-                        tc::umma_commit(&ctl->empty[stage]);
-                        if (++stage == stages) { stage = 0; phase ^= 1; }
-                    }
-                    tc::umma_commit(&ctl->tmem_full[as]);
-                    if (++as == 2) { as = 0; aphase ^= 1; }
-                }
-                PSTAMP(prof, 16);
-            }
-        }
-    } else if (warp >= 4) {
-        // ===================== epilogues =====================
-        const int ew = warp - 4, quarter = warp & 3, cq = ew >> 2;
-        const int et = threadIdx.x - 128;
-        const int ngroups = NT / 8;
-        const int c_begin = 8 * ((ngroups * cq) / 4), c_end = 8 * ((ngroups * (cq + 1)) / 4);
-        float* red1 = &ctl->ys[0][0];           // [4 column quarters][128 features]
-        float* red2 = &ctl->ys[1][0];
-        int as = 0; uint32_t aphase = 0;
-        for (int u = first; u < units; u += stride) {
-            const int ab = u % p.n_ablk, bc = u / p.n_ablk;
-            {   // ---- forward epilogue: log-likelihood total of the unit, R -> shared memory
-                const int a = ab * BM + quarter * 32 + lane;
-                const bool a_ok = a < p.Ma;
-                const uint32_t tacc = tmem_base + (uint32_t)(as * 256) + ((uint32_t)(quarter * 32) << 16);
-                float s1, s2;
-                epilogue_unit<EPI_GLM_FWD, LIK, true>(p, ctl, as, aphase, tacc, NT, a, a_ok, bc, 0, c_begin, c_end, et, s1, s2);
-                if (et == 0) PSTAMP(prof, 9);
-                tc::fence_before_sync();
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // R: generic-proxy stores -> tensor-core reads
-                __syncwarp();
-                if (lane == 0) { tc::mbar_arrive(&ctl->tmem_empty[as]); tc::mbar_arrive(&ctl->r_ready); }
-                epilogue_fwd_unit_total(p, ctl, as, u, et, a_ok ? s1 : 0.0f);
-                if (et == 0) PSTAMP(prof, 11);
-                if (++as == 2) { as = 0; aphase ^= 1; }
-            }
-            // ---- backward epilogues: one per feature block, a thread owns feature f, its columns are the unit's data rows
-            const int row0 = bc * NT;
-            for (int j = 0; j < n_fblk; ++j) {
-                const int fb = j == 0 ? fb_first : (j <= fb_first ? j - 1 : j);
-                const int f = fb * BM + quarter * 32 + lane;
-                const bool f_ok = f < sp.d;
-                const uint32_t tacc = tmem_base + (uint32_t)(as * 256) + ((uint32_t)(quarter * 32) << 16);
-                // X[row][f] for this thread's columns, requested while the MMAs of the block still run
-                const float* xp = sp.Xr + (size_t)row0 * sp.dK + f;
-                float x[32];
-                float s1 = 0.f, s2 = 0.f;
-                bool waited = false;
-                for (int c = c_begin; c < c_end; c += 32) {
-                    const int ncol = min(32, c_end - c);
-#pragma unroll
-                    for (int q = 0; q < 32; ++q)
-                        x[q] = (q < ncol && f_ok && row0 + c + q < sp.n_rows) ? __ldg(xp + (size_t)(c + q) * sp.dK) : 0.0f;
-                    if (!waited) {
-                        tc::mbar_wait(&ctl->tmem_full[as], aphase);
-                        tc::fence_after_sync();
-                        waited = true;
-                        if (j == 0) {
-                            // rs[row] = T[d, row]: the thread that owns "feature" d publishes its columns first.  tcgen05.ld is
-                            // a warp-collective (.sync.aligned): the whole warp that holds lane d loads, one lane stores.
-                            const int f_w0 = fb * BM + quarter * 32;
-                            if (f_w0 <= sp.d && sp.d < f_w0 + 32) {
-                                for (int cc = c_begin; cc < c_end; cc += 8) {
-                                    float v[8];
-                                    tc::tmem_ld8(tacc + (uint32_t)cc, v);
-                                    if (f == sp.d) {
-#pragma unroll
-                                        for (int q = 0; q < 8; ++q) ctl->rs[cc + q] = v[q];
-                                    }
-                                }
-                            }
-                            epi_bar_sync();
-                        }
-                    }
-#pragma unroll
-                    for (int h = 0; h < 4; ++h) {
-                        if (h * 8 < ncol) {
-                            float v[8];
-                            tc::tmem_ld8(tacc + (uint32_t)(c + h * 8), v);
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) {
-                                s2 = fmaf(x[h * 8 + q], v[q], s2);
-                                s1 = fmaf(x[h * 8 + q], ctl->rs[c + h * 8 + q], s1);
-                            }
-                        }
-                    }
-                }
-                if (!waited) {   // (cannot happen: every column quarter has at least one group when NT >= 32)
-                    tc::mbar_wait(&ctl->tmem_full[as], aphase); tc::fence_after_sync();
-                    if (j == 0) epi_bar_sync();
-                }
-                tc::fence_before_sync();
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive(&ctl->tmem_empty[as]);
-                // combine the four column quarters of a feature (fixed order) and write the unit's slab row
-                const int rowi = quarter * 32 + lane;
-                red1[cq * BM + rowi] = s1; red2[cq * BM + rowi] = s2;
-                epi_bar_sync();
-                if (cq == 0 && f_ok) {
-                    const size_t slab = (size_t)u * sp.ldslab;
-                    sp.bpart1[slab + f] = ((red1[rowi] + red1[BM + rowi]) + red1[2 * BM + rowi]) + red1[3 * BM + rowi];
-                    sp.bpart2[slab + f] = ((red2[rowi] + red2[BM + rowi]) + red2[2 * BM + rowi]) + red2[3 * BM + rowi];
-                }
-                epi_bar_sync();
-                if (++as == 2) { as = 0; aphase ^= 1; }
-            }
-            if (et == 0) PSTAMP(prof, 19);
-        }
-    }
-    stamp_max(sp.tl, 10);
-
-    if (threadIdx.x == 0) PSTAMP(prof, 20);
-    grid_barrier(gb);
-    stamp_min(sp.tl, 4);
-    if (threadIdx.x == 0) PSTAMP(prof, 21);
-    tail_phase(sp, ctl, sn, gb);
-    if (threadIdx.x == 0) PSTAMP(prof, 22);
-
-    if (blockIdx.x == 0 && threadIdx.x == 0) sp.gbar[1] = gb.base + (unsigned long long)gb.k * gridDim.x;
-    tc::fence_before_sync();
-    __syncthreads();
-    if (warp == 2) {
-        tc::fence_after_sync();
-        tc::tmem_dealloc(tmem_base, 512);
-    }
-    stamp_max(sp.tl, 11);
-    if (threadIdx.x == 0) PSTAMP(prof, 23);
-}
 
 }  // namespace
 
@@ -1077,62 +871,6 @@ int32_t avi_step_fused_launch(avi_ctx* ctx, const CUtensorMap& tmZ, const CUtens
                     : nc_exp ? cudaLaunchKernelEx(&cfg, k_glm_mf_step<0, false>, tmZ, tmXr, tmXc, tmR, sp)
                              : cudaLaunchKernelEx(&cfg, k_glm_mf_step<0, true>, tmZ, tmXr, tmXc, tmR, sp);
     if (e != cudaSuccess) AVI_FAIL(ctx, AVI_ERR_CUDA, std::string("fused step launch: ") + cudaGetErrorString(e));
-    AVI_LAUNCHED(ctx);
-    return AVI_OK;
-}
-
-int avi_step_fused2_max_nt() {
-    // shared memory: control block + R tile (4 * NT * 128 B) + at least 3 ring slots of 16 KB + NT * 128 B
-    int best = 0;
-    for (int nt = 32; nt <= 256; nt += 16) {
-        const int need = 16 + (int)sizeof(SmemCtl) + 1024 + 4 * nt * 128 + 3 * (A_TILE_BYTES + nt * 128);
-        if (need <= SMEM_LIMIT) best = nt;
-    }
-    return best;
-}
-
-int32_t avi_step_fused2_launch(avi_ctx* ctx, const CUtensorMap& tmZ, const CUtensorMap& tmXr, const CUtensorMap& tmEt,
-                               StepParams& sp) {
-    static bool attr_done = false;
-    if (!attr_done) {
-        AVI_CUDA(ctx, cudaFuncSetAttribute(k_glm_mf_step2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-        AVI_CUDA(ctx, cudaFuncSetAttribute(k_glm_mf_step2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-        attr_done = true;
-    }
-    const int nt = sp.f.nt;
-    if (nt % 16 || nt < 32 || nt > avi_step_fused2_max_nt()) AVI_FAIL(ctx, AVI_ERR_INVALID, "row chunk does not fit the row-stationary kernel");
-    const int fixed = 16 + (int)sizeof(SmemCtl) + 1024 + 4 * nt * 128;
-    const int slot = A_TILE_BYTES + nt * 128;
-    sp.stages_f = std::max(3, std::min(MAX_STAGES, (SMEM_LIMIT - fixed) / slot));
-    sp.stages_b = sp.stages_f;
-    const int smem = fixed + sp.stages_f * slot;
-    if (smem > SMEM_LIMIT) AVI_FAIL(ctx, AVI_ERR_INVALID, "tiles do not fit in shared memory");
-    const int sms = ctx->prop.multiProcessorCount;
-    const int64_t units = (int64_t)sp.f.n_ablk * sp.f.n_bchunk;
-    int grid = (int)std::min<int64_t>(sms, units);
-    grid = std::max(grid, std::min(sms, (int)ceil_div(sp.D, TAIL_MAX_PER_CTA)));
-    if (ceil_div(sp.D, grid) > TAIL_MAX_PER_CTA) AVI_FAIL(ctx, AVI_ERR_UNSUPPORTED, "too many coordinates for the fused tail");
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = ctx->stream;
-    cudaLaunchAttribute at[1];
-    int na = 0;
-    if (avi_pdl_enabled()) {
-        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at[na].val.programmaticStreamSerializationAllowed = 1;
-        ++na;
-    }
-    cfg.attrs = at; cfg.numAttrs = na;
-    sp.tl = ctx->tl;
-    static const bool prof_on = getenv("AVI_STEP_PROF") && atoi(getenv("AVI_STEP_PROF")) != 0;
-    if (prof_on) {
-        if (!g_prof) { if (cudaMalloc(&g_prof, 160 * 32 * sizeof(unsigned long long)) != cudaSuccess) g_prof = nullptr; }
-        if (g_prof && !ctx->capturing) cudaMemsetAsync(g_prof, 0, 160 * 32 * sizeof(unsigned long long), ctx->stream);
-        sp.prof = g_prof; g_prof_grid = grid;
-    }
-    AviTimed timed(ctx, "glm_step");
-    cudaError_t e = sp.f.likelihood == AVI_GLM_BERNOULLI_LOGIT ? cudaLaunchKernelEx(&cfg, k_glm_mf_step2<0>, tmZ, tmXr, tmEt, sp)
-                                                              : cudaLaunchKernelEx(&cfg, k_glm_mf_step2<1>, tmZ, tmXr, tmEt, sp);
-    if (e != cudaSuccess) AVI_FAIL(ctx, AVI_ERR_CUDA, std::string("row-stationary step launch: ") + cudaGetErrorString(e));
     AVI_LAUNCHED(ctx);
     return AVI_OK;
 }

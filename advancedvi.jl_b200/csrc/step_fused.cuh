@@ -32,7 +32,6 @@ struct StepTail {
     float* logp;                   // [Mloc] log pi(z_m) (unused by the kernel: the tail takes sum_m log pi from unit_ll and pre)
     const float* unit_ll; int n_units_f; float w_lik;   // per forward unit: log-likelihood total; likelihood adjustment
     const float *part1, *part2; int nslab, ldslab;      // split-K slabs of sum_m g, sum_m g*eps (backward phase)
-    int tail_prior;                // the tail adds the prior part of the gradient sums itself (row-stationary kernel)
     float *lam, *grad, *m1, *m2, *avg, *sc, *out;
     float* trace; int trace_cap;
     UpdArgs a;
@@ -53,12 +52,12 @@ struct StepParams {
     int d, variant, include_prior;
     float* Zt; int zt_ld, zt_seg;
     float* pre;                    // float4 per sample
-    // row-stationary kernel (k_glm_mf_step2): TF32 copy of eps with ones in column d (A operand of its backward
-    // contraction), feature blocks of 128 over [0, d], the full-data / minibatch X rows for its epilogue
-    float* Et; int n_fblk; const float* Xr; int dK; int n_rows;
-    float *bpart1, *bpart2; int ldslab;
+    // slice-major sampling, one iteration ahead (optimiser loop, plain TF32 mode): the tail phase draws the next
+    // iteration's samples; spart = [2][grid][Mloc] per-sample partial sums (|eps|^2, |beta|^2) + [Mloc] eta
+    int draw_ahead; float* spart; int spart_stride;
     StepTail t;
-    unsigned long long* gbar;      // [2] grid barrier: monotonic arrival counter | its value at the start of the launch
+    unsigned long long* gbar;      // grid barrier: [0] monotonic arrival counter | [1] its value at the start of the launch;
+                                   // [2] completion ticket (estimate_gradient! boundary) | [3] who drew the target's samples ahead
     unsigned long long* tl;        // AVI_TIMELINE: %globaltimer stamps per phase (diagnostic)
     unsigned long long* prof;      // AVI_STEP_PROF: per-CTA stamps [grid][32] (diagnostic)
 };
@@ -75,8 +74,3 @@ struct FusedStepArgs {
 int avi_step_fused_max_per_cta();   // coordinates of the tail one CTA can take
 int32_t avi_step_fused_launch(avi_ctx* ctx, const CUtensorMap& tmZ, const CUtensorMap& tmXr, const CUtensorMap& tmXc,
                               const CUtensorMap& tmR, StepParams& sp);
-// row-stationary variant: a CTA keeps its unit's residual tile in shared memory and runs the backward contraction on
-// it right away (no grid barrier between the contractions, R never reaches global memory)
-int avi_step_fused2_max_nt();
-int32_t avi_step_fused2_launch(avi_ctx* ctx, const CUtensorMap& tmZ, const CUtensorMap& tmXr, const CUtensorMap& tmEt,
-                               StepParams& sp);

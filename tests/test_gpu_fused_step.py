@@ -260,3 +260,39 @@ def test_fused_c2_full_size(avi, ctx):
     (v0, g0, e0), elbos0, lam0 = out[0]
     assert abs(v - v0) <= 2e-6 * abs(v0) and relerr(g, g0) < 2e-5
     assert np.allclose(elbos2, elbos0, rtol=2e-6) and relerr(lam2, lam0) < 2e-5
+
+
+def test_fused_draw_ahead_is_invalidated_by_other_users(avi, ctx):
+    """The tail phase draws the NEXT iteration's samples; they may only be trusted if nothing else rewrote the buffers
+    in between: another optimisation over the same target, a direct log-density call on the target, a `rand` on the
+    same objective.  Interleaving all of those must leave each trajectory bit-identical to running it alone."""
+    n, d, M = 600, 70, 96
+    prob, _ = make_pair(avi, ctx, "logreg_subsampling", n, d, "tf32")
+    prob.set_fused_step(2)
+    q, _ = make_q(avi, d + 1)
+    alg_a = avi.KLMinRepGradDescent(optimizer=avi.Adam(1e-2), n_samples=M, operator=avi.ClipScale())
+    alg_b = avi.KLMinRepGradDescent(optimizer=avi.Descent(1e-3), entropy=avi.StickingTheLandingEntropy(), n_samples=M // 2,
+                                    operator=avi.ClipScale())
+    T = 6
+    _, ia, sa = avi.optimize(KEY, alg_a, T, prob, q)
+    _, ib, sb = avi.optimize(KEY + 1, alg_b, T, prob, q)
+    alone_a, alone_b = [i["elbo"] for i in ia], [i["elbo"] for i in ib]
+    lam_a, lam_b = sa.params()[0], sb.params()[0]
+    for s in (sa, sb):
+        s.close(); s.obj.close()
+    mixed_a, mixed_b, sa, sb = [], [], None, None
+    Z = (0.1 * P.normal_matrix(3, 0, d + 1, 5)).astype(np.float32)
+    for t in range(T):
+        _, i1, sa = avi.optimize(KEY, alg_a, 1, prob, q, state=sa)
+        mixed_a.append(i1[0]["elbo"])
+        if t % 2 == 0:
+            prob.logdensity_and_gradient(Z)              # rewrites the target's tensor-core copy of z
+        _, i2, sb = avi.optimize(KEY + 1, alg_b, 1, prob, q, state=sb)
+        mixed_b.append(i2[0]["elbo"])
+        if t % 3 == 1:
+            sa.obj.rand(q)                                # rewrites the objective's own z / eps
+    assert mixed_a == alone_a and mixed_b == alone_b
+    assert np.array_equal(sa.params()[0], lam_a) and np.array_equal(sb.params()[0], lam_b)
+    for s in (sa, sb):
+        s.close(); s.obj.close()
+    prob.close()
