@@ -57,6 +57,7 @@ SIGNATURES = {
     "avi_comm_buffer": (C.c_int32, [vp, C.c_int64, C.c_char_p]),
     "avi_comm_connect": (C.c_int32, [vp, C.c_int32, C.c_int32, C.c_char_p]),
     "avi_comm_disconnect": (C.c_int32, [vp]),
+    "avi_comm_barrier": (C.c_int32, [vp]),
     "avi_model_mvnormal_diag_create": (C.c_int32, [vp, c_float_p, c_float_p, C.c_int32, C.POINTER(vp)]),
     "avi_model_glm_create": (C.c_int32, [vp, c_float_p, c_float_p, C.c_int64, C.c_int32, C.c_int64, C.c_int32,
                                          C.c_int32, C.c_int32, C.POINTER(vp)]),

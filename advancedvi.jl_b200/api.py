@@ -35,7 +35,7 @@ __all__ = [
     "Descent", "Adam", "DoG", "DoWG", "IdentityOperator", "ClipScale", "ProximalLocationScaleEntropy",
     "NoAveraging", "PolynomialAveraging",
     "KLMinRepGradDescent", "KLMinRepGradProxDescent", "KLMinScoreGradDescent", "ADVI", "BBVI",
-    "optimize", "estimate_objective", "Objective", "AviError", "HostUpdate",
+    "optimize", "estimate_objective", "Objective", "AviError", "HostUpdate", "central_fd_gradient",
     "gaussian_expectation_gradient_and_hessian",
 ]
 
@@ -136,6 +136,10 @@ class Context:
         assert len(handles) == nranks and all(len(x) == 64 for x in handles)
         L.check(L.lib.avi_comm_connect(self.h, rank, nranks, b"".join(handles)), self.h)
         self.rank, self.nranks = rank, nranks
+
+    def comm_barrier(self):
+        """Device-side rendezvous of the connected ranks, enqueued on this context's stream."""
+        L.check(L.lib.avi_comm_barrier(self.h), self.h)
 
     def disconnect_peers(self):
         """Unmap the peers' exchange buffers; call on every rank and synchronise the ranks before re-connecting."""
@@ -244,16 +248,49 @@ class GaussGLM(LogReg):
     likelihood = L.GLM_GAUSSIAN
 
 
+def central_fd_gradient(f, z, rel_step=1e-5):
+    """Central finite differences of a scalar function in Float64: the default gradient of capability-0 targets."""
+    z = np.asarray(z, np.float64).copy()
+    g = np.empty_like(z)
+    for i in range(z.size):
+        h = rel_step * max(1.0, abs(z[i]))
+        zi = z[i]
+        z[i] = zi + h; fp = float(f(z))
+        z[i] = zi - h; fm = float(f(z))
+        z[i] = zi
+        g[i] = (fp - fm) / (2.0 * h)
+    return g
+
+
 class HostCallbackProblem(_Problem):
     """Any LogDensityProblem: fn(z: (D,) float32) -> logp  (capability 0)  or  (logp, grad)  (capability 1).
-    One call per Monte-Carlo sample, as the reference does (src/algorithms/repgradelbo.jl:84-86)."""
+    One call per Monte-Carlo sample, as the reference does (src/algorithms/repgradelbo.jl:84-86).
 
-    def __init__(self, ctx: Context, D: int, fn, capability: int = 1):
+    Capability 0 under RepGradELBO: the reference differentiates through `logdensity` with its AD backend
+    (src/algorithms/repgradelbo.jl:50-62).  The native path has no AD backend, so such a target needs
+    `fallback_gradient`: "central_fd" (central finite differences in Float64) or a callable (f, z) -> gradient; the
+    target is then presented to the library as first-order.  Without it RepGradELBO is refused with an explanation
+    (ScoreGradELBO and estimate_objective never need a gradient)."""
+
+    def __init__(self, ctx: Context, D: int, fn, capability: int = 1, fallback_gradient=None):
+        if capability == 0 and fallback_gradient is not None:
+            grad_of = central_fd_gradient if fallback_gradient == "central_fd" else fallback_gradient
+
+            def scalar(z):
+                r = fn(np.asarray(z, np.float32))
+                return r[0] if isinstance(r, tuple) else r
+
+            def first_order(z):
+                return scalar(z), grad_of(scalar, z.astype(np.float64))
+            fn_used, cap_used = first_order, 1
+        else:
+            fn_used, cap_used = fn, capability
+
         def tramp(user, z, Dn, logp, grad):
             try:
                 zz = np.ctypeslib.as_array(z, shape=(Dn,)).copy()
-                r = fn(zz)
-                if capability >= 1:
+                r = fn_used(zz)
+                if cap_used >= 1:
                     lp, g = r
                     if grad:
                         np.ctypeslib.as_array(grad, shape=(Dn,))[:] = np.asarray(g, dtype=np.float32)
@@ -267,7 +304,7 @@ class HostCallbackProblem(_Problem):
                 return 1
         self._cb = L.LOGDENSITY_FN(tramp)
         h = L.vp()
-        L.check(L.lib.avi_model_hostcallback_create(ctx.h, D, capability, self._cb, None, C.byref(h)), ctx.h)
+        L.check(L.lib.avi_model_hostcallback_create(ctx.h, D, cap_used, self._cb, None, C.byref(h)), ctx.h)
         self.h, self.ctx = h, ctx
 
 
@@ -426,6 +463,8 @@ class ReshufflingBatchSubsampling:
         self.batchsize = int(batchsize)
         if self.batchsize < 1:
             raise ValueError("batchsize must be >= 1")
+        if self.dataset.size and self.dataset.min() < 0:
+            raise ValueError("dataset holds 0-based row indices: negative entries are invalid")
 
     def __len__(self):                                    # reshuffling.jl:23-25
         return -(-len(self.dataset) // self.batchsize)

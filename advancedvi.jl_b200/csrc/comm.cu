@@ -30,6 +30,7 @@ struct CommState {
     void* peer_base[MAX_RANKS] = {nullptr};
     bool opened[MAX_RANKS] = {false};
     CommDev* dev = nullptr;
+    float* bar_buf = nullptr;    // payload of avi_comm_barrier
     PeerTable table{};
     bool connected = false;
 };
@@ -144,6 +145,7 @@ void avi_comm_destroy(avi_ctx* ctx) {
         if (cs->opened[r]) cudaIpcCloseMemHandle(cs->peer_base[r]);
     if (cs->base) cudaFree(cs->base);
     if (cs->dev) cudaFree(cs->dev);
+    if (cs->bar_buf) cudaFree(cs->bar_buf);
     delete cs;
     ctx->comm = nullptr;
 }
@@ -167,11 +169,22 @@ int32_t avi_comm_buffer(avi_ctx* ctx, int64_t max_floats, char* handle_out) {
     // happened before any peer can push into the buffer, i.e. before the handle leaves this call
     AVI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     AVI_CHECK(avi_alloc(ctx, &cs->dev, 1));
+    AVI_CHECK(avi_alloc(ctx, &cs->bar_buf, 16));
     cudaIpcMemHandle_t h;
     AVI_CUDA(ctx, cudaIpcGetMemHandle(&h, cs->base));
     static_assert(sizeof(h) == 64, "CUDA IPC handle size");
     std::memcpy(handle_out, &h, 64);
     return AVI_OK;
+}
+
+// Device-side rendezvous of the ranks on the ctx stream: a one-float exchange (every rank leaves it within an NVLink
+// store latency of the last rank entering).  Measurement harnesses use it to start a timed region together.
+int32_t avi_comm_barrier(avi_ctx* ctx) {
+    if (!ctx) return AVI_ERR_INVALID;
+    CommState* cs = state(ctx);
+    if (!cs || !cs->connected || cs->nranks <= 1) return AVI_OK;
+    cudaSetDevice(ctx->device);
+    return avi_comm_exchange(ctx, cs->bar_buf, 1);
 }
 
 // Unmap every peer's buffer (this rank's own allocation stays).  Ranks call this -- and then synchronise among

@@ -64,7 +64,7 @@ k_sample(const float* __restrict__ lambda, int D, int ld, int m0, int Mloc, cons
     const int m_step = SPLIT == 1 ? (int)gridDim.x * SAMPLE_WARPS : Mloc;
     for (int m = SPLIT == 1 ? blockIdx.x * SAMPLE_WARPS + warp : blockIdx.x; m < Mloc; m += m_step) {
         float part = 0.0f, bsq = 0.0f, eta = 0.0f;
-        float* Erow = E + (size_t)m * ld;
+        float* Erow = E ? E + (size_t)m * ld : nullptr;   // (mean-field forward-only callers do not need eps: E == nullptr)
         float* Zrow = FULLRANK ? nullptr : Z + (size_t)m * ld;
         for (int q = SPLIT == 1 ? lane : threadIdx.x; q < ld / 4; q += 32 * SPLIT) {
             const float4 e = normal4((uint32_t)q, (uint32_t)(m0 + m), c2, c3, pk);
@@ -105,7 +105,7 @@ k_sample(const float* __restrict__ lambda, int D, int ld, int m0, int Mloc, cons
                     if (i + c == hk.d) eta = zv[c];
                 }
             }
-            *reinterpret_cast<float4*>(Erow + i) = make_float4(ev[0], ev[1], ev[2], ev[3]);
+            if (FULLRANK || Erow) *reinterpret_cast<float4*>(Erow + i) = make_float4(ev[0], ev[1], ev[2], ev[3]);
             if (!FULLRANK) *reinterpret_cast<float4*>(Zrow + i) = make_float4(zv[0], zv[1], zv[2], zv[3]);
             if (HOOK && hk.Zt) {
                 float hi[4], lo[4];
@@ -575,7 +575,9 @@ int32_t avi_objective_fused(avi_obj* o, const float* lambda, const StepTail& tai
 int32_t avi_objective_forward_chunk(avi_obj* o, const float* lambda, int m0, int Mc, const ObjDeviceState* ov,
                                     float* sums_dev) {
     avi_ctx* ctx = o->ctx;
-    AVI_CHECK(avi_family_sample(o, lambda, o->Z, o->E, o->esq, Mc, m0, o->d_state, ov));
+    // forward only: eps itself is not needed downstream (|eps_m|^2 is), so the mean-field sampler writes z alone --
+    // the algorithmic 4 (2 D + D M) bytes of SURVEY.md 8(d) K1
+    AVI_CHECK(avi_family_sample(o, lambda, o->Z, o->family == AVI_MEANFIELD ? nullptr : o->E, o->esq, Mc, m0, o->d_state, ov));
     AVI_CHECK(o->model->eval(o->Z, o->ld, Mc, o->logp, nullptr));
     k_forward_sums<<<1, 1024, 0, ctx->stream>>>(lambda, o->D, o->family == AVI_FULLRANK, o->logp, o->esq, Mc, sums_dev);
     AVI_LAUNCHED(ctx);

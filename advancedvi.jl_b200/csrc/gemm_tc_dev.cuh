@@ -46,10 +46,16 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 512;"
 
 // Epilogue of one work unit for one thread: waits for the accumulator stage, consumes the thread's TMEM
 // row (lane) over its column range and returns the per-thread partial sums.
-template <int EPI, int LIK, bool COH = false>
-__device__ __forceinline__ void epilogue_unit(const TcParams& p, SmemCtl* ctl, int as, uint32_t aphase,
+// POST / X3 >= 0 fix TcParams::post_on / the 3xTF32 layout at compile time (the fused iteration kernel executes every
+// instruction of its epilogues once per launch, so code it cannot reach still costs instruction fetches around it);
+// -1: read them from the parameters (stand-alone kernels).
+template <int EPI, int LIK, bool COH = false, int POST = -1, int X3 = -1>
+__device__ __forceinline__ void epilogue_unit(const TcParams& p_, SmemCtl* ctl, int as, uint32_t aphase,
                                               uint32_t tacc, int NT, int a, bool a_ok, int bc, int ks, int c_begin,
                                               int c_end, int et, float& s1, float& s2) {
+    const TcParams& p = p_;
+    const int post_on = POST >= 0 ? POST : p.post_on;
+    const int r_seg = X3 == 0 ? 0 : p.r_seg;
     s1 = 0.0f; s2 = 0.0f;
     if (EPI == EPI_GLM_FWD) {
         int b = bc * NT + et;
@@ -60,12 +66,12 @@ __device__ __forceinline__ void epilogue_unit(const TcParams& p, SmemCtl* ctl, i
         // eps[b][a] for this thread's columns, fetched while the MMAs are still running
         const float* Ea = p.E + a;
         float pr1 = 0.0f, pr2 = 0.0f;
-        if (p.post_on) {
+        if (post_on) {
             // Work that does not depend on this kernel's MMAs, done while they run (the epilogue warps would
             // otherwise sleep on the accumulator barrier):
             // (1) log pi(z_m) = w * sum(partial log-lik of the forward kernel) + log prior, by the a-block-0 CTAs
             const int ab0 = a / BM;
-            if (ab0 == 0 && p.post_on == 1) {   // (post_on == 2, fused iteration: the tail phase takes sum_m log pi itself)
+            if (ab0 == 0 && post_on == 1) {   // (post_on == 2, fused iteration: the tail phase takes sum_m log pi itself)
                 float* red = &ctl->ys[0][0];   // 16 warps x 32 lanes
                 const int ew = et >> 5, ln = et & 31;
                 for (int m0 = (ks * p.n_bchunk + bc) * 32; m0 < p.Nb; m0 += p.n_ksplit * p.n_bchunk * 32) {
@@ -185,7 +191,7 @@ __device__ __forceinline__ void epilogue_unit(const TcParams& p, SmemCtl* ctl, i
 #pragma unroll
                 for (int j = 0; j < 8; ++j) s1 += lpv[j];
                 float rlo[8];
-                if (p.r_seg) {
+                if (r_seg) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const float hi = tc::round_tf32(r[j]);
@@ -198,15 +204,15 @@ __device__ __forceinline__ void epilogue_unit(const TcParams& p, SmemCtl* ctl, i
                 }
                 // (staging this tile through shared memory for 128-byte row stores was measured slower: the
                 // extra STS + barrier cost more than the 32-byte-sector stores; profiles/README.md)
-                if (a_ok && b0 < (p.r_seg ? p.r_seg : p.ldc)) {
+                if (a_ok && b0 < (r_seg ? r_seg : p.ldc)) {
                     float4* dst = reinterpret_cast<float4*>(p.C + (size_t)a * p.ldc + b0);
                     dst[0] = make_float4(r[0], r[1], r[2], r[3]);
                     dst[1] = make_float4(r[4], r[5], r[6], r[7]);
-                    if (p.r_seg) {   // 3xTF32: R is the B operand of the backward contraction: [hi | lo | hi]
-                        float4* dl = reinterpret_cast<float4*>(p.C + (size_t)a * p.ldc + p.r_seg + b0);
+                    if (r_seg) {   // 3xTF32: R is the B operand of the backward contraction: [hi | lo | hi]
+                        float4* dl = reinterpret_cast<float4*>(p.C + (size_t)a * p.ldc + r_seg + b0);
                         dl[0] = make_float4(rlo[0], rlo[1], rlo[2], rlo[3]);
                         dl[1] = make_float4(rlo[4], rlo[5], rlo[6], rlo[7]);
-                        float4* dh = reinterpret_cast<float4*>(p.C + (size_t)a * p.ldc + 2 * (size_t)p.r_seg + b0);
+                        float4* dh = reinterpret_cast<float4*>(p.C + (size_t)a * p.ldc + 2 * (size_t)r_seg + b0);
                         dh[0] = make_float4(r[0], r[1], r[2], r[3]);
                         dh[1] = make_float4(r[4], r[5], r[6], r[7]);
                     }

@@ -136,7 +136,7 @@ __device__ __forceinline__ int preissue_early(const CUtensorMap* tmA, const CUte
 
 // One contraction phase: the single-CTA pipeline of k_gemm_tc (gemm_tc.cu) over the units u = blockIdx.x,
 // blockIdx.x + gridDim.x, ...; the ring and the accumulator stages start from their initial state.
-template <int EPI, int LIK, bool COH>
+template <int EPI, int LIK, int X3>
 __device__ __forceinline__ void tc_phase(const CUtensorMap* tmA, const CUtensorMap* tmB, const TcParams& p, SmemCtl* ctl,
                                          uint8_t* tiles, uint32_t tmem_base, int stages, int pre_issued, int early_op,
                                          unsigned long long* prof, int ps) {
@@ -220,7 +220,7 @@ __device__ __forceinline__ void tc_phase(const CUtensorMap* tmA, const CUtensorM
             const bool a_ok = a < p.Ma;
             const uint32_t tacc = tmem_base + (uint32_t)(as * 256) + ((uint32_t)(quarter * 32) << 16);
             float s1, s2;
-            epilogue_unit<EPI, LIK, COH>(p, ctl, as, aphase, tacc, NT, a, a_ok, bc, ks, c_begin, c_end, et, s1, s2);
+            epilogue_unit<EPI, LIK, true, 2, X3>(p, ctl, as, aphase, tacc, NT, a, a_ok, bc, ks, c_begin, c_end, et, s1, s2);
             if (et == 0) PSTAMP(prof, ps + 3);   // accumulator consumed (epilogue math of the unit done)
             tc::fence_before_sync();
             __syncwarp();
@@ -243,7 +243,7 @@ __device__ __forceinline__ void tc_phase(const CUtensorMap* tmA, const CUtensorM
 // sampling kernel's GLM hook produces (family.cu: k_sample<.., HOOK>): the TF32-rounded beta block Zt (A operand of the
 // forward contraction), |eps_m|^2 and the per-sample prior terms.  Samples are dealt to CTAs in contiguous groups of
 // S = ceil(Mloc / grid); inside a CTA W = 20 / S warps share one sample (fixed-order combine through shared memory).
-__device__ __forceinline__ void sample_phase(const StepParams& sp, SmemCtl* ctl, unsigned long long step,
+__device__ __noinline__ void sample_phase(const StepParams& sp, SmemCtl* ctl, unsigned long long step,
                                              unsigned long long key) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = (sp.Mloc + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -486,6 +486,7 @@ __device__ __forceinline__ void tail_phase(const StepParams& sp, SmemCtl* ctl, c
 #pragma unroll
     for (int w2 = 0; w2 < NW; ++w2) { sl += sm[3 * w2]; spr += sm[3 * w2 + 1]; sq += sm[3 * w2 + 2]; }
     sl = fmaf(t.w_lik, sl, spr);
+    if (tid == 0) PSTAMP(sp.prof, 24);   // inputs loaded, scalars reduced
     if (stl && mine) { v2 = vals[2 * tid]; v3 = vals[2 * tid + 1]; }
     if (staged && mine && i < sp.d) {
         for (int q = 0; q < t.nslab; ++q) { v0 += stage[tid * t.nslab + q]; v1 += stage[tot + tid * t.nslab + q]; }
@@ -568,6 +569,7 @@ __device__ __forceinline__ void tail_phase(const StepParams& sp, SmemCtl* ctl, c
         return;
     }
 
+    if (tid == 0) PSTAMP(sp.prof, 25);   // value known, gradient of the slice stored
     // ---- optimiser step (common.jl:91-94)
     float eta = a.rule == AVI_RULE_DESCENT ? a.h0 : 0.f, v_new = 0.f, r_new = 0.f;
     if (dog) {
@@ -614,6 +616,7 @@ __device__ __forceinline__ void tail_phase(const StepParams& sp, SmemCtl* ctl, c
             if (polyavg) t.avg[p] = (1.0f - w) * (h ? av1 : av0) + w * xx;
         }
     }
+    if (tid == 0) PSTAMP(sp.prof, 26);   // update of the slice stored
     // ---- draw the NEXT iteration's samples for this CTA's slice under the lambda just computed
     const bool ahead = sp.draw_ahead && !sn.halted && !bad;
     if (ahead) {
@@ -649,7 +652,7 @@ __device__ __forceinline__ void tail_phase(const StepParams& sp, SmemCtl* ctl, c
 // timeline slots (AVI_TIMELINE; atomicMin in 0..7, atomicMax in 8..15): first CTA 0 entered | 1 past the dependency wait |
 // 2 past barrier 0 (forward starts) | 3 past barrier 1 (backward starts) | 4 past barrier 2 (tail starts);
 // last CTA 8 left the sample phase | 9 left the forward phase | 10 left the backward phase | 11 done
-template <int LIK, bool COH>
+template <int LIK, int X3>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_glm_mf_step(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmXr,
               const __grid_constant__ CUtensorMap tmXc, const __grid_constant__ CUtensorMap tmR, const StepParams sp) {
@@ -744,7 +747,7 @@ k_glm_mf_step(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ C
         if (lane == 0) ctl->scratch[0] = part;
     }
 
-    tc_phase<EPI_GLM_FWD, LIK, COH>(&tmZ, &tmXr, sp.f, ctl, tiles, tmem_base, sp.stages_f, pre, 2, prof, 6);
+    tc_phase<EPI_GLM_FWD, LIK, X3>(&tmZ, &tmXr, sp.f, ctl, tiles, tmem_base, sp.stages_f, pre, 2, prof, 6);
     stamp_max(sp.tl, 9);
 
     // ---- drain, re-carve the ring for the backward geometry, request its static operand (X columns) while the
@@ -764,7 +767,7 @@ k_glm_mf_step(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ C
     tc::fence_after_sync();
     if (threadIdx.x == 0) PSTAMP(prof, 13);
 
-    tc_phase<EPI_GLM_BWD, 0, COH>(&tmXc, &tmR, sp.b, ctl, tiles, tmem_base, sp.stages_b, pre, 1, prof, 14);
+    tc_phase<EPI_GLM_BWD, 0, X3>(&tmXc, &tmR, sp.b, ctl, tiles, tmem_base, sp.stages_b, pre, 1, prof, 14);
     stamp_max(sp.tl, 10);
 
     if (sp.t.mode != STEP_TAIL_NONE) {
@@ -822,9 +825,10 @@ int32_t avi_step_fused_launch(avi_ctx* ctx, const CUtensorMap& tmZ, const CUtens
                               const CUtensorMap& tmR, StepParams& sp) {
     static bool attr_done = false;
     if (!attr_done) {
-        AVI_CUDA(ctx, cudaFuncSetAttribute(k_glm_mf_step<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-        AVI_CUDA(ctx, cudaFuncSetAttribute(k_glm_mf_step<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-        AVI_CUDA(ctx, cudaFuncSetAttribute(k_glm_mf_step<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        AVI_CUDA(ctx, cudaFuncSetAttribute(k_glm_mf_step<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        AVI_CUDA(ctx, cudaFuncSetAttribute(k_glm_mf_step<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        AVI_CUDA(ctx, cudaFuncSetAttribute(k_glm_mf_step<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        AVI_CUDA(ctx, cudaFuncSetAttribute(k_glm_mf_step<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         attr_done = true;
     }
     const int extra = 16 + (int)sizeof(SmemCtl) + 1024;
@@ -864,12 +868,11 @@ int32_t avi_step_fused_launch(avi_ctx* ctx, const CUtensorMap& tmZ, const CUtens
         sp.prof = g_prof; g_prof_grid = grid;
     }
     AviTimed timed(ctx, "glm_step");
-    // AVI_STEP_NC=1: TIMING EXPERIMENT ONLY -- in-kernel-produced epilogue inputs through the read-only path (results may
-    // be stale): measures what the coherent ld.global.cg loads cost
-    static const bool nc_exp = getenv("AVI_STEP_NC") && atoi(getenv("AVI_STEP_NC")) != 0;
-    cudaError_t e = sp.f.likelihood != AVI_GLM_BERNOULLI_LOGIT ? cudaLaunchKernelEx(&cfg, k_glm_mf_step<1, true>, tmZ, tmXr, tmXc, tmR, sp)
-                    : nc_exp ? cudaLaunchKernelEx(&cfg, k_glm_mf_step<0, false>, tmZ, tmXr, tmXc, tmR, sp)
-                             : cudaLaunchKernelEx(&cfg, k_glm_mf_step<0, true>, tmZ, tmXr, tmXc, tmR, sp);
+    const bool bern = sp.f.likelihood == AVI_GLM_BERNOULLI_LOGIT, x3 = sp.f.r_seg != 0;
+    cudaError_t e = bern ? (x3 ? cudaLaunchKernelEx(&cfg, k_glm_mf_step<0, 1>, tmZ, tmXr, tmXc, tmR, sp)
+                               : cudaLaunchKernelEx(&cfg, k_glm_mf_step<0, 0>, tmZ, tmXr, tmXc, tmR, sp))
+                         : (x3 ? cudaLaunchKernelEx(&cfg, k_glm_mf_step<1, 1>, tmZ, tmXr, tmXc, tmR, sp)
+                               : cudaLaunchKernelEx(&cfg, k_glm_mf_step<1, 0>, tmZ, tmXr, tmXc, tmR, sp));
     if (e != cudaSuccess) AVI_FAIL(ctx, AVI_ERR_CUDA, std::string("fused step launch: ") + cudaGetErrorString(e));
     AVI_LAUNCHED(ctx);
     return AVI_OK;

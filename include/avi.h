@@ -97,6 +97,8 @@ int32_t avi_comm_connect(avi_ctx* ctx, int32_t rank, int32_t nranks, const char*
 /* Unmap the peers' buffers (collective by convention: every rank calls it, then the ranks synchronise, before any
  * rank destroys its context or calls avi_comm_buffer again). */
 int32_t avi_comm_disconnect(avi_ctx* ctx);
+/* Enqueue a device-side rendezvous of the connected ranks on the ctx stream (no-op for a single rank). */
+int32_t avi_comm_barrier(avi_ctx* ctx);
 /* the cudaStream_t every call on this ctx enqueues on (for hosts that order their own work after it) */
 void* avi_ctx_stream(avi_ctx* ctx);
 

@@ -35,7 +35,8 @@ names = {0: "entry", 1: "prologue done", 2: "past dependency wait", 3: "snapshot
          11: "fwd: unit complete", 12: "arrive barrier 1", 13: "past barrier 1",
          14: "bwd: last operand request", 15: "bwd: first operands landed", 16: "bwd: last MMA issued", 17: "bwd: epilogue math done",
          18: "bwd: slab rows stored", 19: "bwd: unit complete (+combine)", 20: "arrive barrier 2", 21: "past barrier 2",
-         22: "tail done", 23: "exit"}
+         24: "tail: inputs loaded, scalars reduced", 25: "tail: value + gradient of the slice", 26: "tail: update stored",
+         22: "tail done (next samples drawn)", 23: "exit"}
 print(f"# rows {rows}, grid {grid}: ns since the first CTA's entry (min / mean / max over CTAs that stamped)")
 for k in sorted(names):
     v = h[:, k][h[:, k] > 0] - t0

