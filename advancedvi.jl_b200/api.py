@@ -276,8 +276,8 @@ class HostCallbackProblem(_Problem):
         if capability == 0 and fallback_gradient is not None:
             grad_of = central_fd_gradient if fallback_gradient == "central_fd" else fallback_gradient
 
-            def scalar(z):
-                r = fn(np.asarray(z, np.float32))
+            def scalar(z):          # (called with Float64 points: differences of Float32 evaluations would drown h)
+                r = fn(z)
                 return r[0] if isinstance(r, tuple) else r
 
             def first_order(z):

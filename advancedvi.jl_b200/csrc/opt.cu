@@ -351,7 +351,9 @@ int32_t steps_prepare(avi_opt* op, int32_t n, const int32_t* idx_host, int64_t b
         if (need > op->idx_cap) {
             AVI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             avi_free(op->idx_dev);
-            op->idx_cap = need;
+            // (the captured iteration holds this pointer: room for calls of up to 1024 iterations, so that a longer call
+            // after a short one does not pay for a re-capture)
+            op->idx_cap = std::max<int64_t>(need, 1024 * batch);
             AVI_CHECK(avi_alloc(ctx, &op->idx_dev, (size_t)need));
             drop_graph(op);
         }

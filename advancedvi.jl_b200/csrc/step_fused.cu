@@ -405,6 +405,67 @@ __device__ __forceinline__ void finalize_samples(const StepParams& sp, int npart
     }
 }
 
+// The exchange of a multi-rank run inside the tail phase (low-latency push protocol of comm_dev.cuh): entry (class c,
+// coordinate i) travels as element c * accv + i, the scalars as elements 4 * accv + {0, 1}; every rank sums the ranks'
+// values in rank order => identical bits everywhere.  __noinline__ on purpose (and StepParams is a __grid_constant__
+// kernel parameter, so taking its address costs nothing): code that a launch does not execute should not sit in the
+// instruction stream of a kernel whose every instruction runs once.
+struct Sums6 { float v0, v1, v2, v3, sl, sq; };
+__device__ __noinline__ Sums6 tail_exchange(const StepParams& sp, SmemCtl* ctl, unsigned int seq, int i, bool mine, bool stl, Sums6 v) {
+    const StepTail& t = sp.t;
+    const int tid = threadIdx.x, accv = t.accv;
+    float* sm = &ctl->ys[1][0];
+    const long long sbase = 4ll * accv;
+    const bool x01 = (t.xmask & STEP_X_V01) != 0, x23 = (t.xmask & STEP_X_V23) != 0 && stl;
+    if (mine) {
+        if (x01) { ll_push(t.comm, seq, (long long)i, v.v0); ll_push(t.comm, seq, (long long)accv + i, v.v1); }
+        if (x23) { ll_push(t.comm, seq, 2ll * accv + i, v.v2); ll_push(t.comm, seq, 3ll * accv + i, v.v3); }
+    }
+    if (blockIdx.x == 0 && tid == NUM_THREADS - 1) {
+        if (t.xmask & STEP_X_S0) ll_push(t.comm, seq, sbase, v.sl);
+        if (t.xmask & STEP_X_S1) ll_push(t.comm, seq, sbase + 1, v.sq);
+    }
+    if (mine) {
+        const long long idx[4] = {(long long)i, (long long)accv + i, 2ll * accv + i, 3ll * accv + i};
+        const bool need[4] = {x01, x01, x23, x23};
+        const float own[4] = {v.v0, v.v1, v.v2, v.v3};
+        float out[4];
+        ll_gather<4>(t.comm, seq, idx, need, own, out);
+        if (x01) { v.v0 = out[0]; v.v1 = out[1]; }
+        if (x23) { v.v2 = out[2]; v.v3 = out[3]; }
+    }
+    if (tid == NUM_THREADS - 1) {
+        const long long idx[2] = {sbase, sbase + 1};
+        const bool need[2] = {(t.xmask & STEP_X_S0) != 0, (t.xmask & STEP_X_S1) != 0};
+        const float own[2] = {v.sl, v.sq};
+        float out[2];
+        ll_gather<2>(t.comm, seq, idx, need, own, out);
+        sm[64] = need[0] ? out[0] : v.sl; sm[65] = need[1] ? out[1] : v.sq;
+    }
+    __syncthreads();
+    v.sl = sm[64]; v.sq = sm[65];
+    return v;
+}
+
+// The three scalars of the value slot, by the two warps without a role in the contraction phases, while the backward
+// contraction runs (their inputs are final after barrier 1): scratch[1] = sum over the forward units of their
+// log-likelihood totals, scratch[2] = sum_m log prior(z_m), scratch[3] = sum_m |eps_m|^2.  Lane-strided + shuffle tree:
+// the same order in every CTA and on every rank.
+__device__ __forceinline__ void tail_scalars(const StepParams& sp, SmemCtl* ctl) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 2) {
+        float sl = 0.f;
+        for (int u = lane; u < sp.t.n_units_f; u += 32) sl += __ldcg(sp.t.unit_ll + u);
+        sl = warp_sum(sl);
+        if (lane == 0) ctl->scratch[1] = sl;
+    } else if (warp == 3) {
+        float spr = 0.f, sq = 0.f;
+        for (int m = lane; m < sp.Mloc; m += 32) { spr += __ldcg(sp.pre + 4 * (size_t)m); sq += __ldcg(sp.esq + m); }
+        spr = warp_sum(spr); sq = warp_sum(sq);
+        if (lane == 0) { ctl->scratch[2] = spr; ctl->scratch[3] = sq; }
+    }
+}
+
 // Tail phase, all CTAs: CTA c owns coordinates [c * per, (c + 1) * per) of mu and of s.
 //   local scalars (every CTA, same order => same bits) -> [exchange] -> value / ELBO / finiteness ->
 //   gradient entries of the slice -> [DoG / DoWG: partial norms + one more grid barrier] -> update of the slice ->
@@ -428,9 +489,8 @@ __device__ __forceinline__ void tail_phase(const StepParams& sp, SmemCtl* ctl, c
     // ---- every load this CTA needs is requested up front (one L2 round trip), the reductions follow
     //  scalars: sum_m log pi(z_m) = w * (sum of the forward units' log-likelihood totals) + sum_m log prior(z_m);
     //           sum_m |eps_m|^2
-    float sl = 0.f, spr = 0.f, sq = 0.f;
-    for (int u = tid; u < t.n_units_f; u += NUM_THREADS) sl += __ldcg(t.unit_ll + u);
-    for (int m = tid; m < sp.Mloc; m += NUM_THREADS) { spr += __ldcg(sp.pre + 4 * (size_t)m); sq += __ldcg(sp.esq + m); }
+    //  (taken by warps 2 and 3 during the backward phase, tail_scalars: if every CTA fetched these few cache lines right
+    //  after the barrier, 144 SMs would queue on the same L2 lines -- measured ~2 us in front of the tail)
     //  this thread's coordinate (j = tid < nc): the split-K slab partials of sum_m g and sum_m g*eps (the eta coordinate
     //  i == d comes complete from the backward epilogue), lambda and the optimiser state
     const bool mine = tid < nc;
@@ -439,15 +499,15 @@ __device__ __forceinline__ void tail_phase(const StepParams& sp, SmemCtl* ctl, c
     float x0 = 0.f, x1 = 1.f, s1m0 = 0.f, s1m1 = 0.f, s2m0 = 0.f, s2m1 = 0.f, av0 = 0.f, av1 = 0.f;
     // (all threads fetch the nc x nslab partials of the slice at once -- one round trip -- and stage them in shared
     // memory; the coordinate's owner adds them up in slab order.  Slices too large for the staging area: owner loop.)
+    // IMPORTANT: every global load of this block goes to a REGISTER first and the shared-memory stores come last.  A
+    // store to shared memory through a generic pointer between two global loads makes the in-order issue wait for the
+    // first load before it can issue the second (measured: 13 serialised L2 round trips, 2.9 us, in this block).
     const int tot = nc * t.nslab;
     const bool staged = 2 * tot <= TAIL_STAGE;
-    if (staged) {
-        for (int idx = tid; idx < tot; idx += NUM_THREADS) {
-            const int j = idx / t.nslab, q = idx - j * t.nslab, ii = c0 + j;
-            const bool beta = ii < sp.d;
-            stage[idx] = beta ? __ldcg(t.part1 + (size_t)q * t.ldslab + ii) : 0.f;
-            stage[tot + idx] = beta ? __ldcg(t.part2 + (size_t)q * t.ldslab + ii) : 0.f;
-        }
+    float sg1 = 0.f, sg2 = 0.f;
+    if (staged && tid < tot) {
+        const int j = tid / t.nslab, q = tid - j * t.nslab, ii = c0 + j;
+        if (ii < sp.d) { sg1 = __ldcg(t.part1 + (size_t)q * t.ldslab + ii); sg2 = __ldcg(t.part2 + (size_t)q * t.ldslab + ii); }
     }
     if (mine) {
         if (i >= sp.d) {
@@ -466,6 +526,16 @@ __device__ __forceinline__ void tail_phase(const StepParams& sp, SmemCtl* ctl, c
             if (polyavg) { av0 = t.avg[i]; av1 = t.avg[D + i]; }
         }
     }
+    if (staged) {
+        if (tid < tot) { stage[tid] = sg1; stage[tot + tid] = sg2; }
+        for (int idx = tid + NUM_THREADS; idx < tot; idx += NUM_THREADS) {   // (slices with more than 640 partials)
+            const int j = idx / t.nslab, q = idx - j * t.nslab, ii = c0 + j;
+            const bool beta = ii < sp.d;
+            const float a1 = beta ? __ldcg(t.part1 + (size_t)q * t.ldslab + ii) : 0.f;
+            const float a2 = beta ? __ldcg(t.part2 + (size_t)q * t.ldslab + ii) : 0.f;
+            stage[idx] = a1; stage[tot + idx] = a2;
+        }
+    }
     //  sticking the landing: sum_m eps and sum_m eps^2 of the slice (warp per coordinate, lanes over the samples)
     if (stl) {
         for (int j = warp; j < nc; j += NW) {
@@ -478,53 +548,18 @@ __device__ __forceinline__ void tail_phase(const StepParams& sp, SmemCtl* ctl, c
             if (lane == 0) { vals[2 * j] = a2; vals[2 * j + 1] = a3; }
         }
     }
-    // one fixed-order reduction for the three scalars (20 warp partials each through shared memory)
-    sl = warp_sum(sl); spr = warp_sum(spr); sq = warp_sum(sq);
-    if (lane == 0) { sm[3 * warp] = sl; sm[3 * warp + 1] = spr; sm[3 * warp + 2] = sq; }
-    __syncthreads();
-    sl = 0.f; spr = 0.f; sq = 0.f;
-#pragma unroll
-    for (int w2 = 0; w2 < NW; ++w2) { sl += sm[3 * w2]; spr += sm[3 * w2 + 1]; sq += sm[3 * w2 + 2]; }
-    sl = fmaf(t.w_lik, sl, spr);
+    __syncthreads();   // stage[] / vals[] complete
+    float sl = fmaf(t.w_lik, ctl->scratch[1], ctl->scratch[2]), sq = ctl->scratch[3];
     if (tid == 0) PSTAMP(sp.prof, 24);   // inputs loaded, scalars reduced
     if (stl && mine) { v2 = vals[2 * tid]; v3 = vals[2 * tid + 1]; }
     if (staged && mine && i < sp.d) {
         for (int q = 0; q < t.nslab; ++q) { v0 += stage[tid * t.nslab + q]; v1 += stage[tot + tid * t.nslab + q]; }
     }
 
-    // ---- exchange over NVLink (low-latency push protocol of comm_dev.cuh): entry (class c, coordinate i) travels as
-    //      element c * accv + i, the scalars as elements 4 * accv + {0, 1}; sums are taken in rank order
+    // ---- exchange over NVLink, multi-rank runs only (out of line: the single-rank iteration does not fetch its code)
     if (NR > 1) {
-        const unsigned int seq = sn.seq;
-        const long long sbase = 4ll * accv;
-        const bool x01 = (t.xmask & STEP_X_V01) != 0, x23 = (t.xmask & STEP_X_V23) != 0 && stl;
-        if (mine) {
-            if (x01) { ll_push(t.comm, seq, (long long)i, v0); ll_push(t.comm, seq, (long long)accv + i, v1); }
-            if (x23) { ll_push(t.comm, seq, 2ll * accv + i, v2); ll_push(t.comm, seq, 3ll * accv + i, v3); }
-        }
-        if (blockIdx.x == 0 && tid == NUM_THREADS - 1) {
-            if (t.xmask & STEP_X_S0) ll_push(t.comm, seq, sbase, sl);
-            if (t.xmask & STEP_X_S1) ll_push(t.comm, seq, sbase + 1, sq);
-        }
-        if (mine) {
-            const long long idx[4] = {(long long)i, (long long)accv + i, 2ll * accv + i, 3ll * accv + i};
-            const bool need[4] = {x01, x01, x23, x23};
-            const float own[4] = {v0, v1, v2, v3};
-            float out[4];
-            ll_gather<4>(t.comm, seq, idx, need, own, out);
-            if (x01) { v0 = out[0]; v1 = out[1]; }
-            if (x23) { v2 = out[2]; v3 = out[3]; }
-        }
-        if (tid == NUM_THREADS - 1) {
-            const long long idx[2] = {sbase, sbase + 1};
-            const bool need[2] = {(t.xmask & STEP_X_S0) != 0, (t.xmask & STEP_X_S1) != 0};
-            const float own[2] = {sl, sq};
-            float out[2];
-            ll_gather<2>(t.comm, seq, idx, need, own, out);
-            sm[64] = need[0] ? out[0] : sl; sm[65] = need[1] ? out[1] : sq;
-        }
-        __syncthreads();
-        sl = sm[64]; sq = sm[65];
+        const Sums6 x = tail_exchange(sp, ctl, sn.seq, i, mine, stl, Sums6{v0, v1, v2, v3, sl, sq});
+        v0 = x.v0; v1 = x.v1; v2 = x.v2; v3 = x.v3; sl = x.sl; sq = x.sq;
     }
 
     MfSums S;
@@ -655,7 +690,8 @@ __device__ __forceinline__ void tail_phase(const StepParams& sp, SmemCtl* ctl, c
 template <int LIK, int X3>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_glm_mf_step(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmXr,
-              const __grid_constant__ CUtensorMap tmXc, const __grid_constant__ CUtensorMap tmR, const StepParams sp) {
+              const __grid_constant__ CUtensorMap tmXc, const __grid_constant__ CUtensorMap tmR,
+              const __grid_constant__ StepParams sp) {
     extern __shared__ uint8_t smem_raw[];
     SmemCtl* ctl = reinterpret_cast<SmemCtl*>((reinterpret_cast<uintptr_t>(smem_raw) + 15) & ~(uintptr_t)15);
     uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ctl) + sizeof(SmemCtl) + 1023) & ~(uintptr_t)1023);
@@ -767,6 +803,7 @@ k_glm_mf_step(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ C
     tc::fence_after_sync();
     if (threadIdx.x == 0) PSTAMP(prof, 13);
 
+    if (sp.t.mode != STEP_TAIL_NONE) tail_scalars(sp, ctl);
     tc_phase<EPI_GLM_BWD, 0, X3>(&tmXc, &tmR, sp.b, ctl, tiles, tmem_base, sp.stages_b, pre, 1, prof, 14);
     stamp_max(sp.tl, 10);
 

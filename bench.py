@@ -267,12 +267,18 @@ class Bench:
             allb = [bb for bb in allb if len(bb) == cfg["batch"]]
             self.batches = parallel.rank_batches(allb, rank, world)
 
-    def run_steps(self, n, vals, elbos):
+    def minibatches(self, n):
+        """Row indices of the next n minibatches of this rank (host side of ReshufflingBatchSubsampling)."""
+        idx = np.ascontiguousarray(np.stack([self.batches[(self._bpos + k) % len(self.batches)] for k in range(n)]), dtype=np.int32)
+        self._bpos += n
+        return idx
+
+    def run_steps(self, n, vals, elbos, idx=None):
         import ctypes as C
         L, nd = self.L, C.c_int32()
         if self.subsampled:
-            idx = np.ascontiguousarray(np.stack([self.batches[(self._bpos + k) % len(self.batches)] for k in range(n)]), dtype=np.int32)
-            self._bpos += n
+            if idx is None:
+                idx = self.minibatches(n)
             L.check(L.lib.avi_opt_steps_subsampled(self.state.h, n, L.iptr(idx), idx.shape[1], L.fptr(vals), L.fptr(elbos),
                                                    C.byref(nd)), self.ctx.h)
         else:
@@ -323,8 +329,11 @@ def device_loop(b, K, W, torch, dist, ext, flush, barrier, sampler_index=None):
         # minibatch indices travel with the call: one blocking call of K steps between two events (X = 2 GB >> L2, the
         # gathered batch is produced inside the step: no flush needed)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        idx = b.minibatches(K)
+        if b.world > 1:
+            b.ctx.comm_barrier()
         e0.record(ext)
-        b.run_steps(K, vals, elbos)
+        b.run_steps(K, vals, elbos, idx)
         e1.record(ext)
         barrier()
         cold_ms = e0.elapsed_time(e1)
