@@ -354,7 +354,7 @@ int32_t steps_prepare(avi_opt* op, int32_t n, const int32_t* idx_host, int64_t b
             // (the captured iteration holds this pointer: room for calls of up to 1024 iterations, so that a longer call
             // after a short one does not pay for a re-capture)
             op->idx_cap = std::max<int64_t>(need, 1024 * batch);
-            AVI_CHECK(avi_alloc(ctx, &op->idx_dev, (size_t)need));
+            AVI_CHECK(avi_alloc(ctx, &op->idx_dev, (size_t)op->idx_cap));
             drop_graph(op);
         }
         AVI_CUDA(ctx, cudaMemcpyAsync(op->idx_dev, idx_host, need * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));

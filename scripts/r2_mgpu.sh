@@ -13,5 +13,5 @@ for l in sys.stdin:
 if [ -n "$EX" ]; then XF="--extras"; else XF="--no-extras"; fi
 timeout 900 $TR --master-port 29513 bench.py --gpus $N --steps 300 --warmup 30 $XF --shard rows 2> $O/mg${N}_bench_rows.err | tee $O/mg${N}_bench_rows.json | summ "N=$N shard=rows"
 tail -3 $O/mg${N}_bench_rows.err | cut -c1-300
-timeout 300 $TR --master-port 29514 bench.py --gpus $N --steps 300 --warmup 30 --no-extras --shard samples 2> $O/mg${N}_bench_samples.err | tee $O/mg${N}_bench_samples.json | summ "N=$N shard=samples"
+timeout 300 $TR --master-port 29514 bench.py --gpus $N --steps 200 --warmup 20 --no-extras --shard samples 2> $O/mg${N}_bench_samples.err | tee $O/mg${N}_bench_samples.json | summ "N=$N shard=samples"
 timeout 200 $TR --master-port 29516 bench.py --impl reference --gpus $N --steps 20 --warmup 5 2>/dev/null | cut -c1-260

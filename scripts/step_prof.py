@@ -14,6 +14,7 @@ from advancedvi_jl_b200.api import _OptState
 
 rows = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 12
+cold = len(sys.argv) > 3 and sys.argv[3] == "cold"      # flush L2 (256 MiB write + read) before the profiled launch
 rng = np.random.default_rng(1)
 X = rng.standard_normal((rows, 1024), dtype=np.float32) / 32.0
 y = (rng.random(rows) < 0.5).astype(np.float32)
@@ -22,7 +23,18 @@ D = 1025; q = avi.MeanFieldGaussian(np.zeros(D, np.float32), np.ones(D, np.float
 alg = avi.KLMinRepGradDescent(optimizer=avi.Adam(1e-3), n_samples=256, operator=avi.ClipScale())
 obj = avi.Objective(1, alg.objective, q, prob)
 st = _OptState(alg, obj, q)
-st.steps_begin(steps); st.steps_enqueue(steps); st.steps_end()
+if cold:
+    import torch
+    ext = torch.cuda.ExternalStream(ctx.stream(), device=0)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    st.steps_begin(steps)
+    for k in range(steps):
+        with torch.cuda.stream(ext):
+            flush.zero_(); flush.sum()
+        st.steps_enqueue(1)
+    st.steps_end()
+else:
+    st.steps_begin(steps); st.steps_enqueue(steps); st.steps_end()
 buf = np.zeros(160 * 32, np.uint64)
 fn = L.lib.avi_step_fused_prof_get
 fn.restype = C.c_int32
@@ -37,6 +49,7 @@ names = {0: "entry", 1: "prologue done", 2: "past dependency wait", 3: "snapshot
          18: "bwd: slab rows stored", 19: "bwd: unit complete (+combine)", 20: "arrive barrier 2", 21: "past barrier 2",
          24: "tail: inputs loaded, scalars reduced", 25: "tail: value + gradient of the slice", 26: "tail: update stored",
          22: "tail done (next samples drawn)", 23: "exit"}
+print(f"# {'COLD (L2 flushed before the launch)' if cold else 'warm'}")
 print(f"# rows {rows}, grid {grid}: ns since the first CTA's entry (min / mean / max over CTAs that stamped)")
 for k in sorted(names):
     v = h[:, k][h[:, k] > 0] - t0
