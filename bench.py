@@ -355,14 +355,15 @@ def device_loop(b, K, W, torch, dist, ext, flush, barrier, sampler_index=None):
         _, cold_elbos, n_cold = b.state.steps_end()
         assert n_cold == K, f"{b.name}: objective diverged"
         barrier()
-        launches = b.ctx.launch_count() - l0
         cold_ms = sum(x.elapsed_time(z) for x, z in ev)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(ext)
+        l0 = b.ctx.launch_count()               # counted over the back-to-back region: the flushed one launches the same
+        e0.record(ext)                          # kernels per step plus, with several ranks, the untimed alignment barrier
         b.run_steps(K, vals, elbos)
         e1.record(ext)
         barrier()
+        launches = b.ctx.launch_count() - l0
         warm_ms = e0.elapsed_time(e1)
     clocks = None
     if sampler:
