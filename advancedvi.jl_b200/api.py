@@ -35,7 +35,7 @@ __all__ = [
     "Descent", "Adam", "DoG", "DoWG", "IdentityOperator", "ClipScale", "ProximalLocationScaleEntropy",
     "NoAveraging", "PolynomialAveraging",
     "KLMinRepGradDescent", "KLMinRepGradProxDescent", "KLMinScoreGradDescent", "ADVI", "BBVI",
-    "optimize", "estimate_objective", "Objective", "AviError", "HostUpdate", "central_fd_gradient",
+    "optimize", "estimate_objective", "Objective", "AviError", "HostUpdate", "HostStep", "central_fd_gradient",
     "gaussian_expectation_gradient_and_hessian",
 ]
 
@@ -750,6 +750,47 @@ class HostUpdate:
         if rc != 0:
             raise AviError(rc, "avi_host_update: unsupported rule / operator or missing state arrays")
         return self.lam
+
+
+class HostStep:
+    """`step` (src/algorithms/common.jl:75-104) with the parameters in HOST memory: every call is one estimate_gradient!
+    through the zero-copy boundary (host lambda in, host gradient out) followed by Optimisers.update! + operator + averager
+    on the host (avi_hoststep_step).  The arrays `lam`, `grad`, `lam_avg` are owned here and bound to the handle once, so a
+    call crosses the FFI with two pointers.  Same arithmetic as Objective.estimate_gradient + HostUpdate.update."""
+
+    def __init__(self, obj: "Objective", optimizer, operator, averager, lambda0, scale_offset: int):
+        self.obj = obj
+        self.lam = np.ascontiguousarray(lambda0, np.float32).copy()
+        self.grad = np.zeros_like(self.lam)
+        self.lam_avg = self.lam.copy()
+        hyper = np.asarray(optimizer.hyper, np.float32)
+        h = L.vp()
+        L.check(L.lib.avi_hoststep_create(obj.h, optimizer.code, L.fptr(hyper), len(hyper), operator.code,
+                                          float(getattr(operator, "param", 0.0)), averager.code,
+                                          float(getattr(averager, "param", 0.0)), int(scale_offset), L.fptr(self.lam),
+                                          L.fptr(self.grad), L.fptr(self.lam_avg), C.byref(h)), obj.ctx.h)
+        self.h = h
+        self._v, self._e = C.c_float(), C.c_float()
+        self._pv, self._pe = C.byref(self._v), C.byref(self._e)
+        self._fn = L.lib.avi_hoststep_step
+
+    def step(self):
+        """-> (value, elbo); `lam`, `grad`, `lam_avg` are updated in place."""
+        rc = self._fn(self.h, self._pv, self._pe)
+        if rc:
+            L.check(rc, self.obj.ctx.h)
+        return self._v.value, self._e.value
+
+    def timing(self):
+        """wall-clock microseconds of the last call's two halves: (estimate_gradient!, host update)"""
+        a, b = C.c_double(), C.c_double()
+        L.lib.avi_hoststep_timing(self.h, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def close(self):
+        if self.h:
+            L.lib.avi_hoststep_destroy(self.h)
+            self.h = None
 
 
 class _OptState:

@@ -458,12 +458,16 @@ int32_t avi_obj_estimate_gradient(avi_obj* o, const float* lambda_host, int64_t 
     const bool zero_copy = zc_env && o->family == AVI_MEANFIELD && P <= (1 << 16);
     auto enqueue = [&]() -> int32_t {
         if (zero_copy) {
+            StepTail ft{};
+            ft.mode = STEP_TAIL_GRAD_OUT;
+            ft.lam = o->d_lambda; ft.host_out = o->h_grad;
+            bool taken = false;
+            // ONE launch: lambda read from the pinned buffer slice by slice, sample -> contractions -> gradient + completion
+            // flag written to pinned host memory (step_fused.cu)
+            AVI_CHECK(avi_objective_fused(o, o->d_lambda, ft, &taken, false, o->h_lambda));
+            if (taken) { o->step += 1; return AVI_OK; }
             AVI_CHECK(avi_obj_stage_lambda(o));
-            {   // sample -> contractions -> gradient + completion flag in pinned host memory: one launch (step_fused.cu)
-                StepTail ft{};
-                ft.mode = STEP_TAIL_GRAD_OUT;
-                ft.lam = o->d_lambda; ft.host_out = o->h_grad;
-                bool taken = false;
+            {   // targets / modes that need all of lambda on the device first: stage-in kernel + the one launch
                 AVI_CHECK(avi_objective_fused(o, o->d_lambda, ft, &taken));
                 if (taken) { o->step += 1; return AVI_OK; }
             }

@@ -195,6 +195,7 @@ struct avi_model {
     // The whole mean-field RepGradELBO iteration (sample -> log-density + gradient sums -> [exchange] -> finalize +
     // update) as ONE kernel launch (step_fused.cuh).  Optional.
     virtual bool fused_step_ok(int Mloc) const { return false; }
+    virtual bool fused_host_lambda_ok() const { return false; }   // fused_step can take lambda from mapped pinned host memory
     virtual int32_t set_fused_step(int mode) { return AVI_ERR_UNSUPPORTED; }
     virtual int32_t fused_step(const FusedStepArgs& a) { return AVI_ERR_UNSUPPORTED; }
 };
@@ -319,7 +320,9 @@ int32_t avi_objective_local(avi_obj* o, const float* lambda);          // sample
 // mode and the optimiser / host-output pointers, the rest is filled here.  *taken = false: nothing was enqueued, use
 // the multi-kernel path.
 struct StepTail;
-int32_t avi_objective_fused(avi_obj* o, const float* lambda, const StepTail& tail, bool* taken, bool dry_run = false);
+// lambda_src != nullptr: lambda has not been staged to the device; the kernel reads it from this mapped pinned host buffer
+int32_t avi_objective_fused(avi_obj* o, const float* lambda, const StepTail& tail, bool* taken, bool dry_run = false,
+                            const float* lambda_src = nullptr);
 // acc -> grad (skip_fr_matrix: leave the D x D block of a full-rank gradient to the caller's fused update)
 int32_t avi_objective_finalize(avi_obj* o, const float* lambda, float* grad, float* out, bool skip_fr_matrix = false,
                                bool fuse_advance = false);

@@ -546,11 +546,12 @@ int32_t avi_objective_local(avi_obj* o, const float* lambda) {
     return AVI_OK;
 }
 
-int32_t avi_objective_fused(avi_obj* o, const float* lambda, const StepTail& tail, bool* taken, bool dry_run) {
+int32_t avi_objective_fused(avi_obj* o, const float* lambda, const StepTail& tail, bool* taken, bool dry_run, const float* lambda_src) {
     avi_ctx* ctx = o->ctx;
     *taken = false;
     if (o->family != AVI_MEANFIELD || o->objective != AVI_REPGRAD || o->Mloc <= 0) return AVI_OK;
     if (!o->model->fused_step_ok(o->Mloc)) return AVI_OK;
+    if (lambda_src && !o->model->fused_host_lambda_ok()) return AVI_OK;
     StepTail t = tail;
     t.acc = o->acc; t.accv = o->accv; t.M = o->M; t.objective = o->objective; t.entropy = o->entropy;
     t.logp = o->logp; t.grad = o->grad; t.out = o->out; t.acc_len = o->acc_len;
@@ -565,6 +566,7 @@ int32_t avi_objective_fused(avi_obj* o, const float* lambda, const StepTail& tai
     if (ceil_div(o->D, ctx->prop.multiProcessorCount) > avi_step_fused_max_per_cta()) return AVI_OK;
     FusedStepArgs fa{};
     fa.dry_run = dry_run;
+    fa.lambda_src = lambda_src;
     fa.lambda = lambda; fa.D = o->D; fa.ld = o->ld; fa.m0 = o->m0; fa.Mloc = o->Mloc; fa.st = o->d_state;
     fa.Z = o->Z; fa.E = o->E; fa.esq = o->esq; fa.logp = o->logp; fa.t = t;
     AVI_CHECK(o->model->fused_step(fa));

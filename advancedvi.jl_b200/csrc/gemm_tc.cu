@@ -394,6 +394,27 @@ int32_t avi_tc_make_tmap(avi_ctx* ctx, CUtensorMap* map, const float* base, int6
     return AVI_OK;
 }
 
+// MN-major TF32 operand stored [k_rows][ld] with the MN index contiguous (mn_cols of them, a multiple of 32), as ONE box
+// per tile: a 3-D view {32 MN elements | k rows | groups of 32 MN elements} whose box {32, 32, groups} lands in shared
+// memory as `groups` consecutive 4 KB blocks -- exactly the layout smem_desc_mn_sw128(.., 4096) describes.  (Separate
+// 2-D boxes per group work too, but every TMA request costs the producer ~18 cycles of the SM's ingest time.)
+int32_t avi_tc_make_tmap_mn3(avi_ctx* ctx, CUtensorMap* map, const float* base, int64_t k_rows, int64_t mn_cols, int64_t ld,
+                             int groups) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) AVI_FAIL(ctx, AVI_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld % 4) || (mn_cols % 32) || mn_cols > ld || groups < 1 || groups > 8 || k_rows < 1)
+        AVI_FAIL(ctx, AVI_ERR_INVALID, "tensor map (MN-major): misaligned operand");
+    cuuint64_t gdim[3] = {32, (cuuint64_t)k_rows, (cuuint64_t)(mn_cols / 32)};
+    cuuint64_t gstr[2] = {(cuuint64_t)ld * sizeof(float), 128};
+    cuuint32_t box[3] = {32, (cuuint32_t)BK, (cuuint32_t)groups};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) AVI_FAIL(ctx, AVI_ERR_CUDA, "cuTensorMapEncodeTiled (MN-major 3-D) failed: " + std::to_string((int)r));
+    return AVI_OK;
+}
+
 static int smem_bytes_for(int nt, int* stages_out, bool pair = false, bool fwd = false) {
     const int stage_bytes = A_TILE_BYTES + (pair ? nt / 2 : nt) * BK * 4;
     const int extra = 1024 + (int)sizeof(SmemCtl);

@@ -22,7 +22,12 @@ struct TcParams {
     // contraction then takes X from the SAME row-major copy the forward contraction uses (X is read once per iteration).
     // The A tensor map has box {32 a-elements, 32 k-rows} and the 32-byte-atom swizzle; a 128 x 32 tile is four boxes.  3xTF32: the k range consists
     // of three segments of a_seg_kb blocks [hi | hi | lo]; the lo part of the source sits a_seg_off elements further.
-    int a_mn, a_seg_kb, a_seg_off;
+    int a_mn, a_seg_kb, a_seg_off;   // a_mn / b_mn = 2: one 3-D box per tile (avi_tc_make_tmap_mn3) instead of one 2-D box per group
+    // fused iteration kernel only: the forward epilogue stores R TRANSPOSED, Rt [data row][sample] (c_mn = 1, ldc = row pitch
+    // of Rt), so that the 32 lanes of a warp -- 32 consecutive samples -- write 128 contiguous bytes per data row (the
+    // sample-major layout made every warp store touch 32 different rows: 2.4 us of the forward epilogue); the backward
+    // contraction then reads it as an MN-major B operand (b_mn = 1): boxes of {32 samples, 32 data rows}, 4 KB apart.
+    int c_mn, b_mn;
     const void* pf_ptr;  // static operand of the NEXT kernel, pulled into L2 by the idle warp 3 while this one computes
     unsigned long long pf_bytes;
     unsigned pf_pace_ns;
@@ -58,6 +63,9 @@ struct TcParams {
 // atom32 = 1: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B (MN-major TF32 operand, tc_common.cuh) instead of the 128-byte swizzle
 int32_t avi_tc_make_tmap(avi_ctx* ctx, CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld,
                          int box_rows, int atom32 = 0);
+// MN-major operand [k_rows][ld] (MN index contiguous, mn_cols % 32 == 0) as one 3-D box {32, 32 k rows, groups} per tile
+int32_t avi_tc_make_tmap_mn3(avi_ctx* ctx, CUtensorMap* map, const float* base, int64_t k_rows, int64_t mn_cols, int64_t ld,
+                             int groups);
 // fills Ma, Nb, n_ablk, n_kblk, nt, n_bchunk, n_ksplit, kb_per_split, ca, cb.  force_cluster: 0 = never cluster
 // allow_pair = 0: single-CTA tiles only (the fused iteration kernel)
 int32_t avi_tc_plan(avi_ctx* ctx, int64_t Ma, int64_t Nb, int64_t K, bool split_k, int force_cluster, TcParams* p,

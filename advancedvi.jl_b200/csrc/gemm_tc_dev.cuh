@@ -27,6 +27,7 @@ struct SmemCtl {
     uint32_t tmem_base;
     int flag;
     float scratch[8];               // fused iteration kernel: values handed from one phase to a later one
+    unsigned long long snap[32];    // fused iteration kernel: entry snapshot of the device state (one warp loads, all read)
     float red16[2][16];             // fused iteration kernel: per-warp partials of a unit's log-likelihood total
     float tail[1024 + 512];         // fused iteration kernel, tail phase: slab staging + per-coordinate sums
     alignas(16) float ys[2][512];   // FWD: y per accumulator stage (<= 256 used); BWD: reduction scratch
@@ -169,7 +170,8 @@ __device__ __forceinline__ void epilogue_unit(const TcParams& p_, SmemCtl* ctl, 
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     float lp, rr;
-                    if (LIK == 0) {
+                    if (p.dbg & 32) { lp = v[j]; rr = yv[j] - v[j]; }   // (dbg 32: timing experiment without the logistic terms)
+                    else if (LIK == 0) {
                         const float l = v[j];
                         const float e = tc::ex2_approx(-1.4426950408889634f * fabsf(l));   // exp(-|l|) in (0, 1]
                         const float inv = tc::rcp_approx(1.0f + e);                         // in [1/2, 1)
@@ -204,7 +206,25 @@ __device__ __forceinline__ void epilogue_unit(const TcParams& p_, SmemCtl* ctl, 
                 }
                 // (staging this tile through shared memory for 128-byte row stores was measured slower: the
                 // extra STS + barrier cost more than the 32-byte-sector stores; profiles/README.md)
-                if (a_ok && b0 < (r_seg ? r_seg : p.ldc)) {
+                if (p.c_mn) {
+                    // transposed store Rt[b][a]: one coalesced 128-byte row segment per warp and data row.  Rows past Nb:
+                    // never read in the plain mode (the tensor map ends at Nb: zero fill), zeros up to the end of the
+                    // segment in the 3xTF32 mode.
+                    if (a_ok && !(p.dbg & 16)) {
+                        float* dst = p.C + (size_t)b0 * p.ldc + a;
+                        const int lim = r_seg ? r_seg : p.Nb;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            if (full || b0 + j < lim) {
+                                dst[(size_t)j * p.ldc] = r[j];
+                                if (r_seg) {
+                                    dst[(size_t)(r_seg + j) * p.ldc] = rlo[j];
+                                    dst[(size_t)(2 * r_seg + j) * p.ldc] = r[j];
+                                }
+                            }
+                        }
+                    }
+                } else if (a_ok && b0 < (r_seg ? r_seg : p.ldc) && !(p.dbg & 16)) {   // (dbg 16: timing experiment without the R stores)
                     float4* dst = reinterpret_cast<float4*>(p.C + (size_t)a * p.ldc + b0);
                     dst[0] = make_float4(r[0], r[1], r[2], r[3]);
                     dst[1] = make_float4(r[4], r[5], r[6], r[7]);

@@ -268,6 +268,7 @@ struct Glm : avi_model {
     // work buffers
     int capM = 0, cap_ld = 0; long long cap_n = 0;
     long long ldR = 0;
+    float* ldpart = nullptr;          // step_fused.cu: per-CTA partials of log det(scale) (host-resident lambda)
     float *R = nullptr, *Zt = nullptr, *llpart = nullptr, *a1p = nullptr, *slabs = nullptr, *spart = nullptr;
     float4* pre = nullptr;
     long long llpart_cap = 0, ap_cap = 0, slab_cap = 0;
@@ -275,7 +276,7 @@ struct Glm : avi_model {
     ~Glm() override {
         avi_free(Xr_full); avi_free(Xc_full); avi_free(y_full); avi_free(Xr_b); avi_free(Xc_b); avi_free(y_b);
         avi_free(idx_own); avi_free(R); avi_free(Zt); avi_free(llpart); avi_free(a1p); avi_free(spart);
-        avi_free(slabs); avi_free(pre); avi_free(tickets); avi_free(gbar);
+        avi_free(slabs); avi_free(pre); avi_free(tickets); avi_free(gbar); avi_free(ldpart);
     }
     bool hooked = false;               // the sampling kernel produced Zt / pre for exactly (hooked_Z, hooked_M)
     const float* hooked_Z = nullptr; int hooked_M = 0;
@@ -321,7 +322,7 @@ struct Glm : avi_model {
         capM = std::max(M, capM); cap_ld = ld; cap_n = std::max(cap_n, n_act);
         ldR = (x3 ? 3 : 1) * round_up(cap_n, 32);
         zt_ld = x3 ? 3 * segd : ld;
-        AVI_CHECK(avi_alloc(ctx, &R, (size_t)capM * ldR));
+        AVI_CHECK(avi_alloc(ctx, &R, (size_t)round_up(capM, 32) * ldR));   // [M][ldR], or transposed [ldR][round_up(M, 4)] (fused_step)
         AVI_CHECK(avi_alloc(ctx, &Zt, (size_t)capM * zt_ld));
         AVI_CHECK(avi_alloc(ctx, &spart, (size_t)capM * (2 * (size_t)ctx->prop.multiProcessorCount + 1)));   // step_fused.cu: draw_slice
         AVI_CHECK(avi_alloc(ctx, &pre, (size_t)capM));
@@ -463,6 +464,11 @@ struct Glm : avi_model {
         const double flops = 4.0 * (double)n_act * d * Mloc * (x3 ? 3.0 : 1.0);
         return fused_mode >= 2 || flops <= 2e11;
     }
+    bool fused_host_lambda_ok() const override {
+        static const bool ahead = !(getenv("AVI_DRAW_AHEAD") && atoi(getenv("AVI_DRAW_AHEAD")) == 0);
+        static const bool host_lam = !(getenv("AVI_HOST_LAMBDA") && atoi(getenv("AVI_HOST_LAMBDA")) == 0);
+        return ahead && host_lam && !x3;
+    }
     int32_t fused_step(const FusedStepArgs& fa) override {
         const int M = fa.Mloc, ld = fa.ld;
         AVI_CHECK(ensure(M, ld));
@@ -496,11 +502,33 @@ struct Glm : avi_model {
         static const bool a_mn = !(getenv("AVI_TC_AMN") && atoi(getenv("AVI_TC_AMN")) == 0);
         if (a_mn) {
             sp.b.a_mn = 1; sp.b.a_seg_kb = x3 ? (int)(segn / 32) : 0; sp.b.a_seg_off = x3 ? segd : 0;
-            AVI_CHECK(avi_tc_make_tmap(ctx, &tmXc, Xr, n_act, x3 ? 3LL * segd : d, dK, 32, /*atom32=*/1));
+            static const bool one_box = !(getenv("AVI_TC_MN3") && atoi(getenv("AVI_TC_MN3")) == 0);
+            if (one_box && dK % 32 == 0) {   // one 3-D box per tile
+                sp.b.a_mn = 2;
+                AVI_CHECK(avi_tc_make_tmap_mn3(ctx, &tmXc, Xr, n_act, dK, dK, 4));
+            } else {
+                AVI_CHECK(avi_tc_make_tmap(ctx, &tmXc, Xr, n_act, x3 ? 3LL * segd : d, dK, 32, /*atom32=*/1));
+            }
         } else {
             AVI_CHECK(avi_tc_make_tmap(ctx, &tmXc, Xc, d, kb(), nP, 128));
         }
-        AVI_CHECK(avi_tc_make_tmap(ctx, &tmR, R, M, kb(), ldR, sp.b.nt));
+        // R between the phases: transposed (data row major) by default, so that the forward epilogue's stores coalesce; the
+        // backward contraction reads it as an MN-major B operand (AVI_TC_BMN=0: sample-major R, K-major operand)
+        static const bool b_mn = !(getenv("AVI_TC_BMN") && atoi(getenv("AVI_TC_BMN")) == 0);
+        if (b_mn) {
+            const long long ldRt = round_up(capM, 32);
+            sp.f.c_mn = 1; sp.f.ldc = (int)ldRt;
+            static const bool one_box = !(getenv("AVI_TC_MN3") && atoi(getenv("AVI_TC_MN3")) == 0);
+            if (one_box && (sp.b.n_bchunk == 1 || sp.b.nt % 32 == 0)) {
+                sp.b.b_mn = 2;
+                AVI_CHECK(avi_tc_make_tmap_mn3(ctx, &tmR, R, kb(), round_up(M, 32), ldRt, (sp.b.nt + 31) / 32));
+            } else {
+                sp.b.b_mn = 1;
+                AVI_CHECK(avi_tc_make_tmap(ctx, &tmR, R, kb(), M, ldRt, 32, /*atom32=*/1));
+            }
+        } else {
+            AVI_CHECK(avi_tc_make_tmap(ctx, &tmR, R, M, kb(), ldR, sp.b.nt));
+        }
         sp.do_sample = 1;
         sp.lambda = fa.lambda; sp.D = fa.D; sp.ld = ld; sp.m0 = fa.m0; sp.Mloc = M; sp.st = fa.st;
         sp.Z = fa.Z; sp.E = fa.E; sp.esq = fa.esq;
@@ -509,7 +537,16 @@ struct Glm : avi_model {
         // draw the next iteration's samples in the tail phase (AVI_DRAW_AHEAD=0: sample phase at the start of every launch)
         static const bool ahead = !(getenv("AVI_DRAW_AHEAD") && atoi(getenv("AVI_DRAW_AHEAD")) == 0);
         sp.draw_ahead = (ahead && fa.t.mode == STEP_TAIL_UPDATE && !x3) ? 1 : 0;
+        // estimate_gradient! boundary with lambda still in pinned host memory: slice-major sampling at the start of the launch
+        // (the tail of this mode never draws ahead), every CTA fetching its own slice from the host
+        if (fa.lambda_src) {
+            if (x3 || fa.t.mode != STEP_TAIL_GRAD_OUT || !ahead) AVI_FAIL(ctx, AVI_ERR_STATE, "fused_step: host-resident lambda needs the slice-major sampler");
+            if (!ldpart) AVI_CHECK(avi_alloc(ctx, &ldpart, 256));
+            sp.draw_ahead = 1; sp.lambda_src = fa.lambda_src; sp.ldpart = ldpart;
+        }
         sp.spart = spart; sp.spart_stride = ctx->prop.multiProcessorCount;
+        static const int tc_dbg = getenv("AVI_TC_DBG") ? atoi(getenv("AVI_TC_DBG")) : 0;   // timing experiments (gemm_tc.cuh)
+        sp.f.dbg = tc_dbg; sp.b.dbg = tc_dbg;
         sp.t = fa.t;
         sp.t.unit_ll = llpart; sp.t.n_units_f = (int)units_f; sp.t.w_lik = w;
         sp.t.part1 = sp.b.part1; sp.t.part2 = sp.b.part2; sp.t.nslab = nslab; sp.t.ldslab = ldslab;

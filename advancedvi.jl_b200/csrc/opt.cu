@@ -632,6 +632,74 @@ int32_t avi_host_update(int32_t rule, const float* hyper, int32_t n_hyper, int32
     return AVI_OK;
 }
 
+// ---- `step` for callers whose parameters live in HOST memory (common.jl:75-104): estimate_gradient! through the
+// zero-copy boundary + Optimisers.update! + operator + averager on the host, one call per iteration.  The handle binds the
+// caller-owned arrays once, so the per-iteration call carries two pointers instead of fifteen arguments.
+struct avi_hoststep {
+    avi_obj* obj;
+    int32_t rule, op_kind, averager, n_hyper;
+    float hyper[4], op_param, avg_param;
+    int64_t P, scale_offset;
+    float *lambda, *grad, *lambda_avg;     // caller-owned, P entries each (lambda_avg may be null without averaging)
+    std::vector<float> m1, m2;
+    float st[SC_N];
+    double last_estimate_us, last_update_us;
+};
+
+int32_t avi_hoststep_create(avi_obj* obj, int32_t rule, const float* hyper, int32_t n_hyper, int32_t op_kind, float op_param,
+                            int32_t averager, float avg_param, int64_t scale_offset, float* lambda, float* grad,
+                            float* lambda_avg, avi_hoststep** out) {
+    if (!obj || !out) return AVI_ERR_INVALID;
+    avi_ctx* ctx = obj->ctx;
+    *out = nullptr;
+    if (!lambda || !grad) AVI_FAIL(ctx, AVI_ERR_INVALID, "hoststep: lambda and grad buffers are required");
+    if (rule != AVI_RULE_DESCENT && rule != AVI_RULE_ADAM) AVI_FAIL(ctx, AVI_ERR_UNSUPPORTED, "hoststep: Descent and Adam only");
+    if (op_kind != AVI_OP_IDENTITY && op_kind != AVI_OP_CLIPSCALE) AVI_FAIL(ctx, AVI_ERR_UNSUPPORTED, "hoststep: IdentityOperator and ClipScale only");
+    if (averager != AVI_AVG_NONE && averager != AVI_AVG_POLYNOMIAL) AVI_FAIL(ctx, AVI_ERR_INVALID, "averager");
+    if (averager == AVI_AVG_POLYNOMIAL && !lambda_avg) AVI_FAIL(ctx, AVI_ERR_INVALID, "hoststep: PolynomialAveraging needs lambda_avg");
+    if (n_hyper < 0 || n_hyper > 4) AVI_FAIL(ctx, AVI_ERR_INVALID, "hoststep: at most 4 hyperparameters");
+    avi_hoststep* hs = new avi_hoststep();
+    hs->obj = obj; hs->rule = rule; hs->op_kind = op_kind; hs->averager = averager; hs->n_hyper = n_hyper;
+    for (int i = 0; i < 4; ++i) hs->hyper[i] = (hyper && i < n_hyper) ? hyper[i] : 0.0f;
+    hs->op_param = op_param; hs->avg_param = avg_param; hs->P = obj->P; hs->scale_offset = scale_offset;
+    hs->lambda = lambda; hs->grad = grad; hs->lambda_avg = lambda_avg;
+    hs->m1.assign((size_t)obj->P, 0.0f); hs->m2.assign((size_t)obj->P, 0.0f);
+    for (int i = 0; i < SC_N; ++i) hs->st[i] = 0.0f;
+    hs->last_estimate_us = hs->last_update_us = 0.0;
+    *out = hs;
+    return AVI_OK;
+}
+
+int32_t avi_hoststep_step(avi_hoststep* hs, float* value, float* elbo) {
+    if (!hs) return AVI_ERR_INVALID;
+    const auto t0 = std::chrono::steady_clock::now();
+    float v = 0.0f, e = 0.0f;
+    int32_t rc = avi_obj_estimate_gradient(hs->obj, hs->lambda, hs->P, hs->grad, &v, &e);
+    if (rc != AVI_OK) return rc;
+    const auto t1 = std::chrono::steady_clock::now();
+    if (value) *value = v;
+    if (elbo) *elbo = e;
+    if (!std::isfinite(v)) return AVI_OK;   // the caller raises (common.jl:83-89); parameters stay untouched
+    rc = avi_host_update(hs->rule, hs->hyper, hs->n_hyper, hs->op_kind, hs->op_param, hs->averager, hs->avg_param, hs->P,
+                         hs->scale_offset, hs->lambda, hs->grad, hs->m1.data(), hs->m2.data(), hs->lambda_avg, hs->st);
+    const auto t2 = std::chrono::steady_clock::now();
+    hs->last_estimate_us = std::chrono::duration<double, std::micro>(t1 - t0).count();
+    hs->last_update_us = std::chrono::duration<double, std::micro>(t2 - t1).count();
+    return rc;
+}
+
+int32_t avi_hoststep_timing(const avi_hoststep* hs, double* estimate_us, double* update_us) {
+    if (!hs) return AVI_ERR_INVALID;
+    if (estimate_us) *estimate_us = hs->last_estimate_us;
+    if (update_us) *update_us = hs->last_update_us;
+    return AVI_OK;
+}
+
+int32_t avi_hoststep_destroy(avi_hoststep* hs) {
+    delete hs;
+    return AVI_OK;
+}
+
 int32_t avi_opt_get(avi_opt* op, float* lambda_host, float* lambda_avg_host, float* grad_host) {
     if (!op) return AVI_ERR_INVALID;
     avi_ctx* ctx = op->ctx;

@@ -105,9 +105,20 @@ __device__ __forceinline__ void load_a_tile(uint8_t* sa, const CUtensorMap* tmA,
     if (!p.a_mn) { tc::tma_load_2d(sa, tmA, bar, kb * BK, ab * BM); return; }
     const int seg = p.a_seg_kb ? kb / p.a_seg_kb : 0, rb = p.a_seg_kb ? kb - seg * p.a_seg_kb : kb;
     const int a0 = ab * BM + (seg == 2 ? p.a_seg_off : 0);
+    if (p.a_mn == 2) { tc::tma_load_3d(sa, tmA, bar, 0, rb * BK, a0 >> 5); return; }
 #pragma unroll
     for (int fb = 0; fb < BM / 32; ++fb) tc::tma_load_2d(sa + fb * 4096, tmA, bar, a0 + fb * 32, rb * BK);
 }
+
+// B tile (NT b-rows x 32 k) of k-block kb into `sb`.  K-major: one box.  MN-major (TcParams.b_mn): ceil(NT / 32) boxes of
+// {32 b-elements, 32 k-rows}, 4 KB apart.
+__device__ __forceinline__ void load_b_tile(uint8_t* sb, const CUtensorMap* tmB, uint64_t* bar, const TcParams& p, int kb, int bc) {
+    if (!p.b_mn) { tc::tma_load_2d(sb, tmB, bar, kb * BK, bc * p.nt); return; }
+    if (p.b_mn == 2) { tc::tma_load_3d(sb, tmB, bar, 0, kb * BK, (bc * p.nt) >> 5); return; }
+    const int nb = (p.nt + 31) >> 5;
+    for (int j = 0; j < nb; ++j) tc::tma_load_2d(sb + j * 4096, tmB, bar, bc * p.nt + j * 32, kb * BK);
+}
+__device__ __forceinline__ int b_tile_bytes(const TcParams& p) { return p.b_mn ? ((p.nt + 31) >> 5) * 4096 : p.nt * BK * 4; }
 
 // The operand that does not depend on the previous phase (X; early_op 1 = A, 2 = B) of this CTA's first unit is
 // requested before the phase's dependency is satisfied: expect_tx without arrive; the producer adds the dependent
@@ -116,7 +127,7 @@ __device__ __forceinline__ int preissue_early(const CUtensorMap* tmA, const CUte
                                               SmemCtl* ctl, uint8_t* tiles, int stages, int early_op) {
     const int units = p.n_ablk * p.n_bchunk * p.n_ksplit;
     if ((int)blockIdx.x >= units) return 0;
-    const int NT = p.nt, stage_bytes = A_TILE_BYTES + NT * BK * 4;
+    const int b_bytes = b_tile_bytes(p), stage_bytes = A_TILE_BYTES + b_bytes;
     const int u = blockIdx.x;
     FUNIT_COORDS(u);
     const int kb0 = ks * p.kb_per_split, kb1 = min(p.n_kblk, kb0 + p.kb_per_split);
@@ -127,8 +138,8 @@ __device__ __forceinline__ int preissue_early(const CUtensorMap* tmA, const CUte
             tc::mbar_expect_tx(&ctl->full[n], (uint32_t)A_TILE_BYTES);
             load_a_tile(sa, tmA, &ctl->full[n], p, kb, ab);
         } else {
-            tc::mbar_expect_tx(&ctl->full[n], (uint32_t)(NT * BK * 4));
-            tc::tma_load_2d(sa + A_TILE_BYTES, tmB, &ctl->full[n], kb * BK, bc * NT);
+            tc::mbar_expect_tx(&ctl->full[n], (uint32_t)b_bytes);
+            load_b_tile(sa + A_TILE_BYTES, tmB, &ctl->full[n], p, kb, bc);
         }
     }
     return n;
@@ -142,7 +153,7 @@ __device__ __forceinline__ void tc_phase(const CUtensorMap* tmA, const CUtensorM
                                          unsigned long long* prof, int ps) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NT = p.nt;
-    const int stage_bytes = A_TILE_BYTES + NT * BK * 4;
+    const int b_bytes = b_tile_bytes(p), stage_bytes = A_TILE_BYTES + b_bytes;
     const int units = p.n_ablk * p.n_bchunk * p.n_ksplit;
     const int first = blockIdx.x, stride = gridDim.x;
     if (warp == 0) {
@@ -159,8 +170,8 @@ __device__ __forceinline__ void tc_phase(const CUtensorMap* tmA, const CUtensorM
                     uint8_t* sa = tiles + stage * stage_bytes;
                     if (kcount < pre_issued) {
                         if (early_op == 1) {
-                            tc::mbar_arrive_expect_tx(&ctl->full[stage], (uint32_t)(NT * BK * 4));
-                            tc::tma_load_2d(sa + A_TILE_BYTES, tmB, &ctl->full[stage], kb * BK, bc * NT);
+                            tc::mbar_arrive_expect_tx(&ctl->full[stage], (uint32_t)b_bytes);
+                            load_b_tile(sa + A_TILE_BYTES, tmB, &ctl->full[stage], p, kb, bc);
                         } else {
                             tc::mbar_arrive_expect_tx(&ctl->full[stage], (uint32_t)A_TILE_BYTES);
                             load_a_tile(sa, tmA, &ctl->full[stage], p, kb, ab);
@@ -168,7 +179,7 @@ __device__ __forceinline__ void tc_phase(const CUtensorMap* tmA, const CUtensorM
                     } else {
                         tc::mbar_arrive_expect_tx(&ctl->full[stage], (uint32_t)stage_bytes);
                         load_a_tile(sa, tmA, &ctl->full[stage], p, kb, ab);
-                        tc::tma_load_2d(sa + A_TILE_BYTES, tmB, &ctl->full[stage], kb * BK, bc * NT);
+                        load_b_tile(sa + A_TILE_BYTES, tmB, &ctl->full[stage], p, kb, bc);
                     }
                     if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
@@ -178,8 +189,9 @@ __device__ __forceinline__ void tc_phase(const CUtensorMap* tmA, const CUtensorM
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (tc::elect_one()) {
-            const uint32_t idesc = tc::idesc_tf32(BM, NT, p.a_mn);
+            const uint32_t idesc = tc::idesc_tf32(BM, NT, p.a_mn, p.b_mn);
             const uint64_t a_step = p.a_mn ? 64u : 2u;   // per K = 8 MMA, in 16-byte units: 8 k-rows of 128 B | 32 B along the row
+            const uint64_t b_step = p.b_mn ? 64u : 2u;
             int stage = 0; uint32_t phase = 0;
             int as = 0; uint32_t aphase = 0;
             for (int u = first; u < units; u += stride) {
@@ -194,10 +206,10 @@ __device__ __forceinline__ void tc_phase(const CUtensorMap* tmA, const CUtensorM
                     if (kb == kb0 && u == first) PSTAMP(prof, ps + 1);   // first operands landed
                     const uint32_t sa = tc::smem_u32(tiles + stage * stage_bytes);
                     const uint64_t da = p.a_mn ? tc::smem_desc_mn_sw128(sa, 4096u) : tc::smem_desc_k_sw128(sa);
-                    const uint64_t db = tc::smem_desc_k_sw128(sa + A_TILE_BYTES);
+                    const uint64_t db = p.b_mn ? tc::smem_desc_mn_sw128(sa + A_TILE_BYTES, 4096u) : tc::smem_desc_k_sw128(sa + A_TILE_BYTES);
 #pragma unroll
                     for (int k = 0; k < BK / 8; ++k)
-                        tc::umma_tf32(tacc, da + a_step * (uint64_t)k, db + (uint64_t)(2 * k), idesc,
+                        tc::umma_tf32(tacc, da + a_step * (uint64_t)k, db + b_step * (uint64_t)k, idesc,
                                       (kb > kb0 || k > 0) ? 1u : 0u);
                     tc::umma_commit(&ctl->empty[stage]);
                     if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -327,6 +339,7 @@ __device__ __noinline__ void sample_phase(const StepParams& sp, SmemCtl* ctl, un
 
 // ---------------------------------------------------------------------------------------------------------
 // State read by every CTA at kernel entry (see the memory-model notes at the top).
+static_assert(sizeof(ObjDeviceState) == 64 && SC_ETA == 5, "the snapshot warp reads ObjDeviceState as 8 words and sc[0..5]");
 struct Snap {
     unsigned long long step, key;
     long long cursor;
@@ -727,23 +740,48 @@ k_glm_mf_step(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ C
         pre = __shfl_sync(0xffffffffu, pre, 0);
     }
 
-    // ---- snapshot of everything the end of this iteration overwrites
+    // ---- snapshot of everything the end of this iteration overwrites.  ONE warp per CTA fetches it (one lane per word,
+    // a single L2 round trip) and hands it over through shared memory: when every thread of every CTA read these few
+    // cache lines itself, 144 x 20 warps x ~15 loads queued on the same L2 lines for ~1.5 us.
+    if (warp == 3) {
+        unsigned long long v = 0ull;
+        const unsigned long long* st64 = reinterpret_cast<const unsigned long long*>(sp.st);
+        if (lane < 8) v = __ldcg(st64 + lane);                       // ObjDeviceState, 8 words (static_assert below)
+        else if (lane == 8) v = __ldcg(sp.gbar + 1);
+        else if (lane == 9) v = __ldcg(sp.gbar + 3);
+        else if (lane < 16) { if (sp.t.mode == STEP_TAIL_UPDATE) v = __float_as_uint(__ldcg(sp.t.sc + (lane - 10))); }
+        else if (lane == 16) { if (sp.t.mode != STEP_TAIL_NONE) v = __float_as_uint(__ldcg(sp.t.out + 3)); }
+        else if (lane == 17) { if (sp.t.mode != STEP_TAIL_NONE && sp.t.comm.nranks > 1) v = *reinterpret_cast<volatile unsigned int*>(&sp.t.comm.dev->seq); }
+        else if (lane >= 24 && sp.t.mode == STEP_TAIL_UPDATE) {
+            // cold-L2 runs: pull this CTA's slice of lambda and of the optimiser state towards L2 now; the tail phase
+            // would otherwise pay a DRAM round trip for them at the very end of the critical path
+            const int per = slice_per(sp.D), c0 = min(sp.D - 1, (int)blockIdx.x * per);
+            const float* base = lane < 26 ? sp.t.lam : lane < 28 ? sp.t.m1 : lane < 30 ? sp.t.m2 : sp.t.avg;
+            if (base) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)(lane & 1) * sp.D + c0));
+        }
+        ctl->snap[lane] = v;
+    }
+    __syncthreads();
     GridBar gb;
-    gb.ctr = sp.gbar; gb.base = __ldcg(sp.gbar + 1); gb.k = 0;
+    gb.ctr = sp.gbar; gb.base = ctl->snap[8]; gb.k = 0;
     Snap sn;
-    sn.step = sp.st->step; sn.key = sp.st->key; sn.cursor = sp.st->batch_cursor; sn.halted = sp.st->halted; sn.tp = sp.st->trace_pos;
+    sn.step = ctl->snap[0]; sn.key = ctl->snap[1]; sn.cursor = (long long)ctl->snap[2];
+    sn.halted = (int)(unsigned)ctl->snap[3]; sn.tp = (int)(ctl->snap[3] >> 32);
+    const int zt_kind = (int)(unsigned)ctl->snap[4], zt_mloc = (int)(unsigned)ctl->snap[5];
+    sn.zt_nparts = (int)(ctl->snap[4] >> 32);
     sn.b1t = sn.b2t = sn.t_avg = sn.v_old = sn.r_old = sn.shift = sn.logdet = 0.f; sn.seq = 0;
-    sn.zt_nparts = sp.st->zt_nparts;
     // (both tags: the objective's -- z, eps are its buffers -- and the target's -- Zt and the partial sums are shared by
     // every objective over that target)
-    sn.zt_ok = sp.draw_ahead && sp.st->zt_kind == 1 && sp.st->zt_step == sn.step && sp.st->zt_key == sn.key &&
-               sp.st->zt_mloc == sp.Mloc && __ldcg(sp.gbar + 3) == (unsigned long long)(uintptr_t)sp.st;
+    sn.zt_ok = sp.draw_ahead && zt_kind == 1 && ctl->snap[6] == sn.step && ctl->snap[7] == sn.key &&
+               zt_mloc == sp.Mloc && ctl->snap[9] == (unsigned long long)(uintptr_t)sp.st;
     if (sp.t.mode != STEP_TAIL_NONE) {
         if (sp.t.mode == STEP_TAIL_UPDATE) {
-            sn.b1t = sp.t.sc[SC_B1T]; sn.b2t = sp.t.sc[SC_B2T]; sn.t_avg = sp.t.sc[SC_T]; sn.v_old = sp.t.sc[SC_V]; sn.r_old = sp.t.sc[SC_R];
+            sn.t_avg = __uint_as_float((unsigned)ctl->snap[10 + SC_T]); sn.v_old = __uint_as_float((unsigned)ctl->snap[10 + SC_V]);
+            sn.r_old = __uint_as_float((unsigned)ctl->snap[10 + SC_R]); sn.b1t = __uint_as_float((unsigned)ctl->snap[10 + SC_B1T]);
+            sn.b2t = __uint_as_float((unsigned)ctl->snap[10 + SC_B2T]);
         }
-        sn.shift = sp.t.out[3];
-        if (sp.t.comm.nranks > 1) sn.seq = *reinterpret_cast<volatile unsigned int*>(&sp.t.comm.dev->seq) + 1u;
+        sn.shift = __uint_as_float((unsigned)ctl->snap[16]);
+        if (sp.t.comm.nranks > 1) sn.seq = (unsigned)ctl->snap[17] + 1u;
     }
 
     if (threadIdx.x == 0) PSTAMP(prof, 3);
@@ -752,12 +790,20 @@ k_glm_mf_step(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ C
         if (!sn.zt_ok) {
             float* lam2 = &ctl->tail[TAIL_STAGE + 2 * TAIL_MAX_PER_CTA];
             const int per = slice_per(sp.D), c0 = (int)blockIdx.x * per;
+            const float* src = sp.lambda_src ? sp.lambda_src : sp.lambda;
             for (int j = threadIdx.x; j < per; j += NUM_THREADS) {
                 const bool in = c0 + j < sp.D;
-                lam2[2 * j] = in ? sp.lambda[c0 + j] : 0.f;
-                lam2[2 * j + 1] = in ? sp.lambda[sp.D + c0 + j] : 0.f;
+                const float m_ = in ? src[c0 + j] : 0.f, s_ = in ? src[sp.D + c0 + j] : 0.f;
+                lam2[2 * j] = m_; lam2[2 * j + 1] = s_;
+                if (sp.lambda_src && in) { sp.t.lam[c0 + j] = m_; sp.t.lam[sp.D + c0 + j] = s_; }   // device copy for the tail
             }
             __syncthreads();
+            if (sp.lambda_src && warp == 2) {   // this slice's share of log det(scale)
+                float part = 0.f;
+                for (int j = lane; j < per; j += 32) if (c0 + j < sp.D) part += __logf(lam2[2 * j + 1]);
+                part = warp_sum(part);
+                if (lane == 0) sp.ldpart[blockIdx.x] = part;
+            }
             draw_slice(sp, lam2, sn.step, sn.key);
             sn.zt_nparts = (sp.D + per - 1) / per;
             stamp_max(sp.tl, 8);
@@ -778,7 +824,8 @@ k_glm_mf_step(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ C
     // forward contraction runs (lambda is not overwritten before the tail phase of this launch)
     if (warp == 2 && sp.t.mode != STEP_TAIL_NONE) {
         float part = 0.f;
-        for (int i = lane; i < sp.D; i += 32) part += __logf(sp.lambda[sp.D + i]);
+        if (sp.lambda_src) { for (int c = lane; c < (int)gridDim.x; c += 32) part += __ldcg(sp.ldpart + c); }   // (published by barrier 0)
+        else for (int i = lane; i < sp.D; i += 32) part += __logf(sp.lambda[sp.D + i]);
         part = warp_sum(part);
         if (lane == 0) ctl->scratch[0] = part;
     }
@@ -869,12 +916,10 @@ int32_t avi_step_fused_launch(avi_ctx* ctx, const CUtensorMap& tmZ, const CUtens
         attr_done = true;
     }
     const int extra = 16 + (int)sizeof(SmemCtl) + 1024;
-    auto stages_for = [&](int nt) {
-        const int stage_bytes = A_TILE_BYTES + nt * BK * 4;
-        return std::max(2, std::min(MAX_STAGES, (SMEM_LIMIT - extra) / stage_bytes));
-    };
-    sp.stages_f = stages_for(sp.f.nt); sp.stages_b = stages_for(sp.b.nt);
-    const int smem = extra + std::max(sp.stages_f * (A_TILE_BYTES + sp.f.nt * BK * 4), sp.stages_b * (A_TILE_BYTES + sp.b.nt * BK * 4));
+    auto stage_bytes_of = [&](const TcParams& p) { return A_TILE_BYTES + (p.b_mn ? ((p.nt + 31) / 32) * 4096 : p.nt * BK * 4); };
+    auto stages_for = [&](const TcParams& p) { return std::max(2, std::min(MAX_STAGES, (SMEM_LIMIT - extra) / stage_bytes_of(p))); };
+    sp.stages_f = stages_for(sp.f); sp.stages_b = stages_for(sp.b);
+    const int smem = extra + std::max(sp.stages_f * stage_bytes_of(sp.f), sp.stages_b * stage_bytes_of(sp.b));
     if (smem > SMEM_LIMIT) AVI_FAIL(ctx, AVI_ERR_INVALID, "tiles do not fit in shared memory");
     if (sp.f.pair || sp.b.pair || sp.f.ca * sp.f.cb != 1 || sp.b.ca * sp.b.cb != 1)
         AVI_FAIL(ctx, AVI_ERR_INVALID, "the fused iteration runs single-CTA tiles only");

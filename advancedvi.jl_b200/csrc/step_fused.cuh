@@ -55,6 +55,9 @@ struct StepParams {
     // slice-major sampling, one iteration ahead (optimiser loop, plain TF32 mode): the tail phase draws the next
     // iteration's samples; spart = [2][grid][Mloc] per-sample partial sums (|eps|^2, |beta|^2) + [Mloc] eta
     int draw_ahead; float* spart; int spart_stride;
+    // estimate_gradient! boundary: lambda arrives in MAPPED PINNED HOST memory; each CTA fetches only its own slice over
+    // PCIe (one round trip), keeps a device copy in t.lam and contributes a partial of log det(scale) to ldpart[grid]
+    const float* lambda_src; float* ldpart;
     StepTail t;
     unsigned long long* gbar;      // grid barrier: [0] monotonic arrival counter | [1] its value at the start of the launch;
                                    // [2] completion ticket (estimate_gradient! boundary) | [3] who drew the target's samples ahead
@@ -66,6 +69,7 @@ struct StepParams {
 struct FusedStepArgs {
     bool dry_run;                  // size every buffer the launch needs, launch nothing (before a graph capture)
     const float* lambda; int D, ld, m0, Mloc;
+    const float* lambda_src;       // != nullptr: lambda is still in mapped pinned host memory (see StepParams)
     ObjDeviceState* st;
     float *Z, *E, *esq, *logp;
     StepTail t;

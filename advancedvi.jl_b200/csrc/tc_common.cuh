@@ -98,6 +98,14 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uin
         : "memory");
 }
 
+// 3-D tile load (MN-major operands: {32 MN elements, k rows, groups of 32 MN elements})
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
 // multicast variant: the tile lands at the same CTA-relative offset in every CTA of cta_mask and each of
 // their mbarriers (same offset) receives the complete_tx
 __device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
@@ -244,8 +252,8 @@ __device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t smem_addr, uint3
 }
 // Instruction descriptor kind::tf32: D = F32 (bits 4-5 = 1), A = B = TF32 (bits 7-9, 10-12 = 2),
 // A / B major at bits 15 / 16 (0 = K-major, 1 = MN-major), N >> 3 at bits 17-22, M >> 4 at bits 24-28.
-__host__ __device__ __forceinline__ uint32_t idesc_tf32(int M, int N, int a_mn = 0) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a_mn ? 1 : 0) << 15) | ((uint32_t)(N >> 3) << 17) |
+__host__ __device__ __forceinline__ uint32_t idesc_tf32(int M, int N, int a_mn = 0, int b_mn = 0) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a_mn ? 1 : 0) << 15) | ((uint32_t)(b_mn ? 1 : 0) << 16) | ((uint32_t)(N >> 3) << 17) |
            ((uint32_t)(M >> 4) << 24);
 }
 

@@ -378,13 +378,14 @@ def device_loop(b, K, W, torch, dist, ext, flush, barrier, sampler_index=None):
 
 
 def e2e_estimate_gradient(b, K, W, torch, dist, ext, flush):
-    """End to end through the reference-facing call: estimate_gradient! with HOST buffers (lambda in, gradient +
-    value out: both transfers inside the timed region), then the host-side Optimisers.update! + ClipScale +
-    PolynomialAveraging of `step` (common.jl:91-94) as compiled host code (avi_host_update).  Wall clock, L2 flushed and
-    the device idle before every step.  Returns (seconds for K steps, breakdown dict)."""
+    """End to end through the reference-facing boundary with HOST buffers: one `step` (common.jl:75-104) = estimate_gradient!
+    (host lambda in, host gradient + value out: both transfers inside the timed region) + the host-side
+    Optimisers.update! + ClipScale + PolynomialAveraging (common.jl:91-94), as ONE C-ABI call per iteration
+    (avi_hoststep_step: the arrays are bound to a handle once).  Wall clock around the Python call, L2 flushed and the
+    device idle before every step.  Returns (seconds for K steps, breakdown dict: the library's own wall clock of the two
+    halves, and what the ctypes crossing adds)."""
     avi = b.avi
-    host = avi.HostUpdate(b.alg.optimizer, b.alg.operator, b.alg.averager, b.q0.destructure(), scale_offset=b.D)
-    gbuf = np.empty(b.obj.P, np.float32)
+    hs = avi.HostStep(b.obj, b.alg.optimizer, b.alg.operator, b.alg.averager, b.q0.destructure(), scale_offset=b.D)
     b.obj.seed(b.cfg["seed"], 0)
     tot, t_call, t_upd = 0.0, 0.0, 0.0
     for k in range(W + K):
@@ -394,17 +395,18 @@ def e2e_estimate_gradient(b, K, W, torch, dist, ext, flush):
             b.ctx.comm_barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        v, g, e = b.obj.estimate_gradient(host.lam, out=gbuf)
+        v, e = hs.step()
         t1 = time.perf_counter()
-        host.update(g)
-        t2 = time.perf_counter()
         if k >= W:
-            tot += t2 - t0; t_call += t1 - t0; t_upd += t2 - t1
+            tc, tu = hs.timing()
+            tot += t1 - t0; t_call += tc; t_upd += tu
+    hs.close()
     if b.world > 1:
         t = torch.tensor([tot], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         tot = t.item()
-    return tot, {"estimate_gradient_call_us": 1e6 * t_call / K, "host_update_us": 1e6 * t_upd / K}
+    return tot, {"estimate_gradient_call_us": t_call / K, "host_update_us": t_upd / K,
+                 "ffi_crossing_us": 1e6 * tot / K - (t_call + t_upd) / K}
 
 
 def kernel_times(b, torch, ext, flush, names, reps=5):
@@ -515,9 +517,10 @@ def main():
     if meanfield and cfg["objective"] == "rep" and not b.subsampled:
         e2e_s, e2e_parts = e2e_estimate_gradient(b, K, W, torch, dist, ext, flush)
         e2e = {"value": K / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": 4 * P, "d2h_bytes_per_step": 4 * (P + 5),
-               "path": "avi_obj_estimate_gradient (estimate_gradient! boundary: host lambda in, host gradient + value + "
-                       "completion flag out) + host Adam/ClipScale/averaging (avi_host_update); wall clock, L2 flushed "
-                       "and device idle before every step", "breakdown": e2e_parts}
+               "path": "avi_hoststep_step = avi_obj_estimate_gradient (estimate_gradient! boundary: host lambda in, host "
+                       "gradient + value + completion flag out) + host Adam/ClipScale/averaging (avi_host_update), one "
+                       "C-ABI call per step; wall clock around the Python call, L2 flushed and device idle before every step",
+               "breakdown": e2e_parts}
     else:
         # the call a user makes for these configs is optimize(): one blocking call per chunk of iterations with the
         # minibatch indices (c5) going host -> device and the ELBO trace coming back

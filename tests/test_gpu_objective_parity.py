@@ -168,9 +168,13 @@ def test_minibatch_index_validation(avi, ctx):
     X, y = Mo.synth_glm_data(n, d, seed=2)
     prob = avi.LogReg(ctx, X, y, gemm="fp32")
     q, _ = make_q(avi, "meanfield", d + 1)
-    for dataset in (np.arange(1, n + 1), np.arange(n) - 1):          # Julia-style 1:n, and a negative index
-        alg = avi.KLMinRepGradDescent(optimizer=avi.Adam(1e-2), n_samples=M, operator=avi.ClipScale(),
-                                      subsampling=avi.ReshufflingBatchSubsampling(dataset, bs))
+    with pytest.raises(ValueError):                                   # the host mirror rejects negative indices up front
+        avi.ReshufflingBatchSubsampling(np.arange(n) - 1, bs)
+    subs = [avi.ReshufflingBatchSubsampling(np.arange(1, n + 1), bs),      # Julia-style 1:n: one index past the end
+            avi.ReshufflingBatchSubsampling(np.arange(n), bs)]
+    subs[1].dataset[3] = -1                                            # past the constructor's check: the library must catch it
+    for sub in subs:
+        alg = avi.KLMinRepGradDescent(optimizer=avi.Adam(1e-2), n_samples=M, operator=avi.ClipScale(), subsampling=sub)
         with pytest.raises(avi.AviError):
             avi.optimize(KEY, alg, 6, prob, q)
     prob.close()
