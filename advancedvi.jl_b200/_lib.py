@@ -96,7 +96,8 @@ SIGNATURES = {
     "avi_hoststep_create": (C.c_int32, [vp, C.c_int32, c_float_p, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_float,
                                         C.c_int64, c_float_p, c_float_p, c_float_p, C.POINTER(vp)]),
     "avi_hoststep_step": (C.c_int32, [vp, c_float_p, c_float_p]),
-    "avi_hoststep_timing": (C.c_int32, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "avi_hoststep_timing": (C.c_int32, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                        C.POINTER(C.c_double)]),
     "avi_hoststep_destroy": (C.c_int32, [vp]),
     "avi_opt_steps_begin": (C.c_int32, [vp, C.c_int32]),
     "avi_opt_steps_enqueue": (C.c_int32, [vp, C.c_int32]),

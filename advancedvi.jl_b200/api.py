@@ -782,10 +782,11 @@ class HostStep:
         return self._v.value, self._e.value
 
     def timing(self):
-        """wall-clock microseconds of the last call's two halves: (estimate_gradient!, host update)"""
-        a, b = C.c_double(), C.c_double()
-        L.lib.avi_hoststep_timing(self.h, C.byref(a), C.byref(b))
-        return a.value, b.value
+        """wall-clock microseconds of the last call: (estimate_gradient!, host update, enqueue, wait for the flag) --
+        the last two are parts of the first"""
+        a, b, c, d = C.c_double(), C.c_double(), C.c_double(), C.c_double()
+        L.lib.avi_hoststep_timing(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d))
+        return a.value, b.value, c.value, d.value
 
     def close(self):
         if self.h:

@@ -1,5 +1,6 @@
 // extern "C" entry points of libavi_b200.so (include/avi.h): lifecycle, targets, objective.
 // The fused step lives in opt.cu.
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <atomic>
@@ -449,6 +450,7 @@ int32_t avi_obj_estimate_gradient(avi_obj* o, const float* lambda_host, int64_t 
     if (!o) return AVI_ERR_INVALID;
     avi_ctx* ctx = o->ctx;
     AVI_CHECK(check_lambda(o, lambda_host, P));
+    const auto tm0 = std::chrono::steady_clock::now();
     cudaSetDevice(ctx->device);
     std::memcpy(o->h_lambda, lambda_host, (size_t)P * sizeof(float));
     // Mean-field: no copy-engine node in the chain.  lambda is staged in by a kernel reading the pinned buffer, and the
@@ -525,6 +527,7 @@ int32_t avi_obj_estimate_gradient(avi_obj* o, const float* lambda_host, int64_t 
         o->eg_calls++;
         o->eg_gen = avi_graph_key(o, true);
     }
+    const auto tm1 = std::chrono::steady_clock::now();
     if (zero_copy) {
         // completion flag = low 32 bits of the device step counter after this call (== the host mirror o->step)
         volatile unsigned int* flag = reinterpret_cast<volatile unsigned int*>(o->h_grad + P + 4);
@@ -545,9 +548,12 @@ int32_t avi_obj_estimate_gradient(avi_obj* o, const float* lambda_host, int64_t 
     } else {
         AVI_CUDA(ctx, avi_stream_wait(ctx));
     }
+    const auto tm2 = std::chrono::steady_clock::now();
     if (grad_host) std::memcpy(grad_host, o->h_grad, (size_t)P * sizeof(float));
     if (value) *value = o->h_grad[P];
     if (elbo) *elbo = o->h_grad[P + 1];
+    o->last_launch_us = std::chrono::duration<double, std::micro>(tm1 - tm0).count();   // diagnostics (avi_hoststep_timing)
+    o->last_wait_us = std::chrono::duration<double, std::micro>(tm2 - tm1).count();
     return AVI_OK;
 }
 

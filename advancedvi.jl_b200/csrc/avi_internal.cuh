@@ -217,6 +217,7 @@ struct FrWork {
 };
 
 struct avi_obj {
+    double last_launch_us = 0.0, last_wait_us = 0.0;   // estimate_gradient!: host time to enqueue / to see the completion flag
     avi_ctx* ctx = nullptr;
     avi_model* model = nullptr;
     int family = 0, objective = 0, entropy = 0;

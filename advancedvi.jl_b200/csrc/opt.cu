@@ -688,10 +688,12 @@ int32_t avi_hoststep_step(avi_hoststep* hs, float* value, float* elbo) {
     return rc;
 }
 
-int32_t avi_hoststep_timing(const avi_hoststep* hs, double* estimate_us, double* update_us) {
+int32_t avi_hoststep_timing(const avi_hoststep* hs, double* estimate_us, double* update_us, double* enqueue_us, double* wait_us) {
     if (!hs) return AVI_ERR_INVALID;
     if (estimate_us) *estimate_us = hs->last_estimate_us;
     if (update_us) *update_us = hs->last_update_us;
+    if (enqueue_us) *enqueue_us = hs->obj->last_launch_us;
+    if (wait_us) *wait_us = hs->obj->last_wait_us;
     return AVI_OK;
 }
 

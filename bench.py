@@ -387,7 +387,7 @@ def e2e_estimate_gradient(b, K, W, torch, dist, ext, flush):
     avi = b.avi
     hs = avi.HostStep(b.obj, b.alg.optimizer, b.alg.operator, b.alg.averager, b.q0.destructure(), scale_offset=b.D)
     b.obj.seed(b.cfg["seed"], 0)
-    tot, t_call, t_upd = 0.0, 0.0, 0.0
+    tot, t_call, t_upd, t_enq, t_wait = 0.0, 0.0, 0.0, 0.0, 0.0
     for k in range(W + K):
         with torch.cuda.stream(ext):
             l2_flush(flush)
@@ -398,14 +398,15 @@ def e2e_estimate_gradient(b, K, W, torch, dist, ext, flush):
         v, e = hs.step()
         t1 = time.perf_counter()
         if k >= W:
-            tc, tu = hs.timing()
-            tot += t1 - t0; t_call += tc; t_upd += tu
+            tc, tu, tq, tw = hs.timing()
+            tot += t1 - t0; t_call += tc; t_upd += tu; t_enq += tq; t_wait += tw
     hs.close()
     if b.world > 1:
         t = torch.tensor([tot], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         tot = t.item()
-    return tot, {"estimate_gradient_call_us": t_call / K, "host_update_us": t_upd / K,
+    return tot, {"estimate_gradient_call_us": t_call / K, "of_which_enqueue_us": t_enq / K,
+                 "of_which_wait_for_completion_flag_us": t_wait / K, "host_update_us": t_upd / K,
                  "ffi_crossing_us": 1e6 * tot / K - (t_call + t_upd) / K}
 
 

@@ -240,13 +240,14 @@ int32_t avi_host_update(int32_t rule, const float* hyper, int32_t n_hyper, int32
  * place), grad (P, receives every gradient), lambda_avg (P or NULL without averaging).  Descent / Adam, IdentityOperator /
  * ClipScale (entries from scale_offset on), NoAveraging / PolynomialAveraging.  A non-finite value slot leaves the
  * parameters untouched and is reported through `value` (the caller raises, common.jl:83-89).  _timing: wall-clock
- * microseconds of the two halves of the last call. */
+ * microseconds of the last call: estimate_gradient! as a whole, the host update, and inside the former the time to
+ * enqueue the launch and the time until the completion flag was seen (any pointer may be NULL). */
 typedef struct avi_hoststep avi_hoststep;
 int32_t avi_hoststep_create(avi_obj* obj, int32_t rule, const float* hyper, int32_t n_hyper, int32_t op, float op_param,
                             int32_t averager, float avg_param, int64_t scale_offset, float* lambda, float* grad,
                             float* lambda_avg, avi_hoststep** out);
 int32_t avi_hoststep_step(avi_hoststep* hs, float* value, float* elbo);
-int32_t avi_hoststep_timing(const avi_hoststep* hs, double* estimate_us, double* update_us);
+int32_t avi_hoststep_timing(const avi_hoststep* hs, double* estimate_us, double* update_us, double* enqueue_us, double* wait_us);
 int32_t avi_hoststep_destroy(avi_hoststep* hs);
 /* current iterate, averaged iterate (output(), common.jl:63-67) and last gradient */
 int32_t avi_opt_get(avi_opt* opt, float* lambda_host, float* lambda_avg_host, float* grad_host);
