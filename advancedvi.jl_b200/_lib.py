@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libavi_b200.so")
+LIB_PATH = os.environ.get("AVI_LIB_PATH") or os.path.join(_HERE, "libavi_b200.so")   # (override: A/B runs of two builds)
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

@@ -213,11 +213,13 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask)
 // 32 lanes x 8 consecutive columns: thread t of the warp receives lane (base_lane + t)
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float v[8]) {
     uint32_t r[8];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+    // load and wait in ONE asm statement: the destination registers are written asynchronously until wait::ld, and
+    // nothing (a compiler-inserted spill store least of all) may touch them in between
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n\t"
+                 "tcgen05.wait::ld.sync.aligned;"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                  : "r"(taddr)
                  : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }

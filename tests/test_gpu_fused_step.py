@@ -328,3 +328,27 @@ def test_hoststep_matches_estimate_gradient_plus_host_update(avi, ctx):
     t_est, t_upd, t_enq, t_wait = hs.timing()
     assert t_est > 0 and t_upd >= 0 and t_enq + t_wait <= t_est
     hs.close(); obj_b.close(); prob.close()
+
+
+def test_first_call_on_fresh_buffers_equals_repeats(avi, ctx):
+    """A visibility or ordering bug between the phases of the single kernel hides behind repeated identical calls (the
+    buffers still hold the previous call's identical intermediates): the FIRST call on a freshly created target is the
+    one that exposes it.  Full C2 size, three fresh targets, first / second / third call bit for bit."""
+    n, d, M = 10000, 1024, 256
+    rng = np.random.default_rng(1)
+    X = rng.standard_normal((n, d), dtype=np.float32) / np.float32(np.sqrt(d))
+    X[:, d - 1] = 1.0
+    y = (rng.random(n) < 0.5).astype(np.float32)
+    D = d + 1
+    q = avi.MeanFieldGaussian(np.zeros(D, np.float32), np.full(D, 0.1, np.float32))
+    lam = q.destructure()
+    for _ in range(3):
+        prob = avi.LogReg(ctx, X, y, gemm="tf32")
+        obj = avi.Objective(1, avi.RepGradELBO(M), q, prob)
+        first = obj.estimate_gradient(lam)
+        g_first = first[1].copy()
+        for _ in range(2):
+            obj.seed(1, 0)
+            again = obj.estimate_gradient(lam)
+            assert again[0] == first[0] and np.array_equal(again[1], g_first)
+        obj.close(); prob.close()
