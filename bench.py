@@ -501,7 +501,8 @@ def main():
     cfg = CONFIGS[args.config]
     ctx = avi.Context(local_rank)
     ext = torch.cuda.ExternalStream(ctx.stream(), device=local_rank)
-    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
+    flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device="cuda")   # (float32: .sum() reads it in place; a uint8
+                                                                                 # buffer is first converted into a 2 GB int64 temporary)
     peaks, src = load_peaks()
     hbm = peaks.get("hbm_gbs", 6650.0)
 

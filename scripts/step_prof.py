@@ -26,7 +26,7 @@ st = _OptState(alg, obj, q)
 if cold:
     import torch
     ext = torch.cuda.ExternalStream(ctx.stream(), device=0)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    flush = torch.empty(64 << 20, dtype=torch.float32, device="cuda")
     st.steps_begin(steps)
     for k in range(steps):
         with torch.cuda.stream(ext):
