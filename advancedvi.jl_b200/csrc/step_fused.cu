@@ -87,24 +87,29 @@ __device__ __forceinline__ void stamp_max(unsigned long long* tl, int slot) {
 #define PSTAMP(prof, slot) do { if (prof) (prof)[(size_t)blockIdx.x * 32 + (slot)] = gtime_ns(); } while (0)
 
 // pipeline barriers for a phase with `stages` ring slots: one WARP, one barrier per lane (the previous phase's barriers are
-// invalidated first).  Done by a single thread this was ~40 dependent shared-memory operations, 0.6 us on the critical
-// path between the forward and the backward phase.
-__device__ __forceinline__ void init_pipeline(SmemCtl* ctl, int stages, int stages_prev) {
+// invalidated first).  which: 1 = the operand ring (full / empty), 2 = the accumulator barriers, 3 = both.
+__device__ __forceinline__ void init_pipeline(SmemCtl* ctl, int stages, int stages_prev, int which = 3) {
     static_assert(2 * MAX_STAGES + 4 <= 32, "one lane per barrier");
     const int lane = threadIdx.x & 31;
     uint64_t* bar = nullptr;
     uint32_t count = 1;
     bool had = false, want = false;
-    if (lane < MAX_STAGES) { bar = &ctl->full[lane]; had = lane < stages_prev; want = lane < stages; }
-    else if (lane < 2 * MAX_STAGES) { const int s = lane - MAX_STAGES; bar = &ctl->empty[s]; had = s < stages_prev; want = s < stages; }
-    else if (lane < 2 * MAX_STAGES + 2) { bar = &ctl->tmem_full[lane - 2 * MAX_STAGES]; had = stages_prev > 0; want = true; }
-    else if (lane < 2 * MAX_STAGES + 4) { bar = &ctl->tmem_empty[lane - 2 * MAX_STAGES - 2]; had = stages_prev > 0; want = true; count = EPI_WARPS; }
+    if (lane < MAX_STAGES) { if (which & 1) { bar = &ctl->full[lane]; had = lane < stages_prev; want = lane < stages; } }
+    else if (lane < 2 * MAX_STAGES) { const int s = lane - MAX_STAGES; if (which & 1) { bar = &ctl->empty[s]; had = s < stages_prev; want = s < stages; } }
+    else if (lane < 2 * MAX_STAGES + 2) { if (which & 2) { bar = &ctl->tmem_full[lane - 2 * MAX_STAGES]; had = stages_prev > 0; want = true; } }
+    else if (lane < 2 * MAX_STAGES + 4) { if (which & 2) { bar = &ctl->tmem_empty[lane - 2 * MAX_STAGES - 2]; had = stages_prev > 0; want = true; count = EPI_WARPS; } }
     if (bar) {
         if (had) mbar_inval(bar);
         if (want) tc::mbar_init(bar, count);
     }
     tc::mbar_fence_init();
     __syncwarp();
+}
+// the operand ring alone, by ONE thread (the producer, while its CTA's epilogue is still running)
+__device__ __forceinline__ void init_ring_thread(SmemCtl* ctl, int stages, int stages_prev) {
+    for (int s = 0; s < stages_prev; ++s) { mbar_inval(&ctl->full[s]); mbar_inval(&ctl->empty[s]); }
+    for (int s = 0; s < stages; ++s) { tc::mbar_init(&ctl->full[s], 1); tc::mbar_init(&ctl->empty[s], 1); }
+    tc::mbar_fence_init();
 }
 
 #define FUNIT_COORDS(u) \
@@ -158,10 +163,18 @@ __device__ __forceinline__ int preissue_early(const CUtensorMap* tmA, const CUte
 
 // One contraction phase: the single-CTA pipeline of k_gemm_tc (gemm_tc.cu) over the units u = blockIdx.x,
 // blockIdx.x + gridDim.x, ...; the ring and the accumulator stages start from their initial state.
+// nextA / nextB / nextp != nullptr (forward phase): as soon as this phase's last MMA has COMPLETED -- the ring is then
+// free, while the epilogue warps still work on the accumulator for microseconds -- the producer thread re-carves the ring
+// for the next phase's geometry and requests that phase's static operand.  Returns (warp 0 only) the number of slots
+// armed, -1 if nothing was handed over.  Doing this after the epilogue cost ~1.8 us of once-executed, instruction-fetch-
+// bound code on the critical path between the phases.
 template <int EPI, int LIK, int X3>
-__device__ __forceinline__ void tc_phase(const CUtensorMap* tmA, const CUtensorMap* tmB, const TcParams& p, SmemCtl* ctl,
-                                         uint8_t* tiles, uint32_t tmem_base, int stages, int pre_issued, int early_op,
-                                         unsigned long long* prof, int ps) {
+__device__ __forceinline__ int tc_phase(const CUtensorMap* tmA, const CUtensorMap* tmB, const TcParams& p, SmemCtl* ctl,
+                                        uint8_t* tiles, uint32_t tmem_base, int stages, int pre_issued, int early_op,
+                                        unsigned long long* prof, int ps, const CUtensorMap* nextA = nullptr,
+                                        const CUtensorMap* nextB = nullptr, const TcParams* nextp = nullptr,
+                                        int next_stages = 0, int next_early_op = 0) {
+    int handed = -1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NT = p.nt;
     const int b_bytes = b_tile_bytes(p), stage_bytes = A_TILE_BYTES + b_bytes;
@@ -196,7 +209,26 @@ __device__ __forceinline__ void tc_phase(const CUtensorMap* tmA, const CUtensorM
                 }
             }
             PSTAMP(prof, ps + 0);   // last operand request issued
+            if (nextp) {
+                // drain: every slot's last release has landed (so no commit of this phase can hit a re-initialised
+                // barrier) and the last unit's accumulator is complete (every MMA has finished reading the ring)
+                const int per_cta = first < units ? (units - first + stride - 1) / stride : 0;
+                if (per_cta > 0) {
+                    for (int i = 0; i < stages; ++i) {
+                        // what the producer would wait for before refilling slot `stage`: the release of its last use
+                        // (a slot that was never filled passes at once)
+                        tc::mbar_wait(&ctl->empty[stage], phase ^ 1);
+                        if (++stage == stages) { stage = 0; phase ^= 1; }
+                    }
+                    const int last = per_cta - 1;
+                    tc::mbar_wait(&ctl->tmem_full[last & 1], (uint32_t)((last >> 1) & 1));
+                }
+                init_ring_thread(ctl, next_stages, stages);
+                handed = preissue_early(nextA, nextB, *nextp, ctl, tiles, next_stages, next_early_op);
+                PSTAMP(prof, 10);   // next phase's ring carved, static operand requested
+            }
         }
+        handed = __reduce_max_sync(0xffffffffu, handed);   // (from whichever lane was elected; the others hold -1)
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (tc::elect_one()) {
@@ -259,6 +291,7 @@ __device__ __forceinline__ void tc_phase(const CUtensorMap* tmA, const CUtensorM
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
     }
+    return handed;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -737,6 +770,8 @@ k_glm_mf_step(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ C
 
     // forward phase: A = Zt (dependent), B = X rows.  A full-data X is static: request it before waiting for the
     // previous kernel; a minibatch copy is rewritten by the gather kernel of this iteration: request it after the wait.
+    // (The dependency wait is taken per warp: warp 3 goes straight to it and fetches the state snapshot while warp 0 is
+    // still issuing the requests for the static operand -- both are ~1 us of once-executed code.)
     int pre = 0;
     if (warp == 0 && sp.f.static_op == 2) {
         if (lane == 0) pre = preissue_early(&tmZ, &tmXr, sp.f, ctl, tiles, sp.stages_f, 2);
@@ -841,20 +876,17 @@ k_glm_mf_step(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ C
         if (lane == 0) ctl->scratch[0] = part;
     }
 
-    tc_phase<EPI_GLM_FWD, LIK, X3>(&tmZ, &tmXr, sp.f, ctl, tiles, tmem_base, sp.stages_f, pre, 2, prof, 6);
+    const int handed = tc_phase<EPI_GLM_FWD, LIK, X3>(&tmZ, &tmXr, sp.f, ctl, tiles, tmem_base, sp.stages_f, pre, 2, prof, 6,
+                                                      &tmXc, &tmR, &sp.b, sp.stages_b, 1);
     stamp_max(sp.tl, 9);
 
     // ---- drain, re-carve the ring for the backward geometry, request its static operand (X columns) while the
     //      other CTAs finish, then the barrier that publishes R
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 1) init_pipeline(ctl, sp.stages_b, sp.stages_f);
+    if (warp == 1) init_pipeline(ctl, sp.stages_b, sp.stages_f, /*accumulator barriers only*/ 2);
     __syncthreads();
-    pre = 0;
-    if (warp == 0) {
-        if (lane == 0) pre = preissue_early(&tmXc, &tmR, sp.b, ctl, tiles, sp.stages_b, 1);
-        pre = __shfl_sync(0xffffffffu, pre, 0);
-    }
+    pre = warp == 0 ? max(handed, 0) : 0;   // (the producer re-carved the ring and requested the X columns long ago)
     if (threadIdx.x == 0) PSTAMP(prof, 12);   // arriving at barrier 1 (ring re-carved, X columns requested)
     grid_barrier(gb);
     stamp_min(sp.tl, 3);

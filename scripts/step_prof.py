@@ -44,7 +44,7 @@ h = buf[:grid * 32].reshape(grid, 32).astype(np.int64)
 t0 = h[:, 0][h[:, 0] > 0].min()
 names = {0: "entry", 1: "prologue done", 2: "past dependency wait", 3: "snapshot read", 4: "sample phase done", 5: "past barrier 0",
          6: "fwd: last operand request", 7: "fwd: first operands landed", 8: "fwd: last MMA issued", 9: "fwd: epilogue math done",
-         11: "fwd: unit complete", 12: "arrive barrier 1", 13: "past barrier 1",
+         10: "ring re-carved for the backward phase", 11: "fwd: unit complete", 12: "arrive barrier 1", 13: "past barrier 1",
          14: "bwd: last operand request", 15: "bwd: first operands landed", 16: "bwd: last MMA issued", 17: "bwd: epilogue math done",
          18: "bwd: slab rows stored", 19: "bwd: unit complete (+combine)", 20: "arrive barrier 2", 21: "past barrier 2",
          24: "tail: inputs loaded, scalars reduced", 25: "tail: value + gradient of the slice", 26: "tail: update stored",
