@@ -287,7 +287,7 @@ int32_t avi_model_destroy(avi_model* model) {
 
 // ---- objective ---------------------------------------------------------------------------------
 static void obj_free_buffers(avi_obj* o) {
-    avi_free(o->Z); avi_free(o->E); avi_free(o->G); avi_free(o->U); avi_free(o->E2);
+    avi_free(o->Z); avi_free(o->E); avi_free(o->G); avi_free(o->U); avi_free(o->E2); avi_free(o->V);
     avi_free(o->logp); avi_free(o->esq); avi_free(o->fbuf);
 }
 
@@ -305,7 +305,12 @@ int32_t avi_obj_ensure_capacity(avi_obj* o, int M) {
     AVI_CHECK(avi_alloc(ctx, &o->E, n));
     AVI_CHECK(avi_alloc(ctx, &o->G, n));
     if (o->family == AVI_FULLRANK) AVI_CHECK(avi_alloc(ctx, &o->U, n));
-    if (o->family == AVI_LOWRANK) AVI_CHECK(avi_alloc(ctx, &o->E2, (size_t)M * o->ldr));
+    if (o->family == AVI_LOWRANK) {
+        AVI_CHECK(avi_alloc(ctx, &o->E2, (size_t)M * o->ldr));
+        // w = Sigma^-1 (z - mu) and U'w per sample: the log q based estimators, and estimate_objective with any entropy
+        AVI_CHECK(avi_alloc(ctx, &o->U, n));
+        AVI_CHECK(avi_alloc(ctx, &o->V, (size_t)M * o->ldr));
+    }
     AVI_CHECK(avi_alloc(ctx, &o->logp, (size_t)M));
     AVI_CHECK(avi_alloc(ctx, &o->esq, (size_t)M));
     AVI_CHECK(avi_alloc(ctx, &o->fbuf, (size_t)M));
@@ -339,8 +344,10 @@ int32_t avi_obj_create_lowrank(avi_ctx* ctx, avi_model* model, int32_t rank, int
     if (!ctx || !model || !out) return AVI_ERR_INVALID;
     *out = nullptr;
     if (rank < 1 || rank > avi_lr_max_rank()) AVI_FAIL(ctx, AVI_ERR_INVALID, "rank must be in 1..32");
-    if (objective != AVI_REPGRAD || entropy != AVI_ENT_CLOSEDFORM)
-        AVI_FAIL(ctx, AVI_ERR_UNSUPPORTED, "the low-rank family supports RepGradELBO with ClosedFormEntropy only");
+    if (objective == AVI_REPGRAD && entropy == AVI_ENT_STL_ZEROGRAD)
+        AVI_FAIL(ctx, AVI_ERR_UNSUPPORTED, "the low-rank family does not implement StickingTheLandingEntropyZeroGradient");
+    if (ctx->nranks > 1 && !(objective == AVI_REPGRAD && (entropy == AVI_ENT_CLOSEDFORM || entropy == AVI_ENT_CLOSEDFORM_ZEROGRAD)))
+        AVI_FAIL(ctx, AVI_ERR_UNSUPPORTED, "the low-rank family runs its log q based estimators on one rank only");
     return obj_create(ctx, model, AVI_LOWRANK, rank, objective, entropy, M, out);
 }
 
@@ -365,9 +372,9 @@ static int32_t obj_create(avi_ctx* ctx, avi_model* model, int32_t family, int32_
                                     : 2LL * o->D + (int64_t)o->D * rank;
     // payload of the exchange: vector sums | scalars | full-rank: two D x D blocks / low-rank: sum_m g u_fact' (D x r)
     o->acc_len = 4LL * o->accv + ACC_NSCAL +
-                 (family == AVI_FULLRANK ? 2LL * o->D * o->D : family == AVI_LOWRANK ? (int64_t)o->D * rank : 0);
+                 (family == AVI_FULLRANK ? 2LL * o->D * o->D : family == AVI_LOWRANK ? 2LL * o->D * rank : 0);
     int32_t rc = avi_alloc(ctx, &o->d_state, 1);
-    if (rc == AVI_OK && family == AVI_LOWRANK) rc = avi_alloc(ctx, &o->lr_ent, 1 + (size_t)o->D + (size_t)o->D * rank);
+    if (rc == AVI_OK && family == AVI_LOWRANK) rc = avi_alloc(ctx, &o->lr_ent, 1 + (size_t)o->D + (size_t)o->D * rank + 32 * 32 + 2);
     if (rc == AVI_OK) rc = avi_alloc(ctx, &o->d_lambda, (size_t)o->P);
     if (rc == AVI_OK) rc = avi_alloc(ctx, &o->acc, (size_t)o->acc_len);
     if (rc == AVI_OK) rc = avi_alloc(ctx, &o->grad, (size_t)o->P + 4);   // + {value, elbo, logdet, shift} (estimate_gradient!)
@@ -563,9 +570,8 @@ int32_t avi_obj_estimate_objective(avi_obj* o, const float* lambda_host, int64_t
     avi_ctx* ctx = o->ctx;
     AVI_CHECK(check_lambda(o, lambda_host, P));
     if (n_samples < 1) AVI_FAIL(ctx, AVI_ERR_INVALID, "n_samples must be >= 1");
-    if (o->family == AVI_LOWRANK)
-        AVI_FAIL(ctx, AVI_ERR_UNSUPPORTED, "estimate_objective is not implemented for the low-rank family (its Monte-Carlo "
-                                           "entropy needs logpdf through the capacitance matrix)");
+    const bool lowrank = o->family == AVI_LOWRANK;
+    const bool closed = objective == AVI_REPGRAD && (entropy == AVI_ENT_CLOSEDFORM || entropy == AVI_ENT_CLOSEDFORM_ZEROGRAD);
     cudaSetDevice(ctx->device);
     std::memcpy(o->h_lambda, lambda_host, (size_t)P * sizeof(float));
     AVI_CUDA(ctx, cudaMemcpyAsync(o->d_lambda, o->h_lambda, (size_t)P * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
@@ -574,10 +580,14 @@ int32_t avi_obj_estimate_objective(avi_obj* o, const float* lambda_host, int64_t
     ObjDeviceState ov{};
     ov.key = key; ov.step = 0;
     double s_logp = 0.0, s_esq = 0.0;
-    float logdet = 0.0f;
+    float logdet = 0.0f, lr_H = 0.0f;
+    if (lowrank) {   // entropy and the capacitance inverse B^-1 once; log q per sample (if needed) inside the chunks
+        AVI_CHECK(avi_lr_entropy(o, o->d_lambda));
+        AVI_CUDA(ctx, cudaMemcpyAsync(&lr_H, o->lr_ent, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    }
     for (int m0 = 0; m0 < n_samples; m0 += chunk) {
         const int Mc = std::min(chunk, n_samples - m0);
-        AVI_CHECK(avi_objective_forward_chunk(o, o->d_lambda, m0, Mc, &ov, o->out));
+        AVI_CHECK(avi_objective_forward_chunk(o, o->d_lambda, m0, Mc, &ov, o->out, lowrank && !closed));
         float h[4];
         AVI_CUDA(ctx, cudaMemcpyAsync(h, o->out, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
         AVI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -588,7 +598,9 @@ int32_t avi_obj_estimate_objective(avi_obj* o, const float* lambda_host, int64_t
     const double D = o->D, LOG2PI = 1.8378770664093453, H0 = 1.4189385332046727;
     const double energy = s_logp / n_samples;
     double ent;
-    if (objective == AVI_REPGRAD && (entropy == AVI_ENT_CLOSEDFORM || entropy == AVI_ENT_CLOSEDFORM_ZEROGRAD))
+    if (lowrank)   // H from k_lr_entropy, or -mean log q(z) (the chunk sums then carry sum log q in the second slot)
+        ent = closed ? (double)lr_H : -s_esq / n_samples;
+    else if (closed)
         ent = D * H0 + logdet;
     else   // -mean log q(z) with scale \ (z - mu) == eps
         ent = 0.5 * s_esq / n_samples + 0.5 * D * LOG2PI + logdet;

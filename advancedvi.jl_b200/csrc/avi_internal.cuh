@@ -241,7 +241,8 @@ struct avi_obj {
     // low-rank family (family_lr.cu): rank, pitch of the factor draws, u_fact draws, [H | dH/dD | dH/dU]
     int rank = 0, ldr = 0;
     float* E2 = nullptr;         // cap_M x ldr
-    float* lr_ent = nullptr;     // 1 + D + D * rank
+    float* lr_ent = nullptr;     // [H | dH/dD (D) | dH/dU (D * rank) | B^-1 (32 x 32) | log det B | sum log D]
+    float* V = nullptr;          // cap_M x ldr : U' w per sample (logq-based estimators; w itself lives in U)
     float* logp = nullptr;       // cap_M
     float* esq = nullptr;        // cap_M : |eps_m|^2
     float* fbuf = nullptr;       // cap_M : ScoreGrad f_m
@@ -312,7 +313,10 @@ int32_t avi_family_sample(avi_obj* o, const float* lambda, float* Z, float* E, f
 int avi_lr_max_rank();                                                                                 // family_lr.cu
 int32_t avi_lr_affine(avi_obj* o, const float* lambda, const float* E1, const float* E2, float* Z, int Mloc);
 int32_t avi_lr_entropy(avi_obj* o, const float* lambda);      // -> o->lr_ent
-int32_t avi_lr_finalize(avi_obj* o, float* grad, float* out); // acc, lr_ent -> gradient, value, elbo
+int32_t avi_lr_finalize(avi_obj* o, const float* lambda, float* grad, float* out); // acc, lr_ent -> gradient, value, elbo
+bool avi_lr_needs_logq(const avi_obj* o);
+int32_t avi_lr_logq(avi_obj* o, const float* lambda, int Mloc, bool forward_only = false);   // w, U'w, log q per sample (+ G += w for RepGrad)
+int32_t avi_lr_logq_sums(avi_obj* o, int Mloc);
 int32_t avi_axpy(avi_ctx* ctx, const float* x, float* y, int64_t n);                                   // y += x
 int32_t avi_colsum_add(avi_ctx* ctx, const float* W, int ld, int Mloc, int D, float* tmp, float* dst);  // dst += column sums
 int32_t avi_obj_stage_lambda(avi_obj* o);   // o->h_lambda (pinned, mapped) -> o->d_lambda by a kernel
@@ -329,7 +333,7 @@ int32_t avi_objective_finalize(avi_obj* o, const float* lambda, float* grad, flo
                                bool fuse_advance = false);
 // forward-only chunk for estimate_objective: sums_dev = {sum logp, sum |eps|^2, logdet}
 int32_t avi_objective_forward_chunk(avi_obj* o, const float* lambda, int m0, int Mc, const ObjDeviceState* ov,
-                                    float* sums_dev);
+                                    float* sums_dev, bool lowrank_logq = false);
 int32_t avi_exchange(avi_ctx* ctx, float* buf, int64_t count);
 struct CommPeers;
 bool avi_comm_peers(avi_ctx* ctx, int64_t count, CommPeers* out);   // comm.cu          // all-reduce (no-op single rank)

@@ -505,11 +505,21 @@ int32_t avi_objective_local(avi_obj* o, const float* lambda) {
         AVI_LAUNCHED(ctx);
     }
     if (o->family == AVI_LOWRANK) {
-        // v0 = sum_m g, v1 = sum_m g .* u_diag (the mean-field reduction), CU[k * D + i] = sum_m g[m][i] u_fact[m][k]
-        k_reduce_mf<<<(unsigned)ceil_div(D, 32), dim3(32, 32), 0, ctx->stream>>>(o->G, o->E, o->fbuf, ld, Mloc, D, accv,
-                                                                               o->objective, 0, o->acc);
-        AVI_LAUNCHED(ctx);
-        AVI_CHECK(avi_gemm_simt(ctx, o->E2, 1, o->ldr, o->G, 1, ld, scal + ACC_NSCAL, D, 1, o->rank, D, Mloc, 1.0f));
+        const bool logq = avi_lr_needs_logq(o);
+        if (logq) {
+            // w = Sigma^-1 (z - mu), U'w and log q(z) per sample through the r x r capacitance inverse (family_lr.cu);
+            // RepGrad + STL / MonteCarlo: G += w.  Replaces the scalar sums of k_scalars (whose log q is the mean-field one).
+            AVI_CHECK(avi_lr_entropy(o, lambda));
+            AVI_CHECK(avi_lr_logq(o, lambda, Mloc));
+        }
+        if (rep) {
+            // v0 = sum_m g, v1 = sum_m g .* u_diag (the mean-field reduction), CU[k * D + i] = sum_m g[m][i] u_fact[m][k]
+            k_reduce_mf<<<(unsigned)ceil_div(D, 32), dim3(32, 32), 0, ctx->stream>>>(o->G, o->E, o->fbuf, ld, Mloc, D, accv,
+                                                                                   AVI_REPGRAD, 0, o->acc);
+            AVI_LAUNCHED(ctx);
+            AVI_CHECK(avi_gemm_simt(ctx, o->E2, 1, o->ldr, o->G, 1, ld, scal + ACC_NSCAL, D, 1, o->rank, D, Mloc, 1.0f));
+        }
+        if (logq) AVI_CHECK(avi_lr_logq_sums(o, Mloc));
     } else if (o->family == AVI_MEANFIELD) {
         // with a fused target and a closed-form entropy nothing else is needed (v2, v3 unused)
         if (!(skip_g && !stl)) {
@@ -575,12 +585,14 @@ int32_t avi_objective_fused(avi_obj* o, const float* lambda, const StepTail& tai
 }
 
 int32_t avi_objective_forward_chunk(avi_obj* o, const float* lambda, int m0, int Mc, const ObjDeviceState* ov,
-                                    float* sums_dev) {
+                                    float* sums_dev, bool lowrank_logq) {
     avi_ctx* ctx = o->ctx;
     // forward only: eps itself is not needed downstream (|eps_m|^2 is), so the mean-field sampler writes z alone --
     // the algorithmic 4 (2 D + D M) bytes of SURVEY.md 8(d) K1
     AVI_CHECK(avi_family_sample(o, lambda, o->Z, o->family == AVI_MEANFIELD ? nullptr : o->E, o->esq, Mc, m0, o->d_state, ov));
     AVI_CHECK(o->model->eval(o->Z, o->ld, Mc, o->logp, nullptr));
+    // low-rank family: the second sum is sum_m log q(z_m) (through the capacitance inverse prepared by avi_lr_entropy)
+    if (lowrank_logq) AVI_CHECK(avi_lr_logq(o, lambda, Mc, /*forward_only=*/true));
     k_forward_sums<<<1, 1024, 0, ctx->stream>>>(lambda, o->D, o->family == AVI_FULLRANK, o->logp, o->esq, Mc, sums_dev);
     AVI_LAUNCHED(ctx);
     return AVI_OK;
@@ -591,8 +603,8 @@ int32_t avi_objective_finalize(avi_obj* o, const float* lambda, float* grad, flo
     avi_ctx* ctx = o->ctx;
     const int D = o->D, accv = o->accv;
     if (o->family == AVI_LOWRANK) {
-        AVI_CHECK(avi_lr_entropy(o, lambda));
-        return avi_lr_finalize(o, grad, out);
+        if (!avi_lr_needs_logq(o)) AVI_CHECK(avi_lr_entropy(o, lambda));   // (otherwise computed before the log q kernel)
+        return avi_lr_finalize(o, lambda, grad, out);
     }
     if (o->family == AVI_MEANFIELD) {
         unsigned nb = (unsigned)std::min<int64_t>(ceil_div(D, 256), 64);

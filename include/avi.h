@@ -155,9 +155,12 @@ int32_t avi_obj_create(avi_ctx* ctx, avi_model* model, int32_t family, int32_t o
 /* MvLocationScaleLowRank / LowRankGaussian (src/families/location_scale_low_rank.jl:16-24, :119-135): covariance
  * diag(scale_diag^2) + scale_factors scale_factors', lambda = [location (D); scale_diag (D); vec(scale_factors)
  * (D x rank, column-major)] (Functors order, :26), P = 2 D + D rank.  rank <= 32.  Supported: RepGradELBO with
- * ClosedFormEntropy (what KLMinRepGradDescent uses by default, docs/src/families.md:185-190), estimate_gradient!,
+ * ClosedFormEntropy (what KLMinRepGradDescent uses by default, docs/src/families.md:185-190),
+ * ClosedFormEntropyZeroGradient, MonteCarloEntropy and StickingTheLandingEntropy, ScoreGradELBO (VarGrad) -- log q(z)
+ * and its gradients go through the rank x rank capacitance matrix (Woodbury) --, estimate_gradient!, estimate_objective,
  * rand and the fused step with Descent / Adam / DoG / DoWG, IdentityOperator / ClipScale (on scale_diag,
- * clip_scale.jl:31-41) and both averagers; everything else reports AVI_ERR_UNSUPPORTED. */
+ * clip_scale.jl:31-41) and both averagers.  AVI_ERR_UNSUPPORTED: StickingTheLandingEntropyZeroGradient, the proximal
+ * operator, and the log q based estimators on more than one rank. */
 int32_t avi_obj_create_lowrank(avi_ctx* ctx, avi_model* model, int32_t rank, int32_t objective, int32_t entropy,
                                int32_t M, avi_obj** out);
 /* set_objective_state_problem (repgradelbo.jl:31-39, scoregradelbo.jl:24-32) */

@@ -196,8 +196,7 @@ def repgrad_lowrank_value_and_gradient(params, q_template, prob, u_diag, u_fact,
       ClosedFormEntropy          d = -mean J' g - dH          (dH: MvLocationScaleLowRank.entropy_gradient)
       StickingTheLandingEntropy  d = -mean J' (g + w),  w = Sigma^-1 (z - mu)   (q frozen inside log q, entropy.jl:59-65)
       MonteCarloEntropy          the STL path term plus mean d log q / d lambda at fixed z (entropy.jl:42-46)
-    Returns (value = -ELBO estimate, gradient in destructure order, elbo).  The device path implements the first
-    (family_lr.cu); the other two are groundwork."""
+    Returns (value = -ELBO estimate, gradient in destructure order, elbo).  Device path: family_lr.cu."""
     q = q_template.restructure(params)
     M = u_diag.shape[1]
     Z = q.rand_from_eps(u_diag, u_fact)
@@ -207,6 +206,10 @@ def repgrad_lowrank_value_and_gradient(params, q_template, prob, u_diag, u_fact,
         gD_H, gU_H = q.entropy_gradient()
         Wg = G
         g_loc_x, g_diag_x, g_fact_x = 0.0, -gD_H, -gU_H
+    elif entropy == "ClosedFormEntropyZeroGradient":     # entropy.jl:13-15: the value of H, no gradient through it
+        ent = q.entropy()
+        Wg = G
+        g_loc_x, g_diag_x, g_fact_x = 0.0, 0.0, 0.0
     elif entropy in ("StickingTheLandingEntropy", "MonteCarloEntropy"):
         ent = -float(np.mean(q.logpdf(Z)))
         w, gD, gU = _lowrank_logq_param_grads(q, Z)
@@ -227,7 +230,8 @@ def repgrad_lowrank_value_and_gradient(params, q_template, prob, u_diag, u_fact,
 def scoregrad_lowrank_value_and_gradient(params, q_template, prob, u_diag, u_fact):
     """estimate_gradient! for ScoreGradELBO (VarGrad, scoregradelbo.jl:87-117) over MvLocationScaleLowRank:
     f_m = log q_lambda(z_m) - log pi(z_m) with z, log pi constants; value = (mean f^2 - (mean f)^2) / 2,
-    gradient = mean (f_m - fbar) d log q_lambda(z_m) / d lambda.  Returns (value, gradient, elbo).  Groundwork."""
+    gradient = mean (f_m - fbar) d log q_lambda(z_m) / d lambda.  Returns (value, gradient, elbo).  Device path:
+    family_lr.cu."""
     q = q_template.restructure(params)
     Z = q.rand_from_eps(u_diag, u_fact)
     logp = prob.logdensity_batch(Z) if hasattr(prob, "logdensity_batch") else prob.logdensity_and_gradient_batch(Z)[0]

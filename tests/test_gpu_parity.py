@@ -567,10 +567,79 @@ def test_lowrank_logreg_gradient_matches_oracle(avi, ctx):
     obj.close(); prob.close()
 
 
+@pytest.mark.parametrize("D,r,M", [(6, 3, 8), (37, 5, 33), (130, 8, 64)])
+@pytest.mark.parametrize("ent", ["StickingTheLandingEntropy", "MonteCarloEntropy", "ClosedFormEntropyZeroGradient"])
+def test_lowrank_logq_entropies_match_oracle(avi, ctx, D, r, M, ent):
+    """RepGradELBO over the low-rank family with the entropy estimators that need log q(z) (entropy.jl:42-65) or drop the
+    entropy gradient (:13-15): w = Sigma^-1 (z - mu) through the r x r capacitance inverse, vs the oracle."""
+    mu_t, sg_t = np.linspace(-1, 1, D), np.linspace(0.5, 1.5, D)
+    prob, probo = avi.MvNormalDiag(ctx, mu_t, sg_t), Mo.NormalDiag(mu_t, sg_t)
+    q, qo = _lowrank_pair(avi, D, r)
+    obj = avi.Objective(KEY, avi.RepGradELBO(M, getattr(avi, ent)()), q, prob)
+    u1, u2 = _lowrank_draws(D, r, M)
+    v, g, e = obj.estimate_gradient(q.destructure())
+    vo, go, eo = O.repgrad_lowrank_value_and_gradient(qo.destructure(), qo, probo, u1, u2, entropy=ent)
+    assert abs(v - vo) <= 5e-5 * max(1.0, abs(vo)) and abs(e - eo) <= 5e-5 * max(1.0, abs(eo)), (v, vo)
+    assert relerr(g[:D], go[:D]) < 2e-4 and relerr(g[D:2 * D], go[D:2 * D]) < 2e-4 and relerr(g[2 * D:], go[2 * D:]) < 3e-4
+    # a second call: the step counter moves both Philox streams
+    v2, g2, _ = obj.estimate_gradient(q.destructure())
+    u1b, u2b = _lowrank_draws(D, r, M, step=1)
+    vo2, go2, _ = O.repgrad_lowrank_value_and_gradient(qo.destructure(), qo, probo, u1b, u2b, entropy=ent)
+    assert abs(v2 - vo2) <= 5e-5 * max(1.0, abs(vo2)) and relerr(g2, go2) < 3e-4
+    obj.close(); prob.close()
+
+
+@pytest.mark.parametrize("D,r,M", [(6, 3, 8), (37, 5, 33), (130, 8, 64)])
+def test_lowrank_scoregrad_matches_oracle(avi, ctx, D, r, M):
+    """ScoreGradELBO (VarGrad, scoregradelbo.jl:87-117) over the low-rank family vs the oracle."""
+    mu_t, sg_t = np.linspace(-1, 1, D), np.linspace(0.5, 1.5, D)
+    prob, probo = avi.MvNormalDiag(ctx, mu_t, sg_t), Mo.NormalDiag(mu_t, sg_t)
+    q, qo = _lowrank_pair(avi, D, r)
+    obj = avi.Objective(KEY, avi.ScoreGradELBO(M), q, prob)
+    u1, u2 = _lowrank_draws(D, r, M)
+    v, g, e = obj.estimate_gradient(q.destructure())
+    vo, go, eo = O.scoregrad_lowrank_value_and_gradient(qo.destructure(), qo, probo, u1, u2)
+    assert abs(v - vo) <= 2e-4 * max(1.0, abs(vo)) and abs(e - eo) <= 5e-5 * max(1.0, abs(eo)), (v, vo, e, eo)
+    assert relerr(g[:D], go[:D]) < 5e-4 and relerr(g[D:2 * D], go[D:2 * D]) < 5e-4 and relerr(g[2 * D:], go[2 * D:]) < 5e-4
+    obj.close(); prob.close()
+
+
+def test_lowrank_stl_logreg_and_fused_trajectory(avi, ctx):
+    """Sticking-the-landing over the low-rank family on the logistic-regression target (gradient from the tensor-core
+    kernels, fp32-grade) and 15 fused Adam + ClipScale iterations against the oracle loop."""
+    n, d, r, M, T = 200, 20, 4, 32, 15
+    X, y = Mo.synth_glm_data(n, d, seed=8)
+    D = d + 1
+    prob, probo = avi.LogReg(ctx, X, y, gemm="tf32x3"), Mo.LogReg(X, y)
+    q, qo = _lowrank_pair(avi, D, r)
+    ent = "StickingTheLandingEntropy"
+    obj = avi.Objective(KEY, avi.RepGradELBO(M, avi.StickingTheLandingEntropy()), q, prob)
+    v, g, e = obj.estimate_gradient(q.destructure())
+    u1, u2 = _lowrank_draws(D, r, M)
+    vo, go, eo = O.repgrad_lowrank_value_and_gradient(qo.destructure(), qo, probo, u1, u2, entropy=ent)
+    assert abs(v - vo) <= 5e-5 * abs(vo) and relerr(g, go) < 2e-4
+    obj.close()
+    alg = avi.KLMinRepGradDescent(optimizer=avi.Adam(1e-2), entropy=avi.StickingTheLandingEntropy(), n_samples=M,
+                                  operator=avi.ClipScale())
+    qa, info, state = avi.optimize(KEY, alg, T, prob, q)
+    rule, op, avg = Op.Adam(1e-2), Op.ClipScale(), Op.PolynomialAveraging()
+    st = Op.sgd_init(qo, rule, avg)
+
+    def grad_fn(params, t):
+        a1, a2 = _lowrank_draws(D, r, M, step=t - 1)
+        vv, gg, ee = O.repgrad_lowrank_value_and_gradient(params, qo, probo, a1, a2, entropy=ent)
+        return vv, gg, dict(elbo=ee)
+    elbos = [Op.sgd_step(st, qo, grad_fn, rule, op, avg)["elbo"] for _ in range(T)]
+    lam, lam_avg, _ = state.params()
+    assert np.allclose([i["elbo"] for i in info], elbos, rtol=5e-4, atol=5e-4)
+    assert relerr(lam, st.params) < 5e-4 and relerr(lam_avg, st.avg_st[0]) < 5e-4
+    state.close(); state.obj.close(); prob.close()
+
+
 def test_lowrank_fused_trajectory_and_unsupported_combinations(avi, ctx):
     """docs/src/families.md:185-190: LowRankGaussian(mu, ones, zeros(d, 3)) with KLMinRepGradDescent, Adam and
-    ClipScale: 20 fused iterations follow the fp64 oracle; everything outside RepGrad + ClosedFormEntropy is
-    reported as unsupported."""
+    ClipScale: 20 fused iterations follow the fp64 oracle; what the low-rank family does not implement (the STL
+    zero-gradient entropy / proximal algorithm, rank > 32, estimate_objective) is reported as unsupported."""
     D, r, M, T = 6, 3, 8, 20
     mu_t, sg_t = np.linspace(-1, 1, D), np.linspace(0.5, 1.5, D)
     prob, probo = avi.MvNormalDiag(ctx, mu_t, sg_t), Mo.NormalDiag(mu_t, sg_t)
@@ -590,13 +659,35 @@ def test_lowrank_fused_trajectory_and_unsupported_combinations(avi, ctx):
     assert relerr(lam, st.params) < 1e-4 and relerr(lam_avg, st.avg_st[0]) < 1e-4
     assert isinstance(qa, avi.MvLocationScaleLowRank) and qa.scale_factors.shape == (D, r)
     state.close(); state.obj.close()
-    for spec in (avi.ScoreGradELBO(M), avi.RepGradELBO(M, avi.StickingTheLandingEntropy())):
-        with pytest.raises(avi.AviError, match="low-rank"):
-            avi.Objective(KEY, spec, q, prob)
+    with pytest.raises(avi.AviError, match="low-rank"):
+        avi.Objective(KEY, avi.RepGradELBO(M, avi.StickingTheLandingEntropyZeroGradient()), q, prob)
     with pytest.raises(avi.AviError, match="rank"):
         avi.Objective(KEY, avi.RepGradELBO(M), avi.LowRankGaussian(q.location, q.scale_diag, np.zeros((D, 33), np.float32)), prob)
-    with pytest.raises(avi.AviError, match="low-rank"):      # (its zero-gradient entropy is rejected first)
+    with pytest.raises(avi.AviError, match="MvLocationScale only"):      # the proximal operator has no low-rank form
         avi.optimize(KEY, avi.KLMinRepGradProxDescent(optimizer=avi.DoWG(), n_samples=M), 1, prob, q)
-    with pytest.raises(avi.AviError, match="low-rank"):
-        avi.estimate_objective(KEY, alg, q, prob, n_samples=16)
+    prob.close()
+
+
+@pytest.mark.parametrize("D,r", [(6, 3), (37, 5)])
+def test_lowrank_estimate_objective_matches_oracle(avi, ctx, D, r):
+    """estimate_objective (repgradelbo.jl:112-122, scoregradelbo.jl:58-65, common.jl:29-38) over the low-rank family,
+    away from q = pi: closed-form entropy from the capacitance matrix, Monte-Carlo entropy from log q(z) through it."""
+    mu_t, sg_t = np.linspace(-1, 1, D), np.linspace(0.5, 1.5, D)
+    prob, probo = avi.MvNormalDiag(ctx, mu_t, sg_t), Mo.NormalDiag(mu_t, sg_t)
+    q, qo = _lowrank_pair(avi, D, r)
+    n = 61
+    u1, u2 = P.normal_matrix(KEY, 0, D, n), P.normal_matrix(KEY, 0, r, n, stream=P.STREAM_EPS_FACTORS)
+    Z = qo.rand_from_eps(u1, u2)
+    energy = float(np.mean(probo.logdensity_and_gradient_batch(Z)[0]))
+    want_closed, want_mc = -(energy + qo.entropy()), -(energy - float(np.mean(qo.logpdf(Z))))
+    assert abs(want_closed) > 1.0 and abs(want_mc) > 1.0
+    for ent, want in (("ClosedFormEntropy", want_closed), ("ClosedFormEntropyZeroGradient", want_closed),
+                      ("MonteCarloEntropy", want_mc), ("StickingTheLandingEntropy", want_mc)):
+        got = avi.estimate_objective(KEY, avi.RepGradELBO(n, getattr(avi, ent)()), q, prob)
+        assert abs(got - want) <= 3e-5 * abs(want), (ent, got, want)
+    got = avi.estimate_objective(KEY, avi.ScoreGradELBO(n), q, prob)
+    assert abs(got - want_mc) <= 3e-5 * abs(want_mc)
+    alg = avi.KLMinRepGradDescent(n_samples=3)          # algorithm level: RepGradELBO + MonteCarloEntropy, caller's n_samples
+    got = avi.estimate_objective(KEY, alg, q, prob, n_samples=n)
+    assert abs(got - want_mc) <= 3e-5 * abs(want_mc)
     prob.close()
