@@ -28,6 +28,13 @@ for fused in (2, 0):                       # whole-iteration kernel, then one ke
     alg = avi.KLMinScoreGradDescent(optimizer=avi.DoG(1e-2), n_samples=M, operator=avi.ClipScale())
     _, info, st = avi.optimize(3, alg, 3, prob, avi.MeanFieldGaussian(np.zeros(D, np.float32), np.full(D, 0.3, np.float32)))
     st.close(); st.obj.close(); prob.close()
+# low-rank family: log q based estimators through the capacitance matrix
+probn = avi.MvNormalDiag(ctx, np.linspace(-1, 1, D), np.linspace(0.5, 1.5, D))
+ql = avi.LowRankGaussian(np.zeros(D, np.float32), np.full(D, 0.7, np.float32), (0.1 * rng.standard_normal((D, 5))).astype(np.float32))
+for spec in (avi.RepGradELBO(M, avi.StickingTheLandingEntropy()), avi.RepGradELBO(M, avi.MonteCarloEntropy()), avi.ScoreGradELBO(M)):
+    o = avi.Objective(3, spec, ql, probn); o.estimate_gradient(ql.destructure()); o.close()
+avi.estimate_objective(3, avi.RepGradELBO(M, avi.MonteCarloEntropy()), ql, probn)
+probn.close()
 print("sanitize case ok")
 PY
 for t in $TOOLS; do
