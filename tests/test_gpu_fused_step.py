@@ -352,3 +352,25 @@ def test_first_call_on_fresh_buffers_equals_repeats(avi, ctx):
             again = obj.estimate_gradient(lam)
             assert again[0] == first[0] and np.array_equal(again[1], g_first)
         obj.close(); prob.close()
+
+
+@pytest.mark.parametrize("n,d,M", [(1, 1, 1), (33, 1, 2), (5, 130, 1), (2, 3, 257), (4100, 2, 5)])
+@pytest.mark.parametrize("gemm,tol_v,tol_g", [("tf32", 5e-4, 2e-3), ("tf32x3", 1e-5, 5e-5)])
+def test_fused_degenerate_shapes(avi, ctx, n, d, M, gemm, tol_v, tol_g):
+    """One data row, one feature, one sample, more samples than rows: the single kernel must neither hang nor lose a
+    unit when most CTAs have no work in a phase (estimate_gradient! vs the oracle, then a few optimiser steps)."""
+    rng = np.random.default_rng(n + d)
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    y = (rng.random(n) < 0.5).astype(np.float32)
+    D = d + 1
+    prob = avi.LogReg(ctx, X, y, gemm=gemm)
+    prob.set_fused_step(2)
+    q, qo = make_q(avi, D)
+    obj = avi.Objective(KEY, avi.RepGradELBO(M), q, prob)
+    v, g, e = obj.estimate_gradient(q.destructure())
+    vo, go, eo = O.repgrad_value_and_gradient(qo.destructure(), qo, Mo.LogReg(X, y), P.normal_matrix(KEY, 0, D, M), "ClosedFormEntropy")
+    assert abs(v - vo) <= tol_v * abs(vo) and relerr(g, go) < tol_g
+    alg = avi.KLMinRepGradDescent(optimizer=avi.Adam(1e-2), n_samples=M, operator=avi.ClipScale())
+    _, info, st = avi.optimize(KEY, alg, 9, prob, q)
+    assert len(info) == 9 and all(np.isfinite(i["elbo"]) for i in info)
+    st.close(); st.obj.close(); obj.close(); prob.close()
