@@ -30,8 +30,11 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1,
 
 // uint32 -> (0,1), exactly representable in fp32 (oracle/philox.py: uniform23): (v + 0.5) * 2^-23 has 24
 // significant bits, so the single fma is exact
+// Computed WITHOUT an int -> float conversion: I2FP runs on the XU pipe next to the MUFU ops, and that pipe is what
+// bounds the sampler (ncu: 87 % busy, 12 XU ops per Philox quad of which 4 were conversions).  1 + v 2^-23 is the float
+// with mantissa bits v; subtracting 1 - 2^-24 (the largest float below 1) leaves v 2^-23 + 2^-24 exactly.
 __device__ __forceinline__ float uniform23(uint32_t x) {
-    return fmaf((float)(x >> 9), 1.1920928955078125e-07f, 5.9604644775390625e-08f);
+    return __uint_as_float(0x3f800000u | (x >> 9)) - 0.99999994f;
 }
 
 // Box-Muller pair from two Philox words, on the SFU pipes (MUFU lg2 / sqrt / sin / cos) and branch-free so
@@ -54,8 +57,12 @@ __device__ __forceinline__ void box_muller_fast(uint32_t x0, uint32_t x1, float&
     const float a = u0 > 0.96875f ? a_series : a_lg2;   // -2 ln u0 > 0
     float r;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
-    const float th = fmaf((float)((int32_t)x1 >> 9), 6.283185307179586f * 1.1920928955078125e-07f,
-                          6.283185307179586f * 5.9604644775390625e-08f);
+    // (float)((int32_t)x1 >> 9) without I2FP (see uniform23): the signed 23-bit value vs plus 2^22 is the unsigned field
+    // with its top bit flipped; 2^23 + that is a float by construction, and 2^23 + 2^22 subtracts exactly.
+    // (sin / cos as quadrant + Taylor polynomials on the FMA pipe instead of MUFU -- 1.3e-7 max error -- made the sampler
+    // SLOWER, 69 vs 56 us at M = 32768: it is bound by instruction issue along its dependency chains, not by the XU pipe.)
+    const float vsf = __uint_as_float(0x4b000000u | ((x1 >> 9) ^ 0x400000u)) - 12582912.0f;
+    const float th = fmaf(vsf, 6.283185307179586f * 1.1920928955078125e-07f, 6.283185307179586f * 5.9604644775390625e-08f);
     n0 = r * __cosf(th);
     n1 = r * __sinf(th);
 }
