@@ -152,6 +152,9 @@ struct SampleHook {
     unsigned long long* zt_owner = nullptr;   // cleared by whoever rewrites the target's sample-derived buffers (step_fused.cu)
     const void* pf_ptr = nullptr;         // static operand of the next kernel to pull into L2 meanwhile (may be null)
     unsigned long long pf_bytes = 0;
+    // full-rank sampler: also write the 3xTF32 split of eps, rows [hi | lo | hi] in segments of er_seg (family_fr.cu)
+    float* Er3 = nullptr;
+    int er_seg = 0;
 };
 
 struct FusedStepArgs;   // step_fused.cuh
@@ -214,6 +217,20 @@ enum { ACC_NSCAL = 8 };
 struct FrWork {
     float *Lr3 = nullptr, *Er3 = nullptr, *Et3 = nullptr, *Wt3 = nullptr, *Ut3 = nullptr, *zslab = nullptr;
     size_t Lr3_cap = 0, Er3_cap = 0, Et3_cap = 0, Wt3_cap = 0, Ut3_cap = 0, zslab_cap = 0;
+    // true while the optimiser loop's update kernel rewrites Lr3 together with lambda (opt.cu: k_fr_update_t), so the
+    // sampling stage does not transpose + split L itself
+    bool Lr3_maintained = false;
+    const void* Lr3_owner = nullptr;   // the optimiser whose update kernel last wrote Lr3 (nullptr: anyone else did)
+    int64_t Lr3_version = -1;          // ... and the avi_opt::lam_version it corresponds to
+};
+
+// what k_fr_outer_prep needs to finish the location block and the value slot in the same launch (family_fr.cu)
+struct FrPrepFinalize {
+    int on = 0;
+    const float* lambda = nullptr;
+    int M = 0, objective = 0, entropy = 0, Mloc = 0, accv = 0;
+    float *grad = nullptr, *out = nullptr;
+    const float *logp = nullptr, *esq = nullptr;
 };
 
 struct avi_obj {
@@ -250,6 +267,7 @@ struct avi_obj {
     float* grad = nullptr;       // P
     float* out = nullptr;        // 4 : value, elbo, logdet, ScoreGrad centring shift
     FrWork fr;
+    bool fr_vec_done = false;    // the local phase already produced grad[0 .. D) and out[0 .. 3) (full-rank, see family.cu)
     // pinned host staging
     float* h_lambda = nullptr;   // P
     float* h_grad = nullptr;     // P + 8: gradient | value, elbo, logdet, shift | completion flag (u32)
@@ -276,6 +294,8 @@ struct avi_opt {
     float* avg = nullptr;    // P averaged iterate
     float* sc = nullptr;     // 16 scalars: see opt.cu
     float* norm_part = nullptr;   // per-CTA partial norms (DoG/DoWG)
+    unsigned int* ticket = nullptr;   // last-CTA election of the tiled full-rank update (always left at 0)
+    int64_t lam_version = 0;      // host-side count of everything that rewrote lam (iterations enqueued, state imports)
     float* trace = nullptr;       // 2 * trace_cap (value, elbo) per iteration of one call
     int trace_cap = 0;
     float* h_trace = nullptr;     // pinned
@@ -350,8 +370,12 @@ int32_t avi_trsm_lt(avi_ctx* ctx, const float* L, int D, const float* E, float* 
 
 // full-rank family on the tensor cores (family_fr.cu)
 bool avi_fr_tc_ok(const avi_obj* o, int Mloc);
-int32_t avi_fr_affine_tc(avi_obj* o, const float* lambda, const float* E, float* Z, int Mloc);
-int32_t avi_fr_outer_tc(avi_obj* o, const float* W, const float* E, float* C, int Mloc, int which, bool reuse_E);
+int32_t avi_fr_affine_prepare(avi_obj* o, int Mloc, float** Er3, int* seg);
+int32_t avi_fr_refresh_split(avi_obj* o, const float* lambda);   // Lr3 = transposed 3xTF32 split of L(lambda)
+int32_t avi_fr_affine_tc(avi_obj* o, const float* lambda, const float* E, float* Z, int Mloc, bool er3_done = false,
+                         const SampleHook* hook = nullptr);
+int32_t avi_fr_outer_tc(avi_obj* o, const float* W, const float* E, float* C, int Mloc, int which, bool reuse_E,
+                        float* colsum = nullptr, const FrPrepFinalize* pf = nullptr);
 void avi_fr_free(avi_obj* o);
 
 // models

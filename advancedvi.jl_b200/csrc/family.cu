@@ -66,9 +66,18 @@ k_sample(const float* __restrict__ lambda, int D, int ld, int m0, int Mloc, cons
         float part = 0.0f, bsq = 0.0f, eta = 0.0f;
         float* Erow = E ? E + (size_t)m * ld : nullptr;   // (mean-field forward-only callers do not need eps: E == nullptr)
         float* Zrow = FULLRANK ? nullptr : Z + (size_t)m * ld;
-        for (int q = SPLIT == 1 ? lane : threadIdx.x; q < ld / 4; q += 32 * SPLIT) {
-            const float4 e = normal4((uint32_t)q, (uint32_t)(m0 + m), c2, c3, pk);
+        float* Er3row = FULLRANK && hk.Er3 ? hk.Er3 + (size_t)m * 3 * hk.er_seg : nullptr;
+        const int qend = (Er3row && hk.er_seg > ld ? hk.er_seg : ld) / 4;
+        for (int q = SPLIT == 1 ? lane : threadIdx.x; q < qend; q += 32 * SPLIT) {
             const int i = 4 * q;
+            if (FULLRANK && i >= ld) {   // zero tail of the split rows beyond the sample buffers' pitch
+                const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                *reinterpret_cast<float4*>(Er3row + i) = z4;
+                *reinterpret_cast<float4*>(Er3row + hk.er_seg + i) = z4;
+                *reinterpret_cast<float4*>(Er3row + 2 * hk.er_seg + i) = z4;
+                continue;
+            }
+            const float4 e = normal4((uint32_t)q, (uint32_t)(m0 + m), c2, c3, pk);
             float ev[4] = {e.x, e.y, e.z, e.w}, zv[4] = {0.f, 0.f, 0.f, 0.f}, zt[4];
             if (i + 3 >= D) {   // the row's last quad: zero the padding columns
 #pragma unroll
@@ -106,6 +115,14 @@ k_sample(const float* __restrict__ lambda, int D, int ld, int m0, int Mloc, cons
                 }
             }
             if (FULLRANK || Erow) *reinterpret_cast<float4*>(Erow + i) = make_float4(ev[0], ev[1], ev[2], ev[3]);
+            if (FULLRANK && Er3row) {   // B-operand pattern of the 3xTF32 contraction Z = L * eps: [hi | lo | hi]
+                float hi[4], lo[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { hi[c] = tc::round_tf32(ev[c]); lo[c] = tc::round_tf32(ev[c] - hi[c]); }
+                *reinterpret_cast<float4*>(Er3row + i) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<float4*>(Er3row + hk.er_seg + i) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                *reinterpret_cast<float4*>(Er3row + 2 * hk.er_seg + i) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            }
             if (!FULLRANK) *reinterpret_cast<float4*>(Zrow + i) = make_float4(zv[0], zv[1], zv[2], zv[3]);
             if (HOOK && hk.Zt) {
                 float hi[4], lo[4];
@@ -312,34 +329,10 @@ __global__ void k_finalize_fr_mat(const float* __restrict__ C1, const float* __r
 
 __global__ void __launch_bounds__(1024)
 k_finalize_fr_vec(const float* __restrict__ acc, int accv, const float* __restrict__ lambda, int D, int M,
-                  int objective, int entropy, float* __restrict__ grad, float* __restrict__ out) {
+                  int objective, int entropy, float* __restrict__ grad, float* __restrict__ out,
+                  const float* __restrict__ logp, const float* __restrict__ esq, int Mloc, int deferred) {
     __shared__ float sm[33];
-    float part = 0.f;
-    for (int i = threadIdx.x; i < D; i += blockDim.x) part += logf(__ldg(lambda + D + (size_t)i * (D + 1)));
-    const float logdet = block_sum(part, sm);
-    const float* scal = acc + 4 * (size_t)accv;
-    const float invM = 1.0f / (float)M;
-    if (objective == AVI_REPGRAD) {
-        for (int i = threadIdx.x; i < D; i += blockDim.x) grad[i] = -acc[i] * invM;
-        if (threadIdx.x == 0) {
-            float ent = (entropy == AVI_ENT_CLOSEDFORM || entropy == AVI_ENT_CLOSEDFORM_ZEROGRAD)
-                            ? (float)D * AVI_H0 + logdet
-                            : 0.5f * scal[1] * invM + 0.5f * (float)D * AVI_LOG2PI + logdet;
-            float value = -(scal[0] * invM + ent);
-            out[0] = value; out[1] = -value; out[2] = logdet;
-        }
-    } else {
-        const float fbar = scal[2] * invM;
-        const float* v2 = acc + 2 * (size_t)accv;
-        for (int i = threadIdx.x; i < D; i += blockDim.x) grad[i] = (acc[i] - fbar * v2[i]) * invM;
-        if (threadIdx.x == 0) {
-            float shift = out[3];
-            out[0] = 0.5f * (scal[3] * invM - fbar * fbar);
-            out[1] = -(fbar + shift);
-            out[2] = logdet;
-            out[3] = fbar + shift;
-        }
-    }
+    fr_vec_finalize(acc, accv, lambda, D, M, objective, entropy, grad, out, logp, esq, Mloc, deferred != 0, true, sm);
 }
 
 __global__ void k_advance(ObjDeviceState* st) { st->step += 1ull; }
@@ -409,11 +402,14 @@ int32_t avi_family_sample(avi_obj* o, const float* lambda, float* Z, float* E, f
         AVI_LAUNCHED(ctx);
         AVI_CHECK(avi_lr_affine(o, lambda, E, o->E2, Z, Mloc));
     } else {
-        LAUNCH_SAMPLE(true, false, SampleHook{});
-        AVI_LAUNCHED(ctx);
         // Z[m][i] = mu[i] + sum_{j <= i} E[m][j] * L[i + D*j]  (scale * eps, location_scale.jl:76)
-        if (avi_fr_tc_ok(o, Mloc)) {
-            AVI_CHECK(avi_fr_affine_tc(o, lambda, E, Z, Mloc));
+        const bool tc = avi_fr_tc_ok(o, Mloc);
+        SampleHook fh{};   // (kind 0: only the split-eps fields are read by the full-rank sampler)
+        if (tc) AVI_CHECK(avi_fr_affine_prepare(o, Mloc, &fh.Er3, &fh.er_seg));
+        LAUNCH_SAMPLE(true, false, fh);
+        AVI_LAUNCHED(ctx);
+        if (tc) {
+            AVI_CHECK(avi_fr_affine_tc(o, lambda, E, Z, Mloc, /*er3_done=*/true, hook));
         } else {   // very large forward-only batches (estimate_objective): exact-fp32 SIMT contraction
             AVI_CHECK(avi_gemm_simt(ctx, E, o->ld, 1, lambda + o->D, 1, o->D, Z, o->ld, 1, Mloc, o->D, o->D, 1.0f, 1));
             k_fr_add_mu<<<Mloc, 256, 0, ctx->stream>>>(lambda, o->D, o->ld, Z);
@@ -427,7 +423,7 @@ int32_t avi_family_sample(avi_obj* o, const float* lambda, float* Z, float* E, f
 // Mean-field RepGrad without a sample-sharded exchange: sum logp / sum |eps|^2 feed only the value slot,
 // so the finalize kernel takes them from the per-sample vectors itself (one launch less per step).
 bool avi_obj_defers_scalars(const avi_obj* o) {
-    return o->family == AVI_MEANFIELD && o->objective == AVI_REPGRAD && o->Mloc > 0 &&
+    return (o->family == AVI_MEANFIELD || o->family == AVI_FULLRANK) && o->objective == AVI_REPGRAD && o->Mloc > 0 &&
            !(o->shard_axis == AVI_SHARD_SAMPLES && o->ctx->nranks > 1);
 }
 
@@ -475,7 +471,9 @@ int32_t avi_objective_local(avi_obj* o, const float* lambda) {
         return AVI_OK;
     }
     SampleHook hook;
-    const bool hooked = o->family == AVI_MEANFIELD && o->model->sample_hook(o->Z, ld, Mloc, &hook);
+    // (the full-rank family runs the hook in the kernel that finishes z = L eps + mu: family_fr.cu)
+    const bool hooked = (o->family == AVI_MEANFIELD || (o->family == AVI_FULLRANK && avi_fr_tc_ok(o, Mloc))) &&
+                        o->model->sample_hook(o->Z, ld, Mloc, &hook);
     {
         const int32_t rc_s = avi_family_sample(o, lambda, o->Z, o->E, o->esq, Mloc, o->m0, o->d_state, nullptr, hooked ? &hook : nullptr);
         if (rc_s != AVI_OK) { o->model->clear_hook(); return rc_s; }
@@ -536,12 +534,23 @@ int32_t avi_objective_local(avi_obj* o, const float* lambda) {
             k_fr_make_w<<<Mloc, 256, 0, ctx->stream>>>(o->G, o->U, o->fbuf, ld, Mloc, rep ? 0 : 1, o->G);
             AVI_LAUNCHED(ctx);
         }
-        k_colsum<<<(unsigned)ceil_div(D, 32), dim3(32, 32), 0, ctx->stream>>>(W, ld, Mloc, D, o->acc);
-        AVI_LAUNCHED(ctx);
-        // C1[j*D + i] = sum_m W[m][i] * E[m][j]: contraction over the samples
+        // C1[j*D + i] = sum_m W[m][i] * E[m][j]: contraction over the samples.  On the tensor-core path the launch that
+        // transposes and splits W and eps also takes the column sums of W and -- RepGrad without a sample-shard
+        // exchange in between -- finishes the location block and the value slot (o->fr_vec_done)
         const bool tc_ok = avi_fr_tc_ok(o, Mloc);
-        if (tc_ok) AVI_CHECK(avi_fr_outer_tc(o, W, o->E, C1, Mloc, 0, false));
-        else AVI_CHECK(avi_gemm_simt(ctx, o->E, 1, ld, W, 1, ld, C1, D, 1, D, D, Mloc, 1.0f));
+        FrPrepFinalize pf{};
+        if (tc_ok && avi_obj_defers_scalars(o)) {
+            pf.on = 1; pf.lambda = lambda; pf.M = o->M; pf.objective = o->objective; pf.entropy = o->entropy;
+            pf.grad = o->grad; pf.out = o->out; pf.logp = o->logp; pf.esq = o->esq; pf.Mloc = Mloc; pf.accv = accv;
+        }
+        if (!tc_ok) {
+            k_colsum<<<(unsigned)ceil_div(D, 32), dim3(32, 32), 0, ctx->stream>>>(W, ld, Mloc, D, o->acc);
+            AVI_LAUNCHED(ctx);
+            AVI_CHECK(avi_gemm_simt(ctx, o->E, 1, ld, W, 1, ld, C1, D, 1, D, D, Mloc, 1.0f));
+        } else {
+            AVI_CHECK(avi_fr_outer_tc(o, W, o->E, C1, Mloc, 0, false, o->acc, &pf));
+            o->fr_vec_done = pf.on != 0;
+        }
         if (!rep) {
             k_colsum<<<(unsigned)ceil_div(D, 32), dim3(32, 32), 0, ctx->stream>>>(o->U, ld, Mloc, D,
                                                                                   o->acc + 2 * (size_t)accv);
@@ -629,8 +638,14 @@ int32_t avi_objective_finalize(avi_obj* o, const float* lambda, float* grad, flo
                                                                                   o->objective, o->entropy, grad);
             AVI_LAUNCHED(ctx);
         }
-        k_finalize_fr_vec<<<1, 1024, 0, ctx->stream>>>(o->acc, accv, lambda, D, o->M, o->objective, o->entropy, grad, out);
-        AVI_LAUNCHED(ctx);
+        // (already done by the pullback's preparation launch when the local phase could: avi_objective_local)
+        const bool done = o->fr_vec_done && grad == o->grad && out == o->out;
+        o->fr_vec_done = false;
+        if (!done) {
+            k_finalize_fr_vec<<<1, 1024, 0, ctx->stream>>>(o->acc, accv, lambda, D, o->M, o->objective, o->entropy, grad, out,
+                                                           o->logp, o->esq, o->Mloc, avi_obj_defers_scalars(o) ? 1 : 0);
+            AVI_LAUNCHED(ctx);
+        }
     }
     return AVI_OK;
 }

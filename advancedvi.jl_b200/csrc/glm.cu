@@ -135,25 +135,40 @@ k_glm_post_sums(const float* __restrict__ Z, const float* __restrict__ E, int ld
 }
 
 // full gradient tail: G[m][i] = sum_s slab[s][m][i] - beta_i / sigma^2, G[m][d] = dlogp/deta, logp[m].
-// One CTA per sample, a thread per coordinate quad: the nslab partial sums are fetched as independent 16-byte
-// loads (ld % 4 == 0 and every buffer is 16-byte aligned).
-__global__ void __launch_bounds__(256)
+// One CTA per sample, a thread per coordinate quad (the launch brings ld / 4 threads rounded up to whole warps, so no
+// thread walks a second quad): the partial sums are fetched in batches of POST_BATCH independent 16-byte loads (ld % 4
+// == 0 and every buffer is 16-byte aligned) and added in slab order -- the kernel is a chain of L2 round trips, so the
+// number of batches is its duration.  The LAST warp assembles logp[m] first (its loads are in flight before the slabs').
+constexpr int POST_BATCH = 12;
+__global__ void __launch_bounds__(512)
 k_glm_post_full(const float* __restrict__ Z, int ld, int d, const float4* __restrict__ pre,
                 const float* __restrict__ slabs, int nslab, long long slab_stride,
                 const float* __restrict__ llpart, int nparts, int ldpart, float w, float* __restrict__ G,
                 float* __restrict__ logp) {
     const int m = blockIdx.x;
     const float4 pm = pre[m];
+    if (threadIdx.x >= blockDim.x - 32) {   // fixed shuffle tree over the partial log-likelihood sums
+        const int lane = threadIdx.x & 31;
+        float s = 0.f;
+#pragma unroll 4
+        for (int q = lane; q < nparts; q += 32) s += llpart[(size_t)q * ldpart + m];
+        s = warp_sum(s);
+        if (lane == 0) logp[m] = fmaf(w, s, pm.x);
+    }
     if (G) {
         for (int q = threadIdx.x; q < ld / 4; q += blockDim.x) {
             const size_t base = (size_t)m * ld + 4 * q;
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 6
-            for (int s = 0; s < nslab; ++s) {
-                const float4 v = *reinterpret_cast<const float4*>(slabs + (size_t)s * slab_stride + base);
-                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-            }
             const float4 z = *reinterpret_cast<const float4*>(Z + base);
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int s0 = 0; s0 < nslab; s0 += POST_BATCH) {
+                float4 v[POST_BATCH];
+#pragma unroll
+                for (int u = 0; u < POST_BATCH; ++u)
+                    v[u] = *reinterpret_cast<const float4*>(slabs + (size_t)min(s0 + u, nslab - 1) * slab_stride + base);   // (unconditional: batched)
+#pragma unroll
+                for (int u = 0; u < POST_BATCH; ++u)
+                    if (s0 + u < nslab) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+            }
             float gv[4] = {acc.x, acc.y, acc.z, acc.w};
             const float zv[4] = {z.x, z.y, z.z, z.w};
 #pragma unroll
@@ -163,12 +178,6 @@ k_glm_post_full(const float* __restrict__ Z, int ld, int d, const float4* __rest
             }
             *reinterpret_cast<float4*>(G + base) = make_float4(gv[0], gv[1], gv[2], gv[3]);
         }
-    }
-    if (threadIdx.x < 32) {   // fixed shuffle tree over the partial log-likelihood sums
-        float s = 0.f;
-        for (int q = threadIdx.x; q < nparts; q += 32) s += llpart[(size_t)q * ldpart + m];
-        s = warp_sum(s);
-        if (threadIdx.x == 0) logp[m] = fmaf(w, s, pm.x);
     }
 }
 
@@ -409,7 +418,8 @@ struct Glm : avi_model {
                 sl = slabs; nslab = p.n_ksplit;
             }
         }
-        k_glm_post_full<<<M, 256, 0, ctx->stream>>>(Z, ld, d, pre, sl, nslab, sstride, llpart, nparts, capM, w, G, logp);
+        k_glm_post_full<<<M, (unsigned)std::min<int64_t>(512, round_up(ld / 4, 32)), 0, ctx->stream>>>(Z, ld, d, pre, sl, nslab, sstride,
+                                                                                                    llpart, nparts, capM, w, G, logp);
         AVI_LAUNCHED(ctx);
         return AVI_OK;
     }

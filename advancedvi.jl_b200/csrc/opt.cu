@@ -181,9 +181,10 @@ k_fr_update(float* __restrict__ lam, float* __restrict__ grad, float* __restrict
     }
 }
 
-__global__ void k_commit(float* __restrict__ sc, const float* __restrict__ out, ObjDeviceState* __restrict__ st,
-                         float* __restrict__ trace, int trace_cap, const float* __restrict__ norm_part, UpdArgs a) {
-    if (threadIdx.x != 0) return;
+// scalar state, trace entry, step counter: what remains of an iteration once every parameter entry is updated
+__device__ __forceinline__ void commit_body(float* __restrict__ sc, const float* __restrict__ out,
+                                            ObjDeviceState* __restrict__ st, float* __restrict__ trace, int trace_cap,
+                                            const float* __restrict__ norm_part, const UpdArgs& a) {
     const float value = out[0];
     if (st->halted) return;
     int tp = st->trace_pos;
@@ -206,6 +207,136 @@ __global__ void k_commit(float* __restrict__ sc, const float* __restrict__ out, 
     st->batch_cursor += 1;
 }
 
+__global__ void k_commit(float* __restrict__ sc, const float* __restrict__ out, ObjDeviceState* __restrict__ st,
+                         float* __restrict__ trace, int trace_cap, const float* __restrict__ norm_part, UpdArgs a) {
+    if (threadIdx.x != 0) return;
+    commit_body(sc, out, st, trace, trace_cap, norm_part, a);
+}
+
+// Full-rank update, tiled: CTA = FRU_ROWS rows x 32 columns of L (entries on or below the diagonal only), a warp-wide
+// access runs along a column (contiguous in the column-major layout).  On top of k_fr_update's arithmetic it
+//   * rewrites the tile of Lr3 -- the transposed 3xTF32 split of L that the NEXT iteration's z = L eps contraction reads
+//     as its A operand (family_fr.cu) -- through a shared-memory transpose, so the sampling stage needs no
+//     transpose-and-split pass over the D x D matrix of its own;
+//   * commits the scalar state in the last CTA to finish (ticket), instead of a k_commit launch: every CTA has read the
+//     old scalars before it takes its ticket.
+// The trailing CTAs (blockIdx.x >= ntc * ntr) update the location block.
+constexpr int FRU_ROWS = 64;
+__global__ void __launch_bounds__(256)
+k_fr_update_t(float* __restrict__ lam, float* __restrict__ grad, float* __restrict__ m1, float* __restrict__ m2,
+              float* __restrict__ avg, float* __restrict__ sc, const float* __restrict__ out,
+              ObjDeviceState* __restrict__ st, const float* __restrict__ C1, const float* __restrict__ C2,
+              const float* __restrict__ scal, int M, int objective, int entropy, UpdArgs a, int ntc, int ntr,
+              float* __restrict__ Lr3, int seg, unsigned int* __restrict__ ticket, float* __restrict__ trace,
+              int trace_cap) {
+    __shared__ float tile[FRU_ROWS / 32][32][33];
+    const int D = a.D;
+    const bool live = !(st->halted || !isfinite(out[0]));
+    const float eta = a.rule == AVI_RULE_DESCENT ? a.h0 : 0.f;
+    const float b1t = sc[SC_B1T], b2t = sc[SC_B2T], w = (a.avg_param + 1.0f) / (sc[SC_T] + a.avg_param);
+    const float bc1 = 1.0f / (1.0f - b1t), bc2 = 1.0f / (1.0f - b2t);   // Adam bias corrections as reciprocals
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int tile_id = blockIdx.x;
+    const bool adam = a.rule == AVI_RULE_ADAM, poly = a.averager == AVI_AVG_POLYNOMIAL;
+    // one parameter entry of Optimisers.update! + operator + averager on register values (k_fr_update's arithmetic)
+    auto entry = [&](float x, float g, float& mt, float& vt, float& av, bool diag) -> float {
+        float dx;
+        if (adam) {
+            mt = a.h1 * mt + (1.0f - a.h1) * g;
+            vt = a.h2 * vt + (1.0f - a.h2) * g * g;
+            dx = __fdividef(mt * bc1, sqrtf(vt * bc2) + a.h3) * a.h0;
+        } else {
+            dx = eta * g;
+        }
+        x -= dx;
+        if (a.op != AVI_OP_IDENTITY && diag) {   // diagonal of the scale
+            if (a.op == AVI_OP_CLIPSCALE) x = fmaxf(x, a.op_param);
+            else x = x + (sqrtf(fmaf(x, x, 4.0f * eta)) - x) * 0.5f;
+        }
+        if (poly) av = (1.0f - w) * av + w * x;
+        return x;
+    };
+    if (live) {
+        if (tile_id >= ntc * ntr) {   // location block (gradient written by the finalize stage)
+            const int i = (tile_id - ntc * ntr) * 256 + (int)threadIdx.x;
+            if (i < D) {
+                float mt = adam ? m1[i] : 0.f, vt = adam ? m2[i] : 0.f, av = poly ? avg[i] : 0.f;
+                const float x = entry(lam[i], grad[i], mt, vt, av, false);
+                lam[i] = x;
+                if (adam) { m1[i] = mt; m2[i] = vt; }
+                if (poly) avg[i] = av;
+            }
+        } else {
+            const int j0 = (tile_id % ntc) * 32, i0 = (tile_id / ntc) * FRU_ROWS;
+            if (i0 + FRU_ROWS > j0) {   // (tiles entirely above the diagonal hold nothing)
+                // every load of the thread's 8 entries is issued before the first dependent instruction: the kernel
+                // is a stream over 36 bytes per entry and its duration is the number of exposed memory round trips
+                constexpr int NE = (FRU_ROWS / 32) * 4;
+                float x[NE], mt[NE], vt[NE], av[NE], c1[NE], c2[NE];
+                bool ok[NE];
+#pragma unroll
+                for (int e = 0; e < NE; ++e) {
+                    const int i = i0 + (e >> 2) * 32 + tx, j = j0 + ty * 4 + (e & 3);
+                    ok[e] = i < D && j < D && i >= j;
+                    const size_t idx = ok[e] ? (size_t)j * D + i : 0;
+                    const size_t p = (size_t)D + idx;
+                    x[e] = ok[e] ? lam[p] : 0.f;
+                    c1[e] = ok[e] ? C1[idx] : 0.f;
+                    c2[e] = ok[e] && objective != AVI_REPGRAD ? C2[idx] : 0.f;
+                    mt[e] = ok[e] && adam ? m1[p] : 0.f;
+                    vt[e] = ok[e] && adam ? m2[p] : 0.f;
+                    av[e] = ok[e] && poly ? avg[p] : 0.f;
+                }
+                float g[NE];
+#pragma unroll
+                for (int e = 0; e < NE; ++e) {
+                    const int i = i0 + (e >> 2) * 32 + tx, j = j0 + ty * 4 + (e & 3);
+                    g[e] = fr_grad_value(c1[e], c2[e], scal, x[e], i == j, M, objective, entropy);
+                    if (ok[e]) x[e] = entry(x[e], g[e], mt[e], vt[e], av[e], i == j);
+                }
+#pragma unroll
+                for (int e = 0; e < NE; ++e) {
+                    const int i = i0 + (e >> 2) * 32 + tx, j = j0 + ty * 4 + (e & 3);
+                    if (ok[e]) {
+                        const size_t p = (size_t)D + (size_t)j * D + i;
+                        grad[p] = g[e];
+                        lam[p] = x[e];
+                        if (adam) { m1[p] = mt[e]; m2[p] = vt[e]; }
+                        if (poly) avg[p] = av[e];
+                    }
+                }
+                if (Lr3) {
+#pragma unroll
+                    for (int e = 0; e < NE; ++e) tile[e >> 2][ty * 4 + (e & 3)][tx] = x[e];
+                    __syncthreads();
+                    // row i of Lr3 holds [hi | hi | lo] of L(i, .) in segments of seg: 32 consecutive columns per warp store
+#pragma unroll
+                    for (int r = ty; r < FRU_ROWS; r += 8) {
+                        const int i = i0 + r, j = j0 + tx;
+                        if (i < D && j < D && i >= j) {
+                            const float xv = tile[r >> 5][tx][r & 31];
+                            const float hi = tc::round_tf32(xv), lo = tc::round_tf32(xv - hi);
+                            float* dst = Lr3 + (size_t)i * 3 * seg + j;
+                            dst[0] = hi; dst[seg] = hi; dst[2 * (size_t)seg] = lo;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    // last CTA out commits (its ticket is taken after this CTA's reads of sc / st above)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int t = atomicAdd(ticket, 1u);
+        if (t == gridDim.x - 1) {
+            *ticket = 0u;
+            __threadfence();
+            commit_body(sc, out, st, trace, trace_cap, nullptr, a);
+        }
+    }
+}
+
 __global__ void k_begin_call(ObjDeviceState* st) { st->trace_pos = 0; st->batch_cursor = 0; st->halted = 0; }
 
 UpdArgs make_args(const avi_opt* op) {
@@ -218,6 +349,15 @@ UpdArgs make_args(const avi_opt* op) {
 }
 
 constexpr int NORM_BLOCKS_MAX = 256;
+
+// does the iteration's update kernel maintain the split of L for the next iteration's sampling stage?
+bool fr_maintains_split(const avi_opt* op) {
+    static const bool on = !(getenv("AVI_FR_TILED_UPDATE") && atoi(getenv("AVI_FR_TILED_UPDATE")) == 0) &&
+                           !(getenv("AVI_FR_KEEP_SPLIT") && atoi(getenv("AVI_FR_KEEP_SPLIT")) == 0);
+    const avi_obj* o = op->obj;
+    return on && o->family == AVI_FULLRANK && op->rule != AVI_RULE_DOG && op->rule != AVI_RULE_DOWG && o->Mloc > 0 &&
+           avi_fr_tc_ok(o, o->Mloc);
+}
 
 // enqueue ONE iteration of `step` (common.jl:75-104 minus the callback)
 int32_t enqueue_iteration(avi_opt* op, bool subsampled, int64_t batch) {
@@ -255,7 +395,14 @@ int32_t enqueue_iteration(avi_opt* op, bool subsampled, int64_t batch) {
     o->fused_exchange = mf_tail && o->shard_axis == AVI_SHARD_SAMPLES && ctx->nranks > 1 &&
                         avi_comm_peers(ctx, o->acc_len, &tail.comm);
     if (!o->fused_exchange) tail.comm.nranks = 1;
+    // full-rank: the update kernel below keeps the transposed split of L (the sampling stage's A operand) in step with
+    // lambda, so the sampling stage skips its own pass over the D x D matrix (steps_launch refreshes it before the first
+    // iteration of a call when anything else touched lambda or the buffer)
+    const bool dog_rule = op->rule == AVI_RULE_DOG || op->rule == AVI_RULE_DOWG;
+    const bool maintain = fr_maintains_split(op);
+    o->fr.Lr3_maintained = maintain;
     int32_t rc_local = avi_objective_local(o, op->lam);
+    o->fr.Lr3_maintained = false;
     o->fused_exchange = false;
     AVI_CHECK(rc_local);
     // (running this tail inside the last CTA of the target's final kernel was measured SLOWER than its own
@@ -274,12 +421,22 @@ int32_t enqueue_iteration(avi_opt* op, bool subsampled, int64_t batch) {
         if (ctx->tl) k_tl_commit<<<1, 32, 0, ctx->stream>>>(ctx->tl, ctx->tl_hist, o->d_state);
         return AVI_OK;
     }
-    const bool dog_rule = op->rule == AVI_RULE_DOG || op->rule == AVI_RULE_DOWG;
     if (o->family == AVI_FULLRANK && !dog_rule) {
         AVI_CHECK(avi_objective_finalize(o, op->lam, o->grad, o->out, /*skip_fr_matrix=*/true));
         const float* scal = o->acc + 4 * (size_t)o->accv;
         const float* C1 = scal + ACC_NSCAL;
         const float* C2 = C1 + (size_t)o->D * o->D;
+        static const bool tiled = !(getenv("AVI_FR_TILED_UPDATE") && atoi(getenv("AVI_FR_TILED_UPDATE")) == 0);
+        if (tiled) {
+            // gradient of the scale block + rule + operator + averager + next iteration's split of L + commit: one launch
+            const int ntc = (int)ceil_div(o->D, 32), ntr = (int)ceil_div(o->D, FRU_ROWS), nloc = (int)ceil_div(o->D, 256);
+            k_fr_update_t<<<(unsigned)(ntc * ntr + nloc), 256, 0, ctx->stream>>>(
+                op->lam, o->grad, op->m1, op->m2, op->avg, op->sc, o->out, o->d_state, C1, C2, scal, o->M, o->objective,
+                o->entropy, a, ntc, ntr, maintain ? o->fr.Lr3 : (float*)nullptr, (int)round_up(o->D, 32), op->ticket,
+                op->trace, op->trace_cap);
+            AVI_LAUNCHED(ctx);
+            return AVI_OK;
+        }
         k_fr_update<<<(unsigned)o->D + 1u, 256, 0, ctx->stream>>>(op->lam, o->grad, op->m1, op->m2, op->avg, op->sc, o->out, o->d_state, C1,
                                                  C2, scal, o->M, o->objective, o->entropy, a);
         AVI_LAUNCHED(ctx);
@@ -416,6 +573,17 @@ int32_t steps_prepare(avi_opt* op, int32_t n, const int32_t* idx_host, int64_t b
 int32_t steps_launch(avi_opt* op, int32_t n) {
     avi_ctx* ctx = op->ctx;
     if (op->call_enqueued + n > op->call_cap) AVI_FAIL(ctx, AVI_ERR_INVALID, "more iterations enqueued than avi_opt_steps_begin reserved");
+    if (n > 0 && fr_maintains_split(op)) {
+        // the iterations assume Lr3 == split(L of op->lam): true if the last writer of both was this optimiser's own
+        // update kernel; otherwise (first call, warm start, the objective evaluated at another lambda meanwhile,
+        // buffers reallocated) rebuild it once, outside the captured iteration
+        FrWork& w = op->obj->fr;
+        if (w.Lr3_owner != op || w.Lr3_version != op->lam_version) AVI_CHECK(avi_fr_refresh_split(op->obj, op->lam));
+        op->lam_version += n;
+        w.Lr3_owner = op; w.Lr3_version = op->lam_version;
+    } else {
+        op->lam_version += n;
+    }
     if (op->use_graph) {
         int32_t left = n;
         if (op->graph_u_exec)
@@ -545,6 +713,7 @@ int32_t avi_opt_create(avi_obj* obj, int32_t rule, const float* hyper, int32_t n
     if (rc == AVI_OK) rc = avi_alloc(ctx, &op->avg, (size_t)P);
     if (rc == AVI_OK) rc = avi_alloc(ctx, &op->sc, SC_N);
     if (rc == AVI_OK) rc = avi_alloc(ctx, &op->norm_part, 2 * NORM_BLOCKS_MAX);
+    if (rc == AVI_OK) rc = avi_alloc(ctx, &op->ticket, 4);
     if (rc != AVI_OK) { avi_opt_destroy(op); return rc; }
     float sc[SC_N] = {0};
     sc[SC_T] = 1.0f;   // PolynomialAveraging state starts at (x0, 1)  (averaging.jl:42)
@@ -573,7 +742,7 @@ int32_t avi_opt_destroy(avi_opt* op) {
     if (!op) return AVI_OK;
     cudaStreamSynchronize(op->ctx->stream);
     drop_graph(op);
-    avi_free(op->lam); avi_free(op->m1); avi_free(op->m2); avi_free(op->avg); avi_free(op->sc);
+    avi_free(op->lam); avi_free(op->m1); avi_free(op->m2); avi_free(op->avg); avi_free(op->sc); avi_free(op->ticket);
     avi_free(op->norm_part); avi_free(op->trace); avi_free(op->idx_dev);
     if (op->h_trace) cudaFreeHost(op->h_trace);
     delete op;
@@ -773,6 +942,7 @@ int32_t avi_opt_state_import(avi_opt* op, const void* buf_host, int64_t nbytes) 
     AVI_CUDA(ctx, avi_copy(ctx, op->sc, p, SC_N * sizeof(float), cudaMemcpyHostToDevice)); p += SC_N * sizeof(float);
     AVI_CUDA(ctx, avi_copy(ctx, op->obj->out, p, 4 * sizeof(float), cudaMemcpyHostToDevice));
     op->iteration = h.iteration;
+    op->lam_version += 1;   // (lambda replaced: a maintained split of L is stale)
     return avi_obj_seed(op->obj, h.key, h.step);
 }
 
