@@ -472,7 +472,12 @@ static int max_active_clusters(avi_ctx* ctx, int csz) {
 // cycles per column; ~6000 fixed per wave.  Multicast does not reduce what an SM ingests, so clusters only pay when
 // L2 bandwidth is the limit; they stay available (force_cluster = 2 / AVI_TC_CLUSTER=2, AVI_TC_CA/CB) and tested.
 int32_t avi_tc_plan(avi_ctx* ctx, int64_t Ma, int64_t Nb, int64_t K, bool split_k, int force_cluster, TcParams* p,
-                    int allow_pair) {
+                    int allow_pair, int max_ksplit, int nt_search) {
+    // split-K plans use the widest tile unless nt_search (plain store epilogue: a narrower tile means more b-chunks,
+    // fewer k-splits -- fewer partial slabs for the reduction that follows -- and a shorter epilogue per CTA);
+    // AVI_TC_SNT forces a width for A/B runs
+    const int snt_env = env_int("AVI_TC_SNT", 0);
+    if (snt_env < 0) nt_search = 0;
     const int sms = ctx->prop.multiProcessorCount;
     p->Ma = (int)Ma; p->Nb = (int)Nb;
     p->n_ablk = (int)ceil_div(Ma, BM);
@@ -491,9 +496,10 @@ int32_t avi_tc_plan(avi_ctx* ctx, int64_t Ma, int64_t Nb, int64_t K, bool split_
             const int nt_env = env_int("AVI_TC_NT", 0);
             const int ca_env = env_int(split_k ? "AVI_TC_BCA" : "AVI_TC_CA", 0), cb_env = env_int(split_k ? "AVI_TC_BCB" : "AVI_TC_CB", 0);
             if ((ca_env && ca != ca_env) || (cb_env && cb != cb_env)) continue;
-            for (int nt = split_k ? nt_hi : 16; nt <= nt_hi; nt += 16) {
+            for (int nt = (split_k && !nt_search) ? nt_hi : 16; nt <= nt_hi; nt += 16) {
                 if (nt % (8 * ca)) continue;
                 if (nt_env && !split_k && nt != std::min(nt_env, nt_hi)) continue;
+                if (snt_env > 0 && split_k && nt_search && nt != std::min(snt_env, nt_hi)) continue;
                 const int n_bchunk = (int)ceil_div(Nb, nt);
                 if (cb > 1 && cb > n_bchunk) continue;
                 const int64_t tiles = ceil_div(p->n_ablk, ca) * ceil_div(n_bchunk, cb);
@@ -501,6 +507,7 @@ int32_t avi_tc_plan(avi_ctx* ctx, int64_t Ma, int64_t Nb, int64_t K, bool split_
                 if (split_k) {
                     int want = (int)std::max<int64_t>(1, maxc / tiles);
                     want = std::min(want, p->n_kblk);
+                    if (max_ksplit > 0) want = std::min(want, max_ksplit);
                     kbps = (int)ceil_div(p->n_kblk, want);
                     n_ksplit = (int)ceil_div(p->n_kblk, kbps);
                 }
@@ -531,6 +538,7 @@ int32_t avi_tc_plan(avi_ctx* ctx, int64_t Ma, int64_t Nb, int64_t K, bool split_
             if (split_k) {
                 int want = (int)std::max<int64_t>(1, maxp / tiles);
                 want = std::min(want, p->n_kblk);
+                if (max_ksplit > 0) want = std::min(want, max_ksplit);
                 kbps = (int)ceil_div(p->n_kblk, want);
                 n_ksplit = (int)ceil_div(p->n_kblk, kbps);
             }
@@ -636,12 +644,9 @@ int32_t avi_tc_launch(avi_ctx* ctx, int epi, const CUtensorMap& tmA, const CUten
 int32_t avi_tc_gemm_store(avi_ctx* ctx, const float* A, int64_t Ma, int64_t lda, const float* B, int64_t Nb, int64_t ldb,
                           int64_t K, float* C, int64_t ldc, int64_t slab_stride, int max_slabs, int* n_slabs) {
     TcParams p{};
-    AVI_CHECK(avi_tc_plan(ctx, Ma, Nb, K, max_slabs > 1, 0, &p));
-    if (p.n_ksplit > max_slabs) {   // the caller's slab buffer bounds the split
-        p.n_ksplit = max_slabs;
-        p.kb_per_split = (int)ceil_div(p.n_kblk, p.n_ksplit);
-        p.n_ksplit = (int)ceil_div(p.n_kblk, p.kb_per_split);
-    }
+    AVI_CHECK(avi_tc_plan(ctx, Ma, Nb, K, max_slabs > 1, 0, &p, 1, /*the caller's slab buffer bounds the split*/ max_slabs,
+                          /*nt_search=*/1));
+    if (p.n_ksplit > max_slabs) AVI_FAIL(ctx, AVI_ERR_INVALID, "split-K plan exceeds the slab buffer");
     CUtensorMap tmA, tmB;
     AVI_CHECK(avi_tc_make_tmap(ctx, &tmA, A, Ma, K, lda, 128 / p.cb));
     AVI_CHECK(avi_tc_make_tmap(ctx, &tmB, B, Nb, K, ldb, p.pair ? p.nt / 2 : p.nt / p.ca));

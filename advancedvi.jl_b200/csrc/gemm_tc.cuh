@@ -68,8 +68,9 @@ int32_t avi_tc_make_tmap_mn3(avi_ctx* ctx, CUtensorMap* map, const float* base, 
                              int groups);
 // fills Ma, Nb, n_ablk, n_kblk, nt, n_bchunk, n_ksplit, kb_per_split, ca, cb.  force_cluster: 0 = never cluster
 // allow_pair = 0: single-CTA tiles only (the fused iteration kernel)
+// max_ksplit > 0 bounds the number of k-splits; nt_search: split-K plans may use tiles narrower than the widest one
 int32_t avi_tc_plan(avi_ctx* ctx, int64_t Ma, int64_t Nb, int64_t K, bool split_k, int force_cluster, TcParams* p,
-                    int allow_pair = 1);
+                    int allow_pair = 1, int max_ksplit = 0, int nt_search = 0);
 int32_t avi_tc_launch(avi_ctx* ctx, int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p);
 // generic contraction with the plain store epilogue (full-rank family): see gemm_tc.cu
 int32_t avi_tc_gemm_store(avi_ctx* ctx, const float* A, int64_t Ma, int64_t lda, const float* B, int64_t Nb, int64_t ldb,

@@ -387,8 +387,9 @@ struct Glm : avi_model {
         return AVI_OK;
     }
 
-    int32_t backward_setup(int M, TcParams* p, CUtensorMap* tmA, CUtensorMap* tmB) {
-        AVI_CHECK(avi_tc_plan(ctx, d, M, kb(), true, cluster_mode, p));
+    // store: the plain store epilogue follows (full gradient G): the planner may trade k-splits for b-chunks
+    int32_t backward_setup(int M, TcParams* p, CUtensorMap* tmA, CUtensorMap* tmB, bool store = false) {
+        AVI_CHECK(avi_tc_plan(ctx, d, M, kb(), true, cluster_mode, p, 1, 0, store ? 1 : 0));
         p->static_op = subsampled ? 0 : 1;   // A = X columns
         p->tl = ctx->tl; p->tl_id = 2;
         AVI_CHECK(avi_tc_make_tmap(ctx, tmA, Xc, d, kb(), nP, 128 / p->cb));
@@ -410,7 +411,7 @@ struct Glm : avi_model {
                 sl = G; nslab = 1; sstride = 0;
             } else {
                 TcParams p{}; CUtensorMap tmA, tmB;
-                AVI_CHECK(backward_setup(M, &p, &tmA, &tmB));
+                AVI_CHECK(backward_setup(M, &p, &tmA, &tmB, /*store=*/true));
                 sstride = (long long)capM * ld;
                 AVI_CHECK(ensure_buf(&slabs, &slab_cap, sstride * p.n_ksplit));
                 p.C = slabs; p.ldc = ld; p.slab_stride = sstride;

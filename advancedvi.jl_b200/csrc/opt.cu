@@ -221,7 +221,7 @@ __global__ void k_commit(float* __restrict__ sc, const float* __restrict__ out, 
 //   * commits the scalar state in the last CTA to finish (ticket), instead of a k_commit launch: every CTA has read the
 //     old scalars before it takes its ticket.
 // The trailing CTAs (blockIdx.x >= ntc * ntr) update the location block.
-constexpr int FRU_ROWS = 64;
+template <int FRU_ROWS>
 __global__ void __launch_bounds__(256)
 k_fr_update_t(float* __restrict__ lam, float* __restrict__ grad, float* __restrict__ m1, float* __restrict__ m2,
               float* __restrict__ avg, float* __restrict__ sc, const float* __restrict__ out,
@@ -429,8 +429,11 @@ int32_t enqueue_iteration(avi_opt* op, bool subsampled, int64_t batch) {
         static const bool tiled = !(getenv("AVI_FR_TILED_UPDATE") && atoi(getenv("AVI_FR_TILED_UPDATE")) == 0);
         if (tiled) {
             // gradient of the scale block + rule + operator + averager + next iteration's split of L + commit: one launch
-            const int ntc = (int)ceil_div(o->D, 32), ntr = (int)ceil_div(o->D, FRU_ROWS), nloc = (int)ceil_div(o->D, 256);
-            k_fr_update_t<<<(unsigned)(ntc * ntr + nloc), 256, 0, ctx->stream>>>(
+            static const int fru_rows = getenv("AVI_FRU_ROWS") ? atoi(getenv("AVI_FRU_ROWS")) : 64;   // rows per CTA: 32 | 64 | 128
+            const int rows = fru_rows == 32 || fru_rows == 128 ? fru_rows : 64;
+            const int ntc = (int)ceil_div(o->D, 32), ntr = (int)ceil_div(o->D, rows), nloc = (int)ceil_div(o->D, 256);
+            auto kern = rows == 32 ? k_fr_update_t<32> : rows == 128 ? k_fr_update_t<128> : k_fr_update_t<64>;
+            kern<<<(unsigned)(ntc * ntr + nloc), 256, 0, ctx->stream>>>(
                 op->lam, o->grad, op->m1, op->m2, op->avg, op->sc, o->out, o->d_state, C1, C2, scal, o->M, o->objective,
                 o->entropy, a, ntc, ntr, maintain ? o->fr.Lr3 : (float*)nullptr, (int)round_up(o->D, 32), op->ticket,
                 op->trace, op->trace_cap);
