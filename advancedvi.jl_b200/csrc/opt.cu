@@ -429,8 +429,8 @@ int32_t enqueue_iteration(avi_opt* op, bool subsampled, int64_t batch) {
         static const bool tiled = !(getenv("AVI_FR_TILED_UPDATE") && atoi(getenv("AVI_FR_TILED_UPDATE")) == 0);
         if (tiled) {
             // gradient of the scale block + rule + operator + averager + next iteration's split of L + commit: one launch
-            static const int fru_rows = getenv("AVI_FRU_ROWS") ? atoi(getenv("AVI_FRU_ROWS")) : 64;   // rows per CTA: 32 | 64 | 128
-            const int rows = fru_rows == 32 || fru_rows == 128 ? fru_rows : 64;
+            static const int fru_rows = getenv("AVI_FRU_ROWS") ? atoi(getenv("AVI_FRU_ROWS")) : 32;   // rows per CTA: 32 | 64 | 128 (measured on C3: 88.6 | 90.2 | 93.7 us per step)
+            const int rows = fru_rows == 64 || fru_rows == 128 ? fru_rows : 32;
             const int ntc = (int)ceil_div(o->D, 32), ntr = (int)ceil_div(o->D, rows), nloc = (int)ceil_div(o->D, 256);
             auto kern = rows == 32 ? k_fr_update_t<32> : rows == 128 ? k_fr_update_t<128> : k_fr_update_t<64>;
             kern<<<(unsigned)(ntc * ntr + nloc), 256, 0, ctx->stream>>>(

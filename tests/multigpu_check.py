@@ -110,7 +110,71 @@ def main():
         ctx.close()
         if rank == 0:
             print(f"multigpu_check ok: world={world} native_exchange={native}", flush=True)
-    st0.close(); st0.obj.close(); p0.close(); c0.close()
+    st0.close(); st0.obj.close(); p0.close()
+
+    # ---- full-rank family: its exchange payloads (the D x D contraction under sample sharding, the M x D gradient block
+    # under row sharding) exceed the low-latency lanes and take the pull protocol (comm.cu: k_allreduce_oneshot) ----
+    nF, dF, MF = 2000, 160, 128
+    XF, yF = Mo.synth_glm_data(nF, dF, seed=5)
+    DF = dF + 1
+    rngF = np.random.default_rng(3)
+    LF = np.tril(0.05 * rngF.standard_normal((DF, DF))).astype(np.float32)
+    LF[np.diag_indices(DF)] = 0.4
+    qF = avi.FullRankGaussian(0.1 * rngF.standard_normal(DF).astype(np.float32), LF)
+    lamF = qF.destructure()
+    specs = {"rep": lambda: avi.RepGradELBO(MF), "stl": lambda: avi.RepGradELBO(MF, avi.StickingTheLandingEntropy()),
+             "score": lambda: avi.ScoreGradELBO(MF)}
+    pF0 = avi.LogReg(c0, XF, yF, gemm="tf32")
+    resF = {}
+    for kind, mk in specs.items():
+        o0 = avi.Objective(key, mk(), qF, pF0)
+        resF[kind] = o0.estimate_gradient(lamF)
+        o0.close()
+    algF = avi.KLMinRepGradDescent(optimizer=avi.Adam(1e-2), n_samples=MF, operator=avi.ClipScale())
+    _, infoF0, stF0 = avi.optimize(key, algF, 10, pF0, qF)
+    lamF0, _, _ = stF0.params()
+    stF0.close(); stF0.obj.close(); pF0.close(); c0.close()
+    ctx = avi.Context(lr)
+    parallel.connect(ctx, max_floats=4 * 192 + 64 + 2 * DF * DF + MF * 164, native=True)
+    vals, elbos, nd = np.empty(10, np.float32), np.empty(10, np.float32), C.c_int32()
+    for axis in ("samples", "rows"):
+        if axis == "samples":
+            prob = avi.LogReg(ctx, XF, yF, gemm="tf32")
+            m0, ml = parallel.sample_shard(MF, rank, world)
+        else:
+            r0, nr = parallel.row_shard(nF, rank, world, align=32)
+            prob = avi.LogReg(ctx, XF[r0:r0 + nr], yF[r0:r0 + nr], n_data=nF, gemm="tf32")
+            prob.set_data_shard(world, nF, include_prior=(rank == 0))
+
+        def shard(o):
+            if axis == "samples":
+                o.set_sample_shard(m0, ml)
+            else:
+                o.set_shard_axis(L.SHARD_ROWS)
+
+        for kind, mk in specs.items():
+            o = avi.Objective(key, mk(), qF, prob)
+            shard(o)
+            v, g, e = o.estimate_gradient(lamF)
+            v0, g0, e0 = resF[kind]
+            tol = 2e-3 if kind == "score" else 5e-5
+            assert abs(v - v0) <= tol * abs(v0) + 1e-6, ("full-rank", axis, kind, v, v0)
+            assert np.linalg.norm(g - g0) <= tol * np.linalg.norm(g0), ("full-rank", axis, kind, np.linalg.norm(g - g0), np.linalg.norm(g0))
+            gather_equal(g, f"full-rank {axis}-sharded grad {kind}")
+            o.close()
+        obj = avi.Objective(key, algF.objective, qF, prob)
+        shard(obj)
+        st = _OptState(algF, obj, qF)
+        L.check(L.lib.avi_opt_steps(st.h, 10, L.fptr(vals), L.fptr(elbos), C.byref(nd)), ctx.h)
+        assert nd.value == 10
+        lam1, _, _ = st.params()
+        assert np.linalg.norm(lam1 - lamF0) <= 1e-4 * np.linalg.norm(lamF0), ("full-rank", axis, np.linalg.norm(lam1 - lamF0))
+        assert abs(elbos[9] - infoF0[9]["elbo"]) <= 1e-4 * abs(infoF0[9]["elbo"])
+        gather_equal(lam1, f"full-rank lambda after 10 {axis}-sharded steps")
+        st.close(); obj.close(); prob.close()
+    ctx.close()
+    if rank == 0:
+        print(f"multigpu_check ok: world={world} full-rank family (pull-protocol exchange)", flush=True)
     dist.barrier()
     dist.destroy_process_group()
 
