@@ -29,6 +29,7 @@ from . import _lib as L
 __all__ = [
     "Context", "MvNormalDiag", "LogReg", "GaussGLM", "HostCallbackProblem",
     "MvLocationScale", "MeanFieldGaussian", "FullRankGaussian", "MvLocationScaleLowRank", "LowRankGaussian",
+    "Normal", "Laplace", "TDist",
     "ClosedFormEntropy", "MonteCarloEntropy", "StickingTheLandingEntropy",
     "ClosedFormEntropyZeroGradient", "StickingTheLandingEntropyZeroGradient",
     "RepGradELBO", "ScoreGradELBO", "SubsampledObjective", "ReshufflingBatchSubsampling",
@@ -310,10 +311,43 @@ class HostCallbackProblem(_Problem):
 
 # ---------------------------------------------------------------------------------------------
 # variational family (host container; the arithmetic is in the library)
-class MvLocationScale:
-    """src/families/location_scale.jl:15-19 with dist = Normal(0, 1); float32 only."""
+class Normal:
+    """Normal(0, 1): the base distribution of MeanFieldGaussian / FullRankGaussian."""
+    code, param = 0, 0.0
 
-    def __init__(self, location, scale):
+    def __repr__(self):
+        return "Normal(0, 1)"
+
+
+class Laplace(Normal):
+    """Laplace(0, 1) base distribution (docs/src/families.md:88-101)."""
+    code, param = 1, 0.0
+
+    def __repr__(self):
+        return "Laplace(0, 1)"
+
+
+class TDist(Normal):
+    """TDist(nu) base distribution (docs/src/families.md:72-86)."""
+    code = 2
+
+    def __init__(self, nu: float):
+        if not nu > 0:
+            raise ValueError("TDist: nu must be positive")
+        self.param = float(nu)
+
+    def __repr__(self):
+        return f"TDist({self.param})"
+
+
+class MvLocationScale:
+    """MvLocationScale(location, scale, dist) (src/families/location_scale.jl:15-19); dist = Normal(0, 1) unless given
+    (Laplace(), TDist(nu): docs/src/families.md:72-101); float32 only."""
+
+    def __init__(self, location, scale, dist=None):
+        self.dist = dist if dist is not None else Normal()
+        if not isinstance(self.dist, Normal):
+            raise TypeError("dist must be Normal(), Laplace() or TDist(nu)")
         for a in (location, scale):
             if np.asarray(a).dtype not in (np.float32,):
                 raise TypeError("MvLocationScale: the B200 path supports Float32 only "
@@ -344,8 +378,8 @@ class MvLocationScale:
         D = len(self.location)
         flat = np.asarray(flat, dtype=np.float32)
         if self.is_meanfield:
-            return MvLocationScale(flat[:D].copy(), flat[D:].copy())
-        return MvLocationScale(flat[:D].copy(), flat[D:].reshape(D, D, order="F").copy())
+            return MvLocationScale(flat[:D].copy(), flat[D:].copy(), self.dist)
+        return MvLocationScale(flat[:D].copy(), flat[D:].reshape(D, D, order="F").copy(), self.dist)
 
 
 class MvLocationScaleLowRank:
@@ -629,6 +663,9 @@ class Objective:
             L.check(L.lib.avi_obj_create(self.ctx.h, prob.h, q.family, base.kind, base.entropy.code, base.n_samples,
                                          C.byref(h)), self.ctx.h)
         self.h = h
+        dist = getattr(q, "dist", None)
+        if dist is not None and dist.code != 0:
+            L.check(L.lib.avi_obj_set_base(h, dist.code, dist.param), self.ctx.h)
         self.P = int(L.lib.avi_obj_num_params(h))
         self._ptr = _PtrCache()
         self._v, self._e = C.c_float(), C.c_float()

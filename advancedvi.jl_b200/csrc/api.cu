@@ -288,7 +288,8 @@ int32_t avi_model_destroy(avi_model* model) {
 // ---- objective ---------------------------------------------------------------------------------
 static void obj_free_buffers(avi_obj* o) {
     avi_free(o->Z); avi_free(o->E); avi_free(o->G); avi_free(o->U); avi_free(o->E2); avi_free(o->V);
-    avi_free(o->logp); avi_free(o->esq); avi_free(o->fbuf);
+    o->logp = nullptr;   // (lives behind G)
+    avi_free(o->esq); avi_free(o->fbuf);
 }
 
 }  // extern "C"
@@ -303,7 +304,10 @@ int32_t avi_obj_ensure_capacity(avi_obj* o, int M) {
     const size_t n = (size_t)M * o->ld;
     AVI_CHECK(avi_alloc(ctx, &o->Z, n));
     AVI_CHECK(avi_alloc(ctx, &o->E, n));
-    AVI_CHECK(avi_alloc(ctx, &o->G, n));
+    // log pi(z_m) sits right behind the gradient block: under row sharding both are partial sums over the data rows and
+    // travel in ONE exchange (family.cu)
+    AVI_CHECK(avi_alloc(ctx, &o->G, n + (size_t)round_up(M, 4)));
+    o->logp = o->G + n;
     if (o->family == AVI_FULLRANK) AVI_CHECK(avi_alloc(ctx, &o->U, n));
     if (o->family == AVI_LOWRANK) {
         AVI_CHECK(avi_alloc(ctx, &o->E2, (size_t)M * o->ldr));
@@ -311,7 +315,6 @@ int32_t avi_obj_ensure_capacity(avi_obj* o, int M) {
         AVI_CHECK(avi_alloc(ctx, &o->U, n));
         AVI_CHECK(avi_alloc(ctx, &o->V, (size_t)M * o->ldr));
     }
-    AVI_CHECK(avi_alloc(ctx, &o->logp, (size_t)M));
     AVI_CHECK(avi_alloc(ctx, &o->esq, (size_t)M));
     AVI_CHECK(avi_alloc(ctx, &o->fbuf, (size_t)M));
     return AVI_OK;
@@ -404,6 +407,19 @@ int32_t avi_obj_destroy(avi_obj* o) {
     if (o->h_lambda) cudaFreeHost(o->h_lambda);
     if (o->h_grad) cudaFreeHost(o->h_grad);
     delete o;
+    return AVI_OK;
+}
+
+int32_t avi_obj_set_base(avi_obj* obj, int32_t base, float param) {
+    if (!obj) return AVI_ERR_INVALID;
+    avi_ctx* ctx = obj->ctx;
+    if (obj->family == AVI_LOWRANK && base != AVI_BASE_NORMAL)
+        AVI_FAIL(ctx, AVI_ERR_UNSUPPORTED, "the low-rank family is Gaussian (src/families/location_scale_low_rank.jl:119-135)");
+    BaseDist b;
+    if (!avi_base_make(base, param, &b))
+        AVI_FAIL(ctx, AVI_ERR_INVALID, "base distribution: AVI_BASE_NORMAL, AVI_BASE_LAPLACE or AVI_BASE_STUDENT_T with 0 < nu < 1e6");
+    if (b.kind != obj->base.kind || b.nu != obj->base.nu) obj->generation++;   // captured iterations hold the old draws
+    obj->base = b;
     return AVI_OK;
 }
 
@@ -595,7 +611,7 @@ int32_t avi_obj_estimate_objective(avi_obj* o, const float* lambda_host, int64_t
     }
     // restore the ScoreGrad centring slot clobbered above
     AVI_CUDA(ctx, cudaMemsetAsync(o->out, 0, 4 * sizeof(float), ctx->stream));
-    const double D = o->D, LOG2PI = 1.8378770664093453, H0 = 1.4189385332046727;
+    const double D = o->D, LOG2PI = 1.8378770664093453, H0 = o->base.h0;   // (1.4189385... for Normal(0, 1))
     const double energy = s_logp / n_samples;
     double ent;
     if (lowrank)   // H from k_lr_entropy, or -mean log q(z) (the chunk sums then carry sum log q in the second slot)

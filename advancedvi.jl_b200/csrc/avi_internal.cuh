@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../include/avi.h"
+#include "base_dist.cuh"
 
 #define AVI_VERSION 100
 
@@ -159,6 +160,7 @@ struct SampleHook {
 
 struct FusedStepArgs;   // step_fused.cuh
 
+
 // Layout shared by every sample-major buffer: row m (one Monte-Carlo sample) holds `ld` floats,
 // coordinate i at [m * ld + i]  ==  a D x M column-major matrix with leading dimension ld.
 struct avi_model {
@@ -227,6 +229,7 @@ struct FrWork {
 // what k_fr_outer_prep needs to finish the location block and the value slot in the same launch (family_fr.cu)
 struct FrPrepFinalize {
     int on = 0;
+    float h0 = AVI_H0;   // entropy of the base distribution
     const float* lambda = nullptr;
     int M = 0, objective = 0, entropy = 0, Mloc = 0, accv = 0;
     float *grad = nullptr, *out = nullptr;
@@ -267,6 +270,7 @@ struct avi_obj {
     float* grad = nullptr;       // P
     float* out = nullptr;        // 4 : value, elbo, logdet, ScoreGrad centring shift
     FrWork fr;
+    BaseDist base;               // base distribution of MvLocationScale (base_dist.cuh); Normal(0, 1) by default
     bool fr_vec_done = false;    // the local phase already produced grad[0 .. D) and out[0 .. 3) (full-rank, see family.cu)
     // pinned host staging
     float* h_lambda = nullptr;   // P
@@ -355,6 +359,7 @@ int32_t avi_objective_finalize(avi_obj* o, const float* lambda, float* grad, flo
 int32_t avi_objective_forward_chunk(avi_obj* o, const float* lambda, int m0, int Mc, const ObjDeviceState* ov,
                                     float* sums_dev, bool lowrank_logq = false);
 int32_t avi_exchange(avi_ctx* ctx, float* buf, int64_t count);
+int64_t avi_comm_capacity(avi_ctx* ctx);   // comm.cu: floats per native exchange, -1 = not connected (callback exchange)
 struct CommPeers;
 bool avi_comm_peers(avi_ctx* ctx, int64_t count, CommPeers* out);   // comm.cu          // all-reduce (no-op single rank)
 int32_t avi_obj_advance(avi_obj* o);
@@ -366,7 +371,8 @@ int32_t avi_gemm_simt(avi_ctx* ctx, const float* A, long long sa_r, long long sa
                       long long sb_r, long long sb_k, float* C, long long sc_r, long long sc_c, int Ma,
                       int Nb, int K, float alpha, int tri_b = 0);
 // U = L^{-T} E for a column-major lower-triangular L (D x D): row m of U solves L' u = e_m.
-int32_t avi_trsm_lt(avi_ctx* ctx, const float* L, int D, const float* E, float* U, int ld, int M);
+// (base: the right-hand side is -score(e) of the base distribution, == e for Normal(0, 1))
+int32_t avi_trsm_lt(avi_ctx* ctx, const float* L, int D, const float* E, float* U, int ld, int M, const BaseDist& base = BaseDist{});
 
 // full-rank family on the tensor cores (family_fr.cu)
 bool avi_fr_tc_ok(const avi_obj* o, int Mloc);

@@ -146,6 +146,12 @@ bool avi_comm_peers(avi_ctx* ctx, int64_t count, CommPeers* out) {
     return true;
 }
 
+// largest payload (floats) the native exchange takes; -1 when the peers are not connected
+int64_t avi_comm_capacity(avi_ctx* ctx) {
+    CommState* cs = state(ctx);
+    return cs && cs->connected ? cs->max_floats : -1;
+}
+
 int32_t avi_comm_exchange(avi_ctx* ctx, float* buf, int64_t count) {
     CommState* cs = state(ctx);
     if (!cs || !cs->connected) return AVI_ERR_UNSUPPORTED;

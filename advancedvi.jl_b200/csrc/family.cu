@@ -36,7 +36,7 @@ template <bool FULLRANK, bool HOOK, int SPLIT>
 __global__ void __launch_bounds__(32 * SAMPLE_WARPS)
 k_sample(const float* __restrict__ lambda, int D, int ld, int m0, int Mloc, const ObjDeviceState* __restrict__ st,
          ObjDeviceState st_val, int use_val, uint32_t stream_id, float* __restrict__ Z,
-         float* __restrict__ E, float* __restrict__ esq, SampleHook hk) {
+         float* __restrict__ E, float* __restrict__ esq, SampleHook hk, BaseDist bd) {
     extern __shared__ __align__(16) float s_ms[];   // STAGE: [ld] mu, [ld] s
     constexpr bool STAGE = !FULLRANK && SPLIT == 1;
     if (HOOK) tl_min(hk.tl, 0);
@@ -77,7 +77,7 @@ k_sample(const float* __restrict__ lambda, int D, int ld, int m0, int Mloc, cons
                 *reinterpret_cast<float4*>(Er3row + 2 * hk.er_seg + i) = z4;
                 continue;
             }
-            const float4 e = normal4((uint32_t)q, (uint32_t)(m0 + m), c2, c3, pk);
+            const float4 e = base_draw4(bd, (uint32_t)q, (uint32_t)(m0 + m), c2, c3, pk);   // u ~ dist (eps for Normal(0, 1))
             float ev[4] = {e.x, e.y, e.z, e.w}, zv[4] = {0.f, 0.f, 0.f, 0.f}, zt[4];
             if (i + 3 >= D) {   // the row's last quad: zero the padding columns
 #pragma unroll
@@ -103,8 +103,13 @@ k_sample(const float* __restrict__ lambda, int D, int ld, int m0, int Mloc, cons
 #pragma unroll
                 for (int c = 0; c < 4; ++c) zv[c] = fmaf(sv[c], ev[c], mv[c]);   // padding: 0 * 0 + 0
             }
+            if (bd.kind == AVI_BASE_NORMAL) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) part = fmaf(ev[c], ev[c], part);
+                for (int c = 0; c < 4; ++c) part = fmaf(ev[c], ev[c], part);
+            } else {   // sum_i -2 log phi(u_i) - log 2 pi: |eps|^2's role in log q(z) for any base (base_dist.cuh)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) part += i + c < D ? base_nl2(bd, ev[c]) : 0.0f;
+            }
             if (HOOK) {
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
@@ -207,7 +212,7 @@ k_scalars(const float* __restrict__ lambda, int D, int fullrank, int objective, 
 //   both     : v2 = sum eps, v3 = sum eps^2
 __global__ void __launch_bounds__(1024)
 k_reduce_mf(const float* __restrict__ G, const float* __restrict__ E, const float* __restrict__ fbuf,
-            int ld, int Mloc, int D, int accv, int objective, int skip_g, float* __restrict__ acc) {
+            int ld, int Mloc, int D, int accv, int objective, int skip_g, float* __restrict__ acc, BaseDist bd) {
     __shared__ float sm[4][32][33];
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int i = blockIdx.x * 32 + tx;
@@ -215,10 +220,11 @@ k_reduce_mf(const float* __restrict__ G, const float* __restrict__ E, const floa
     if (i < D) {
         for (int m = ty; m < Mloc; m += 32) {
             float e = E[(size_t)m * ld + i];
-            v2 += e; v3 = fmaf(e, e, v3);
+            const float sc = base_negscore(bd, e);   // -d log phi / du: e itself for Normal(0, 1)
+            v2 += sc; v3 = fmaf(sc, e, v3);
             if (objective == AVI_SCOREGRAD) {
                 float f = fbuf[m];
-                v0 = fmaf(f, e, v0); v1 = fmaf(f * e, e, v1);
+                v0 = fmaf(f, sc, v0); v1 = fmaf(f * sc, e, v1);
             } else if (!skip_g) {
                 float g = G[(size_t)m * ld + i];
                 v0 += g; v1 = fmaf(g, e, v1);
@@ -243,12 +249,13 @@ __global__ void __launch_bounds__(1024)
 k_finalize_mf(const float* __restrict__ acc, int accv, const float* __restrict__ lambda, int D, int M,
               int objective, int entropy, const float* __restrict__ logp, const float* __restrict__ esq, int Mloc,
               int deferred, float* __restrict__ grad, float* __restrict__ out, float* __restrict__ host_out,
-              ObjDeviceState* __restrict__ advance_st) {
+              ObjDeviceState* __restrict__ advance_st, float h0) {
     __shared__ float sm[33];
     pdl_trigger();
     pdl_wait();
     const float* s = lambda + D;
-    const MfSums S = mf_collect_sums(lambda, D, acc + 4 * (size_t)accv, logp, esq, Mloc, deferred, sm);
+    MfSums S = mf_collect_sums(lambda, D, acc + 4 * (size_t)accv, logp, esq, Mloc, deferred, sm);
+    S.h0 = h0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < D; i += gridDim.x * blockDim.x) {
         float gm, gs;
         mf_grad_entry(acc, accv, __ldg(s + i), i, M, objective, entropy, S, gm, gs);
@@ -330,9 +337,9 @@ __global__ void k_finalize_fr_mat(const float* __restrict__ C1, const float* __r
 __global__ void __launch_bounds__(1024)
 k_finalize_fr_vec(const float* __restrict__ acc, int accv, const float* __restrict__ lambda, int D, int M,
                   int objective, int entropy, float* __restrict__ grad, float* __restrict__ out,
-                  const float* __restrict__ logp, const float* __restrict__ esq, int Mloc, int deferred) {
+                  const float* __restrict__ logp, const float* __restrict__ esq, int Mloc, int deferred, float h0) {
     __shared__ float sm[33];
-    fr_vec_finalize(acc, accv, lambda, D, M, objective, entropy, grad, out, logp, esq, Mloc, deferred != 0, true, sm);
+    fr_vec_finalize(acc, accv, lambda, D, M, objective, entropy, grad, out, logp, esq, Mloc, deferred != 0, true, sm, h0);
 }
 
 __global__ void k_advance(ObjDeviceState* st) { st->step += 1ull; }
@@ -383,9 +390,9 @@ int32_t avi_family_sample(avi_obj* o, const float* lambda, float* Z, float* E, f
 #define LAUNCH_SAMPLE(FR, HK, HOOKV)                                                                                 \
     do {                                                                                                             \
         if (split) avi_launch_pdl(ctx, k_sample<FR, HK, SAMPLE_WARPS>, dim3(sgrid), dim3(32 * SAMPLE_WARPS), 0,       \
-            lambda, o->D, o->ld, m0, Mloc, st, sv, use_val, (uint32_t)AVI_STREAM_EPS, Z, E, esq, HOOKV);              \
+            lambda, o->D, o->ld, m0, Mloc, st, sv, use_val, (uint32_t)AVI_STREAM_EPS, Z, E, esq, HOOKV, o->base);     \
         else avi_launch_pdl(ctx, k_sample<FR, HK, 1>, dim3(sgrid), dim3(32 * SAMPLE_WARPS), stage_bytes,              \
-            lambda, o->D, o->ld, m0, Mloc, st, sv, use_val, (uint32_t)AVI_STREAM_EPS, Z, E, esq, HOOKV);              \
+            lambda, o->D, o->ld, m0, Mloc, st, sv, use_val, (uint32_t)AVI_STREAM_EPS, Z, E, esq, HOOKV, o->base);     \
     } while (0)
     if (o->family == AVI_MEANFIELD) {
         if (hook && hook->kind == 1) LAUNCH_SAMPLE(false, true, *hook);
@@ -398,7 +405,7 @@ int32_t avi_family_sample(avi_obj* o, const float* lambda, float* Z, float* E, f
         AVI_LAUNCHED(ctx);
         avi_launch_pdl(ctx, k_sample<true, false, SAMPLE_WARPS>, dim3((unsigned)Mloc), dim3(32 * SAMPLE_WARPS), 0, lambda,
                        o->rank, o->ldr, m0, Mloc, st, sv, use_val, (uint32_t)AVI_STREAM_EPS_FACTORS, (float*)nullptr, o->E2,
-                       o->fbuf, SampleHook{});
+                       o->fbuf, SampleHook{}, BaseDist{});
         AVI_LAUNCHED(ctx);
         AVI_CHECK(avi_lr_affine(o, lambda, E, o->E2, Z, Mloc));
     } else {
@@ -482,6 +489,7 @@ int32_t avi_objective_local(avi_obj* o, const float* lambda) {
     const bool stl = o->entropy == AVI_ENT_STL || o->entropy == AVI_ENT_STL_ZEROGRAD;
     const bool rows = o->shard_axis == AVI_SHARD_ROWS && ctx->nranks > 1;
     int skip_g = 0;
+    bool logp_sent = false;
     if (rep) {
         if (o->family == AVI_MEANFIELD && o->model->has_gradsums()) {
             AVI_CHECK(o->model->eval_gradsums(o->Z, o->E, ld, Mloc, o->logp, o->acc, o->acc + accv));
@@ -489,14 +497,18 @@ int32_t avi_objective_local(avi_obj* o, const float* lambda) {
             if (rows) AVI_CHECK(avi_exchange(ctx, o->acc, 2LL * accv));
         } else {
             AVI_CHECK(o->model->eval(o->Z, ld, Mloc, o->logp, o->G));
-            if (rows) AVI_CHECK(avi_exchange(ctx, o->G, (int64_t)Mloc * ld));
+            if (rows) {   // G and (when the buffers are full: logp starts where G ends) log pi in one exchange
+                const int64_t cap = avi_comm_capacity(ctx);
+                logp_sent = Mloc == o->cap_M && (cap < 0 || (int64_t)Mloc * ld + Mloc <= cap);
+                AVI_CHECK(avi_exchange(ctx, o->G, (int64_t)Mloc * ld + (logp_sent ? Mloc : 0)));
+            }
         }
     } else {
         AVI_CHECK(o->model->eval(o->Z, ld, Mloc, o->logp, nullptr));
     }
     // row sharding: every rank holds all samples and a slice of the data rows; log pi and its
     // gradient are sums over rows, everything after this point is replicated arithmetic
-    if (rows) AVI_CHECK(avi_exchange(ctx, o->logp, Mloc));
+    if (rows && !logp_sent) AVI_CHECK(avi_exchange(ctx, o->logp, Mloc));
     if (!avi_obj_defers_scalars(o)) {
         k_scalars<<<1, 1024, 0, ctx->stream>>>(lambda, D, o->family == AVI_FULLRANK, o->objective, o->logp, o->esq,
                                                Mloc, o->out, o->fbuf, scal);
@@ -513,7 +525,7 @@ int32_t avi_objective_local(avi_obj* o, const float* lambda) {
         if (rep) {
             // v0 = sum_m g, v1 = sum_m g .* u_diag (the mean-field reduction), CU[k * D + i] = sum_m g[m][i] u_fact[m][k]
             k_reduce_mf<<<(unsigned)ceil_div(D, 32), dim3(32, 32), 0, ctx->stream>>>(o->G, o->E, o->fbuf, ld, Mloc, D, accv,
-                                                                                   AVI_REPGRAD, 0, o->acc);
+                                                                                   AVI_REPGRAD, 0, o->acc, BaseDist{});
             AVI_LAUNCHED(ctx);
             AVI_CHECK(avi_gemm_simt(ctx, o->E2, 1, o->ldr, o->G, 1, ld, scal + ACC_NSCAL, D, 1, o->rank, D, Mloc, 1.0f));
         }
@@ -522,7 +534,7 @@ int32_t avi_objective_local(avi_obj* o, const float* lambda) {
         // with a fused target and a closed-form entropy nothing else is needed (v2, v3 unused)
         if (!(skip_g && !stl)) {
             k_reduce_mf<<<(unsigned)ceil_div(D, 32), dim3(32, 32), 0, ctx->stream>>>(
-                o->G, o->E, o->fbuf, ld, Mloc, D, accv, o->objective, skip_g, o->acc);
+                o->G, o->E, o->fbuf, ld, Mloc, D, accv, o->objective, skip_g, o->acc, o->base);
             AVI_LAUNCHED(ctx);
         }
     } else {
@@ -530,7 +542,7 @@ int32_t avi_objective_local(avi_obj* o, const float* lambda) {
         float* C2 = C1 + (size_t)D * D;
         const float* W = o->G;
         if (!rep || stl) {
-            AVI_CHECK(avi_trsm_lt(ctx, lambda + D, D, o->E, o->U, ld, Mloc));
+            AVI_CHECK(avi_trsm_lt(ctx, lambda + D, D, o->E, o->U, ld, Mloc, o->base));
             k_fr_make_w<<<Mloc, 256, 0, ctx->stream>>>(o->G, o->U, o->fbuf, ld, Mloc, rep ? 0 : 1, o->G);
             AVI_LAUNCHED(ctx);
         }
@@ -542,6 +554,7 @@ int32_t avi_objective_local(avi_obj* o, const float* lambda) {
         if (tc_ok && avi_obj_defers_scalars(o)) {
             pf.on = 1; pf.lambda = lambda; pf.M = o->M; pf.objective = o->objective; pf.entropy = o->entropy;
             pf.grad = o->grad; pf.out = o->out; pf.logp = o->logp; pf.esq = o->esq; pf.Mloc = Mloc; pf.accv = accv;
+            pf.h0 = o->base.h0;
         }
         if (!tc_ok) {
             k_colsum<<<(unsigned)ceil_div(D, 32), dim3(32, 32), 0, ctx->stream>>>(W, ld, Mloc, D, o->acc);
@@ -559,9 +572,9 @@ int32_t avi_objective_local(avi_obj* o, const float* lambda) {
             else AVI_CHECK(avi_gemm_simt(ctx, o->E, 1, ld, o->U, 1, ld, C2, D, 1, D, D, Mloc, 1.0f));
         }
     }
-    // sample sharding: the partial sums are the exchange payload
+    // sample sharding: the partial sums are the exchange payload (full-rank RepGrad: the second D x D block is unused)
     if (o->shard_axis == AVI_SHARD_SAMPLES && ctx->nranks > 1 && !o->fused_exchange)
-        AVI_CHECK(avi_exchange(ctx, o->acc, o->acc_len));
+        AVI_CHECK(avi_exchange(ctx, o->acc, o->family == AVI_FULLRANK && rep ? o->acc_len - (int64_t)D * D : o->acc_len));
     return AVI_OK;
 }
 
@@ -569,6 +582,7 @@ int32_t avi_objective_fused(avi_obj* o, const float* lambda, const StepTail& tai
     avi_ctx* ctx = o->ctx;
     *taken = false;
     if (o->family != AVI_MEANFIELD || o->objective != AVI_REPGRAD || o->Mloc <= 0) return AVI_OK;
+    if (o->base.kind != AVI_BASE_NORMAL) return AVI_OK;   // (the single-launch iteration draws Normal(0, 1) itself)
     if (!o->model->fused_step_ok(o->Mloc)) return AVI_OK;
     if (lambda_src && !o->model->fused_host_lambda_ok()) return AVI_OK;
     StepTail t = tail;
@@ -624,7 +638,7 @@ int32_t avi_objective_finalize(avi_obj* o, const float* lambda, float* grad, flo
                                        o->objective, o->entropy, (const float*)o->logp, (const float*)o->esq, o->Mloc,
                                        avi_obj_defers_scalars(o) ? 1 : 0, grad, out,
                                        fuse_advance ? o->h_grad : (float*)nullptr,
-                                       fuse_advance ? o->d_state : (ObjDeviceState*)nullptr);
+                                       fuse_advance ? o->d_state : (ObjDeviceState*)nullptr, o->base.h0);
         if (e != cudaSuccess) AVI_FAIL(ctx, AVI_ERR_CUDA, std::string("finalize launch: ") + cudaGetErrorString(e));
         AVI_LAUNCHED(ctx);
     } else {
@@ -643,7 +657,7 @@ int32_t avi_objective_finalize(avi_obj* o, const float* lambda, float* grad, flo
         o->fr_vec_done = false;
         if (!done) {
             k_finalize_fr_vec<<<1, 1024, 0, ctx->stream>>>(o->acc, accv, lambda, D, o->M, o->objective, o->entropy, grad, out,
-                                                           o->logp, o->esq, o->Mloc, avi_obj_defers_scalars(o) ? 1 : 0);
+                                                           o->logp, o->esq, o->Mloc, avi_obj_defers_scalars(o) ? 1 : 0, o->base.h0);
             AVI_LAUNCHED(ctx);
         }
     }

@@ -127,7 +127,7 @@ k_fr_outer_prep(const float* __restrict__ W, const float* __restrict__ E, int Ml
     if (blockIdx.z == 2) {
         if (blockIdx.x == 1 && blockIdx.y == 0 && pf.on) {
             fr_vec_finalize(v, pf.accv, pf.lambda, D, pf.M, pf.objective, pf.entropy, pf.grad, pf.out, pf.logp, pf.esq,
-                            pf.Mloc, /*deferred=*/true, /*write_grad=*/false, &t[0][0]);
+                            pf.Mloc, /*deferred=*/true, /*write_grad=*/false, &t[0][0], pf.h0);
             return;
         }
         if (blockIdx.x != 0) return;

@@ -37,7 +37,7 @@ __device__ __forceinline__ void fr_vec_finalize(const float* __restrict__ acc, i
                                                 int D, int M, int objective, int entropy, float* __restrict__ grad,
                                                 float* __restrict__ out, const float* __restrict__ logp,
                                                 const float* __restrict__ esq, int Mloc, bool deferred, bool write_grad,
-                                                float* sm) {
+                                                float* sm, float h0 = AVI_H0) {
     float part = 0.f;
     for (int i = threadIdx.x; i < D; i += blockDim.x) part += logf(__ldg(lambda + D + (size_t)i * (D + 1)));
     const float logdet = block_sum(part, sm);
@@ -56,7 +56,7 @@ __device__ __forceinline__ void fr_vec_finalize(const float* __restrict__ acc, i
             for (int i = threadIdx.x; i < D; i += blockDim.x) grad[i] = -acc[i] * invM;
         if (threadIdx.x == 0) {
             float ent = (entropy == AVI_ENT_CLOSEDFORM || entropy == AVI_ENT_CLOSEDFORM_ZEROGRAD)
-                            ? (float)D * AVI_H0 + logdet
+                            ? (float)D * h0 + logdet
                             : 0.5f * s1 * invM + 0.5f * (float)D * AVI_LOG2PI + logdet;
             float value = -(s0 * invM + ent);
             out[0] = value; out[1] = -value; out[2] = logdet;

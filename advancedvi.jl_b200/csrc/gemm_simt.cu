@@ -69,7 +69,7 @@ gemm_simt_kernel(const float* __restrict__ A, long long sa_r, long long sa_k,
 // phase 2 back-substitutes inside the 32 x 32 diagonal block with warp shuffles.
 template <int S>
 __global__ void __launch_bounds__(256)
-k_trsm_lt(const float* __restrict__ L, int D, const float* __restrict__ E, float* __restrict__ U, int ld, int M) {
+k_trsm_lt(const float* __restrict__ L, int D, const float* __restrict__ E, float* __restrict__ U, int ld, int M, BaseDist bd) {
     extern __shared__ float smem[];
     float* u = smem;                      // [S][D]
     float* rb = u + (size_t)S * D;        // [S][32]
@@ -104,7 +104,7 @@ k_trsm_lt(const float* __restrict__ L, int D, const float* __restrict__ E, float
                 float t = warp_sum(part[s]);
                 if (lane == 0) {
                     int m = mb + s;
-                    float e = (i < D && m < M) ? E[(size_t)m * ld + i] : 0.0f;
+                    float e = (i < D && m < M) ? base_negscore(bd, E[(size_t)m * ld + i]) : 0.0f;
                     rb[s * 32 + ii] = e - t;
                 }
             }
@@ -131,13 +131,13 @@ k_trsm_lt(const float* __restrict__ L, int D, const float* __restrict__ E, float
 }
 
 template <int S>
-int32_t launch_trsm(avi_ctx* ctx, const float* L, int D, const float* E, float* U, int ld, int M) {
+int32_t launch_trsm(avi_ctx* ctx, const float* L, int D, const float* E, float* U, int ld, int M, const BaseDist& bd) {
     size_t smem = ((size_t)S * D + S * 32 + 32 * 33) * sizeof(float);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k_trsm_lt<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) AVI_FAIL(ctx, AVI_ERR_CUDA, std::string("trsm smem: ") + cudaGetErrorString(e));
     }
-    k_trsm_lt<S><<<(unsigned)ceil_div(M, S), 256, smem, ctx->stream>>>(L, D, E, U, ld, M);
+    k_trsm_lt<S><<<(unsigned)ceil_div(M, S), 256, smem, ctx->stream>>>(L, D, E, U, ld, M, bd);
     AVI_LAUNCHED(ctx);
     return AVI_OK;
 }
@@ -162,12 +162,12 @@ int32_t avi_gemm_simt(avi_ctx* ctx, const float* A, long long sa_r, long long sa
     return AVI_OK;
 }
 
-int32_t avi_trsm_lt(avi_ctx* ctx, const float* L, int D, const float* E, float* U, int ld, int M) {
+int32_t avi_trsm_lt(avi_ctx* ctx, const float* L, int D, const float* E, float* U, int ld, int M, const BaseDist& bd) {
     if (M <= 0) return AVI_OK;
     const size_t budget = 200 * 1024 - (32 * 33) * sizeof(float);
     auto fits = [&](int S) { return ((size_t)S * D + S * 32) * sizeof(float) <= budget; };
-    if (fits(16) && M >= 16) return launch_trsm<16>(ctx, L, D, E, U, ld, M);
-    if (fits(4)) return launch_trsm<4>(ctx, L, D, E, U, ld, M);
-    if (fits(1)) return launch_trsm<1>(ctx, L, D, E, U, ld, M);
+    if (fits(16) && M >= 16) return launch_trsm<16>(ctx, L, D, E, U, ld, M, bd);
+    if (fits(4)) return launch_trsm<4>(ctx, L, D, E, U, ld, M, bd);
+    if (fits(1)) return launch_trsm<1>(ctx, L, D, E, U, ld, M, bd);
     AVI_FAIL(ctx, AVI_ERR_UNSUPPORTED, "full-rank dimension too large for the triangular solve");
 }

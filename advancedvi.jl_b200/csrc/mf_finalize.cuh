@@ -8,6 +8,7 @@
 // sums over the GLOBAL M samples: s0 = sum logp, s1 = sum |eps|^2, s2 = sum f, s3 = sum f^2 (f shifted)
 struct MfSums {
     float s0, s1, s2, s3, logdet;
+    float h0 = AVI_H0;   // entropy of the base distribution (base_dist.cuh); Normal(0, 1) unless the caller overrides it
 };
 
 // gradient entries (d/d mu_i, d/d s_i) of -ELBO (RepGrad) or of the VarGrad value (ScoreGrad) from the
@@ -44,7 +45,7 @@ __device__ __forceinline__ void mf_outputs(int D, int M, int objective, int entr
     const float invM = 1.0f / (float)M;
     if (objective == AVI_REPGRAD) {
         const float ent = (entropy == AVI_ENT_CLOSEDFORM || entropy == AVI_ENT_CLOSEDFORM_ZEROGRAD)
-                              ? (float)D * AVI_H0 + S.logdet
+                              ? (float)D * S.h0 + S.logdet
                               : 0.5f * S.s1 * invM + 0.5f * (float)D * AVI_LOG2PI + S.logdet;
         value = -(S.s0 * invM + ent);
         elbo = -value;

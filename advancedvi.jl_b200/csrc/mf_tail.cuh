@@ -34,6 +34,7 @@ struct MfTailArgs {
     int tl_s;
     CommPeers comm;    // comm.nranks > 1: the sample-sharded exchange of `acc` runs inside this kernel
     long long acc_len;
+    float h0;          // entropy of the base distribution (base_dist.cuh)
 };
 
 // block sum for a 1024-thread CTA addressed by a linear thread id (any block shape); fixed tree
@@ -216,6 +217,7 @@ __device__ __forceinline__ void mf_finalize_update_body(const MfTailArgs& t) {
     const float b1t = sc[SC_B1T], b2t = sc[SC_B2T], t_avg = sc[SC_T], v_old = sc[SC_V], r_old = sc[SC_R];
 
     MfSums S;
+    S.h0 = t.h0;
     float part = 0.f;
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) part += (tid + k * NTH < D) ? __logf(x[k][1]) : 0.f;

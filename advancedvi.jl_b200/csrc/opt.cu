@@ -389,6 +389,7 @@ int32_t enqueue_iteration(avi_opt* op, bool subsampled, int64_t batch) {
     tail.logp = o->logp; tail.esq = o->esq; tail.Mloc = o->Mloc; tail.deferred = avi_obj_defers_scalars(o) ? 1 : 0;
     tail.lam = op->lam; tail.grad = o->grad; tail.m1 = op->m1; tail.m2 = op->m2; tail.avg = op->avg; tail.sc = op->sc;
     tail.out = o->out; tail.st = o->d_state; tail.trace = op->trace; tail.trace_cap = op->trace_cap; tail.a = a;
+    tail.h0 = o->base.h0;
     // sample sharding over the native NVLink exchange: the tail kernel performs the all-reduce itself
     tail.comm.nranks = 1; tail.acc_len = o->acc_len;
     const bool mf_tail = o->family == AVI_MEANFIELD && o->D <= 8 * 1024;

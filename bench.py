@@ -250,8 +250,11 @@ class Bench:
         self.m_loc = M
         if world > 1:
             P = self.obj.P
-            parallel.connect(ctx, max_floats=(4 * ((D + 31) // 32 * 32) + 64) if cfg["family"] == "meanfield" else P + 4 * D + 4096,
-                             native=True)
+            # exchange payload: the partial-sum vector (mean-field), or for the full-rank family the D x D contraction(s)
+            # under sample sharding / the M x D gradient block under row sharding
+            pad = (D + 31) // 32 * 32
+            parallel.connect(ctx, max_floats=(4 * pad + 64) if cfg["family"] == "meanfield"
+                             else max(2 * D * D + 4 * pad + 64, M * ((D + 3) // 4 * 4)), native=True)
             if self.subsampled or self.shard == "rows":
                 self.obj.set_shard_axis(L.SHARD_ROWS)
             else:

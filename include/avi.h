@@ -59,6 +59,8 @@ enum { AVI_GLM_SUBSAMPLING = 0, AVI_GLM_BASIC = 1 };
 enum { AVI_GEMM_SIMT_FP32 = 0, AVI_GEMM_TF32 = 1, AVI_GEMM_TF32X3 = 2 };
 /* which axis a multi-rank run partitions */
 enum { AVI_SHARD_NONE = 0, AVI_SHARD_SAMPLES = 1, AVI_SHARD_ROWS = 2 };
+/* base distribution `dist` of MvLocationScale(location, scale, dist) (src/families/location_scale.jl:15-19) */
+enum { AVI_BASE_NORMAL = 0, AVI_BASE_LAPLACE = 1, AVI_BASE_STUDENT_T = 2 };
 
 /* ---- lifecycle ------------------------------------------------------------------------- */
 int32_t avi_version(void);
@@ -163,6 +165,16 @@ int32_t avi_obj_create(avi_ctx* ctx, avi_model* model, int32_t family, int32_t o
  * operator, and the log q based estimators on more than one rank. */
 int32_t avi_obj_create_lowrank(avi_ctx* ctx, avi_model* model, int32_t rank, int32_t objective, int32_t entropy,
                                int32_t M, avi_obj** out);
+/* Base distribution of MvLocationScale(location, scale, dist) for the mean-field and full-rank families: Normal(0, 1)
+ * (default; MeanFieldGaussian / FullRankGaussian), Laplace(0, 1) or TDist(param) (docs/src/families.md:72-101).  The base
+ * supplies the draws of rand (location_scale.jl:71-87: z = scale * u + location, u iid from dist), logpdf
+ * (:59-63: sum_i logpdf(dist, u_i) - logdet(scale)) and entropy (:52-57: D * entropy(dist) + logdet(scale)); every
+ * objective, entropy estimator, estimate_objective and the optimiser loop work with any base.  Draws are counter-based
+ * (Philox) like the normals: Laplace by inversion, Student-t by Bailey's polar transform (no rejection).  The
+ * single-launch iteration is a Normal(0, 1) kernel: other bases run the multi-kernel path.  AVI_ERR_UNSUPPORTED for the
+ * low-rank family (LowRankGaussian is Gaussian by definition) and for ProximalLocationScaleEntropy-style zero-gradient
+ * closed forms nothing changes (the entropy constant does not enter a gradient). */
+int32_t avi_obj_set_base(avi_obj* obj, int32_t base, float param);
 /* set_objective_state_problem (repgradelbo.jl:31-39, scoregradelbo.jl:24-32) */
 int32_t avi_obj_set_model(avi_obj* obj, avi_model* model);
 /* eps[i, m] at step t is a pure function of (key, t, m, i) (Philox4x32-10 + Box-Muller);

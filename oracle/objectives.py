@@ -81,12 +81,14 @@ def repgrad_value_and_gradient(params, q_template: MvLocationScale, prob, eps: n
     sd = q.scale_diag()
     stl = entropy in ("StickingTheLandingEntropy", "StickingTheLandingEntropyZeroGradient")
     if stl:
-        # w_m = g_m - grad_z log q_stop(z_m) = g_m + L^{-T} eps_m
+        # w_m = g_m - grad_z log q_stop(z_m) = g_m - L^{-T} score(eps_m), score = d log phi / du of the base
+        # distribution: -u for Normal(0, 1), i.e. the g_m + L^{-T} eps_m of Appendix A.3
+        sc = -q.dist.score(eps)
         if q.is_meanfield:
-            W = G + eps / sd[:, None]
+            W = G + sc / sd[:, None]
         else:
             from scipy.linalg import solve_triangular
-            W = G + solve_triangular(q.scale.T, eps, lower=False)
+            W = G + solve_triangular(q.scale.T, sc, lower=False)
     else:
         W = G
     g_mu = -np.mean(W, axis=1)
@@ -130,16 +132,17 @@ def scoregrad_value_and_gradient(params, q_template: MvLocationScale, prob, eps)
     value = (np.mean(f * f) - np.mean(f) ** 2) / 2
     c = f - np.mean(f)
     u = q.standardize(Z)                                  # == eps up to rounding
+    s = -q.dist.score(u)                                  # -d log phi / du of the base distribution: u for Normal(0, 1)
     sd = q.scale_diag()
     if q.is_meanfield:
-        g_mu = np.mean(c[None, :] * u, axis=1) / sd
-        g_sc = np.mean(c[None, :] * (u * u - 1.0), axis=1) / sd
+        g_mu = np.mean(c[None, :] * s, axis=1) / sd
+        g_sc = np.mean(c[None, :] * (s * u - 1.0), axis=1) / sd
     else:
         from scipy.linalg import solve_triangular
-        # d logq/d mu = L^{-T} u ; d logq/d L = tril(L^{-T} u u') - diag(1/L_ii)
-        Linv_T_u = solve_triangular(q.scale.T, u, lower=False)
+        # d logq/d mu = L^{-T} s ; d logq/d L = tril(L^{-T} s u') - diag(1/L_ii)
+        Linv_T_u = solve_triangular(q.scale.T, s, lower=False)
         g_mu = np.mean(c[None, :] * Linv_T_u, axis=1)
-        S = (u * c[None, :]) @ u.T / M
+        S = (s * c[None, :]) @ u.T / M
         g_sc = np.tril(solve_triangular(q.scale.T, S, lower=False)) - np.mean(c) * np.diag(1.0 / sd)
     elbo = np.mean(logpi - logq)                          # :113-114
     return value, _scale_grad_pack(q, g_mu, g_sc), elbo

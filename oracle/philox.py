@@ -103,6 +103,42 @@ def normal_matrix(key: int, step: int, D: int, M: int, m0: int = 0,
     return np.ascontiguousarray(eps).astype(dtype)
 
 
+STREAM_EPS_B = 4      # second word block of the Student-t base draws (two variates per Philox block)
+
+
+def _eps_words(key: int, step: int, D: int, M: int, m0: int, stream: int) -> np.ndarray:
+    """The raw Philox words behind `normal_matrix`: (nq, M, 4) uint32, same counter layout."""
+    nq = (D + 3) // 4
+    ctr = np.empty((nq, M, 4), dtype=np.uint64)
+    ctr[..., 0] = np.arange(nq, dtype=np.uint64)[:, None]
+    ctr[..., 1] = (np.arange(M, dtype=np.uint64) + np.uint64(m0))[None, :]
+    ctr[..., 2] = np.uint64(int(step) & 0xFFFFFFFF)
+    ctr[..., 3] = np.uint64((int(stream) & 0xFF) | (((int(step) >> 32) & 0xFFFFFF) << 8))
+    return philox4x32_10(ctr, split_key(key))
+
+
+def laplace_matrix(key: int, step: int, D: int, M: int, m0: int = 0, dtype=np.float64) -> np.ndarray:
+    """iid Laplace(0, 1) draws in R^{D x M} (base distribution of docs/src/families.md:88-101) by inversion of the CDF
+    of the 23-bit uniform of every Philox word: p < 1/2 -> log(2 p), else -log(2 (1 - p)).  Word k of block (i // 4, m)
+    is coordinate 4 (i // 4) + k, as for the normals."""
+    p = uniform23(_eps_words(key, step, D, M, m0, STREAM_EPS))          # (nq, M, 4)
+    u = np.where(p < 0.5, np.log(2.0 * p), -np.log(2.0 * (1.0 - p)))
+    return np.ascontiguousarray(np.transpose(u, (0, 2, 1)).reshape(-1, M)[:D]).astype(dtype)
+
+
+def student_t_matrix(key: int, step: int, D: int, M: int, nu: float, m0: int = 0, dtype=np.float64) -> np.ndarray:
+    """iid TDist(nu) draws in R^{D x M} (docs/src/families.md:72-86) without rejection (Bailey 1994): with U, V
+    uniform, sqrt(nu (U^(-2/nu) - 1)) cos(2 pi V) is t_nu.  The sine partner is not independent of the cosine one, so a
+    pair of words gives ONE variate: coordinates 4q, 4q+1 come from words (0,1), (2,3) of the eps-stream block
+    (q, m) and 4q+2, 4q+3 from the block of STREAM_EPS_B."""
+    def half(stream):
+        x = _eps_words(key, step, D, M, m0, stream)
+        U, V = uniform23(x[..., 0::2]), uniform23(x[..., 1::2])          # (nq, M, 2)
+        return np.sqrt(nu * np.expm1(-(2.0 / nu) * np.log(U))) * np.cos(2.0 * np.pi * V)
+    t = np.concatenate([half(STREAM_EPS), half(STREAM_EPS_B)], axis=-1)   # (nq, M, 4)
+    return np.ascontiguousarray(np.transpose(t, (0, 2, 1)).reshape(-1, M)[:D]).astype(dtype)
+
+
 def uniform_u32(key: int, n: int, stream: int, offset: int = 0) -> np.ndarray:
     """n raw uint32 words from stream `stream` (counter = (j // 4 + offset, 0, 0, stream))."""
     nb = (n + 3) // 4

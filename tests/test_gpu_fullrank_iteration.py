@@ -76,18 +76,18 @@ def test_fullrank_trajectory_matches_oracle_exact_fp32(avi, ctx):
     q, info, st = avi.optimize(KEY, _alg(avi, M), T, prob, q0)
     lam, avg, _ = st.params()
     qo = F.FullRankGaussian(q0.location.astype(np.float64), q0.scale.astype(np.float64))
-    po = Mo.LogReg(X.astype(np.float64), y.astype(np.float64))
-    lam_o = qo.destructure()
-    rule = Op.Adam(5e-3)
-    rs = rule.init(lam_o)
-    op = Op.ClipScale(1e-5)
+    po = Mo.LogReg(X, y)
+    rule, op, avgr = Op.Adam(5e-3), Op.ClipScale(), Op.PolynomialAveraging()
+    so = Op.sgd_init(qo, rule, avgr)
+
+    def grad_fn(params, t):
+        v, g, e = O.repgrad_value_and_gradient(params, qo, po, P.normal_matrix(KEY, t - 1, D, M), "ClosedFormEntropy")
+        return v, g, dict(elbo=e)
     for t in range(T):
-        eps = P.normal_matrix(KEY, t, D, M)
-        v, g, elbo = O.repgrad_value_and_gradient(lam_o, qo, po, eps, "ClosedFormEntropy")
-        rs, lam_o = rule.apply(rs, lam_o, g)
-        lam_o = op.apply(qo, lam_o)
+        elbo = Op.sgd_step(so, qo, grad_fn, rule, op, avgr)["elbo"]
         assert abs(info[t]["elbo"] - elbo) <= 5e-5 * abs(elbo), (t, info[t]["elbo"], elbo)
-    assert np.linalg.norm(lam - lam_o) <= 2e-4 * np.linalg.norm(lam_o)
+    assert np.linalg.norm(lam - so.params) <= 2e-4 * np.linalg.norm(so.params)
+    assert np.linalg.norm(avg - so.avg_st[0]) <= 2e-4 * np.linalg.norm(so.avg_st[0])
     st.close(); st.obj.close(); prob.close()
 
 

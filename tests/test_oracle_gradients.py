@@ -161,3 +161,78 @@ def test_lowrank_scoregrad_vs_fd():
     assert np.isclose(v, forward(lam))
     assert np.allclose(g, _fd(forward, lam), rtol=2e-6, atol=2e-7)
     assert np.isclose(e, np.mean(logp - q.logpdf(Z)))
+
+
+# ---- non-Gaussian base distributions of MvLocationScale (docs/src/families.md:72-101) ------------------------------
+def _base(name):
+    return F.LaplaceDist() if name == "laplace" else F.TDistBase(5.0)
+
+
+def _base_draws(name, key, step, D, M):
+    return P.laplace_matrix(key, step, D, M) if name == "laplace" else P.student_t_matrix(key, step, D, M, 5.0)
+
+
+@pytest.mark.parametrize("base", ["laplace", "tdist"])
+@pytest.mark.parametrize("family", ["meanfield", "fullrank"])
+@pytest.mark.parametrize("entropy", O.ENTROPIES)
+def test_repgrad_closed_form_vs_fd_nongaussian_base(base, family, entropy):
+    """The closed forms with eps -> u (draws of the base) and eps -> -score(u) in the sticking-the-landing term equal
+    what AD returns for the restated forward, for every entropy estimator."""
+    D, M = 4, 3
+    prob = make_problem("logreg_subsampling", D)
+    q0 = make_q(family, D)
+    q = F.MvLocationScale(q0.location, q0.scale, _base(base))
+    u = _base_draws(base, 3, 7, D, M)
+    lam = q.destructure()
+    q_stop = q.restructure(lam)
+    v, g, elbo = O.repgrad_value_and_gradient(lam, q, prob, u, entropy)
+    f = lambda p: O.repgrad_forward(p, q, q_stop, prob, u, entropy)
+    assert np.isclose(v, f(lam), rtol=1e-12)
+    g_fd = fd_grad(f, lam)
+    if family == "fullrank":
+        mask = np.concatenate([np.ones(D, bool), np.tril(np.ones((D, D), bool)).reshape(-1, order="F")])
+        g_fd = np.where(mask, g_fd, 0.0)
+    assert np.allclose(g, g_fd, rtol=2e-5, atol=2e-6)
+    if entropy in ("ClosedFormEntropy", "StickingTheLandingEntropy"):   # the round-1 groundwork function agrees
+        v2, g2, _ = O.repgrad_general_base_value_and_gradient(lam, q, prob, u, entropy)
+        assert np.isclose(v, v2, rtol=1e-13) and np.allclose(g, g2, rtol=1e-12, atol=1e-14)
+
+
+@pytest.mark.parametrize("base", ["laplace", "tdist"])
+@pytest.mark.parametrize("family", ["meanfield", "fullrank"])
+def test_scoregrad_closed_form_vs_fd_nongaussian_base(base, family):
+    D, M = 4, 6
+    prob = make_problem("logreg_basic", D)
+    q0 = make_q(family, D)
+    q = F.MvLocationScale(q0.location, q0.scale, _base(base))
+    u = _base_draws(base, 3, 2, D, M)
+    lam = q.destructure()
+    Z = q.rand_from_eps(u)
+    logpi = prob.logdensity_batch(Z)
+    v, g, elbo = O.scoregrad_value_and_gradient(lam, q, prob, u)
+    f = lambda p: O.scoregrad_forward(p, q, Z, logpi)
+    assert np.isclose(v, f(lam), rtol=1e-10)
+    g_fd = fd_grad(f, lam)
+    if family == "fullrank":
+        mask = np.concatenate([np.ones(D, bool), np.tril(np.ones((D, D), bool)).reshape(-1, order="F")])
+        g_fd = np.where(mask, g_fd, 0.0)
+    # (Laplace: the score is discontinuous at 0 -- no draw sits there, and FD with h = 1e-6 stays on one side)
+    assert np.allclose(g, g_fd, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("base,nu", [("laplace", None), ("tdist", 3.0), ("tdist", 7.5)])
+def test_base_draws_follow_their_distribution(base, nu):
+    """The counter-based samplers the device mirrors (inversion for Laplace, Bailey's polar transform for Student-t):
+    Kolmogorov-Smirnov against scipy's CDF, moments, and independence of the coordinates that share a Philox block."""
+    from scipy import stats
+    key = 0x38BEF07CF9CC549D
+    x = P.laplace_matrix(key, 0, 64, 4000) if base == "laplace" else P.student_t_matrix(key, 0, 64, 4000, nu)
+    dist = stats.laplace() if base == "laplace" else stats.t(nu)
+    assert stats.kstest(x.ravel()[:40000], dist.cdf).pvalue > 1e-3
+    assert abs(np.median(x)) < 0.02
+    for a, b in ((0, 1), (0, 2), (1, 3)):
+        assert abs(np.corrcoef(np.abs(x[a]), np.abs(x[b]))[0, 1]) < 0.06
+    # entropy / logpdf of the oracle's base classes against scipy
+    d = F.LaplaceDist() if base == "laplace" else F.TDistBase(nu)
+    assert np.isclose(d.entropy(), dist.entropy(), rtol=1e-12)
+    assert np.allclose(d.logpdf(x[:3, :50]), dist.logpdf(x[:3, :50]), rtol=1e-12, atol=1e-12)
