@@ -14,7 +14,7 @@ using AdvancedVI, ADTypes, DiffResults, LogDensityProblems, Random
 using Optimisers
 using LinearAlgebra
 using LinearAlgebra: Diagonal, LowerTriangular
-using Distributions: Normal
+using Distributions: Normal, Laplace, TDist, dof, params
 using AdvancedVI: RepGradELBO, ScoreGradELBO, SubsampledObjective, MvLocationScale, MvLocationScaleLowRank,
                   ClosedFormEntropy, MonteCarloEntropy, StickingTheLandingEntropy, ClosedFormEntropyZeroGradient,
                   StickingTheLandingEntropyZeroGradient, KLMinRepGradDescent, KLMinRepGradProxDescent,
@@ -202,6 +202,14 @@ entropy_code(::ClosedFormEntropyZeroGradient) = 3
 entropy_code(::StickingTheLandingEntropyZeroGradient) = 4
 kind_code(::RepGradELBO) = 0
 kind_code(::ScoreGradELBO) = 1
+# base distribution `dist` of MvLocationScale(location, scale, dist) (location_scale.jl:15-19; docs/src/families.md:72-101)
+# -> (AVI_BASE_* code, parameter) of avi_obj_set_base
+base_code(d::Normal) = params(d) == (0, 1) ? (Int32(0), 0.0f0) :
+    throw(ArgumentError("AutoB200: the Normal base distribution must be Normal(0, 1) (got $d)"))
+base_code(d::Laplace) = params(d) == (0, 1) ? (Int32(1), 0.0f0) :
+    throw(ArgumentError("AutoB200: the Laplace base distribution must be Laplace(0, 1) (got $d)"))
+base_code(d::TDist) = (Int32(2), Float32(dof(d)))
+base_code(d) = throw(ArgumentError("AutoB200 supports the base distributions Normal(0, 1), Laplace(0, 1) and TDist(nu) (got $d)"))
 objective_entropy_code(obj::RepGradELBO) = entropy_code(obj.entropy)
 objective_entropy_code(::ScoreGradELBO) = 0
 
@@ -218,6 +226,10 @@ function make_state(key::UInt64, kind, entropy, n_samples, q, p::NativeTarget, p
     end
     st = B200ObjState(r[], p)
     finalizer(s -> @ccall(libavi.avi_obj_destroy(s.h::Ptr{Cvoid})::Int32), st)
+    if q isa MvLocationScale
+        bc, bp = base_code(q.dist)
+        bc == 0 || check(@ccall(libavi.avi_obj_set_base(st.h::Ptr{Cvoid}, bc::Int32, bp::Float32)::Int32), c.h)
+    end
     # the Julia rng is used only to draw the Philox key: same seed => identical run (klminrepgraddescent.jl:40-57)
     check(@ccall(libavi.avi_obj_seed(st.h::Ptr{Cvoid}, key::UInt64, 0::UInt64)::Int32), c.h)
     return st
