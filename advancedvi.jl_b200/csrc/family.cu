@@ -32,7 +32,8 @@ namespace {
 // SPLIT == 1 is the bandwidth shape: CTAs stride over groups of SAMPLE_WARPS samples and (mean-field) keep
 // mu and s zero-padded in shared memory, so the per-quad work is Philox + Box-Muller + 2 LDS.128 + 2 STG.128.
 constexpr int SAMPLE_WARPS = 4;
-template <bool FULLRANK, bool HOOK, int SPLIT>
+// GBASE: base distribution other than Normal(0, 1) (base_dist.cuh); the Gaussian instantiations carry none of that code
+template <bool FULLRANK, bool HOOK, int SPLIT, bool GBASE = false>
 __global__ void __launch_bounds__(32 * SAMPLE_WARPS)
 k_sample(const float* __restrict__ lambda, int D, int ld, int m0, int Mloc, const ObjDeviceState* __restrict__ st,
          ObjDeviceState st_val, int use_val, uint32_t stream_id, float* __restrict__ Z,
@@ -77,7 +78,8 @@ k_sample(const float* __restrict__ lambda, int D, int ld, int m0, int Mloc, cons
                 *reinterpret_cast<float4*>(Er3row + 2 * hk.er_seg + i) = z4;
                 continue;
             }
-            const float4 e = base_draw4(bd, (uint32_t)q, (uint32_t)(m0 + m), c2, c3, pk);   // u ~ dist (eps for Normal(0, 1))
+            const float4 e = GBASE ? base_draw4(bd, (uint32_t)q, (uint32_t)(m0 + m), c2, c3, pk)   // u ~ dist
+                                   : normal4((uint32_t)q, (uint32_t)(m0 + m), c2, c3, pk);
             float ev[4] = {e.x, e.y, e.z, e.w}, zv[4] = {0.f, 0.f, 0.f, 0.f}, zt[4];
             if (i + 3 >= D) {   // the row's last quad: zero the padding columns
 #pragma unroll
@@ -103,7 +105,7 @@ k_sample(const float* __restrict__ lambda, int D, int ld, int m0, int Mloc, cons
 #pragma unroll
                 for (int c = 0; c < 4; ++c) zv[c] = fmaf(sv[c], ev[c], mv[c]);   // padding: 0 * 0 + 0
             }
-            if (bd.kind == AVI_BASE_NORMAL) {
+            if (!GBASE) {
 #pragma unroll
                 for (int c = 0; c < 4; ++c) part = fmaf(ev[c], ev[c], part);
             } else {   // sum_i -2 log phi(u_i) - log 2 pi: |eps|^2's role in log q(z) for any base (base_dist.cuh)
@@ -387,12 +389,17 @@ int32_t avi_family_sample(avi_obj* o, const float* lambda, float* Z, float* E, f
     const bool split = Mloc <= 8192 || stage_bytes > 48 * 1024;
     const unsigned sgrid = split ? (unsigned)Mloc
                                  : (unsigned)std::min<int64_t>(ceil_div(Mloc, SAMPLE_WARPS), (int64_t)ctx->prop.multiProcessorCount * 12);
+#define LAUNCH_SAMPLE_B(FR, HK, HOOKV, GB)                                                                           \
+    do {                                                                                                             \
+        if (split) avi_launch_pdl(ctx, k_sample<FR, HK, SAMPLE_WARPS, GB>, dim3(sgrid), dim3(32 * SAMPLE_WARPS), 0,   \
+            lambda, o->D, o->ld, m0, Mloc, st, sv, use_val, (uint32_t)AVI_STREAM_EPS, Z, E, esq, HOOKV, o->base);     \
+        else avi_launch_pdl(ctx, k_sample<FR, HK, 1, GB>, dim3(sgrid), dim3(32 * SAMPLE_WARPS), stage_bytes,          \
+            lambda, o->D, o->ld, m0, Mloc, st, sv, use_val, (uint32_t)AVI_STREAM_EPS, Z, E, esq, HOOKV, o->base);     \
+    } while (0)
 #define LAUNCH_SAMPLE(FR, HK, HOOKV)                                                                                 \
     do {                                                                                                             \
-        if (split) avi_launch_pdl(ctx, k_sample<FR, HK, SAMPLE_WARPS>, dim3(sgrid), dim3(32 * SAMPLE_WARPS), 0,       \
-            lambda, o->D, o->ld, m0, Mloc, st, sv, use_val, (uint32_t)AVI_STREAM_EPS, Z, E, esq, HOOKV, o->base);     \
-        else avi_launch_pdl(ctx, k_sample<FR, HK, 1>, dim3(sgrid), dim3(32 * SAMPLE_WARPS), stage_bytes,              \
-            lambda, o->D, o->ld, m0, Mloc, st, sv, use_val, (uint32_t)AVI_STREAM_EPS, Z, E, esq, HOOKV, o->base);     \
+        if (o->base.kind == AVI_BASE_NORMAL) LAUNCH_SAMPLE_B(FR, HK, HOOKV, false);                                   \
+        else LAUNCH_SAMPLE_B(FR, HK, HOOKV, true);                                                                    \
     } while (0)
     if (o->family == AVI_MEANFIELD) {
         if (hook && hook->kind == 1) LAUNCH_SAMPLE(false, true, *hook);
@@ -424,6 +431,7 @@ int32_t avi_family_sample(avi_obj* o, const float* lambda, float* Z, float* E, f
         }
     }
 #undef LAUNCH_SAMPLE
+#undef LAUNCH_SAMPLE_B
     return AVI_OK;
 }
 
