@@ -1,0 +1,204 @@
+"""Static checks of julia/AdvancedVIB200.jl -- the `@ccall` glue a maintainer adds to AdvancedVI.jl.
+
+Julia is not installed in this image, so the file cannot be executed here; what CAN be verified without Julia is that
+every foreign call in it binds an entry point that include/avi.h declares and libavi_b200.so exports, with the
+declared number of arguments and argument types that agree with the C prototype (pointer / 32-bit / 64-bit / float),
+that its block structure is balanced, that no name is used before it is imported, and -- when the reference checkout
+is present -- that every AdvancedVI function it extends and every name it imports exists in the reference's sources."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GLUE = os.path.join(ROOT, "julia", "AdvancedVIB200.jl")
+HEADER = os.path.join(ROOT, "include", "avi.h")
+REF = "/root/reference"
+
+
+def _strip_c_comments(s):
+    return re.sub(r"/\*.*?\*/", " ", s, flags=re.S)
+
+
+def header_prototypes():
+    """name -> list of C parameter type strings"""
+    src = _strip_c_comments(open(HEADER).read())
+    protos = {}
+    for m in re.finditer(r"\b(int32_t|int64_t|const char\s*\*|void)\s+(avi_\w+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+        args = [a.strip() for a in m.group(3).replace("\n", " ").split(",")] if m.group(3).strip() not in ("", "void") else []
+        protos[m.group(2)] = args
+    return protos
+
+
+def _strip_julia(s):
+    """comments and string literals out (keeps line structure)"""
+    s = re.sub(r'""".*?"""', lambda m: '""' + "\n" * m.group(0).count("\n"), s, flags=re.S)   # docstrings
+    s = re.sub(r"#=.*?=#", lambda m: "\n" * m.group(0).count("\n"), s, flags=re.S)             # block comments
+    out = []
+    for line in s.split("\n"):
+        buf, i, in_str = [], 0, False
+        while i < len(line):
+            ch = line[i]
+            if in_str:
+                if ch == "\\":
+                    i += 2
+                    continue
+                if ch == '"':
+                    in_str = False
+                i += 1
+                continue
+            if ch == '"':
+                in_str = True
+                buf.append('""')
+                i += 1
+                continue
+            if ch == "#":
+                break
+            buf.append(ch)
+            i += 1
+        out.append("".join(buf))
+    return "\n".join(out)
+
+
+def _split_top_level(s, sep=","):
+    parts, depth, cur = [], 0, []
+    for ch in s:
+        if ch in "([{":
+            depth += 1
+        elif ch in ")]}":
+            depth -= 1
+        if ch == sep and depth == 0:
+            parts.append("".join(cur))
+            cur = []
+        else:
+            cur.append(ch)
+    if "".join(cur).strip():
+        parts.append("".join(cur))
+    return [p.strip() for p in parts]
+
+
+def glue_ccalls():
+    """[(symbol, [julia arg type, ...], return type)]"""
+    src = _strip_julia(open(GLUE).read())
+    calls = []
+    for m in re.finditer(r"@ccall\s*\(?\s*libavi\.(avi_\w+)\(", src):
+        i = m.end()
+        depth, j = 1, i
+        while depth:
+            depth += {"(": 1, ")": -1}.get(src[j], 0)
+            j += 1
+        args = _split_top_level(src[i:j - 1].replace("\n", " "))
+        ret = re.match(r"\s*::\s*(\w+(\{[^}]*\})?)", src[j:])
+        types = []
+        for a in args:
+            depth, k = 0, len(a) - 1        # the LAST top-level `::` of the argument
+            pos = -1
+            while k > 0:
+                depth += {")": 1, "]": 1, "}": 1, "(": -1, "[": -1, "{": -1}.get(a[k], 0)
+                if depth == 0 and a[k - 1:k + 1] == "::":
+                    pos = k - 1
+                    break
+                k -= 1
+            assert pos >= 0, f"{m.group(1)}: argument without a type annotation: {a!r}"
+            types.append(a[pos + 2:].strip())
+        calls.append((m.group(1), types, ret.group(1) if ret else None))
+    return calls
+
+
+def _c_class(t):
+    t = t.replace("const ", "").strip()
+    if "*" in t or "avi_allreduce_fn" in t or "avi_logdensity_fn" in t or re.search(r"_fn\b", t):
+        return "ptr"
+    base = t.split()[0]
+    return {"int32_t": "i32", "int64_t": "i64", "uint64_t": "u64", "uint32_t": "u32", "float": "f32", "double": "f64"}[base]
+
+
+def _jl_class(t):
+    if t.startswith(("Ptr{", "Ref{")) or t in ("Cstring", "Ptr"):
+        return "ptr"
+    return {"Int32": "i32", "Cint": "i32", "Int64": "i64", "Clonglong": "i64", "UInt64": "u64", "UInt32": "u32",
+            "Float32": "f32", "Cfloat": "f32", "Float64": "f64", "Cdouble": "f64"}[t]
+
+
+def test_every_ccall_binds_a_declared_and_exported_symbol_with_matching_signature():
+    protos = header_prototypes()
+    assert len(protos) > 50
+    lib = ctypes.CDLL(os.path.join(ROOT, "advancedvi.jl_b200", "libavi_b200.so"))
+    calls = glue_ccalls()
+    assert len(calls) >= 25
+    for name, jl_types, ret in calls:
+        assert name in protos, f"{name} is not declared in include/avi.h"
+        assert hasattr(lib, name), f"{name} is not exported by libavi_b200.so"
+        c_args = protos[name]
+        assert len(c_args) == len(jl_types), f"{name}: {len(jl_types)} arguments in the glue, {len(c_args)} in avi.h"
+        for k, (ct, jt) in enumerate(zip(c_args, jl_types)):
+            assert _c_class(ct) == _jl_class(jt), f"{name}: argument {k} is `{ct}` in avi.h but `{jt}` in the glue"
+        assert ret in ("Int32", "Int64", "Cstring", "Cvoid"), (name, ret)
+
+
+def test_block_structure_is_balanced():
+    """Every function / if / for / while / let / struct / module / begin / try / do / quote / macro has its `end`
+    (`a[end]` and generators / comprehensions live inside brackets and are not block structure)."""
+    for path in (GLUE, os.path.join(ROOT, "julia", "test", "runtests.jl")):
+        src = _strip_julia(open(path).read())
+        depth = 0          # nesting of ( and [
+        opens = ends = 0
+        for tok in re.finditer(r"[\[\]()]|\b(function|if|for|while|let|struct|module|begin|try|do|quote|macro|end)\b", src):
+            t = tok.group(0)
+            if t in "([":
+                depth += 1
+            elif t in ")]":
+                depth -= 1
+                assert depth >= 0, f"{os.path.basename(path)}: unbalanced bracket near offset {tok.start()}"
+            elif t == "end":
+                if depth == 0:
+                    ends += 1
+            elif t in ("for", "if"):
+                if depth == 0:
+                    opens += 1
+            else:
+                opens += 1          # (`function` / `begin` / `do` blocks may sit inside a call's parentheses)
+                if depth > 0 and t in ("function", "begin", "do", "let", "try", "quote"):
+                    ends -= 1       # ... and so does their `end`: account for it here
+        assert depth == 0, f"{os.path.basename(path)}: unbalanced brackets"
+        assert opens == ends, f"{os.path.basename(path)}: {opens} block openers vs {ends} `end`"
+
+
+def test_names_are_imported_before_use():
+    """The round-1 glue used Optimisers, LinearAlgebra.AbstractTriangular and Normal without importing them."""
+    raw = open(GLUE).read()
+    src = _strip_julia(raw)
+    header = src[:src.index("const libavi")]
+    for mod in ("Optimisers", "LinearAlgebra", "Random", "DiffResults", "LogDensityProblems", "ADTypes", "AdvancedVI"):
+        if re.search(rf"\b{mod}\.", src):
+            assert re.search(rf"\busing\b[^\n]*\b{mod}\b", header) or re.search(rf"\bimport\b[^\n]*\b{mod}\b", header), mod
+    imported = set(re.findall(r"\b[A-Z]\w+", " ".join(re.findall(r"using \w+: ([^\n]*(?:\n {4,}[^\n]*)*)", header))))
+    for name in ("Normal", "Laplace", "TDist", "Diagonal", "LowerTriangular", "RepGradELBO", "ScoreGradELBO", "SubsampledObjective",
+                 "MvLocationScale", "MvLocationScaleLowRank", "ClipScale", "IdentityOperator", "PolynomialAveraging", "DoG", "DoWG"):
+        if re.search(rf"(?<![\w.]){name}\b", src[len(header):]):
+            assert name in imported, f"{name} is used but not imported"
+    # every struct field read through `.c.` exists on Ctx (round 1 read prob.c.device, which Ctx did not have)
+    ctx_def = re.search(r"mutable struct Ctx(.*?)\nend", src, flags=re.S).group(1)
+    ctx_fields = set(re.findall(r"^\s*(\w+)::", ctx_def, flags=re.M))
+    for f in set(re.findall(r"\.c\.(\w+)", src)):
+        assert f in ctx_fields, f"Ctx has no field `{f}`"
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "src")), reason="reference checkout not present")
+def test_extended_functions_and_imported_names_exist_in_the_reference():
+    ref_src = ""
+    for dp, _, fns in os.walk(os.path.join(REF, "src")):
+        for fn in fns:
+            if fn.endswith(".jl"):
+                ref_src += open(os.path.join(dp, fn)).read() + "\n"
+    src = _strip_julia(open(GLUE).read())
+    for fn in set(re.findall(r"function AdvancedVI\.(\w+!?)\(", src)) | set(re.findall(r"^AdvancedVI\.(\w+!?)\(", src, flags=re.M)):
+        assert re.search(rf"function {re.escape(fn)}\s*[({{]|^{re.escape(fn)}\(|\b{re.escape(fn)}\(.*\) =", ref_src, flags=re.M), \
+            f"AdvancedVI.{fn} is extended by the glue but not defined in the reference"
+    header = src[:src.index("const libavi")]
+    names = re.findall(r"\b\w+", " ".join(re.findall(r"using AdvancedVI: ([^\n]*(?:\n {4,}[^\n]*)*)", header)))
+    assert len(names) > 10
+    for name in names:
+        assert re.search(rf"\b(struct|function|abstract type)\s+{name}\b|^{name}\(|const {name}\b", ref_src, flags=re.M), \
+            f"`{name}` is imported from AdvancedVI but not defined in the reference"
