@@ -224,23 +224,25 @@ __global__ void k_glm_layout(const float* __restrict__ src, long long n, int d, 
 
 // minibatch gather: rows idx[cursor*batch + j] of the full data -> contiguous batch buffers (both layouts).
 // 3xTF32 (segd > 0): the source row is [hi | lo | hi]; Xc_b rows are rebuilt as [hi | hi | lo] in segments of segnb.
+// idx == nullptr: identity (Xr_full is then the batch buffer itself: only the column layout is rebuilt, see
+// Glm::ensure_cols); write_rows == 0: Xr_b / y_b are left alone.
 __global__ void k_glm_gather(const float* __restrict__ Xr_full, const float* __restrict__ y_full, int dK, int d,
                              const int32_t* __restrict__ idx, const ObjDeviceState* __restrict__ st, long long batch,
                              long long nPb, int segd, long long segnb, float* __restrict__ Xr_b,
-                             float* __restrict__ Xc_b, float* __restrict__ y_b) {
+                             float* __restrict__ Xc_b, float* __restrict__ y_b, int write_rows) {
     __shared__ float t[32][33];
-    const int32_t* ix = idx + (st ? st->batch_cursor * batch : 0);
+    const int32_t* ix = idx ? idx + (st ? st->batch_cursor * batch : 0) : nullptr;
     const long long j0 = (long long)blockIdx.x * 32;
     const int c0 = blockIdx.y * 32;
     for (int yy = threadIdx.y; yy < 32; yy += blockDim.y) {
         long long j = j0 + yy; int c = c0 + threadIdx.x;
         float v = 0.0f;
         if (j < batch && c < dK) {
-            v = Xr_full[(size_t)ix[j] * dK + c];
-            Xr_b[(size_t)j * dK + c] = v;
+            v = Xr_full[(size_t)(ix ? (long long)ix[j] : j) * dK + c];
+            if (write_rows) Xr_b[(size_t)j * dK + c] = v;
         }
         t[yy][threadIdx.x] = v;
-        if (blockIdx.y == 0 && threadIdx.x == 0 && j < batch) y_b[j] = y_full[ix[j]];
+        if (write_rows && blockIdx.y == 0 && threadIdx.x == 0 && j < batch) y_b[j] = y_full[ix ? (long long)ix[j] : j];
     }
     __syncthreads();
     for (int yy = threadIdx.y; yy < 32; yy += blockDim.y) {
@@ -255,6 +257,23 @@ __global__ void k_glm_gather(const float* __restrict__ Xr_full, const float* __r
                 if (c - segd < d) Xc_b[(size_t)(c - segd) * nPb + 2 * segnb + j] = v;
             }
         }
+    }
+}
+
+// minibatch gather, rows only: row idx[cursor*batch + j] -> row j of the batch buffer, 16 bytes per thread.  What the
+// whole-iteration kernel needs (it reads the row-major copy for both contractions); the column layout is rebuilt on
+// demand for the kernels that want it (Glm::ensure_cols).
+__global__ void __launch_bounds__(128)
+k_glm_gather_rows(const float* __restrict__ Xr_full, const float* __restrict__ y_full, int dK,
+                  const int32_t* __restrict__ idx, const ObjDeviceState* __restrict__ st, long long batch,
+                  float* __restrict__ Xr_b, float* __restrict__ y_b) {
+    const int32_t* ix = idx + (st ? st->batch_cursor * batch : 0);
+    for (long long j = blockIdx.x; j < batch; j += gridDim.x) {
+        const long long r = ix[j];
+        const float4* src = reinterpret_cast<const float4*>(Xr_full + (size_t)r * dK);
+        float4* dst = reinterpret_cast<float4*>(Xr_b + (size_t)j * dK);
+        for (int q = threadIdx.x; q < dK / 4; q += blockDim.x) dst[q] = __ldg(src + q);
+        if (threadIdx.x == 0) y_b[j] = y_full[r];
     }
 }
 
@@ -389,6 +408,7 @@ struct Glm : avi_model {
 
     // store: the plain store epilogue follows (full gradient G): the planner may trade k-splits for b-chunks
     int32_t backward_setup(int M, TcParams* p, CUtensorMap* tmA, CUtensorMap* tmB, bool store = false) {
+        AVI_CHECK(ensure_cols());
         AVI_CHECK(avi_tc_plan(ctx, d, M, kb(), true, cluster_mode, p, 1, 0, store ? 1 : 0));
         p->static_op = subsampled ? 0 : 1;   // A = X columns
         p->tl = ctx->tl; p->tl_id = 2;
@@ -407,6 +427,7 @@ struct Glm : avi_model {
         if (G) {
             if (!tc_mode()) {
                 // G[m][i] = sum_j R[m][j] Xc[i][j]
+                AVI_CHECK(ensure_cols());
                 AVI_CHECK(avi_gemm_simt(ctx, R, ldR, 1, Xc, nP, 1, G, ld, 1, M, d, (int)n_act, 1.0f));
                 sl = G; nslab = 1; sstride = 0;
             } else {
@@ -521,6 +542,7 @@ struct Glm : avi_model {
                 AVI_CHECK(avi_tc_make_tmap(ctx, &tmXc, Xr, n_act, x3 ? 3LL * segd : d, dK, 32, /*atom32=*/1));
             }
         } else {
+            if (!fa.dry_run) AVI_CHECK(ensure_cols());
             AVI_CHECK(avi_tc_make_tmap(ctx, &tmXc, Xc, d, kb(), nP, 128));
         }
         // R between the phases: transposed (data row major) by default, so that the forward epilogue's stores coalesce; the
@@ -577,13 +599,35 @@ struct Glm : avi_model {
         AVI_CHECK(avi_alloc(ctx, &y_b, (size_t)batch_cap));
         return AVI_OK;
     }
-    int32_t gather(const int32_t* idx_dev, long long batch, const ObjDeviceState* st) {
+    // Xc_b holds the columns of the rows currently in Xr_b?  (The device-side gather of the optimiser loop copies rows
+    // only; whoever needs the column layout -- the stand-alone backward contraction, the SIMT path -- rebuilds it.)
+    bool cols_valid = true;
+    int32_t ensure_cols() {
+        if (!subsampled || cols_valid) return AVI_OK;
+        dim3 grid((unsigned)ceil_div(segn_b, 32), (unsigned)ceil_div(dK, 32));
+        k_glm_gather<<<grid, dim3(32, 8), 0, ctx->stream>>>(Xr_b, y_b, dK, d, (const int32_t*)nullptr, (const ObjDeviceState*)nullptr,
+                                                            n_act, nP_b, x3 ? segd : 0, segn_b, Xr_b, Xc_b, y_b, 0);
+        AVI_LAUNCHED(ctx);
+        cols_valid = true;
+        return AVI_OK;
+    }
+    int32_t gather(const int32_t* idx_dev, long long batch, const ObjDeviceState* st, bool rows_only = false) {
         AVI_CHECK(ensure_batch(batch));
+        static const bool lazy_cols = !(getenv("AVI_GATHER_ROWS") && atoi(getenv("AVI_GATHER_ROWS")) == 0);
+        if (rows_only && lazy_cols && dK % 4 == 0) {
+            k_glm_gather_rows<<<(unsigned)std::min<long long>(batch, 8192), 128, 0, ctx->stream>>>(Xr_full, y_full, dK, idx_dev, st,
+                                                                                                  batch, Xr_b, y_b);
+            AVI_LAUNCHED(ctx);
+            cols_valid = false;
+            Xr = Xr_b; Xc = Xc_b; y = y_b; n_act = batch; nP = nP_b; segn = segn_b; subsampled = true;
+            return AVI_OK;
+        }
         // the pitch of Xc_b follows the allocated capacity so that captured tensor maps stay valid
         dim3 grid((unsigned)ceil_div(segn_b, 32), (unsigned)ceil_div(dK, 32));
         k_glm_gather<<<grid, dim3(32, 8), 0, ctx->stream>>>(Xr_full, y_full, dK, d, idx_dev, st, batch, nP_b,
-                                                            x3 ? segd : 0, segn_b, Xr_b, Xc_b, y_b);
+                                                            x3 ? segd : 0, segn_b, Xr_b, Xc_b, y_b, 1);
         AVI_LAUNCHED(ctx);
+        cols_valid = true;
         // (buffers and pitches follow the allocated capacity: graphs captured on a view of this shape stay valid; a
         // different shape is a different view_key())
         Xr = Xr_b; Xc = Xc_b; y = y_b; n_act = batch; nP = nP_b; segn = segn_b; subsampled = true;
@@ -605,7 +649,7 @@ struct Glm : avi_model {
     }
     int32_t subsample_dev(const int32_t* idx_dev, int64_t batch, const ObjDeviceState* st) override {
         if (batch <= 0 || batch > n_full) AVI_FAIL(ctx, AVI_ERR_INVALID, "bad batch size");
-        return gather(idx_dev, batch, st);
+        return gather(idx_dev, batch, st, /*rows_only=*/true);
     }
     int32_t set_gemm_mode(int m) override {
         if (m == mode) return AVI_OK;
