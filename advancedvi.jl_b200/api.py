@@ -728,6 +728,18 @@ class Objective:
         L.check(L.lib.avi_obj_rand(self.h, L.fptr(params), len(params), L.fptr(Z), L.fptr(E)), self.ctx.h)
         return np.ascontiguousarray(Z.T), np.ascontiguousarray(E.T)
 
+    def rand_batch_match_samples_with_objective(self, q: MvLocationScale, n_samples: int):
+        """rand_batch_match_samples_with_objective!(rng, q, n_samples, prob, u_buf, grad_buf), the sampling stage of
+        FisherMinBatchMatch (src/algorithms/fisherminbatchmatch.jl:81-111) -> (u, z, grad (each D x n_samples), fisher,
+        logpi_avg); the draws are the objective's Philox stream at its current step (which then advances)."""
+        params = q.destructure()
+        D = len(q)
+        U, Z, G = (np.empty((n_samples, D), np.float32) for _ in range(3))
+        fisher, lp = C.c_float(), C.c_float()
+        L.check(L.lib.avi_obj_batch_match_samples(self.h, L.fptr(params), len(params), int(n_samples), L.fptr(U), L.fptr(Z),
+                                                  L.fptr(G), C.byref(fisher), C.byref(lp)), self.ctx.h)
+        return (np.ascontiguousarray(U.T), np.ascontiguousarray(Z.T), np.ascontiguousarray(G.T), fisher.value, lp.value)
+
     def gaussian_expectation_gradient_and_hessian(self, q: MvLocationScale, n_samples: int):
         """gaussian_expectation_gradient_and_hessian!(rng, q, n_samples, grad_buf, hess_buf, prob), first-order (Stein)
         branch of src/algorithms/gauss_expected_grad_hess.jl:20-58 -> (logpi_avg, grad (D), hess (D, D)); the draws

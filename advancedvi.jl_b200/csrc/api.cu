@@ -697,6 +697,51 @@ int32_t avi_obj_gauss_expected_grad_hess(avi_obj* o, const float* lambda_host, i
     return AVI_OK;
 }
 
+// rand_batch_match_samples_with_objective! (src/algorithms/fisherminbatchmatch.jl:81-111): the full-rank sampling
+// kernels, the target's batched log-density + gradient, T = G C (row b: C' grad_b; exact-fp32 SIMT contraction over
+// the lower triangle) and per-sample |u_b + T_b|^2; sums finish on the host in double.  Chunks of <= 4096 samples.
+int32_t avi_obj_batch_match_samples(avi_obj* o, const float* lambda_host, int64_t P, int32_t n_samples, float* u_host,
+                                    float* z_host, float* grad_host, float* fisher, float* logpi_avg) {
+    if (!o || !fisher || !logpi_avg) return AVI_ERR_INVALID;
+    avi_ctx* ctx = o->ctx;
+    if (o->family != AVI_FULLRANK || o->base.kind != AVI_BASE_NORMAL)
+        AVI_FAIL(ctx, AVI_ERR_INVALID, "rand_batch_match_samples_with_objective! needs a full-rank (triangular scale) Gaussian");
+    if (o->model->capability < 1)
+        AVI_FAIL(ctx, AVI_ERR_UNSUPPORTED, "`FisherMinBatchMatch` requires at least first-order differentiation capability");
+    AVI_CHECK(check_lambda(o, lambda_host, P));
+    if (n_samples < 1) AVI_FAIL(ctx, AVI_ERR_INVALID, "n_samples must be >= 1");
+    if (ctx->nranks > 1 && o->shard_axis == AVI_SHARD_ROWS) AVI_FAIL(ctx, AVI_ERR_UNSUPPORTED, "row-sharded targets are not supported here");
+    cudaSetDevice(ctx->device);
+    const int D = o->D, ld = o->ld;
+    const int chunk = std::min(n_samples, 4096);
+    AVI_CHECK(avi_obj_ensure_capacity(o, chunk));
+    std::memcpy(o->h_lambda, lambda_host, (size_t)P * sizeof(float));
+    AVI_CUDA(ctx, cudaMemcpyAsync(o->d_lambda, o->h_lambda, (size_t)P * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<float> lp((size_t)chunk), fr((size_t)chunk);
+    double s_logp = 0.0, s_fisher = 0.0;
+    const size_t row = (size_t)D * sizeof(float), pitch = (size_t)ld * sizeof(float);
+    for (int m0 = 0; m0 < n_samples; m0 += chunk) {
+        const int Mc = std::min(chunk, n_samples - m0);
+        AVI_CHECK(avi_family_sample(o, o->d_lambda, o->Z, o->E, o->esq, Mc, m0, o->d_state, nullptr));
+        AVI_CHECK(o->model->eval(o->Z, ld, Mc, o->logp, o->G));
+        // T[b][j] = sum_{i >= j} G[b][i] C[i + D j]: a = sample b (rows of G), b = column j of C, k = i
+        AVI_CHECK(avi_gemm_simt(ctx, o->G, ld, 1, o->d_lambda + D, D, 1, o->U, ld, 1, Mc, D, D, 1.0f));
+        AVI_CHECK(avi_rowsq_sum(ctx, o->E, o->U, ld, D, Mc, o->fbuf));   // fbuf[b] = |u_b + T_b|^2
+        AVI_CUDA(ctx, cudaMemcpyAsync(lp.data(), o->logp, (size_t)Mc * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        AVI_CUDA(ctx, cudaMemcpyAsync(fr.data(), o->fbuf, (size_t)Mc * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        if (u_host) AVI_CUDA(ctx, cudaMemcpy2DAsync(u_host + (size_t)m0 * D, row, o->E, pitch, row, (size_t)Mc, cudaMemcpyDeviceToHost, ctx->stream));
+        if (z_host) AVI_CUDA(ctx, cudaMemcpy2DAsync(z_host + (size_t)m0 * D, row, o->Z, pitch, row, (size_t)Mc, cudaMemcpyDeviceToHost, ctx->stream));
+        if (grad_host) AVI_CUDA(ctx, cudaMemcpy2DAsync(grad_host + (size_t)m0 * D, row, o->G, pitch, row, (size_t)Mc, cudaMemcpyDeviceToHost, ctx->stream));
+        AVI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int b = 0; b < Mc; ++b) { s_logp += lp[(size_t)b]; s_fisher += fr[(size_t)b]; }
+    }
+    AVI_CHECK(avi_obj_advance(o));
+    AVI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *fisher = (float)(s_fisher / n_samples);
+    *logpi_avg = (float)(s_logp / n_samples);
+    return AVI_OK;
+}
+
 // Random.shuffle(rng, dataset) of src/reshuffling.jl:29 as a pure function of (key, shuffle_index):
 // Fisher-Yates, descending i, j = (word_i * (i + 1)) >> 32 with word_i the i-th Philox4x32-10 output
 // word of counter (i / 4, shuffle_index, 0, STREAM_SHUFFLE).  Host-side integer arithmetic.

@@ -342,6 +342,7 @@ bool avi_lr_needs_logq(const avi_obj* o);
 int32_t avi_lr_logq(avi_obj* o, const float* lambda, int Mloc, bool forward_only = false);   // w, U'w, log q per sample (+ G += w for RepGrad)
 int32_t avi_lr_logq_sums(avi_obj* o, int Mloc);
 int32_t avi_axpy(avi_ctx* ctx, const float* x, float* y, int64_t n);                                   // y += x
+int32_t avi_rowsq_sum(avi_ctx* ctx, const float* A, const float* B, int ld, int D, int M, float* out);   // out[m] = |A_m + B_m|^2
 int32_t avi_colsum_add(avi_ctx* ctx, const float* W, int ld, int Mloc, int D, float* tmp, float* dst);  // dst += column sums
 int32_t avi_obj_stage_lambda(avi_obj* o);   // o->h_lambda (pinned, mapped) -> o->d_lambda by a kernel
 int32_t avi_objective_local(avi_obj* o, const float* lambda);          // sample + model + reduce -> acc

@@ -452,6 +452,25 @@ int32_t avi_axpy(avi_ctx* ctx, const float* x, float* y, int64_t n) {
     AVI_LAUNCHED(ctx);
     return AVI_OK;
 }
+// out[m] = sum_i (A[m][i] + B[m][i])^2: one CTA per sample, fixed summation order
+__global__ void __launch_bounds__(256)
+k_rowsq_sum(const float* __restrict__ A, const float* __restrict__ B, int ld, int D, float* __restrict__ out) {
+    __shared__ float sm[33];
+    const int m = blockIdx.x;
+    float part = 0.f;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+        const float v = A[(size_t)m * ld + i] + B[(size_t)m * ld + i];
+        part = fmaf(v, v, part);
+    }
+    part = block_sum(part, sm);
+    if (threadIdx.x == 0) out[m] = part;
+}
+int32_t avi_rowsq_sum(avi_ctx* ctx, const float* A, const float* B, int ld, int D, int M, float* out) {
+    if (M <= 0) return AVI_OK;
+    k_rowsq_sum<<<(unsigned)M, 256, 0, ctx->stream>>>(A, B, ld, D, out);
+    AVI_LAUNCHED(ctx);
+    return AVI_OK;
+}
 int32_t avi_colsum_add(avi_ctx* ctx, const float* W, int ld, int Mloc, int D, float* tmp, float* dst) {
     k_colsum<<<(unsigned)ceil_div(D, 32), dim3(32, 32), 0, ctx->stream>>>(W, ld, Mloc, D, tmp);
     AVI_LAUNCHED(ctx);

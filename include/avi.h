@@ -208,6 +208,14 @@ int32_t avi_obj_rand(avi_obj* obj, const float* lambda_host, int64_t P, float* Z
  * = C' \ mean(u grad log pi(z)').  obj must be a full-rank objective (lambda = [m; vec(C)]); draws come from the
  * objective's Philox stream at its current step, which then advances.  The sampling stage of KLMinWassFwdBwd,
  * KLMinNaturalGradDescent and KLMinSqrtNaturalGradDescent (klminwassfwdbwd.jl:101, klminnaturalgraddescent.jl:120). */
+/* rand_batch_match_samples_with_objective!(rng, q, n_samples, prob, u_buf, grad_buf) -- the sampling stage of
+ * FisherMinBatchMatch, src/algorithms/fisherminbatchmatch.jl:81-111: u ~ N(0, I) (D x n), z = C u + mu, grad[:, b] =
+ * grad log pi(z_b), *logpi_avg = mean log pi(z_b) and the Fisher-divergence estimate *fisher = sum |-u - C' grad|^2 / n.
+ * u_host, z_host, grad_host: D x n_samples column-major (any may be NULL).  obj must be a full-rank Gaussian objective
+ * (lambda = [mu; vec(C)]) over a target with capability >= 1; the draws are the objective's Philox stream at its
+ * current step, which then advances.  The d x d batch-and-match update itself stays on the host (:140-190). */
+int32_t avi_obj_batch_match_samples(avi_obj* obj, const float* lambda_host, int64_t P, int32_t n_samples, float* u_host,
+                                    float* z_host, float* grad_host, float* fisher, float* logpi_avg);
 int32_t avi_obj_gauss_expected_grad_hess(avi_obj* obj, const float* lambda_host, int64_t P, int32_t n_samples,
                                          float* logpi_avg, float* grad_host, float* hess_host);
 int32_t avi_obj_destroy(avi_obj* obj);

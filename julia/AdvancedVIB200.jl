@@ -304,6 +304,23 @@ function AdvancedVI.gaussian_expectation_gradient_and_hessian!(rng::Random.Abstr
     return lp[], grad_buf, hess_buf
 end
 
+# sampling stage of FisherMinBatchMatch (src/algorithms/fisherminbatchmatch.jl:81-111) over a native target
+function AdvancedVI.rand_batch_match_samples_with_objective!(rng::Random.AbstractRNG,
+        q::MvLocationScale{<:LinearAlgebra.AbstractTriangular,<:Normal}, n_samples::Int, prob::NativeProblem,
+        u_buf::AbstractMatrix{Float32}=Matrix{Float32}(undef, length(q.location), n_samples),
+        grad_buf::AbstractMatrix{Float32}=Matrix{Float32}(undef, length(q.location), n_samples))
+    params, _ = Optimisers.destructure(q)
+    st = make_state(rand(rng, UInt64), 0, 0, 1, q, prob, params)
+    d = length(q.location)
+    u, z, g = (Matrix{Float32}(undef, d, n_samples) for _ in 1:3)
+    fisher, lp = Ref{Float32}(0), Ref{Float32}(0)
+    check(@ccall(libavi.avi_obj_batch_match_samples(st.h::Ptr{Cvoid}, params::Ptr{Float32}, length(params)::Int64,
+                 n_samples::Int32, u::Ptr{Float32}, z::Ptr{Float32}, g::Ptr{Float32}, fisher::Ptr{Float32},
+                 lp::Ptr{Float32})::Int32), prob.c.h)
+    u_buf .= u; grad_buf .= g
+    return u_buf, z, grad_buf, fisher[], lp[]
+end
+
 # ---- optional fast path: the whole `step` on the device (src/algorithms/common.jl:40-120) ------------------
 # `init`/`step`/`output` methods for the three ParamSpaceSGD algorithm types when their adtype is AutoB200 and the
 # objective is not subsampled: parameters, optimiser state and the averaged iterate stay on the GPU (avi_opt_*); one

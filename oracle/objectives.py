@@ -181,6 +181,18 @@ def gaussian_expectation_gradient_and_hessian(q: MvLocationScale, prob, u):
     return logpi_avg, grad, hess
 
 
+def rand_batch_match_samples_with_objective(q: MvLocationScale, prob, u):
+    """rand_batch_match_samples_with_objective! (src/algorithms/fisherminbatchmatch.jl:81-111) for given standard normal
+    draws u (D x n): z = C u + mu (:91), grad_buf[:, b] = grad log pi(z_b) and the running log pi sum (:93-98), the
+    Fisher-divergence estimate sum |-u - C' grad|^2 / n (:100-108).  Returns (u, z, grad, fisher, logpi_avg)."""
+    n = u.shape[1]
+    mu, Cs = q.location, (np.diag(q.scale) if q.is_meanfield else q.scale)
+    z = Cs @ u + mu[:, None]
+    logp, G = prob.logdensity_and_gradient_batch(z)
+    fisher = float(np.sum((-u - Cs.T @ G) ** 2) / n)
+    return u, z, G, fisher, float(np.sum(logp) / n)
+
+
 def _lowrank_logq_param_grads(q, Z):
     """Per-sample gradients of log q_lambda(z) w.r.t. lambda at FIXED z for the low-rank Gaussian:
     w = Sigma^-1 (z - mu);  d/d mu = w,  d/d D_i = D_i (w_i^2 - (Sigma^-1)_ii),  d/d U = w (w' U) - Sigma^-1 U.

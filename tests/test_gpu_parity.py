@@ -475,6 +475,35 @@ def test_c2_full_size_properties(avi, ctx):
     prob.close()
 
 
+# --- rand_batch_match_samples_with_objective! (src/algorithms/fisherminbatchmatch.jl:81-111) ----------------------
+@pytest.mark.parametrize("n_samples", [48, 4500])      # one chunk / two chunks of 4096
+def test_batch_match_sampling_stage_matches_oracle(avi, ctx, n_samples):
+    """The sampling stage of FisherMinBatchMatch on the device vs the oracle on the same Philox draws: u, z = C u + mu,
+    the per-sample gradients, the Fisher-divergence estimate sum |-u - C' grad|^2 / n and mean log pi (fp32 SIMT
+    arithmetic vs fp64: 2e-5 relative; the draws within 4e-6 absolute)."""
+    n, d = 300, 11
+    X, y = Mo.synth_glm_data(n, d, seed=9)
+    D = d + 1
+    prob, probo = avi.LogReg(ctx, X, y, gemm="fp32"), Mo.LogReg(X, y)
+    mu = 0.1 * P.normal_matrix(5, 0, D, 1)[:, 0]
+    Lm = np.tril(0.05 * P.normal_matrix(6, 0, D, D)) + 0.4 * np.eye(D)
+    q = avi.FullRankGaussian(mu.astype(np.float32), Lm.astype(np.float32))
+    qo = F.FullRankGaussian(mu.astype(np.float32).astype(np.float64), Lm.astype(np.float32).astype(np.float64))
+    obj = avi.Objective(KEY, avi.RepGradELBO(8), q, prob)
+    for step in range(2):      # the call advances the step: the second one uses fresh draws
+        u, z, g, fisher, lp = obj.rand_batch_match_samples_with_objective(q, n_samples)
+        uo, zo, go, fo, lpo = O.rand_batch_match_samples_with_objective(qo, probo, P.normal_matrix(KEY, step, D, n_samples))
+        assert u.shape == (D, n_samples) and np.abs(u - uo).max() < 4e-6
+        assert np.abs(z - zo).max() < 2e-5 and relerr(g, go) < 2e-5
+        assert abs(fisher - fo) <= 2e-5 * abs(fo) and abs(lp - lpo) <= 2e-5 * abs(lpo)
+    # the reference's capability check (fisherminbatchmatch.jl:63-70) and family requirement
+    qmf = avi.MeanFieldGaussian(np.zeros(D, np.float32), np.ones(D, np.float32))
+    omf = avi.Objective(KEY, avi.RepGradELBO(8), qmf, prob)
+    with pytest.raises(avi.AviError):
+        omf.rand_batch_match_samples_with_objective(qmf, 4)
+    omf.close(); obj.close(); prob.close()
+
+
 # --- gaussian_expectation_gradient_and_hessian! (src/algorithms/gauss_expected_grad_hess.jl) ---------------------
 @pytest.mark.parametrize("n_samples", [64, 5000])      # one chunk / several chunks of 4096 (+ SIMT tail path)
 def test_gauss_expected_grad_hess_matches_oracle(avi, ctx, n_samples):
