@@ -347,8 +347,6 @@ int32_t avi_obj_create_lowrank(avi_ctx* ctx, avi_model* model, int32_t rank, int
     if (!ctx || !model || !out) return AVI_ERR_INVALID;
     *out = nullptr;
     if (rank < 1 || rank > avi_lr_max_rank()) AVI_FAIL(ctx, AVI_ERR_INVALID, "rank must be in 1..32");
-    if (objective == AVI_REPGRAD && entropy == AVI_ENT_STL_ZEROGRAD)
-        AVI_FAIL(ctx, AVI_ERR_UNSUPPORTED, "the low-rank family does not implement StickingTheLandingEntropyZeroGradient");
     if (ctx->nranks > 1 && !(objective == AVI_REPGRAD && (entropy == AVI_ENT_CLOSEDFORM || entropy == AVI_ENT_CLOSEDFORM_ZEROGRAD)))
         AVI_FAIL(ctx, AVI_ERR_UNSUPPORTED, "the low-rank family runs its log q based estimators on one rank only");
     return obj_create(ctx, model, AVI_LOWRANK, rank, objective, entropy, M, out);

@@ -225,6 +225,7 @@ __global__ void k_lr_scale_rows(const float* __restrict__ W, const float* __rest
 //   RepGrad  value = -(mean log pi + H^),  H^ = H (closed forms) or -mean log q (MonteCarlo / STL)
 //     ClosedFormEntropy            [-v0/M | -v1/M - dH/dD | -CU/M - dH/dU]
 //     ClosedFormEntropyZeroGradient, StickingTheLandingEntropy (v0, v1, CU then come from g + w): no dH terms
+//     StickingTheLandingEntropyZeroGradient: StickingTheLandingEntropy's with + dH/dD, + dH/dU
 //     MonteCarloEntropy            [(v2 - v0)/M | (D .* v3 - v1)/M - dH/dD | (CU2 - CU)/M - dH/dU]
 //   ScoreGrad (v0, v1, CU weighted by c_m): [v0/M | D .* v1/M | CU/M], value = (mean f^2 - (mean f)^2) / 2
 __global__ void __launch_bounds__(256)
@@ -235,6 +236,7 @@ k_lr_finalize(const float* __restrict__ acc, int accv, const float* __restrict__
     const long long P = 2LL * D + (long long)D * r;
     const bool score = objective == AVI_SCOREGRAD;
     const bool dH = !score && (entropy == AVI_ENT_CLOSEDFORM || entropy == AVI_ENT_MONTECARLO);
+    const bool dHplus = !score && entropy == AVI_ENT_STL_ZEROGRAD;   // STL - H(q) + H(q_stop): + grad H (entropy.jl:80-90)
     const bool mc = !score && entropy == AVI_ENT_MONTECARLO;
     const float* v0 = acc; const float* v1 = acc + accv; const float* v2 = acc + 2 * (size_t)accv; const float* v3 = acc + 3 * (size_t)accv;
     for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
@@ -246,10 +248,12 @@ k_lr_finalize(const float* __restrict__ acc, int accv, const float* __restrict__
             const float d = __ldg(lambda + D + i);
             g = score ? d * v1[i] * invM : (mc ? (d * v3[i] - v1[i]) * invM : -v1[i] * invM);
             if (dH) g -= ent[1 + i];
+            if (dHplus) g += ent[1 + i];
         } else {
             const long long q = p - 2LL * D;
             g = score ? CU[q] * invM : (mc ? (CU2[q] - CU[q]) * invM : -CU[q] * invM);
             if (dH) g -= ent[1 + D + q];
+            if (dHplus) g += ent[1 + D + q];
         }
         grad[p] = g;
     }
@@ -287,7 +291,8 @@ int32_t avi_lr_entropy(avi_obj* o, const float* lambda) {
 
 // the estimators that need log q(z): everything but RepGradELBO with a closed-form entropy
 bool avi_lr_needs_logq(const avi_obj* o) {
-    return o->objective == AVI_SCOREGRAD || o->entropy == AVI_ENT_MONTECARLO || o->entropy == AVI_ENT_STL;
+    return o->objective == AVI_SCOREGRAD || o->entropy == AVI_ENT_MONTECARLO || o->entropy == AVI_ENT_STL ||
+           o->entropy == AVI_ENT_STL_ZEROGRAD;
 }
 
 // w, U'w and log q per sample (into o->U, o->V, o->esq), the scalar sums, and for ScoreGrad the centred weights (o->fbuf).

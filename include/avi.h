@@ -161,8 +161,9 @@ int32_t avi_obj_create(avi_ctx* ctx, avi_model* model, int32_t family, int32_t o
  * ClosedFormEntropyZeroGradient, MonteCarloEntropy and StickingTheLandingEntropy, ScoreGradELBO (VarGrad) -- log q(z)
  * and its gradients go through the rank x rank capacitance matrix (Woodbury) --, estimate_gradient!, estimate_objective,
  * rand and the fused step with Descent / Adam / DoG / DoWG, IdentityOperator / ClipScale (on scale_diag,
- * clip_scale.jl:31-41) and both averagers.  AVI_ERR_UNSUPPORTED: StickingTheLandingEntropyZeroGradient, the proximal
- * operator, and the log q based estimators on more than one rank. */
+ * clip_scale.jl:31-41) and both averagers; every entropy estimator of entropy.jl.  AVI_ERR_UNSUPPORTED: the proximal
+ * operator (defined for MvLocationScale only, proximal_location_scale_entropy.jl:46-61) and the log q based estimators
+ * on more than one rank. */
 int32_t avi_obj_create_lowrank(avi_ctx* ctx, avi_model* model, int32_t rank, int32_t objective, int32_t entropy,
                                int32_t M, avi_obj** out);
 /* Base distribution of MvLocationScale(location, scale, dist) for the mean-field and full-rank families: Normal(0, 1)

@@ -225,12 +225,16 @@ def repgrad_lowrank_value_and_gradient(params, q_template, prob, u_diag, u_fact,
         ent = q.entropy()
         Wg = G
         g_loc_x, g_diag_x, g_fact_x = 0.0, 0.0, 0.0
-    elif entropy in ("StickingTheLandingEntropy", "MonteCarloEntropy"):
+    elif entropy in ("StickingTheLandingEntropy", "MonteCarloEntropy", "StickingTheLandingEntropyZeroGradient"):
         ent = -float(np.mean(q.logpdf(Z)))
         w, gD, gU = _lowrank_logq_param_grads(q, Z)
         Wg = G + w
         if entropy == "MonteCarloEntropy":   # + d/d lambda of mean log q_lambda(z) at fixed z (the value has -H_MC = +mean log q)
             g_loc_x, g_diag_x, g_fact_x = np.mean(w, axis=1), np.mean(gD, axis=1), np.mean(gU, axis=2)
+        elif entropy == "StickingTheLandingEntropyZeroGradient":
+            # entropy.jl:80-90: STL - H(q) + H(q_stop): the value is STL's, the gradient gains +grad H(q)
+            gD_H, gU_H = q.entropy_gradient()
+            g_loc_x, g_diag_x, g_fact_x = 0.0, gD_H, gU_H
         else:
             g_loc_x, g_diag_x, g_fact_x = 0.0, 0.0, 0.0
     else:

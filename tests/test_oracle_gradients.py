@@ -128,7 +128,7 @@ def test_lowrank_woodbury_pieces():
     assert np.allclose(SinvU, np.linalg.solve(Sigma, q.scale_factors), rtol=1e-10)
 
 
-@pytest.mark.parametrize("entropy", ["StickingTheLandingEntropy", "MonteCarloEntropy"])
+@pytest.mark.parametrize("entropy", ["StickingTheLandingEntropy", "MonteCarloEntropy", "StickingTheLandingEntropyZeroGradient"])
 def test_lowrank_repgrad_logpdf_entropies_vs_fd(entropy):
     """Closed forms vs central differences of the forward closure the reference differentiates
     (repgradelbo.jl:142-149 with entropy.jl:42-46 / :59-65: q frozen inside log q for STL)."""
@@ -141,8 +141,9 @@ def test_lowrank_repgrad_logpdf_entropies_vs_fd(entropy):
         qx = q.restructure(x)
         Z = qx.rand_from_eps(u1, u2)
         logp, _ = prob.logdensity_and_gradient_batch(Z)
-        q_in_logpdf = q if entropy == "StickingTheLandingEntropy" else qx    # q_stop vs live q
-        return -(np.mean(logp) - np.mean(q_in_logpdf.logpdf(Z)))
+        q_in_logpdf = qx if entropy == "MonteCarloEntropy" else q    # live q vs q_stop
+        extra = -qx.entropy() + q.entropy() if entropy == "StickingTheLandingEntropyZeroGradient" else 0.0   # entropy.jl:86-89
+        return -(np.mean(logp) - np.mean(q_in_logpdf.logpdf(Z)) + extra)
     assert np.isclose(v, forward(lam))
     assert np.allclose(g, _fd(forward, lam), rtol=2e-6, atol=2e-7)
 
