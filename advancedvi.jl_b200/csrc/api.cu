@@ -432,6 +432,7 @@ int32_t avi_obj_set_model(avi_obj* obj, avi_model* model) {
 int32_t avi_obj_seed(avi_obj* obj, uint64_t key, uint64_t step) {
     if (!obj) return AVI_ERR_INVALID;
     obj->key = key; obj->step = step;
+    obj->fr.Lr3_owner = nullptr;   // (anything an optimiser loop drew ahead belongs to the old key / step)
     return obj_push_state(obj);
 }
 

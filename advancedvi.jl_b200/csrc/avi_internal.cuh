@@ -224,6 +224,10 @@ struct FrWork {
     bool Lr3_maintained = false;
     const void* Lr3_owner = nullptr;   // the optimiser whose update kernel last wrote Lr3 (nullptr: anyone else did)
     int64_t Lr3_version = -1;          // ... and the avi_opt::lam_version it corresponds to
+    int64_t owner_generation = -1;     // ... and the objective's generation then (shard / target / base changes)
+    // true while the optimiser loop's update kernel also draws the NEXT iteration's eps (E, Er3, |eps|^2): the sampling
+    // stage then starts at the contraction (same validity rules as Lr3)
+    bool eps_ahead = false;
 };
 
 // what k_fr_outer_prep needs to finish the location block and the value slot in the same launch (family_fr.cu)
@@ -234,6 +238,12 @@ struct FrPrepFinalize {
     int M = 0, objective = 0, entropy = 0, Mloc = 0, accv = 0;
     float *grad = nullptr, *out = nullptr;
     const float *logp = nullptr, *esq = nullptr;
+};
+
+// arguments of the draw-ahead CTAs of the tiled full-rank update kernel (opt.cu); nctas == 0: none
+struct FrDrawAhead {
+    int nctas = 0, Mloc = 0, m0 = 0, ld = 0;
+    float *E = nullptr, *Er3 = nullptr, *esq = nullptr;
 };
 
 struct avi_obj {
@@ -379,6 +389,7 @@ int32_t avi_trsm_lt(avi_ctx* ctx, const float* L, int D, const float* E, float* 
 bool avi_fr_tc_ok(const avi_obj* o, int Mloc);
 int32_t avi_fr_affine_prepare(avi_obj* o, int Mloc, float** Er3, int* seg);
 int32_t avi_fr_refresh_split(avi_obj* o, const float* lambda);   // Lr3 = transposed 3xTF32 split of L(lambda)
+int32_t avi_fr_draw_current(avi_obj* o, const float* lambda);    // family.cu: eps (E, Er3, |eps|^2) of the objective's current step
 int32_t avi_fr_affine_tc(avi_obj* o, const float* lambda, const float* E, float* Z, int Mloc, bool er3_done = false,
                          const SampleHook* hook = nullptr);
 int32_t avi_fr_outer_tc(avi_obj* o, const float* W, const float* E, float* C, int Mloc, int which, bool reuse_E,

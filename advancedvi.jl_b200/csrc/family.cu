@@ -375,8 +375,19 @@ k_forward_sums(const float* __restrict__ lambda, int D, int fullrank, const floa
 }  // namespace
 
 // ==============================================================================================
+static int32_t family_sample_impl(avi_obj* o, const float* lambda, float* Z, float* E, float* esq, int Mloc, int m0,
+                                  const ObjDeviceState* st, const ObjDeviceState* ov, const SampleHook* hook, bool sample_only);
 int32_t avi_family_sample(avi_obj* o, const float* lambda, float* Z, float* E, float* esq, int Mloc, int m0,
                           const ObjDeviceState* st, const ObjDeviceState* ov, const SampleHook* hook) {
+    return family_sample_impl(o, lambda, Z, E, esq, Mloc, m0, st, ov, hook, false);
+}
+// full-rank: the eps-draw of the objective's current step alone (E, the split of eps, |eps|^2), no contraction
+int32_t avi_fr_draw_current(avi_obj* o, const float* lambda) {
+    if (o->family != AVI_FULLRANK || o->Mloc <= 0) return AVI_OK;
+    return family_sample_impl(o, lambda, o->Z, o->E, o->esq, o->Mloc, o->m0, o->d_state, nullptr, nullptr, true);
+}
+static int32_t family_sample_impl(avi_obj* o, const float* lambda, float* Z, float* E, float* esq, int Mloc, int m0,
+                                  const ObjDeviceState* st, const ObjDeviceState* ov, const SampleHook* hook, bool sample_only) {
     avi_ctx* ctx = o->ctx;
     if (Mloc <= 0) return AVI_OK;
     ObjDeviceState sv{};
@@ -420,8 +431,11 @@ int32_t avi_family_sample(avi_obj* o, const float* lambda, float* Z, float* E, f
         const bool tc = avi_fr_tc_ok(o, Mloc);
         SampleHook fh{};   // (kind 0: only the split-eps fields are read by the full-rank sampler)
         if (tc) AVI_CHECK(avi_fr_affine_prepare(o, Mloc, &fh.Er3, &fh.er_seg));
-        LAUNCH_SAMPLE(true, false, fh);
-        AVI_LAUNCHED(ctx);
+        if (!(o->fr.eps_ahead && tc && E == o->E && esq == o->esq)) {   // (else: drawn by the previous iteration's update kernel)
+            LAUNCH_SAMPLE(true, false, fh);
+            AVI_LAUNCHED(ctx);
+        }
+        if (sample_only) return AVI_OK;
         if (tc) {
             AVI_CHECK(avi_fr_affine_tc(o, lambda, E, Z, Mloc, /*er3_done=*/true, hook));
         } else {   // very large forward-only batches (estimate_objective): exact-fp32 SIMT contraction

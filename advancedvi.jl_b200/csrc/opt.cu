@@ -15,6 +15,7 @@
 #include "avi_internal.cuh"
 #include "device_utils.cuh"
 #include "fr_finalize.cuh"
+#include "fr_sample.cuh"
 #include "mf_finalize.cuh"
 #include "mf_tail.cuh"
 #include "step_fused.cuh"
@@ -228,15 +229,33 @@ k_fr_update_t(float* __restrict__ lam, float* __restrict__ grad, float* __restri
               ObjDeviceState* __restrict__ st, const float* __restrict__ C1, const float* __restrict__ C2,
               const float* __restrict__ scal, int M, int objective, int entropy, UpdArgs a, int ntc, int ntr,
               float* __restrict__ Lr3, int seg, unsigned int* __restrict__ ticket, float* __restrict__ trace,
-              int trace_cap) {
+              int trace_cap, FrDrawAhead da) {
     __shared__ float tile[FRU_ROWS / 32][32][33];
     const int D = a.D;
     const bool live = !(st->halted || !isfinite(out[0]));
+    if ((int)blockIdx.x < da.nctas) {
+        // ---- the NEXT iteration's eps (two samples per CTA, 128 threads each): eps depends on (key, step, sample,
+        // coordinate) only, so it is drawn here, under the shadow of the optimiser-state stream, instead of by a launch
+        // of its own at the top of the next iteration.  A step that is not applied keeps its counter: nothing to draw.
+        __shared__ float ssum[2][4];
+        const int half = threadIdx.x >> 7, t = threadIdx.x & 127;
+        const int m = 2 * (int)blockIdx.x + half;
+        const unsigned long long step_next = st->step + 1ull;
+        float tot = 0.0f;
+        if (live && m < da.Mloc) {
+            const PhiloxKeys pk(st->key);
+            tot = fr_sample_row_part(t, m, da.m0 + m, D, da.ld, seg, (uint32_t)step_next, eps_ctr3(step_next, AVI_STREAM_EPS), pk,
+                                     da.E, da.Er3);
+        }
+        if ((t & 31) == 0) ssum[half][t >> 5] = tot;
+        __syncthreads();
+        if (live && m < da.Mloc && t == 0) da.esq[m] = ((ssum[half][0] + ssum[half][1]) + ssum[half][2]) + ssum[half][3];
+    }
     const float eta = a.rule == AVI_RULE_DESCENT ? a.h0 : 0.f;
     const float b1t = sc[SC_B1T], b2t = sc[SC_B2T], w = (a.avg_param + 1.0f) / (sc[SC_T] + a.avg_param);
     const float bc1 = 1.0f / (1.0f - b1t), bc2 = 1.0f / (1.0f - b2t);   // Adam bias corrections as reciprocals
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int tile_id = blockIdx.x;
+    const int tile_id = (int)blockIdx.x - da.nctas;   // (negative: a sampling CTA, handled above)
     const bool adam = a.rule == AVI_RULE_ADAM, poly = a.averager == AVI_AVG_POLYNOMIAL;
     // one parameter entry of Optimisers.update! + operator + averager on register values (k_fr_update's arithmetic)
     auto entry = [&](float x, float g, float& mt, float& vt, float& av, bool diag) -> float {
@@ -256,7 +275,7 @@ k_fr_update_t(float* __restrict__ lam, float* __restrict__ grad, float* __restri
         if (poly) av = (1.0f - w) * av + w * x;
         return x;
     };
-    if (live) {
+    if (live && tile_id >= 0) {
         if (tile_id >= ntc * ntr) {   // location block (gradient written by the finalize stage)
             const int i = (tile_id - ntc * ntr) * 256 + (int)threadIdx.x;
             if (i < D) {
@@ -350,6 +369,13 @@ UpdArgs make_args(const avi_opt* op) {
 
 constexpr int NORM_BLOCKS_MAX = 256;
 
+// ... and does it also draw the next iteration's eps?  (Normal(0, 1) base, the one-CTA-per-sample sampler shape)
+bool fr_draws_ahead(const avi_opt* op) {
+    static const bool on = !(getenv("AVI_FR_DRAW_AHEAD") && atoi(getenv("AVI_FR_DRAW_AHEAD")) == 0);
+    const avi_obj* o = op->obj;
+    return on && o->base.kind == AVI_BASE_NORMAL && o->Mloc <= 8192;
+}
+
 // does the iteration's update kernel maintain the split of L for the next iteration's sampling stage?
 bool fr_maintains_split(const avi_opt* op) {
     static const bool on = !(getenv("AVI_FR_TILED_UPDATE") && atoi(getenv("AVI_FR_TILED_UPDATE")) == 0) &&
@@ -402,8 +428,9 @@ int32_t enqueue_iteration(avi_opt* op, bool subsampled, int64_t batch) {
     const bool dog_rule = op->rule == AVI_RULE_DOG || op->rule == AVI_RULE_DOWG;
     const bool maintain = fr_maintains_split(op);
     o->fr.Lr3_maintained = maintain;
+    o->fr.eps_ahead = maintain && fr_draws_ahead(op);   // (... and draws the next iteration's eps: k_fr_update_t)
     int32_t rc_local = avi_objective_local(o, op->lam);
-    o->fr.Lr3_maintained = false;
+    o->fr.Lr3_maintained = false; o->fr.eps_ahead = false;
     o->fused_exchange = false;
     AVI_CHECK(rc_local);
     // (running this tail inside the last CTA of the target's final kernel was measured SLOWER than its own
@@ -434,10 +461,15 @@ int32_t enqueue_iteration(avi_opt* op, bool subsampled, int64_t batch) {
             const int rows = fru_rows == 64 || fru_rows == 128 ? fru_rows : 32;
             const int ntc = (int)ceil_div(o->D, 32), ntr = (int)ceil_div(o->D, rows), nloc = (int)ceil_div(o->D, 256);
             auto kern = rows == 32 ? k_fr_update_t<32> : rows == 128 ? k_fr_update_t<128> : k_fr_update_t<64>;
-            kern<<<(unsigned)(ntc * ntr + nloc), 256, 0, ctx->stream>>>(
+            FrDrawAhead da{};
+            if (maintain && fr_draws_ahead(op)) {
+                da.nctas = (int)ceil_div(o->Mloc, 2); da.Mloc = o->Mloc; da.m0 = o->m0; da.ld = o->ld;
+                da.E = o->E; da.Er3 = o->fr.Er3; da.esq = o->esq;
+            }
+            kern<<<(unsigned)(da.nctas + ntc * ntr + nloc), 256, 0, ctx->stream>>>(
                 op->lam, o->grad, op->m1, op->m2, op->avg, op->sc, o->out, o->d_state, C1, C2, scal, o->M, o->objective,
                 o->entropy, a, ntc, ntr, maintain ? o->fr.Lr3 : (float*)nullptr, (int)round_up(o->D, 32), op->ticket,
-                op->trace, op->trace_cap);
+                op->trace, op->trace_cap, da);
             AVI_LAUNCHED(ctx);
             return AVI_OK;
         }
@@ -582,9 +614,12 @@ int32_t steps_launch(avi_opt* op, int32_t n) {
         // update kernel; otherwise (first call, warm start, the objective evaluated at another lambda meanwhile,
         // buffers reallocated) rebuild it once, outside the captured iteration
         FrWork& w = op->obj->fr;
-        if (w.Lr3_owner != op || w.Lr3_version != op->lam_version) AVI_CHECK(avi_fr_refresh_split(op->obj, op->lam));
+        if (w.Lr3_owner != op || w.Lr3_version != op->lam_version || w.owner_generation != op->obj->generation) {
+            AVI_CHECK(avi_fr_refresh_split(op->obj, op->lam));
+            if (fr_draws_ahead(op)) AVI_CHECK(avi_fr_draw_current(op->obj, op->lam));   // eps of the step about to run
+        }
         op->lam_version += n;
-        w.Lr3_owner = op; w.Lr3_version = op->lam_version;
+        w.Lr3_owner = op; w.Lr3_version = op->lam_version; w.owner_generation = op->obj->generation;
     } else {
         op->lam_version += n;
     }
