@@ -304,7 +304,7 @@ struct Glm : avi_model {
     ~Glm() override {
         avi_free(Xr_full); avi_free(Xc_full); avi_free(y_full); avi_free(Xr_b); avi_free(Xc_b); avi_free(y_b);
         avi_free(idx_own); avi_free(R); avi_free(Zt); avi_free(llpart); avi_free(a1p); avi_free(spart);
-        avi_free(slabs); avi_free(pre); avi_free(tickets); avi_free(gbar); avi_free(ldpart);
+        avi_free(slabs); avi_free(pre); avi_free(tickets); avi_free(gbar); avi_free(ldpart); avi_free(dummy_st);
     }
     bool hooked = false;               // the sampling kernel produced Zt / pre for exactly (hooked_Z, hooked_M)
     const float* hooked_Z = nullptr; int hooked_M = 0;
@@ -417,9 +417,76 @@ struct Glm : avi_model {
         return AVI_OK;
     }
 
+    // logdensity_and_gradient for all M samples as ONE persistent launch (the forward and backward phases of the
+    // whole-iteration kernel, step_fused.cu, with a plain store epilogue): X is read once (row-major copy for both
+    // contractions, the second time as an MN-major operand), the residuals travel transposed, one prologue / teardown
+    // instead of two.  Leaves the split-K slabs of G and the partial log-likelihoods for k_glm_post_full.
+    float* dummy_st = nullptr;   // the kernel's entry snapshot reads an ObjDeviceState; this path has none to show it
+    bool fused_store_ok(int M) const {
+        static const bool on = !(getenv("AVI_FUSED_EVAL") && atoi(getenv("AVI_FUSED_EVAL")) == 0);
+        return on && !x3 && fused_step_ok(M) && dK % 4 == 0;
+    }
+    int32_t eval_fused_store(const float* Z, int ld, int M, int* nparts, const float** sl, int* nslab, long long* sstride) {
+        const bool pre_done = hooked && hooked_Z == Z && hooked_M == M;
+        clear_hook();
+        if (!pre_done) {
+            k_glm_pre<<<M, 256, 0, ctx->stream>>>(Z, ld, d, variant, include_prior, Zt, zt_ld, 0, pre, gbar + 3);
+            AVI_LAUNCHED(ctx);
+        }
+        if (!dummy_st) AVI_CHECK(avi_alloc(ctx, &dummy_st, 32));
+        StepParams sp{};
+        AVI_CHECK(avi_tc_plan(ctx, M, n_act, kf(), false, 0, &sp.f, 0));
+        sp.f.C = R; sp.f.y = y; sp.f.w = likeadj(); sp.f.likelihood = likelihood; sp.f.r_seg = 0;
+        sp.f.static_op = subsampled ? 0 : 2;
+        AVI_CHECK(ensure_buf(&llpart, &llpart_cap, (long long)sp.f.n_bchunk * 4 * capM));
+        sp.f.part1 = llpart; sp.f.ldpart = capM; sp.f.post_on = 0;   // per-sample partials, as the stand-alone forward kernel
+        AVI_CHECK(avi_tc_plan(ctx, d, M, kb(), true, 0, &sp.b, 0, 0, /*nt_search=*/1));
+        sp.b.static_op = subsampled ? 0 : 1;
+        *sstride = (long long)capM * ld;
+        AVI_CHECK(ensure_buf(&slabs, &slab_cap, *sstride * sp.b.n_ksplit));
+        sp.b.C = slabs; sp.b.ldc = ld; sp.b.slab_stride = *sstride; sp.b.post_on = 0;
+        CUtensorMap tmZ, tmXr, tmXc, tmR;
+        AVI_CHECK(avi_tc_make_tmap(ctx, &tmZ, Zt, M, kf(), zt_ld, 128));
+        AVI_CHECK(avi_tc_make_tmap(ctx, &tmXr, Xr, n_act, kf(), dK, sp.f.nt));
+        static const bool one_box = !(getenv("AVI_TC_MN3") && atoi(getenv("AVI_TC_MN3")) == 0);
+        if (one_box && dK % 32 == 0) {   // MN-major A operand straight from the row-major copy: one 3-D box per tile
+            sp.b.a_mn = 2;
+            AVI_CHECK(avi_tc_make_tmap_mn3(ctx, &tmXc, Xr, n_act, dK, dK, 4));
+        } else {
+            sp.b.a_mn = 1;
+            AVI_CHECK(avi_tc_make_tmap(ctx, &tmXc, Xr, n_act, d, dK, 32, /*atom32=*/1));
+        }
+        const long long ldRt = round_up(capM, 32);
+        sp.f.c_mn = 1; sp.f.ldc = (int)ldRt;   // R transposed [data row][sample]: coalesced forward stores, MN-major B operand
+        if (one_box && (sp.b.n_bchunk == 1 || sp.b.nt % 32 == 0)) {
+            sp.b.b_mn = 2;
+            AVI_CHECK(avi_tc_make_tmap_mn3(ctx, &tmR, R, kb(), round_up(M, 32), ldRt, (sp.b.nt + 31) / 32));
+        } else {
+            sp.b.b_mn = 1;
+            AVI_CHECK(avi_tc_make_tmap(ctx, &tmR, R, kb(), M, ldRt, 32, /*atom32=*/1));
+        }
+        sp.bwd_store = 1; sp.do_sample = 0; sp.draw_ahead = 0;
+        sp.D = d + 1; sp.ld = ld; sp.Mloc = M; sp.st = reinterpret_cast<ObjDeviceState*>(dummy_st);
+        sp.d = d; sp.variant = variant; sp.include_prior = include_prior;
+        sp.Zt = Zt; sp.zt_ld = zt_ld; sp.pre = reinterpret_cast<float*>(pre);
+        sp.t.mode = STEP_TAIL_NONE; sp.t.comm.nranks = 1;
+        sp.gbar = gbar;
+        AVI_CHECK(avi_step_fused_launch(ctx, tmZ, tmXr, tmXc, tmR, sp));
+        *nparts = sp.f.n_bchunk * 4; *sl = slabs; *nslab = sp.b.n_ksplit;
+        return AVI_OK;
+    }
+
     int32_t eval(const float* Z, int ld, int M, float* logp, float* G) override {
         if (M <= 0) return AVI_OK;
         AVI_CHECK(ensure(M, ld));
+        if (G && tc_mode() && fused_store_ok(M)) {
+            int np = 0, ns = 0; long long ss = 0; const float* s0 = nullptr;
+            AVI_CHECK(eval_fused_store(Z, ld, M, &np, &s0, &ns, &ss));
+            k_glm_post_full<<<M, (unsigned)std::min<int64_t>(512, round_up(ld / 4, 32)), 0, ctx->stream>>>(Z, ld, d, pre, s0, ns, ss, llpart, np,
+                                                                                                   capM, likeadj(), G, logp);
+            AVI_LAUNCHED(ctx);
+            return AVI_OK;
+        }
         int nparts = 0;
         AVI_CHECK(forward(Z, ld, M, &nparts, G != nullptr));
         const float w = likeadj();

@@ -744,7 +744,7 @@ __device__ __forceinline__ void tail_phase(const StepParams& sp, SmemCtl* ctl, c
 // timeline slots (AVI_TIMELINE; atomicMin in 0..7, atomicMax in 8..15): first CTA 0 entered | 1 past the dependency wait |
 // 2 past barrier 0 (forward starts) | 3 past barrier 1 (backward starts) | 4 past barrier 2 (tail starts);
 // last CTA 8 left the sample phase | 9 left the forward phase | 10 left the backward phase | 11 done
-template <int LIK, int X3>
+template <int LIK, int X3, int BEPI = EPI_GLM_BWD>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_glm_mf_step(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmXr,
               const __grid_constant__ CUtensorMap tmXc, const __grid_constant__ CUtensorMap tmR,
@@ -894,7 +894,7 @@ k_glm_mf_step(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ C
     if (threadIdx.x == 0) PSTAMP(prof, 13);
 
     if (sp.t.mode != STEP_TAIL_NONE) tail_scalars(sp, ctl);
-    tc_phase<EPI_GLM_BWD, 0, X3>(&tmXc, &tmR, sp.b, ctl, tiles, tmem_base, sp.stages_b, pre, 1, prof, 14);
+    tc_phase<BEPI, 0, X3>(&tmXc, &tmR, sp.b, ctl, tiles, tmem_base, sp.stages_b, pre, 1, prof, 14);
     stamp_max(sp.tl, 10);
 
     if (sp.t.mode != STEP_TAIL_NONE) {
@@ -956,6 +956,8 @@ int32_t avi_step_fused_launch(avi_ctx* ctx, const CUtensorMap& tmZ, const CUtens
         AVI_CUDA(ctx, cudaFuncSetAttribute(k_glm_mf_step<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         AVI_CUDA(ctx, cudaFuncSetAttribute(k_glm_mf_step<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         AVI_CUDA(ctx, cudaFuncSetAttribute(k_glm_mf_step<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        AVI_CUDA(ctx, cudaFuncSetAttribute(k_glm_mf_step<0, 0, EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        AVI_CUDA(ctx, cudaFuncSetAttribute(k_glm_mf_step<1, 0, EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         attr_done = true;
     }
     const int extra = 16 + (int)sizeof(SmemCtl) + 1024;
@@ -992,8 +994,17 @@ int32_t avi_step_fused_launch(avi_ctx* ctx, const CUtensorMap& tmZ, const CUtens
         if (g_prof && !ctx->capturing) cudaMemsetAsync(g_prof, 0, 160 * 32 * sizeof(unsigned long long), ctx->stream);
         sp.prof = g_prof; g_prof_grid = grid;
     }
-    AviTimed timed(ctx, "glm_step");
+    AviTimed timed(ctx, sp.bwd_store ? "glm_fwd_bwd" : "glm_step");
     const bool bern = sp.f.likelihood == AVI_GLM_BERNOULLI_LOGIT, x3 = sp.f.r_seg != 0;
+    if (sp.bwd_store) {
+        if (x3 || sp.t.mode != STEP_TAIL_NONE || sp.do_sample || sp.draw_ahead)
+            AVI_FAIL(ctx, AVI_ERR_INVALID, "the gradient-store variant runs forward + backward only, plain TF32");
+        cudaError_t es = bern ? cudaLaunchKernelEx(&cfg, k_glm_mf_step<0, 0, EPI_STORE>, tmZ, tmXr, tmXc, tmR, sp)
+                              : cudaLaunchKernelEx(&cfg, k_glm_mf_step<1, 0, EPI_STORE>, tmZ, tmXr, tmXc, tmR, sp);
+        if (es != cudaSuccess) AVI_FAIL(ctx, AVI_ERR_CUDA, std::string("fused forward + backward launch: ") + cudaGetErrorString(es));
+        AVI_LAUNCHED(ctx);
+        return AVI_OK;
+    }
     cudaError_t e = bern ? (x3 ? cudaLaunchKernelEx(&cfg, k_glm_mf_step<0, 1>, tmZ, tmXr, tmXc, tmR, sp)
                                : cudaLaunchKernelEx(&cfg, k_glm_mf_step<0, 0>, tmZ, tmXr, tmXc, tmR, sp))
                          : (x3 ? cudaLaunchKernelEx(&cfg, k_glm_mf_step<1, 1>, tmZ, tmXr, tmXc, tmR, sp)

@@ -44,6 +44,11 @@ struct StepTail {
 struct StepParams {
     TcParams f, b;                 // forward / backward contraction plans (no clusters, no CTA pairs)
     int stages_f, stages_b;
+    // bwd_store != 0 (requires t.mode == STEP_TAIL_NONE, do_sample == 0, draw_ahead == 0): the backward phase writes the
+    // FULL gradient block as split-K slabs b.C[ks][sample][coordinate] (plain store epilogue) instead of the mean-field
+    // sums, and the forward phase leaves per-sample partial log-likelihoods (f.post_on = 0): the batched
+    // logdensity_and_gradient of the target for the families that need every g_m (full-rank, low-rank, Stein / BaM stages)
+    int bwd_store;
     // sample phase
     int do_sample;                 // 0: Z, Zt, E, esq, pre come from the stand-alone sampling kernel
     const float* lambda; int D, ld, m0, Mloc;
