@@ -440,7 +440,10 @@ struct Glm : avi_model {
         sp.f.static_op = subsampled ? 0 : 2;
         AVI_CHECK(ensure_buf(&llpart, &llpart_cap, (long long)sp.f.n_bchunk * 4 * capM));
         sp.f.part1 = llpart; sp.f.ldpart = capM; sp.f.post_on = 0;   // per-sample partials, as the stand-alone forward kernel
-        AVI_CHECK(avi_tc_plan(ctx, d, M, kb(), true, 0, &sp.b, 0, 0, /*nt_search=*/1));
+        // widest backward tile (more k-splits: 6 us instead of 10 us of mainloop at C3, twice the slabs) unless
+        // AVI_FUSED_EVAL_WIDE=0 leaves the width to the planner (measured on C3: 11.35 k vs 11.17 k steps/s)
+        static const bool wide = !(getenv("AVI_FUSED_EVAL_WIDE") && atoi(getenv("AVI_FUSED_EVAL_WIDE")) == 0);
+        AVI_CHECK(avi_tc_plan(ctx, d, M, kb(), true, 0, &sp.b, 0, 0, /*nt_search=*/wide ? 0 : 1));
         sp.b.static_op = subsampled ? 0 : 1;
         *sstride = (long long)capM * ld;
         AVI_CHECK(ensure_buf(&slabs, &slab_cap, *sstride * sp.b.n_ksplit));
