@@ -447,6 +447,8 @@ def roofline_for(b, ktime, peaks, src, x3=False):
     n_loc, d, m_loc = (b.rows_local if not b.subsampled else cfg["batch"]), cfg["d"], b.m_loc
     if "glm_step" in ktime:
         dom, flops, kname = "glm_step", 4.0 * n_loc * d * m_loc, "k_glm_mf_step (sample + forward + backward + tail, one launch)"
+    elif "glm_fwd_bwd" in ktime:   # the target's batched logdensity_and_gradient as one persistent launch (full-rank path)
+        dom, flops, kname = "glm_fwd_bwd", 4.0 * n_loc * d * m_loc, "k_glm_mf_step<EPI_STORE> (forward + backward, gradient block stored; one launch)"
     else:
         cands = {k: v for k, v in ktime.items() if k in ("glm_fwd", "glm_bwd")}
         if not cands:
@@ -541,7 +543,7 @@ def main():
         e2e = {"value": K / dt, "unit": "steps/s", "h2d_bytes_per_step": 4 * cfg.get("batch", 0), "d2h_bytes_per_step": 8,
                "path": "avi_opt_steps[_subsampled] (the optimize() loop: minibatch indices host -> device, (value, elbo) trace "
                        "device -> host, one synchronisation per call of K iterations); wall clock"}
-    ktime = kernel_times(b, torch, ext, flush, ("glm_step", "sample", "glm_fwd", "glm_bwd", "gemm_store"))
+    ktime = kernel_times(b, torch, ext, flush, ("glm_step", "glm_fwd_bwd", "sample", "glm_fwd", "glm_bwd", "gemm_store"))
     roofline = roofline_for(b, ktime, peaks, src, x3=args.gemm == "tf32x3")
 
     # the sample+transform kernel at a bandwidth-relevant size (output 134 MB > 126 MB L2): same kernel, M = 32768, as
@@ -596,7 +598,7 @@ def main():
             b3 = Bench("c2", args, ctx, rank, world, local_rank, "tf32x3")
             c3_ms, w3_ms, l3, fe3, _ = device_loop(b3, K, W, torch, dist, ext, flush, barrier)
             e3_s, e3_parts = e2e_estimate_gradient(b3, K, W, torch, dist, ext, flush)
-            k3 = kernel_times(b3, torch, ext, flush, ("glm_step", "glm_fwd", "glm_bwd"))
+            k3 = kernel_times(b3, torch, ext, flush, ("glm_step", "glm_fwd_bwd", "glm_fwd", "glm_bwd"))
             line["alt_precision"] = {
                 "mode": "tf32x3 (hi/lo split operands, 3 tensor-core products per algorithmic product, fp32-grade)",
                 "value": K / (c3_ms * 1e-3), "ms_per_step": c3_ms / K, "value_l2_resident": K / (w3_ms * 1e-3),
@@ -657,7 +659,7 @@ def main():
                 bx = Bench(name, args, ctx, rank, world, local_rank, args.gemm)
                 setup_s = time.perf_counter() - t_setup
                 cm, wm, ln, fe, _ = device_loop(bx, k2, w2, torch, dist, ext, flush, barrier)
-                kt = kernel_times(bx, torch, ext, flush, ("glm_step", "glm_fwd", "glm_bwd"), reps=3)
+                kt = kernel_times(bx, torch, ext, flush, ("glm_step", "glm_fwd_bwd", "glm_fwd", "glm_bwd"), reps=3)
                 rf = roofline_for(bx, kt, peaks, src)
                 line["configs"][name] = {"workload": CONFIGS[name]["workload"], "value": k2 / (cm * 1e-3), "unit": "steps/s",
                                          "ms_per_step": cm / k2, "value_l2_resident": k2 / (wm * 1e-3), "steps": k2, "warmup": w2,

@@ -73,7 +73,7 @@ int32_t avi_ctx_info(avi_ctx* ctx, int32_t* sm_count, int64_t* hbm_bytes, int32_
 /* number of kernels launched on this ctx since creation (bench.py "gpu_launches") */
 int64_t avi_ctx_launch_count(const avi_ctx* ctx);
 
-/* Device timing of the named hot kernels ("sample", "glm_fwd", "glm_bwd", "gemm_store") with CUDA events
+/* Device timing of the named hot kernels ("sample", "glm_step", "glm_fwd_bwd", "glm_fwd", "glm_bwd", "gemm_store") with CUDA events
  * on the ctx stream, for roofline reporting.  While enabled, avi_opt_steps launches eagerly (no graph). */
 int32_t avi_ctx_timing(avi_ctx* ctx, int32_t enable);
 /* Diagnostic step timeline (AVI_TIMELINE=1 in the environment at avi_ctx_create): %globaltimer stamps (ns) of the
