@@ -185,4 +185,28 @@ end
         sub_val = estimate_objective(StableRNG(SEED), sub_obj, q, prob; n_samples=10^5)
         @test full_val ≈ sub_val rtol = 0.1
     end
+
+    # test/families/location_scale.jl:22-25 + docs/src/families.md:72-101: MvLocationScale with a non-Gaussian base
+    # distribution.  The native path draws the base itself (avi_obj_set_base), so the check is distributional: the ELBO
+    # estimate at q == q is finite and a short run moves the location towards the target's mean.
+    @testset "base distribution $(basedist)" for basedist in [Laplace(0.0f0, 1.0f0), TDist(5.0f0)]
+        q_t = MvLocationScale(zeros(Float32, n_dims), Diagonal(ones(Float32, n_dims)), basedist)
+        alg = KLMinRepGradDescent(AD; n_samples=10, optimizer=Optimisers.Adam(1.0f-2), operator=ClipScale())
+        q_avg, info, _ = optimize(StableRNG(SEED), alg, 200, model, q_t; show_progress=false)
+        @test q_avg isa MvLocationScale && q_avg.dist == basedist
+        @test all(isfinite, [i.elbo for i in info])
+        @test sum(abs2, q_avg.location - μ_true) < sum(abs2, q_t.location - μ_true)
+        @test_throws ArgumentError AdvancedVIB200.base_code(Normal(1.0f0, 2.0f0))
+    end
+
+    # src/algorithms/fisherminbatchmatch.jl:81-111: the sampling stage of FisherMinBatchMatch over a native target
+    @testset "rand_batch_match_samples_with_objective!" begin
+        q_fr = FullRankGaussian(zeros(Float32, n_dims), LowerTriangular(Matrix{Float32}(I, n_dims, n_dims)))
+        u, z, g, fisher, logπ_avg = AdvancedVI.rand_batch_match_samples_with_objective!(StableRNG(SEED), q_fr, 64, model)
+        @test size(u) == size(z) == size(g) == (n_dims, 64)
+        @test z ≈ q_fr.scale * u .+ q_fr.location rtol = 1.0f-5
+        @test g ≈ -(z .- μ_true) ./ diag(L_true) .^ 2 rtol = 1.0f-4              # test/models/normal.jl:8-11
+        @test fisher ≈ sum(abs2, -u - q_fr.scale' * g) / 64 rtol = 1.0f-4
+        @test logπ_avg ≈ mean(LogDensityProblems.logdensity(model, z[:, b]) for b in 1:64) rtol = 1.0f-4
+    end
 end
