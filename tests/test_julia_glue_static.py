@@ -78,9 +78,9 @@ def _split_top_level(s, sep=","):
     return [p.strip() for p in parts]
 
 
-def glue_ccalls():
+def glue_ccalls(text=None):
     """[(symbol, [julia arg type, ...], return type)]"""
-    src = _strip_julia(open(GLUE).read())
+    src = _strip_julia(open(GLUE).read() if text is None else text)
     calls = []
     for m in re.finditer(r"@ccall\s*\(?\s*libavi\.(avi_\w+)\(", src):
         i = m.end()
@@ -121,12 +121,7 @@ def _jl_class(t):
             "Float32": "f32", "Cfloat": "f32", "Float64": "f64", "Cdouble": "f64"}[t]
 
 
-def test_every_ccall_binds_a_declared_and_exported_symbol_with_matching_signature():
-    protos = header_prototypes()
-    assert len(protos) > 50
-    lib = ctypes.CDLL(os.path.join(ROOT, "advancedvi.jl_b200", "libavi_b200.so"))
-    calls = glue_ccalls()
-    assert len(calls) >= 25
+def check_ccalls(calls, protos, lib):
     for name, jl_types, ret in calls:
         assert name in protos, f"{name} is not declared in include/avi.h"
         assert hasattr(lib, name), f"{name} is not exported by libavi_b200.so"
@@ -135,6 +130,31 @@ def test_every_ccall_binds_a_declared_and_exported_symbol_with_matching_signatur
         for k, (ct, jt) in enumerate(zip(c_args, jl_types)):
             assert _c_class(ct) == _jl_class(jt), f"{name}: argument {k} is `{ct}` in avi.h but `{jt}` in the glue"
         assert ret in ("Int32", "Int64", "Cstring", "Cvoid"), (name, ret)
+
+
+def test_every_ccall_binds_a_declared_and_exported_symbol_with_matching_signature():
+    protos = header_prototypes()
+    assert len(protos) > 50
+    lib = ctypes.CDLL(os.path.join(ROOT, "advancedvi.jl_b200", "libavi_b200.so"))
+    calls = glue_ccalls()
+    assert len(calls) >= 25
+    check_ccalls(calls, protos, lib)
+
+
+def test_the_checker_catches_broken_bindings():
+    """The checks above are only worth something if they fail on a broken glue: an undeclared symbol, a dropped argument,
+    a 32-bit integer where the header has 64 bits, a float passed where a pointer is expected."""
+    protos = header_prototypes()
+    lib = ctypes.CDLL(os.path.join(ROOT, "advancedvi.jl_b200", "libavi_b200.so"))
+    good = 'check(@ccall(libavi.avi_obj_set_base(st.h::Ptr{Cvoid}, bc::Int32, bp::Float32)::Int32), c.h)'
+    check_ccalls(glue_ccalls(good), protos, lib)
+    for bad in (good.replace("avi_obj_set_base", "avi_obj_set_basis"),                       # no such entry point
+                good.replace(", bp::Float32", ""),                                            # argument dropped
+                good.replace("bc::Int32", "bc::Int64"),                                       # wrong integer width
+                good.replace("st.h::Ptr{Cvoid}", "st.h::Float32"),                            # handle passed by value
+                'check(@ccall(libavi.avi_model_subsample(p.h::Ptr{Cvoid}, p.idx::Ptr{Int32}, length(p.idx)::Int32)::Int32), c)'):
+        with pytest.raises(AssertionError):
+            check_ccalls(glue_ccalls(bad), protos, lib)
 
 
 def test_block_structure_is_balanced():
