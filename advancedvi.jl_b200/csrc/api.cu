@@ -421,6 +421,15 @@ int32_t avi_obj_set_base(avi_obj* obj, int32_t base, float param) {
     return AVI_OK;
 }
 
+int32_t avi_base_constants(int32_t base, float param, float* entropy, float* log_normaliser) {
+    BaseDist b;
+    if (!entropy || !log_normaliser || !avi_base_make(base, param, &b)) return AVI_ERR_INVALID;
+    *entropy = b.h0;
+    // base_nl2(u) = -2 log phi(u) - log(2 pi) has the additive constant nl2_c = -2 log phi(0) - log(2 pi)
+    *log_normaliser = (float)(-0.5 * ((double)b.nl2_c + 1.8378770664093453));
+    return AVI_OK;
+}
+
 int32_t avi_obj_set_model(avi_obj* obj, avi_model* model) {
     if (!obj || !model) return AVI_ERR_INVALID;
     if (model->D != obj->D) AVI_FAIL(obj->ctx, AVI_ERR_INVALID, "dimension of the new target differs");

@@ -176,6 +176,11 @@ int32_t avi_obj_create_lowrank(avi_ctx* ctx, avi_model* model, int32_t rank, int
  * low-rank family (LowRankGaussian is Gaussian by definition) and for ProximalLocationScaleEntropy-style zero-gradient
  * closed forms nothing changes (the entropy constant does not enter a gradient). */
 int32_t avi_obj_set_base(avi_obj* obj, int32_t base, float param);
+/* The two constants the kernels take from a base distribution, computed on the host (no device needed): *entropy =
+ * entropy(dist) (location_scale.jl:52-57 multiplies it by D) and *log_normaliser = log phi(0), the additive constant of
+ * logpdf(dist, u) (Normal: -log(2 pi)/2; Laplace: -log 2; TDist(nu): lgamma((nu+1)/2) - lgamma(nu/2) - log(nu pi)/2).
+ * AVI_ERR_INVALID for an unknown base or nu outside (0, 1e6). */
+int32_t avi_base_constants(int32_t base, float param, float* entropy, float* log_normaliser);
 /* set_objective_state_problem (repgradelbo.jl:31-39, scoregradelbo.jl:24-32) */
 int32_t avi_obj_set_model(avi_obj* obj, avi_model* model);
 /* eps[i, m] at step t is a pure function of (key, t, m, i) (Philox4x32-10 + Box-Muller);

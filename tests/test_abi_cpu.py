@@ -146,3 +146,20 @@ def test_lowrank_host_container_matches_oracle_layout():
         avi.LowRankGaussian(mu.astype(np.float64), sd, U)
     with pytest.raises(ValueError):
         avi.LowRankGaussian(mu, sd[:-1], U)
+
+
+@pytest.mark.parametrize("base,param", [(0, 0.0), (1, 0.0), (2, 0.7), (2, 2.5), (2, 5.0), (2, 30.0), (2, 1000.0)])
+def test_base_distribution_constants_match_scipy(base, param):
+    """entropy(dist) and the log normaliser the kernels use for MvLocationScale(location, scale, dist)
+    (src/families/location_scale.jl:52-63; docs/src/families.md:72-101), host arithmetic of csrc/base_dist.cuh
+    (lgamma + an asymptotic digamma) against scipy: 2e-7 relative (they are stored as float32)."""
+    import ctypes as C
+    from scipy import stats
+    from advancedvi_jl_b200 import _lib as L
+    dist = [stats.norm(), stats.laplace(), stats.t(param)][base]
+    h, c = C.c_float(), C.c_float()
+    assert L.lib.avi_base_constants(base, param, C.byref(h), C.byref(c)) == 0
+    assert abs(h.value - dist.entropy()) <= 2e-7 * max(1.0, abs(dist.entropy()))
+    assert abs(c.value - dist.logpdf(0.0)) <= 2e-7 * max(1.0, abs(dist.logpdf(0.0)))
+    assert L.lib.avi_base_constants(2, 0.0, C.byref(h), C.byref(c)) != 0       # nu must be positive
+    assert L.lib.avi_base_constants(7, 1.0, C.byref(h), C.byref(c)) != 0       # unknown base
