@@ -385,3 +385,20 @@ def test_nongaussian_base_repgrad_closed_form_vs_fd(covtype, dist, entropy):
         fd = fd * mask
     assert np.isclose(v, forward(lam))
     assert np.allclose(g, fd, rtol=5e-6, atol=5e-7)
+
+
+def test_batch_match_fisher_divergence_vanishes_at_truth():
+    """rand_batch_match_samples_with_objective! (src/algorithms/fisherminbatchmatch.jl:81-111): at q == pi (a Gaussian
+    with scale C) grad log pi(z) = -C^-T u, so -u - C' grad log pi(z) == 0 and the Fisher-divergence estimate is zero
+    for ANY draws (:100-108); away from it it is positive; log pi_avg is the sample mean of the log-density."""
+    D, n = 6, 40
+    mu = np.linspace(-1.0, 2.0, D)
+    C = np.tril(0.1 * np.ones((D, D))) + np.diag(0.5 + 0.1 * np.arange(D))
+    prob = Mo.NormalDense(mu, C)
+    u = P.normal_matrix(7, 3, D, n)
+    uo, z, g, fisher, lp = O.rand_batch_match_samples_with_objective(F.FullRankGaussian(mu, C), prob, u)
+    assert uo is u and np.allclose(z, C @ u + mu[:, None])
+    assert fisher < 1e-24
+    assert np.isclose(lp, np.mean(prob.logdensity_and_gradient_batch(z)[0]))
+    _, _, _, fisher_off, _ = O.rand_batch_match_samples_with_objective(F.FullRankGaussian(mu + 0.3, 1.2 * C), prob, u)
+    assert fisher_off > 1e-2
