@@ -76,6 +76,7 @@ SIGNATURES = {
     "avi_obj_set_model": (C.c_int32, [vp, vp]),
     "avi_obj_set_base": (C.c_int32, [vp, C.c_int32, C.c_float]),
     "avi_base_constants": (C.c_int32, [C.c_int32, C.c_float, c_float_p, c_float_p]),
+    "avi_check_indices": (C.c_int32, [C.POINTER(C.c_int32), C.c_int64, C.c_int64, c_i64_p]),
     "avi_obj_batch_match_samples": (C.c_int32, [vp, c_float_p, C.c_int64, C.c_int32, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p]),
     "avi_obj_seed": (C.c_int32, [vp, C.c_uint64, C.c_uint64]),
     "avi_obj_get_step": (C.c_int32, [vp, C.POINTER(C.c_uint64)]),

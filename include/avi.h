@@ -250,6 +250,10 @@ int32_t avi_opt_steps(avi_opt* opt, int32_t n, float* value_host, float* elbo_ho
 int32_t avi_opt_steps_begin(avi_opt* opt, int32_t capacity);
 int32_t avi_opt_steps_enqueue(avi_opt* opt, int32_t n);
 int32_t avi_opt_steps_end(avi_opt* opt, float* value_host, float* elbo_host, int32_t* n_done);
+/* Range check of minibatch indices (0-based rows of the target), what avi_opt_steps_subsampled applies to idx_host before
+ * anything reaches the device: AVI_OK iff every idx[j] lies in [0, rows); otherwise AVI_ERR_INVALID with *first_bad (may
+ * be NULL) = the first offending position.  Host only. */
+int32_t avi_check_indices(const int32_t* idx, int64_t n, int64_t rows, int64_t* first_bad);
 /* same, with the minibatch of every iteration given up front: idx_host holds n * batch row
  * indices (SubsampledObjective, src/algorithms/subsampledobjective.jl:64-90) */
 int32_t avi_opt_steps_subsampled(avi_opt* opt, int32_t n, const int32_t* idx_host, int64_t batch,

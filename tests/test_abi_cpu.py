@@ -163,3 +163,33 @@ def test_base_distribution_constants_match_scipy(base, param):
     assert abs(c.value - dist.logpdf(0.0)) <= 2e-7 * max(1.0, abs(dist.logpdf(0.0)))
     assert L.lib.avi_base_constants(2, 0.0, C.byref(h), C.byref(c)) != 0       # nu must be positive
     assert L.lib.avi_base_constants(7, 1.0, C.byref(h), C.byref(c)) != 0       # unknown base
+
+
+def test_check_indices_matches_a_plain_scan():
+    """avi_check_indices (the range check in front of avi_opt_steps_subsampled): same verdict and same first offending
+    position as the obvious loop, for clean arrays, one bad entry anywhere (also across the 4096-entry block edges),
+    negative entries, and the empty array."""
+    import ctypes as C
+    from advancedvi_jl_b200 import _lib as L
+    rng = np.random.default_rng(0)
+    rows = 1000
+    bad = C.c_int64()
+
+    def check(a):
+        a = np.ascontiguousarray(a, np.int32)
+        rc = L.lib.avi_check_indices(a.ctypes.data_as(C.POINTER(C.c_int32)), a.size, rows, C.byref(bad))
+        wrong = np.flatnonzero((a < 0) | (a >= rows))
+        assert (rc == 0) == (wrong.size == 0)
+        assert bad.value == (wrong[0] if wrong.size else -1)
+    check(np.empty(0, np.int32))
+    for n in (1, 5, 4095, 4096, 4097, 3 * 4096 + 17):
+        a = rng.integers(0, rows, n)
+        check(a)
+        for pos in {0, n - 1, n // 2, min(n - 1, 4095), min(n - 1, 4096)}:
+            for v in (rows, -1, 2 ** 31 - 1, -2 ** 31):
+                b = a.copy(); b[pos] = v
+                check(b)
+        if n > 10:
+            b = a.copy(); b[[3, n - 2]] = [-5, rows + 5]
+            check(b)
+    assert L.lib.avi_check_indices(None, 3, rows, C.byref(bad)) != 0
