@@ -20,12 +20,17 @@ Pinning status ("parity partially pinned"):
     moments against an independent scipy MvNormal, rule convergence), against
     closed-form expectations, against central finite differences of the restated
     forward passes, and (Philox) against the Random123 known-answer vectors.
-  * NOT pinned (no golden vector exists in the reference): the RNG stream values
-    (Julia Xoshiro/StableRNG + ziggurat randn is replaced by counter-based
-    Philox4x32-10 + Box-Muller on both oracle and GPU), the docs-only logistic
-    regression model arithmetic (Distributions.jl BernoulliLogit / MvNormal /
-    LogNormal formulas restated from their definitions), Optimisers.jl Adam
-    arithmetic, and the full-rank flatten layout.  DESIGN.md repeats this.
+  * It is additionally pinned against an INDEPENDENT AD backend and independent
+    library arithmetic (tests/test_oracle_independent_ad.py): the reference's forward
+    closures, its family and its documented regression models restated in PyTorch from
+    the reference's source text and differentiated with autograd (values and gradients
+    to 1e-10), torch.distributions for the densities, torch.optim for Adam / Descent.
+  * NOT pinned by reference outputs (no golden vector exists in the reference): the RNG
+    stream values (Julia Xoshiro/StableRNG + ziggurat randn is replaced by counter-based
+    Philox4x32-10 + Box-Muller on both oracle and GPU) and the full-rank flatten layout;
+    the docs-only logistic-regression arithmetic and the Optimisers.jl Adam arithmetic
+    only through the independent implementations of the previous item.  DESIGN.md
+    repeats this.
 """
 
 from . import philox, family, models, objectives, optim, reshuffling  # noqa: F401
