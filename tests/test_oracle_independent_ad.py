@@ -189,3 +189,90 @@ def test_adam_and_descent_match_torch_optim():
             p.grad = torch.from_numpy(grad(p.detach().numpy()))
             opt_t.step()
             assert np.allclose(x, p.detach().numpy(), rtol=1e-12, atol=1e-14)
+
+
+# ---- non-Gaussian base distributions (docs/src/families.md:72-101) through torch.distributions -----------------------
+def _torch_base(name, nu):
+    D = torch.distributions
+    return D.Laplace(0.0, 1.0) if name == "laplace" else D.StudentT(nu)
+
+
+@pytest.mark.parametrize("base,nu", [("laplace", None), ("tdist", 5.0)])
+@pytest.mark.parametrize("family", ["meanfield", "fullrank"])
+@pytest.mark.parametrize("entropy", ["ClosedFormEntropy", "MonteCarloEntropy", "StickingTheLandingEntropy"])
+def test_nongaussian_base_closed_forms_equal_autograd(base, nu, family, entropy):
+    """MvLocationScale(location, scale, dist): logpdf = sum logpdf(dist, scale \\ (z - location)) - logdet(scale),
+    entropy = D entropy(dist) + logdet(scale) (location_scale.jl:52-63) with torch's Laplace / StudentT."""
+    X, y = _data(n=20, d=3)
+    D, M = 4, 5
+    prob = Mo.LogReg(X, y, n_data=50)
+    Xt, yt = torch.from_numpy(X), torch.from_numpy(y)
+    target = lambda th: logreg_logdensity_torch(th, Xt, yt, 50, "subsampling")
+    dist_t = _torch_base(base, nu)
+    dist_o = F.LaplaceDist() if base == "laplace" else F.TDistBase(nu)
+    mu = 0.1 * np.arange(D) - 0.2
+    scale = (0.5 + 0.1 * np.arange(D)) if family == "meanfield" else np.tril(0.1 * np.ones((D, D))) + np.diag(0.5 + 0.1 * np.arange(D))
+    q = F.MvLocationScale(mu, scale, dist_o)
+    lam = q.destructure()
+    u = P.laplace_matrix(3, 7, D, M) if base == "laplace" else P.student_t_matrix(3, 7, D, M, nu)
+    v, g, _ = O.repgrad_value_and_gradient(lam, q, prob, u, entropy)
+
+    def logpdf_b(z, m_, L_):
+        w = torch.linalg.solve_triangular(L_, z - m_[:, None], upper=False)
+        return dist_t.log_prob(w).sum(0) - torch.log(torch.diagonal(L_)).sum()
+    lt = torch.tensor(lam, requires_grad=True)
+    m_, L_ = q_pieces(lt, D, family == "meanfield")
+    ms, Ls = q_pieces(torch.tensor(lam), D, family == "meanfield")
+    z = L_ @ torch.from_numpy(u) + m_[:, None]
+    energy = torch.stack([target(z[:, k]) for k in range(M)]).mean()
+    if entropy == "ClosedFormEntropy":
+        ent = D * dist_t.entropy() + torch.log(torch.diagonal(L_)).sum()
+    elif entropy == "MonteCarloEntropy":
+        ent = -logpdf_b(z, m_, L_).mean()
+    else:
+        ent = -logpdf_b(z, ms, Ls).mean()
+    val = -(energy + ent)
+    val.backward()
+    assert abs(v - val.item()) <= 1e-10 * abs(val.item())
+    assert np.allclose(g, lt.grad.numpy(), rtol=1e-8, atol=1e-10)
+
+
+# ---- the low-rank family against torch.distributions.LowRankMultivariateNormal --------------------------------------
+def test_lowrank_family_and_gradients_against_torch():
+    """MvLocationScaleLowRank (src/families/location_scale_low_rank.jl): covariance diag(D^2) + U U'.  logpdf / entropy
+    (Woodbury + matrix determinant lemma in the oracle, :35-67) against LowRankMultivariateNormal, and the RepGradELBO
+    closed forms (closed-form / Monte-Carlo / sticking-the-landing entropy) against autograd through rand (:79-86)."""
+    d, r, M = 6, 2, 5
+    rng = np.random.default_rng(2)
+    loc = 0.3 * rng.standard_normal(d)
+    sd = 0.5 + 0.3 * rng.random(d)
+    U = 0.2 * rng.standard_normal((d, r))
+    q = F.MvLocationScaleLowRank(loc, sd, U)
+    Z = rng.standard_normal((d, 9))
+    ref = torch.distributions.LowRankMultivariateNormal(torch.from_numpy(loc), torch.from_numpy(U), torch.from_numpy(sd ** 2))
+    assert np.allclose(q.logpdf(Z), ref.log_prob(torch.from_numpy(Z.T)).numpy(), rtol=1e-11)
+    assert np.isclose(q.entropy(), ref.entropy().item(), rtol=1e-12)
+
+    X, y = _data(n=20, d=d - 1)
+    prob = Mo.LogReg(X, y, n_data=50)
+    Xt, yt = torch.from_numpy(X), torch.from_numpy(y)
+    target = lambda th: logreg_logdensity_torch(th, Xt, yt, 50, "subsampling")
+    lam = q.destructure()
+    u1, u2 = P.normal_matrix(5, 0, d, M), P.normal_matrix(5, 0, r, M, stream=P.STREAM_EPS_FACTORS)
+    for entropy in ("ClosedFormEntropy", "MonteCarloEntropy", "StickingTheLandingEntropy"):
+        v, g, _ = O.repgrad_lowrank_value_and_gradient(lam, q, prob, u1, u2, entropy)
+        lt = torch.tensor(lam, requires_grad=True)
+        m_, d_, U_ = lt[:d], lt[d:2 * d], lt[2 * d:].reshape(r, d).T          # destructure order, column-major factors
+        z = d_[:, None] * torch.from_numpy(u1) + U_ @ torch.from_numpy(u2) + m_[:, None]
+        energy = torch.stack([target(z[:, k]) for k in range(M)]).mean()
+        live = torch.distributions.LowRankMultivariateNormal(m_, U_, d_ ** 2)
+        if entropy == "ClosedFormEntropy":
+            ent = live.entropy()
+        elif entropy == "MonteCarloEntropy":
+            ent = -live.log_prob(z.T).mean()
+        else:
+            ent = -ref.log_prob(z.T).mean()
+        val = -(energy + ent)
+        val.backward()
+        assert abs(v - val.item()) <= 1e-10 * abs(val.item()), entropy
+        assert np.allclose(g, lt.grad.numpy(), rtol=1e-7, atol=1e-9), entropy
