@@ -3,7 +3,9 @@
 The reference (Julia) cannot run in this image, so these vectors are produced by the CPU oracle (oracle/, fp64),
 which is itself pinned against the reference's known-answer tests (tests/test_oracle_known_answers.py).  They are
 regression pins: the oracle must keep reproducing them bit for bit (fp64, same numpy arithmetic), and the CUDA path
-must reproduce them within the fp32 / TF32 tolerances written in tests/test_golden_vectors.py.
+must reproduce them within the fp32 / TF32 tolerances written in tests/test_golden_vectors.py.  An independent check of
+the stored OUTPUTS exists too: tests/test_oracle_independent_ad.py recomputes them from the stored inputs with PyTorch
+autograd over a restatement of the reference's forward closures that does not use oracle/.
 
     python tests/golden/make_golden.py        (from the repository root; overwrites the fixture)
 """
