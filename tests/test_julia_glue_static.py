@@ -222,3 +222,25 @@ def test_extended_functions_and_imported_names_exist_in_the_reference():
     for name in names:
         assert re.search(rf"\b(struct|function|abstract type)\s+{name}\b|^{name}\(|const {name}\b", ref_src, flags=re.M), \
             f"`{name}` is imported from AdvancedVI but not defined in the reference"
+
+
+def test_project_toml_lists_every_package_the_glue_and_its_tests_use():
+    """julia/Project.toml: every `using X` of the glue and of runtests.jl is a dependency, with the UUID the reference's
+    own Project.toml / test/Project.toml gives that package (when the reference checkout is present)."""
+    toml = open(os.path.join(ROOT, "julia", "Project.toml")).read()
+    deps = dict(re.findall(r'^(\w+) = "([0-9a-f-]{36})"', toml, flags=re.M))
+    used = set()
+    for path in (GLUE, os.path.join(ROOT, "julia", "test", "runtests.jl")):
+        for line in _strip_julia(open(path).read()).split("\n"):
+            m = re.match(r"\s*using\s+(.*)", line)
+            if m and not m.group(1).startswith("."):
+                for part in m.group(1).split(":")[0].split(","):
+                    used.add(part.strip())
+    assert used and used <= set(deps), used - set(deps)
+    if os.path.isdir(REF):
+        ref = open(os.path.join(REF, "Project.toml")).read() + open(os.path.join(REF, "test", "Project.toml")).read()
+        ref_ids = dict(re.findall(r'^(\w+) = "([0-9a-f-]{36})"', ref, flags=re.M))
+        for name, uid in deps.items():
+            if name in ref_ids:
+                assert ref_ids[name] == uid, name
+        assert re.search(r'^uuid = "' + deps["AdvancedVI"] + '"', ref, flags=re.M)
