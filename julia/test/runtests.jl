@@ -2,7 +2,7 @@
 #
 # NOT EXECUTED IN THIS REPOSITORY'S CI (no Julia in the build image, SURVEY.md F2); it is what a maintainer with Julia,
 # AdvancedVI.jl v0.7 and a B200 runs:
-#     LIBAVI_B200=/path/to/libavi_b200.so julia --project=. julia/test/runtests.jl
+#     LIBAVI_B200=/path/to/libavi_b200.so julia --project=julia julia/test/runtests.jl
 # Each testset names the reference test it mirrors; the Python mirror (tests/test_gpu_*.py) runs the same call
 # sequences against the same library on every round.  Everything is Float32 (the native path's only element type;
 # `AutoB200` raises an ArgumentError otherwise, tested below).
