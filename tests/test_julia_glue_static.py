@@ -244,3 +244,24 @@ def test_project_toml_lists_every_package_the_glue_and_its_tests_use():
             if name in ref_ids:
                 assert ref_ids[name] == uid, name
         assert re.search(r'^uuid = "' + deps["AdvancedVI"] + '"', ref, flags=re.M)
+
+
+_BASE_FUNCTIONS = set("""length size zeros ones fill similar copy collect map sum abs2 rand randn isnothing isa get get! haskey
+push! throw error string unsafe_string finalizer reinterpret pointer convert eltype typeof min max minimum maximum any all first
+last isempty vec reshape transpose adjoint view copyto! unsafe_copyto! div rem mod ceil floor round sqrt exp log abs println print
+show repr zero one iszero isfinite isnan ntuple getfield setfield! getproperty setproperty! hasproperty hasfield fieldnames nameof
+eachindex axes range vcat hcat cat getindex setindex! in keys values pairs tuple something ifelse merge unsafe_wrap unsafe_load
+unsafe_store! deepcopy identity foreach filter reduce mapreduce findfirst sort sort! unique reverse dof params diag tril triu
+inv det logdet dot norm mul! ldiv! sizeof include joinpath dirname abspath parse float new""".split())
+
+
+def test_every_called_function_is_defined_imported_or_base():
+    """A name that is called but neither defined in the module, nor a closure / keyword argument, nor a Base /
+    LinearAlgebra / Distributions function the module imports: the round-1 glue had several."""
+    src = _strip_julia(open(GLUE).read())
+    called = set(re.findall(r"(?<![\w.@:])([a-z_][A-Za-z0-9_!]*)\(", src))
+    defined = set(re.findall(r"function\s+(?:\w+\.)?([A-Za-z_][\w!]*)", src))
+    defined |= set(re.findall(r"^\s*(?:\w+\.)?([a-z_][\w!]*)\([^=\n]*\)\s*(?:where[^=\n]*)?=(?!=)", src, flags=re.M))
+    local = set(re.findall(r"\b([a-z_]\w*)\s*(?:=|::)", src)) | set(re.findall(r"[(,;]\s*([a-z_]\w*)\s*(?:[,;)]|::)", src))
+    unknown = sorted(called - defined - _BASE_FUNCTIONS - local)
+    assert not unknown, f"called but never defined / imported: {unknown}"
