@@ -20,3 +20,4 @@ def test_two_rank_parity():
                         os.path.join(ROOT, "tests", "multigpu_check.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "native_exchange=True" in r.stdout and "native_exchange=False" in r.stdout
+    assert "full-rank family (pull-protocol exchange)" in r.stdout
